@@ -1,0 +1,115 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see ojson.hpp header).
+// C entry points so tests/, smoke() and bench.py's cpu_baseline / --impl reference legs can
+// drive the restatement through ctypes.  Built by oracle/Makefile into oracle/liboracle.so.
+#include <atomic>
+#include <chrono>
+#include <thread>
+
+#include "stream.hpp"
+#include "translate.hpp"
+
+using namespace oracle;
+
+extern "C" {
+
+struct oracle_result {
+  int32_t status;      // oracle::Status
+  int32_t body_kind;   // oracle::BodyKind
+  int32_t stream;
+  int32_t has_mutated;
+  uint64_t body_len, path_len, model_len, err_len, mutated_len;
+  char* body; char* path; char* model; char* err; char* mutated;
+};
+
+static char* dup(const std::string& s) { char* p = (char*)malloc(s.size() + 1); memcpy(p, s.data(), s.size()); p[s.size()] = 0; return p; }
+
+void oracle_chat_translate(int schema, const char* body, uint64_t len, const char* model_override, const char* prefix,
+                           int cost_configured, int force, oracle_result* out) {
+  TranslateResult r = chat_translate(schema, std::string_view(body, len), model_override ? model_override : "", prefix ? prefix : "", cost_configured != 0, force != 0);
+  memset(out, 0, sizeof *out);
+  out->status = r.err.status; out->body_kind = r.body_kind; out->stream = r.stream; out->has_mutated = r.has_mutated;
+  std::string path; for (auto& h : r.headers) if (h.name == ":path") path = h.value;
+  out->body = dup(r.body); out->body_len = r.body.size();
+  out->path = dup(path); out->path_len = path.size();
+  out->model = dup(r.model); out->model_len = r.model.size();
+  out->err = dup(r.err.msg); out->err_len = r.err.msg.size();
+  out->mutated = dup(r.mutated_body); out->mutated_len = r.mutated_body.size();
+}
+void oracle_result_free(oracle_result* r) { free(r->body); free(r->path); free(r->model); free(r->err); free(r->mutated); memset(r, 0, sizeof *r); }
+
+// Batch form used for CPU-baseline timing: translate n bodies with `threads` workers, return
+// total output bytes and per-body status/len (no output retention).  Seconds of wall time returned.
+double oracle_chat_translate_batch(int schema, const uint8_t* bodies, const uint64_t* offsets, uint32_t n, int cost_configured,
+                                   int threads, int32_t* status, uint32_t* out_len, uint64_t* total_out) {
+  std::atomic<uint32_t> next{0}; std::atomic<uint64_t> tot{0};
+  auto t0 = std::chrono::steady_clock::now();
+  auto work = [&] {
+    for (;;) {
+      uint32_t i = next.fetch_add(64);
+      if (i >= n) break;
+      uint32_t e = std::min(n, i + 64); uint64_t loc = 0;
+      for (; i < e; i++) {
+        TranslateResult r = chat_translate(schema, std::string_view((const char*)bodies + offsets[i], offsets[i + 1] - offsets[i]), "", "", cost_configured != 0, false);
+        if (status) status[i] = r.err.status;
+        if (out_len) out_len[i] = (uint32_t)r.body.size();
+        loc += r.body.size();
+      }
+      tot += loc;
+    }
+  };
+  if (threads <= 1) work();
+  else { std::vector<std::thread> th; for (int t = 0; t < threads; t++) th.emplace_back(work); for (auto& t : th) t.join(); }
+  if (total_out) *total_out = tot.load();
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// ---- S1: streaming usage scan
+struct oracle_usage { uint32_t input, output, total, cached, cache_creation, reasoning, mask; };
+static void put(oracle_usage* o, const TokenUsage& u) { o->input = u.input; o->output = u.output; o->total = u.total; o->cached = u.cached; o->cache_creation = u.cache_creation; o->reasoning = u.reasoning; o->mask = u.mask; }
+
+void* oracle_sse_open() { return new SSEOpenAIState(); }
+void oracle_sse_close(void* h) { delete (SSEOpenAIState*)h; }
+// feeds one chunk; `call` = usage returned by this ResponseBody call
+void oracle_sse_feed(void* h, const char* chunk, uint64_t len, oracle_usage* call) {
+  auto* st = (SSEOpenAIState*)h; TokenUsage u = sse_openai_feed(*st, std::string_view(chunk, len)); put(call, u);
+}
+uint64_t oracle_sse_model(void* h, char* buf, uint64_t cap) {
+  auto* st = (SSEOpenAIState*)h; uint64_t n = std::min<uint64_t>(cap, st->streaming_model.size()); memcpy(buf, st->streaming_model.data(), n); return st->streaming_model.size();
+}
+uint64_t oracle_sse_buffered(void* h) { return ((SSEOpenAIState*)h)->buffered.size(); }
+
+// Whole-stream helper for batch timing/parity: stream s = chunks [chunk_off[s], chunk_off[s+1]) of the
+// chunk table (byte offsets chunk_byte_off[c]..chunk_byte_off[c+1]); result = Override-accumulated usage.
+double oracle_sse_batch(const uint8_t* bytes, const uint64_t* chunk_byte_off, const uint32_t* chunk_off, uint32_t n_streams, int threads, oracle_usage* out) {
+  std::atomic<uint32_t> next{0};
+  auto t0 = std::chrono::steady_clock::now();
+  auto work = [&] {
+    for (;;) {
+      uint32_t s = next.fetch_add(16); if (s >= n_streams) break;
+      uint32_t e = std::min(n_streams, s + 16);
+      for (; s < e; s++) {
+        SSEOpenAIState st; TokenUsage acc;
+        for (uint32_t c = chunk_off[s]; c < chunk_off[s + 1]; c++) {
+          TokenUsage u = sse_openai_feed(st, std::string_view((const char*)bytes + chunk_byte_off[c], chunk_byte_off[c + 1] - chunk_byte_off[c]));
+          acc.override_with(u);
+        }
+        put(&out[s], acc);
+      }
+    }
+  };
+  if (threads <= 1) work();
+  else { std::vector<std::thread> th; for (int t = 0; t < threads; t++) th.emplace_back(work); for (auto& t : th) t.join(); }
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+int oracle_response_openai(const char* body, uint64_t len, const char* request_model, oracle_usage* out, char* model_buf, uint64_t cap, uint64_t* model_len) {
+  TokenUsage tu; std::string rm;
+  bool ok = response_openai(std::string_view(body, len), request_model ? request_model : "", tu, rm);
+  put(out, tu); uint64_t n = std::min<uint64_t>(cap, rm.size()); memcpy(model_buf, rm.data(), n); *model_len = rm.size();
+  return ok ? 0 : 1;
+}
+uint64_t oracle_eval_cost(int type, const oracle_usage* u) { TokenUsage t; t.input = u->input; t.output = u->output; t.total = u->total; t.cached = u->cached; t.cache_creation = u->cache_creation; t.reasoning = u->reasoning; t.mask = u->mask; return eval_cost(type, t); }
+
+// float formatting probe for tests
+uint64_t oracle_fmt_f64(double v, char* buf, uint64_t cap) { std::string s; oj::enc_f64(s, v); uint64_t n = std::min<uint64_t>(cap, s.size()); memcpy(buf, s.data(), n); return s.size(); }
+}

@@ -1,0 +1,79 @@
+"""Pin the CPU oracle against the reference's own known-answer vectors.
+
+Fixtures were lifted from /root/reference by tests/golden/extract_goldens.py; the fake upstream in the
+reference compares expRequestBody with bytes.Equal, so equality here is byte-exact parity."""
+import json
+import os
+
+import pytest
+
+import _oracle as O
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+CASES = json.load(open(os.path.join(G, "testupstream_cases.json"), encoding="utf-8"))["cases"]
+OVERRIDE = {"modelname-override": "override-model"}
+RESTATED = {"openai", "aws-bedrock", "modelname-override"}
+
+
+def _chat_cases():
+    for c in CASES:
+        if c.get("path", "/v1/chat/completions").split("?")[0] != "/v1/chat/completions":
+            continue
+        if c.get("backend") not in RESTATED or "expRequestBody" not in c:
+            continue
+        yield c
+
+
+@pytest.mark.parametrize("case", list(_chat_cases()), ids=lambda c: c["name"])
+def test_request_translate_golden(case):
+    backend = case["backend"]
+    schema = "openai" if backend in ("openai", "modelname-override") else backend
+    # TestStreamingUsageInclusionWithCosts (path None) runs with costs configured; TestWithTestUpstream too
+    # (GlobalLLMRequestCosts is set, testupstream_test.go:55-59).
+    t = O.chat_translate(schema, case["requestBody"].encode(), model_override=OVERRIDE.get(backend, ""), cost_configured=True)
+    assert t.status == O.OK, t.err
+    exp = case["expRequestBody"].encode()
+    got = t.body if t.body_kind == O.BYTES else case["requestBody"].encode()
+    assert got == exp
+    if "expPath" in case:
+        assert t.path == case["expPath"]
+
+
+def test_malformed_json_is_400():
+    c = next(c for c in CASES if c["name"].endswith("malformed JSON request"))
+    t = O.chat_translate("openai", c["requestBody"].encode())
+    assert t.status == O.MALFORMED_400
+    assert t.err.startswith("malformed request: failed to parse JSON for /v1/chat/completions:")
+
+
+USAGE = json.load(open(os.path.join(G, "sse_usage_cases.json")))["cases"]
+
+
+@pytest.mark.parametrize("case", USAGE, ids=lambda c: c["name"])
+def test_sse_usage_golden(case):
+    s = O.SSEStream()
+    for feed, exp in zip(case["feeds"], case["exp"]):
+        u = s.feed(feed.encode())
+        assert list(u.as_tuple()) == exp
+    if case["buffered_empty"]:
+        assert s.buffered() == 0
+
+
+def test_streaming_golden_usage_and_model():
+    # testupstream_test.go:495-500: the OpenAI SSE stream; usage 13/12/25, details present with zeros.
+    c = next(c for c in CASES if c["name"] == "openai - /v1/chat/completions - streaming")
+    s = O.SSEStream()
+    acc = None
+    body = c["expResponseBody"].encode()
+    for i in range(0, len(body), 7):  # ragged chunks
+        u = s.feed(body[i:i + 7])
+        if u.mask:
+            acc = u.as_tuple()
+    assert acc == (13, 0, 0, 12, 25, 0)
+    assert s.model() == b"gpt-4o-mini-2024-07-18"
+
+
+@pytest.mark.parametrize("v,exp", [(0.7, "0.7"), (1.0, "1"), (0.1, "0.1"), (0.0, "0"), (1e21, "1e+21"), (1e20, "100000000000000000000"),
+                                   (1e-6, "0.000001"), (1e-7, "1e-7"), (0.5, "0.5"), (123456.789, "123456.789"), (-2.5e-9, "-2.5e-9"), (3.0e25, "3e+25")])
+def test_go_float_format(v, exp):
+    assert O.fmt_f64(v) == exp
