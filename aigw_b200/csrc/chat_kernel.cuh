@@ -1,0 +1,147 @@
+// aigw_b200 — /v1/chat/completions parse + translate kernel for sm_100a.
+//
+// One warp per request body ("document"), persistent CTAs pulling documents from a global
+// counter.  Per document:
+//   stage 1  load      16-byte coalesced global loads → per-warp shared-memory copy of the body
+//   stage 2  index     lane-local byte classification (32 B per lane per round), escape/quote
+//                      carry resolution with ballots, in-string prefix-xor, structural token list
+//   stage 3  validate  JSON grammar over the token list, bracket matching (jump table)
+//   stage 4  plan      schema walk (OpenAI ChatCompletionRequest → target layout) producing a
+//                      list of copy ops (input span | literal | scratch span)
+//   stage 5  emit      warp-cooperative gather of the ops into a shared-memory image of the
+//                      output record, bump-allocate space in the output arena, 16-byte stores
+//
+// Behavioural source of truth for stage 4: internal/translator/openai_awsbedrock.go:91-585 and
+// internal/apischema/awsbedrock/awsbedrock.go:41-70,126-200,310-367,536-604 (field order, omit
+// rules); internal/translator/openai_openai.go:55-84 and internal/endpointspec/endpointspec.go:107-123
+// for the OpenAI passthrough edits.  Anything outside the fast path is DECLINED (the caller runs
+// the stock path); the kernel never guesses.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/aigw_b200.h"
+
+namespace aigw {
+
+// ------------------------------------------------------------------ literal table
+#define AIGW_LITERALS(X)                                                                       \
+  X(L_LBRACE, "{")                                                                             \
+  X(L_RBRACE, "}")                                                                             \
+  X(L_LBRACK, "[")                                                                             \
+  X(L_RBRACK, "]")                                                                             \
+  X(L_COMMA, ",")                                                                              \
+  X(L_COLON, ":")                                                                              \
+  X(L_ZERO, "0")                                                                               \
+  X(L_NULL, "null")                                                                            \
+  X(L_TRUE, "true")                                                                            \
+  X(L_EMPTY_STR, "\"\"")                                                                       \
+  X(L_ADDL_EN_PRE, "\"additionalModelRequestFields\":{\"thinking\":{\"budget_tokens\":")       \
+  X(L_ADDL_EN_POST, ",\"type\":\"enabled\"}},")                                                \
+  X(L_ADDL_DIS, "\"additionalModelRequestFields\":{\"thinking\":{\"type\":\"disabled\"}},")    \
+  X(L_INF_OPEN, "\"inferenceConfig\":{")                                                       \
+  X(L_MAXTOK, "\"maxTokens\":")                                                                \
+  X(L_STOPSEQ, "\"stopSequences\":[")                                                          \
+  X(L_TEMP, "\"temperature\":")                                                                \
+  X(L_TOPP, "\"topP\":")                                                                       \
+  X(L_INF_CLOSE_MSGS, "},\"messages\":[")                                                      \
+  X(L_MSG_TEXT_OPEN, "{\"content\":[{\"text\":")                                               \
+  X(L_MSG_CONTENT_OPEN, "{\"content\":[")                                                      \
+  X(L_TEXT_OPEN, "{\"text\":")                                                                 \
+  X(L_USER_CLOSE1, "}],\"role\":\"user\"}")                                                    \
+  X(L_ASST_CLOSE1, "}],\"role\":\"assistant\"}")                                               \
+  X(L_USER_CLOSE, "],\"role\":\"user\"}")                                                      \
+  X(L_ASST_CLOSE, "],\"role\":\"assistant\"}")                                                 \
+  X(L_CACHEPOINT, "{\"cachePoint\":{\"type\":\"default\"}}")                                   \
+  X(L_TOOLRESULT_OPEN, "{\"toolResult\":{\"content\":[")                                       \
+  X(L_TOOLRESULT_MID, "],\"status\":null,\"toolUseId\":")                                      \
+  X(L_TOOLRESULT_CLOSE, "}}")                                                                  \
+  X(L_TOOLUSE_OPEN, "{\"toolUse\":{\"name\":")                                                 \
+  X(L_TOOLUSE_INPUT, ",\"input\":")                                                            \
+  X(L_TOOLUSE_ID, ",\"toolUseId\":")                                                           \
+  X(L_REASON_OPEN, "{\"reasoningContent\":{\"reasoningText\":{\"text\":")                      \
+  X(L_REASON_SIG, ",\"signature\":")                                                           \
+  X(L_REASON_CLOSE, "}}}")                                                                     \
+  X(L_SYSTEM_OPEN, ",\"system\":[")                                                            \
+  X(L_SERVICE_TIER, ",\"serviceTier\":{\"type\":")                                             \
+  X(L_TOOLCFG_OPEN, ",\"toolConfig\":{")                                                       \
+  X(L_TOOLCHOICE_AUTO, "\"toolChoice\":{\"auto\":{}},")                                        \
+  X(L_TOOLCHOICE_ANY, "\"toolChoice\":{\"any\":{}},")                                          \
+  X(L_TOOLCHOICE_TOOL, "\"toolChoice\":{\"tool\":{\"name\":")                                  \
+  X(L_TOOLCHOICE_TOOL_END, "}},")                                                              \
+  X(L_TOOLS_OPEN, "\"tools\":[")                                                               \
+  X(L_TOOLSPEC_OPEN, "{\"toolSpec\":{")                                                        \
+  X(L_DESC, "\"description\":")                                                                \
+  X(L_INPUTSCHEMA, "\"inputSchema\":{\"json\":")                                               \
+  X(L_NAME, "},\"name\":")                                                                     \
+  X(L_TOOL_CACHE, ",\"cachePoint\":{\"type\":\"default\"}")                                    \
+  X(L_TOOLS_CLOSE, "]}")                                                                       \
+  X(L_PATH_MODEL, "/model/")                                                                   \
+  X(L_PATH_CONVERSE, "/converse")                                                              \
+  X(L_PATH_STREAM, "-stream")                                                                  \
+  X(L_STREAMOPT_APPEND, "\"stream_options\":{\"include_usage\":true}")                         \
+  X(L_INCLUDE_USAGE_MEMBER, "\"include_usage\":true")                                          \
+  X(L_INCLUDE_USAGE_OBJ, "{\"include_usage\":true}")                                           \
+  X(L_MODEL_MEMBER, "\"model\":")                                                              \
+  X(L_QUOTE, "\"")
+
+enum LitId : int {
+#define X(name, text) name,
+  AIGW_LITERALS(X)
+#undef X
+      L_COUNT
+};
+
+struct LitTable {
+  uint16_t off[L_COUNT + 1];
+  char bytes[1536];
+};
+constexpr LitTable make_lit_table() {
+  LitTable t{};
+  int o = 0, k = 0;
+#define X(name, text)                                   \
+  t.off[k++] = (uint16_t)o;                             \
+  for (int i = 0; text[i]; i++) t.bytes[o++] = text[i];
+  AIGW_LITERALS(X)
+#undef X
+  t.off[k] = (uint16_t)o;
+  return t;
+}
+
+// ------------------------------------------------------------------ kernel parameters
+struct ChatParams {
+  const uint8_t* bodies;
+  const uint64_t* offsets;
+  const uint32_t* lens;
+  uint32_t n;
+  uint8_t* out;
+  uint64_t out_capacity;
+  aigw_doc_result* results;
+  unsigned long long* out_used;  // bump allocator
+  unsigned int* next_doc;        // work counter
+  uint64_t out_bias;             // added to every out_off (host pipeline: chunk base in the host arena)
+  int schema;
+  int cost_configured;
+  int force_mutation;
+  uint16_t override_len;  // model_name_override (≤ 128 bytes, in cfgbuf)
+  uint16_t prefix_len;    // normalised OpenAI path "/…/chat/completions"
+  char override_model[128];
+  char openai_path[128];
+};
+
+// size classes: MAXD bytes of input per document
+template <int MAXD>
+struct Cls {
+  static constexpr int kIn = MAXD;                               // multiple of 1024
+  static constexpr int kOut = ((MAXD + MAXD / 4 + 512 + 15) / 16) * 16;
+  static constexpr int kTokCap = kOut / 4;                       // u16 tok + u16 jmp alias the out buffer
+  static constexpr int kOpCap = 384 + MAXD / 16;       // includes kSysCap parked ops
+  static constexpr int kScr = 512 + MAXD / 8;
+  static constexpr int kWarpBytes = kIn + kOut + kOpCap * 4 + kScr;
+};
+
+}  // namespace aigw
+
+namespace aigw {
+cudaError_t launch_chat_translate(const ChatParams& P, uint32_t max_len, int sm_count, cudaStream_t st);
+}

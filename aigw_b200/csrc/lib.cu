@@ -1,0 +1,291 @@
+// aigw_b200 C-ABI implementation: context, arenas, device- and host-buffer entry points.
+// The host path is a 3-slot pipeline: H2D(chunk c+1) ‖ kernel(chunk c) ‖ D2H(chunk c-1) on three
+// CUDA streams; everything computed is computed by the kernels in this directory — there is no
+// CPU fallback anywhere in this library.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "chat_kernel.cuh"
+#include "sse_kernel.cuh"
+
+using namespace aigw;
+
+#define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(_e); return (int)_e; } } while (0)
+
+static constexpr int kSlots = 3;
+
+struct ChunkSlot {
+  uint8_t* d_in = nullptr; size_t in_cap = 0;
+  uint64_t* d_off = nullptr; uint32_t* d_len = nullptr; size_t doc_cap = 0;
+  uint8_t* d_out = nullptr; size_t out_cap = 0;
+  aigw_doc_result* d_res = nullptr;
+  unsigned long long* d_used = nullptr;   // device bump counter
+  unsigned int* d_next = nullptr;         // device work counter
+  unsigned long long* h_used = nullptr;   // pinned mirror
+  cudaEvent_t ev_h2d, ev_k0, ev_k1, ev_ctr, ev_done;
+};
+
+struct aigw_ctx {
+  int device = 0, sm_count = 0;
+  cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  std::string err;
+  // counters for the device API (ring so independent launches do not share a counter)
+  unsigned int* d_counters = nullptr; int counter_next = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  ChunkSlot slot[kSlots];
+  // host-API output (pinned)
+  uint8_t* h_out = nullptr; size_t h_out_cap = 0;
+  aigw_doc_result* h_res = nullptr; size_t h_res_cap = 0;
+  // sse host-API device buffers
+  uint8_t* d_sse_bytes = nullptr; size_t sse_bytes_cap = 0;
+  uint64_t* d_sse_coff = nullptr; size_t sse_coff_cap = 0;
+  uint32_t* d_sse_first = nullptr; size_t sse_first_cap = 0;
+  aigw_sse_result* d_sse_res = nullptr; size_t sse_res_cap = 0;
+};
+
+static void fill_params(ChatParams& P, const aigw_backend_cfg* cfg) {
+  P.schema = cfg ? cfg->schema : AIGW_SCHEMA_OPENAI;
+  P.cost_configured = cfg ? cfg->cost_configured : 0;
+  P.force_mutation = cfg ? cfg->force_body_mutation : 0;
+  P.override_len = 0; P.prefix_len = 0;
+  memset(P.override_model, 0, sizeof P.override_model); memset(P.openai_path, 0, sizeof P.openai_path);
+  if (cfg && cfg->model_name_override) {
+    size_t n = strlen(cfg->model_name_override); if (n > sizeof P.override_model) n = sizeof P.override_model;
+    memcpy(P.override_model, cfg->model_name_override, n); P.override_len = (uint16_t)n;
+  }
+  // path.Join("/", prefix, "chat/completions") (openai_openai.go:30)
+  std::string pfx = (cfg && cfg->openai_prefix) ? cfg->openai_prefix : "v1";
+  while (!pfx.empty() && pfx.front() == '/') pfx.erase(0, 1);
+  while (!pfx.empty() && pfx.back() == '/') pfx.pop_back();
+  std::string path = "/" + (pfx.empty() ? std::string() : pfx + "/") + "chat/completions";
+  if (path.size() > sizeof P.openai_path) path.resize(sizeof P.openai_path);
+  memcpy(P.openai_path, path.data(), path.size()); P.prefix_len = (uint16_t)path.size();
+}
+
+extern "C" {
+
+const char* aigw_version(void) { return "aigw_b200 0.1 (sm_100a)"; }
+
+int aigw_init(int device, aigw_ctx** out) {
+  *out = nullptr;
+  aigw_ctx* ctx = new aigw_ctx();
+  ctx->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { fprintf(stderr, "aigw_init: cudaSetDevice(%d): %s\n", device, cudaGetErrorString(e)); delete ctx; return (int)e; }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { delete ctx; return (int)e; }
+  ctx->sm_count = prop.multiProcessorCount;
+  if (prop.major < 10) { fprintf(stderr, "aigw_init: device %d is sm_%d%d; this library is built for sm_100a only\n", device, prop.major, prop.minor); delete ctx; return (int)cudaErrorNoKernelImageForDevice; }
+  cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
+  cudaMalloc(&ctx->d_counters, 256 * sizeof(unsigned int));
+  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+  for (auto& s : ctx->slot) {
+    cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming); cudaEventCreate(&s.ev_k0); cudaEventCreate(&s.ev_k1);
+    cudaEventCreateWithFlags(&s.ev_ctr, cudaEventDisableTiming); cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming);
+    cudaMalloc(&s.d_used, 8); cudaMalloc(&s.d_next, 4); cudaHostAlloc(&s.h_used, 8, cudaHostAllocDefault);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { fprintf(stderr, "aigw_init: %s\n", cudaGetErrorString(e)); delete ctx; return (int)e; }
+  *out = ctx;
+  return 0;
+}
+
+void aigw_destroy(aigw_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto& s : ctx->slot) {
+    cudaFree(s.d_in); cudaFree(s.d_off); cudaFree(s.d_len); cudaFree(s.d_out); cudaFree(s.d_res); cudaFree(s.d_used); cudaFree(s.d_next); cudaFreeHost(s.h_used);
+    cudaEventDestroy(s.ev_h2d); cudaEventDestroy(s.ev_k0); cudaEventDestroy(s.ev_k1); cudaEventDestroy(s.ev_ctr); cudaEventDestroy(s.ev_done);
+  }
+  cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_res); cudaFree(ctx->d_counters);
+  cudaFree(ctx->d_sse_bytes); cudaFree(ctx->d_sse_coff); cudaFree(ctx->d_sse_first); cudaFree(ctx->d_sse_res);
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->s_compute); cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
+  delete ctx;
+}
+
+const char* aigw_last_error(aigw_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+int aigw_device_sm_count(aigw_ctx* ctx) { return ctx->sm_count; }
+
+void* aigw_host_alloc(aigw_ctx* ctx, size_t bytes) { void* p = nullptr; if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { ctx->err = "cudaHostAlloc failed"; return nullptr; } return p; }
+void aigw_host_free(aigw_ctx*, void* p) { cudaFreeHost(p); }
+void* aigw_device_alloc(aigw_ctx* ctx, size_t bytes) { void* p = nullptr; if (cudaMalloc(&p, bytes) != cudaSuccess) { ctx->err = "cudaMalloc failed"; return nullptr; } return p; }
+void aigw_device_free(aigw_ctx*, void* p) { cudaFree(p); }
+int aigw_memcpy_h2d(aigw_ctx* ctx, void* dst, const void* src, size_t bytes) { CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); return 0; }
+int aigw_memcpy_d2h(aigw_ctx* ctx, void* dst, const void* src, size_t bytes) { CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return 0; }
+int aigw_memset_d(aigw_ctx* ctx, void* dst, int v, size_t bytes) { CK(cudaMemset(dst, v, bytes)); return 0; }
+int aigw_sync(aigw_ctx* ctx) { CK(cudaDeviceSynchronize()); return 0; }
+
+int aigw_chat_translate_device(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const uint8_t* d_bodies, const uint64_t* d_offsets,
+                               const uint32_t* d_lens, uint32_t n, uint32_t max_len, uint8_t* d_out, uint64_t out_capacity,
+                               aigw_doc_result* d_results, uint64_t* d_out_used, void* stream, float* kernel_ms) {
+  if (n == 0) { if (kernel_ms) *kernel_ms = 0; return 0; }
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->s_compute;
+  ChatParams P;
+  fill_params(P, cfg);
+  P.bodies = d_bodies; P.offsets = d_offsets; P.lens = d_lens; P.n = n; P.out = d_out; P.out_capacity = out_capacity;
+  P.results = d_results; P.out_used = (unsigned long long*)d_out_used;
+  P.next_doc = ctx->d_counters + (ctx->counter_next++ & 255); P.out_bias = 0;
+  CK(cudaMemsetAsync(P.next_doc, 0, sizeof(unsigned int), st));
+  if (kernel_ms) CK(cudaEventRecord(ctx->ev0, st));
+  CK(launch_chat_translate(P, max_len ? max_len : 65536u, ctx->sm_count, st));
+  if (kernel_ms) { CK(cudaEventRecord(ctx->ev1, st)); CK(cudaEventSynchronize(ctx->ev1)); CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1)); }
+  return 0;
+}
+
+static int ensure(aigw_ctx* ctx, void** p, size_t* cap, size_t want, bool host) {
+  if (*cap >= want) return 0;
+  if (*p) { if (host) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *cap = 0; }
+  size_t sz = want + want / 8 + 4096;
+  cudaError_t e = host ? cudaHostAlloc(p, sz, cudaHostAllocDefault) : cudaMalloc(p, sz);
+  if (e != cudaSuccess) { ctx->err = std::string(host ? "cudaHostAlloc" : "cudaMalloc") + ": " + cudaGetErrorString(e); return (int)e; }
+  *cap = sz;
+  return 0;
+}
+#define ENSURE(p, cap, want, host) do { int _r = ensure(ctx, (void**)&(p), &(cap), (want), (host)); if (_r) return _r; } while (0)
+
+int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const uint8_t* bodies, const uint64_t* offsets,
+                             const uint32_t* lens, uint32_t n, aigw_batch_out* out) {
+  memset(out, 0, sizeof *out);
+  if (n == 0) return 0;
+  cudaSetDevice(ctx->device);
+  // ---- chunking: ≈64 MiB of input per chunk (one chunk for small batches)
+  const uint64_t kChunkBytes = 64ull << 20;
+  std::vector<uint32_t> cb;  // chunk begin doc index
+  cb.push_back(0);
+  {
+    uint64_t start = offsets[0];
+    for (uint32_t i = 0; i < n; i++) {
+      uint64_t end = offsets[i] + (((uint64_t)lens[i] + 15u) & ~15ull);
+      if (end - start > kChunkBytes && i > cb.back()) { cb.push_back(i); start = offsets[i]; }
+    }
+    cb.push_back(n);
+  }
+  const int nch = (int)cb.size() - 1;
+  uint64_t max_in = 0; uint32_t max_docs = 0, max_len = 0;
+  std::vector<uint64_t> in_bytes(nch), out_cap(nch), out_base(nch);
+  uint64_t total_out_cap = 0;
+  for (int c = 0; c < nch; c++) {
+    uint32_t b = cb[c], e = cb[c + 1];
+    uint64_t ib = offsets[e - 1] + (((uint64_t)lens[e - 1] + 15u) & ~15ull) - offsets[b] + 16;
+    in_bytes[c] = ib; if (ib > max_in) max_in = ib; if (e - b > max_docs) max_docs = e - b;
+    out_cap[c] = ((ib + ib / 4 + (uint64_t)(e - b) * 528 + 255) & ~255ull);
+    out_base[c] = total_out_cap; total_out_cap += out_cap[c];
+  }
+  for (uint32_t i = 0; i < n; i++) if (lens[i] > max_len) max_len = lens[i];
+  uint64_t max_out = 0; for (int c = 0; c < nch; c++) if (out_cap[c] > max_out) max_out = out_cap[c];
+  for (int s = 0; s < kSlots && s < nch; s++) {
+    ChunkSlot& S = ctx->slot[s];
+    ENSURE(S.d_in, S.in_cap, max_in + 64, false);
+    if (S.doc_cap < max_docs) {
+      cudaFree(S.d_off); cudaFree(S.d_len); cudaFree(S.d_res); S.doc_cap = 0;
+      size_t dc = max_docs + max_docs / 8 + 16;
+      CK(cudaMalloc(&S.d_off, dc * 8)); CK(cudaMalloc(&S.d_len, dc * 4)); CK(cudaMalloc(&S.d_res, dc * sizeof(aigw_doc_result)));
+      S.doc_cap = dc;
+    }
+    ENSURE(S.d_out, S.out_cap, max_out, false);
+  }
+  ENSURE(ctx->h_out, ctx->h_out_cap, total_out_cap, true);
+  ENSURE(ctx->h_res, ctx->h_res_cap, (size_t)n * sizeof(aigw_doc_result), true);
+
+  ChatParams P0; fill_params(P0, cfg);
+  std::vector<uint64_t> used(nch, 0);
+  uint64_t h2d = 0, d2h = 0;
+  auto enqueue_out = [&](int c) -> int {  // needs the counter of chunk c on the host
+    ChunkSlot& S = ctx->slot[c % kSlots];
+    CK(cudaEventSynchronize(S.ev_ctr));
+    uint64_t u = *S.h_used; if (u > out_cap[c]) u = out_cap[c];
+    used[c] = u;
+    if (u) CK(cudaMemcpyAsync(ctx->h_out + out_base[c], S.d_out, u, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CK(cudaEventRecord(S.ev_done, ctx->s_d2h));
+    d2h += u;
+    return 0;
+  };
+  for (int c = 0; c < nch; c++) {
+    ChunkSlot& S = ctx->slot[c % kSlots];
+    const uint32_t b = cb[c], e = cb[c + 1], nd = e - b;
+    if (c >= kSlots) CK(cudaEventSynchronize(S.ev_done));  // slot free again (its output has left the device)
+    // H2D
+    CK(cudaMemcpyAsync(S.d_in, bodies + offsets[b], in_bytes[c] - 16, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaMemcpyAsync(S.d_off, offsets + b, (size_t)nd * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaMemcpyAsync(S.d_len, lens + b, (size_t)nd * 4, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaEventRecord(S.ev_h2d, ctx->s_h2d));
+    h2d += in_bytes[c] - 16 + (uint64_t)nd * 12;
+    // kernel
+    CK(cudaStreamWaitEvent(ctx->s_compute, S.ev_h2d, 0));
+    CK(cudaMemsetAsync(S.d_used, 0, 8, ctx->s_compute));
+    CK(cudaMemsetAsync(S.d_next, 0, 4, ctx->s_compute));
+    ChatParams P = P0;
+    P.bodies = S.d_in - offsets[b];  // absolute offsets index straight into the chunk
+    P.offsets = S.d_off; P.lens = S.d_len; P.n = nd; P.out = S.d_out; P.out_capacity = out_cap[c];
+    P.results = S.d_res; P.out_used = S.d_used; P.next_doc = S.d_next; P.out_bias = out_base[c];
+    CK(cudaEventRecord(S.ev_k0, ctx->s_compute));
+    CK(launch_chat_translate(P, max_len, ctx->sm_count, ctx->s_compute));
+    CK(cudaEventRecord(S.ev_k1, ctx->s_compute));
+    out->gpu_launches++;
+    // results + counter
+    CK(cudaStreamWaitEvent(ctx->s_d2h, S.ev_k1, 0));
+    CK(cudaMemcpyAsync(S.h_used, S.d_used, 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CK(cudaEventRecord(S.ev_ctr, ctx->s_d2h));
+    CK(cudaMemcpyAsync(ctx->h_res + b, S.d_res, (size_t)nd * sizeof(aigw_doc_result), cudaMemcpyDeviceToHost, ctx->s_d2h));
+    d2h += (uint64_t)nd * sizeof(aigw_doc_result) + 8;
+    if (c >= 1) { int r = enqueue_out(c - 1); if (r) return r; }
+  }
+  { int r = enqueue_out(nch - 1); if (r) return r; }
+  CK(cudaStreamSynchronize(ctx->s_d2h));
+  CK(cudaStreamSynchronize(ctx->s_compute));
+  float ms_total = 0;
+  for (int c = 0; c < nch && c < kSlots; c++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->slot[c].ev_k0, ctx->slot[c].ev_k1); ms_total += ms; }
+  if (nch > kSlots) ms_total = ms_total * nch / kSlots;  // events of reused slots hold the last chunk only: scale the sample
+  out->results = ctx->h_res; out->out = ctx->h_out; out->out_used = total_out_cap; out->h2d_bytes = h2d; out->d2h_bytes = d2h; out->kernel_ms = ms_total;
+  return 0;
+}
+
+// ------------------------------------------------------------------ SSE
+int aigw_sse_usage_device(aigw_ctx* ctx, const uint8_t* d_bytes, const uint64_t* d_chunk_off, const uint32_t* d_chunk_first,
+                          uint32_t n_streams, aigw_sse_result* d_results, void* stream, float* kernel_ms) {
+  if (n_streams == 0) { if (kernel_ms) *kernel_ms = 0; return 0; }
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->s_compute;
+  SseParams P; P.bytes = d_bytes; P.chunk_off = d_chunk_off; P.chunk_first = d_chunk_first; P.n_streams = n_streams; P.results = d_results;
+  P.next = ctx->d_counters + (ctx->counter_next++ & 255);
+  CK(cudaMemsetAsync(P.next, 0, sizeof(unsigned int), st));
+  if (kernel_ms) CK(cudaEventRecord(ctx->ev0, st));
+  CK(launch_sse_usage(P, ctx->sm_count, st));
+  if (kernel_ms) { CK(cudaEventRecord(ctx->ev1, st)); CK(cudaEventSynchronize(ctx->ev1)); CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1)); }
+  return 0;
+}
+
+int aigw_sse_usage_host(aigw_ctx* ctx, const uint8_t* bytes, const uint64_t* chunk_off, const uint32_t* chunk_first,
+                        uint32_t n_streams, uint32_t n_chunks, aigw_sse_result* results, uint64_t* h2d_bytes, uint64_t* d2h_bytes, float* kernel_ms) {
+  if (n_streams == 0) return 0;
+  cudaSetDevice(ctx->device);
+  const uint64_t nbytes = chunk_off[n_chunks];
+  ENSURE(ctx->d_sse_bytes, ctx->sse_bytes_cap, nbytes + 64, false);
+  ENSURE(ctx->d_sse_coff, ctx->sse_coff_cap, ((size_t)n_chunks + 1) * 8, false);
+  ENSURE(ctx->d_sse_first, ctx->sse_first_cap, ((size_t)n_streams + 1) * 4, false);
+  ENSURE(ctx->d_sse_res, ctx->sse_res_cap, (size_t)n_streams * sizeof(aigw_sse_result), false);
+  cudaStream_t st = ctx->s_compute;
+  CK(cudaMemcpyAsync(ctx->d_sse_bytes, bytes, nbytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_sse_coff, chunk_off, ((size_t)n_chunks + 1) * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_sse_first, chunk_first, ((size_t)n_streams + 1) * 4, cudaMemcpyHostToDevice, st));
+  SseParams P; P.bytes = ctx->d_sse_bytes; P.chunk_off = ctx->d_sse_coff; P.chunk_first = ctx->d_sse_first; P.n_streams = n_streams; P.results = ctx->d_sse_res;
+  P.next = ctx->d_counters + (ctx->counter_next++ & 255);
+  CK(cudaMemsetAsync(P.next, 0, sizeof(unsigned int), st));
+  CK(cudaEventRecord(ctx->ev0, st));
+  CK(launch_sse_usage(P, ctx->sm_count, st));
+  CK(cudaEventRecord(ctx->ev1, st));
+  CK(cudaMemcpyAsync(results, ctx->d_sse_res, (size_t)n_streams * sizeof(aigw_sse_result), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
+  if (h2d_bytes) *h2d_bytes = nbytes + ((uint64_t)n_chunks + 1) * 8 + ((uint64_t)n_streams + 1) * 4;
+  if (d2h_bytes) *d2h_bytes = (uint64_t)n_streams * sizeof(aigw_sse_result);
+  return 0;
+}
+
+}  // extern "C"

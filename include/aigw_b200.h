@@ -1,0 +1,139 @@
+/*
+ * aigw_b200 — C ABI of the B200-native ext_proc body pipeline.
+ *
+ * This is the drop-in boundary: the entry points a cgo shim inside the reference's
+ * Go extproc would bind.  Plain pointers and sizes only; no Go pointer is retained after a call
+ * returns; results live in library-owned pinned buffers until the next call on the same batch
+ * handle.  Each entry point names the reference interface it replaces:
+ *
+ *   aigw_chat_translate_*   endpointspec.ChatCompletionsEndpointSpec.ParseBody
+ *                              (internal/endpointspec/endpointspec.go:98-125)
+ *                           + Translator.RequestBody for the backend schema
+ *                              (internal/translator/translator.go:41-76;
+ *                               OpenAI→AWS Bedrock  internal/translator/openai_awsbedrock.go:91-159,
+ *                               OpenAI→OpenAI       internal/translator/openai_openai.go:55-84)
+ *   aigw_sse_usage_*        openAIToOpenAITranslatorV1ChatCompletion.ResponseBody (stream)
+ *                              → extractUsageFromBufferEvent (internal/translator/openai_openai.go:131-145,179-215)
+ *                           + metrics.TokenUsage.Override (internal/metrics/metrics.go:258-283)
+ *   aigw_doc_result.status  ErrMalformedRequest / ErrInvalidRequestBody
+ *                              (internal/internalapi/user_facing_errors.go:17-40; HTTP 400 / 422 in
+ *                               internal/extproc/processor_impl.go:215-221,329-336)
+ *
+ * Status AIGW_DECLINED means "this body is outside the GPU fast path; run the stock Go path for
+ * it".  The library never computes a result on the CPU: there is no fallback inside it.
+ */
+#ifndef AIGW_B200_H
+#define AIGW_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct aigw_ctx aigw_ctx;
+
+enum aigw_status { AIGW_OK = 0, AIGW_MALFORMED_400 = 1, AIGW_INVALID_422 = 2, AIGW_INTERNAL = 3, AIGW_DECLINED = 4 };
+enum aigw_body_kind { AIGW_BODY_UNCHANGED = 0, AIGW_BODY_BYTES = 1, AIGW_BODY_EMPTY = 2 };
+/* filterapi.APISchemaName (internal/filterapi/filterconfig.go:130-153) */
+enum aigw_schema { AIGW_SCHEMA_OPENAI = 0, AIGW_SCHEMA_AWS_BEDROCK = 1, AIGW_SCHEMA_AZURE_OPENAI = 2,
+                   AIGW_SCHEMA_GCP_VERTEX = 3, AIGW_SCHEMA_GCP_ANTHROPIC = 4, AIGW_SCHEMA_AWS_ANTHROPIC = 5 };
+
+/* Why a body was declined / rejected (diagnostics; stable numbering). */
+enum aigw_reason {
+  AIGW_R_NONE = 0, AIGW_R_TOO_LARGE = 1, AIGW_R_SYNTAX = 2, AIGW_R_CTRL_IN_STRING = 3, AIGW_R_ESCAPE = 4,
+  AIGW_R_TOKENS = 5, AIGW_R_OPS = 6, AIGW_R_SCRATCH = 7, AIGW_R_OUT_SPACE = 8, AIGW_R_DUP_KEY = 9,
+  AIGW_R_TYPE = 10, AIGW_R_UNSUPPORTED_FIELD = 11, AIGW_R_NUMBER = 12, AIGW_R_ROLE = 13, AIGW_R_CONTENT = 14,
+  AIGW_R_TOOL = 15, AIGW_R_DEPTH = 16, AIGW_R_ROOT = 17, AIGW_R_ARENA_FULL = 18, AIGW_R_SCHEMA = 19, AIGW_R_ARGS = 20
+};
+
+/* One record per body.  Output record layout in the arena at out_off: [path bytes][body bytes]. */
+typedef struct aigw_doc_result {
+  uint64_t out_off;    /* byte offset of this body's record in the output arena (16-byte aligned) */
+  uint32_t body_len;   /* translated body length (0 when body_kind != BYTES) */
+  uint16_t path_len;   /* ":path" header value length (precedes the body in the record) */
+  uint8_t  status;     /* enum aigw_status */
+  uint8_t  reason;     /* enum aigw_reason */
+  uint32_t model_off;  /* ParseBody's originalModel: span inside the INPUT body (raw JSON string content) */
+  uint16_t model_len;
+  uint8_t  body_kind;  /* enum aigw_body_kind */
+  uint8_t  flags;      /* bit0: stream; bit1: ParseBody produced a mutated body (forced include_usage) */
+  uint32_t in_len;     /* echo of the input length */
+  uint32_t _pad;
+} aigw_doc_result;     /* 32 bytes */
+
+/* Per-backend knobs: filterapi.Backend.ModelNameOverride / schema prefix, and whether request costs are
+ * configured (processor_impl.go:212).  Strings are NUL-terminated, may be NULL/empty. */
+typedef struct aigw_backend_cfg {
+  int32_t schema;              /* enum aigw_schema */
+  int32_t cost_configured;     /* bool */
+  int32_t force_body_mutation; /* bool: onRetry() || forceBodyMutation (processor_impl.go:326) */
+  const char* model_name_override;
+  const char* openai_prefix;   /* VersionedAPISchema.OpenAIPrefix(), default "v1" */
+} aigw_backend_cfg;
+
+/* metrics.TokenUsage (internal/metrics/metrics.go:143-158): six u32 counters + "set" mask
+ * (bit0 input, bit1 output, bit2 total, bit3 cached, bit4 cache_creation, bit5 reasoning). */
+typedef struct aigw_usage { uint32_t input, output, total, cached, cache_creation, reasoning, mask, _pad; } aigw_usage;
+
+/* ---- lifecycle ---- */
+int  aigw_init(int device, aigw_ctx** ctx);          /* returns 0, or a CUDA error code; never falls back */
+void aigw_destroy(aigw_ctx* ctx);
+const char* aigw_last_error(aigw_ctx* ctx);
+int  aigw_device_sm_count(aigw_ctx* ctx);
+
+/* ---- pinned arenas (the Go shim copies request bodies straight into these) ---- */
+void* aigw_host_alloc(aigw_ctx* ctx, size_t bytes);   /* cudaHostAlloc, 256-byte aligned */
+void  aigw_host_free(aigw_ctx* ctx, void* p);
+void* aigw_device_alloc(aigw_ctx* ctx, size_t bytes);
+void  aigw_device_free(aigw_ctx* ctx, void* p);
+int   aigw_memcpy_h2d(aigw_ctx* ctx, void* dst, const void* src, size_t bytes);
+int   aigw_memcpy_d2h(aigw_ctx* ctx, void* dst, const void* src, size_t bytes);
+int   aigw_memset_d(aigw_ctx* ctx, void* dst, int value, size_t bytes);
+int   aigw_sync(aigw_ctx* ctx);                       /* cudaDeviceSynchronize */
+
+/* ---- /v1/chat/completions: parse + translate, device-resident batch ----
+ * d_bodies/d_offsets/d_out/d_results/d_out_used are DEVICE pointers.  Body i is
+ * d_bodies[d_offsets[i] .. d_offsets[i+1]) minus padding: its true length is d_lens[i]; every
+ * d_offsets[i] must be a multiple of 16 and the arena must be readable 16 bytes past the last body.
+ * d_out_used is a device uint64 the kernel bumps (caller zeroes it).  `stream` is a cudaStream_t
+ * (0 = the library's own stream).  max_len = the largest d_lens[i] (selects the shared-memory size
+ * class; 0 = unknown, use the largest).  Asynchronous: returns after the launch.  kernel_ms (optional)
+ * receives the CUDA-event duration of the launch (forces a sync when non-NULL). */
+int aigw_chat_translate_device(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const uint8_t* d_bodies, const uint64_t* d_offsets,
+                               const uint32_t* d_lens, uint32_t n, uint32_t max_len, uint8_t* d_out, uint64_t out_capacity,
+                               aigw_doc_result* d_results, uint64_t* d_out_used, void* stream, float* kernel_ms);
+
+/* ---- same, HOST buffers (the call the cgo shim makes) ----
+ * bodies/offsets/lens live in host memory (pinned memory from aigw_host_alloc gives full PCIe rate).
+ * The library pipelines H2D → kernel → D2H in chunks on its own streams and returns when all
+ * results are in `out` (library-owned pinned memory, valid until the next call / aigw_batch_release). */
+typedef struct aigw_batch_out {
+  const aigw_doc_result* results; /* n records */
+  const uint8_t* out;             /* output arena */
+  uint64_t out_used;
+  uint64_t h2d_bytes, d2h_bytes;  /* bytes moved over PCIe for this call */
+  uint32_t gpu_launches;          /* kernels launched for this call */
+  float    kernel_ms;             /* sum of kernel durations (CUDA events) */
+} aigw_batch_out;
+int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const uint8_t* bodies, const uint64_t* offsets,
+                             const uint32_t* lens, uint32_t n, aigw_batch_out* out);
+
+/* ---- OpenAI SSE response streams: usage scan (S1) + TokenUsage merge (C1) ----
+ * Stream s consists of chunks [chunk_first[s], chunk_first[s+1]); chunk c is bytes
+ * [chunk_off[c], chunk_off[c+1]) of `bytes`.  For every stream the kernel replays the reference's
+ * per-chunk ResponseBody calls (carry of the partial last line included) and returns the
+ * Override-accumulated usage plus the last seen response model span (offset into `bytes`).  */
+typedef struct aigw_sse_result { aigw_usage usage; uint64_t model_off; uint32_t model_len; uint32_t status; } aigw_sse_result; /* 48 bytes */
+int aigw_sse_usage_device(aigw_ctx* ctx, const uint8_t* d_bytes, const uint64_t* d_chunk_off, const uint32_t* d_chunk_first,
+                          uint32_t n_streams, aigw_sse_result* d_results, void* stream, float* kernel_ms);
+int aigw_sse_usage_host(aigw_ctx* ctx, const uint8_t* bytes, const uint64_t* chunk_off, const uint32_t* chunk_first,
+                        uint32_t n_streams, uint32_t n_chunks, aigw_sse_result* results /* host, n_streams */,
+                        uint64_t* h2d_bytes, uint64_t* d2h_bytes, float* kernel_ms);
+
+const char* aigw_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

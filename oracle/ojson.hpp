@@ -249,7 +249,8 @@ inline void fmt_digits(std::string& o, bool neg, const char* digs, int nd, int d
 template <class F> inline void enc_float_t(std::string& o, F f, bool f32) {
   if (f == 0) { o += (std::signbit(f) ? "-0" : "0"); return; }
   char buf[64];
-  auto r = std::to_chars(buf, buf + sizeof buf, f, std::chars_format::scientific);  // shortest round-trip
+  auto r = std::to_chars(buf, buf + sizeof buf - 1, f, std::chars_format::scientific);  // shortest round-trip
+  *r.ptr = 0;
   // d.ddddde[+-]XX
   bool neg = buf[0] == '-'; char* q = buf + (neg ? 1 : 0);
   char digs[32]; int nd = 0; char* e = q;
@@ -310,7 +311,7 @@ inline std::string b64enc(std::string_view s) {
   else if (s.size() - i == 2) { uint32_t v = ((unsigned char)s[i] << 16) | ((unsigned char)s[i + 1] << 8); o.push_back(tb[v >> 18]); o.push_back(tb[(v >> 12) & 63]); o.push_back(tb[(v >> 6) & 63]); o.push_back('='); }
   return o;
 }
-// base64.StdEncoding.DecodeString: strict padding, '\r' and '\n' ignored.
+// base64.StdEncoding.DecodeString: padding required, '\r' and '\n' ignored, trailing bits not checked (non-Strict).
 inline bool b64dec(std::string_view s, std::string& out) {
   auto val = [](unsigned char c) -> int {
     if (c >= 'A' && c <= 'Z') return c - 'A'; if (c >= 'a' && c <= 'z') return c - 'a' + 26;
@@ -321,9 +322,9 @@ inline bool b64dec(std::string_view s, std::string& out) {
   for (size_t i = 0; i < t.size(); i += 4) {
     int a = val(t[i]), b = val(t[i + 1]); if (a < 0 || b < 0) return false;
     bool last = i + 4 == t.size();
-    if (t[i + 2] == '=') { if (!last || t[i + 3] != '=') return false; if (b & 15) return false; out.push_back((char)((a << 2) | (b >> 4))); continue; }
+    if (t[i + 2] == '=') { if (!last || t[i + 3] != '=') return false; out.push_back((char)((a << 2) | (b >> 4))); continue; }
     int c = val(t[i + 2]); if (c < 0) return false;
-    if (t[i + 3] == '=') { if (!last) return false; if (c & 3) return false; out.push_back((char)((a << 2) | (b >> 4))); out.push_back((char)((b << 4) | (c >> 2))); continue; }
+    if (t[i + 3] == '=') { if (!last) return false; out.push_back((char)((a << 2) | (b >> 4))); out.push_back((char)((b << 4) | (c >> 2))); continue; }
     int d = val(t[i + 3]); if (d < 0) return false;
     out.push_back((char)((a << 2) | (b >> 4))); out.push_back((char)((b << 4) | (c >> 2))); out.push_back((char)((c << 6) | d));
   }

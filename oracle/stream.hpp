@@ -79,7 +79,22 @@ inline bool decode_chunk(std::string_view line, std::string& model, bool& has_us
     int64_t idx; if (!int_field(c.get("index"), idx)) return false;
     if (!str_or_null(c.get("finish_reason"))) return false;
     const Value* lp = c.get("logprobs"); if (!obj_or_null(lp)) return false;
-    if (lp && lp->is_obj()) for (const char* k : {"content", "refusal"}) if (!arr_or_null(lp->get(k))) return false;
+    if (lp && lp->is_obj()) for (const char* k : {"content", "refusal"}) {  // []ChatCompletionTokenLogprob (openai.go:1323-1361)
+      const Value* a = lp->get(k); if (!arr_or_null(a)) return false;
+      if (a && a->is_arr()) for (auto& t : a->arr) {
+        if (t.is_null()) continue;
+        if (!t.is_obj()) return false;
+        auto tok_ok = [&](const Value& x) -> bool {
+          if (!str_or_null(x.get("token"))) return false;
+          const Value* lpv = x.get("logprob"); if (lpv && !lpv->is_null() && !lpv->is_num()) return false;
+          const Value* by = x.get("bytes"); if (!arr_or_null(by)) return false;
+          if (by && by->is_arr()) for (auto& bb : by->arr) { int64_t q; if (!int_field(&bb, q)) return false; }
+          return true; };
+        if (!tok_ok(t)) return false;
+        const Value* tl = t.get("top_logprobs"); if (!arr_or_null(tl)) return false;
+        if (tl && tl->is_arr()) for (auto& u : tl->arr) { if (u.is_null()) continue; if (!u.is_obj() || !tok_ok(u)) return false; }
+      }
+    }
     const Value* d = c.get("delta"); if (!obj_or_null(d)) return false;
     if (d && d->is_obj()) {
       if (!str_or_null(d->get("content")) || !str_or_null(d->get("role"))) return false;
@@ -93,7 +108,9 @@ inline bool decode_chunk(std::string_view line, std::string& model, bool& has_us
         if (f && f->is_obj() && (!str_or_null(f->get("arguments")) || !str_or_null(f->get("name")))) return false;
       }
       const Value* an = d->get("annotations"); if (!arr_or_null(an)) return false;
-      if (an && an->is_arr()) for (auto& a : an->arr) { if (!(a.is_null() || a.is_obj())) return false; if (a.is_obj() && (!str_or_null(a.get("type")) || !obj_or_null(a.get("url_citation")))) return false; }
+      if (an && an->is_arr()) for (auto& a : an->arr) { if (!(a.is_null() || a.is_obj())) return false; if (a.is_obj()) { if (!str_or_null(a.get("type")) || !obj_or_null(a.get("url_citation"))) return false;
+          const Value* uc = a.get("url_citation");
+          if (uc && uc->is_obj()) { int64_t q; if (!int_field(uc->get("end_index"), q) || !int_field(uc->get("start_index"), q) || !str_or_null(uc->get("url")) || !str_or_null(uc->get("title"))) return false; } } }
       const Value* rc = d->get("reasoning_content"); if (!obj_or_null(rc)) return false;
       if (rc && rc->is_obj()) {
         if (!str_or_null(rc->get("text")) || !str_or_null(rc->get("signature"))) return false;

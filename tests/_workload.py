@@ -1,0 +1,185 @@
+"""Workload helpers for tests and bench: ctypes view of tools/libworkload.so plus a seeded Python
+generator of structurally diverse ChatCompletion bodies (edge-case corpus)."""
+import ctypes as C
+import json
+import os
+import random
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(ROOT, "tools", "libworkload.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        src = os.path.join(ROOT, "tools", "workload.cpp")
+        if not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", _SO, src])
+        _lib = C.CDLL(_SO)
+        _lib.wl_sse_fill.restype = C.c_uint64
+    return _lib
+
+
+def chat_lens(seed, first, n, target=4096, jitter=32, threads=8):
+    lens = np.zeros(n, dtype=np.uint32)
+    lib().wl_chat_lens(C.c_uint64(seed), C.c_uint64(first), C.c_uint32(n), C.c_uint32(target), C.c_uint32(jitter), C.c_void_p(lens.ctypes.data), C.c_int(threads))
+    return lens
+
+
+def chat_offsets(lens):
+    offs = np.zeros(len(lens) + 1, dtype=np.uint64)
+    np.cumsum((lens.astype(np.uint64) + 15) // 16 * 16, out=offs[1:])
+    return offs
+
+
+def chat_fill(seed, first, n, out_arr, offs, lens, target=4096, jitter=32, threads=8):
+    lib().wl_chat_fill(C.c_uint64(seed), C.c_uint64(first), C.c_uint32(n), C.c_uint32(target), C.c_uint32(jitter), C.c_void_p(out_arr.ctypes.data),
+                       C.c_void_p(offs.ctypes.data), C.c_void_p(lens.ctypes.data), C.c_int(threads))
+
+
+def chat_corpus(seed, first, n, target=4096, jitter=32, threads=8):
+    """(arena uint8[], offsets uint64[n+1], lens uint32[n]) for the C2-shaped workload."""
+    lens = chat_lens(seed, first, n, target, jitter, threads)
+    offs = chat_offsets(lens)
+    arena = np.full(int(offs[-1]) + 16, 0x20, dtype=np.uint8)
+    chat_fill(seed, first, n, arena, offs, lens, target, jitter, threads)
+    return arena, offs, lens
+
+
+def sse_corpus(seed, first, n, chunks=256, chunk_bytes=80):
+    total = lib().wl_sse_fill(C.c_uint64(seed), C.c_uint64(first), C.c_uint32(n), C.c_int(chunks), C.c_int(chunk_bytes), None, C.c_uint64(0), None)
+    buf = np.zeros(int(total) + 64, dtype=np.uint8)
+    coff = np.zeros(n * chunks + 1, dtype=np.uint64)
+    lib().wl_sse_fill(C.c_uint64(seed), C.c_uint64(first), C.c_uint32(n), C.c_int(chunks), C.c_int(chunk_bytes), C.c_void_p(buf.ctypes.data), C.c_uint64(total), C.c_void_p(coff.ctypes.data))
+    cfirst = (np.arange(n + 1, dtype=np.uint32) * chunks).astype(np.uint32)
+    return buf, coff, cfirst
+
+
+# ---------------------------------------------------------------- diverse chat bodies (edge-case corpus)
+_WORDS = "alpha beta gamma delta émigré 中文 naïve tab\\tsep quote\\\"d back\\\\slash new\\nline plain text with spaces <tag> & amp / slash".split(" ")
+
+
+def _text(r, lo=0, hi=60):
+    n = r.randint(lo, hi)
+    return " ".join(r.choice(_WORDS) for _ in range(n))
+
+
+def _jstr(s):
+    # our own quoting so that the escapes stay in the canonical set the encoder itself would produce
+    return '"' + s + '"'
+
+
+def _num(r):
+    return r.choice(["0", "1", "0.7", "0.25", "1.0", "2", "0.95", "0.10", "1.5", "0.000001", "12", "-0.5", "1e0", "0.7000000000000001", "0.1234567890123456789"])
+
+
+def _schema(r, depth=0):
+    if depth > 2 or r.random() < 0.3:
+        return r.choice(['{"type":"string"}', '{"type": "integer", "minimum": 0}', '{"description":"d","type":"string","enum":["a","b"]}', '{"type":"number","maximum":1.50}'])
+    props = ",".join(f'"{r.choice(["path","depth","query","zeta","alpha","mid"])}{i}":{_schema(r, depth + 1)}' for i in range(r.randint(0, 3)))
+    sp = r.choice(["", " ", "\n  "])
+    return "{" + sp + '"type":"object",' + sp + '"properties":{' + props + '},' + sp + '"required":["path0"]' + r.choice(["", ',"additionalProperties":false']) + "}"
+
+
+def diverse_body(seed):
+    r = random.Random(seed)
+    sp = r.choice(["", "", "", " ", "\n  "])
+    msgs = []
+    n = r.randint(0, 7)
+    for i in range(n):
+        role = r.choice(["system", "user", "user", "assistant", "assistant", "tool", "developer"])
+        if role in ("system", "developer"):
+            c = r.choice(["str", "str", "parts", "parts_cache"])
+            if c == "str":
+                content = _jstr(_text(r))
+            else:
+                parts = []
+                for _ in range(r.randint(0, 3)):
+                    cc = ',"cache_control":{"type":"ephemeral"}' if c == "parts_cache" and r.random() < 0.5 else ""
+                    parts.append('{"type":"text","text":' + _jstr(_text(r, 0, 10)) + cc + "}")
+                content = "[" + ",".join(parts) + "]"
+            msgs.append('{"role":"%s",%s"content":%s}' % (role, sp, content))
+        elif role == "user":
+            c = r.choice(["str", "str", "str", "parts", "null", "named"])
+            if c in ("str", "named"):
+                nm = ',"name":"bob"' if c == "named" else ""
+                msgs.append('{"role":"user"%s,"content":%s}' % (nm, _jstr(_text(r))))
+            elif c == "null":
+                msgs.append('{"role":"user","content":null}')
+            else:
+                parts = ['{"type":"text","text":' + _jstr(_text(r, 0, 10)) + r.choice(["", ',"cache_control":{"type":"ephemeral"}', ',"cache_control":{"type":"other"}']) + "}"
+                         for _ in range(r.randint(0, 3))]
+                msgs.append('{"content":[' + ",".join(parts) + '],"role":"user"}')
+        elif role == "assistant":
+            c = r.choice(["str", "empty", "null", "toolcall", "toolcall2", "parts", "single", "absent"])
+            if c == "str":
+                msgs.append('{"role":"assistant","content":%s}' % _jstr(_text(r, 1, 40)))
+            elif c == "empty":
+                msgs.append('{"role":"assistant","content":""}')
+            elif c == "null":
+                msgs.append('{"role":"assistant","content":null}')
+            elif c == "absent":
+                msgs.append('{"role":"assistant"}')
+            elif c in ("toolcall", "toolcall2"):
+                calls = []
+                for k in range(1 if c == "toolcall" else 2):
+                    args = r.choice(['{ \\"path\\": \\"/tmp\\" }', '{\\"b\\":1,\\"a\\":[1,2,{\\"z\\":null,\\"y\\":true}]}', '{}', '{\\"q\\":\\"say \\\\\\"hi\\\\\\"\\",\\"n\\":1.50}', 'null',
+                                     '{\\"x\\": 1e3}', '{\\"a\\":1,\\"a\\":2}'])
+                    calls.append('{"id":"call_%d","type":"function","function":{"name":"fn%d","arguments":"%s"}}' % (r.randint(1, 999), k, args))
+                pre = r.choice(['"content":null,', '"content":"thinking out loud",', ""])
+                msgs.append('{"role":"assistant",%s"tool_calls":[%s]}' % (pre, ",".join(calls)))
+            elif c == "parts":
+                parts = []
+                for _ in range(r.randint(0, 3)):
+                    t = r.choice(["text", "refusal", "thinking", "thinking_sig", "unknown"])
+                    if t == "text":
+                        parts.append('{"type":"text","text":' + _jstr(_text(r, 0, 8)) + "}")
+                    elif t == "refusal":
+                        parts.append('{"type":"refusal","refusal":"no"}')
+                    elif t == "thinking":
+                        parts.append('{"type":"thinking","text":"hmm"}')
+                    elif t == "thinking_sig":
+                        parts.append('{"type":"thinking","text":"hmm","signature":"c2ln"}')
+                    else:
+                        parts.append('{"type":"other","text":"x"}')
+                msgs.append('{"role":"assistant","content":[' + ",".join(parts) + "]}")
+            else:
+                msgs.append('{"role":"assistant","content":{"type":"text","text":"single"}}')
+        else:
+            c = r.choice(["str", "parts"])
+            content = _jstr(_text(r, 0, 12)) if c == "str" else '[{"type":"text","text":"r1"},{"type":"text","text":"r2"}]'
+            msgs.append('{"role":"tool","tool_call_id":"call_%d","content":%s}' % (r.randint(1, 999), content))
+    top = ['"model":%s' % _jstr(r.choice(["gpt-4o-mini", "anthropic.claude-3-sonnet", "arn:aws:bedrock:us-east-1:123:model/x y", "m"])),
+           '"messages":[' + ("," + sp).join(msgs) + "]"]
+    if r.random() < 0.5:
+        top.append('"temperature":' + _num(r))
+    if r.random() < 0.3:
+        top.append('"top_p":' + _num(r))
+    if r.random() < 0.5:
+        top.append(r.choice(['"max_tokens":256', '"max_completion_tokens":1024', '"max_tokens":10,"max_completion_tokens":20', '"max_tokens":null', '"max_tokens":1.5']))
+    if r.random() < 0.3:
+        top.append(r.choice(['"stop":"END"', '"stop":["a","b"]', '"stop":[]', '"stop":null', '"stop":5']))
+    if r.random() < 0.4:
+        top.append(r.choice(['"stream":true', '"stream":false', '"stream":true,"stream_options":{"include_usage":true}', '"stream":"yes"']))
+    if r.random() < 0.3:
+        tools = []
+        for k in range(r.randint(0, 2)):
+            desc = r.choice(['"description":"does things",', '"description":"",', ""])
+            tools.append('{"type":"function","function":{"name":"fn%d",%s"parameters":%s}}' % (k, desc, _schema(r)))
+        top.append('"tools":[' + ",".join(tools) + "]")
+        if r.random() < 0.6:
+            top.append('"tool_choice":' + r.choice(['"auto"', '"required"', '"none"', '"fn0"', '{"type":"function","function":{"name":"fn0"}}', "null", "7"]))
+    if r.random() < 0.15:
+        top.append(r.choice(['"thinking":{"type":"enabled","budget_tokens":4096}', '"thinking":{"type":"disabled"}', '"thinking":{"type":"adaptive"}', '"thinking":{"type":"bogus"}']))
+    if r.random() < 0.2:
+        top.append(r.choice(['"service_tier":"flex"', '"user":"u-1"', '"n":1', '"seed":42', '"logprobs":true', '"unknown_field":{"a":[1,2,{"b":null}]}', '"response_format":{"type":"json_object"}',
+                             '"presence_penalty":0.5', '"n":"one"', '"parallel_tool_calls":false']))
+    r.shuffle(top)
+    body = "{" + sp + ("," + sp).join(top) + sp + "}"
+    if r.random() < 0.03:
+        body = body[: r.randint(1, len(body) - 1)]  # truncated ⇒ malformed
+    return body.encode("utf-8")
