@@ -92,9 +92,9 @@ enum LitId : int {
       L_COUNT
 };
 
-struct LitTable {
+struct alignas(16) LitTable {
   uint16_t off[L_COUNT + 1];
-  char bytes[1536];
+  alignas(16) char bytes[1536];   // copied to shared memory with 32-bit loads
 };
 constexpr LitTable make_lit_table() {
   LitTable t{};

@@ -38,7 +38,7 @@ static const FieldDef kFields[] = {
 };
 static constexpr int kNumFields = sizeof(kFields) / sizeof(kFields[0]);
 
-struct SchemaBlob {
+struct alignas(16) SchemaBlob {
   Node nodes[N_COUNT];
   Field fields[64];
   char keys[768];
