@@ -19,7 +19,7 @@ assert SseResult.itemsize == 48
 
 EXPORTS = ["aigw_version", "aigw_init", "aigw_destroy", "aigw_last_error", "aigw_device_sm_count", "aigw_host_alloc", "aigw_host_free",
            "aigw_device_alloc", "aigw_device_free", "aigw_memcpy_h2d", "aigw_memcpy_d2h", "aigw_memset_d", "aigw_sync",
-           "aigw_chat_translate_device", "aigw_chat_translate_host", "aigw_sse_usage_device", "aigw_sse_usage_host"]
+           "aigw_chat_translate_device", "aigw_chat_last_profile", "aigw_chat_translate_host", "aigw_sse_usage_device", "aigw_sse_usage_host"]
 
 
 class BackendCfg(C.Structure):
@@ -61,6 +61,7 @@ def load_library():
     L.aigw_sync.argtypes = [C.c_void_p]
     L.aigw_chat_translate_device.argtypes = [C.c_void_p, C.POINTER(BackendCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
                                              C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    L.aigw_chat_last_profile.argtypes = [C.c_void_p, C.POINTER(C.c_float * 3), C.POINTER(C.c_int)]
     L.aigw_chat_translate_host.argtypes = [C.c_void_p, C.POINTER(BackendCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(_BatchOut)]
     L.aigw_sse_usage_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
     L.aigw_sse_usage_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64),
@@ -177,6 +178,12 @@ class Context:
         self._check(self.L.aigw_chat_translate_device(self.h, C.byref(cfg), d_bodies, d_offs, d_lens, n, max_len, d_out, out_cap, d_res, d_used, None,
                                                       C.byref(ms) if timed else None), "chat_translate_device")
         return ms.value
+
+    def chat_last_profile(self):
+        ms = (C.c_float * 3)()
+        nl = C.c_int(0)
+        self.L.aigw_chat_last_profile(self.h, C.byref(ms), C.byref(nl))
+        return {"index_ms": ms[0], "walk_ms": ms[1], "emit_ms": ms[2], "launches": nl.value}
 
     # ---- SSE usage
     def sse_usage_host(self, bytes_arr, chunk_off, chunk_first):

@@ -1,10 +1,19 @@
 // See chat_kernel.cuh for the design.  sm_100a only.
+//
+// v2 layout of the work (driven by profiles/r01_chat_v1.md: 72 % of v1's time was single-lane
+// sequential code at ~22 cycles per instruction):
+//   * tokens carry their byte (tty) and a precomputed key / value id (tkid) that 32 lanes compute in
+//     parallel, so the schema walk compares one byte instead of strings;
+//   * the copy-op under construction lives in registers; shared memory is touched once per finished op;
+//   * the output record is assembled as 16-byte chunks (one chunk per lane, funnel-shifted unaligned
+//     reads from shared memory) and stored straight to the arena — no shared-memory image of the
+//     output, which lifts residency from 12 to 17+ warps per SM.
 #include "chat_kernel.cuh"
 
 namespace aigw {
 
 __device__ __constant__ LitTable c_lits = make_lit_table();
-static constexpr LitTable h_lits = make_lit_table();
+static_assert(make_lit_table().off[L_COUNT] + 8 <= sizeof(LitTable::bytes), "literal table overflow (keep slack for unaligned reads)");
 
 #define FULL 0xffffffffu
 
@@ -16,47 +25,108 @@ __device__ __forceinline__ bool is_ws(uint32_t c) { return c == ' ' || c == '\n'
 __device__ __forceinline__ bool is_op(uint32_t c) { return c == '{' || c == '}' || c == '[' || c == ']' || c == ':' || c == ','; }
 __device__ __forceinline__ bool is_digit(uint32_t c) { return c - '0' < 10u; }
 
+// ------------------------------------------------------------------ key / value ids
+enum Kid : uint8_t {
+  K_NONE = 0,
+  K_model, K_messages, K_max_tokens, K_max_completion_tokens, K_modalities, K_temperature, K_top_p, K_tools, K_tool_choice, K_thinking, K_top_logprobs,
+  K_stop, K_stream, K_stream_options, K_service_tier, K_seed, K_safetySettings, K_frequency_penalty, K_logit_bias, K_logprobs, K_n, K_presence_penalty,
+  K_parallel_tool_calls, K_prediction, K_response_format, K_reasoning_effort, K_verbosity, K_user, K_audio, K_web_search_options, K_generationConfig,
+  K_guided_choice, K_guided_regex, K_guided_json, K_TOP_END,
+  K_role = K_TOP_END, K_content, K_name, K_tool_calls, K_tool_call_id, K_refusal, K_type, K_text, K_cache_control, K_ttl, K_signature, K_redactedContent,
+  K_id, K_function, K_arguments, K_description, K_strict, K_parameters, K_google_search, K_budget_tokens, K_includeThoughts, K_include_usage,
+  K_COUNT
+};
+static_assert(K_TOP_END <= 63, "top-level seen mask is 64 bits");
+enum Vid : uint8_t {
+  V_NONE = 0, V_user, V_assistant, V_system, V_developer, V_tool, V_text, V_refusal, V_thinking, V_redacted_thinking, V_ephemeral,
+  V_enabled, V_disabled, V_adaptive, V_auto, V_required
+};
+
+template <int N>
+__device__ __forceinline__ bool eqn(const uint8_t* p, const char (&lit)[N]) {
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < N - 1; k++) ok &= (p[k] == (uint8_t)lit[k]);
+  return ok;
+}
+#define KMATCH(lit, id) if (eqn(p, lit)) return id;
+__device__ uint32_t key_id(const uint8_t* p, uint32_t n) {
+  switch (n) {
+    case 1: KMATCH("n", K_n) break;
+    case 2: KMATCH("id", K_id) break;
+    case 3: KMATCH("ttl", K_ttl) break;
+    case 4: KMATCH("role", K_role) KMATCH("name", K_name) KMATCH("type", K_type) KMATCH("text", K_text) KMATCH("stop", K_stop) KMATCH("seed", K_seed) KMATCH("user", K_user) break;
+    case 5: KMATCH("model", K_model) KMATCH("tools", K_tools) KMATCH("top_p", K_top_p) KMATCH("audio", K_audio) break;
+    case 6: KMATCH("stream", K_stream) KMATCH("strict", K_strict) break;
+    case 7: KMATCH("content", K_content) KMATCH("refusal", K_refusal) break;
+    case 8: KMATCH("messages", K_messages) KMATCH("thinking", K_thinking) KMATCH("logprobs", K_logprobs) KMATCH("function", K_function) break;
+    case 9: KMATCH("verbosity", K_verbosity) KMATCH("signature", K_signature) KMATCH("arguments", K_arguments) break;
+    case 10: KMATCH("max_tokens", K_max_tokens) KMATCH("modalities", K_modalities) KMATCH("tool_calls", K_tool_calls) KMATCH("logit_bias", K_logit_bias) KMATCH("prediction", K_prediction) KMATCH("parameters", K_parameters) break;
+    case 11: KMATCH("temperature", K_temperature) KMATCH("tool_choice", K_tool_choice) KMATCH("description", K_description) KMATCH("guided_json", K_guided_json) break;
+    case 12: KMATCH("service_tier", K_service_tier) KMATCH("top_logprobs", K_top_logprobs) KMATCH("tool_call_id", K_tool_call_id) KMATCH("guided_regex", K_guided_regex) break;
+    case 13: KMATCH("cache_control", K_cache_control) KMATCH("guided_choice", K_guided_choice) KMATCH("budget_tokens", K_budget_tokens) KMATCH("google_search", K_google_search) KMATCH("include_usage", K_include_usage) break;
+    case 14: KMATCH("stream_options", K_stream_options) KMATCH("safetySettings", K_safetySettings) break;
+    case 15: KMATCH("response_format", K_response_format) KMATCH("redactedContent", K_redactedContent) KMATCH("includeThoughts", K_includeThoughts) break;
+    case 16: KMATCH("presence_penalty", K_presence_penalty) KMATCH("reasoning_effort", K_reasoning_effort) KMATCH("generationConfig", K_generationConfig) break;
+    case 17: KMATCH("frequency_penalty", K_frequency_penalty) break;
+    case 18: KMATCH("web_search_options", K_web_search_options) break;
+    case 19: KMATCH("parallel_tool_calls", K_parallel_tool_calls) break;
+    case 21: KMATCH("max_completion_tokens", K_max_completion_tokens) break;
+    default: break;
+  }
+  return K_NONE;
+}
+__device__ uint32_t val_id(const uint8_t* p, uint32_t n) {
+  switch (n) {
+    case 4: KMATCH("user", V_user) KMATCH("tool", V_tool) KMATCH("text", V_text) KMATCH("auto", V_auto) break;
+    case 6: KMATCH("system", V_system) break;
+    case 7: KMATCH("refusal", V_refusal) KMATCH("enabled", V_enabled) break;
+    case 8: KMATCH("thinking", V_thinking) KMATCH("disabled", V_disabled) KMATCH("adaptive", V_adaptive) KMATCH("required", V_required) break;
+    case 9: KMATCH("assistant", V_assistant) KMATCH("developer", V_developer) KMATCH("ephemeral", V_ephemeral) break;
+    case 17: KMATCH("redacted_thinking", V_redacted_thinking) break;
+    default: break;
+  }
+  return V_NONE;
+}
+#undef KMATCH
+
 // ------------------------------------------------------------------ token view of one JSON text
 struct Doc {
   const uint8_t* s;   // bytes
   uint32_t len;       // valid bytes
   const uint16_t* tok;
   uint16_t* jmp;
+  const uint8_t* ty;  // byte at the token position
+  const uint8_t* id;  // key id (token followed by ':') or value id (other strings); 0 elsewhere
   int nt;
   uint32_t kind;      // op source kind: 0 input, 2 scratch
 
-  __device__ __forceinline__ uint32_t tb(int i) const { return s[tok[i]]; }
   __device__ __forceinline__ int next(int i) const {
-    uint32_t b = tb(i);
+    const uint32_t b = ty[i];
     if (b == '{' || b == '[') return jmp[i] + 1;
     if (b == '"') return i + 2;
     return i + 1;
   }
+  // member / element iteration: after value v, the next key or element (or the closing token)
+  __device__ __forceinline__ int after(int v) const { int nx = next(v); if (ty[nx] == ',') nx++; return nx; }
   __device__ __forceinline__ uint32_t str_off(int i) const { return tok[i] + 1u; }
   __device__ __forceinline__ uint32_t str_len(int i) const { return (uint32_t)tok[i + 1] - tok[i] - 1u; }
-  __device__ bool str_eq(int i, const char* lit, uint32_t n) const {
-    if (str_len(i) != n) return false;
-    const uint8_t* p = s + str_off(i);
-    for (uint32_t k = 0; k < n; k++) if (p[k] != (uint8_t)lit[k]) return false;
-    return true;
-  }
   __device__ bool str_has_backslash(int i) const {
-    const uint8_t* p = s + str_off(i); uint32_t n = str_len(i);
+    const uint8_t* p = s + str_off(i); const uint32_t n = str_len(i);
     for (uint32_t k = 0; k < n; k++) if (p[k] == '\\') return true;
     return false;
   }
   __device__ uint32_t scalar_end(int i) const {
     uint32_t p = tok[i];
-    while (p < len) { uint32_t c = s[p]; if (is_ws(c) || is_op(c) || c == '"') break; p++; }
+    while (p < len) { const uint32_t c = s[p]; if (is_ws(c) || is_op(c) || c == '"') break; p++; }
     return p;
   }
-  __device__ __forceinline__ bool is_null(int i) const { return tb(i) == 'n'; }
 };
 
 // JSON scalar grammar: number | true | false | null
 __device__ bool scalar_valid(const uint8_t* p, uint32_t n) {
   if (n == 0) return false;
-  uint32_t c = p[0];
+  const uint32_t c = p[0];
   if (c == 't') return n == 4 && p[1] == 'r' && p[2] == 'u' && p[3] == 'e';
   if (c == 'f') return n == 5 && p[1] == 'a' && p[2] == 'l' && p[3] == 's' && p[4] == 'e';
   if (c == 'n') return n == 4 && p[1] == 'u' && p[2] == 'l' && p[3] == 'l';
@@ -74,22 +144,21 @@ __device__ bool scalar_valid(const uint8_t* p, uint32_t n) {
   return i == n;
 }
 
-// Stage 3: grammar check + bracket matching over the token list (single lane).
-// Returns 0 ok, else an aigw_reason.
+// Stage 3: grammar check + bracket matching over the token list (single lane).  0 ok, else aigw_reason.
 __device__ int validate_tokens(Doc& d) {
   const int MAXDEPTH = 48;
   uint16_t open_idx[MAXDEPTH];
   uint64_t isobj = 0;
   int depth = 0;
-  // state: 0 value expected, 1 key or '}' , 2 key, 3 ':', 4 ',' or close, 5 value or ']', 6 done
+  // state: 0 value expected, 1 key or '}', 2 key, 3 ':', 4 ',' or close, 5 value or ']', 6 done
   int st = 0;
   int i = 0;
   const int nt = d.nt;
   while (i < nt) {
-    uint32_t b = d.tb(i);
+    const uint32_t b = d.ty[i];
     if (st == 6) return AIGW_R_SYNTAX;
     if (b == '"') {
-      if (i + 1 >= nt || d.tb(i + 1) != '"') return AIGW_R_SYNTAX;
+      if (i + 1 >= nt || d.ty[i + 1] != '"') return AIGW_R_SYNTAX;
       if (st == 1 || st == 2) st = 3;
       else if (st == 0 || st == 5) st = depth ? 4 : 6;
       else return AIGW_R_SYNTAX;
@@ -104,7 +173,7 @@ __device__ int validate_tokens(Doc& d) {
     }
     if (b == '}' || b == ']') {
       if (depth == 0) return AIGW_R_SYNTAX;
-      bool obj = (isobj >> (depth - 1)) & 1;
+      const bool obj = (isobj >> (depth - 1)) & 1;
       if (b == '}') { if (!obj || !(st == 1 || st == 4)) return AIGW_R_SYNTAX; }
       else { if (obj || !(st == 5 || st == 4)) return AIGW_R_SYNTAX; }
       depth--;
@@ -116,9 +185,8 @@ __device__ int validate_tokens(Doc& d) {
       if (st != 4) return AIGW_R_SYNTAX;
       st = ((isobj >> (depth - 1)) & 1) ? 2 : 0; i++; continue;
     }
-    // scalar
     if (!(st == 0 || st == 5)) return AIGW_R_SYNTAX;
-    uint32_t e = d.scalar_end(i);
+    const uint32_t e = d.scalar_end(i);
     if (!scalar_valid(d.s + d.tok[i], e - d.tok[i])) return AIGW_R_SYNTAX;
     st = depth ? 4 : 6; i++;
   }
@@ -127,83 +195,81 @@ __device__ int validate_tokens(Doc& d) {
 
 // ------------------------------------------------------------------ copy-op plan
 // op = kind(2) | len(14) | off(16); kind 0 input bytes, 1 literal table, 2 scratch.
-// Main ops occupy [0, cap); "system" ops (emitted after the messages array) are parked in
-// [cap, cap + kSysCap) and appended once the messages are done.
-static constexpr int kSysCap = 96;
+// The op being extended is held in registers (ckind/coff/clen) and written when the next one starts.
+// "System" ops (emitted after the messages array) are parked in ops[cap .. cap+kSysCap).
 struct Plan {
   uint32_t* ops;
   int nops, nsys, cap;
+  uint32_t ckind, coff, clen;  // clen == 0 ⇒ nothing pending
   uint32_t olen;
-  int err;               // aigw_reason, 0 = fine
+  int err;
 
+  __device__ __forceinline__ void flush() {
+    if (clen) {
+      if (nops >= cap) { err = AIGW_R_OPS; clen = 0; return; }
+      ops[nops++] = (ckind << 30) | (clen << 16) | coff;
+      clen = 0;
+    }
+  }
   __device__ void push(uint32_t kind, uint32_t off, uint32_t len) {
+    olen += len;
+    if (clen && kind == ckind && coff + clen == off && clen + len <= 16383u) { clen += len; return; }
     while (len) {
-      uint32_t l = len < 16383u ? len : 16383u;
-      if (nops > 0) {
-        uint32_t p = ops[nops - 1];
-        uint32_t pl = (p >> 16) & 0x3fffu, po = p & 0xffffu;
-        if ((p >> 30) == kind && po + pl == off && pl + l <= 16383u) {
-          ops[nops - 1] = (kind << 30) | ((pl + l) << 16) | po;
-          olen += l; off += l; len -= l; continue;
-        }
-      }
-      if (nops >= cap) { err = AIGW_R_OPS; return; }
-      ops[nops++] = (kind << 30) | (l << 16) | off;
-      olen += l; off += l; len -= l;
+      flush();
+      const uint32_t l = len < 16383u ? len : 16383u;
+      ckind = kind; coff = off; clen = l;
+      off += l; len -= l;
     }
   }
   __device__ void push_sys(uint32_t kind, uint32_t off, uint32_t len) {
     while (len) {
-      uint32_t l = len < 16383u ? len : 16383u;
+      const uint32_t l = len < 16383u ? len : 16383u;
       if (nsys >= kSysCap) { err = AIGW_R_OPS; return; }
       ops[cap + nsys++] = (kind << 30) | (l << 16) | off;
       off += l; len -= l;
     }
   }
   __device__ __forceinline__ void lit(int id, bool sys = false) {
-    uint32_t o = c_lits.off[id], l = c_lits.off[id + 1] - o;
+    const uint32_t o = c_lits.off[id], l = c_lits.off[id + 1] - o;
     if (sys) push_sys(1, o, l); else push(1, o, l);
   }
   __device__ __forceinline__ void src(const Doc& d, uint32_t off, uint32_t len, bool sys = false) {
     if (sys) push_sys(d.kind, off, len); else push(d.kind, off, len);
   }
   __device__ void flush_sys() {
-    for (int k = 0; k < nsys; k++) { uint32_t p = ops[cap + k]; push(p >> 30, p & 0xffffu, (p >> 16) & 0x3fffu); }
+    for (int k = 0; k < nsys; k++) { const uint32_t p = ops[cap + k]; push(p >> 30, p & 0xffffu, (p >> 16) & 0x3fffu); }
     nsys = 0;
   }
 };
 
-// Scratch bump allocator (per warp)
-struct Scratch {
-  uint8_t* p; uint32_t n, cap;
-};
+struct Scratch { uint8_t* p; uint32_t n, cap; };
 
 // ------------------------------------------------------------------ canonical scalars
 // A JSON number literal that strconv would print back digit-for-digit once trailing fractional
 // zeros are dropped: -?(0|[1-9]\d*)(\.\d+)? , ≤ 15 significant digits, |v| ≥ 1e-6 unless zero.
-// Returns the emitted length (prefix of the literal), 0 when not canonical.
+// Returns the emitted length (a prefix of the literal), 0 when not canonical.
 __device__ uint32_t canon_number(const uint8_t* p, uint32_t n, bool integer_only) {
   uint32_t i = 0;
   bool neg = false;
   if (p[0] == '-') { neg = true; i = 1; }
-  uint32_t int_start = i;
+  const uint32_t int_start = i;
   while (i < n && is_digit(p[i])) i++;
-  uint32_t int_digits = i - int_start;
+  const uint32_t int_digits = i - int_start;
   if (int_digits == 0) return 0;
-  bool int_zero = (int_digits == 1 && p[int_start] == '0');
+  const bool int_zero = (int_digits == 1 && p[int_start] == '0');
   if (i == n) {
     if (integer_only) { if (int_digits > 18) return 0; if (neg && int_zero) return 0; return n; }
     if (int_digits > 15) return 0;
     return n;  // "-0" prints "-0" for a float64
   }
-  if (integer_only || p[i] != '.') return 0;  // exponent form, or fraction where an int is required
-  uint32_t dot = i; i++;
-  uint32_t frac_start = i;
+  if (integer_only || p[i] != '.') return 0;
+  const uint32_t dot = i; i++;
+  const uint32_t frac_start = i;
   while (i < n && is_digit(p[i])) i++;
-  if (i != n) return 0;  // exponent
+  if (i != n) return 0;
   uint32_t fe = n;
   while (fe > frac_start && p[fe - 1] == '0') fe--;
-  uint32_t frac_digits = fe - frac_start;
+  const uint32_t frac_digits = fe - frac_start;
   if (frac_digits == 0) return dot;  // "1.0" → "1", "-0.0" → "-0"
   uint32_t sig;
   if (int_zero) {
@@ -217,25 +283,23 @@ __device__ uint32_t canon_number(const uint8_t* p, uint32_t n, bool integer_only
 
 // ------------------------------------------------------------------ generic canonical re-serialisation
 // Go: decode into interface{} / map[string]any, then marshal ⇒ compact, keys sorted, numbers via float64.
-__device__ int cmp_keys(const Doc& d, int a, int b) {  // key tokens (opening quotes)
-  const uint8_t* pa = d.s + d.str_off(a); uint32_t la = d.str_len(a);
-  const uint8_t* pb = d.s + d.str_off(b); uint32_t lb = d.str_len(b);
-  uint32_t m = la < lb ? la : lb;
+__device__ int cmp_keys(const Doc& d, int a, int b) {
+  const uint8_t* pa = d.s + d.str_off(a); const uint32_t la = d.str_len(a);
+  const uint8_t* pb = d.s + d.str_off(b); const uint32_t lb = d.str_len(b);
+  const uint32_t m = la < lb ? la : lb;
   for (uint32_t k = 0; k < m; k++) { if (pa[k] != pb[k]) return pa[k] < pb[k] ? -1 : 1; }
   return la == lb ? 0 : (la < lb ? -1 : 1);
 }
 
 __device__ void emit_scalar_any(const Doc& d, Plan& pl, int vi, bool sys) {
-  uint32_t c = d.tb(vi);
-  uint32_t e = d.scalar_end(vi), o = d.tok[vi];
+  const uint32_t c = d.ty[vi];
+  const uint32_t e = d.scalar_end(vi), o = d.tok[vi];
   if (c == 't' || c == 'f' || c == 'n') { pl.src(d, o, e - o, sys); return; }
-  uint32_t l = canon_number(d.s + o, e - o, false);
+  const uint32_t l = canon_number(d.s + o, e - o, false);
   if (!l) { pl.err = AIGW_R_NUMBER; return; }
   pl.src(d, o, l, sys);
 }
 
-// Emit value at token `root` canonically (compact, keys sorted, numbers as float64 prints them).
-// Iterative with an explicit frame stack; object members are selected in key order.
 __device__ void emit_any(const Doc& d, Plan& pl, int root, bool sys = false) {
   const int MAXF = 24;
   int f_open[MAXF]; int f_state[MAXF];  // array: current element token; object: last emitted key token (-1 none)
@@ -246,11 +310,11 @@ __device__ void emit_any(const Doc& d, Plan& pl, int root, bool sys = false) {
     if (pl.err) return;
     if (need_value) {
       need_value = false;
-      const uint32_t c = d.tb(vi);
+      const uint32_t c = d.ty[vi];
       if (c == '"') pl.src(d, d.tok[vi], (uint32_t)d.tok[vi + 1] - d.tok[vi] + 1u, sys);
       else if (c == '[') {
         pl.src(d, d.tok[vi], 1, sys);
-        if (d.tb(vi + 1) == ']') pl.src(d, d.tok[vi + 1], 1, sys);
+        if (d.ty[vi + 1] == ']') pl.src(d, d.tok[vi + 1], 1, sys);
         else {
           if (sp >= MAXF) { pl.err = AIGW_R_DEPTH; return; }
           f_open[sp] = vi; f_state[sp] = vi + 1; sp++;
@@ -264,22 +328,19 @@ __device__ void emit_any(const Doc& d, Plan& pl, int root, bool sys = false) {
     }
     if (sp == 0) return;
     const int open = f_open[sp - 1];
-    if (d.tb(open) == '[') {
+    if (d.ty[open] == '[') {
       const int nx = d.next(f_state[sp - 1]);
       pl.src(d, d.tok[nx], 1, sys);  // ',' or ']'
-      if (d.tb(nx) == ',') { f_state[sp - 1] = nx + 1; vi = nx + 1; need_value = true; }
+      if (d.ty[nx] == ',') { f_state[sp - 1] = nx + 1; vi = nx + 1; need_value = true; }
       else sp--;
     } else {
       const int last = f_state[sp - 1];
       int best = -1, cnt = 0;
-      for (int m = open + 1; d.tb(m) != '}';) {
+      for (int m = open + 1; d.ty[m] != '}'; m = d.after(m + 3)) {
         if (d.str_has_backslash(m)) { pl.err = AIGW_R_ESCAPE; return; }
         const int c1 = last < 0 ? 1 : cmp_keys(d, m, last);
         if (c1 == 0 && m != last) { pl.err = AIGW_R_DUP_KEY; return; }
         if (c1 > 0 && (best < 0 || cmp_keys(d, m, best) < 0)) best = m;
-        int nx = d.next(m + 3);
-        if (d.tb(nx) == ',') nx++;
-        m = nx;
         if (++cnt > 64) { pl.err = AIGW_R_UNSUPPORTED_FIELD; return; }
       }
       if (best < 0) { pl.src(d, d.tok[d.jmp[open]], 1, sys); sp--; continue; }
@@ -294,31 +355,31 @@ __device__ void emit_any(const Doc& d, Plan& pl, int root, bool sys = false) {
 }
 
 // Sequential tokenizer for a scratch-resident JSON text (tool-call arguments after unescaping).
-// Returns number of tokens, or -reason.
-__device__ int tokenize_seq(const uint8_t* s, uint32_t len, uint16_t* tok, int cap) {
+// `base` is added to every position.  Returns number of tokens, or -reason.
+__device__ int tokenize_seq(const uint8_t* s, uint32_t len, uint32_t base, uint16_t* tok, uint8_t* ty, int cap) {
   int nt = 0; uint32_t i = 0;
   while (i < len) {
-    uint32_t c = s[i];
+    const uint32_t c = s[i];
     if (is_ws(c)) { i++; continue; }
     if (nt + 2 > cap) return -AIGW_R_TOKENS;
     if (c == '"') {
-      tok[nt++] = (uint16_t)i; i++;
+      tok[nt] = (uint16_t)(base + i); ty[nt++] = '"'; i++;
       for (;;) {
         if (i >= len) return -AIGW_R_SYNTAX;
-        uint32_t ch = s[i];
+        const uint32_t ch = s[i];
         if (ch == '"') break;
         if (ch < 0x20) return -AIGW_R_CTRL_IN_STRING;
         if (ch == '\\') {
           if (i + 1 >= len) return -AIGW_R_SYNTAX;
-          uint32_t e = s[i + 1];
+          const uint32_t e = s[i + 1];
           if (!(e == '"' || e == '\\' || e == 'n' || e == 'r' || e == 't')) return -AIGW_R_ESCAPE;
           i += 2; continue;
         }
         i++;
       }
-      tok[nt++] = (uint16_t)i; i++; continue;
+      tok[nt] = (uint16_t)(base + i); ty[nt++] = '"'; i++; continue;
     }
-    tok[nt++] = (uint16_t)i;
+    tok[nt] = (uint16_t)(base + i); ty[nt++] = (uint8_t)c;
     if (is_op(c)) { i++; continue; }
     while (i < len && !is_ws(s[i]) && !is_op(s[i]) && s[i] != '"') i++;
   }
@@ -330,59 +391,50 @@ struct Walker {
   Doc d;
   Plan pl;
   Scratch sc;
-  uint16_t* tok_tail; int tok_tail_cap;  // free token/jump space for nested documents
-  uint16_t* jmp_tail;
+  uint16_t* tok_tail; uint16_t* jmp_tail; uint8_t* ty_tail; int tail_cap;  // free token space for nested documents
   const ChatParams* P;
-  int reason;  // decline reason
+  int reason;
 
   __device__ __forceinline__ void decline(int r) { if (!reason) reason = r; }
   __device__ __forceinline__ bool bad() const { return reason != 0 || pl.err != 0; }
 
-  // value type helpers (null counts as "absent": zero value)
-  __device__ __forceinline__ bool is_str(int v) const { return d.tb(v) == '"'; }
-  __device__ __forceinline__ bool is_obj(int v) const { return d.tb(v) == '{'; }
-  __device__ __forceinline__ bool is_arr(int v) const { return d.tb(v) == '['; }
-  __device__ __forceinline__ bool is_bool(int v) const { uint32_t c = d.tb(v); return c == 't' || c == 'f'; }
-  __device__ __forceinline__ bool is_num(int v) const { uint32_t c = d.tb(v); return c == '-' || is_digit(c); }
-  __device__ __forceinline__ bool is_null(int v) const { return d.tb(v) == 'n'; }
+  __device__ __forceinline__ bool is_str(int v) const { return d.ty[v] == '"'; }
+  __device__ __forceinline__ bool is_obj(int v) const { return d.ty[v] == '{'; }
+  __device__ __forceinline__ bool is_arr(int v) const { return d.ty[v] == '['; }
+  __device__ __forceinline__ bool is_bool(int v) const { const uint32_t c = d.ty[v]; return c == 't' || c == 'f'; }
+  __device__ __forceinline__ bool is_num(int v) const { const uint32_t c = d.ty[v]; return c == '-' || is_digit(c); }
+  __device__ __forceinline__ bool is_null(int v) const { return d.ty[v] == 'n'; }
 
-  __device__ void emit_str(int v, bool sys = false) { pl.src(d, d.tok[v], (uint32_t)d.tok[v + 1] - d.tok[v] + 1u, sys); }
+  __device__ __forceinline__ void emit_str(int v, bool sys = false) { pl.src(d, d.tok[v], (uint32_t)d.tok[v + 1] - d.tok[v] + 1u, sys); }
 
-  // returns value token or -1; flags duplicates of that key
-  __device__ int find(int obj, const char* key, uint32_t n) {
+  // value token of member `key` in object `obj`, -1 when absent or null; duplicates decline
+  __device__ int find(int obj, uint32_t key) {
     int r = -1;
-    for (int m = obj + 1; d.tb(m) != '}';) {
-      if (d.str_eq(m, key, n)) { if (r >= 0) { decline(AIGW_R_DUP_KEY); return -1; } r = m + 3; }
-      int nx = d.next(m + 3);
-      if (d.tb(nx) == ',') nx++;
-      m = nx;
+    for (int m = obj + 1; d.ty[m] != '}'; m = d.after(m + 3)) {
+      if (d.id[m] == key) { if (r >= 0) { decline(AIGW_R_DUP_KEY); return -1; } r = m + 3; }
     }
     if (r >= 0 && is_null(r)) return -1;
     return r;
   }
   // cache_control: object whose "type" == "ephemeral" (anthropic_helper.go:261-263)
-  __device__ bool cache_enabled(int obj) {
-    int cc = find(obj, "cache_control", 13);
+  __device__ bool cache_enabled(int cc) {
     if (cc < 0) return false;
     if (!is_obj(cc)) { decline(AIGW_R_TYPE); return false; }
-    int t = find(cc, "type", 4);
-    int ttl = find(cc, "ttl", 3);
-    if (ttl >= 0 && !is_str(ttl)) { decline(AIGW_R_TYPE); return false; }
-    if (t < 0) return false;
+    int t = -1, ttl = -1;
+    for (int m = cc + 1; d.ty[m] != '}'; m = d.after(m + 3)) {
+      const uint32_t k = d.id[m];
+      if (k == K_type) { if (t >= 0) { decline(AIGW_R_DUP_KEY); return false; } t = m + 3; }
+      else if (k == K_ttl) { if (ttl >= 0) { decline(AIGW_R_DUP_KEY); return false; } ttl = m + 3; }
+    }
+    if (ttl >= 0 && !is_null(ttl) && !is_str(ttl)) { decline(AIGW_R_TYPE); return false; }
+    if (t < 0 || is_null(t)) return false;
     if (!is_str(t)) { decline(AIGW_R_TYPE); return false; }
-    return d.str_eq(t, "ephemeral", 9);
+    return d.id[t] == V_ephemeral;
   }
-  __device__ void emit_int_field(int v) {
-    uint32_t e = d.scalar_end(v), o = d.tok[v];
+  __device__ void emit_num_field(int v, bool integer) {
+    const uint32_t e = d.scalar_end(v), o = d.tok[v];
     if (!is_num(v)) { decline(AIGW_R_TYPE); return; }
-    uint32_t l = canon_number(d.s + o, e - o, true);
-    if (!l) { decline(AIGW_R_NUMBER); return; }
-    pl.src(d, o, l);
-  }
-  __device__ void emit_float_field(int v) {
-    uint32_t e = d.scalar_end(v), o = d.tok[v];
-    if (!is_num(v)) { decline(AIGW_R_TYPE); return; }
-    uint32_t l = canon_number(d.s + o, e - o, false);
+    const uint32_t l = canon_number(d.s + o, e - o, integer);
     if (!l) { decline(AIGW_R_NUMBER); return; }
     pl.src(d, o, l);
   }
@@ -393,27 +445,43 @@ struct Walker {
     else if (kind == 1) ok = is_bool(v);
     else {
       ok = is_num(v);
-      if (ok && kind == 2) { uint32_t e = d.scalar_end(v), o = d.tok[v]; ok = canon_number(d.s + o, e - o, true) != 0; if (!ok) { decline(AIGW_R_NUMBER); return false; } }
+      if (ok && kind == 2) { const uint32_t e = d.scalar_end(v), o = d.tok[v]; ok = canon_number(d.s + o, e - o, true) != 0; if (!ok) { decline(AIGW_R_NUMBER); return false; } }
     }
     if (!ok) decline(AIGW_R_TYPE);
     return ok;
   }
 
-  // text part list for system / developer / tool messages: [{"text":…,"type":…,"cache_control":…}]
-  // emits {"text":S}[,{"cachePoint":…}] per element (cache only when with_cache)
+  // one {"type":…,"text":…,"cache_control":…} element: fields by id in one pass (null ⇒ absent)
+  struct Part { int type, text, cache, refusal, signature, redacted; };
+  __device__ bool scan_part(int e, Part& p) {
+    p.type = p.text = p.cache = p.refusal = p.signature = p.redacted = -1;
+    uint32_t seen = 0;
+    for (int m = e + 1; d.ty[m] != '}'; m = d.after(m + 3)) {
+      int slot;
+      switch (d.id[m]) { case K_type: slot = 0; break; case K_text: slot = 1; break; case K_cache_control: slot = 2; break; case K_refusal: slot = 3; break;
+        case K_signature: slot = 4; break; case K_redactedContent: slot = 5; break; default: slot = -1; }
+      if (slot < 0) continue;
+      if (seen & (1u << slot)) { decline(AIGW_R_DUP_KEY); return false; }
+      seen |= 1u << slot;
+      const int v = is_null(m + 3) ? -1 : m + 3;
+      switch (slot) { case 0: p.type = v; break; case 1: p.text = v; break; case 2: p.cache = v; break; case 3: p.refusal = v; break; case 4: p.signature = v; break; case 5: p.redacted = v; break; }
+    }
+    return true;
+  }
+
+  // text part list for system / developer / tool messages (ChatCompletionContentPartTextParam)
   __device__ void emit_text_parts(int arr, bool with_cache, bool sys, bool& first) {
-    for (int e = arr + 1; d.tb(e) != ']';) {
+    for (int e = arr + 1; d.ty[e] != ']'; e = d.after(e)) {
       if (!is_obj(e)) { decline(AIGW_R_CONTENT); return; }
-      int t = find(e, "text", 4), ty = find(e, "type", 4);
-      if ((t >= 0 && !is_str(t)) || (ty >= 0 && !is_str(ty))) { decline(AIGW_R_TYPE); return; }
-      bool cache = cache_enabled(e);
+      Part p; if (!scan_part(e, p)) return;
+      if ((p.text >= 0 && !is_str(p.text)) || (p.type >= 0 && !is_str(p.type))) { decline(AIGW_R_TYPE); return; }
+      const bool cache = cache_enabled(p.cache);
       if (bad()) return;
       if (!first) pl.lit(L_COMMA, sys); first = false;
       pl.lit(L_TEXT_OPEN, sys);
-      if (t >= 0) emit_str(t, sys); else pl.lit(L_EMPTY_STR, sys);
+      if (p.text >= 0) emit_str(p.text, sys); else pl.lit(L_EMPTY_STR, sys);
       pl.lit(L_RBRACE, sys);
       if (with_cache && cache) { pl.lit(L_COMMA, sys); pl.lit(L_CACHEPOINT, sys); }
-      int nx = d.next(e); if (d.tb(nx) == ',') nx++; e = nx;
     }
   }
 
@@ -423,30 +491,19 @@ struct Walker {
     g.role_v = g.content = g.name = g.tool_calls = g.tool_call_id = g.refusal = g.audio = -1;
     if (!is_obj(m)) { decline(AIGW_R_ROLE); return -1; }
     uint32_t seen = 0;
-    for (int k = m + 1; d.tb(k) != '}';) {
-      int v = k + 3;
-      uint32_t n = d.str_len(k);
-      int which = -1;
-      if (n == 4) { if (d.str_eq(k, "role", 4)) which = 0; else if (d.str_eq(k, "name", 4)) which = 2; }
-      else if (n == 7) { if (d.str_eq(k, "content", 7)) which = 1; else if (d.str_eq(k, "refusal", 7)) which = 5; }
-      else if (n == 10) { if (d.str_eq(k, "tool_calls", 10)) which = 3; }
-      else if (n == 12) { if (d.str_eq(k, "tool_call_id", 12)) which = 4; }
-      else if (n == 5) { if (d.str_eq(k, "audio", 5)) which = 6; }
-      if (which >= 0) {
-        if (seen & (1u << which)) { decline(AIGW_R_DUP_KEY); return -1; }
-        seen |= 1u << which;
-        switch (which) { case 0: g.role_v = v; break; case 1: g.content = v; break; case 2: g.name = v; break; case 3: g.tool_calls = v; break;
-          case 4: g.tool_call_id = v; break; case 5: g.refusal = v; break; case 6: g.audio = v; break; }
-      }
-      int nx = d.next(v); if (d.tb(nx) == ',') nx++; k = nx;
+    for (int k = m + 1; d.ty[k] != '}'; k = d.after(k + 3)) {
+      const int v = k + 3;
+      int which;
+      switch (d.id[k]) { case K_role: which = 0; break; case K_content: which = 1; break; case K_name: which = 2; break; case K_tool_calls: which = 3; break;
+        case K_tool_call_id: which = 4; break; case K_refusal: which = 5; break; case K_audio: which = 6; break; default: which = -1; }
+      if (which < 0) continue;
+      if (seen & (1u << which)) { decline(AIGW_R_DUP_KEY); return -1; }
+      seen |= 1u << which;
+      switch (which) { case 0: g.role_v = v; break; case 1: g.content = v; break; case 2: g.name = v; break; case 3: g.tool_calls = v; break;
+        case 4: g.tool_call_id = v; break; case 5: g.refusal = v; break; case 6: g.audio = v; break; }
     }
     if (g.role_v < 0 || !is_str(g.role_v)) { decline(AIGW_R_ROLE); return -1; }
-    int r = g.role_v;
-    if (d.str_eq(r, "user", 4)) return 0;
-    if (d.str_eq(r, "assistant", 9)) return 1;
-    if (d.str_eq(r, "system", 6)) return 2;
-    if (d.str_eq(r, "developer", 9)) return 3;
-    if (d.str_eq(r, "tool", 4)) return 4;
+    switch (d.id[g.role_v]) { case V_user: return 0; case V_assistant: return 1; case V_system: return 2; case V_developer: return 3; case V_tool: return 4; default: break; }
     decline(AIGW_R_ROLE); return -1;
   }
 
@@ -466,25 +523,21 @@ struct Walker {
 
   // ---- tool call arguments: JSON text inside a JSON string → map[string]any → marshal
   __device__ void emit_arguments(int v) {
-    // unescape into scratch
-    uint32_t off = d.str_off(v), n = d.str_len(v);
-    if (sc.n + n + 1 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
+    const uint32_t off = d.str_off(v), n = d.str_len(v);
+    if (sc.n + n + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
     uint8_t* dst = sc.p + sc.n; uint32_t w = 0;
     const uint8_t* p = d.s + off;
     for (uint32_t i = 0; i < n; i++) {
       uint32_t c = p[i];
-      if (c == '\\') { uint32_t e = p[++i]; c = e == 'n' ? '\n' : e == 'r' ? '\r' : e == 't' ? '\t' : e; }
+      if (c == '\\') { const uint32_t e = p[++i]; c = e == 'n' ? '\n' : e == 'r' ? '\r' : e == 't' ? '\t' : e; }
       dst[w++] = (uint8_t)c;
     }
-    uint32_t base = sc.n; sc.n += (w + 1u) & ~1u;
-    int nt = tokenize_seq(dst, w, tok_tail, tok_tail_cap);
+    const uint32_t base = sc.n; sc.n += (w + 1u) & ~1u;
+    const int nt = tokenize_seq(dst, w, base, tok_tail, ty_tail, tail_cap);
     if (nt <= 0) { decline(nt == 0 ? AIGW_R_ARGS : -nt); return; }
-    Doc a; a.s = sc.p; a.len = base + w; a.tok = tok_tail; a.jmp = jmp_tail; a.nt = nt; a.kind = 2;
-    // token positions are relative to dst: rebase to scratch origin
-    for (int i = 0; i < nt; i++) tok_tail[i] = (uint16_t)(tok_tail[i] + base);
-    int r = validate_tokens(a);
-    if (r) { decline(AIGW_R_ARGS); return; }
-    uint32_t c0 = a.tb(0);
+    Doc a; a.s = sc.p; a.len = base + w; a.tok = tok_tail; a.jmp = jmp_tail; a.ty = ty_tail; a.id = ty_tail; a.nt = nt; a.kind = 2;
+    if (validate_tokens(a)) { decline(AIGW_R_ARGS); return; }
+    const uint32_t c0 = a.ty[0];
     if (c0 == 'n') { pl.lit(L_NULL); return; }
     if (c0 != '{') { decline(AIGW_R_ARGS); return; }
     emit_any(a, pl, 0);
@@ -493,51 +546,52 @@ struct Walker {
   // ---- Bedrock assistant content blocks (openai_awsbedrock.go:309-419)
   __device__ void bedrock_asst_part(int e, bool& first) {
     if (!is_obj(e)) { decline(AIGW_R_CONTENT); return; }
-    int ty = find(e, "type", 4), text = find(e, "text", 4), refusal = find(e, "refusal", 7), sig = find(e, "signature", 9), red = find(e, "redactedContent", 15);
-    if ((ty >= 0 && !is_str(ty)) || (text >= 0 && !is_str(text)) || (refusal >= 0 && !is_str(refusal)) || (sig >= 0 && !is_str(sig))) { decline(AIGW_R_TYPE); return; }
-    if (red >= 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-    bool cache = cache_enabled(e);
+    Part p; if (!scan_part(e, p)) return;
+    if ((p.type >= 0 && !is_str(p.type)) || (p.text >= 0 && !is_str(p.text)) || (p.refusal >= 0 && !is_str(p.refusal)) || (p.signature >= 0 && !is_str(p.signature))) { decline(AIGW_R_TYPE); return; }
+    if (p.redacted >= 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+    const bool cache = cache_enabled(p.cache);
     if (bad()) return;
-    if (ty < 0) return;  // type "" matches no case
+    if (p.type < 0) return;  // type "" matches no case
     bool emitted = false;
-    if (d.str_eq(ty, "text", 4)) { if (text >= 0) { if (!first) pl.lit(L_COMMA); first = false; pl.lit(L_TEXT_OPEN); emit_str(text); pl.lit(L_RBRACE); emitted = true; } }
-    else if (d.str_eq(ty, "refusal", 7)) { if (refusal >= 0) { if (!first) pl.lit(L_COMMA); first = false; pl.lit(L_TEXT_OPEN); emit_str(refusal); pl.lit(L_RBRACE); emitted = true; } }
-    else if (d.str_eq(ty, "thinking", 8)) {
-      if (text >= 0) {
+    const uint32_t ty = d.id[p.type];
+    if (ty == V_text) { if (p.text >= 0) { if (!first) pl.lit(L_COMMA); first = false; pl.lit(L_TEXT_OPEN); emit_str(p.text); pl.lit(L_RBRACE); emitted = true; } }
+    else if (ty == V_refusal) { if (p.refusal >= 0) { if (!first) pl.lit(L_COMMA); first = false; pl.lit(L_TEXT_OPEN); emit_str(p.refusal); pl.lit(L_RBRACE); emitted = true; } }
+    else if (ty == V_thinking) {
+      if (p.text >= 0) {
         if (!first) pl.lit(L_COMMA); first = false;
-        pl.lit(L_REASON_OPEN); emit_str(text);
-        if (sig >= 0 && d.str_len(sig) > 0) { pl.lit(L_REASON_SIG); emit_str(sig); }
+        pl.lit(L_REASON_OPEN); emit_str(p.text);
+        if (p.signature >= 0 && d.str_len(p.signature) > 0) { pl.lit(L_REASON_SIG); emit_str(p.signature); }
         pl.lit(L_REASON_CLOSE); emitted = true;
       }
-    } else if (d.str_eq(ty, "redacted_thinking", 17)) { /* RedactedContent nil ⇒ nothing */ }
+    }
     if (emitted && cache) { pl.lit(L_COMMA); pl.lit(L_CACHEPOINT); }
   }
 
   __device__ void bedrock_assistant(const Msg& g) {
     pl.lit(L_MSG_CONTENT_OPEN);
     bool first = true;
-    int c = g.content;
+    const int c = g.content;
     if (c >= 0 && !is_null(c)) {
       if (is_str(c)) { if (d.str_len(c) > 0) { pl.lit(L_TEXT_OPEN); emit_str(c); pl.lit(L_RBRACE); first = false; } }
-      else if (is_arr(c)) { for (int e = c + 1; d.tb(e) != ']';) { bedrock_asst_part(e, first); if (bad()) return; int nx = d.next(e); if (d.tb(nx) == ',') nx++; e = nx; } }
+      else if (is_arr(c)) { for (int e = c + 1; d.ty[e] != ']'; e = d.after(e)) { bedrock_asst_part(e, first); if (bad()) return; } }
       else if (is_obj(c)) bedrock_asst_part(c, first);
       else { decline(AIGW_R_CONTENT); return; }
     }
     if (g.audio >= 0 && !is_null(g.audio)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
     if (g.name >= 0 && !is_null(g.name) && !is_str(g.name)) { decline(AIGW_R_TYPE); return; }
     if (g.refusal >= 0 && !is_null(g.refusal) && !is_str(g.refusal)) { decline(AIGW_R_TYPE); return; }
-    int tcs = g.tool_calls;
+    const int tcs = g.tool_calls;
     if (tcs >= 0 && !is_null(tcs)) {
       if (!is_arr(tcs)) { decline(AIGW_R_TYPE); return; }
-      for (int e = tcs + 1; d.tb(e) != ']';) {
+      for (int e = tcs + 1; d.ty[e] != ']'; e = d.after(e)) {
         if (!is_obj(e)) { decline(AIGW_R_TOOL); return; }
-        int id = find(e, "id", 2), fn = find(e, "function", 8), ty = find(e, "type", 4);
-        (void)cache_enabled(e);
+        const int id = find(e, K_id), fn = find(e, K_function), ty = find(e, K_type);
+        (void)cache_enabled(find(e, K_cache_control));
         if (bad()) return;
         if (id < 0 || !is_str(id)) { decline(AIGW_R_TOOL); return; }  // nil id panics in the reference
         if (ty >= 0 && !is_str(ty)) { decline(AIGW_R_TYPE); return; }
         int name = -1, args = -1;
-        if (fn >= 0) { if (!is_obj(fn)) { decline(AIGW_R_TYPE); return; } name = find(fn, "name", 4); args = find(fn, "arguments", 9); }
+        if (fn >= 0) { if (!is_obj(fn)) { decline(AIGW_R_TYPE); return; } name = find(fn, K_name); args = find(fn, K_arguments); }
         if (bad()) return;
         if ((name >= 0 && !is_str(name)) || (args >= 0 && !is_str(args))) { decline(AIGW_R_TYPE); return; }
         if (args < 0) { decline(AIGW_R_ARGS); return; }  // "" fails to unmarshal in the reference
@@ -549,14 +603,13 @@ struct Walker {
         if (bad()) return;
         pl.lit(L_TOOLUSE_ID); emit_str(id);
         pl.lit(L_TOOLRESULT_CLOSE);
-        int nx = d.next(e); if (d.tb(nx) == ',') nx++; e = nx;
       }
     }
     pl.lit(L_ASST_CLOSE);
   }
 
   __device__ void bedrock_user(const Msg& g) {
-    int c = g.content;
+    const int c = g.content;
     if (g.name >= 0 && !is_null(g.name) && !is_str(g.name)) { decline(AIGW_R_TYPE); return; }
     if (c < 0) { decline(AIGW_R_CONTENT); return; }  // absent ⇒ 422
     if (is_null(c)) { pl.lit(L_MSG_TEXT_OPEN); pl.lit(L_EMPTY_STR); pl.lit(L_USER_CLOSE1); return; }
@@ -564,24 +617,22 @@ struct Walker {
     if (!is_arr(c)) { decline(AIGW_R_CONTENT); return; }
     pl.lit(L_MSG_CONTENT_OPEN);
     bool first = true;
-    for (int e = c + 1; d.tb(e) != ']';) {
+    for (int e = c + 1; d.ty[e] != ']'; e = d.after(e)) {
       if (!is_obj(e)) { decline(AIGW_R_CONTENT); return; }
-      int ty = find(e, "type", 4);
-      if (ty < 0 || !is_str(ty) || !d.str_eq(ty, "text", 4)) { decline(AIGW_R_CONTENT); return; }  // images/audio/files: stock path
-      int text = find(e, "text", 4);
-      if (text >= 0 && !is_str(text)) { decline(AIGW_R_TYPE); return; }
-      bool cache = cache_enabled(e);
+      Part p; if (!scan_part(e, p)) return;
+      if (p.type < 0 || !is_str(p.type) || d.id[p.type] != V_text) { decline(AIGW_R_CONTENT); return; }  // images/audio/files: stock path
+      if (p.text >= 0 && !is_str(p.text)) { decline(AIGW_R_TYPE); return; }
+      const bool cache = cache_enabled(p.cache);
       if (bad()) return;
       if (!first) pl.lit(L_COMMA); first = false;
-      pl.lit(L_TEXT_OPEN); if (text >= 0) emit_str(text); else pl.lit(L_EMPTY_STR); pl.lit(L_RBRACE);
+      pl.lit(L_TEXT_OPEN); if (p.text >= 0) emit_str(p.text); else pl.lit(L_EMPTY_STR); pl.lit(L_RBRACE);
       if (cache) { pl.lit(L_COMMA); pl.lit(L_CACHEPOINT); }
-      int nx = d.next(e); if (d.tb(nx) == ',') nx++; e = nx;
     }
     pl.lit(L_USER_CLOSE);
   }
 
   __device__ void bedrock_system(const Msg& g, bool& sys_first) {
-    int c = g.content;
+    const int c = g.content;
     if (g.name >= 0 && !is_null(g.name) && !is_str(g.name)) { decline(AIGW_R_TYPE); return; }
     if (c < 0) { decline(AIGW_R_CONTENT); return; }
     if (is_str(c)) { if (!sys_first) pl.lit(L_COMMA, true); sys_first = false; pl.lit(L_TEXT_OPEN, true); emit_str(c, true); pl.lit(L_RBRACE, true); }
@@ -596,48 +647,26 @@ struct Walker {
     t.model = t.messages = t.temperature = t.top_p = t.max_tokens = t.mct = t.stop = t.stream = t.stream_options = t.tools = t.tool_choice = t.thinking = t.service_tier = -1;
     if (d.nt == 0 || !is_obj(0)) { decline(AIGW_R_ROOT); return false; }
     uint64_t seen = 0;
-    for (int k = 1; d.tb(k) != '}';) {
-      int v = k + 3;
-      uint32_t n = d.str_len(k);
-      const uint8_t* kp = d.s + d.str_off(k);
-      int id = -1;  // index into the table below
-      // kinds: 0 str, 1 bool, 2 int, 3 float, 8 handled, 9 unsupported-when-present, 10 any
-      #define KEY(lit, ident, kindv) if (id < 0 && n == sizeof(lit) - 1 && d.str_eq(k, lit, sizeof(lit) - 1)) { id = ident; kind = kindv; }
-      int kind = -1;
-      uint32_t c0 = n ? kp[0] : 0;
-      switch (c0) {
-        case 'm': KEY("model", 0, 8) KEY("messages", 1, 8) KEY("max_tokens", 2, 8) KEY("max_completion_tokens", 3, 8) KEY("modalities", 20, 9) break;
-        case 't': KEY("temperature", 4, 8) KEY("top_p", 5, 8) KEY("tools", 6, 8) KEY("tool_choice", 7, 8) KEY("thinking", 8, 8) KEY("top_logprobs", 21, 2) break;
-        case 's': KEY("stop", 9, 8) KEY("stream", 10, 8) KEY("stream_options", 11, 8) KEY("service_tier", 12, 8) KEY("seed", 22, 2) KEY("safetySettings", 23, 9) break;
-        case 'f': KEY("frequency_penalty", 24, 3) break;
-        case 'l': KEY("logit_bias", 25, 9) KEY("logprobs", 26, 1) break;
-        case 'n': KEY("n", 27, 2) break;
-        case 'p': KEY("presence_penalty", 28, 3) KEY("parallel_tool_calls", 29, 1) KEY("prediction", 30, 9) break;
-        case 'r': KEY("response_format", 31, 9) KEY("reasoning_effort", 32, 0) break;
-        case 'v': KEY("verbosity", 33, 0) break;
-        case 'u': KEY("user", 34, 0) break;
-        case 'a': KEY("audio", 35, 9) break;
-        case 'w': KEY("web_search_options", 36, 9) break;
-        case 'g': KEY("generationConfig", 37, 9) KEY("guided_choice", 38, 9) KEY("guided_regex", 39, 0) KEY("guided_json", 40, 10) break;
-        default: break;
+    for (int k = 1; d.ty[k] != '}'; k = d.after(k + 3)) {
+      const int v = k + 3;
+      const uint32_t id = d.id[k];
+      if (id == K_NONE || id >= K_TOP_END) continue;
+      if (seen & (1ull << id)) { decline(AIGW_R_DUP_KEY); return false; }
+      seen |= 1ull << id;
+      if (is_null(v)) continue;
+      switch (id) {
+        case K_model: t.model = v; break; case K_messages: t.messages = v; break; case K_max_tokens: t.max_tokens = v; break; case K_max_completion_tokens: t.mct = v; break;
+        case K_temperature: t.temperature = v; break; case K_top_p: t.top_p = v; break; case K_tools: t.tools = v; break; case K_tool_choice: t.tool_choice = v; break;
+        case K_thinking: t.thinking = v; break; case K_stop: t.stop = v; break; case K_stream: t.stream = v; break; case K_stream_options: t.stream_options = v; break;
+        case K_service_tier: t.service_tier = v; break;
+        case K_reasoning_effort: case K_verbosity: case K_user: case K_guided_regex: if (!check_scalar_type(v, 0)) return false; break;
+        case K_logprobs: case K_parallel_tool_calls: if (!check_scalar_type(v, 1)) return false; break;
+        case K_top_logprobs: case K_seed: case K_n: if (!check_scalar_type(v, 2)) return false; break;
+        case K_frequency_penalty: case K_presence_penalty: if (!check_scalar_type(v, 3)) return false; break;
+        case K_guided_json: break;  // json.RawMessage: anything
+        default: decline(AIGW_R_UNSUPPORTED_FIELD); return false;  // modalities, audio, prediction, response_format, logit_bias, …: stock path
       }
-      #undef KEY
-      if (id >= 0) {
-        if (seen & (1ull << id)) { decline(AIGW_R_DUP_KEY); return false; }
-        seen |= 1ull << id;
-        if (!is_null(v)) {
-          if (kind == 9) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
-          if (kind >= 0 && kind <= 3) { if (!check_scalar_type(v, kind)) return false; }
-          if (kind == 8) switch (id) {
-            case 0: t.model = v; break; case 1: t.messages = v; break; case 2: t.max_tokens = v; break; case 3: t.mct = v; break;
-            case 4: t.temperature = v; break; case 5: t.top_p = v; break; case 6: t.tools = v; break; case 7: t.tool_choice = v; break;
-            case 8: t.thinking = v; break; case 9: t.stop = v; break; case 10: t.stream = v; break; case 11: t.stream_options = v; break; case 12: t.service_tier = v; break;
-          }
-        }
-      }
-      int nx = d.next(v); if (d.tb(nx) == ',') nx++; k = nx;
     }
-    // types of the handled fields
     if (t.model >= 0 && (!is_str(t.model) || d.str_has_backslash(t.model))) { decline(is_str(t.model) ? AIGW_R_ESCAPE : AIGW_R_TYPE); return false; }
     if (t.messages >= 0 && !is_arr(t.messages)) { decline(AIGW_R_TYPE); return false; }
     if (t.stream >= 0 && !is_bool(t.stream)) { decline(AIGW_R_TYPE); return false; }
@@ -645,7 +674,7 @@ struct Walker {
     if (t.tools >= 0 && !is_arr(t.tools)) { decline(AIGW_R_TYPE); return false; }
     if (t.stream_options >= 0) {
       if (!is_obj(t.stream_options)) { decline(AIGW_R_TYPE); return false; }
-      int iu = find(t.stream_options, "include_usage", 13);
+      const int iu = find(t.stream_options, K_include_usage);
       if (iu >= 0 && !is_bool(iu)) { decline(AIGW_R_TYPE); return false; }
     }
     if (t.temperature >= 0 && !is_num(t.temperature)) { decline(AIGW_R_TYPE); return false; }
@@ -657,7 +686,7 @@ struct Walker {
 
   __device__ bool model_contains(int mv, const char* needle, uint32_t n) {
     if (mv < 0) return false;
-    const uint8_t* p = d.s + d.str_off(mv); uint32_t L = d.str_len(mv);
+    const uint8_t* p = d.s + d.str_off(mv); const uint32_t L = d.str_len(mv);
     for (uint32_t i = 0; i + n <= L; i++) { uint32_t k = 0; while (k < n && p[i + k] == (uint8_t)needle[k]) k++; if (k == n) return true; }
     return false;
   }
@@ -671,17 +700,17 @@ struct Walker {
     else { mp = nullptr; ml = 0; }
     bool clean = true;
     for (uint32_t i = 0; i < ml; i++) {
-      uint32_t c = mp[i];
-      bool keep = (c - 'a' < 26u) || (c - 'A' < 26u) || (c - '0' < 10u) || c == '-' || c == '_' || c == '.' || c == '~' || c == '$' || c == '&' || c == '+' || c == ':' || c == '=' || c == '@';
+      const uint32_t c = mp[i];
+      const bool keep = (c - 'a' < 26u) || (c - 'A' < 26u) || (c - '0' < 10u) || c == '-' || c == '_' || c == '.' || c == '~' || c == '$' || c == '&' || c == '+' || c == ':' || c == '=' || c == '@';
       if (!keep) { clean = false; break; }
     }
     if (clean && !P->override_len) { if (ml) pl.src(d, d.str_off(t.model), ml); }
     else {
-      if (sc.n + 3 * ml > sc.cap) { decline(AIGW_R_SCRATCH); return; }
+      if (sc.n + 3 * ml + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
       uint8_t* o = sc.p + sc.n; uint32_t w = 0;
       for (uint32_t i = 0; i < ml; i++) {
-        uint32_t c = mp[i];
-        bool keep = (c - 'a' < 26u) || (c - 'A' < 26u) || (c - '0' < 10u) || c == '-' || c == '_' || c == '.' || c == '~' || c == '$' || c == '&' || c == '+' || c == ':' || c == '=' || c == '@';
+        const uint32_t c = mp[i];
+        const bool keep = (c - 'a' < 26u) || (c - 'A' < 26u) || (c - '0' < 10u) || c == '-' || c == '_' || c == '.' || c == '~' || c == '$' || c == '&' || c == '+' || c == ':' || c == '=' || c == '@';
         if (keep) o[w++] = (uint8_t)c;
         else { const char* hx = "0123456789ABCDEF"; o[w++] = '%'; o[w++] = hx[c >> 4]; o[w++] = hx[c & 15]; }
       }
@@ -698,49 +727,50 @@ struct Walker {
     if (bad()) return;
     pl.lit(L_LBRACE);
     if (t.thinking >= 0) {  // openai.go:911-945, openai_awsbedrock.go:57-78
-      int th = t.thinking;
+      const int th = t.thinking;
       if (!is_obj(th)) { decline(AIGW_R_TYPE); return; }
-      int ty = find(th, "type", 4);
+      const int ty = find(th, K_type);
       if (ty < 0 || !is_str(ty)) { decline(AIGW_R_TYPE); return; }
-      if (d.str_eq(ty, "enabled", 7)) {
-        int bt = find(th, "budget_tokens", 13), it = find(th, "includeThoughts", 15);
+      const uint32_t tv = d.id[ty];
+      if (tv == V_enabled) {
+        const int bt = find(th, K_budget_tokens), it = find(th, K_includeThoughts);
         if (it >= 0 && !is_bool(it)) { decline(AIGW_R_TYPE); return; }
         pl.lit(L_ADDL_EN_PRE);
-        if (bt >= 0) emit_int_field(bt); else pl.lit(L_ZERO);
+        if (bt >= 0) emit_num_field(bt, true); else pl.lit(L_ZERO);
         pl.lit(L_ADDL_EN_POST);
-      } else if (d.str_eq(ty, "disabled", 8)) pl.lit(L_ADDL_DIS);
-      else if (d.str_eq(ty, "adaptive", 8)) {}
+      } else if (tv == V_disabled) pl.lit(L_ADDL_DIS);
+      else if (tv == V_adaptive) {}
       else { decline(AIGW_R_TYPE); return; }
       if (bad()) return;
     }
     pl.lit(L_INF_OPEN);
     bool f = true;
-    int mt = t.mct >= 0 ? t.mct : t.max_tokens;  // cmp.Or(MaxCompletionTokens, MaxTokens)
-    if (mt >= 0) { pl.lit(L_MAXTOK); emit_int_field(mt); f = false; }
+    const int mt = t.mct >= 0 ? t.mct : t.max_tokens;  // cmp.Or(MaxCompletionTokens, MaxTokens)
+    if (mt >= 0) { pl.lit(L_MAXTOK); emit_num_field(mt, true); f = false; }
     if (t.stop >= 0) {
-      int s = t.stop;
+      const int s = t.stop;
       if (is_str(s)) { if (!f) pl.lit(L_COMMA); f = false; pl.lit(L_STOPSEQ); emit_str(s); pl.lit(L_RBRACK); }
       else if (is_arr(s)) {
-        if (d.tb(s + 1) != ']') {
+        if (d.ty[s + 1] != ']') {
           if (!f) pl.lit(L_COMMA); f = false; pl.lit(L_STOPSEQ);
           bool sf = true;
-          for (int e = s + 1; d.tb(e) != ']';) { if (!is_str(e)) { decline(AIGW_R_TYPE); return; } if (!sf) pl.lit(L_COMMA); sf = false; emit_str(e); int nx = d.next(e); if (d.tb(nx) == ',') nx++; e = nx; }
+          for (int e = s + 1; d.ty[e] != ']'; e = d.after(e)) { if (!is_str(e)) { decline(AIGW_R_TYPE); return; } if (!sf) pl.lit(L_COMMA); sf = false; emit_str(e); }
           pl.lit(L_RBRACK);
         }
       } else { decline(AIGW_R_TYPE); return; }
     }
-    if (t.temperature >= 0) { if (!f) pl.lit(L_COMMA); f = false; pl.lit(L_TEMP); emit_float_field(t.temperature); }
-    if (t.top_p >= 0) { if (!f) pl.lit(L_COMMA); f = false; pl.lit(L_TOPP); emit_float_field(t.top_p); }
+    if (t.temperature >= 0) { if (!f) pl.lit(L_COMMA); f = false; pl.lit(L_TEMP); emit_num_field(t.temperature, false); }
+    if (t.top_p >= 0) { if (!f) pl.lit(L_COMMA); f = false; pl.lit(L_TOPP); emit_num_field(t.top_p, false); }
     pl.lit(L_INF_CLOSE_MSGS);
     if (bad()) return;
     // messages (openai_awsbedrock.go:489-585)
     bool mfirst = true, sys_first = true;
     if (t.messages >= 0) {
       int e = t.messages + 1;
-      while (d.tb(e) != ']') {
-        Msg g; int role = scan_message(e, g);
+      while (d.ty[e] != ']') {
+        Msg g; const int role = scan_message(e, g);
         if (bad()) return;
-        int nx = d.next(e); if (d.tb(nx) == ',') nx++;
+        int nx = d.after(e);
         if (role == 2 || role == 3) { bedrock_system(g, sys_first); e = nx; if (bad()) return; continue; }
         if (!mfirst) pl.lit(L_COMMA); mfirst = false;
         if (role == 0) bedrock_user(g);
@@ -749,14 +779,13 @@ struct Walker {
           pl.lit(L_MSG_CONTENT_OPEN);
           bedrock_tool_result(g);
           if (bad()) return;
-          // coalesce the following tool messages (openai_awsbedrock.go:559-575)
-          while (d.tb(nx) != ']') {
-            Msg g2; int r2 = scan_message(nx, g2);
+          while (d.ty[nx] != ']') {  // coalesce the following tool messages (openai_awsbedrock.go:559-575)
+            Msg g2; const int r2 = scan_message(nx, g2);
             if (bad()) return;
             if (r2 != 4) break;
             pl.lit(L_COMMA); bedrock_tool_result(g2);
             if (bad()) return;
-            int n2 = d.next(nx); if (d.tb(n2) == ',') n2++; nx = n2;
+            nx = d.after(nx);
           }
           pl.lit(L_USER_CLOSE);
         }
@@ -768,39 +797,40 @@ struct Walker {
     if (pl.nsys) { pl.lit(L_SYSTEM_OPEN); pl.flush_sys(); pl.lit(L_RBRACK); }
     if (t.service_tier >= 0 && d.str_len(t.service_tier) > 0) { pl.lit(L_SERVICE_TIER); emit_str(t.service_tier); pl.lit(L_RBRACE); }
     // tool_choice decodes (and can fail) whether or not tools are present (openai.go:1194-1210)
-    int tc_kind = 0, tc_name = -1;  // 1 auto, 2 any, 3 tool{name=tc_name or ""}
+    int tc_kind = 0, tc_name = -1;  // 1 auto, 2 any, 3 tool{name}
     if (t.tool_choice >= 0) {
       const int tc = t.tool_choice;
       if (is_str(tc)) {
-        if (d.str_eq(tc, "auto", 4)) tc_kind = 1;
-        else if (d.str_eq(tc, "required", 8)) tc_kind = 2;
+        const uint32_t tv = d.id[tc];
+        if (tv == V_auto) tc_kind = 1;
+        else if (tv == V_required) tc_kind = 2;
         else if (model_contains(t.model, "anthropic", 9) && model_contains(t.model, "claude", 6)) { tc_kind = 3; tc_name = tc; }
       } else if (is_obj(tc)) {
-        const int ty = find(tc, "type", 4), fn = find(tc, "function", 8);
+        const int ty = find(tc, K_type), fn = find(tc, K_function);
         if (ty >= 0 && !is_str(ty)) { decline(AIGW_R_TYPE); return; }
-        if (fn >= 0) { if (!is_obj(fn)) { decline(AIGW_R_TYPE); return; } tc_name = find(fn, "name", 4); if (tc_name >= 0 && !is_str(tc_name)) { decline(AIGW_R_TYPE); return; } }
+        if (fn >= 0) { if (!is_obj(fn)) { decline(AIGW_R_TYPE); return; } tc_name = find(fn, K_name); if (tc_name >= 0 && !is_str(tc_name)) { decline(AIGW_R_TYPE); return; } }
         if (bad()) return;
         tc_kind = 3;
       } else { decline(AIGW_R_TYPE); return; }
     }
     // tools (openai_awsbedrock.go:162-226)
-    if (t.tools >= 0 && d.tb(t.tools + 1) != ']') {
+    if (t.tools >= 0 && d.ty[t.tools + 1] != ']') {
       pl.lit(L_TOOLCFG_OPEN);
       if (tc_kind == 1) pl.lit(L_TOOLCHOICE_AUTO);
       else if (tc_kind == 2) pl.lit(L_TOOLCHOICE_ANY);
       else if (tc_kind == 3) { pl.lit(L_TOOLCHOICE_TOOL); if (tc_name >= 0) emit_str(tc_name); else pl.lit(L_EMPTY_STR); pl.lit(L_TOOLCHOICE_TOOL_END); }
       pl.lit(L_TOOLS_OPEN);
       bool tf = true;
-      for (int e = t.tools + 1; d.tb(e) != ']';) {
+      for (int e = t.tools + 1; d.ty[e] != ']'; e = d.after(e)) {
         if (!is_obj(e)) { decline(AIGW_R_TOOL); return; }
-        int ty = find(e, "type", 4), fn = find(e, "function", 8), gs = find(e, "google_search", 13);
+        const int ty = find(e, K_type), fn = find(e, K_function), gs = find(e, K_google_search);
         if (ty >= 0 && !is_str(ty)) { decline(AIGW_R_TYPE); return; }
         if (gs >= 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
         if (bad()) return;
         if (fn >= 0) {
           if (!is_obj(fn)) { decline(AIGW_R_TYPE); return; }
-          int nm = find(fn, "name", 4), ds = find(fn, "description", 11), st = find(fn, "strict", 6), pr = find(fn, "parameters", 10);
-          bool cache = cache_enabled(fn);
+          const int nm = find(fn, K_name), ds = find(fn, K_description), st = find(fn, K_strict), pr = find(fn, K_parameters);
+          const bool cache = cache_enabled(find(fn, K_cache_control));
           if (bad()) return;
           if ((nm >= 0 && !is_str(nm)) || (ds >= 0 && !is_str(ds)) || (st >= 0 && !is_bool(st))) { decline(AIGW_R_TYPE); return; }
           if (!tf) pl.lit(L_COMMA); tf = false;
@@ -813,7 +843,6 @@ struct Walker {
           if (cache) pl.lit(L_TOOL_CACHE);
           pl.lit(L_RBRACE);
         }
-        int nx = d.next(e); if (d.tb(nx) == ',') nx++; e = nx;
       }
       pl.lit(L_TOOLS_CLOSE);
     }
@@ -821,36 +850,81 @@ struct Walker {
   }
 };
 
-// ------------------------------------------------------------------ the kernel
+// 16 bytes starting at an arbitrary shared-memory address (buffers carry ≥ 4 bytes of slack)
+__device__ __forceinline__ uint4 lds16_unaligned(const uint8_t* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  const uint32_t sh = (a & 3u) * 8u;
+  const uint32_t* w = (const uint32_t*)(p - (a & 3u));
+  const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+  uint4 r;
+  r.x = __funnelshift_r(w0, w1, sh); r.y = __funnelshift_r(w1, w2, sh); r.z = __funnelshift_r(w2, w3, sh); r.w = __funnelshift_r(w3, w4, sh);
+  return r;
+}
+
+// ------------------------------------------------------------------ the kernels
+// Three launches per sub-batch of documents, intermediates in a reusable global workspace:
+//   K1 index  (warp per document)    stage 1+2+2.5 → tok / ty / id arrays, token count
+//   K2 walk   (thread per document)  stage 3+4     → jump table, copy ops, scratch, plan header
+//   K3 emit   (warp per document)    stage 5       → output record + result
+// K2 is where SIMT pays: 32 structurally similar bodies share every instruction fetch.
+struct PlanOut { uint32_t nops, olen, path_len, model_off; uint16_t model_len; uint8_t flags, reason; };  // 20 bytes
+
+template <int MAXD>
+struct Work {  // per-document slots in the workspace
+  using C = Cls<MAXD>;
+  static constexpr size_t kTokB = (size_t)C::kTok * 2, kJmpB = (size_t)C::kTok * 2, kTyB = C::kTok, kIdB = C::kTok;
+  static constexpr size_t kOpsB = (size_t)(C::kOps + kSysCap) * 4, kScrB = C::kScr;
+  static constexpr size_t kPerDoc = kTokB + kJmpB + kTyB + kIdB + kOpsB + kScrB + 32;
+};
+
+struct WorkPtrs { uint16_t* tok; uint16_t* jmp; uint8_t* ty; uint8_t* id; uint32_t* ops; uint8_t* scr; uint32_t* ntok; PlanOut* plan; };
+
+template <int MAXD>
+__host__ __device__ inline WorkPtrs carve(uint8_t* base, size_t ndocs) {
+  using W = Work<MAXD>;
+  WorkPtrs w; uint8_t* p = base;
+  w.tok = (uint16_t*)p; p += W::kTokB * ndocs;
+  w.jmp = (uint16_t*)p; p += W::kJmpB * ndocs;
+  w.ops = (uint32_t*)p; p += W::kOpsB * ndocs;
+  w.ntok = (uint32_t*)p; p += 4 * ndocs;
+  w.plan = (PlanOut*)p; p += 24 * ndocs;
+  w.ty = p; p += W::kTyB * ndocs;
+  w.id = p; p += W::kIdB * ndocs;
+  w.scr = p;
+  return w;
+}
+
+__device__ __forceinline__ aigw_doc_result blank_result(uint32_t len) {
+  aigw_doc_result res;
+  res.out_off = 0; res.body_len = 0; res.path_len = 0; res.status = AIGW_DECLINED; res.reason = AIGW_R_NONE;
+  res.model_off = 0; res.model_len = 0; res.body_kind = AIGW_BODY_UNCHANGED; res.flags = 0; res.in_len = len; res._pad = 0;
+  return res;
+}
+
+// ---- K1: structural index, one warp per document
 template <int MAXD, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) chat_translate_kernel(const __grid_constant__ ChatParams P) {
+__global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_constant__ ChatParams P, uint32_t doc0, uint32_t ndocs, uint8_t* work, unsigned int* counter) {
   using C = Cls<MAXD>;
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint8_t* s_lits = smem;  // literal bytes, shared by the CTA
-  for (uint32_t i = threadIdx.x; i < sizeof(c_lits.bytes) / 4; i += blockDim.x) ((uint32_t*)s_lits)[i] = ((const uint32_t*)c_lits.bytes)[i];
-  __syncthreads();
-  uint8_t* wb = smem + sizeof(c_lits.bytes) + (size_t)warp * C::kWarpBytes;
+  constexpr int kWarpBytes = C::kIn + C::kTok * 4;
+  uint8_t* wb = smem + (size_t)warp * kWarpBytes;
   uint8_t* s_in = wb;
-  uint8_t* s_out = wb + C::kIn;
-  uint16_t* s_tok = (uint16_t*)s_out;
-  uint16_t* s_jmp = s_tok + C::kTokCap;
-  uint32_t* s_ops = (uint32_t*)(wb + C::kIn + C::kOut);
-  uint8_t* s_scr = wb + C::kIn + C::kOut + C::kOpCap * 4;
+  uint16_t* s_tok = (uint16_t*)(wb + C::kIn);
+  uint8_t* s_ty = (uint8_t*)(s_tok + C::kTok);
+  uint8_t* s_id = s_ty + C::kTok;
+  const WorkPtrs wp = carve<MAXD>(work, ndocs);
 
   for (;;) {
-    uint32_t doc = 0;
-    if (lane == 0) doc = atomicAdd(P.next_doc, 1u);
-    doc = __shfl_sync(FULL, doc, 0);
-    if (doc >= P.n) break;
+    uint32_t li = 0;
+    if (lane == 0) li = atomicAdd(counter, 1u);
+    li = __shfl_sync(FULL, li, 0);
+    if (li >= ndocs) break;
+    const uint32_t doc = doc0 + li;
     const uint32_t len = P.lens[doc];
     const uint8_t* g = P.bodies + P.offsets[doc];
-    aigw_doc_result res;
-    res.out_off = 0; res.body_len = 0; res.path_len = 0; res.status = AIGW_DECLINED; res.reason = AIGW_R_NONE;
-    res.model_off = 0; res.model_len = 0; res.body_kind = AIGW_BODY_UNCHANGED; res.flags = 0; res.in_len = len; res._pad = 0;
     if (len > (uint32_t)MAXD || len == 0) {
-      res.reason = len ? AIGW_R_TOO_LARGE : AIGW_R_SYNTAX;
-      if (lane == 0) P.results[doc] = res;
+      if (lane == 0) wp.ntok[li] = 0x80000000u | (len ? AIGW_R_TOO_LARGE : AIGW_R_SYNTAX);
       continue;
     }
     // ---- stage 1: load (16-byte coalesced), pad the last round with spaces
@@ -881,21 +955,21 @@ __global__ void __launch_bounds__(WARPS * 32) chat_translate_kernel(const __grid
         mctl |= nib_from_ff(__vcmpltu4(w[j], 0x20202020u)) << (4 * j);
       }
       // escaped characters: odd-length backslash runs, carry across lanes
-      const uint32_t tail = __clz(~mb);  // backslash run length at the top of this lane's 32 bytes
-      const uint32_t odd = __ballot_sync(FULL, tail < 32u && (tail & 1u));
-      const uint32_t full = __ballot_sync(FULL, tail == 32u);
-      uint32_t cin;
-      {
-        const uint32_t below = ~full & ((1u << lane) - 1u);
-        if (below == 0) cin = carry_esc; else cin = (odd >> (31 - __clz(below))) & 1u;
-      }
-      {
-        // carry out of the round = carry into a virtual lane 32
-        const uint32_t below = ~full;
-        carry_esc = below == 0 ? carry_esc : (odd >> (31 - __clz(below))) & 1u;
-      }
-      uint32_t esc;
-      {
+      uint32_t esc = 0;
+      const uint32_t any_bs = __ballot_sync(FULL, mb != 0);
+      if (any_bs | carry_esc) {
+        const uint32_t tail = __clz(~mb);  // backslash run length at the top of this lane's 32 bytes
+        const uint32_t odd = __ballot_sync(FULL, tail < 32u && (tail & 1u));
+        const uint32_t full = __ballot_sync(FULL, tail == 32u);
+        uint32_t cin;
+        {
+          const uint32_t below = ~full & ((1u << lane) - 1u);
+          if (below == 0) cin = carry_esc; else cin = (odd >> (31 - __clz(below))) & 1u;
+        }
+        {
+          const uint32_t below = ~full;
+          carry_esc = below == 0 ? carry_esc : (odd >> (31 - __clz(below))) & 1u;
+        }
         const uint32_t bs = mb & ~cin;  // a leading backslash that is itself escaped starts no run
         const uint32_t follows = (bs << 1) | cin;
         const uint32_t even = 0x55555555u;
@@ -934,15 +1008,15 @@ __global__ void __launch_bounds__(WARPS * 32) chat_translate_kernel(const __grid
         carry_sc = __shfl_sync(FULL, msc >> 31, 31);
         mtok |= msc & ~((msc << 1) | prev);
       }
-      // compact token positions
+      // compact token positions (+ the byte at each position)
       const uint32_t cnt = __popc(mtok);
       uint32_t incl = cnt;
 #pragma unroll
       for (int sft = 1; sft < 32; sft <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, sft); if (lane >= sft) incl += v; }
       const uint32_t total = __shfl_sync(FULL, incl, 31);
       uint32_t wpos = ntok + incl - cnt;
-      if (ntok + total > (uint32_t)C::kTokCap) flags |= 4u;
-      else { uint32_t m = mtok; while (m) { const int j = __ffs(m) - 1; m &= m - 1; s_tok[wpos++] = (uint16_t)(base + j); } }
+      if (ntok + total > (uint32_t)C::kTok) flags |= 4u;
+      else { uint32_t m = mtok; while (m) { const int j = __ffs(m) - 1; m &= m - 1; s_tok[wpos] = (uint16_t)(base + j); s_ty[wpos] = s_in[base + j]; wpos++; } }
       ntok += total;
     }
     flags = __reduce_or_sync(FULL, flags);
@@ -952,50 +1026,135 @@ __global__ void __launch_bounds__(WARPS * 32) chat_translate_kernel(const __grid
     else if (flags & 1u) reason = AIGW_R_CTRL_IN_STRING;
     else if (flags & 2u) reason = AIGW_R_ESCAPE;
     else if (carry_str) reason = AIGW_R_SYNTAX;
-    // ---- stages 3+4 on lane 0
-    uint32_t nops = 0, olen = 0, path_len = 0, model_off = 0, model_len = 0, rflags = 0, body_kind = AIGW_BODY_BYTES;
-    if (lane == 0 && !reason) {
-      Walker W;
-      W.d.s = s_in; W.d.len = len; W.d.tok = s_tok; W.d.jmp = s_jmp; W.d.nt = (int)ntok; W.d.kind = 0;
-      W.pl.ops = s_ops; W.pl.nops = 0; W.pl.nsys = 0; W.pl.cap = C::kOpCap - kSysCap; W.pl.olen = 0; W.pl.err = 0;
-      W.sc.p = s_scr; W.sc.n = 0; W.sc.cap = C::kScr;
-      W.tok_tail = s_tok + ntok; W.jmp_tail = s_jmp + ntok; W.tok_tail_cap = C::kTokCap - (int)ntok;
-      W.P = &P; W.reason = 0;
-      reason = validate_tokens(W.d);
-      if (!reason) {
-        Walker::Top t;
-        if (W.scan_top(t)) {
-          const bool stream = t.stream >= 0 && W.d.tb(t.stream) == 't';
-          if (t.model >= 0) { model_off = W.d.str_off(t.model); model_len = W.d.str_len(t.model); }
-          rflags = stream ? 1u : 0u;
-          if (P.schema == AIGW_SCHEMA_AWS_BEDROCK) W.plan_bedrock(t, stream, path_len);
-          else W.decline(AIGW_R_SCHEMA);
+    if (reason) { if (lane == 0) wp.ntok[li] = 0x80000000u | (uint32_t)reason; continue; }
+    // ---- stage 2.5: key / value ids, one string token per lane.  Quote tokens alternate open/close,
+    // so the opening quotes are the quote tokens of even rank.
+    {
+      uint32_t qbase = 0;
+      for (uint32_t b0 = 0; b0 < ntok; b0 += 32) {
+        const uint32_t i = b0 + lane;
+        const bool isq = i < ntok && s_ty[i] == '"';
+        const uint32_t qm = __ballot_sync(FULL, isq);
+        uint32_t id = 0;
+        if (isq) {
+          const uint32_t rank = qbase + __popc(qm & ((1u << lane) - 1u));
+          if ((rank & 1u) == 0 && i + 1 < ntok) {
+            const uint32_t o = (uint32_t)s_tok[i] + 1u, n = (uint32_t)s_tok[i + 1] - s_tok[i] - 1u;
+            const bool is_key = i + 2 < ntok && s_ty[i + 2] == ':';
+            id = is_key ? key_id(s_in + o, n) : val_id(s_in + o, n);
+          }
         }
-        reason = W.reason ? W.reason : W.pl.err;
-        nops = W.pl.nops; olen = W.pl.olen;
-        if (!reason && olen > (uint32_t)C::kOut) reason = AIGW_R_OUT_SPACE;
+        if (i < ntok) s_id[i] = (uint8_t)id;
+        qbase += __popc(qm);
       }
-    }
-    reason = __shfl_sync(FULL, reason, 0);
-    if (reason) {
-      res.reason = (uint8_t)reason;
-      if (lane == 0) P.results[doc] = res;
       __syncwarp();
+    }
+    // ---- write the token arrays out, coalesced
+    {
+      uint16_t* gt = wp.tok + (size_t)li * C::kTok; uint8_t* gy = wp.ty + (size_t)li * C::kTok; uint8_t* gi = wp.id + (size_t)li * C::kTok;
+      const uint32_t nw2 = (ntok + 1) >> 1, nw4 = (ntok + 3) >> 2;
+      for (uint32_t i = lane; i < nw2; i += 32) ((uint32_t*)gt)[i] = ((const uint32_t*)s_tok)[i];
+      for (uint32_t i = lane; i < nw4; i += 32) { ((uint32_t*)gy)[i] = ((const uint32_t*)s_ty)[i]; ((uint32_t*)gi)[i] = ((const uint32_t*)s_id)[i]; }
+      if (lane == 0) wp.ntok[li] = ntok;
+    }
+    __syncwarp();
+  }
+}
+
+// ---- K2: validate + schema walk, one thread per document
+template <int MAXD>
+__global__ void __launch_bounds__(128) chat_walk_kernel(const __grid_constant__ ChatParams P, uint32_t doc0, uint32_t ndocs, uint8_t* work) {
+  using C = Cls<MAXD>;
+  const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= ndocs) return;
+  const WorkPtrs wp = carve<MAXD>(work, ndocs);
+  const uint32_t doc = doc0 + li;
+  const uint32_t nt_word = wp.ntok[li];
+  PlanOut po; po.nops = 0; po.olen = 0; po.path_len = 0; po.model_off = 0; po.model_len = 0; po.flags = 0; po.reason = 0;
+  if (nt_word & 0x80000000u) { po.reason = (uint8_t)(nt_word & 0xff); wp.plan[li] = po; return; }
+  const uint32_t ntok = nt_word;
+  Walker W;
+  W.d.s = P.bodies + P.offsets[doc]; W.d.len = P.lens[doc];
+  W.d.tok = wp.tok + (size_t)li * C::kTok; W.d.jmp = wp.jmp + (size_t)li * C::kTok; W.d.ty = wp.ty + (size_t)li * C::kTok; W.d.id = wp.id + (size_t)li * C::kTok;
+  W.d.nt = (int)ntok; W.d.kind = 0;
+  W.pl.ops = wp.ops + (size_t)li * (C::kOps + kSysCap); W.pl.nops = 0; W.pl.nsys = 0; W.pl.cap = C::kOps; W.pl.clen = 0; W.pl.ckind = 0; W.pl.coff = 0; W.pl.olen = 0; W.pl.err = 0;
+  W.sc.p = wp.scr + (size_t)li * C::kScr; W.sc.n = 0; W.sc.cap = C::kScr - 4;
+  W.tok_tail = (uint16_t*)W.d.tok + ntok; W.jmp_tail = W.d.jmp + ntok; W.ty_tail = (uint8_t*)W.d.ty + ntok; W.tail_cap = C::kTok - (int)ntok;
+  W.P = &P; W.reason = 0;
+  int reason = validate_tokens(W.d);
+  uint32_t path_len = 0;
+  if (!reason) {
+    Walker::Top t;
+    if (W.scan_top(t)) {
+      const bool stream = t.stream >= 0 && W.d.ty[t.stream] == 't';
+      if (t.model >= 0) { po.model_off = W.d.str_off(t.model); po.model_len = (uint16_t)W.d.str_len(t.model); }
+      po.flags = stream ? 1u : 0u;
+      if (P.schema == AIGW_SCHEMA_AWS_BEDROCK) W.plan_bedrock(t, stream, path_len);
+      else W.decline(AIGW_R_SCHEMA);
+    }
+    W.pl.flush();
+    reason = W.reason ? W.reason : W.pl.err;
+    if (!reason && W.pl.nops == 0) reason = AIGW_R_OPS;
+  }
+  po.reason = (uint8_t)reason; po.nops = (uint32_t)W.pl.nops; po.olen = W.pl.olen; po.path_len = path_len;
+  wp.plan[li] = po;
+}
+
+
+// ---- K3: emit, one warp per document
+template <int MAXD, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) chat_emit_kernel(const __grid_constant__ ChatParams P, uint32_t doc0, uint32_t ndocs, uint8_t* work, unsigned int* counter) {
+  using C = Cls<MAXD>;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* s_lits = smem;
+  for (uint32_t i = threadIdx.x; i < sizeof(c_lits.bytes) / 4; i += blockDim.x) ((uint32_t*)s_lits)[i] = ((const uint32_t*)c_lits.bytes)[i];
+  __syncthreads();
+  constexpr int kWarpBytes = C::kIn + C::kOps * 8 + ((C::kScr + 15) & ~15);
+  uint8_t* wb = smem + sizeof(c_lits.bytes) + (size_t)warp * kWarpBytes;
+  uint8_t* s_in = wb;
+  uint32_t* s_ops = (uint32_t*)(wb + C::kIn);
+  uint32_t* s_pre = s_ops + C::kOps;
+  uint8_t* s_scr = (uint8_t*)(s_pre + C::kOps);
+  const WorkPtrs wp = carve<MAXD>(work, ndocs);
+
+  for (;;) {
+    uint32_t li = 0;
+    if (lane == 0) li = atomicAdd(counter, 1u);
+    li = __shfl_sync(FULL, li, 0);
+    if (li >= ndocs) break;
+    const uint32_t doc = doc0 + li;
+    const uint32_t len = P.lens[doc];
+    const PlanOut po = wp.plan[li];
+    aigw_doc_result res = blank_result(len);
+    if (po.reason) {
+      res.reason = po.reason;
+      if (lane == 0) P.results[doc] = res;
       continue;
     }
-    nops = __shfl_sync(FULL, nops, 0); olen = __shfl_sync(FULL, olen, 0);
-    __syncwarp();
-    // ---- stage 5: emit.  tok/jmp (aliasing s_out) are dead from here on.
+    const uint32_t nops = po.nops, olen = po.olen;
+    // stage the body, the ops (+ exclusive prefix of their lengths) and the scratch bytes they reference
     {
-      uint32_t dst = 0;
-      const uint8_t* lits = s_lits;
-      for (uint32_t k = 0; k < nops; k++) {
-        const uint32_t op = s_ops[k];
-        const uint32_t kind = op >> 30, l = (op >> 16) & 0x3fffu, off = op & 0xffffu;
-        if (kind == 1) { for (uint32_t i = lane; i < l; i += 32) s_out[dst + i] = lits[off + i]; }
-        else { const uint8_t* sp = (kind == 0 ? s_in : s_scr) + off; for (uint32_t i = lane; i < l; i += 32) s_out[dst + i] = sp[i]; }
-        dst += l;
+      const uint4* g4 = (const uint4*)(P.bodies + P.offsets[doc]);
+      uint4* s4 = (uint4*)s_in;
+      const uint32_t n16 = (len + 15u) >> 4;
+      for (uint32_t i = lane; i < n16; i += 32) s4[i] = __ldg(g4 + i);
+      const uint32_t* gops = wp.ops + (size_t)li * (C::kOps + kSysCap);
+      uint32_t run = 0, scr_hi = 0;
+      for (uint32_t b0 = 0; b0 < nops; b0 += 32) {
+        const uint32_t k = b0 + lane;
+        const uint32_t op = k < nops ? gops[k] : 0u;
+        const uint32_t l = (op >> 16) & 0x3fffu;
+        if ((op >> 30) == 2u) scr_hi = max(scr_hi, (op & 0xffffu) + l);
+        uint32_t incl = l;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, sft); if (lane >= sft) incl += v; }
+        if (k < nops) { s_ops[k] = op; s_pre[k] = run + incl - l; }
+        run += __shfl_sync(FULL, incl, 31);
       }
+      scr_hi = __reduce_max_sync(FULL, scr_hi);
+      const uint8_t* gs = wp.scr + (size_t)li * C::kScr;
+      for (uint32_t i = lane; i < ((scr_hi + 3u) >> 2); i += 32) ((uint32_t*)s_scr)[i] = ((const uint32_t*)gs)[i];
     }
     __syncwarp();
     const uint32_t rec = (olen + 15u) & ~15u;
@@ -1005,16 +1164,39 @@ __global__ void __launch_bounds__(WARPS * 32) chat_translate_kernel(const __grid
     if (obase + rec > P.out_capacity) {
       res.reason = AIGW_R_ARENA_FULL;
       if (lane == 0) P.results[doc] = res;
+      __syncwarp();
       continue;
     }
     {
       uint4* o4 = (uint4*)(P.out + obase);
-      const uint4* s4 = (const uint4*)s_out;
-      for (uint32_t i = lane; i < (rec >> 4); i += 32) o4[i] = s4[i];
+      const uint32_t nchunks = rec >> 4;
+      for (uint32_t c = lane; c < nchunks; c += 32) {
+        const uint32_t pos = c << 4;
+        uint32_t lo = 0, hi = nops - 1;  // largest k with pre[k] <= pos
+        while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (s_pre[mid] <= pos) lo = mid; else hi = mid - 1; }
+        uint32_t k = lo;
+        uint32_t op = s_ops[k];
+        uint32_t kind = op >> 30, l = (op >> 16) & 0x3fffu, off = op & 0xffffu;
+        uint32_t within = pos - s_pre[k];
+        const uint8_t* sp = (kind == 0 ? s_in : kind == 1 ? s_lits : s_scr) + off;
+        uint4 v;
+        if (l - within >= 16u) v = lds16_unaligned(sp + within);
+        else {
+          uint32_t wv[4] = {0, 0, 0, 0};
+          for (int b = 0; b < 16; b++) {
+            while (within >= l && k + 1 < nops) { k++; op = s_ops[k]; kind = op >> 30; l = (op >> 16) & 0x3fffu; off = op & 0xffffu; within = 0; sp = (kind == 0 ? s_in : kind == 1 ? s_lits : s_scr) + off; }
+            uint32_t byte = 0;
+            if (within < l) { byte = sp[within]; within++; }
+            wv[b >> 2] |= byte << ((b & 3) * 8);
+          }
+          v.x = wv[0]; v.y = wv[1]; v.z = wv[2]; v.w = wv[3];
+        }
+        o4[c] = v;
+      }
     }
     if (lane == 0) {
-      res.out_off = obase + P.out_bias; res.body_len = olen - path_len; res.path_len = (uint16_t)path_len; res.status = AIGW_OK; res.reason = 0;
-      res.model_off = model_off; res.model_len = (uint16_t)model_len; res.body_kind = (uint8_t)body_kind; res.flags = (uint8_t)rflags;
+      res.out_off = obase + P.out_bias; res.body_len = olen - po.path_len; res.path_len = (uint16_t)po.path_len; res.status = AIGW_OK; res.reason = 0;
+      res.model_off = po.model_off; res.model_len = po.model_len; res.body_kind = AIGW_BODY_BYTES; res.flags = po.flags;
       P.results[doc] = res;
     }
     __syncwarp();
@@ -1022,36 +1204,70 @@ __global__ void __launch_bounds__(WARPS * 32) chat_translate_kernel(const __grid
 }
 
 // ------------------------------------------------------------------ host-side launcher
+template <int MAXD>
+size_t work_bytes_cls(size_t ndocs) { return Work<MAXD>::kPerDoc * ndocs + 256; }
+
 template <int MAXD, int WARPS>
-static cudaError_t launch_cls(const ChatParams& P, int sm_count, cudaStream_t st, int* blocks_out) {
+static cudaError_t launch_cls(const ChatParams& P, int sm_count, cudaStream_t st, uint8_t* work, size_t work_cap, unsigned int* counters, cudaEvent_t* ev, int ev_cap) {
   using C = Cls<MAXD>;
-  const size_t smem = sizeof(LitTable::bytes) + (size_t)C::kWarpBytes * WARPS;
+  const size_t smem1 = (size_t)(C::kIn + C::kTok * 4) * WARPS;
+  const size_t smem3 = sizeof(LitTable::bytes) + (size_t)(C::kIn + C::kOps * 8 + ((C::kScr + 15) & ~15)) * WARPS;
   static bool configured = false;
-  static int blocks_per_sm = 1;
+  static int bps1 = 1, bps3 = 1;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(chat_translate_kernel<MAXD, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(chat_index_kernel<MAXD, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, chat_translate_kernel<MAXD, WARPS>, WARPS * 32, smem);
+    e = cudaFuncSetAttribute(chat_emit_kernel<MAXD, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
     if (e != cudaSuccess) return e;
-    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps1, chat_index_kernel<MAXD, WARPS>, WARPS * 32, smem1);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps3, chat_emit_kernel<MAXD, WARPS>, WARPS * 32, smem3);
+    if (e != cudaSuccess) return e;
+    if (bps1 < 1) bps1 = 1; if (bps3 < 1) bps3 = 1;
     configured = true;
   }
-  long long want = ((long long)P.n + WARPS - 1) / WARPS;
-  long long grid = (long long)sm_count * blocks_per_sm;  // persistent: a multiple of the SM count
-  if (want < grid) grid = want;
-  if (grid < 1) grid = 1;
-  if (blocks_out) *blocks_out = (int)grid;
-  chat_translate_kernel<MAXD, WARPS><<<(unsigned)grid, WARPS * 32, smem, st>>>(P);
+  size_t sub = work_cap / Work<MAXD>::kPerDoc;
+  if (sub > 262144) sub = 262144;
+  if (sub == 0) return cudaErrorMemoryAllocation;
+  int ci = 0;
+  for (uint32_t doc0 = 0; doc0 < P.n; doc0 += (uint32_t)sub) {
+    const uint32_t nd = (uint32_t)(P.n - doc0 < sub ? P.n - doc0 : sub);
+    unsigned int* c1 = counters + (ci++ & 63); unsigned int* c3 = counters + (ci++ & 63);
+    cudaMemsetAsync(c1, 0, 4, st); cudaMemsetAsync(c3, 0, 4, st);
+    long long want = ((long long)nd + WARPS - 1) / WARPS;
+    long long g1 = (long long)sm_count * bps1; if (want < g1) g1 = want;
+    long long g3 = (long long)sm_count * bps3; if (want < g3) g3 = want;
+    const int sb = (int)(doc0 / sub);
+    const bool timed = ev && 4 * sb + 3 < ev_cap;
+    if (timed) cudaEventRecord(ev[4 * sb + 0], st);
+    chat_index_kernel<MAXD, WARPS><<<(unsigned)g1, WARPS * 32, smem1, st>>>(P, doc0, nd, work, c1);
+    if (timed) cudaEventRecord(ev[4 * sb + 1], st);
+    chat_walk_kernel<MAXD><<<(nd + 127) / 128, 128, 0, st>>>(P, doc0, nd, work);
+    if (timed) cudaEventRecord(ev[4 * sb + 2], st);
+    chat_emit_kernel<MAXD, WARPS><<<(unsigned)g3, WARPS * 32, smem3, st>>>(P, doc0, nd, work, c3);
+    if (timed) cudaEventRecord(ev[4 * sb + 3], st);
+  }
   return cudaGetLastError();
 }
 
-cudaError_t launch_chat_translate(const ChatParams& P, uint32_t max_len, int sm_count, cudaStream_t st) {
-  if (max_len <= 2048) return launch_cls<2048, 2>(P, sm_count, st, nullptr);
-  if (max_len <= 5120) return launch_cls<5120, 2>(P, sm_count, st, nullptr);
-  if (max_len <= 9216) return launch_cls<9216, 2>(P, sm_count, st, nullptr);
-  if (max_len <= 17408) return launch_cls<17408, 1>(P, sm_count, st, nullptr);
-  if (max_len <= 33792) return launch_cls<33792, 1>(P, sm_count, st, nullptr);
-  return launch_cls<65536, 1>(P, sm_count, st, nullptr);
+size_t chat_work_bytes(uint32_t max_len, size_t ndocs) {
+  if (max_len <= 2048) return work_bytes_cls<2048>(ndocs);
+  if (max_len <= 5120) return work_bytes_cls<5120>(ndocs);
+  if (max_len <= 9216) return work_bytes_cls<9216>(ndocs);
+  if (max_len <= 17408) return work_bytes_cls<17408>(ndocs);
+  if (max_len <= 33792) return work_bytes_cls<33792>(ndocs);
+  return work_bytes_cls<65536>(ndocs);
+}
+
+cudaError_t launch_chat_translate(const ChatParams& P, uint32_t max_len, int sm_count, cudaStream_t st, uint8_t* work, size_t work_cap, unsigned int* counters, int* launches,
+                                  cudaEvent_t* ev, int ev_cap) {
+  if (launches) { size_t per = chat_work_bytes(max_len, 1) - 256; size_t sub = work_cap / per; if (sub > 262144) sub = 262144; if (sub == 0) sub = 1; *launches = 3 * (int)((P.n + sub - 1) / sub); }
+  if (max_len <= 2048) return launch_cls<2048, 4>(P, sm_count, st, work, work_cap, counters, ev, ev_cap);
+  if (max_len <= 5120) return launch_cls<5120, 4>(P, sm_count, st, work, work_cap, counters, ev, ev_cap);
+  if (max_len <= 9216) return launch_cls<9216, 2>(P, sm_count, st, work, work_cap, counters, ev, ev_cap);
+  if (max_len <= 17408) return launch_cls<17408, 2>(P, sm_count, st, work, work_cap, counters, ev, ev_cap);
+  if (max_len <= 33792) return launch_cls<33792, 1>(P, sm_count, st, work, work_cap, counters, ev, ev_cap);
+  return launch_cls<65536, 1>(P, sm_count, st, work, work_cap, counters, ev, ev_cap);
 }
 
 }  // namespace aigw

@@ -129,19 +129,22 @@ struct ChatParams {
   char openai_path[128];
 };
 
-// size classes: MAXD bytes of input per document
+// size classes: MAXD bytes of input per document.  Per-warp shared memory:
+//   in[kIn] | tpos u16[kTok] | jmp u16[kTok] | tty u8[kTok] | tkid u8[kTok] | ops u32[kOps+kSys] | pre u32[kOps] | scr[kScr]
+static constexpr int kSysCap = 64;
 template <int MAXD>
 struct Cls {
-  static constexpr int kIn = MAXD;                               // multiple of 1024
-  static constexpr int kOut = ((MAXD + MAXD / 4 + 512 + 15) / 16) * 16;
-  static constexpr int kTokCap = kOut / 4;                       // u16 tok + u16 jmp alias the out buffer
-  static constexpr int kOpCap = 384 + MAXD / 16;       // includes kSysCap parked ops
-  static constexpr int kScr = 512 + MAXD / 8;
-  static constexpr int kWarpBytes = kIn + kOut + kOpCap * 4 + kScr;
+  static constexpr int kIn = MAXD + 16;                  // multiple of 16; slack for unaligned word reads
+  static constexpr int kTok = (MAXD / 8 + 63) / 64 * 64; // one token per 8 input bytes, else the body is declined
+  static constexpr int kOps = 160 + MAXD / 32;
+  static constexpr int kScr = 256 + MAXD / 8;
+  static constexpr int kWarpBytes = kIn + kTok * 6 + (kOps + kSysCap) * 4 + kOps * 4 + kScr;
 };
 
-}  // namespace aigw
+// Workspace: chat_work_bytes(max_len, docs_per_sub_batch) bytes hold one sub-batch of intermediates; the launcher
+// walks P.n documents in sub-batches that fit `work_cap` (3 launches per sub-batch).  `counters`: ≥ 64 device uints.
+size_t chat_work_bytes(uint32_t max_len, size_t ndocs);
+cudaError_t launch_chat_translate(const ChatParams& P, uint32_t max_len, int sm_count, cudaStream_t st, uint8_t* work, size_t work_cap,
+                                  unsigned int* counters, int* launches, cudaEvent_t* stage_events, int stage_event_cap);
 
-namespace aigw {
-cudaError_t launch_chat_translate(const ChatParams& P, uint32_t max_len, int sm_count, cudaStream_t st);
-}
+}  // namespace aigw

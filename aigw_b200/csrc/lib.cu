@@ -38,6 +38,9 @@ struct aigw_ctx {
   // host-API output (pinned)
   uint8_t* h_out = nullptr; size_t h_out_cap = 0;
   aigw_doc_result* h_res = nullptr; size_t h_res_cap = 0;
+  // chat workspace (intermediates of one sub-batch) + per-stage timing events
+  uint8_t* d_work = nullptr; size_t work_cap = 0;
+  cudaEvent_t stage_ev[64]; float stage_ms[3] = {0, 0, 0}; int last_launches = 0;
   // sse host-API device buffers
   uint8_t* d_sse_bytes = nullptr; size_t sse_bytes_cap = 0;
   uint64_t* d_sse_coff = nullptr; size_t sse_coff_cap = 0;
@@ -64,6 +67,17 @@ static void fill_params(ChatParams& P, const aigw_backend_cfg* cfg) {
   memcpy(P.openai_path, path.data(), path.size()); P.prefix_len = (uint16_t)path.size();
 }
 
+static int ensure(aigw_ctx* ctx, void** p, size_t* cap, size_t want, bool host) {
+  if (*cap >= want) return 0;
+  if (*p) { if (host) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *cap = 0; }
+  size_t sz = want + want / 8 + 4096;
+  cudaError_t e = host ? cudaHostAlloc(p, sz, cudaHostAllocDefault) : cudaMalloc(p, sz);
+  if (e != cudaSuccess) { ctx->err = std::string(host ? "cudaHostAlloc" : "cudaMalloc") + ": " + cudaGetErrorString(e); return (int)e; }
+  *cap = sz;
+  return 0;
+}
+#define ENSURE(p, cap, want, host) do { int _r = ensure(ctx, (void**)&(p), &(cap), (want), (host)); if (_r) return _r; } while (0)
+
 extern "C" {
 
 const char* aigw_version(void) { return "aigw_b200 0.1 (sm_100a)"; }
@@ -84,6 +98,7 @@ int aigw_init(int device, aigw_ctx** out) {
   cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
   cudaMalloc(&ctx->d_counters, 256 * sizeof(unsigned int));
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+  for (auto& e2 : ctx->stage_ev) cudaEventCreate(&e2);
   for (auto& s : ctx->slot) {
     cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming); cudaEventCreate(&s.ev_k0); cudaEventCreate(&s.ev_k1);
     cudaEventCreateWithFlags(&s.ev_ctr, cudaEventDisableTiming); cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming);
@@ -103,7 +118,8 @@ void aigw_destroy(aigw_ctx* ctx) {
     cudaFree(s.d_in); cudaFree(s.d_off); cudaFree(s.d_len); cudaFree(s.d_out); cudaFree(s.d_res); cudaFree(s.d_used); cudaFree(s.d_next); cudaFreeHost(s.h_used);
     cudaEventDestroy(s.ev_h2d); cudaEventDestroy(s.ev_k0); cudaEventDestroy(s.ev_k1); cudaEventDestroy(s.ev_ctr); cudaEventDestroy(s.ev_done);
   }
-  cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_res); cudaFree(ctx->d_counters);
+  cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_res); cudaFree(ctx->d_counters); cudaFree(ctx->d_work);
+  for (auto& e2 : ctx->stage_ev) cudaEventDestroy(e2);
   cudaFree(ctx->d_sse_bytes); cudaFree(ctx->d_sse_coff); cudaFree(ctx->d_sse_first); cudaFree(ctx->d_sse_res);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->s_compute); cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
@@ -131,24 +147,29 @@ int aigw_chat_translate_device(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const
   fill_params(P, cfg);
   P.bodies = d_bodies; P.offsets = d_offsets; P.lens = d_lens; P.n = n; P.out = d_out; P.out_capacity = out_capacity;
   P.results = d_results; P.out_used = (unsigned long long*)d_out_used;
-  P.next_doc = ctx->d_counters + (ctx->counter_next++ & 255); P.out_bias = 0;
-  CK(cudaMemsetAsync(P.next_doc, 0, sizeof(unsigned int), st));
+  P.next_doc = nullptr; P.out_bias = 0;
+  const uint32_t ml = max_len ? max_len : 65536u;
+  {  // workspace for one sub-batch (≤ 128 Ki documents); the launcher loops over sub-batches
+    const size_t sub = n < 131072u ? n : 131072u;
+    ENSURE(ctx->d_work, ctx->work_cap, chat_work_bytes(ml, sub), false);
+  }
   if (kernel_ms) CK(cudaEventRecord(ctx->ev0, st));
-  CK(launch_chat_translate(P, max_len ? max_len : 65536u, ctx->sm_count, st));
-  if (kernel_ms) { CK(cudaEventRecord(ctx->ev1, st)); CK(cudaEventSynchronize(ctx->ev1)); CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1)); }
+  CK(launch_chat_translate(P, ml, ctx->sm_count, st, ctx->d_work, ctx->work_cap, ctx->d_counters, &ctx->last_launches, kernel_ms ? ctx->stage_ev : nullptr, 64));
+  if (kernel_ms) {
+    CK(cudaEventRecord(ctx->ev1, st)); CK(cudaEventSynchronize(ctx->ev1)); CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
+    ctx->stage_ms[0] = ctx->stage_ms[1] = ctx->stage_ms[2] = 0;
+    const int nsb = ctx->last_launches / 3;
+    for (int sb = 0; sb < nsb && 4 * sb + 3 < 64; sb++) for (int k = 0; k < 3; k++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->stage_ev[4 * sb + k], ctx->stage_ev[4 * sb + k + 1]); ctx->stage_ms[k] += ms; }
+  }
   return 0;
 }
 
-static int ensure(aigw_ctx* ctx, void** p, size_t* cap, size_t want, bool host) {
-  if (*cap >= want) return 0;
-  if (*p) { if (host) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *cap = 0; }
-  size_t sz = want + want / 8 + 4096;
-  cudaError_t e = host ? cudaHostAlloc(p, sz, cudaHostAllocDefault) : cudaMalloc(p, sz);
-  if (e != cudaSuccess) { ctx->err = std::string(host ? "cudaHostAlloc" : "cudaMalloc") + ": " + cudaGetErrorString(e); return (int)e; }
-  *cap = sz;
+/* per-stage CUDA-event times (index, walk, emit) and launch count of the last timed aigw_chat_translate_device call */
+int aigw_chat_last_profile(aigw_ctx* ctx, float stage_ms[3], int* launches) {
+  for (int k = 0; k < 3; k++) stage_ms[k] = ctx->stage_ms[k];
+  if (launches) *launches = ctx->last_launches;
   return 0;
 }
-#define ENSURE(p, cap, want, host) do { int _r = ensure(ctx, (void**)&(p), &(cap), (want), (host)); if (_r) return _r; } while (0)
 
 int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const uint8_t* bodies, const uint64_t* offsets,
                              const uint32_t* lens, uint32_t n, aigw_batch_out* out) {
@@ -191,6 +212,7 @@ int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const u
     }
     ENSURE(S.d_out, S.out_cap, max_out, false);
   }
+  ENSURE(ctx->d_work, ctx->work_cap, chat_work_bytes(max_len, max_docs), false);
   ENSURE(ctx->h_out, ctx->h_out_cap, total_out_cap, true);
   ENSURE(ctx->h_res, ctx->h_res_cap, (size_t)n * sizeof(aigw_doc_result), true);
 
@@ -220,15 +242,15 @@ int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const u
     // kernel
     CK(cudaStreamWaitEvent(ctx->s_compute, S.ev_h2d, 0));
     CK(cudaMemsetAsync(S.d_used, 0, 8, ctx->s_compute));
-    CK(cudaMemsetAsync(S.d_next, 0, 4, ctx->s_compute));
     ChatParams P = P0;
     P.bodies = S.d_in - offsets[b];  // absolute offsets index straight into the chunk
     P.offsets = S.d_off; P.lens = S.d_len; P.n = nd; P.out = S.d_out; P.out_capacity = out_cap[c];
     P.results = S.d_res; P.out_used = S.d_used; P.next_doc = S.d_next; P.out_bias = out_base[c];
     CK(cudaEventRecord(S.ev_k0, ctx->s_compute));
-    CK(launch_chat_translate(P, max_len, ctx->sm_count, ctx->s_compute));
+    int nl = 0;
+    CK(launch_chat_translate(P, max_len, ctx->sm_count, ctx->s_compute, ctx->d_work, ctx->work_cap, ctx->d_counters, &nl, nullptr, 0));
     CK(cudaEventRecord(S.ev_k1, ctx->s_compute));
-    out->gpu_launches++;
+    out->gpu_launches += nl;
     // results + counter
     CK(cudaStreamWaitEvent(ctx->s_d2h, S.ev_k1, 0));
     CK(cudaMemcpyAsync(S.h_used, S.d_used, 8, cudaMemcpyDeviceToHost, ctx->s_d2h));

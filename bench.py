@@ -180,10 +180,11 @@ def main():
         ctx.chat_translate_device(cfg, d_in, d_off, d_len, n, max_len, d_out, out_cap, d_res, d_used)
     sampler = ClockSampler(local); sampler.start()
     barrier()
-    t0 = time.perf_counter(); kms = []
+    t0 = time.perf_counter(); kms = []; stage = np.zeros(3); dev_launches = 0
     for _ in range(a.steps):
         ctx.memset(d_used, 0, 8)
         kms.append(ctx.chat_translate_device(cfg, d_in, d_off, d_len, n, max_len, d_out, out_cap, d_res, d_used))
+        pr = ctx.chat_last_profile(); stage += [pr["index_ms"], pr["walk_ms"], pr["emit_ms"]]; dev_launches += pr["launches"]
     barrier()
     wall = time.perf_counter() - t0
     dev_s = float(np.sum(kms)) / 1e3
@@ -196,7 +197,7 @@ def main():
         ctx.dfree(p)
 
     # ---- end-to-end through the host-buffer C-ABI call
-    e2e = None; p50 = None; launches = a.steps
+    e2e = None; p50 = None; launches = dev_launches
     if not a.skip_e2e:
         for _ in range(max(1, min(a.warmup, 2))):
             _, _, st = ctx.chat_translate_host(cfg, arena, offs, lens)
@@ -237,7 +238,10 @@ def main():
                            "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB in + {out_bytes / 1e6:.0f} MB out per step vs 126 MB L2)", "sharding": "hash(request-id)→device, no collective",
                            "wall_ms_per_step_incl_launch": wall_max / a.steps * 1e3},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                             "kernel": "chat_translate_kernel<5120,2>", "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": dev_s / a.steps * 1e3},
+                             "kernel": "chat_index_kernel + chat_walk_kernel + chat_emit_kernel (the three stages of one translate pass)",
+                             "algorithmic_bytes_per_step": alg_bytes, "avg_step_ms": dev_s / a.steps * 1e3,
+                             "stage_ms_per_step": {"index": stage[0] / a.steps, "walk": stage[1] / a.steps, "emit": stage[2] / a.steps},
+                             "launches_per_step": dev_launches // max(1, a.steps)},
                 "gpu_launches": launches, "clocks": clocks}
         if e2e:
             line["e2e"] = {"value": tot_bodies * a.steps / e_wall_max, "unit": "bodies/s", "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),

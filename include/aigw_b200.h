@@ -104,6 +104,10 @@ int aigw_chat_translate_device(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const
                                const uint32_t* d_lens, uint32_t n, uint32_t max_len, uint8_t* d_out, uint64_t out_capacity,
                                aigw_doc_result* d_results, uint64_t* d_out_used, void* stream, float* kernel_ms);
 
+/* CUDA-event time of the three stages (index, walk, emit) and the launch count of the last aigw_chat_translate_device
+ * call that passed kernel_ms != NULL. */
+int aigw_chat_last_profile(aigw_ctx* ctx, float stage_ms[3], int* launches);
+
 /* ---- same, HOST buffers (the call the cgo shim makes) ----
  * bodies/offsets/lens live in host memory (pinned memory from aigw_host_alloc gives full PCIe rate).
  * The library pipelines H2D → kernel → D2H in chunks on its own streams and returns when all
