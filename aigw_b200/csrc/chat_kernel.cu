@@ -1208,7 +1208,7 @@ template <int MAXD>
 size_t work_bytes_cls(size_t ndocs) { return Work<MAXD>::kPerDoc * ndocs + 256; }
 
 template <int MAXD, int WARPS>
-static cudaError_t launch_cls(const ChatParams& P, int sm_count, cudaStream_t st, uint8_t* work, size_t work_cap, unsigned int* counters, cudaEvent_t* ev, int ev_cap) {
+static cudaError_t launch_cls(const ChatParams& P, uint32_t first, int sm_count, cudaStream_t st, uint8_t* work, size_t work_cap, unsigned int* counters, cudaEvent_t* ev, int ev_cap) {
   using C = Cls<MAXD>;
   const size_t smem1 = (size_t)(C::kIn + C::kTok * 4) * WARPS;
   const size_t smem3 = sizeof(LitTable::bytes) + (size_t)(C::kIn + C::kOps * 8 + ((C::kScr + 15) & ~15)) * WARPS;
@@ -1230,14 +1230,15 @@ static cudaError_t launch_cls(const ChatParams& P, int sm_count, cudaStream_t st
   if (sub > 262144) sub = 262144;
   if (sub == 0) return cudaErrorMemoryAllocation;
   int ci = 0;
-  for (uint32_t doc0 = 0; doc0 < P.n; doc0 += (uint32_t)sub) {
-    const uint32_t nd = (uint32_t)(P.n - doc0 < sub ? P.n - doc0 : sub);
+  for (uint32_t rel = 0; rel < P.n; rel += (uint32_t)sub) {
+    const uint32_t doc0 = first + rel;
+    const uint32_t nd = (uint32_t)(P.n - rel < sub ? P.n - rel : sub);
     unsigned int* c1 = counters + (ci++ & 63); unsigned int* c3 = counters + (ci++ & 63);
     cudaMemsetAsync(c1, 0, 4, st); cudaMemsetAsync(c3, 0, 4, st);
     long long want = ((long long)nd + WARPS - 1) / WARPS;
     long long g1 = (long long)sm_count * bps1; if (want < g1) g1 = want;
     long long g3 = (long long)sm_count * bps3; if (want < g3) g3 = want;
-    const int sb = (int)(doc0 / sub);
+    const int sb = (int)(rel / sub);
     const bool timed = ev && 4 * sb + 3 < ev_cap;
     if (timed) cudaEventRecord(ev[4 * sb + 0], st);
     chat_index_kernel<MAXD, WARPS><<<(unsigned)g1, WARPS * 32, smem1, st>>>(P, doc0, nd, work, c1);
@@ -1259,15 +1260,21 @@ size_t chat_work_bytes(uint32_t max_len, size_t ndocs) {
   return work_bytes_cls<65536>(ndocs);
 }
 
+cudaError_t launch_chat_translate_range(const ChatParams& P, uint32_t first, uint32_t count, uint32_t max_len, int sm_count, cudaStream_t st, uint8_t* work, size_t work_cap,
+                                        unsigned int* counters, int* launches) {
+  ChatParams Q = P; Q.n = count;
+  return launch_chat_translate(Q, max_len, sm_count, st, work, work_cap, counters, launches, nullptr, 0, first);
+}
+
 cudaError_t launch_chat_translate(const ChatParams& P, uint32_t max_len, int sm_count, cudaStream_t st, uint8_t* work, size_t work_cap, unsigned int* counters, int* launches,
-                                  cudaEvent_t* ev, int ev_cap) {
+                                  cudaEvent_t* ev, int ev_cap, uint32_t first) {
   if (launches) { size_t per = chat_work_bytes(max_len, 1) - 256; size_t sub = work_cap / per; if (sub > 262144) sub = 262144; if (sub == 0) sub = 1; *launches = 3 * (int)((P.n + sub - 1) / sub); }
-  if (max_len <= 2048) return launch_cls<2048, 4>(P, sm_count, st, work, work_cap, counters, ev, ev_cap);
-  if (max_len <= 5120) return launch_cls<5120, 4>(P, sm_count, st, work, work_cap, counters, ev, ev_cap);
-  if (max_len <= 9216) return launch_cls<9216, 2>(P, sm_count, st, work, work_cap, counters, ev, ev_cap);
-  if (max_len <= 17408) return launch_cls<17408, 2>(P, sm_count, st, work, work_cap, counters, ev, ev_cap);
-  if (max_len <= 33792) return launch_cls<33792, 1>(P, sm_count, st, work, work_cap, counters, ev, ev_cap);
-  return launch_cls<65536, 1>(P, sm_count, st, work, work_cap, counters, ev, ev_cap);
+  if (max_len <= 2048) return launch_cls<2048, 4>(P, first, sm_count, st, work, work_cap, counters, ev, ev_cap);
+  if (max_len <= 5120) return launch_cls<5120, 4>(P, first, sm_count, st, work, work_cap, counters, ev, ev_cap);
+  if (max_len <= 9216) return launch_cls<9216, 2>(P, first, sm_count, st, work, work_cap, counters, ev, ev_cap);
+  if (max_len <= 17408) return launch_cls<17408, 2>(P, first, sm_count, st, work, work_cap, counters, ev, ev_cap);
+  if (max_len <= 33792) return launch_cls<33792, 1>(P, first, sm_count, st, work, work_cap, counters, ev, ev_cap);
+  return launch_cls<65536, 1>(P, first, sm_count, st, work, work_cap, counters, ev, ev_cap);
 }
 
 }  // namespace aigw

@@ -145,6 +145,9 @@ struct Cls {
 // walks P.n documents in sub-batches that fit `work_cap` (3 launches per sub-batch).  `counters`: ≥ 64 device uints.
 size_t chat_work_bytes(uint32_t max_len, size_t ndocs);
 cudaError_t launch_chat_translate(const ChatParams& P, uint32_t max_len, int sm_count, cudaStream_t st, uint8_t* work, size_t work_cap,
-                                  unsigned int* counters, int* launches, cudaEvent_t* stage_events, int stage_event_cap);
+                                  unsigned int* counters, int* launches, cudaEvent_t* stage_events, int stage_event_cap, uint32_t first = 0);
+// documents [first, first+count): offsets / lens / results are indexed with the global document number
+cudaError_t launch_chat_translate_range(const ChatParams& P, uint32_t first, uint32_t count, uint32_t max_len, int sm_count, cudaStream_t st, uint8_t* work,
+                                        size_t work_cap, unsigned int* counters, int* launches);
 
 }  // namespace aigw

@@ -40,6 +40,7 @@ struct aigw_ctx {
   aigw_doc_result* h_res = nullptr; size_t h_res_cap = 0;
   // chat workspace (intermediates of one sub-batch) + per-stage timing events
   uint8_t* d_work = nullptr; size_t work_cap = 0;
+  unsigned long long* d_used_arr = nullptr; unsigned long long* h_used_arr = nullptr; size_t used_cap = 0;  // per-chunk bump counters
   cudaEvent_t stage_ev[64]; float stage_ms[3] = {0, 0, 0}; int last_launches = 0;
   // sse host-API device buffers
   uint8_t* d_sse_bytes = nullptr; size_t sse_bytes_cap = 0;
@@ -71,7 +72,7 @@ static int ensure(aigw_ctx* ctx, void** p, size_t* cap, size_t want, bool host) 
   if (*cap >= want) return 0;
   if (*p) { if (host) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *cap = 0; }
   size_t sz = want + want / 8 + 4096;
-  cudaError_t e = host ? cudaHostAlloc(p, sz, cudaHostAllocDefault) : cudaMalloc(p, sz);
+  cudaError_t e = host ? cudaHostAlloc(p, sz, cudaHostAllocMapped) : cudaMalloc(p, sz);
   if (e != cudaSuccess) { ctx->err = std::string(host ? "cudaHostAlloc" : "cudaMalloc") + ": " + cudaGetErrorString(e); return (int)e; }
   *cap = sz;
   return 0;
@@ -118,7 +119,7 @@ void aigw_destroy(aigw_ctx* ctx) {
     cudaFree(s.d_in); cudaFree(s.d_off); cudaFree(s.d_len); cudaFree(s.d_out); cudaFree(s.d_res); cudaFree(s.d_used); cudaFree(s.d_next); cudaFreeHost(s.h_used);
     cudaEventDestroy(s.ev_h2d); cudaEventDestroy(s.ev_k0); cudaEventDestroy(s.ev_k1); cudaEventDestroy(s.ev_ctr); cudaEventDestroy(s.ev_done);
   }
-  cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_res); cudaFree(ctx->d_counters); cudaFree(ctx->d_work);
+  cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_res); cudaFree(ctx->d_counters); cudaFree(ctx->d_work); cudaFree(ctx->d_used_arr); cudaFreeHost(ctx->h_used_arr);
   for (auto& e2 : ctx->stage_ev) cudaEventDestroy(e2);
   cudaFree(ctx->d_sse_bytes); cudaFree(ctx->d_sse_coff); cudaFree(ctx->d_sse_first); cudaFree(ctx->d_sse_res);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
@@ -173,98 +174,91 @@ int aigw_chat_last_profile(aigw_ctx* ctx, float stage_ms[3], int* launches) {
 
 int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const uint8_t* bodies, const uint64_t* offsets,
                              const uint32_t* lens, uint32_t n, aigw_batch_out* out) {
+  // Pipeline: H2D DMA of chunk c+1 (copy engine) overlaps the three kernels of chunk c, whose emit stage stores the
+  // output records and the per-body results directly into mapped pinned host memory (posted PCIe writes, 512 B per
+  // warp store).  No device→host copy and no host synchronisation until the end of the call.
   memset(out, 0, sizeof *out);
   if (n == 0) return 0;
   cudaSetDevice(ctx->device);
-  // ---- chunking: ≈64 MiB of input per chunk (one chunk for small batches)
-  const uint64_t kChunkBytes = 64ull << 20;
+  const uint64_t kChunkBytes = 256ull << 20;
   std::vector<uint32_t> cb;  // chunk begin doc index
   cb.push_back(0);
+  uint32_t max_len = 0;
   {
     uint64_t start = offsets[0];
     for (uint32_t i = 0; i < n; i++) {
-      uint64_t end = offsets[i] + (((uint64_t)lens[i] + 15u) & ~15ull);
+      const uint64_t end = offsets[i] + (((uint64_t)lens[i] + 15u) & ~15ull);
       if (end - start > kChunkBytes && i > cb.back()) { cb.push_back(i); start = offsets[i]; }
+      if (lens[i] > max_len) max_len = lens[i];
     }
     cb.push_back(n);
   }
   const int nch = (int)cb.size() - 1;
-  uint64_t max_in = 0; uint32_t max_docs = 0, max_len = 0;
+  uint64_t max_in = 0; uint32_t max_docs = 0;
   std::vector<uint64_t> in_bytes(nch), out_cap(nch), out_base(nch);
   uint64_t total_out_cap = 0;
   for (int c = 0; c < nch; c++) {
-    uint32_t b = cb[c], e = cb[c + 1];
-    uint64_t ib = offsets[e - 1] + (((uint64_t)lens[e - 1] + 15u) & ~15ull) - offsets[b] + 16;
+    const uint32_t b = cb[c], e = cb[c + 1];
+    const uint64_t ib = offsets[e - 1] + (((uint64_t)lens[e - 1] + 15u) & ~15ull) - offsets[b] + 16;
     in_bytes[c] = ib; if (ib > max_in) max_in = ib; if (e - b > max_docs) max_docs = e - b;
     out_cap[c] = ((ib + ib / 4 + (uint64_t)(e - b) * 528 + 255) & ~255ull);
     out_base[c] = total_out_cap; total_out_cap += out_cap[c];
   }
-  for (uint32_t i = 0; i < n; i++) if (lens[i] > max_len) max_len = lens[i];
-  uint64_t max_out = 0; for (int c = 0; c < nch; c++) if (out_cap[c] > max_out) max_out = out_cap[c];
-  for (int s = 0; s < kSlots && s < nch; s++) {
+  const int nslots = nch < 2 ? 1 : 2;
+  for (int s = 0; s < nslots; s++) {
     ChunkSlot& S = ctx->slot[s];
     ENSURE(S.d_in, S.in_cap, max_in + 64, false);
     if (S.doc_cap < max_docs) {
-      cudaFree(S.d_off); cudaFree(S.d_len); cudaFree(S.d_res); S.doc_cap = 0;
-      size_t dc = max_docs + max_docs / 8 + 16;
-      CK(cudaMalloc(&S.d_off, dc * 8)); CK(cudaMalloc(&S.d_len, dc * 4)); CK(cudaMalloc(&S.d_res, dc * sizeof(aigw_doc_result)));
+      cudaFree(S.d_off); cudaFree(S.d_len); S.doc_cap = 0;
+      const size_t dc = max_docs + max_docs / 8 + 16;
+      CK(cudaMalloc(&S.d_off, dc * 8)); CK(cudaMalloc(&S.d_len, dc * 4));
       S.doc_cap = dc;
     }
-    ENSURE(S.d_out, S.out_cap, max_out, false);
   }
-  ENSURE(ctx->d_work, ctx->work_cap, chat_work_bytes(max_len, max_docs), false);
+  ENSURE(ctx->d_work, ctx->work_cap, chat_work_bytes(max_len, max_docs < 131072u ? max_docs : 131072u), false);
   ENSURE(ctx->h_out, ctx->h_out_cap, total_out_cap, true);
   ENSURE(ctx->h_res, ctx->h_res_cap, (size_t)n * sizeof(aigw_doc_result), true);
+  if ((size_t)nch > ctx->used_cap) {
+    cudaFree(ctx->d_used_arr); cudaFreeHost(ctx->h_used_arr); ctx->used_cap = 0;
+    const size_t cap = (size_t)nch + 64;
+    CK(cudaMalloc(&ctx->d_used_arr, cap * 8)); CK(cudaHostAlloc(&ctx->h_used_arr, cap * 8, cudaHostAllocDefault));
+    ctx->used_cap = cap;
+  }
+  uint8_t* dev_out = nullptr; aigw_doc_result* dev_res = nullptr;  // device views of the pinned arenas
+  CK(cudaHostGetDevicePointer((void**)&dev_out, ctx->h_out, 0));
+  CK(cudaHostGetDevicePointer((void**)&dev_res, ctx->h_res, 0));
 
   ChatParams P0; fill_params(P0, cfg);
-  std::vector<uint64_t> used(nch, 0);
-  uint64_t h2d = 0, d2h = 0;
-  auto enqueue_out = [&](int c) -> int {  // needs the counter of chunk c on the host
-    ChunkSlot& S = ctx->slot[c % kSlots];
-    CK(cudaEventSynchronize(S.ev_ctr));
-    uint64_t u = *S.h_used; if (u > out_cap[c]) u = out_cap[c];
-    used[c] = u;
-    if (u) CK(cudaMemcpyAsync(ctx->h_out + out_base[c], S.d_out, u, cudaMemcpyDeviceToHost, ctx->s_d2h));
-    CK(cudaEventRecord(S.ev_done, ctx->s_d2h));
-    d2h += u;
-    return 0;
-  };
+  uint64_t h2d = 0;
+  CK(cudaMemsetAsync(ctx->d_used_arr, 0, (size_t)nch * 8, ctx->s_compute));
+  CK(cudaEventRecord(ctx->ev0, ctx->s_compute));
   for (int c = 0; c < nch; c++) {
-    ChunkSlot& S = ctx->slot[c % kSlots];
+    ChunkSlot& S = ctx->slot[c % nslots];
     const uint32_t b = cb[c], e = cb[c + 1], nd = e - b;
-    if (c >= kSlots) CK(cudaEventSynchronize(S.ev_done));  // slot free again (its output has left the device)
-    // H2D
+    if (c >= nslots) CK(cudaStreamWaitEvent(ctx->s_h2d, S.ev_k1, 0));  // the slot's previous chunk has been consumed
     CK(cudaMemcpyAsync(S.d_in, bodies + offsets[b], in_bytes[c] - 16, cudaMemcpyHostToDevice, ctx->s_h2d));
     CK(cudaMemcpyAsync(S.d_off, offsets + b, (size_t)nd * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
     CK(cudaMemcpyAsync(S.d_len, lens + b, (size_t)nd * 4, cudaMemcpyHostToDevice, ctx->s_h2d));
     CK(cudaEventRecord(S.ev_h2d, ctx->s_h2d));
     h2d += in_bytes[c] - 16 + (uint64_t)nd * 12;
-    // kernel
     CK(cudaStreamWaitEvent(ctx->s_compute, S.ev_h2d, 0));
-    CK(cudaMemsetAsync(S.d_used, 0, 8, ctx->s_compute));
     ChatParams P = P0;
     P.bodies = S.d_in - offsets[b];  // absolute offsets index straight into the chunk
-    P.offsets = S.d_off; P.lens = S.d_len; P.n = nd; P.out = S.d_out; P.out_capacity = out_cap[c];
-    P.results = S.d_res; P.out_used = S.d_used; P.next_doc = S.d_next; P.out_bias = out_base[c];
-    CK(cudaEventRecord(S.ev_k0, ctx->s_compute));
+    P.offsets = S.d_off - b; P.lens = S.d_len - b; P.n = nd;
+    P.out = dev_out + out_base[c]; P.out_capacity = out_cap[c];
+    P.results = dev_res; P.out_used = ctx->d_used_arr + c; P.next_doc = nullptr; P.out_bias = out_base[c];
+    // documents keep their global index: kernels address offsets/lens/results with doc0 + i
     int nl = 0;
-    CK(launch_chat_translate(P, max_len, ctx->sm_count, ctx->s_compute, ctx->d_work, ctx->work_cap, ctx->d_counters, &nl, nullptr, 0));
+    CK(launch_chat_translate_range(P, b, nd, max_len, ctx->sm_count, ctx->s_compute, ctx->d_work, ctx->work_cap, ctx->d_counters, &nl));
     CK(cudaEventRecord(S.ev_k1, ctx->s_compute));
     out->gpu_launches += nl;
-    // results + counter
-    CK(cudaStreamWaitEvent(ctx->s_d2h, S.ev_k1, 0));
-    CK(cudaMemcpyAsync(S.h_used, S.d_used, 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
-    CK(cudaEventRecord(S.ev_ctr, ctx->s_d2h));
-    CK(cudaMemcpyAsync(ctx->h_res + b, S.d_res, (size_t)nd * sizeof(aigw_doc_result), cudaMemcpyDeviceToHost, ctx->s_d2h));
-    d2h += (uint64_t)nd * sizeof(aigw_doc_result) + 8;
-    if (c >= 1) { int r = enqueue_out(c - 1); if (r) return r; }
   }
-  { int r = enqueue_out(nch - 1); if (r) return r; }
-  CK(cudaStreamSynchronize(ctx->s_d2h));
+  CK(cudaEventRecord(ctx->ev1, ctx->s_compute));
+  CK(cudaMemcpyAsync(ctx->h_used_arr, ctx->d_used_arr, (size_t)nch * 8, cudaMemcpyDeviceToHost, ctx->s_compute));
   CK(cudaStreamSynchronize(ctx->s_compute));
-  float ms_total = 0;
-  for (int c = 0; c < nch && c < kSlots; c++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->slot[c].ev_k0, ctx->slot[c].ev_k1); ms_total += ms; }
-  if (nch > kSlots) ms_total = ms_total * nch / kSlots;  // events of reused slots hold the last chunk only: scale the sample
+  uint64_t d2h = (uint64_t)n * sizeof(aigw_doc_result) + (uint64_t)nch * 8;
+  for (int c = 0; c < nch; c++) d2h += ctx->h_used_arr[c] < out_cap[c] ? ctx->h_used_arr[c] : out_cap[c];
+  float ms_total = 0; cudaEventElapsedTime(&ms_total, ctx->ev0, ctx->ev1);
   out->results = ctx->h_res; out->out = ctx->h_out; out->out_used = total_out_cap; out->h2d_bytes = h2d; out->d2h_bytes = d2h; out->kernel_ms = ms_total;
   return 0;
 }
