@@ -103,7 +103,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--bodies", type=int, default=int(os.environ.get("AIGW_BENCH_BODIES", 1_000_000)), help="bodies per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=40_000)
+    ap.add_argument("--cpu-sample", type=int, default=400_000)
     ap.add_argument("--skip-e2e", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
@@ -117,7 +117,7 @@ def main():
         if rank != 0:
             return
         entry.build()
-        n = min(a.bodies, 60_000)
+        n = min(a.bodies, 400_000)
         arena, offs, lens = W.chat_corpus(SEED, 0, n, threads=ncpu)
         times = []
         for s in range(a.warmup + a.steps):
@@ -157,7 +157,7 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload, all host threads and 1 thread
     cpu = None
     if rank == 0 and world == 1:
-        r1, n1, _ = cpu_oracle_rate(arena, offs, lens, max(2000, a.cpu_sample // 8), 1)
+        r1, n1, _ = cpu_oracle_rate(arena, offs, lens, max(2000, min(a.cpu_sample // 8, 50_000)), 1)
         rN, nN, _ = cpu_oracle_rate(arena, offs, lens, a.cpu_sample, ncpu)
         rN2, _, _ = cpu_oracle_rate(arena, offs, lens, a.cpu_sample, ncpu)
         cpu = {"value": max(rN, rN2), "unit": "bodies/s", "cores": ncpu, "kind": "port", "sample": f"first {nN} bodies of the workload, {ncpu} threads (1 thread: {r1:.0f} bodies/s on {n1})",
