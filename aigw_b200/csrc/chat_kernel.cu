@@ -16,6 +16,9 @@ __device__ __constant__ LitTable c_lits = make_lit_table();
 static_assert(make_lit_table().off[L_COUNT] + 8 <= sizeof(LitTable::bytes), "literal table overflow (keep slack for unaligned reads)");
 
 #define FULL 0xffffffffu
+#ifndef AIGW_WALK_BLOCKS
+#define AIGW_WALK_BLOCKS 4
+#endif
 
 // ------------------------------------------------------------------ small device helpers
 __device__ __forceinline__ uint32_t nib_from_ff(uint32_t m) {  // m: 0xFF per selected byte → 4-bit mask
@@ -37,87 +40,119 @@ enum Kid : uint8_t {
   K_COUNT
 };
 static_assert(K_TOP_END <= 63, "top-level seen mask is 64 bits");
+static_assert(K_COUNT <= 63, "ids are 6 bits in the token word");
 enum Vid : uint8_t {
   V_NONE = 0, V_user, V_assistant, V_system, V_developer, V_tool, V_text, V_refusal, V_thinking, V_redacted_thinking, V_ephemeral,
   V_enabled, V_disabled, V_adaptive, V_auto, V_required
 };
 
-template <int N>
-__device__ __forceinline__ bool eqn(const uint8_t* p, const char (&lit)[N]) {
-  bool ok = true;
+// Perfect-enough hash tables (FNV-1a, open addressing, verified by a byte compare) built at compile time and copied to
+// shared memory by the index kernel: every lane runs the same few instructions whatever the string is.
+#define AIGW_KEYS(X) \
+  X("n", K_n) X("id", K_id) X("ttl", K_ttl) X("role", K_role) X("name", K_name) X("type", K_type) X("text", K_text) X("stop", K_stop) X("seed", K_seed) X("user", K_user) \
+  X("model", K_model) X("tools", K_tools) X("top_p", K_top_p) X("audio", K_audio) X("stream", K_stream) X("strict", K_strict) X("content", K_content) X("refusal", K_refusal) \
+  X("messages", K_messages) X("thinking", K_thinking) X("logprobs", K_logprobs) X("function", K_function) X("verbosity", K_verbosity) X("signature", K_signature) \
+  X("arguments", K_arguments) X("max_tokens", K_max_tokens) X("modalities", K_modalities) X("tool_calls", K_tool_calls) X("logit_bias", K_logit_bias) X("prediction", K_prediction) \
+  X("parameters", K_parameters) X("temperature", K_temperature) X("tool_choice", K_tool_choice) X("description", K_description) X("guided_json", K_guided_json) \
+  X("service_tier", K_service_tier) X("top_logprobs", K_top_logprobs) X("tool_call_id", K_tool_call_id) X("guided_regex", K_guided_regex) X("cache_control", K_cache_control) \
+  X("guided_choice", K_guided_choice) X("budget_tokens", K_budget_tokens) X("google_search", K_google_search) X("include_usage", K_include_usage) X("stream_options", K_stream_options) \
+  X("safetySettings", K_safetySettings) X("response_format", K_response_format) X("redactedContent", K_redactedContent) X("includeThoughts", K_includeThoughts) \
+  X("presence_penalty", K_presence_penalty) X("reasoning_effort", K_reasoning_effort) X("generationConfig", K_generationConfig) X("frequency_penalty", K_frequency_penalty) \
+  X("web_search_options", K_web_search_options) X("parallel_tool_calls", K_parallel_tool_calls) X("max_completion_tokens", K_max_completion_tokens)
+#define AIGW_VALS(X) \
+  X("user", V_user) X("tool", V_tool) X("text", V_text) X("auto", V_auto) X("system", V_system) X("refusal", V_refusal) X("enabled", V_enabled) X("thinking", V_thinking) \
+  X("disabled", V_disabled) X("adaptive", V_adaptive) X("required", V_required) X("assistant", V_assistant) X("developer", V_developer) X("ephemeral", V_ephemeral) \
+  X("redacted_thinking", V_redacted_thinking)
+
+static constexpr int kKeySlots = 128, kValSlots = 32, kMaxIdLen = 24;
+// slot = { six little-endian words of the string zero-padded to 24 bytes, len | id << 8 }
+struct IdSlot { uint32_t w[6]; uint32_t meta; };
+struct alignas(16) IdTables { IdSlot key[kKeySlots]; IdSlot val[kValSlots]; };
+__host__ __device__ constexpr uint32_t id_hash(const uint32_t* v, uint32_t n) {
+  uint32_t h = v[0] * 0x9E3779B1u ^ v[1] * 0x85EBCA77u ^ v[2] * 0xC2B2AE3Du ^ v[3] * 0x27D4EB2Fu ^ v[4] * 0x165667B1u ^ v[5] * 0x2545F491u;
+  h ^= h >> 15; h += n * 0x9E3779B1u; h ^= h >> 13;
+  return h;
+}
+constexpr void id_insert(IdSlot* tab, int slots, const char* lit, int idv) {
+  uint32_t v[6] = {0, 0, 0, 0, 0, 0};
+  int n = 0; while (lit[n]) { v[n >> 2] |= (uint32_t)(uint8_t)lit[n] << ((n & 3) * 8); n++; }
+  int sl = id_hash(v, (uint32_t)n) & (slots - 1);
+  while (tab[sl].meta) sl = (sl + 1) & (slots - 1);
+  for (int k = 0; k < 6; k++) tab[sl].w[k] = v[k];
+  tab[sl].meta = (uint32_t)n | ((uint32_t)idv << 8);
+}
+constexpr IdTables make_id_tables() {
+  IdTables t{};
+#define X(lit, idv) id_insert(t.key, kKeySlots, lit, idv);
+  AIGW_KEYS(X)
+#undef X
+#define X(lit, idv) id_insert(t.val, kValSlots, lit, idv);
+  AIGW_VALS(X)
+#undef X
+  return t;
+}
+__device__ __constant__ IdTables c_ids = make_id_tables();
+
+// id of a short string (1 ≤ n ≤ kMaxIdLen) held in shared memory, against the key or the value table (also in shared
+// memory).  Straight-line code: seven aligned word loads, funnel shifts, length mask, multiplicative hash, ≤ 4 probes.
+__device__ __forceinline__ uint32_t lookup_id(const IdTables* T, const uint8_t* p, uint32_t n, bool key) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  const uint32_t sh = (a & 3u) * 8u;
+  const uint32_t* wp = (const uint32_t*)(p - (a & 3u));
+  uint32_t x[7];
 #pragma unroll
-  for (int k = 0; k < N - 1; k++) ok &= (p[k] == (uint8_t)lit[k]);
-  return ok;
-}
-#define KMATCH(lit, id) if (eqn(p, lit)) return id;
-__device__ uint32_t key_id(const uint8_t* p, uint32_t n) {
-  switch (n) {
-    case 1: KMATCH("n", K_n) break;
-    case 2: KMATCH("id", K_id) break;
-    case 3: KMATCH("ttl", K_ttl) break;
-    case 4: KMATCH("role", K_role) KMATCH("name", K_name) KMATCH("type", K_type) KMATCH("text", K_text) KMATCH("stop", K_stop) KMATCH("seed", K_seed) KMATCH("user", K_user) break;
-    case 5: KMATCH("model", K_model) KMATCH("tools", K_tools) KMATCH("top_p", K_top_p) KMATCH("audio", K_audio) break;
-    case 6: KMATCH("stream", K_stream) KMATCH("strict", K_strict) break;
-    case 7: KMATCH("content", K_content) KMATCH("refusal", K_refusal) break;
-    case 8: KMATCH("messages", K_messages) KMATCH("thinking", K_thinking) KMATCH("logprobs", K_logprobs) KMATCH("function", K_function) break;
-    case 9: KMATCH("verbosity", K_verbosity) KMATCH("signature", K_signature) KMATCH("arguments", K_arguments) break;
-    case 10: KMATCH("max_tokens", K_max_tokens) KMATCH("modalities", K_modalities) KMATCH("tool_calls", K_tool_calls) KMATCH("logit_bias", K_logit_bias) KMATCH("prediction", K_prediction) KMATCH("parameters", K_parameters) break;
-    case 11: KMATCH("temperature", K_temperature) KMATCH("tool_choice", K_tool_choice) KMATCH("description", K_description) KMATCH("guided_json", K_guided_json) break;
-    case 12: KMATCH("service_tier", K_service_tier) KMATCH("top_logprobs", K_top_logprobs) KMATCH("tool_call_id", K_tool_call_id) KMATCH("guided_regex", K_guided_regex) break;
-    case 13: KMATCH("cache_control", K_cache_control) KMATCH("guided_choice", K_guided_choice) KMATCH("budget_tokens", K_budget_tokens) KMATCH("google_search", K_google_search) KMATCH("include_usage", K_include_usage) break;
-    case 14: KMATCH("stream_options", K_stream_options) KMATCH("safetySettings", K_safetySettings) break;
-    case 15: KMATCH("response_format", K_response_format) KMATCH("redactedContent", K_redactedContent) KMATCH("includeThoughts", K_includeThoughts) break;
-    case 16: KMATCH("presence_penalty", K_presence_penalty) KMATCH("reasoning_effort", K_reasoning_effort) KMATCH("generationConfig", K_generationConfig) break;
-    case 17: KMATCH("frequency_penalty", K_frequency_penalty) break;
-    case 18: KMATCH("web_search_options", K_web_search_options) break;
-    case 19: KMATCH("parallel_tool_calls", K_parallel_tool_calls) break;
-    case 21: KMATCH("max_completion_tokens", K_max_completion_tokens) break;
-    default: break;
+  for (int k = 0; k < 7; k++) x[k] = wp[k];
+  uint32_t v[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    const uint32_t rem = n > 4u * k ? n - 4u * k : 0u;
+    const uint32_t m = rem >= 4u ? 0xffffffffu : ((1u << (8u * rem)) - 1u);
+    v[k] = __funnelshift_r(x[k], x[k + 1], sh) & m;
   }
-  return K_NONE;
-}
-__device__ uint32_t val_id(const uint8_t* p, uint32_t n) {
-  switch (n) {
-    case 4: KMATCH("user", V_user) KMATCH("tool", V_tool) KMATCH("text", V_text) KMATCH("auto", V_auto) break;
-    case 6: KMATCH("system", V_system) break;
-    case 7: KMATCH("refusal", V_refusal) KMATCH("enabled", V_enabled) break;
-    case 8: KMATCH("thinking", V_thinking) KMATCH("disabled", V_disabled) KMATCH("adaptive", V_adaptive) KMATCH("required", V_required) break;
-    case 9: KMATCH("assistant", V_assistant) KMATCH("developer", V_developer) KMATCH("ephemeral", V_ephemeral) break;
-    case 17: KMATCH("redacted_thinking", V_redacted_thinking) break;
-    default: break;
+  const uint32_t h = id_hash(v, n);
+  const IdSlot* tab = key ? T->key : T->val;
+  const uint32_t mask = key ? (kKeySlots - 1) : (kValSlots - 1);
+  uint32_t sl = h & mask;
+#pragma unroll 1
+  for (int probe = 0; probe < 6; probe++) {
+    const IdSlot e = tab[sl];
+    if (e.meta == 0) return 0;
+    if ((e.meta & 0xffu) == n && e.w[0] == v[0] && e.w[1] == v[1] && e.w[2] == v[2] && e.w[3] == v[3] && e.w[4] == v[4] && e.w[5] == v[5]) return e.meta >> 8;
+    sl = (sl + 1) & mask;
   }
-  return V_NONE;
+  return 0;
 }
-#undef KMATCH
 
 // ------------------------------------------------------------------ token view of one JSON text
+// token word = pos(16) | byte at pos(8) | id(6) | esc(1): id = key id (string followed by ':'), value id (other
+// strings), or the scalar's length (numbers / literals; 63 = longer); esc = the string contains a backslash.
 struct Doc {
   const uint8_t* s;   // bytes
   uint32_t len;       // valid bytes
-  const uint16_t* tok;
+  const uint32_t* tw; // token words
   uint16_t* jmp;
-  const uint8_t* ty;  // byte at the token position
-  const uint8_t* id;  // key id (token followed by ':') or value id (other strings); 0 elsewhere
   int nt;
   uint32_t kind;      // op source kind: 0 input, 2 scratch
 
+  __device__ __forceinline__ uint32_t ty(int i) const { return (tw[i] >> 16) & 0xffu; }
+  __device__ __forceinline__ uint32_t tok(int i) const { return tw[i] & 0xffffu; }
+  __device__ __forceinline__ uint32_t id(int i) const { return (tw[i] >> 24) & 0x3fu; }
   __device__ __forceinline__ int next(int i) const {
-    const uint32_t b = ty[i];
+    const uint32_t b = ty(i);
     if (b == '{' || b == '[') return jmp[i] + 1;
     if (b == '"') return i + 2;
     return i + 1;
   }
   // member / element iteration: after value v, the next key or element (or the closing token)
-  __device__ __forceinline__ int after(int v) const { int nx = next(v); if (ty[nx] == ',') nx++; return nx; }
-  __device__ __forceinline__ uint32_t str_off(int i) const { return tok[i] + 1u; }
-  __device__ __forceinline__ uint32_t str_len(int i) const { return (uint32_t)tok[i + 1] - tok[i] - 1u; }
-  __device__ bool str_has_backslash(int i) const {
-    const uint8_t* p = s + str_off(i); const uint32_t n = str_len(i);
-    for (uint32_t k = 0; k < n; k++) if (p[k] == '\\') return true;
-    return false;
-  }
+  __device__ __forceinline__ int after(int v) const { int nx = next(v); if (ty(nx) == ',') nx++; return nx; }
+  __device__ __forceinline__ uint32_t str_off(int i) const { return tok(i) + 1u; }
+  __device__ __forceinline__ uint32_t str_len(int i) const { return tok(i + 1) - tok(i) - 1u; }
+  __device__ __forceinline__ bool str_has_backslash(int i) const { return (tw[i] >> 30) & 1u; }
   __device__ uint32_t scalar_end(int i) const {
-    uint32_t p = tok[i];
+    const uint32_t w = tw[i];
+    const uint32_t l = (w >> 24) & 0x3fu;
+    uint32_t p = w & 0xffffu;
+    if (l && l < 63u) return p + l;
     while (p < len) { const uint32_t c = s[p]; if (is_ws(c) || is_op(c) || c == '"') break; p++; }
     return p;
   }
@@ -155,10 +190,10 @@ __device__ int validate_tokens(Doc& d) {
   int i = 0;
   const int nt = d.nt;
   while (i < nt) {
-    const uint32_t b = d.ty[i];
+    const uint32_t b = d.ty(i);
     if (st == 6) return AIGW_R_SYNTAX;
     if (b == '"') {
-      if (i + 1 >= nt || d.ty[i + 1] != '"') return AIGW_R_SYNTAX;
+      if (i + 1 >= nt || d.ty(i + 1) != '"') return AIGW_R_SYNTAX;
       if (st == 1 || st == 2) st = 3;
       else if (st == 0 || st == 5) st = depth ? 4 : 6;
       else return AIGW_R_SYNTAX;
@@ -187,7 +222,7 @@ __device__ int validate_tokens(Doc& d) {
     }
     if (!(st == 0 || st == 5)) return AIGW_R_SYNTAX;
     const uint32_t e = d.scalar_end(i);
-    if (!scalar_valid(d.s + d.tok[i], e - d.tok[i])) return AIGW_R_SYNTAX;
+    if (!scalar_valid(d.s + d.tok(i), e - d.tok(i))) return AIGW_R_SYNTAX;
     st = depth ? 4 : 6; i++;
   }
   return st == 6 ? 0 : AIGW_R_SYNTAX;
@@ -292,8 +327,8 @@ __device__ int cmp_keys(const Doc& d, int a, int b) {
 }
 
 __device__ void emit_scalar_any(const Doc& d, Plan& pl, int vi, bool sys) {
-  const uint32_t c = d.ty[vi];
-  const uint32_t e = d.scalar_end(vi), o = d.tok[vi];
+  const uint32_t c = d.ty(vi);
+  const uint32_t e = d.scalar_end(vi), o = d.tok(vi);
   if (c == 't' || c == 'f' || c == 'n') { pl.src(d, o, e - o, sys); return; }
   const uint32_t l = canon_number(d.s + o, e - o, false);
   if (!l) { pl.err = AIGW_R_NUMBER; return; }
@@ -310,42 +345,42 @@ __device__ void emit_any(const Doc& d, Plan& pl, int root, bool sys = false) {
     if (pl.err) return;
     if (need_value) {
       need_value = false;
-      const uint32_t c = d.ty[vi];
-      if (c == '"') pl.src(d, d.tok[vi], (uint32_t)d.tok[vi + 1] - d.tok[vi] + 1u, sys);
+      const uint32_t c = d.ty(vi);
+      if (c == '"') pl.src(d, d.tok(vi), (uint32_t)d.tok(vi + 1) - d.tok(vi) + 1u, sys);
       else if (c == '[') {
-        pl.src(d, d.tok[vi], 1, sys);
-        if (d.ty[vi + 1] == ']') pl.src(d, d.tok[vi + 1], 1, sys);
+        pl.src(d, d.tok(vi), 1, sys);
+        if (d.ty(vi + 1) == ']') pl.src(d, d.tok(vi + 1), 1, sys);
         else {
           if (sp >= MAXF) { pl.err = AIGW_R_DEPTH; return; }
           f_open[sp] = vi; f_state[sp] = vi + 1; sp++;
           vi = vi + 1; need_value = true; continue;
         }
       } else if (c == '{') {
-        pl.src(d, d.tok[vi], 1, sys);
+        pl.src(d, d.tok(vi), 1, sys);
         if (sp >= MAXF) { pl.err = AIGW_R_DEPTH; return; }
         f_open[sp] = vi; f_state[sp] = -1; sp++;
       } else emit_scalar_any(d, pl, vi, sys);
     }
     if (sp == 0) return;
     const int open = f_open[sp - 1];
-    if (d.ty[open] == '[') {
+    if (d.ty(open) == '[') {
       const int nx = d.next(f_state[sp - 1]);
-      pl.src(d, d.tok[nx], 1, sys);  // ',' or ']'
-      if (d.ty[nx] == ',') { f_state[sp - 1] = nx + 1; vi = nx + 1; need_value = true; }
+      pl.src(d, d.tok(nx), 1, sys);  // ',' or ']'
+      if (d.ty(nx) == ',') { f_state[sp - 1] = nx + 1; vi = nx + 1; need_value = true; }
       else sp--;
     } else {
       const int last = f_state[sp - 1];
       int best = -1, cnt = 0;
-      for (int m = open + 1; d.ty[m] != '}'; m = d.after(m + 3)) {
+      for (int m = open + 1; d.ty(m) != '}'; m = d.after(m + 3)) {
         if (d.str_has_backslash(m)) { pl.err = AIGW_R_ESCAPE; return; }
         const int c1 = last < 0 ? 1 : cmp_keys(d, m, last);
         if (c1 == 0 && m != last) { pl.err = AIGW_R_DUP_KEY; return; }
         if (c1 > 0 && (best < 0 || cmp_keys(d, m, best) < 0)) best = m;
         if (++cnt > 64) { pl.err = AIGW_R_UNSUPPORTED_FIELD; return; }
       }
-      if (best < 0) { pl.src(d, d.tok[d.jmp[open]], 1, sys); sp--; continue; }
+      if (best < 0) { pl.src(d, d.tok(d.jmp[open]), 1, sys); sp--; continue; }
       if (last >= 0) pl.lit(L_COMMA, sys);
-      const uint32_t ko = d.tok[best], kc = d.tok[best + 1], colon = d.tok[best + 2];
+      const uint32_t ko = d.tok(best), kc = d.tok(best + 1), colon = d.tok(best + 2);
       if (colon == kc + 1u) pl.src(d, ko, colon + 1u - ko, sys);
       else { pl.src(d, ko, kc + 1u - ko, sys); pl.lit(L_COLON, sys); }
       f_state[sp - 1] = best;
@@ -356,14 +391,16 @@ __device__ void emit_any(const Doc& d, Plan& pl, int root, bool sys = false) {
 
 // Sequential tokenizer for a scratch-resident JSON text (tool-call arguments after unescaping).
 // `base` is added to every position.  Returns number of tokens, or -reason.
-__device__ int tokenize_seq(const uint8_t* s, uint32_t len, uint32_t base, uint16_t* tok, uint8_t* ty, int cap) {
+__device__ int tokenize_seq(const uint8_t* s, uint32_t len, uint32_t base, uint32_t* tw, int cap) {
   int nt = 0; uint32_t i = 0;
   while (i < len) {
     const uint32_t c = s[i];
     if (is_ws(c)) { i++; continue; }
     if (nt + 2 > cap) return -AIGW_R_TOKENS;
     if (c == '"') {
-      tok[nt] = (uint16_t)(base + i); ty[nt++] = '"'; i++;
+      const int open = nt;
+      tw[nt++] = (base + i) | ((uint32_t)'"' << 16); i++;
+      uint32_t esc = 0;
       for (;;) {
         if (i >= len) return -AIGW_R_SYNTAX;
         const uint32_t ch = s[i];
@@ -373,15 +410,18 @@ __device__ int tokenize_seq(const uint8_t* s, uint32_t len, uint32_t base, uint1
           if (i + 1 >= len) return -AIGW_R_SYNTAX;
           const uint32_t e = s[i + 1];
           if (!(e == '"' || e == '\\' || e == 'n' || e == 'r' || e == 't')) return -AIGW_R_ESCAPE;
-          i += 2; continue;
+          esc = 1; i += 2; continue;
         }
         i++;
       }
-      tok[nt] = (uint16_t)(base + i); ty[nt++] = '"'; i++; continue;
+      tw[open] |= esc << 30;
+      tw[nt++] = (base + i) | ((uint32_t)'"' << 16); i++; continue;
     }
-    tok[nt] = (uint16_t)(base + i); ty[nt++] = (uint8_t)c;
-    if (is_op(c)) { i++; continue; }
+    const uint32_t start = i;
+    if (is_op(c)) { tw[nt++] = (base + i) | (c << 16); i++; continue; }
     while (i < len && !is_ws(s[i]) && !is_op(s[i]) && s[i] != '"') i++;
+    const uint32_t l = i - start;
+    tw[nt++] = (base + start) | (c << 16) | ((l < 63u ? l : 63u) << 24);
   }
   return nt;
 }
@@ -391,27 +431,27 @@ struct Walker {
   Doc d;
   Plan pl;
   Scratch sc;
-  uint16_t* tok_tail; uint16_t* jmp_tail; uint8_t* ty_tail; int tail_cap;  // free token space for nested documents
+  uint32_t* tw_tail; uint16_t* jmp_tail; int tail_cap;  // free token space for nested documents
   const ChatParams* P;
   int reason;
 
   __device__ __forceinline__ void decline(int r) { if (!reason) reason = r; }
   __device__ __forceinline__ bool bad() const { return reason != 0 || pl.err != 0; }
 
-  __device__ __forceinline__ bool is_str(int v) const { return d.ty[v] == '"'; }
-  __device__ __forceinline__ bool is_obj(int v) const { return d.ty[v] == '{'; }
-  __device__ __forceinline__ bool is_arr(int v) const { return d.ty[v] == '['; }
-  __device__ __forceinline__ bool is_bool(int v) const { const uint32_t c = d.ty[v]; return c == 't' || c == 'f'; }
-  __device__ __forceinline__ bool is_num(int v) const { const uint32_t c = d.ty[v]; return c == '-' || is_digit(c); }
-  __device__ __forceinline__ bool is_null(int v) const { return d.ty[v] == 'n'; }
+  __device__ __forceinline__ bool is_str(int v) const { return d.ty(v) == '"'; }
+  __device__ __forceinline__ bool is_obj(int v) const { return d.ty(v) == '{'; }
+  __device__ __forceinline__ bool is_arr(int v) const { return d.ty(v) == '['; }
+  __device__ __forceinline__ bool is_bool(int v) const { const uint32_t c = d.ty(v); return c == 't' || c == 'f'; }
+  __device__ __forceinline__ bool is_num(int v) const { const uint32_t c = d.ty(v); return c == '-' || is_digit(c); }
+  __device__ __forceinline__ bool is_null(int v) const { return d.ty(v) == 'n'; }
 
-  __device__ __forceinline__ void emit_str(int v, bool sys = false) { pl.src(d, d.tok[v], (uint32_t)d.tok[v + 1] - d.tok[v] + 1u, sys); }
+  __device__ __forceinline__ void emit_str(int v, bool sys = false) { pl.src(d, d.tok(v), (uint32_t)d.tok(v + 1) - d.tok(v) + 1u, sys); }
 
   // value token of member `key` in object `obj`, -1 when absent or null; duplicates decline
   __device__ int find(int obj, uint32_t key) {
     int r = -1;
-    for (int m = obj + 1; d.ty[m] != '}'; m = d.after(m + 3)) {
-      if (d.id[m] == key) { if (r >= 0) { decline(AIGW_R_DUP_KEY); return -1; } r = m + 3; }
+    for (int m = obj + 1; d.ty(m) != '}'; m = d.after(m + 3)) {
+      if (d.id(m) == key) { if (r >= 0) { decline(AIGW_R_DUP_KEY); return -1; } r = m + 3; }
     }
     if (r >= 0 && is_null(r)) return -1;
     return r;
@@ -421,18 +461,18 @@ struct Walker {
     if (cc < 0) return false;
     if (!is_obj(cc)) { decline(AIGW_R_TYPE); return false; }
     int t = -1, ttl = -1;
-    for (int m = cc + 1; d.ty[m] != '}'; m = d.after(m + 3)) {
-      const uint32_t k = d.id[m];
+    for (int m = cc + 1; d.ty(m) != '}'; m = d.after(m + 3)) {
+      const uint32_t k = d.id(m);
       if (k == K_type) { if (t >= 0) { decline(AIGW_R_DUP_KEY); return false; } t = m + 3; }
       else if (k == K_ttl) { if (ttl >= 0) { decline(AIGW_R_DUP_KEY); return false; } ttl = m + 3; }
     }
     if (ttl >= 0 && !is_null(ttl) && !is_str(ttl)) { decline(AIGW_R_TYPE); return false; }
     if (t < 0 || is_null(t)) return false;
     if (!is_str(t)) { decline(AIGW_R_TYPE); return false; }
-    return d.id[t] == V_ephemeral;
+    return d.id(t) == V_ephemeral;
   }
   __device__ void emit_num_field(int v, bool integer) {
-    const uint32_t e = d.scalar_end(v), o = d.tok[v];
+    const uint32_t e = d.scalar_end(v), o = d.tok(v);
     if (!is_num(v)) { decline(AIGW_R_TYPE); return; }
     const uint32_t l = canon_number(d.s + o, e - o, integer);
     if (!l) { decline(AIGW_R_NUMBER); return; }
@@ -445,7 +485,7 @@ struct Walker {
     else if (kind == 1) ok = is_bool(v);
     else {
       ok = is_num(v);
-      if (ok && kind == 2) { const uint32_t e = d.scalar_end(v), o = d.tok[v]; ok = canon_number(d.s + o, e - o, true) != 0; if (!ok) { decline(AIGW_R_NUMBER); return false; } }
+      if (ok && kind == 2) { const uint32_t e = d.scalar_end(v), o = d.tok(v); ok = canon_number(d.s + o, e - o, true) != 0; if (!ok) { decline(AIGW_R_NUMBER); return false; } }
     }
     if (!ok) decline(AIGW_R_TYPE);
     return ok;
@@ -456,9 +496,9 @@ struct Walker {
   __device__ bool scan_part(int e, Part& p) {
     p.type = p.text = p.cache = p.refusal = p.signature = p.redacted = -1;
     uint32_t seen = 0;
-    for (int m = e + 1; d.ty[m] != '}'; m = d.after(m + 3)) {
+    for (int m = e + 1; d.ty(m) != '}'; m = d.after(m + 3)) {
       int slot;
-      switch (d.id[m]) { case K_type: slot = 0; break; case K_text: slot = 1; break; case K_cache_control: slot = 2; break; case K_refusal: slot = 3; break;
+      switch (d.id(m)) { case K_type: slot = 0; break; case K_text: slot = 1; break; case K_cache_control: slot = 2; break; case K_refusal: slot = 3; break;
         case K_signature: slot = 4; break; case K_redactedContent: slot = 5; break; default: slot = -1; }
       if (slot < 0) continue;
       if (seen & (1u << slot)) { decline(AIGW_R_DUP_KEY); return false; }
@@ -471,7 +511,7 @@ struct Walker {
 
   // text part list for system / developer / tool messages (ChatCompletionContentPartTextParam)
   __device__ void emit_text_parts(int arr, bool with_cache, bool sys, bool& first) {
-    for (int e = arr + 1; d.ty[e] != ']'; e = d.after(e)) {
+    for (int e = arr + 1; d.ty(e) != ']'; e = d.after(e)) {
       if (!is_obj(e)) { decline(AIGW_R_CONTENT); return; }
       Part p; if (!scan_part(e, p)) return;
       if ((p.text >= 0 && !is_str(p.text)) || (p.type >= 0 && !is_str(p.type))) { decline(AIGW_R_TYPE); return; }
@@ -491,10 +531,10 @@ struct Walker {
     g.role_v = g.content = g.name = g.tool_calls = g.tool_call_id = g.refusal = g.audio = -1;
     if (!is_obj(m)) { decline(AIGW_R_ROLE); return -1; }
     uint32_t seen = 0;
-    for (int k = m + 1; d.ty[k] != '}'; k = d.after(k + 3)) {
+    for (int k = m + 1; d.ty(k) != '}'; k = d.after(k + 3)) {
       const int v = k + 3;
       int which;
-      switch (d.id[k]) { case K_role: which = 0; break; case K_content: which = 1; break; case K_name: which = 2; break; case K_tool_calls: which = 3; break;
+      switch (d.id(k)) { case K_role: which = 0; break; case K_content: which = 1; break; case K_name: which = 2; break; case K_tool_calls: which = 3; break;
         case K_tool_call_id: which = 4; break; case K_refusal: which = 5; break; case K_audio: which = 6; break; default: which = -1; }
       if (which < 0) continue;
       if (seen & (1u << which)) { decline(AIGW_R_DUP_KEY); return -1; }
@@ -503,7 +543,7 @@ struct Walker {
         case 4: g.tool_call_id = v; break; case 5: g.refusal = v; break; case 6: g.audio = v; break; }
     }
     if (g.role_v < 0 || !is_str(g.role_v)) { decline(AIGW_R_ROLE); return -1; }
-    switch (d.id[g.role_v]) { case V_user: return 0; case V_assistant: return 1; case V_system: return 2; case V_developer: return 3; case V_tool: return 4; default: break; }
+    switch (d.id(g.role_v)) { case V_user: return 0; case V_assistant: return 1; case V_system: return 2; case V_developer: return 3; case V_tool: return 4; default: break; }
     decline(AIGW_R_ROLE); return -1;
   }
 
@@ -533,11 +573,11 @@ struct Walker {
       dst[w++] = (uint8_t)c;
     }
     const uint32_t base = sc.n; sc.n += (w + 1u) & ~1u;
-    const int nt = tokenize_seq(dst, w, base, tok_tail, ty_tail, tail_cap);
+    const int nt = tokenize_seq(dst, w, base, tw_tail, tail_cap);
     if (nt <= 0) { decline(nt == 0 ? AIGW_R_ARGS : -nt); return; }
-    Doc a; a.s = sc.p; a.len = base + w; a.tok = tok_tail; a.jmp = jmp_tail; a.ty = ty_tail; a.id = ty_tail; a.nt = nt; a.kind = 2;
+    Doc a; a.s = sc.p; a.len = base + w; a.tw = tw_tail; a.jmp = jmp_tail; a.nt = nt; a.kind = 2;
     if (validate_tokens(a)) { decline(AIGW_R_ARGS); return; }
-    const uint32_t c0 = a.ty[0];
+    const uint32_t c0 = a.ty(0);
     if (c0 == 'n') { pl.lit(L_NULL); return; }
     if (c0 != '{') { decline(AIGW_R_ARGS); return; }
     emit_any(a, pl, 0);
@@ -553,7 +593,7 @@ struct Walker {
     if (bad()) return;
     if (p.type < 0) return;  // type "" matches no case
     bool emitted = false;
-    const uint32_t ty = d.id[p.type];
+    const uint32_t ty = d.id(p.type);
     if (ty == V_text) { if (p.text >= 0) { if (!first) pl.lit(L_COMMA); first = false; pl.lit(L_TEXT_OPEN); emit_str(p.text); pl.lit(L_RBRACE); emitted = true; } }
     else if (ty == V_refusal) { if (p.refusal >= 0) { if (!first) pl.lit(L_COMMA); first = false; pl.lit(L_TEXT_OPEN); emit_str(p.refusal); pl.lit(L_RBRACE); emitted = true; } }
     else if (ty == V_thinking) {
@@ -573,7 +613,7 @@ struct Walker {
     const int c = g.content;
     if (c >= 0 && !is_null(c)) {
       if (is_str(c)) { if (d.str_len(c) > 0) { pl.lit(L_TEXT_OPEN); emit_str(c); pl.lit(L_RBRACE); first = false; } }
-      else if (is_arr(c)) { for (int e = c + 1; d.ty[e] != ']'; e = d.after(e)) { bedrock_asst_part(e, first); if (bad()) return; } }
+      else if (is_arr(c)) { for (int e = c + 1; d.ty(e) != ']'; e = d.after(e)) { bedrock_asst_part(e, first); if (bad()) return; } }
       else if (is_obj(c)) bedrock_asst_part(c, first);
       else { decline(AIGW_R_CONTENT); return; }
     }
@@ -583,7 +623,7 @@ struct Walker {
     const int tcs = g.tool_calls;
     if (tcs >= 0 && !is_null(tcs)) {
       if (!is_arr(tcs)) { decline(AIGW_R_TYPE); return; }
-      for (int e = tcs + 1; d.ty[e] != ']'; e = d.after(e)) {
+      for (int e = tcs + 1; d.ty(e) != ']'; e = d.after(e)) {
         if (!is_obj(e)) { decline(AIGW_R_TOOL); return; }
         const int id = find(e, K_id), fn = find(e, K_function), ty = find(e, K_type);
         (void)cache_enabled(find(e, K_cache_control));
@@ -617,10 +657,10 @@ struct Walker {
     if (!is_arr(c)) { decline(AIGW_R_CONTENT); return; }
     pl.lit(L_MSG_CONTENT_OPEN);
     bool first = true;
-    for (int e = c + 1; d.ty[e] != ']'; e = d.after(e)) {
+    for (int e = c + 1; d.ty(e) != ']'; e = d.after(e)) {
       if (!is_obj(e)) { decline(AIGW_R_CONTENT); return; }
       Part p; if (!scan_part(e, p)) return;
-      if (p.type < 0 || !is_str(p.type) || d.id[p.type] != V_text) { decline(AIGW_R_CONTENT); return; }  // images/audio/files: stock path
+      if (p.type < 0 || !is_str(p.type) || d.id(p.type) != V_text) { decline(AIGW_R_CONTENT); return; }  // images/audio/files: stock path
       if (p.text >= 0 && !is_str(p.text)) { decline(AIGW_R_TYPE); return; }
       const bool cache = cache_enabled(p.cache);
       if (bad()) return;
@@ -647,9 +687,9 @@ struct Walker {
     t.model = t.messages = t.temperature = t.top_p = t.max_tokens = t.mct = t.stop = t.stream = t.stream_options = t.tools = t.tool_choice = t.thinking = t.service_tier = -1;
     if (d.nt == 0 || !is_obj(0)) { decline(AIGW_R_ROOT); return false; }
     uint64_t seen = 0;
-    for (int k = 1; d.ty[k] != '}'; k = d.after(k + 3)) {
+    for (int k = 1; d.ty(k) != '}'; k = d.after(k + 3)) {
       const int v = k + 3;
-      const uint32_t id = d.id[k];
+      const uint32_t id = d.id(k);
       if (id == K_NONE || id >= K_TOP_END) continue;
       if (seen & (1ull << id)) { decline(AIGW_R_DUP_KEY); return false; }
       seen |= 1ull << id;
@@ -731,7 +771,7 @@ struct Walker {
       if (!is_obj(th)) { decline(AIGW_R_TYPE); return; }
       const int ty = find(th, K_type);
       if (ty < 0 || !is_str(ty)) { decline(AIGW_R_TYPE); return; }
-      const uint32_t tv = d.id[ty];
+      const uint32_t tv = d.id(ty);
       if (tv == V_enabled) {
         const int bt = find(th, K_budget_tokens), it = find(th, K_includeThoughts);
         if (it >= 0 && !is_bool(it)) { decline(AIGW_R_TYPE); return; }
@@ -751,10 +791,10 @@ struct Walker {
       const int s = t.stop;
       if (is_str(s)) { if (!f) pl.lit(L_COMMA); f = false; pl.lit(L_STOPSEQ); emit_str(s); pl.lit(L_RBRACK); }
       else if (is_arr(s)) {
-        if (d.ty[s + 1] != ']') {
+        if (d.ty(s + 1) != ']') {
           if (!f) pl.lit(L_COMMA); f = false; pl.lit(L_STOPSEQ);
           bool sf = true;
-          for (int e = s + 1; d.ty[e] != ']'; e = d.after(e)) { if (!is_str(e)) { decline(AIGW_R_TYPE); return; } if (!sf) pl.lit(L_COMMA); sf = false; emit_str(e); }
+          for (int e = s + 1; d.ty(e) != ']'; e = d.after(e)) { if (!is_str(e)) { decline(AIGW_R_TYPE); return; } if (!sf) pl.lit(L_COMMA); sf = false; emit_str(e); }
           pl.lit(L_RBRACK);
         }
       } else { decline(AIGW_R_TYPE); return; }
@@ -767,7 +807,7 @@ struct Walker {
     bool mfirst = true, sys_first = true;
     if (t.messages >= 0) {
       int e = t.messages + 1;
-      while (d.ty[e] != ']') {
+      while (d.ty(e) != ']') {
         Msg g; const int role = scan_message(e, g);
         if (bad()) return;
         int nx = d.after(e);
@@ -779,7 +819,7 @@ struct Walker {
           pl.lit(L_MSG_CONTENT_OPEN);
           bedrock_tool_result(g);
           if (bad()) return;
-          while (d.ty[nx] != ']') {  // coalesce the following tool messages (openai_awsbedrock.go:559-575)
+          while (d.ty(nx) != ']') {  // coalesce the following tool messages (openai_awsbedrock.go:559-575)
             Msg g2; const int r2 = scan_message(nx, g2);
             if (bad()) return;
             if (r2 != 4) break;
@@ -801,7 +841,7 @@ struct Walker {
     if (t.tool_choice >= 0) {
       const int tc = t.tool_choice;
       if (is_str(tc)) {
-        const uint32_t tv = d.id[tc];
+        const uint32_t tv = d.id(tc);
         if (tv == V_auto) tc_kind = 1;
         else if (tv == V_required) tc_kind = 2;
         else if (model_contains(t.model, "anthropic", 9) && model_contains(t.model, "claude", 6)) { tc_kind = 3; tc_name = tc; }
@@ -814,14 +854,14 @@ struct Walker {
       } else { decline(AIGW_R_TYPE); return; }
     }
     // tools (openai_awsbedrock.go:162-226)
-    if (t.tools >= 0 && d.ty[t.tools + 1] != ']') {
+    if (t.tools >= 0 && d.ty(t.tools + 1) != ']') {
       pl.lit(L_TOOLCFG_OPEN);
       if (tc_kind == 1) pl.lit(L_TOOLCHOICE_AUTO);
       else if (tc_kind == 2) pl.lit(L_TOOLCHOICE_ANY);
       else if (tc_kind == 3) { pl.lit(L_TOOLCHOICE_TOOL); if (tc_name >= 0) emit_str(tc_name); else pl.lit(L_EMPTY_STR); pl.lit(L_TOOLCHOICE_TOOL_END); }
       pl.lit(L_TOOLS_OPEN);
       bool tf = true;
-      for (int e = t.tools + 1; d.ty[e] != ']'; e = d.after(e)) {
+      for (int e = t.tools + 1; d.ty(e) != ']'; e = d.after(e)) {
         if (!is_obj(e)) { decline(AIGW_R_TOOL); return; }
         const int ty = find(e, K_type), fn = find(e, K_function), gs = find(e, K_google_search);
         if (ty >= 0 && !is_str(ty)) { decline(AIGW_R_TYPE); return; }
@@ -862,34 +902,37 @@ __device__ __forceinline__ uint4 lds16_unaligned(const uint8_t* p) {
 }
 
 // ------------------------------------------------------------------ the kernels
-// Three launches per sub-batch of documents, intermediates in a reusable global workspace:
-//   K1 index  (warp per document)    stage 1+2+2.5 → tok / ty / id arrays, token count
-//   K2 walk   (thread per document)  stage 3+4     → jump table, copy ops, scratch, plan header
-//   K3 emit   (warp per document)    stage 5       → output record + result
-// K2 is where SIMT pays: 32 structurally similar bodies share every instruction fetch.
+// Launch sequence per sub-batch of documents, intermediates in a reusable global workspace:
+//   K1 index   (warp per document)    stage 1+2+2.5 → token words, token count, histogram of token counts
+//   Ks sort    (tiny)                 counting sort of the documents by token count → permutation
+//   K2 walk    (thread per document)  stage 3+4 → jump table, copy ops, scratch, plan header
+//   K3 emit    (warp per document)    stage 5 → output record + result
+// K2 is where SIMT pays: 32 bodies with the same token count (≈ the same shape) share every instruction fetch.
 struct PlanOut { uint32_t nops, olen, path_len, model_off; uint16_t model_len; uint8_t flags, reason; };  // 20 bytes
+static constexpr int kBins = 1024;
 
 template <int MAXD>
 struct Work {  // per-document slots in the workspace
   using C = Cls<MAXD>;
-  static constexpr size_t kTokB = (size_t)C::kTok * 2, kJmpB = (size_t)C::kTok * 2, kTyB = C::kTok, kIdB = C::kTok;
+  static constexpr size_t kTwB = (size_t)C::kTok * 4, kJmpB = (size_t)C::kTok * 2;
   static constexpr size_t kOpsB = (size_t)(C::kOps + kSysCap) * 4, kScrB = C::kScr;
-  static constexpr size_t kPerDoc = kTokB + kJmpB + kTyB + kIdB + kOpsB + kScrB + 32;
+  static constexpr size_t kPerDoc = kTwB + kJmpB + kOpsB + kScrB + 32;
 };
 
-struct WorkPtrs { uint16_t* tok; uint16_t* jmp; uint8_t* ty; uint8_t* id; uint32_t* ops; uint8_t* scr; uint32_t* ntok; PlanOut* plan; };
+struct WorkPtrs { uint32_t* tw; uint16_t* jmp; uint32_t* ops; uint8_t* scr; uint32_t* ntok; PlanOut* plan; uint32_t* perm; uint32_t* bins; uint32_t* cursor; };
 
 template <int MAXD>
 __host__ __device__ inline WorkPtrs carve(uint8_t* base, size_t ndocs) {
   using W = Work<MAXD>;
   WorkPtrs w; uint8_t* p = base;
-  w.tok = (uint16_t*)p; p += W::kTokB * ndocs;
-  w.jmp = (uint16_t*)p; p += W::kJmpB * ndocs;
+  w.bins = (uint32_t*)p; p += kBins * 4;
+  w.cursor = (uint32_t*)p; p += kBins * 4;
+  w.tw = (uint32_t*)p; p += W::kTwB * ndocs;
   w.ops = (uint32_t*)p; p += W::kOpsB * ndocs;
   w.ntok = (uint32_t*)p; p += 4 * ndocs;
-  w.plan = (PlanOut*)p; p += 24 * ndocs;
-  w.ty = p; p += W::kTyB * ndocs;
-  w.id = p; p += W::kIdB * ndocs;
+  w.perm = (uint32_t*)p; p += 4 * ndocs;
+  w.plan = (PlanOut*)p; p += 20 * ndocs;
+  w.jmp = (uint16_t*)p; p += W::kJmpB * ndocs;
   w.scr = p;
   return w;
 }
@@ -907,12 +950,17 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
   using C = Cls<MAXD>;
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int kWarpBytes = C::kIn + C::kTok * 4;
-  uint8_t* wb = smem + (size_t)warp * kWarpBytes;
+  // CTA-shared tables: key/value id hash tables and the byte class LUT (0 scalar character, 1 whitespace, 2 structural)
+  IdTables* s_ids = (IdTables*)smem;
+  uint8_t* s_cls = smem + sizeof(IdTables);
+  for (uint32_t i = threadIdx.x; i < sizeof(IdTables) / 4; i += blockDim.x) ((uint32_t*)s_ids)[i] = ((const uint32_t*)&c_ids)[i];
+  for (uint32_t c = threadIdx.x; c < 256; c += blockDim.x) s_cls[c] = is_ws(c) ? 1 : is_op(c) ? 2 : (c == '"' ? 3 : 0);
+  __syncthreads();
+  constexpr int kWarpBytes = C::kIn + C::kTok * 6;
+  uint8_t* wb = smem + sizeof(IdTables) + 256 + (size_t)warp * kWarpBytes;
   uint8_t* s_in = wb;
-  uint16_t* s_tok = (uint16_t*)(wb + C::kIn);
-  uint8_t* s_ty = (uint8_t*)(s_tok + C::kTok);
-  uint8_t* s_id = s_ty + C::kTok;
+  uint32_t* s_tw = (uint32_t*)(wb + C::kIn);
+  uint16_t* s_bs = (uint16_t*)(s_tw + C::kTok);
   const WorkPtrs wp = carve<MAXD>(work, ndocs);
 
   for (;;) {
@@ -941,7 +989,7 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
     }
     // ---- stage 2: structural index
     uint32_t carry_esc = 0, carry_str = 0, carry_sc = 0;
-    uint32_t ntok = 0;
+    uint32_t ntok = 0, bs_run = 0;
     uint32_t flags = 0;  // bit0 ctrl in string, bit1 bad escape, bit2 token overflow
     for (uint32_t r = 0; r < rounds; r++) {
       const uint32_t base = (r << 10) + (lane << 5);
@@ -955,7 +1003,7 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
         mctl |= nib_from_ff(__vcmpltu4(w[j], 0x20202020u)) << (4 * j);
       }
       // escaped characters: odd-length backslash runs, carry across lanes
-      uint32_t esc = 0;
+      uint32_t esc = 0, bs_lane = 0;
       const uint32_t any_bs = __ballot_sync(FULL, mb != 0);
       if (any_bs | carry_esc) {
         const uint32_t tail = __clz(~mb);  // backslash run length at the top of this lane's 32 bytes
@@ -977,7 +1025,14 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
         const uint32_t seq_even = odd_starts + bs;  // carry-out handled through `tail`
         const uint32_t invert = seq_even << 1;
         esc = (even ^ invert) & follows;
-      }
+        // running backslash count in front of this lane (tokens remember it: a string has an escape iff the count moves)
+        const uint32_t pc = __popc(mb);
+        uint32_t incl = pc;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, sft); if (lane >= sft) incl += v; }
+        bs_lane = bs_run + incl - pc;
+        bs_run += __shfl_sync(FULL, incl, 31);
+      } else bs_lane = bs_run;
       const uint32_t uq = mq & ~esc;
       uint32_t ps = uq;
       ps ^= ps << 1; ps ^= ps << 2; ps ^= ps << 4; ps ^= ps << 8; ps ^= ps << 16;
@@ -991,15 +1046,18 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
         uint32_t e = esc & ps;
         while (e) { const int j = __ffs(e) - 1; e &= e - 1; const uint32_t c = s_in[base + j]; if (!(c == '"' || c == '\\' || c == 'n' || c == 'r' || c == 't')) flags |= 2u; }
       }
-      // bytes outside strings: classify sparsely
+      // bytes outside strings: classify sparsely through the LUT
       uint32_t mtok = uq, msc = 0;
       {
         uint32_t o = ~ps & ~uq;
         while (o) {
           const int j = __ffs(o) - 1; o &= o - 1;
           const uint32_t c = s_in[base + j];
-          if (is_ws(c)) continue;
-          if (is_op(c)) mtok |= 1u << j; else msc |= 1u << j;
+          // 128-bit bitmaps: whitespace {09,0A,0D,20}, structural {2C,3A,5B,5D,7B,7D}
+          const uint64_t lo = c < 64u, sel = 1ull << (c & 63u);
+          const bool ws_ = lo && (sel & 0x0000000100002600ull);
+          const bool op_ = c < 128u && (sel & (lo ? 0x0400100000000000ull : 0x2800000028000000ull));
+          if (op_) mtok |= 1u << j; else if (!ws_) msc |= 1u << j;
         }
       }
       {
@@ -1008,7 +1066,7 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
         carry_sc = __shfl_sync(FULL, msc >> 31, 31);
         mtok |= msc & ~((msc << 1) | prev);
       }
-      // compact token positions (+ the byte at each position)
+      // compact token words: position | byte
       const uint32_t cnt = __popc(mtok);
       uint32_t incl = cnt;
 #pragma unroll
@@ -1016,7 +1074,15 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
       const uint32_t total = __shfl_sync(FULL, incl, 31);
       uint32_t wpos = ntok + incl - cnt;
       if (ntok + total > (uint32_t)C::kTok) flags |= 4u;
-      else { uint32_t m = mtok; while (m) { const int j = __ffs(m) - 1; m &= m - 1; s_tok[wpos] = (uint16_t)(base + j); s_ty[wpos] = s_in[base + j]; wpos++; } }
+      else {
+        uint32_t m = mtok;
+        while (m) {
+          const int j = __ffs(m) - 1; m &= m - 1;
+          s_tw[wpos] = (base + j) | ((uint32_t)s_in[base + j] << 16);
+          s_bs[wpos] = (uint16_t)(bs_lane + __popc(mb & ((1u << j) - 1u)));
+          wpos++;
+        }
+      }
       ntok += total;
     }
     flags = __reduce_or_sync(FULL, flags);
@@ -1027,47 +1093,82 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
     else if (flags & 2u) reason = AIGW_R_ESCAPE;
     else if (carry_str) reason = AIGW_R_SYNTAX;
     if (reason) { if (lane == 0) wp.ntok[li] = 0x80000000u | (uint32_t)reason; continue; }
-    // ---- stage 2.5: key / value ids, one string token per lane.  Quote tokens alternate open/close,
-    // so the opening quotes are the quote tokens of even rank.
+    // ---- stage 2.5, one token per lane: strings get their key / value id and the escape flag (quote tokens alternate
+    // open/close, so opening quotes are the quote tokens of even rank); scalars get their length
     {
       uint32_t qbase = 0;
       for (uint32_t b0 = 0; b0 < ntok; b0 += 32) {
         const uint32_t i = b0 + lane;
-        const bool isq = i < ntok && s_ty[i] == '"';
+        uint32_t w = i < ntok ? s_tw[i] : 0u;
+        const uint32_t ty = (w >> 16) & 0xffu;
+        const bool isq = i < ntok && ty == '"';
         const uint32_t qm = __ballot_sync(FULL, isq);
-        uint32_t id = 0;
         if (isq) {
           const uint32_t rank = qbase + __popc(qm & ((1u << lane) - 1u));
           if ((rank & 1u) == 0 && i + 1 < ntok) {
-            const uint32_t o = (uint32_t)s_tok[i] + 1u, n = (uint32_t)s_tok[i + 1] - s_tok[i] - 1u;
-            const bool is_key = i + 2 < ntok && s_ty[i + 2] == ':';
-            id = is_key ? key_id(s_in + o, n) : val_id(s_in + o, n);
+            const uint32_t o = (w & 0xffffu) + 1u, n = (s_tw[i + 1] & 0xffffu) - o;
+            const uint32_t esc = s_bs[i + 1] != s_bs[i];
+            uint32_t id = 0;
+            if (!esc && n >= 1u && n <= (uint32_t)kMaxIdLen) {
+              const bool is_key = i + 2 < ntok && ((s_tw[i + 2] >> 16) & 0xffu) == ':';
+              id = lookup_id(s_ids, s_in + o, n, is_key);
+            }
+            w |= (id << 24) | (esc << 30);
           }
+        } else if (i < ntok && s_cls[ty] == 0) {
+          uint32_t p = w & 0xffffu, l = 0;
+          while (l < 63u && p + l < len && s_cls[s_in[p + l]] == 0) l++;
+          w |= l << 24;
         }
-        if (i < ntok) s_id[i] = (uint8_t)id;
+        __syncwarp();
+        if (i < ntok) s_tw[i] = w;
         qbase += __popc(qm);
       }
       __syncwarp();
     }
-    // ---- write the token arrays out, coalesced
+    // ---- write the token words out, coalesced; histogram of token counts for the shape sort
     {
-      uint16_t* gt = wp.tok + (size_t)li * C::kTok; uint8_t* gy = wp.ty + (size_t)li * C::kTok; uint8_t* gi = wp.id + (size_t)li * C::kTok;
-      const uint32_t nw2 = (ntok + 1) >> 1, nw4 = (ntok + 3) >> 2;
-      for (uint32_t i = lane; i < nw2; i += 32) ((uint32_t*)gt)[i] = ((const uint32_t*)s_tok)[i];
-      for (uint32_t i = lane; i < nw4; i += 32) { ((uint32_t*)gy)[i] = ((const uint32_t*)s_ty)[i]; ((uint32_t*)gi)[i] = ((const uint32_t*)s_id)[i]; }
+      uint32_t* gt = wp.tw + (size_t)li * C::kTok;
+      for (uint32_t i = lane; i < ntok; i += 32) gt[i] = s_tw[i];
       if (lane == 0) wp.ntok[li] = ntok;
     }
     __syncwarp();
   }
 }
 
-// ---- K2: validate + schema walk, one thread per document
-template <int MAXD>
-__global__ void __launch_bounds__(128) chat_walk_kernel(const __grid_constant__ ChatParams P, uint32_t doc0, uint32_t ndocs, uint8_t* work) {
-  using C = Cls<MAXD>;
+// ---- Ks: counting sort by token count (documents with the same count almost always have the same shape)
+__device__ __forceinline__ uint32_t bin_of(uint32_t w) { return (w & 0x80000000u) ? 0u : (w < (uint32_t)kBins ? w : (uint32_t)kBins - 1u); }
+__global__ void __launch_bounds__(1024) chat_hist_kernel(const uint32_t* ntok, uint32_t* bins, uint32_t ndocs) {
+  __shared__ uint32_t s[kBins];
+  s[threadIdx.x] = 0;
+  __syncthreads();
+  for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < ndocs; li += gridDim.x * blockDim.x) atomicAdd(&s[bin_of(ntok[li])], 1u);
+  __syncthreads();
+  if (s[threadIdx.x]) atomicAdd(&bins[threadIdx.x], s[threadIdx.x]);
+}
+__global__ void __launch_bounds__(1024) chat_scan_bins_kernel(const uint32_t* bins, uint32_t* cursor) {
+  __shared__ uint32_t s[kBins];
+  const int t = threadIdx.x;
+  const uint32_t v = bins[t];
+  s[t] = v;
+  __syncthreads();
+  for (int off = 1; off < kBins; off <<= 1) { const uint32_t x = t >= off ? s[t - off] : 0u; __syncthreads(); s[t] += x; __syncthreads(); }
+  cursor[t] = s[t] - v;
+}
+__global__ void __launch_bounds__(256) chat_scatter_kernel(const uint32_t* ntok, uint32_t* cursor, uint32_t* perm, uint32_t ndocs) {
   const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
   if (li >= ndocs) return;
+  perm[atomicAdd(&cursor[bin_of(ntok[li])], 1u)] = li;
+}
+
+// ---- K2: validate + schema walk, one thread per document
+template <int MAXD>
+__global__ void __launch_bounds__(128, AIGW_WALK_BLOCKS) chat_walk_kernel(const __grid_constant__ ChatParams P, uint32_t doc0, uint32_t ndocs, uint8_t* work) {
+  using C = Cls<MAXD>;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= ndocs) return;
   const WorkPtrs wp = carve<MAXD>(work, ndocs);
+  const uint32_t li = wp.perm[tid];  // shape-sorted order
   const uint32_t doc = doc0 + li;
   const uint32_t nt_word = wp.ntok[li];
   PlanOut po; po.nops = 0; po.olen = 0; po.path_len = 0; po.model_off = 0; po.model_len = 0; po.flags = 0; po.reason = 0;
@@ -1075,18 +1176,18 @@ __global__ void __launch_bounds__(128) chat_walk_kernel(const __grid_constant__ 
   const uint32_t ntok = nt_word;
   Walker W;
   W.d.s = P.bodies + P.offsets[doc]; W.d.len = P.lens[doc];
-  W.d.tok = wp.tok + (size_t)li * C::kTok; W.d.jmp = wp.jmp + (size_t)li * C::kTok; W.d.ty = wp.ty + (size_t)li * C::kTok; W.d.id = wp.id + (size_t)li * C::kTok;
+  W.d.tw = wp.tw + (size_t)li * C::kTok; W.d.jmp = wp.jmp + (size_t)li * C::kTok;
   W.d.nt = (int)ntok; W.d.kind = 0;
   W.pl.ops = wp.ops + (size_t)li * (C::kOps + kSysCap); W.pl.nops = 0; W.pl.nsys = 0; W.pl.cap = C::kOps; W.pl.clen = 0; W.pl.ckind = 0; W.pl.coff = 0; W.pl.olen = 0; W.pl.err = 0;
   W.sc.p = wp.scr + (size_t)li * C::kScr; W.sc.n = 0; W.sc.cap = C::kScr - 4;
-  W.tok_tail = (uint16_t*)W.d.tok + ntok; W.jmp_tail = W.d.jmp + ntok; W.ty_tail = (uint8_t*)W.d.ty + ntok; W.tail_cap = C::kTok - (int)ntok;
+  W.tw_tail = (uint32_t*)W.d.tw + ntok; W.jmp_tail = W.d.jmp + ntok; W.tail_cap = C::kTok - (int)ntok;
   W.P = &P; W.reason = 0;
   int reason = validate_tokens(W.d);
   uint32_t path_len = 0;
   if (!reason) {
     Walker::Top t;
     if (W.scan_top(t)) {
-      const bool stream = t.stream >= 0 && W.d.ty[t.stream] == 't';
+      const bool stream = t.stream >= 0 && W.d.ty(t.stream) == 't';
       if (t.model >= 0) { po.model_off = W.d.str_off(t.model); po.model_len = (uint16_t)W.d.str_len(t.model); }
       po.flags = stream ? 1u : 0u;
       if (P.schema == AIGW_SCHEMA_AWS_BEDROCK) W.plan_bedrock(t, stream, path_len);
@@ -1205,12 +1306,12 @@ __global__ void __launch_bounds__(WARPS * 32) chat_emit_kernel(const __grid_cons
 
 // ------------------------------------------------------------------ host-side launcher
 template <int MAXD>
-size_t work_bytes_cls(size_t ndocs) { return Work<MAXD>::kPerDoc * ndocs + 256; }
+size_t work_bytes_cls(size_t ndocs) { return Work<MAXD>::kPerDoc * ndocs + 2 * kBins * 4 + 256; }
 
 template <int MAXD, int WARPS>
 static cudaError_t launch_cls(const ChatParams& P, uint32_t first, int sm_count, cudaStream_t st, uint8_t* work, size_t work_cap, unsigned int* counters, cudaEvent_t* ev, int ev_cap) {
   using C = Cls<MAXD>;
-  const size_t smem1 = (size_t)(C::kIn + C::kTok * 4) * WARPS;
+  const size_t smem1 = sizeof(IdTables) + 256 + (size_t)(C::kIn + C::kTok * 6) * WARPS;
   const size_t smem3 = sizeof(LitTable::bytes) + (size_t)(C::kIn + C::kOps * 8 + ((C::kScr + 15) & ~15)) * WARPS;
   static bool configured = false;
   static int bps1 = 1, bps3 = 1;
@@ -1226,7 +1327,7 @@ static cudaError_t launch_cls(const ChatParams& P, uint32_t first, int sm_count,
     if (bps1 < 1) bps1 = 1; if (bps3 < 1) bps3 = 1;
     configured = true;
   }
-  size_t sub = work_cap / Work<MAXD>::kPerDoc;
+  size_t sub = (work_cap - 2 * kBins * 4 - 256) / Work<MAXD>::kPerDoc;
   if (sub > 262144) sub = 262144;
   if (sub == 0) return cudaErrorMemoryAllocation;
   int ci = 0;
@@ -1235,6 +1336,8 @@ static cudaError_t launch_cls(const ChatParams& P, uint32_t first, int sm_count,
     const uint32_t nd = (uint32_t)(P.n - rel < sub ? P.n - rel : sub);
     unsigned int* c1 = counters + (ci++ & 63); unsigned int* c3 = counters + (ci++ & 63);
     cudaMemsetAsync(c1, 0, 4, st); cudaMemsetAsync(c3, 0, 4, st);
+    const WorkPtrs wp = carve<MAXD>(work, nd);
+    cudaMemsetAsync(wp.bins, 0, kBins * 4, st);
     long long want = ((long long)nd + WARPS - 1) / WARPS;
     long long g1 = (long long)sm_count * bps1; if (want < g1) g1 = want;
     long long g3 = (long long)sm_count * bps3; if (want < g3) g3 = want;
@@ -1243,6 +1346,9 @@ static cudaError_t launch_cls(const ChatParams& P, uint32_t first, int sm_count,
     if (timed) cudaEventRecord(ev[4 * sb + 0], st);
     chat_index_kernel<MAXD, WARPS><<<(unsigned)g1, WARPS * 32, smem1, st>>>(P, doc0, nd, work, c1);
     if (timed) cudaEventRecord(ev[4 * sb + 1], st);
+    chat_hist_kernel<<<(nd + 16383) / 16384 < 64 ? (nd + 16383) / 16384 : 64, kBins, 0, st>>>(wp.ntok, wp.bins, nd);
+    chat_scan_bins_kernel<<<1, kBins, 0, st>>>(wp.bins, wp.cursor);
+    chat_scatter_kernel<<<(nd + 255) / 256, 256, 0, st>>>(wp.ntok, wp.cursor, wp.perm, nd);
     chat_walk_kernel<MAXD><<<(nd + 127) / 128, 128, 0, st>>>(P, doc0, nd, work);
     if (timed) cudaEventRecord(ev[4 * sb + 2], st);
     chat_emit_kernel<MAXD, WARPS><<<(unsigned)g3, WARPS * 32, smem3, st>>>(P, doc0, nd, work, c3);
@@ -1268,7 +1374,7 @@ cudaError_t launch_chat_translate_range(const ChatParams& P, uint32_t first, uin
 
 cudaError_t launch_chat_translate(const ChatParams& P, uint32_t max_len, int sm_count, cudaStream_t st, uint8_t* work, size_t work_cap, unsigned int* counters, int* launches,
                                   cudaEvent_t* ev, int ev_cap, uint32_t first) {
-  if (launches) { size_t per = chat_work_bytes(max_len, 1) - 256; size_t sub = work_cap / per; if (sub > 262144) sub = 262144; if (sub == 0) sub = 1; *launches = 3 * (int)((P.n + sub - 1) / sub); }
+  if (launches) { size_t per = chat_work_bytes(max_len, 1) - 256 - 2 * kBins * 4; size_t sub = (work_cap - 2 * kBins * 4 - 256) / per; if (sub > 262144) sub = 262144; if (sub == 0) sub = 1; *launches = 6 * (int)((P.n + sub - 1) / sub); }
   if (max_len <= 2048) return launch_cls<2048, 4>(P, first, sm_count, st, work, work_cap, counters, ev, ev_cap);
   if (max_len <= 5120) return launch_cls<5120, 4>(P, first, sm_count, st, work, work_cap, counters, ev, ev_cap);
   if (max_len <= 9216) return launch_cls<9216, 2>(P, first, sm_count, st, work, work_cap, counters, ev, ev_cap);

@@ -159,7 +159,7 @@ int aigw_chat_translate_device(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const
   if (kernel_ms) {
     CK(cudaEventRecord(ctx->ev1, st)); CK(cudaEventSynchronize(ctx->ev1)); CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
     ctx->stage_ms[0] = ctx->stage_ms[1] = ctx->stage_ms[2] = 0;
-    const int nsb = ctx->last_launches / 3;
+    const int nsb = ctx->last_launches / 6;
     for (int sb = 0; sb < nsb && 4 * sb + 3 < 64; sb++) for (int k = 0; k < 3; k++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->stage_ev[4 * sb + k], ctx->stage_ev[4 * sb + k + 1]); ctx->stage_ms[k] += ms; }
   }
   return 0;
