@@ -13,7 +13,7 @@
 namespace aigw {
 
 __device__ __constant__ LitTable c_lits = make_lit_table();
-static_assert(make_lit_table().off[L_COUNT] + 8 <= sizeof(LitTable::bytes), "literal table overflow (keep slack for unaligned reads)");
+static_assert(make_lit_table().off[L_COUNT] + 24 <= sizeof(LitTable::bytes), "literal table overflow (keep slack for unaligned reads)");
 
 #define FULL 0xffffffffu
 #ifndef AIGW_WALK_BLOCKS
@@ -238,6 +238,7 @@ struct Plan {
   uint32_t ckind, coff, clen;  // clen == 0 ⇒ nothing pending
   uint32_t olen;
   int err;
+  bool dry;  // validate only: count nothing, store nothing
 
   __device__ __forceinline__ void flush() {
     if (clen) {
@@ -247,6 +248,7 @@ struct Plan {
     }
   }
   __device__ void push(uint32_t kind, uint32_t off, uint32_t len) {
+    if (dry) return;
     olen += len;
     if (clen && kind == ckind && coff + clen == off && clen + len <= 16383u) { clen += len; return; }
     while (len) {
@@ -257,6 +259,7 @@ struct Plan {
     }
   }
   __device__ void push_sys(uint32_t kind, uint32_t off, uint32_t len) {
+    if (dry) { nsys = 1; return; }
     while (len) {
       const uint32_t l = len < 16383u ? len : 16383u;
       if (nsys >= kSysCap) { err = AIGW_R_OPS; return; }
@@ -272,6 +275,7 @@ struct Plan {
     if (sys) push_sys(d.kind, off, len); else push(d.kind, off, len);
   }
   __device__ void flush_sys() {
+    if (dry) { nsys = 0; return; }
     for (int k = 0; k < nsys; k++) { const uint32_t p = ops[cap + k]; push(p >> 30, p & 0xffffu, (p >> 16) & 0x3fffu); }
     nsys = 0;
   }
@@ -680,11 +684,12 @@ struct Walker {
     else decline(AIGW_R_CONTENT);
   }
 
-  struct Top { int model, messages, temperature, top_p, max_tokens, mct, stop, stream, stream_options, tools, tool_choice, thinking, service_tier; };
+  struct Top { int model, messages, temperature, top_p, max_tokens, mct, stop, stream, stream_options, tools, tool_choice, thinking, service_tier;
+               int model_raw, so_raw; /* value tokens even when null; -1 when the key is absent */ };
 
   // top-level member scan with type checks for every known field (endpointspec.go:102-105)
   __device__ bool scan_top(Top& t) {
-    t.model = t.messages = t.temperature = t.top_p = t.max_tokens = t.mct = t.stop = t.stream = t.stream_options = t.tools = t.tool_choice = t.thinking = t.service_tier = -1;
+    t.model = t.messages = t.temperature = t.top_p = t.max_tokens = t.mct = t.stop = t.stream = t.stream_options = t.tools = t.tool_choice = t.thinking = t.service_tier = t.model_raw = t.so_raw = -1;
     if (d.nt == 0 || !is_obj(0)) { decline(AIGW_R_ROOT); return false; }
     uint64_t seen = 0;
     for (int k = 1; d.ty(k) != '}'; k = d.after(k + 3)) {
@@ -693,6 +698,7 @@ struct Walker {
       if (id == K_NONE || id >= K_TOP_END) continue;
       if (seen & (1ull << id)) { decline(AIGW_R_DUP_KEY); return false; }
       seen |= 1ull << id;
+      if (id == K_model) t.model_raw = v; else if (id == K_stream_options) t.so_raw = v;
       if (is_null(v)) continue;
       switch (id) {
         case K_model: t.model = v; break; case K_messages: t.messages = v; break; case K_max_tokens: t.max_tokens = v; break; case K_max_completion_tokens: t.mct = v; break;
@@ -888,6 +894,82 @@ struct Walker {
     }
     pl.lit(L_RBRACE);
   }
+
+  // ---- OpenAI → OpenAI passthrough (openai_openai.go:55-84) on top of ParseBody's forced include_usage
+  // (endpointspec.go:107-123).  Edits follow tidwall/sjson `set`: an existing value is spliced in place, a missing key is
+  // appended before the closing brace of the deepest existing object, and a rebuilt root loses the bytes outside its braces.
+  __device__ void plan_passthrough(const Top& t, bool stream, uint32_t& path_len, uint32_t& out_flags, uint32_t& body_kind) {
+    // validation = the Bedrock walk with the plan in dry mode (its accept set ⊆ ParseBody's)
+    { uint32_t pl0 = 0; pl.dry = true; plan_bedrock(t, stream, pl0); pl.dry = false; pl.nsys = 0; sc.n = 0; }
+    if (bad()) return;
+    // ":path" = path.Join("/", prefix, "chat/completions")
+    {
+      const uint32_t n = P->prefix_len;
+      if (sc.n + n + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
+      for (uint32_t i = 0; i < n; i++) sc.p[sc.n + i] = (uint8_t)P->openai_path[i];
+      pl.push(2, sc.n, n); sc.n += (n + 1u) & ~1u;
+    }
+    path_len = pl.olen;
+    // which edits?
+    bool inc_true = false; int iu_raw = -1;
+    if (t.stream_options >= 0) {
+      for (int m = t.stream_options + 1; d.ty(m) != '}'; m = d.after(m + 3)) if (d.id(m) == K_include_usage) { iu_raw = m + 3; break; }
+      inc_true = iu_raw >= 0 && d.ty(iu_raw) == 't';
+    }
+    const bool need_usage = stream && P->cost_configured && !inc_true;
+    const bool need_model = P->override_len != 0;
+    if (need_model) for (uint32_t i = 0; i < P->override_len; i++) { const uint32_t c = (uint8_t)P->override_model[i]; if (c < 0x20 || c > 0x7f || c == '"' || c == '\\') { decline(AIGW_R_UNSUPPORTED_FIELD); return; } }
+    if (need_usage) out_flags |= 2u;
+    if (!need_usage && !need_model) {
+      if (P->force_mutation) { pl.src(d, 0, d.len); body_kind = AIGW_BODY_BYTES; } else body_kind = AIGW_BODY_UNCHANGED;
+      return;
+    }
+    body_kind = AIGW_BODY_BYTES;
+    const int root_close = d.jmp[0];
+    const bool root_empty = root_close == 1;
+    // edit A (usage) and edit B (model): [a_b, a_e) replaced or insertion at a_b == a_e
+    uint32_t a_b = 0xffffffffu, a_e = 0; int a_kind = 0;  // 1 replace with true, 2 append member in stream_options, 3 replace with object, 4 append at root
+    bool a_comma = false;
+    if (need_usage) {
+      if (iu_raw >= 0) { a_kind = 1; a_b = d.tok(iu_raw); a_e = d.scalar_end(iu_raw); }
+      else if (t.stream_options >= 0) { a_kind = 2; const int cl = d.jmp[t.stream_options]; a_b = a_e = d.tok(cl); a_comma = cl != t.stream_options + 1; }
+      else if (t.so_raw >= 0) { a_kind = 3; a_b = d.tok(t.so_raw); a_e = d.scalar_end(t.so_raw); }
+      else { a_kind = 4; a_b = a_e = d.tok(root_close); a_comma = !root_empty; }
+    }
+    uint32_t b_b = 0xffffffffu, b_e = 0; int b_kind = 0;  // 1 replace value, 2 append at root
+    if (need_model) {
+      if (t.model_raw >= 0) { b_kind = 1; b_b = d.tok(t.model_raw); b_e = is_str(t.model_raw) ? d.tok(t.model_raw + 1) + 1u : d.scalar_end(t.model_raw); }
+      else { b_kind = 2; b_b = b_e = d.tok(root_close); }
+    }
+    const bool drop_outside = a_kind == 4 || b_kind == 2;
+    uint32_t cur = drop_outside ? d.tok(0) : 0u;
+    const uint32_t end = drop_outside ? d.tok(root_close) + 1u : d.len;
+    // override literal into scratch
+    uint32_t ov_off = 0;
+    if (need_model) {
+      const uint32_t n = P->override_len;
+      if (sc.n + n + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
+      ov_off = sc.n; for (uint32_t i = 0; i < n; i++) sc.p[sc.n + i] = (uint8_t)P->override_model[i];
+      sc.n += (n + 1u) & ~1u;
+    }
+    for (int pass = 0; pass < 2; pass++) {
+      // the earlier edit first; at equal positions (both root appends) usage goes first, as in the reference's call order
+      const bool do_a = pass == 0 ? (a_kind && (!b_kind || a_b <= b_b)) : (a_kind && b_kind && a_b > b_b);
+      const bool do_b = pass == 0 ? (b_kind && !do_a) : (b_kind && a_kind && a_b <= b_b);
+      if (do_a) {
+        pl.src(d, cur, a_b - cur); cur = a_e;
+        if (a_kind == 1) pl.lit(L_TRUE);
+        else if (a_kind == 2) { if (a_comma) pl.lit(L_COMMA); pl.lit(L_INCLUDE_USAGE_MEMBER); }
+        else if (a_kind == 3) pl.lit(L_INCLUDE_USAGE_OBJ);
+        else { if (a_comma) pl.lit(L_COMMA); pl.lit(L_STREAMOPT_APPEND); }
+      } else if (do_b) {
+        pl.src(d, cur, b_b - cur); cur = b_e;
+        if (b_kind == 2) { if (!root_empty || a_kind == 4) pl.lit(L_COMMA); pl.lit(L_MODEL_MEMBER); }
+        pl.lit(L_QUOTE); pl.push(2, ov_off, P->override_len); pl.lit(L_QUOTE);
+      }
+    }
+    pl.src(d, cur, end - cur);
+  }
 };
 
 // 16 bytes starting at an arbitrary shared-memory address (buffers carry ≥ 4 bytes of slack)
@@ -995,12 +1077,16 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
       const uint32_t base = (r << 10) + (lane << 5);
       const uint4 a = *(const uint4*)(s_in + base), b = *(const uint4*)(s_in + base + 16);
       const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-      uint32_t mq = 0, mb = 0, mctl = 0;
+      uint32_t mq = 0, mb = 0, mctl = 0, anyctl = 0;
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         mq |= nib_from_ff(__vcmpeq4(w[j], 0x22222222u)) << (4 * j);
         mb |= nib_from_ff(__vcmpeq4(w[j], 0x5c5c5c5cu)) << (4 * j);
-        mctl |= nib_from_ff(__vcmpltu4(w[j], 0x20202020u)) << (4 * j);
+        anyctl |= __vcmpltu4(w[j], 0x20202020u);
+      }
+      if (anyctl) {  // rare in compact JSON: build the full mask only then
+#pragma unroll
+        for (int j = 0; j < 8; j++) mctl |= nib_from_ff(__vcmpltu4(w[j], 0x20202020u)) << (4 * j);
       }
       // escaped characters: odd-length backslash runs, carry across lanes
       uint32_t esc = 0, bs_lane = 0;
@@ -1178,8 +1264,8 @@ __global__ void __launch_bounds__(128, AIGW_WALK_BLOCKS) chat_walk_kernel(const 
   W.d.s = P.bodies + P.offsets[doc]; W.d.len = P.lens[doc];
   W.d.tw = wp.tw + (size_t)li * C::kTok; W.d.jmp = wp.jmp + (size_t)li * C::kTok;
   W.d.nt = (int)ntok; W.d.kind = 0;
-  W.pl.ops = wp.ops + (size_t)li * (C::kOps + kSysCap); W.pl.nops = 0; W.pl.nsys = 0; W.pl.cap = C::kOps; W.pl.clen = 0; W.pl.ckind = 0; W.pl.coff = 0; W.pl.olen = 0; W.pl.err = 0;
-  W.sc.p = wp.scr + (size_t)li * C::kScr; W.sc.n = 0; W.sc.cap = C::kScr - 4;
+  W.pl.ops = wp.ops + (size_t)li * (C::kOps + kSysCap); W.pl.nops = 0; W.pl.nsys = 0; W.pl.cap = C::kOps; W.pl.clen = 0; W.pl.ckind = 0; W.pl.coff = 0; W.pl.olen = 0; W.pl.err = 0; W.pl.dry = false;
+  W.sc.p = wp.scr + (size_t)li * C::kScr; W.sc.n = 0; W.sc.cap = C::kScr - 20;
   W.tw_tail = (uint32_t*)W.d.tw + ntok; W.jmp_tail = W.d.jmp + ntok; W.tail_cap = C::kTok - (int)ntok;
   W.P = &P; W.reason = 0;
   int reason = validate_tokens(W.d);
@@ -1191,6 +1277,7 @@ __global__ void __launch_bounds__(128, AIGW_WALK_BLOCKS) chat_walk_kernel(const 
       if (t.model >= 0) { po.model_off = W.d.str_off(t.model); po.model_len = (uint16_t)W.d.str_len(t.model); }
       po.flags = stream ? 1u : 0u;
       if (P.schema == AIGW_SCHEMA_AWS_BEDROCK) W.plan_bedrock(t, stream, path_len);
+      else if (P.schema == AIGW_SCHEMA_OPENAI) { uint32_t fl = po.flags, bk = AIGW_BODY_BYTES; W.plan_passthrough(t, stream, path_len, fl, bk); po.flags = (uint8_t)(fl | (bk == AIGW_BODY_UNCHANGED ? 0x80u : 0u)); }
       else W.decline(AIGW_R_SCHEMA);
     }
     W.pl.flush();
@@ -1283,21 +1370,43 @@ __global__ void __launch_bounds__(WARPS * 32) chat_emit_kernel(const __grid_cons
         uint4 v;
         if (l - within >= 16u) v = lds16_unaligned(sp + within);
         else {
-          uint32_t wv[4] = {0, 0, 0, 0};
-          for (int b = 0; b < 16; b++) {
-            while (within >= l && k + 1 < nops) { k++; op = s_ops[k]; kind = op >> 30; l = (op >> 16) & 0x3fffu; off = op & 0xffffu; within = 0; sp = (kind == 0 ? s_in : kind == 1 ? s_lits : s_scr) + off; }
-            uint32_t byte = 0;
-            if (within < l) { byte = sp[within]; within++; }
-            wv[b >> 2] |= byte << ((b & 3) * 8);
+          // the chunk straddles op boundaries: OR together one shifted, masked 16-byte read per overlapping op
+          v = make_uint4(0, 0, 0, 0);
+          uint32_t filled = 0;
+          for (;;) {
+            if (within >= l) {
+              if (++k >= nops) break;
+              op = s_ops[k]; kind = op >> 30; l = (op >> 16) & 0x3fffu; off = op & 0xffffu; within = 0;
+              sp = (kind == 0 ? s_in : kind == 1 ? s_lits : s_scr) + off;
+              continue;
+            }
+            const uint32_t take = min(l - within, 16u - filled);
+            uint4 x = lds16_unaligned(sp + within);
+            {  // keep the first `take` bytes
+              const uint32_t t0 = take, t1 = take > 4u ? take - 4u : 0u, t2 = take > 8u ? take - 8u : 0u, t3 = take > 12u ? take - 12u : 0u;
+              x.x &= t0 >= 4u ? 0xffffffffu : ((1u << (8u * t0)) - 1u);
+              x.y &= t1 >= 4u ? 0xffffffffu : ((1u << (8u * t1)) - 1u);
+              x.z &= t2 >= 4u ? 0xffffffffu : ((1u << (8u * t2)) - 1u);
+              x.w &= t3 >= 4u ? 0xffffffffu : ((1u << (8u * t3)) - 1u);
+            }
+            {  // shift left by `filled` bytes (128-bit) and merge
+              const uint32_t bsh = (filled & 3u) * 8u, wsh = filled >> 2;
+              const uint32_t r0 = x.x << bsh, r1 = __funnelshift_l(x.x, x.y, bsh), r2 = __funnelshift_l(x.y, x.z, bsh), r3 = __funnelshift_l(x.z, x.w, bsh);
+              if (wsh == 0) { v.x |= r0; v.y |= r1; v.z |= r2; v.w |= r3; }
+              else if (wsh == 1) { v.y |= r0; v.z |= r1; v.w |= r2; }
+              else if (wsh == 2) { v.z |= r0; v.w |= r1; }
+              else v.w |= r0;
+            }
+            filled += take; within += take;
+            if (filled >= 16u) break;
           }
-          v.x = wv[0]; v.y = wv[1]; v.z = wv[2]; v.w = wv[3];
         }
         o4[c] = v;
       }
     }
     if (lane == 0) {
       res.out_off = obase + P.out_bias; res.body_len = olen - po.path_len; res.path_len = (uint16_t)po.path_len; res.status = AIGW_OK; res.reason = 0;
-      res.model_off = po.model_off; res.model_len = po.model_len; res.body_kind = AIGW_BODY_BYTES; res.flags = po.flags;
+      res.model_off = po.model_off; res.model_len = po.model_len; res.body_kind = (po.flags & 0x80u) ? AIGW_BODY_UNCHANGED : AIGW_BODY_BYTES; res.flags = po.flags & 0x7fu;
       P.results[doc] = res;
     }
     __syncwarp();

@@ -83,6 +83,42 @@ def test_diverse_corpus(ctx):
     assert accepted > len(bodies) // 3
 
 
+def test_reference_goldens_passthrough(ctx):
+    """OpenAI-schema goldens (testupstream_test.go:266,383,1617,1635,1653,1671): passthrough, model override, forced include_usage."""
+    import aigw_b200 as A
+    cases = [c for c in json.load(open(os.path.join(G, "testupstream_cases.json"), encoding="utf-8"))["cases"]
+             if c.get("backend") in ("openai", "modelname-override") and "expRequestBody" in c and c.get("path", "/v1/chat/completions") == "/v1/chat/completions"]
+    assert len(cases) >= 5
+    for c in cases:
+        ov = "override-model" if c["backend"] == "modelname-override" else None
+        g = ctx.chat_translate(ctx.cfg("openai", model_override=ov, cost_configured=True), [c["requestBody"].encode()])[0]
+        assert g["status"] == A.AIGW_OK, (c["name"], g["reason"])
+        got = g["body"] if g["body_kind"] == 1 else c["requestBody"].encode()
+        assert got == c["expRequestBody"].encode(), c["name"]
+        assert g["path"] == b"/v1/chat/completions"
+
+
+@pytest.mark.parametrize("override,cost,force", [(None, False, False), ("override-model", False, False), (None, True, False), ("ovr", True, False), (None, False, True)])
+def test_passthrough_parity(ctx, override, cost, force):
+    import aigw_b200 as A
+    arena, offs, lens = W.chat_corpus(2, 5000, 600)
+    bodies = [bytes(arena[int(offs[i]):int(offs[i]) + int(lens[i])]) for i in range(len(lens))] + [W.diverse_body(s) for s in range(1500)]
+    bodies += [b'{}', b' {"model":"m"} ', b'{"stream":true}', b'  {"stream":true,"stream_options":null}\n', b'{"stream":true,"stream_options":{}}', b'{"stream":true,"stream_options":{"x":1}}',
+               b'{"model":null,"stream":true,"stream_options":{"include_usage":null}}', b'{"messages":[],"stream":true,"stream_options":{"include_usage":true}}']
+    cfg = ctx.cfg("openai", model_override=override, cost_configured=cost, force=force)
+    got = ctx.chat_translate(cfg, bodies)
+    n_ok = 0
+    for i, (b, g) in enumerate(zip(bodies, got)):
+        o = O.chat_translate("openai", b, model_override=override or "", cost_configured=cost, force=force)
+        if g["status"] == A.AIGW_OK:
+            n_ok += 1
+            assert o.status == O.OK, (i, b[:200], o.err)
+            assert g["body_kind"] == o.body_kind, (i, b[:200], g["body_kind"], o.body_kind)
+            assert g["body"] == (o.body if o.body_kind == O.BYTES else b""), (i, b[:300], g["body"][:300], o.body[:300])
+            assert g["path"].decode() == o.path and g["model"] == o.model and g["stream"] == o.stream
+    assert n_ok > 600
+
+
 def test_model_override_path(ctx):
     bodies = [b'{"model":"gpt-4o","messages":[{"role":"user","content":"hi"}],"stream":true}',
               b'{"messages":[{"role":"user","content":"no model"}]}']
