@@ -19,7 +19,7 @@ assert SseResult.itemsize == 48
 
 EXPORTS = ["aigw_version", "aigw_init", "aigw_destroy", "aigw_last_error", "aigw_device_sm_count", "aigw_host_alloc", "aigw_host_free",
            "aigw_device_alloc", "aigw_device_free", "aigw_memcpy_h2d", "aigw_memcpy_d2h", "aigw_memset_d", "aigw_sync",
-           "aigw_chat_translate_device", "aigw_chat_last_profile", "aigw_chat_translate_host", "aigw_sse_usage_device", "aigw_sse_usage_host"]
+           "aigw_chat_translate_device", "aigw_chat_last_profile", "aigw_chat_translate_host", "aigw_sse_usage_device", "aigw_sse_usage_host", "aigw_response_usage_device", "aigw_response_usage_host", "aigw_usage_costs_device"]
 
 
 class BackendCfg(C.Structure):
@@ -66,6 +66,9 @@ def load_library():
     L.aigw_sse_usage_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
     L.aigw_sse_usage_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64),
                                       C.POINTER(C.c_uint64), C.POINTER(C.c_float)]
+    L.aigw_response_usage_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.aigw_response_usage_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    L.aigw_usage_costs_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -194,6 +197,15 @@ class Context:
         self._check(self.L.aigw_sse_usage_host(self.h, bytes_arr.ctypes.data, chunk_off.ctypes.data, chunk_first.ctypes.data, n_streams, n_chunks,
                                                res.ctypes.data, C.byref(h2d), C.byref(d2h), C.byref(ms)), "sse_usage_host")
         return res, {"h2d_bytes": h2d.value, "d2h_bytes": d2h.value, "kernel_ms": ms.value}
+
+    def response_usage_host(self, arena, offs, lens, cost_types=()):
+        n = len(lens)
+        res = np.zeros(n, dtype=SseResult)
+        ct = np.array(cost_types, dtype=np.int32)
+        costs = np.zeros((n, max(1, len(ct))), dtype=np.uint64)
+        self._check(self.L.aigw_response_usage_host(self.h, arena.ctypes.data, offs.ctypes.data, lens.ctypes.data, n, res.ctypes.data,
+                                                    ct.ctypes.data if len(ct) else None, len(ct), costs.ctypes.data if len(ct) else None), "response_usage_host")
+        return res, costs[:, :len(ct)]
 
     def sse_usage_device(self, d_bytes, d_chunk_off, d_chunk_first, n_streams, d_res, timed=True):
         ms = C.c_float(0)

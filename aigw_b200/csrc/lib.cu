@@ -304,4 +304,46 @@ int aigw_sse_usage_host(aigw_ctx* ctx, const uint8_t* bytes, const uint64_t* chu
   return 0;
 }
 
+// ------------------------------------------------------------------ R1 + C2
+int aigw_response_usage_device(aigw_ctx* ctx, const uint8_t* d_bodies, const uint64_t* d_offsets, const uint32_t* d_lens, uint32_t n,
+                               aigw_sse_result* d_results, void* stream, float* kernel_ms) {
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->s_compute;
+  if (kernel_ms) CK(cudaEventRecord(ctx->ev0, st));
+  CK(launch_response_usage(d_bodies, d_offsets, d_lens, n, d_results, st));
+  if (kernel_ms) { CK(cudaEventRecord(ctx->ev1, st)); CK(cudaEventSynchronize(ctx->ev1)); CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1)); }
+  return 0;
+}
+
+int aigw_response_usage_host(aigw_ctx* ctx, const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n, aigw_sse_result* results,
+                             const int32_t* cost_types, uint32_t n_costs, uint64_t* costs) {
+  if (n == 0) return 0;
+  cudaSetDevice(ctx->device);
+  const uint64_t nbytes = offsets[n - 1] + lens[n - 1] - offsets[0];
+  ENSURE(ctx->d_sse_bytes, ctx->sse_bytes_cap, nbytes + 64, false);
+  ENSURE(ctx->d_sse_coff, ctx->sse_coff_cap, ((size_t)n + 1) * 8 + (size_t)n_costs * 8 * n + 64, false);
+  ENSURE(ctx->d_sse_first, ctx->sse_first_cap, ((size_t)n + 1) * 4 + (size_t)n_costs * 4 + 64, false);
+  ENSURE(ctx->d_sse_res, ctx->sse_res_cap, (size_t)n * sizeof(aigw_sse_result), false);
+  cudaStream_t st = ctx->s_compute;
+  CK(cudaMemcpyAsync(ctx->d_sse_bytes, bodies + offsets[0], nbytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_sse_coff, offsets, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_sse_first, lens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CK(launch_response_usage(ctx->d_sse_bytes - offsets[0], ctx->d_sse_coff, ctx->d_sse_first, n, ctx->d_sse_res, st));
+  CK(cudaMemcpyAsync(results, ctx->d_sse_res, (size_t)n * sizeof(aigw_sse_result), cudaMemcpyDeviceToHost, st));
+  if (n_costs && costs) {
+    int32_t* d_types = (int32_t*)(ctx->d_sse_first + n + 1);
+    unsigned long long* d_costs = (unsigned long long*)(ctx->d_sse_coff + n + 1);
+    CK(cudaMemcpyAsync(d_types, cost_types, (size_t)n_costs * 4, cudaMemcpyHostToDevice, st));
+    CK(launch_usage_costs(ctx->d_sse_res, n, d_types, n_costs, d_costs, st));
+    CK(cudaMemcpyAsync(costs, d_costs, (size_t)n * n_costs * 8, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int aigw_usage_costs_device(aigw_ctx* ctx, const aigw_sse_result* d_results, uint32_t n, const int32_t* d_cost_types, uint32_t n_costs, uint64_t* d_costs, void* stream) {
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->s_compute;
+  CK(launch_usage_costs(d_results, n, d_cost_types, n_costs, (unsigned long long*)d_costs, st));
+  return 0;
+}
+
 }  // extern "C"

@@ -11,7 +11,7 @@
 
 namespace aigw { namespace tj {
 
-enum Kind : uint8_t { K_ANY = 0, K_STR, K_INT, K_FLOAT, K_BOOL, K_OBJ, K_ARR, K_CREATED, K_B64 };
+enum Kind : uint8_t { K_ANY = 0, K_STR, K_INT, K_FLOAT, K_BOOL, K_OBJ, K_ARR, K_CREATED, K_B64, K_STROBJ /* string, or the object node in `elem` */ };
 
 struct Field { uint16_t koff; uint8_t klen; uint8_t node; };  // key bytes at keys[koff..koff+klen)
 struct Node { uint8_t kind; uint8_t cap; uint8_t f0; uint8_t nf; uint8_t elem; };
@@ -133,7 +133,7 @@ __device__ inline int skip_any(const uint8_t* p, int i, int n) {
 }
 
 // Typed walk of p[0..n).  Returns true when json.Unmarshal into the schema's root type would succeed.
-__device__ inline bool walk(const uint8_t* p, int n, const Node* nodes, const Field* fields, const char* keys, int root, Capture& cap) {
+__device__ inline bool walk(const uint8_t* p, int n, const Node* nodes, const Field* fields, const char* keys, int root, Capture& cap, bool allow_trailing = false) {
   const int MAXD = 12;
   uint8_t st_node[MAXD]; uint32_t st_seen[MAXD];
   int sp = 0;
@@ -143,8 +143,9 @@ __device__ inline bool walk(const uint8_t* p, int n, const Node* nodes, const Fi
     // ---- a value of type `node` starts here
     while (i < n && ws(p[i])) i++;
     if (i >= n) return false;
-    const Node nd = nodes[node];
+    Node nd = nodes[node];
     uint32_t c = p[i];
+    if (nd.kind == K_STROBJ) { if (c == '"' || c == 'n') nd.kind = K_STR; else { node = nd.elem; nd = nodes[node]; } }
     bool descend = false;
     if (nd.kind == K_ANY) { i = skip_any(p, i, n); if (i < 0) return false; }
     else if (c == 'n') {
@@ -204,7 +205,7 @@ __device__ inline bool walk(const uint8_t* p, int n, const Node* nodes, const Fi
     // ---- after a value (or at the first member of an object)
     for (;;) {
       if (!descend) {
-        if (sp == 0) { while (i < n && ws(p[i])) i++; return i == n; }
+        if (sp == 0) { if (allow_trailing) return true; while (i < n && ws(p[i])) i++; return i == n; }
         while (i < n && ws(p[i])) i++;
         if (i >= n) return false;
         const Node par = nodes[st_node[sp - 1]];

@@ -135,6 +135,19 @@ int aigw_sse_usage_host(aigw_ctx* ctx, const uint8_t* bytes, const uint64_t* chu
                         uint32_t n_streams, uint32_t n_chunks, aigw_sse_result* results /* host, n_streams */,
                         uint64_t* h2d_bytes, uint64_t* d2h_bytes, float* kernel_ms);
 
+/* ---- non-stream OpenAI-schema responses: usage + response model (R1) and the direct cost selectors (C2) ----
+ * Replaces openAIToOpenAITranslatorV1ChatCompletion.ResponseBody for buffered responses
+ * (internal/translator/openai_openai.go:146-174) and evalCost's six selectors (internal/extproc/processor_impl.go:707-756;
+ * cost type: 0 input, 1 cached_input, 2 cache_creation_input, 3 output, 4 total, 5 reasoning).  Result status: 0 decoded,
+ * AIGW_INTERNAL = the reference's "failed to unmarshal body", AIGW_DECLINED = run the stock path.  model_len == 0 ⇒ the caller
+ * falls back to the request model (cmp.Or in the reference).  Body i is bodies[offsets[i] .. offsets[i]+lens[i]). */
+int aigw_response_usage_device(aigw_ctx* ctx, const uint8_t* d_bodies, const uint64_t* d_offsets, const uint32_t* d_lens, uint32_t n,
+                               aigw_sse_result* d_results, void* stream, float* kernel_ms);
+int aigw_response_usage_host(aigw_ctx* ctx, const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n,
+                             aigw_sse_result* results, const int32_t* cost_types, uint32_t n_costs, uint64_t* costs /* n * n_costs, may be NULL */);
+int aigw_usage_costs_device(aigw_ctx* ctx, const aigw_sse_result* d_results, uint32_t n, const int32_t* d_cost_types, uint32_t n_costs,
+                            uint64_t* d_costs, void* stream);
+
 const char* aigw_version(void);
 
 #ifdef __cplusplus

@@ -155,17 +155,85 @@ inline TokenUsage sse_openai_feed(SSEOpenAIState& st, std::string_view chunk) {
 }
 
 // R1 (OpenAI): json.NewDecoder(body).Decode(&ChatCompletionResponse{}) then usage/model (openai_openai.go:146-174).
-// Only `usage` and `model` decide the outputs; the rest of the response is type-checked shallowly.
+// Type checks follow internal/apischema/openai/openai.go:1269-1306 (response), :1365-1422 (choice, message), :1323-1361 (logprobs),
+// :1424-1452 (annotations, audio), :1456-1461 (thinking blocks), :1840-1873 (reasoning_content union); the two genai-typed
+// Gemini extras (safety_ratings, grounding_metadata) are only syntax-checked (their types live in google.golang.org/genai).
+inline bool logprobs_ok(const Value* lp) {
+  if (!obj_or_null(lp)) return false;
+  if (lp && lp->is_obj()) for (const char* k : {"content", "refusal"}) {
+    const Value* a = lp->get(k); if (!arr_or_null(a)) return false;
+    if (a && a->is_arr()) for (auto& t : a->arr) {
+      if (t.is_null()) continue;
+      if (!t.is_obj()) return false;
+      auto tok_ok = [&](const Value& x) -> bool {
+        if (!str_or_null(x.get("token"))) return false;
+        const Value* lpv = x.get("logprob"); if (lpv && !lpv->is_null() && !lpv->is_num()) return false;
+        const Value* by = x.get("bytes"); if (!arr_or_null(by)) return false;
+        if (by && by->is_arr()) for (auto& bb : by->arr) { int64_t q; if (!int_field(&bb, q)) return false; }
+        return true; };
+      if (!tok_ok(t)) return false;
+      const Value* tl = t.get("top_logprobs"); if (!arr_or_null(tl)) return false;
+      if (tl && tl->is_arr()) for (auto& u : tl->arr) { if (u.is_null()) continue; if (!u.is_obj() || !tok_ok(u)) return false; }
+    }
+  }
+  return true;
+}
+inline bool annotations_ok(const Value* an) {
+  if (!arr_or_null(an)) return false;
+  if (an && an->is_arr()) for (auto& a : an->arr) {
+    if (a.is_null()) continue;
+    if (!a.is_obj()) return false;
+    if (!str_or_null(a.get("type")) || !obj_or_null(a.get("url_citation"))) return false;
+    const Value* uc = a.get("url_citation");
+    if (uc && uc->is_obj()) { int64_t q; if (!int_field(uc->get("end_index"), q) || !int_field(uc->get("start_index"), q) || !str_or_null(uc->get("url")) || !str_or_null(uc->get("title"))) return false; }
+  }
+  return true;
+}
 inline bool response_openai(std::string_view body, const std::string& request_model, TokenUsage& tu, std::string& response_model) {
-  Value v; std::string err;
-  // json.Decoder reads ONE value; trailing bytes are not an error.
-  oj::Parser ps(body.data(), body.size());
+  Value v;
+  oj::Parser ps(body.data(), body.size());  // json.Decoder reads ONE value; trailing bytes are not an error
   if (!ps.value(v)) return false;
   tu = TokenUsage{}; response_model = request_model;
   TokenUsage u2; u2.mask = TokenUsage::IN | TokenUsage::OUT | TokenUsage::TOTAL;
   if (v.is_obj()) {
     for (const char* k : {"id", "model", "service_tier", "system_fingerprint", "object", "obfuscation"}) if (!str_or_null(v.get(k))) return false;
-    if (!arr_or_null(v.get("choices"))) return false;
+    if (const Value* c = v.get("created")) {
+      std::string raw(body.substr(c->b, c->e - c->b));
+      size_t dot = raw.find('.'); if (dot != std::string::npos) raw.resize(dot);
+      int64_t q; if (!oj::num_to_i64(raw, q)) return false;
+    }
+    const Value* ch = v.get("choices"); if (!arr_or_null(ch)) return false;
+    if (ch && ch->is_arr()) for (auto& c : ch->arr) {
+      if (c.is_null()) continue;
+      if (!c.is_obj()) return false;
+      int64_t idx; if (!int_field(c.get("index"), idx) || !str_or_null(c.get("finish_reason")) || !logprobs_ok(c.get("logprobs"))) return false;
+      const Value* m = c.get("message"); if (!obj_or_null(m)) return false;
+      if (m && m->is_obj()) {
+        if (!str_or_null(m->get("content")) || !str_or_null(m->get("role")) || !annotations_ok(m->get("annotations"))) return false;
+        const Value* tcs = m->get("tool_calls"); if (!arr_or_null(tcs)) return false;
+        if (tcs && tcs->is_arr()) for (auto& tc : tcs->arr) {
+          if (tc.is_null()) continue;
+          if (!tc.is_obj() || !str_or_null(tc.get("id")) || !str_or_null(tc.get("type"))) return false;
+          const Value* f = tc.get("function"); if (!obj_or_null(f)) return false;
+          if (f && f->is_obj() && (!str_or_null(f->get("arguments")) || !str_or_null(f->get("name")))) return false;
+          const Value* cc = tc.get("cache_control"); if (!obj_or_null(cc)) return false;
+          if (cc && cc->is_obj() && (!str_or_null(cc->get("type")) || !str_or_null(cc->get("ttl")))) return false;
+        }
+        const Value* au = m->get("audio"); if (!obj_or_null(au)) return false;
+        if (au && au->is_obj()) { int64_t q; if (!str_or_null(au->get("data")) || !int_field(au->get("expires_at"), q) || !str_or_null(au->get("id")) || !str_or_null(au->get("transcript"))) return false; }
+        if (const Value* rc = m->get("reasoning_content"); rc && !rc->is_null() && !rc->is_str()) {
+          if (!rc->is_obj()) return false;
+          const Value* blk = rc->get("reasoningContent"); if (!obj_or_null(blk)) return false;
+          if (blk && blk->is_obj()) {
+            const Value* rt = blk->get("reasoningText"); if (!obj_or_null(rt)) return false;
+            if (rt && rt->is_obj() && (!str_or_null(rt->get("text")) || !str_or_null(rt->get("signature")))) return false;
+            if (const Value* red = blk->get("redactedContent"); red && !red->is_null()) { std::string tmp; if (!red->is_str() || !oj::b64dec(red->s, tmp)) return false; }
+          }
+        }
+        const Value* tb = m->get("thinking_blocks"); if (!arr_or_null(tb)) return false;
+        if (tb && tb->is_arr()) for (auto& t : tb->arr) { if (t.is_null()) continue; if (!t.is_obj()) return false; for (const char* k : {"type", "thinking", "signature", "data"}) if (!str_or_null(t.get(k))) return false; }
+      }
+    }
     const Value* u = v.get("usage");
     if (!obj_or_null(u)) return false;
     if (u && u->is_obj()) { u2 = TokenUsage{}; if (!decode_usage(*u, u2)) return false; }

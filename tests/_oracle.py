@@ -101,3 +101,16 @@ def fmt_f64(v: float) -> str:
     buf = C.create_string_buffer(64)
     n = lib().oracle_fmt_f64(v, buf, 64)
     return buf.raw[:n].decode()
+
+
+def response_openai(body: bytes, request_model: bytes = b""):
+    """(ok, Usage, response_model bytes) — R1, internal/translator/openai_openai.go:146-174."""
+    u = Usage()
+    buf = C.create_string_buffer(4096)
+    ml = C.c_uint64(0)
+    rc = lib().oracle_response_openai(body, len(body), request_model, C.byref(u), buf, 4096, C.byref(ml))
+    return rc == 0, u, buf.raw[:ml.value]
+
+
+def eval_cost(cost_type: int, u: Usage) -> int:
+    return lib().oracle_eval_cost(cost_type, C.byref(u))
