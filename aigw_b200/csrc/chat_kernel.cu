@@ -43,7 +43,7 @@ static_assert(K_TOP_END <= 63, "top-level seen mask is 64 bits");
 static_assert(K_COUNT <= 63, "ids are 6 bits in the token word");
 enum Vid : uint8_t {
   V_NONE = 0, V_user, V_assistant, V_system, V_developer, V_tool, V_text, V_refusal, V_thinking, V_redacted_thinking, V_ephemeral,
-  V_enabled, V_disabled, V_adaptive, V_auto, V_required
+  V_enabled, V_disabled, V_adaptive, V_auto, V_required, V_image_url, V_input_audio, V_file
 };
 
 // Perfect-enough hash tables (FNV-1a, open addressing, verified by a byte compare) built at compile time and copied to
@@ -62,7 +62,7 @@ enum Vid : uint8_t {
 #define AIGW_VALS(X) \
   X("user", V_user) X("tool", V_tool) X("text", V_text) X("auto", V_auto) X("system", V_system) X("refusal", V_refusal) X("enabled", V_enabled) X("thinking", V_thinking) \
   X("disabled", V_disabled) X("adaptive", V_adaptive) X("required", V_required) X("assistant", V_assistant) X("developer", V_developer) X("ephemeral", V_ephemeral) \
-  X("redacted_thinking", V_redacted_thinking)
+  X("redacted_thinking", V_redacted_thinking) X("image_url", V_image_url) X("input_audio", V_input_audio) X("file", V_file)
 
 static constexpr int kKeySlots = 128, kValSlots = 32, kMaxIdLen = 24;
 // slot = { six little-endian words of the string zero-padded to 24 bytes, len | id << 8 }
@@ -438,8 +438,10 @@ struct Walker {
   uint32_t* tw_tail; uint16_t* jmp_tail; int tail_cap;  // free token space for nested documents
   const ChatParams* P;
   int reason;
+  int pending;  // first translator-side error (422 / internal): reported only if the rest of the body neither declines nor fails ParseBody
 
   __device__ __forceinline__ void decline(int r) { if (!reason) reason = r; }
+  __device__ __forceinline__ void pend(int r) { if (!pending) pending = r; }
   __device__ __forceinline__ bool bad() const { return reason != 0 || pl.err != 0; }
 
   __device__ __forceinline__ bool is_str(int v) const { return d.ty(v) == '"'; }
@@ -463,21 +465,21 @@ struct Walker {
   // cache_control: object whose "type" == "ephemeral" (anthropic_helper.go:261-263)
   __device__ bool cache_enabled(int cc) {
     if (cc < 0) return false;
-    if (!is_obj(cc)) { decline(AIGW_R_TYPE); return false; }
+    if (!is_obj(cc)) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
     int t = -1, ttl = -1;
     for (int m = cc + 1; d.ty(m) != '}'; m = d.after(m + 3)) {
       const uint32_t k = d.id(m);
       if (k == K_type) { if (t >= 0) { decline(AIGW_R_DUP_KEY); return false; } t = m + 3; }
       else if (k == K_ttl) { if (ttl >= 0) { decline(AIGW_R_DUP_KEY); return false; } ttl = m + 3; }
     }
-    if (ttl >= 0 && !is_null(ttl) && !is_str(ttl)) { decline(AIGW_R_TYPE); return false; }
+    if (ttl >= 0 && !is_null(ttl) && !is_str(ttl)) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
     if (t < 0 || is_null(t)) return false;
-    if (!is_str(t)) { decline(AIGW_R_TYPE); return false; }
+    if (!is_str(t)) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
     return d.id(t) == V_ephemeral;
   }
   __device__ void emit_num_field(int v, bool integer) {
     const uint32_t e = d.scalar_end(v), o = d.tok(v);
-    if (!is_num(v)) { decline(AIGW_R_TYPE); return; }
+    if (!is_num(v)) { decline(AIGW_R_E400_TYPE); return; }
     const uint32_t l = canon_number(d.s + o, e - o, integer);
     if (!l) { decline(AIGW_R_NUMBER); return; }
     pl.src(d, o, l);
@@ -491,7 +493,7 @@ struct Walker {
       ok = is_num(v);
       if (ok && kind == 2) { const uint32_t e = d.scalar_end(v), o = d.tok(v); ok = canon_number(d.s + o, e - o, true) != 0; if (!ok) { decline(AIGW_R_NUMBER); return false; } }
     }
-    if (!ok) decline(AIGW_R_TYPE);
+    if (!ok) decline(AIGW_R_E400_TYPE);
     return ok;
   }
 
@@ -516,9 +518,9 @@ struct Walker {
   // text part list for system / developer / tool messages (ChatCompletionContentPartTextParam)
   __device__ void emit_text_parts(int arr, bool with_cache, bool sys, bool& first) {
     for (int e = arr + 1; d.ty(e) != ']'; e = d.after(e)) {
-      if (!is_obj(e)) { decline(AIGW_R_CONTENT); return; }
+      if (!is_obj(e)) { decline(is_null(e) ? AIGW_R_CONTENT : AIGW_R_E400_TYPE); return; }  // null element = zero struct in the reference
       Part p; if (!scan_part(e, p)) return;
-      if ((p.text >= 0 && !is_str(p.text)) || (p.type >= 0 && !is_str(p.type))) { decline(AIGW_R_TYPE); return; }
+      if ((p.text >= 0 && !is_str(p.text)) || (p.type >= 0 && !is_str(p.type))) { decline(AIGW_R_E400_TYPE); return; }
       const bool cache = cache_enabled(p.cache);
       if (bad()) return;
       if (!first) pl.lit(L_COMMA, sys); first = false;
@@ -533,7 +535,7 @@ struct Walker {
   // role: 0 user 1 assistant 2 system 3 developer 4 tool
   __device__ int scan_message(int m, Msg& g) {
     g.role_v = g.content = g.name = g.tool_calls = g.tool_call_id = g.refusal = g.audio = -1;
-    if (!is_obj(m)) { decline(AIGW_R_ROLE); return -1; }
+    if (!is_obj(m)) { decline(AIGW_R_E400_ROLE); return -1; }
     uint32_t seen = 0;
     for (int k = m + 1; d.ty(k) != '}'; k = d.after(k + 3)) {
       const int v = k + 3;
@@ -546,22 +548,22 @@ struct Walker {
       switch (which) { case 0: g.role_v = v; break; case 1: g.content = v; break; case 2: g.name = v; break; case 3: g.tool_calls = v; break;
         case 4: g.tool_call_id = v; break; case 5: g.refusal = v; break; case 6: g.audio = v; break; }
     }
-    if (g.role_v < 0 || !is_str(g.role_v)) { decline(AIGW_R_ROLE); return -1; }
+    if (g.role_v < 0 || !is_str(g.role_v)) { decline(AIGW_R_E400_ROLE); return -1; }
     switch (d.id(g.role_v)) { case V_user: return 0; case V_assistant: return 1; case V_system: return 2; case V_developer: return 3; case V_tool: return 4; default: break; }
-    decline(AIGW_R_ROLE); return -1;
+    decline(AIGW_R_E400_ROLE); return -1;
   }
 
   // ---- Bedrock: tool result block for one tool message (openai_awsbedrock.go:451-486)
   __device__ void bedrock_tool_result(const Msg& g) {
     pl.lit(L_TOOLRESULT_OPEN);
-    if (g.content < 0) { decline(AIGW_R_CONTENT); return; }   // absent ⇒ 422, null ⇒ 400 in the reference
-    if (is_str(g.content)) { pl.lit(L_TEXT_OPEN); emit_str(g.content); pl.lit(L_RBRACE); }
+    if (g.content < 0) pend(AIGW_R_E422_CONTENT);   // absent ⇒ 422 "message 'content' must be a string or an array"
+    else if (is_str(g.content)) { pl.lit(L_TEXT_OPEN); emit_str(g.content); pl.lit(L_RBRACE); }
     else if (is_arr(g.content)) { bool first = true; emit_text_parts(g.content, false, false, first); }
-    else { decline(AIGW_R_CONTENT); return; }
+    else { decline(AIGW_R_E400_CONTENT); return; }  // null / number / object: ContentUnion rejects it
     pl.lit(L_TOOLRESULT_MID);
     int id = g.tool_call_id;
     if (id >= 0 && is_null(id)) id = -1;
-    if (id >= 0) { if (!is_str(id)) { decline(AIGW_R_TYPE); return; } emit_str(id); } else pl.lit(L_EMPTY_STR);
+    if (id >= 0) { if (!is_str(id)) { decline(AIGW_R_E400_TYPE); return; } emit_str(id); } else pl.lit(L_EMPTY_STR);
     pl.lit(L_TOOLRESULT_CLOSE);
   }
 
@@ -578,20 +580,21 @@ struct Walker {
     }
     const uint32_t base = sc.n; sc.n += (w + 1u) & ~1u;
     const int nt = tokenize_seq(dst, w, base, tw_tail, tail_cap);
-    if (nt <= 0) { decline(nt == 0 ? AIGW_R_ARGS : -nt); return; }
+    if (nt == 0 || nt == -AIGW_R_SYNTAX) { pend(AIGW_R_E500_ARGS); pl.lit(L_NULL); return; }
+    if (nt < 0) { decline(-nt); return; }
     Doc a; a.s = sc.p; a.len = base + w; a.tw = tw_tail; a.jmp = jmp_tail; a.nt = nt; a.kind = 2;
-    if (validate_tokens(a)) { decline(AIGW_R_ARGS); return; }
+    { const int vr = validate_tokens(a); if (vr == AIGW_R_SYNTAX) { pend(AIGW_R_E500_ARGS); pl.lit(L_NULL); return; } if (vr) { decline(vr); return; } }
     const uint32_t c0 = a.ty(0);
     if (c0 == 'n') { pl.lit(L_NULL); return; }
-    if (c0 != '{') { decline(AIGW_R_ARGS); return; }
+    if (c0 != '{') { pend(AIGW_R_E500_ARGS); pl.lit(L_NULL); return; }  // not a map: "failed to unmarshal tool call arguments"
     emit_any(a, pl, 0);
   }
 
   // ---- Bedrock assistant content blocks (openai_awsbedrock.go:309-419)
   __device__ void bedrock_asst_part(int e, bool& first) {
-    if (!is_obj(e)) { decline(AIGW_R_CONTENT); return; }
+    if (!is_obj(e)) { decline(is_null(e) ? AIGW_R_CONTENT : AIGW_R_E400_CONTENT); return; }
     Part p; if (!scan_part(e, p)) return;
-    if ((p.type >= 0 && !is_str(p.type)) || (p.text >= 0 && !is_str(p.text)) || (p.refusal >= 0 && !is_str(p.refusal)) || (p.signature >= 0 && !is_str(p.signature))) { decline(AIGW_R_TYPE); return; }
+    if ((p.type >= 0 && !is_str(p.type)) || (p.text >= 0 && !is_str(p.text)) || (p.refusal >= 0 && !is_str(p.refusal)) || (p.signature >= 0 && !is_str(p.signature))) { decline(AIGW_R_E400_TYPE); return; }
     if (p.redacted >= 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
     const bool cache = cache_enabled(p.cache);
     if (bad()) return;
@@ -619,31 +622,32 @@ struct Walker {
       if (is_str(c)) { if (d.str_len(c) > 0) { pl.lit(L_TEXT_OPEN); emit_str(c); pl.lit(L_RBRACE); first = false; } }
       else if (is_arr(c)) { for (int e = c + 1; d.ty(e) != ']'; e = d.after(e)) { bedrock_asst_part(e, first); if (bad()) return; } }
       else if (is_obj(c)) bedrock_asst_part(c, first);
-      else { decline(AIGW_R_CONTENT); return; }
+      else { decline(AIGW_R_E400_CONTENT); return; }
     }
     if (g.audio >= 0 && !is_null(g.audio)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-    if (g.name >= 0 && !is_null(g.name) && !is_str(g.name)) { decline(AIGW_R_TYPE); return; }
-    if (g.refusal >= 0 && !is_null(g.refusal) && !is_str(g.refusal)) { decline(AIGW_R_TYPE); return; }
+    if (g.name >= 0 && !is_null(g.name) && !is_str(g.name)) { decline(AIGW_R_E400_TYPE); return; }
+    if (g.refusal >= 0 && !is_null(g.refusal) && !is_str(g.refusal)) { decline(AIGW_R_E400_TYPE); return; }
     const int tcs = g.tool_calls;
     if (tcs >= 0 && !is_null(tcs)) {
-      if (!is_arr(tcs)) { decline(AIGW_R_TYPE); return; }
+      if (!is_arr(tcs)) { decline(AIGW_R_E400_TYPE); return; }
       for (int e = tcs + 1; d.ty(e) != ']'; e = d.after(e)) {
-        if (!is_obj(e)) { decline(AIGW_R_TOOL); return; }
+        if (!is_obj(e)) { decline(is_null(e) ? AIGW_R_TOOL : AIGW_R_E400_TYPE); return; }
         const int id = find(e, K_id), fn = find(e, K_function), ty = find(e, K_type);
         (void)cache_enabled(find(e, K_cache_control));
         if (bad()) return;
-        if (id < 0 || !is_str(id)) { decline(AIGW_R_TOOL); return; }  // nil id panics in the reference
-        if (ty >= 0 && !is_str(ty)) { decline(AIGW_R_TYPE); return; }
+        if (id < 0) { decline(AIGW_R_TOOL); return; }  // nil id panics in the reference
+        if (!is_str(id)) { decline(AIGW_R_E400_TYPE); return; }
+        if (ty >= 0 && !is_str(ty)) { decline(AIGW_R_E400_TYPE); return; }
         int name = -1, args = -1;
-        if (fn >= 0) { if (!is_obj(fn)) { decline(AIGW_R_TYPE); return; } name = find(fn, K_name); args = find(fn, K_arguments); }
+        if (fn >= 0) { if (!is_obj(fn)) { decline(AIGW_R_E400_TYPE); return; } name = find(fn, K_name); args = find(fn, K_arguments); }
         if (bad()) return;
-        if ((name >= 0 && !is_str(name)) || (args >= 0 && !is_str(args))) { decline(AIGW_R_TYPE); return; }
-        if (args < 0) { decline(AIGW_R_ARGS); return; }  // "" fails to unmarshal in the reference
+        if ((name >= 0 && !is_str(name)) || (args >= 0 && !is_str(args))) { decline(AIGW_R_E400_TYPE); return; }
+        if (args < 0) pend(AIGW_R_E500_ARGS);  // "" fails to unmarshal in the reference
         if (!first) pl.lit(L_COMMA); first = false;
         pl.lit(L_TOOLUSE_OPEN);
         if (name >= 0) emit_str(name); else pl.lit(L_EMPTY_STR);
         pl.lit(L_TOOLUSE_INPUT);
-        emit_arguments(args);
+        if (args >= 0) emit_arguments(args); else pl.lit(L_NULL);
         if (bad()) return;
         pl.lit(L_TOOLUSE_ID); emit_str(id);
         pl.lit(L_TOOLRESULT_CLOSE);
@@ -654,18 +658,22 @@ struct Walker {
 
   __device__ void bedrock_user(const Msg& g) {
     const int c = g.content;
-    if (g.name >= 0 && !is_null(g.name) && !is_str(g.name)) { decline(AIGW_R_TYPE); return; }
-    if (c < 0) { decline(AIGW_R_CONTENT); return; }  // absent ⇒ 422
+    if (g.name >= 0 && !is_null(g.name) && !is_str(g.name)) { decline(AIGW_R_E400_TYPE); return; }
+    if (c < 0) { pend(AIGW_R_E422_CONTENT); return; }  // absent ⇒ 422 "unexpected content type for user message"
     if (is_null(c)) { pl.lit(L_MSG_TEXT_OPEN); pl.lit(L_EMPTY_STR); pl.lit(L_USER_CLOSE1); return; }
     if (is_str(c)) { pl.lit(L_MSG_TEXT_OPEN); emit_str(c); pl.lit(L_USER_CLOSE1); return; }
-    if (!is_arr(c)) { decline(AIGW_R_CONTENT); return; }
+    if (!is_arr(c)) { decline(AIGW_R_E400_CONTENT); return; }
     pl.lit(L_MSG_CONTENT_OPEN);
     bool first = true;
     for (int e = c + 1; d.ty(e) != ']'; e = d.after(e)) {
-      if (!is_obj(e)) { decline(AIGW_R_CONTENT); return; }
+      if (!is_obj(e)) { decline(AIGW_R_E400_CONTENT); return; }
       Part p; if (!scan_part(e, p)) return;
-      if (p.type < 0 || !is_str(p.type) || d.id(p.type) != V_text) { decline(AIGW_R_CONTENT); return; }  // images/audio/files: stock path
-      if (p.text >= 0 && !is_str(p.text)) { decline(AIGW_R_TYPE); return; }
+      if (p.type < 0 || !is_str(p.type)) { decline(AIGW_R_E400_CONTENT); return; }  // no type / unknown type
+      if (d.id(p.type) != V_text) {  // image_url / input_audio / file are valid but left to the stock path; anything else is unknown
+        const uint32_t tv = d.id(p.type);
+        decline((tv == V_image_url || tv == V_input_audio || tv == V_file || d.str_has_backslash(p.type)) ? AIGW_R_CONTENT : AIGW_R_E400_CONTENT); return;
+      }
+      if (p.text >= 0 && !is_str(p.text)) { decline(AIGW_R_E400_TYPE); return; }
       const bool cache = cache_enabled(p.cache);
       if (bad()) return;
       if (!first) pl.lit(L_COMMA); first = false;
@@ -677,11 +685,11 @@ struct Walker {
 
   __device__ void bedrock_system(const Msg& g, bool& sys_first) {
     const int c = g.content;
-    if (g.name >= 0 && !is_null(g.name) && !is_str(g.name)) { decline(AIGW_R_TYPE); return; }
-    if (c < 0) { decline(AIGW_R_CONTENT); return; }
+    if (g.name >= 0 && !is_null(g.name) && !is_str(g.name)) { decline(AIGW_R_E400_TYPE); return; }
+    if (c < 0) { pend(AIGW_R_E422_CONTENT); return; }
     if (is_str(c)) { if (!sys_first) pl.lit(L_COMMA, true); sys_first = false; pl.lit(L_TEXT_OPEN, true); emit_str(c, true); pl.lit(L_RBRACE, true); }
     else if (is_arr(c)) emit_text_parts(c, true, true, sys_first);
-    else decline(AIGW_R_CONTENT);
+    else decline(AIGW_R_E400_CONTENT);
   }
 
   struct Top { int model, messages, temperature, top_p, max_tokens, mct, stop, stream, stream_options, tools, tool_choice, thinking, service_tier;
@@ -690,7 +698,7 @@ struct Walker {
   // top-level member scan with type checks for every known field (endpointspec.go:102-105)
   __device__ bool scan_top(Top& t) {
     t.model = t.messages = t.temperature = t.top_p = t.max_tokens = t.mct = t.stop = t.stream = t.stream_options = t.tools = t.tool_choice = t.thinking = t.service_tier = t.model_raw = t.so_raw = -1;
-    if (d.nt == 0 || !is_obj(0)) { decline(AIGW_R_ROOT); return false; }
+    if (d.nt == 0 || !is_obj(0)) { decline(d.nt && is_null(0) ? AIGW_R_ROOT : AIGW_R_E400_TYPE); return false; }
     uint64_t seen = 0;
     for (int k = 1; d.ty(k) != '}'; k = d.after(k + 3)) {
       const int v = k + 3;
@@ -713,18 +721,18 @@ struct Walker {
         default: decline(AIGW_R_UNSUPPORTED_FIELD); return false;  // modalities, audio, prediction, response_format, logit_bias, …: stock path
       }
     }
-    if (t.model >= 0 && (!is_str(t.model) || d.str_has_backslash(t.model))) { decline(is_str(t.model) ? AIGW_R_ESCAPE : AIGW_R_TYPE); return false; }
-    if (t.messages >= 0 && !is_arr(t.messages)) { decline(AIGW_R_TYPE); return false; }
-    if (t.stream >= 0 && !is_bool(t.stream)) { decline(AIGW_R_TYPE); return false; }
-    if (t.service_tier >= 0 && !is_str(t.service_tier)) { decline(AIGW_R_TYPE); return false; }
-    if (t.tools >= 0 && !is_arr(t.tools)) { decline(AIGW_R_TYPE); return false; }
+    if (t.model >= 0 && (!is_str(t.model) || d.str_has_backslash(t.model))) { decline(is_str(t.model) ? AIGW_R_ESCAPE : AIGW_R_E400_TYPE); return false; }
+    if (t.messages >= 0 && !is_arr(t.messages)) { decline(AIGW_R_E400_TYPE); return false; }
+    if (t.stream >= 0 && !is_bool(t.stream)) { decline(AIGW_R_E400_TYPE); return false; }
+    if (t.service_tier >= 0 && !is_str(t.service_tier)) { decline(AIGW_R_E400_TYPE); return false; }
+    if (t.tools >= 0 && !is_arr(t.tools)) { decline(AIGW_R_E400_TYPE); return false; }
     if (t.stream_options >= 0) {
-      if (!is_obj(t.stream_options)) { decline(AIGW_R_TYPE); return false; }
+      if (!is_obj(t.stream_options)) { decline(AIGW_R_E400_TYPE); return false; }
       const int iu = find(t.stream_options, K_include_usage);
-      if (iu >= 0 && !is_bool(iu)) { decline(AIGW_R_TYPE); return false; }
+      if (iu >= 0 && !is_bool(iu)) { decline(AIGW_R_E400_TYPE); return false; }
     }
-    if (t.temperature >= 0 && !is_num(t.temperature)) { decline(AIGW_R_TYPE); return false; }
-    if (t.top_p >= 0 && !is_num(t.top_p)) { decline(AIGW_R_TYPE); return false; }
+    if (t.temperature >= 0 && !is_num(t.temperature)) { decline(AIGW_R_E400_TYPE); return false; }
+    if (t.top_p >= 0 && !is_num(t.top_p)) { decline(AIGW_R_E400_TYPE); return false; }
     if (t.max_tokens >= 0 && !check_scalar_type(t.max_tokens, 2)) return false;
     if (t.mct >= 0 && !check_scalar_type(t.mct, 2)) return false;
     return !bad();
@@ -774,19 +782,19 @@ struct Walker {
     pl.lit(L_LBRACE);
     if (t.thinking >= 0) {  // openai.go:911-945, openai_awsbedrock.go:57-78
       const int th = t.thinking;
-      if (!is_obj(th)) { decline(AIGW_R_TYPE); return; }
+      if (!is_obj(th)) { decline(AIGW_R_E400_TYPE); return; }
       const int ty = find(th, K_type);
-      if (ty < 0 || !is_str(ty)) { decline(AIGW_R_TYPE); return; }
+      if (ty < 0 || !is_str(ty)) { decline(AIGW_R_E400_TYPE); return; }
       const uint32_t tv = d.id(ty);
       if (tv == V_enabled) {
         const int bt = find(th, K_budget_tokens), it = find(th, K_includeThoughts);
-        if (it >= 0 && !is_bool(it)) { decline(AIGW_R_TYPE); return; }
+        if (it >= 0 && !is_bool(it)) { decline(AIGW_R_E400_TYPE); return; }
         pl.lit(L_ADDL_EN_PRE);
         if (bt >= 0) emit_num_field(bt, true); else pl.lit(L_ZERO);
         pl.lit(L_ADDL_EN_POST);
       } else if (tv == V_disabled) pl.lit(L_ADDL_DIS);
       else if (tv == V_adaptive) {}
-      else { decline(AIGW_R_TYPE); return; }
+      else { decline(AIGW_R_E400_TYPE); return; }
       if (bad()) return;
     }
     pl.lit(L_INF_OPEN);
@@ -800,10 +808,10 @@ struct Walker {
         if (d.ty(s + 1) != ']') {
           if (!f) pl.lit(L_COMMA); f = false; pl.lit(L_STOPSEQ);
           bool sf = true;
-          for (int e = s + 1; d.ty(e) != ']'; e = d.after(e)) { if (!is_str(e)) { decline(AIGW_R_TYPE); return; } if (!sf) pl.lit(L_COMMA); sf = false; emit_str(e); }
+          for (int e = s + 1; d.ty(e) != ']'; e = d.after(e)) { if (!is_str(e)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; } if (!sf) pl.lit(L_COMMA); sf = false; emit_str(e); }
           pl.lit(L_RBRACK);
         }
-      } else { decline(AIGW_R_TYPE); return; }
+      } else { decline(AIGW_R_UNSUPPORTED_FIELD); return; }  // stop of another type: openai-go union behaviour is not pinned
     }
     if (t.temperature >= 0) { if (!f) pl.lit(L_COMMA); f = false; pl.lit(L_TEMP); emit_num_field(t.temperature, false); }
     if (t.top_p >= 0) { if (!f) pl.lit(L_COMMA); f = false; pl.lit(L_TOPP); emit_num_field(t.top_p, false); }
@@ -853,11 +861,11 @@ struct Walker {
         else if (model_contains(t.model, "anthropic", 9) && model_contains(t.model, "claude", 6)) { tc_kind = 3; tc_name = tc; }
       } else if (is_obj(tc)) {
         const int ty = find(tc, K_type), fn = find(tc, K_function);
-        if (ty >= 0 && !is_str(ty)) { decline(AIGW_R_TYPE); return; }
-        if (fn >= 0) { if (!is_obj(fn)) { decline(AIGW_R_TYPE); return; } tc_name = find(fn, K_name); if (tc_name >= 0 && !is_str(tc_name)) { decline(AIGW_R_TYPE); return; } }
+        if (ty >= 0 && !is_str(ty)) { decline(AIGW_R_E400_TYPE); return; }
+        if (fn >= 0) { if (!is_obj(fn)) { decline(AIGW_R_E400_TYPE); return; } tc_name = find(fn, K_name); if (tc_name >= 0 && !is_str(tc_name)) { decline(AIGW_R_E400_TYPE); return; } }
         if (bad()) return;
         tc_kind = 3;
-      } else { decline(AIGW_R_TYPE); return; }
+      } else { decline(AIGW_R_E400_TYPE); return; }
     }
     // tools (openai_awsbedrock.go:162-226)
     if (t.tools >= 0 && d.ty(t.tools + 1) != ']') {
@@ -868,17 +876,17 @@ struct Walker {
       pl.lit(L_TOOLS_OPEN);
       bool tf = true;
       for (int e = t.tools + 1; d.ty(e) != ']'; e = d.after(e)) {
-        if (!is_obj(e)) { decline(AIGW_R_TOOL); return; }
+        if (!is_obj(e)) { decline(is_null(e) ? AIGW_R_TOOL : AIGW_R_E400_TYPE); return; }
         const int ty = find(e, K_type), fn = find(e, K_function), gs = find(e, K_google_search);
-        if (ty >= 0 && !is_str(ty)) { decline(AIGW_R_TYPE); return; }
+        if (ty >= 0 && !is_str(ty)) { decline(AIGW_R_E400_TYPE); return; }
         if (gs >= 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
         if (bad()) return;
         if (fn >= 0) {
-          if (!is_obj(fn)) { decline(AIGW_R_TYPE); return; }
+          if (!is_obj(fn)) { decline(AIGW_R_E400_TYPE); return; }
           const int nm = find(fn, K_name), ds = find(fn, K_description), st = find(fn, K_strict), pr = find(fn, K_parameters);
           const bool cache = cache_enabled(find(fn, K_cache_control));
           if (bad()) return;
-          if ((nm >= 0 && !is_str(nm)) || (ds >= 0 && !is_str(ds)) || (st >= 0 && !is_bool(st))) { decline(AIGW_R_TYPE); return; }
+          if ((nm >= 0 && !is_str(nm)) || (ds >= 0 && !is_str(ds)) || (st >= 0 && !is_bool(st))) { decline(AIGW_R_E400_TYPE); return; }
           if (!tf) pl.lit(L_COMMA); tf = false;
           pl.lit(L_TOOLSPEC_OPEN);
           if (ds >= 0 && d.str_len(ds) > 0) { pl.lit(L_DESC); emit_str(ds); pl.lit(L_COMMA); }
@@ -902,6 +910,7 @@ struct Walker {
     // validation = the Bedrock walk with the plan in dry mode (its accept set ⊆ ParseBody's)
     { uint32_t pl0 = 0; pl.dry = true; plan_bedrock(t, stream, pl0); pl.dry = false; pl.nsys = 0; sc.n = 0; }
     if (bad()) return;
+    if (pending) { decline(AIGW_R_CONTENT); return; }  // 422 / internal errors belong to the Bedrock translator; here the body is merely outside the fast path
     // ":path" = path.Join("/", prefix, "chat/completions")
     {
       const uint32_t n = P->prefix_len;
@@ -1054,7 +1063,7 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
     const uint32_t len = P.lens[doc];
     const uint8_t* g = P.bodies + P.offsets[doc];
     if (len > (uint32_t)MAXD || len == 0) {
-      if (lane == 0) wp.ntok[li] = 0x80000000u | (len ? AIGW_R_TOO_LARGE : AIGW_R_SYNTAX);
+      if (lane == 0) wp.ntok[li] = 0x80000000u | (len ? AIGW_R_TOO_LARGE : AIGW_R_E400_SYNTAX);
       continue;
     }
     // ---- stage 1: load (16-byte coalesced), pad the last round with spaces
@@ -1177,7 +1186,7 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
     if (flags & 4u) reason = AIGW_R_TOKENS;
     else if (flags & 1u) reason = AIGW_R_CTRL_IN_STRING;
     else if (flags & 2u) reason = AIGW_R_ESCAPE;
-    else if (carry_str) reason = AIGW_R_SYNTAX;
+    else if (carry_str) reason = AIGW_R_E400_SYNTAX;
     if (reason) { if (lane == 0) wp.ntok[li] = 0x80000000u | (uint32_t)reason; continue; }
     // ---- stage 2.5, one token per lane: strings get their key / value id and the escape flag (quote tokens alternate
     // open/close, so opening quotes are the quote tokens of even rank); scalars get their length
@@ -1267,8 +1276,9 @@ __global__ void __launch_bounds__(128, AIGW_WALK_BLOCKS) chat_walk_kernel(const 
   W.pl.ops = wp.ops + (size_t)li * (C::kOps + kSysCap); W.pl.nops = 0; W.pl.nsys = 0; W.pl.cap = C::kOps; W.pl.clen = 0; W.pl.ckind = 0; W.pl.coff = 0; W.pl.olen = 0; W.pl.err = 0; W.pl.dry = false;
   W.sc.p = wp.scr + (size_t)li * C::kScr; W.sc.n = 0; W.sc.cap = C::kScr - 20;
   W.tw_tail = (uint32_t*)W.d.tw + ntok; W.jmp_tail = W.d.jmp + ntok; W.tail_cap = C::kTok - (int)ntok;
-  W.P = &P; W.reason = 0;
+  W.P = &P; W.reason = 0; W.pending = 0;
   int reason = validate_tokens(W.d);
+  if (reason == AIGW_R_SYNTAX) reason = AIGW_R_E400_SYNTAX;
   uint32_t path_len = 0;
   if (!reason) {
     Walker::Top t;
@@ -1281,7 +1291,7 @@ __global__ void __launch_bounds__(128, AIGW_WALK_BLOCKS) chat_walk_kernel(const 
       else W.decline(AIGW_R_SCHEMA);
     }
     W.pl.flush();
-    reason = W.reason ? W.reason : W.pl.err;
+    reason = W.reason ? W.reason : W.pl.err ? W.pl.err : W.pending;
     if (!reason && W.pl.nops == 0) reason = AIGW_R_OPS;
   }
   po.reason = (uint8_t)reason; po.nops = (uint32_t)W.pl.nops; po.olen = W.pl.olen; po.path_len = path_len;
@@ -1317,6 +1327,7 @@ __global__ void __launch_bounds__(WARPS * 32) chat_emit_kernel(const __grid_cons
     aigw_doc_result res = blank_result(len);
     if (po.reason) {
       res.reason = po.reason;
+      res.status = po.reason >= 48 ? AIGW_INTERNAL : po.reason >= 40 ? AIGW_INVALID_422 : po.reason >= 32 ? AIGW_MALFORMED_400 : AIGW_DECLINED;
       if (lane == 0) P.results[doc] = res;
       continue;
     }

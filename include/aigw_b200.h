@@ -44,7 +44,11 @@ enum aigw_reason {
   AIGW_R_NONE = 0, AIGW_R_TOO_LARGE = 1, AIGW_R_SYNTAX = 2, AIGW_R_CTRL_IN_STRING = 3, AIGW_R_ESCAPE = 4,
   AIGW_R_TOKENS = 5, AIGW_R_OPS = 6, AIGW_R_SCRATCH = 7, AIGW_R_OUT_SPACE = 8, AIGW_R_DUP_KEY = 9,
   AIGW_R_TYPE = 10, AIGW_R_UNSUPPORTED_FIELD = 11, AIGW_R_NUMBER = 12, AIGW_R_ROLE = 13, AIGW_R_CONTENT = 14,
-  AIGW_R_TOOL = 15, AIGW_R_DEPTH = 16, AIGW_R_ROOT = 17, AIGW_R_ARENA_FULL = 18, AIGW_R_SCHEMA = 19, AIGW_R_ARGS = 20
+  AIGW_R_TOOL = 15, AIGW_R_DEPTH = 16, AIGW_R_ROOT = 17, AIGW_R_ARENA_FULL = 18, AIGW_R_SCHEMA = 19, AIGW_R_ARGS = 20,
+  /* definite reference errors, reported with the matching status (the shim builds the user-facing message):
+   * 32..39 ⇒ AIGW_MALFORMED_400 (ParseBody), 40..47 ⇒ AIGW_INVALID_422 (translator), 48..55 ⇒ AIGW_INTERNAL */
+  AIGW_R_E400_SYNTAX = 32, AIGW_R_E400_TYPE = 33, AIGW_R_E400_ROLE = 34, AIGW_R_E400_CONTENT = 35,
+  AIGW_R_E422_CONTENT = 40, AIGW_R_E500_ARGS = 48
 };
 
 /* One record per body.  Output record layout in the arena at out_off: [path bytes][body bytes]. */

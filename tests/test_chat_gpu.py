@@ -40,11 +40,16 @@ def _check_against_oracle(ctx, schema, bodies, model_override=None, cost_configu
             assert g["path"].decode() == o.path, (i, g["path"], o.path)
             assert g["model"] == o.model and g["stream"] == o.stream
             assert g["body_kind"] == o.body_kind
-        else:
-            assert g["status"] == A.AIGW_DECLINED
+        elif g["status"] == A.AIGW_DECLINED:
             declined[g["reason"]] += 1
             if must_accept:
                 raise AssertionError(f"body {i} declined with reason {g['reason']}: {b[:300]!r}")
+        else:
+            # a definite reference error: the status class must be the oracle's (400 ParseBody, 422 translator, internal)
+            assert g["status"] == o.status, (i, b[:300], g["status"], g["reason"], o.status, o.err)
+            declined["status%d" % g["status"]] += 1
+            if must_accept:
+                raise AssertionError(f"body {i} rejected with status {g['status']}: {b[:300]!r}")
     return declined
 
 
@@ -81,6 +86,41 @@ def test_diverse_corpus(ctx):
     accepted = len(bodies) - sum(d.values())
     print("declined by reason:", dict(d), "accepted:", accepted)
     assert accepted > len(bodies) // 3
+    assert d["status1"] > 100  # ParseBody errors are reported as such, not declined
+
+
+def test_error_statuses(ctx):
+    """400 (ParseBody) / 422 (translator) / internal, as the reference classifies them (user_facing_errors.go:17-40)."""
+    import aigw_b200 as A
+    cases = [
+        (b'{"model": "something", "messages": [invalid json', 1),                                  # testupstream_test.go:183-196
+        (b'{"model":"m","messages":[{"role":"wizard","content":"x"}]}', 1),                        # openai_test.go:317
+        (b'{"model":"m","messages":[{"content":"x"}]}', 1),                                        # openai_test.go:311
+        (b'{"model":"m","messages":[{"role":"user","content":[{"text":"x"}]}]}', 1),               # openai_test.go:76 (no type)
+        (b'{"model":"m","messages":[{"role":"user","content":[{"type":"video","text":"x"}]}]}', 1),
+        (b'{"model":"m","messages":[{"role":"assistant","content":5}]}', 1),                       # openai_test.go:2139
+        (b'{"model":5,"messages":[]}', 1), (b'{"model":"m","messages":{}}', 1), (b'{"model":"m","temperature":"hot"}', 1),
+        (b'{"model":"m","messages":[{"role":"system","content":null}]}', 1),
+        (b'{"model":"m","thinking":{"type":"bogus"}}', 1), (b'{"model":"m","tool_choice":7}', 1),
+        (b'{"model":"m","messages":[{"role":"user"}]}', 2), (b'{"model":"m","messages":[{"role":"system"}]}', 2), (b'{"model":"m","messages":[{"role":"tool","tool_call_id":"x"}]}', 2),
+        (b'{"model":"m","messages":[{"role":"user"},{"role":"user","content":7}]}', 1),             # a later ParseBody error outranks the translator error
+        (b'{"model":"m","messages":[{"role":"assistant","tool_calls":[{"id":"a","function":{"name":"f","arguments":"not json"}}]}]}', 3),
+        (b'{"model":"m","messages":[{"role":"assistant","tool_calls":[{"id":"a","function":{"name":"f","arguments":"[1]"}}]}]}', 3),
+        (b'{"model":"m","messages":[{"role":"assistant","tool_calls":[{"id":"a","function":{"name":"f"}}]}]}', 3),
+    ]
+    got = ctx.chat_translate(ctx.cfg("aws-bedrock"), [c[0] for c in cases])
+    for (b, exp), g in zip(cases, got):
+        o = O.chat_translate("aws-bedrock", b)
+        assert o.status == exp, (b, o.status, o.err)
+        assert g["status"] == exp, (b, g["status"], g["reason"])
+    # the same bodies through the passthrough schema: only ParseBody errors remain errors
+    got = ctx.chat_translate(ctx.cfg("openai"), [c[0] for c in cases])
+    for (b, exp), g in zip(cases, got):
+        o = O.chat_translate("openai", b)
+        if g["status"] not in (A.AIGW_DECLINED,):
+            assert g["status"] == o.status, (b, g["status"], o.status)
+        if exp == 1:
+            assert g["status"] == A.AIGW_MALFORMED_400
 
 
 def test_reference_goldens_passthrough(ctx):
@@ -139,8 +179,9 @@ def test_edge_cases(ctx):
     # spot checks: syntactically broken or exotic bodies must never be "OK"
     cfg = ctx.cfg("aws-bedrock")
     got = ctx.chat_translate(cfg, bodies)
-    for idx in (0, 1, 3, 4, 7, 9, 10):
-        assert got[idx]["status"] == A.AIGW_DECLINED, (idx, got[idx])
+    for idx in (0, 1, 4, 7, 9, 10):
+        assert got[idx]["status"] == A.AIGW_MALFORMED_400, (idx, got[idx])
+    assert got[3]["status"] == A.AIGW_DECLINED
     for idx in (2, 5, 6, 8, 14, 15, 16, 17, 20):
         assert got[idx]["status"] == A.AIGW_OK, (idx, got[idx])
 
