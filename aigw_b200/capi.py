@@ -24,7 +24,7 @@ EXPORTS = ["aigw_version", "aigw_init", "aigw_destroy", "aigw_last_error", "aigw
 
 class BackendCfg(C.Structure):
     _fields_ = [("schema", C.c_int32), ("cost_configured", C.c_int32), ("force_body_mutation", C.c_int32),
-                ("model_name_override", C.c_char_p), ("openai_prefix", C.c_char_p)]
+                ("model_name_override", C.c_char_p), ("openai_prefix", C.c_char_p), ("api_version", C.c_char_p)]
 
 
 class _BatchOut(C.Structure):
@@ -141,13 +141,14 @@ class Context:
         self._check(self.L.aigw_sync(self.h), "sync")
 
     @staticmethod
-    def cfg(schema, model_override=None, cost_configured=False, force=False, prefix=None):
+    def cfg(schema, model_override=None, cost_configured=False, force=False, prefix=None, api_version=None):
         c = BackendCfg()
         c.schema = SCHEMA[schema] if isinstance(schema, str) else int(schema)
         c.cost_configured = int(cost_configured)
         c.force_body_mutation = int(force)
         c.model_name_override = model_override.encode() if model_override else None
         c.openai_prefix = prefix.encode() if prefix else None
+        c.api_version = api_version.encode() if api_version else None
         return c
 
     # ---- chat translate, host buffers (the call the shim makes)

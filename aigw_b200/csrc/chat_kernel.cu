@@ -979,6 +979,35 @@ struct Walker {
     }
     pl.src(d, cur, end - cur);
   }
+
+  // ---- OpenAI → Azure OpenAI (openai_azureopenai.go:37-62): the body is never rewritten; ":path" carries the deployment
+  // (= request model or the override, NOT path-escaped) and the api-version.
+  __device__ void plan_azure(const Top& t, bool stream, uint32_t& path_len, uint32_t& out_flags, uint32_t& body_kind) {
+    { uint32_t pl0 = 0; pl.dry = true; plan_bedrock(t, stream, pl0); pl.dry = false; pl.nsys = 0; sc.n = 0; }
+    if (bad()) return;
+    if (pending) { decline(AIGW_R_CONTENT); return; }
+    if (stream && P->cost_configured) {  // ParseBody's forced include_usage still marks the request (endpointspec.go:107-123)
+      int iu = -1;
+      if (t.stream_options >= 0) iu = find(t.stream_options, K_include_usage);
+      if (!(iu >= 0 && d.ty(iu) == 't')) out_flags |= 2u;
+    }
+    pl.lit(L_AZURE_PREFIX);
+    if (P->override_len) {
+      const uint32_t n = P->override_len;
+      if (sc.n + n + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
+      for (uint32_t i = 0; i < n; i++) sc.p[sc.n + i] = (uint8_t)P->override_model[i];
+      pl.push(2, sc.n, n); sc.n += (n + 1u) & ~1u;
+    } else if (t.model >= 0) pl.src(d, d.str_off(t.model), d.str_len(t.model));
+    pl.lit(L_AZURE_SUFFIX);
+    {
+      const uint32_t n = P->version_len;
+      if (sc.n + n + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
+      for (uint32_t i = 0; i < n; i++) sc.p[sc.n + i] = (uint8_t)P->api_version[i];
+      pl.push(2, sc.n, n); sc.n += (n + 1u) & ~1u;
+    }
+    path_len = pl.olen;
+    body_kind = AIGW_BODY_UNCHANGED;
+  }
 };
 
 // 16 bytes starting at an arbitrary shared-memory address (buffers carry ≥ 4 bytes of slack)
@@ -1288,6 +1317,7 @@ __global__ void __launch_bounds__(128, AIGW_WALK_BLOCKS) chat_walk_kernel(const 
       po.flags = stream ? 1u : 0u;
       if (P.schema == AIGW_SCHEMA_AWS_BEDROCK) W.plan_bedrock(t, stream, path_len);
       else if (P.schema == AIGW_SCHEMA_OPENAI) { uint32_t fl = po.flags, bk = AIGW_BODY_BYTES; W.plan_passthrough(t, stream, path_len, fl, bk); po.flags = (uint8_t)(fl | (bk == AIGW_BODY_UNCHANGED ? 0x80u : 0u)); }
+      else if (P.schema == AIGW_SCHEMA_AZURE_OPENAI) { uint32_t fl = po.flags, bk = AIGW_BODY_UNCHANGED; W.plan_azure(t, stream, path_len, fl, bk); po.flags = (uint8_t)(fl | 0x80u); }
       else W.decline(AIGW_R_SCHEMA);
     }
     W.pl.flush();

@@ -83,7 +83,9 @@ namespace aigw {
   X(L_INCLUDE_USAGE_MEMBER, "\"include_usage\":true")                                          \
   X(L_INCLUDE_USAGE_OBJ, "{\"include_usage\":true}")                                           \
   X(L_MODEL_MEMBER, "\"model\":")                                                              \
-  X(L_QUOTE, "\"")
+  X(L_QUOTE, "\"")                                                                         \
+  X(L_AZURE_PREFIX, "/openai/deployments/")                                                    \
+  X(L_AZURE_SUFFIX, "/chat/completions?api-version=")
 
 enum LitId : int {
 #define X(name, text) name,
@@ -125,6 +127,8 @@ struct ChatParams {
   int force_mutation;
   uint16_t override_len;  // model_name_override (≤ 128 bytes, in cfgbuf)
   uint16_t prefix_len;    // normalised OpenAI path "/…/chat/completions"
+  uint16_t version_len;   // VersionedAPISchema.Version (Azure api-version)
+  char api_version[64];
   char override_model[128];
   char openai_path[128];
 };

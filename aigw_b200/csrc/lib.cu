@@ -53,7 +53,8 @@ static void fill_params(ChatParams& P, const aigw_backend_cfg* cfg) {
   P.schema = cfg ? cfg->schema : AIGW_SCHEMA_OPENAI;
   P.cost_configured = cfg ? cfg->cost_configured : 0;
   P.force_mutation = cfg ? cfg->force_body_mutation : 0;
-  P.override_len = 0; P.prefix_len = 0;
+  P.override_len = 0; P.prefix_len = 0; P.version_len = 0; memset(P.api_version, 0, sizeof P.api_version);
+  if (cfg && cfg->api_version) { size_t n = strlen(cfg->api_version); if (n > sizeof P.api_version) n = sizeof P.api_version; memcpy(P.api_version, cfg->api_version, n); P.version_len = (uint16_t)n; }
   memset(P.override_model, 0, sizeof P.override_model); memset(P.openai_path, 0, sizeof P.openai_path);
   if (cfg && cfg->model_name_override) {
     size_t n = strlen(cfg->model_name_override); if (n > sizeof P.override_model) n = sizeof P.override_model;

@@ -74,6 +74,7 @@ typedef struct aigw_backend_cfg {
   int32_t force_body_mutation; /* bool: onRetry() || forceBodyMutation (processor_impl.go:326) */
   const char* model_name_override;
   const char* openai_prefix;   /* VersionedAPISchema.OpenAIPrefix(), default "v1" */
+  const char* api_version;     /* VersionedAPISchema.Version (Azure api-version); may be NULL */
 } aigw_backend_cfg;
 
 /* metrics.TokenUsage (internal/metrics/metrics.go:143-158): six u32 counters + "set" mask

@@ -299,6 +299,17 @@ inline TranslateResult request_body(std::string_view original, const Value& root
 }
 }  // namespace openai_passthrough
 
+// ---------------------------------------------------------------- Azure OpenAI (openai_azureopenai.go:37-62)
+namespace azure {
+inline TranslateResult request_body(std::string_view original, const ChatReq& r, const std::string& api_version, const std::string& model_override, bool force) {
+  TranslateResult res; res.stream = r.stream; res.model = r.model;
+  res.request_model = model_override.empty() ? r.model : model_override;
+  res.headers.push_back({":path", "/openai/deployments/" + res.request_model + "/chat/completions?api-version=" + api_version});
+  if (force) res.headers.push_back({"content-length", std::to_string(original.size())});
+  return res;  // body nil: never mutated
+}
+}  // namespace azure
+
 enum Schema : int { SCHEMA_OPENAI = 0, SCHEMA_AWS_BEDROCK = 1, SCHEMA_AZURE_OPENAI = 2, SCHEMA_GCP_VERTEX = 3, SCHEMA_GCP_ANTHROPIC = 4, SCHEMA_AWS_ANTHROPIC = 5 };
 
 // ParseBody + GetTranslator + RequestBody for one /v1/chat/completions body
@@ -319,6 +330,7 @@ inline TranslateResult chat_translate(int schema, std::string_view body, const s
   switch (schema) {
     case SCHEMA_AWS_BEDROCK: res = bedrock::request_body(r, model_override); break;
     case SCHEMA_OPENAI: res = openai_passthrough::request_body(cur, *curroot, r, prefix, model_override, force || has_mut); break;
+    case SCHEMA_AZURE_OPENAI: res = azure::request_body(cur, r, prefix /* carries the api-version for this schema */, model_override, force || has_mut); break;
     default: res.err = Error{DECLINED, "schema not restated yet"}; break;
   }
   res.mutated_body = mutated; res.has_mutated = has_mut; res.model = r.model; res.stream = r.stream;

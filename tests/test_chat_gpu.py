@@ -159,6 +159,29 @@ def test_passthrough_parity(ctx, override, cost, force):
     assert n_ok > 600
 
 
+def test_azure_openai(ctx):
+    """openai_azureopenai.go:37-62: path from the deployment (model or override) + api-version, body untouched.
+    Reference golden: testupstream_test.go "azure-openai - /v1/chat/completions" expects /openai/deployments/something/chat/completions."""
+    import aigw_b200 as A
+    arena, offs, lens = W.chat_corpus(2, 9000, 300)
+    bodies = [bytes(arena[int(offs[i]):int(offs[i]) + int(lens[i])]) for i in range(len(lens))] + [W.diverse_body(s) for s in range(800)]
+    bodies.append(b'{"model":"something","messages":[{"role":"system","content":"You are a chatbot."}]}')
+    for ov in (None, "my-deployment"):
+        got = ctx.chat_translate(ctx.cfg("azure-openai", model_override=ov, api_version="2025-01-01-preview", cost_configured=True), bodies)
+        n_ok = 0
+        for b, g in zip(bodies, got):
+            o = O.chat_translate("azure-openai", b, model_override=ov or "", prefix="2025-01-01-preview", cost_configured=True)
+            if g["status"] == A.AIGW_OK:
+                n_ok += 1
+                assert o.status == O.OK and g["body_kind"] == 0 and g["body"] == b"" and o.body_kind == O.UNCHANGED
+                assert g["path"].decode() == o.path and g["stream"] == o.stream and g["model"] == o.model
+            elif g["status"] != A.AIGW_DECLINED:
+                assert g["status"] == o.status
+        assert n_ok > 500
+    g = ctx.chat_translate(ctx.cfg("azure-openai", api_version="v9"), [bodies[-1]])[0]
+    assert g["path"] == b"/openai/deployments/something/chat/completions?api-version=v9"
+
+
 def test_model_override_path(ctx):
     bodies = [b'{"model":"gpt-4o","messages":[{"role":"user","content":"hi"}],"stream":true}',
               b'{"messages":[{"role":"user","content":"no model"}]}']
