@@ -693,11 +693,12 @@ struct Walker {
   }
 
   struct Top { int model, messages, temperature, top_p, max_tokens, mct, stop, stream, stream_options, tools, tool_choice, thinking, service_tier;
-               int model_raw, so_raw; /* value tokens even when null; -1 when the key is absent */ };
+               int model_raw, so_raw; /* value tokens even when null; -1 when the key is absent */
+               int reasoning_effort; };
 
   // top-level member scan with type checks for every known field (endpointspec.go:102-105)
   __device__ bool scan_top(Top& t) {
-    t.model = t.messages = t.temperature = t.top_p = t.max_tokens = t.mct = t.stop = t.stream = t.stream_options = t.tools = t.tool_choice = t.thinking = t.service_tier = t.model_raw = t.so_raw = -1;
+    t.model = t.messages = t.temperature = t.top_p = t.max_tokens = t.mct = t.stop = t.stream = t.stream_options = t.tools = t.tool_choice = t.thinking = t.service_tier = t.model_raw = t.so_raw = t.reasoning_effort = -1;
     if (d.nt == 0 || !is_obj(0)) { decline(d.nt && is_null(0) ? AIGW_R_ROOT : AIGW_R_E400_TYPE); return false; }
     uint64_t seen = 0;
     for (int k = 1; d.ty(k) != '}'; k = d.after(k + 3)) {
@@ -713,7 +714,8 @@ struct Walker {
         case K_temperature: t.temperature = v; break; case K_top_p: t.top_p = v; break; case K_tools: t.tools = v; break; case K_tool_choice: t.tool_choice = v; break;
         case K_thinking: t.thinking = v; break; case K_stop: t.stop = v; break; case K_stream: t.stream = v; break; case K_stream_options: t.stream_options = v; break;
         case K_service_tier: t.service_tier = v; break;
-        case K_reasoning_effort: case K_verbosity: case K_user: case K_guided_regex: if (!check_scalar_type(v, 0)) return false; break;
+        case K_reasoning_effort: if (!check_scalar_type(v, 0)) return false; t.reasoning_effort = v; break;
+        case K_verbosity: case K_user: case K_guided_regex: if (!check_scalar_type(v, 0)) return false; break;
         case K_logprobs: case K_parallel_tool_calls: if (!check_scalar_type(v, 1)) return false; break;
         case K_top_logprobs: case K_seed: case K_n: if (!check_scalar_type(v, 2)) return false; break;
         case K_frequency_penalty: case K_presence_penalty: if (!check_scalar_type(v, 3)) return false; break;
@@ -1007,6 +1009,218 @@ struct Walker {
     }
     path_len = pl.olen;
     body_kind = AIGW_BODY_UNCHANGED;
+  }
+
+  // raw model bytes (override or request model) appended as-is (GCP paths) or url.PathEscape'd (AWS paths)
+  __device__ void emit_model(const Top& t, bool escape) {
+    const uint8_t* mp; uint32_t ml;
+    if (P->override_len) { mp = (const uint8_t*)P->override_model; ml = P->override_len; }
+    else if (t.model >= 0) { mp = d.s + d.str_off(t.model); ml = d.str_len(t.model); }
+    else return;
+    if (sc.n + 3 * ml + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
+    uint8_t* o = sc.p + sc.n; uint32_t w = 0;
+    for (uint32_t i = 0; i < ml; i++) {
+      const uint32_t c = mp[i];
+      const bool keep = !escape || (c - 'a' < 26u) || (c - 'A' < 26u) || (c - '0' < 10u) || c == '-' || c == '_' || c == '.' || c == '~' || c == '$' || c == '&' || c == '+' || c == ':' || c == '=' || c == '@';
+      if (keep) o[w++] = (uint8_t)c;
+      else { const char* hx = "0123456789ABCDEF"; o[w++] = '%'; o[w++] = hx[c >> 4]; o[w++] = hx[c & 15]; }
+    }
+    pl.push(2, sc.n, w); sc.n += (w + 1u) & ~1u;
+  }
+
+  // {"text":S[,"cache_control":{"type":"ephemeral"}],"type":"text"}; empty text has no pinned layout ⇒ decline
+  __device__ void an_text_block(int str_tok, bool cache, bool sys) {
+    if (d.str_len(str_tok) == 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+    pl.lit(L_TEXT_OPEN, sys); emit_str(str_tok, sys); pl.lit(cache ? L_AN_TEXT_CACHE_CLOSE : L_AN_TEXT_CLOSE, sys);
+  }
+  __device__ bool cache_simple(int cc) {  // cache_control limited to {"type":…}: a ttl has no pinned position
+    if (cc < 0) return false;
+    for (int m = cc + 1; d.ty(m) != '}'; m = d.after(m + 3)) if (d.id(m) == K_ttl && !is_null(m + 3)) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
+    return cache_enabled(cc);
+  }
+  // is_error of a tool result: the content string decodes to a JSON object that has an "error" key (anthropic_helper.go:531-539)
+  __device__ bool an_is_error(int v) {
+    const uint32_t off = d.str_off(v), n = d.str_len(v);
+    const uint8_t* p = d.s + off;
+    uint32_t k = 0; while (k < n && (p[k] == ' ')) k++;
+    if (k >= n || (p[k] != '{' && p[k] != '\\')) return false;  // cannot be an object
+    if (sc.n + n + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return false; }
+    uint8_t* dst = sc.p + sc.n; uint32_t w = 0;
+    for (uint32_t i = 0; i < n; i++) { uint32_t c = p[i]; if (c == '\\') { const uint32_t e = p[++i]; c = e == 'n' ? '\n' : e == 'r' ? '\r' : e == 't' ? '\t' : e; } dst[w++] = (uint8_t)c; }
+    const uint32_t base = sc.n;  // scratch is only borrowed: nothing emitted references it
+    const int nt = tokenize_seq(dst, w, base, tw_tail, tail_cap);
+    if (nt == 0 || nt == -AIGW_R_SYNTAX) return false;
+    if (nt < 0) { decline(-nt); return false; }
+    Doc a; a.s = sc.p; a.len = base + w; a.tw = tw_tail; a.jmp = jmp_tail; a.nt = nt; a.kind = 2;
+    const int vr = validate_tokens(a);
+    if (vr == AIGW_R_SYNTAX) return false;
+    if (vr) { decline(vr); return false; }
+    if (a.ty(0) != '{') return false;
+    for (int m = 1; a.ty(m) != '}'; m = a.after(m + 3)) {
+      if (a.str_has_backslash(m)) { decline(AIGW_R_ESCAPE); return false; }
+      if (a.str_len(m) == 5) { const uint8_t* q = a.s + a.str_off(m); if (q[0] == 'e' && q[1] == 'r' && q[2] == 'r' && q[3] == 'o' && q[4] == 'r') return true; }
+    }
+    return false;
+  }
+
+  // ---- OpenAI → Anthropic messages API behind GCP rawPredict / AWS InvokeModel (anthropic_helper.go:455-569,661-747;
+  // openai_gcpanthropic.go:56-100; openai_awsanthropic.go:54-100).  Only the layout the reference's goldens pin is
+  // produced (testupstream_test.go:203,216,291,355,369,549); fields whose position the SDK decides are declined.
+  __device__ void plan_anthropic(const Top& t, bool stream, bool gcp, uint32_t& path_len) {
+    { uint32_t pl0 = 0; pl.dry = true; plan_bedrock(t, stream, pl0); pl.dry = false; pl.nsys = 0; sc.n = 0; }
+    if (bad()) return;
+    pending = 0;  // Bedrock's translator errors do not apply; this translator's own are found below
+    if (t.temperature >= 0 || t.top_p >= 0 || t.stop >= 0 || t.thinking >= 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+    if (t.tools >= 0 && d.ty(t.tools + 1) != ']') { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+    if (t.reasoning_effort >= 0 && d.str_len(t.reasoning_effort) > 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+    // ":path"
+    if (gcp) { pl.lit(L_AN_GCP_PATH); emit_model(t, false); pl.lit(stream ? L_AN_STREAMRAWPREDICT : L_AN_RAWPREDICT); }
+    else { pl.lit(L_PATH_MODEL); emit_model(t, true); pl.lit(stream ? L_AN_INVOKE_STREAM : L_AN_INVOKE); }
+    path_len = pl.olen;
+    if (bad()) return;
+    pl.lit(L_AN_OPEN);
+    const int mt = t.mct >= 0 ? t.mct : t.max_tokens;
+    if (mt >= 0) emit_num_field(mt, true); else pl.lit(L_ZERO);
+    pl.lit(L_AN_MSGS);
+    bool mfirst = true, sys_first = true;
+    if (t.messages >= 0) {
+      int e = t.messages + 1;
+      while (d.ty(e) != ']') {
+        Msg g; const int role = scan_message(e, g);
+        if (bad()) return;
+        int nx = d.after(e);
+        if (role == 2 || role == 3) {  // one system block per message; text parts are concatenated into one string
+          const int c = g.content;
+          if (c < 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+          if (!sys_first) pl.lit(L_COMMA, true); sys_first = false;
+          if (is_str(c)) an_text_block(c, false, true);
+          else {
+            bool cache = false; uint32_t total = 0;
+            pl.lit(L_TEXT_OPEN, true); pl.lit(L_QUOTE, true);
+            for (int q = c + 1; d.ty(q) != ']'; q = d.after(q)) {
+              Part p; if (!scan_part(q, p)) return;
+              if (p.text >= 0) { pl.src(d, d.str_off(p.text), d.str_len(p.text), true); total += d.str_len(p.text); }
+              if (cache_simple(p.cache)) cache = true;
+              if (bad()) return;
+            }
+            if (total == 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+            pl.lit(L_QUOTE, true); pl.lit(cache ? L_AN_TEXT_CACHE_CLOSE : L_AN_TEXT_CLOSE, true);
+          }
+          if (bad()) return;
+          e = nx; continue;
+        }
+        if (!mfirst) pl.lit(L_COMMA); mfirst = false;
+        pl.lit(L_MSG_CONTENT_OPEN);
+        if (role == 0) {
+          const int c = g.content;
+          if (c < 0) { pend(AIGW_R_E500_ARGS); }  // "unsupported OpenAI content type: <nil>"
+          else if (is_null(c)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+          else if (is_str(c)) an_text_block(c, false, false);
+          else {
+            if (d.ty(c + 1) == ']') { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+            bool first = true;
+            for (int q = c + 1; d.ty(q) != ']'; q = d.after(q)) {
+              Part p; if (!scan_part(q, p)) return;
+              if (p.text < 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+              const bool cache = cache_simple(p.cache);
+              if (bad()) return;
+              if (!first) pl.lit(L_COMMA); first = false;
+              an_text_block(p.text, cache, false);
+            }
+          }
+          if (bad()) return;
+          pl.lit(L_USER_CLOSE);
+        } else if (role == 1) {
+          bool first = true;
+          const int c = g.content;
+          if (c >= 0 && !is_null(c)) {
+            if (is_str(c)) { if (d.str_len(c) > 0) { an_text_block(c, false, false); first = false; } }
+            else {
+              const bool arr = is_arr(c);
+              for (int q = arr ? c + 1 : c; arr ? d.ty(q) != ']' : q == c; q = arr ? d.after(q) : -1) {
+                Part p; if (!scan_part(q, p)) return;
+                if (p.type < 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+                const uint32_t ty = d.id(p.type);
+                int src = -1; bool cache = false;
+                if (ty == V_text) { src = p.text; cache = cache_simple(p.cache); }
+                else if (ty == V_refusal) src = p.refusal;
+                else { decline(AIGW_R_UNSUPPORTED_FIELD); return; }  // thinking blocks, unknown types
+                if (bad()) return;
+                if (src >= 0) { if (!first) pl.lit(L_COMMA); first = false; an_text_block(src, cache, false); if (bad()) return; }
+                if (!arr) break;
+              }
+            }
+          }
+          const int tcs = g.tool_calls;
+          if (tcs >= 0 && !is_null(tcs)) {
+            for (int q = tcs + 1; d.ty(q) != ']'; q = d.after(q)) {
+              const int id = find(q, K_id), fn = find(q, K_function);
+              if (cache_enabled(find(q, K_cache_control))) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+              int name = -1, args = -1;
+              if (fn >= 0) { name = find(fn, K_name); args = find(fn, K_arguments); }
+              if (bad()) return;
+              if (id < 0) { decline(AIGW_R_TOOL); return; }
+              if (args < 0) pend(AIGW_R_E500_ARGS);
+              if (!first) pl.lit(L_COMMA); first = false;
+              pl.lit(L_AN_TOOLUSE_OPEN); emit_str(id); pl.lit(L_TOOLUSE_INPUT);
+              if (args >= 0) emit_arguments(args); else pl.lit(L_NULL);
+              if (bad()) return;
+              pl.lit(L_AN_NAME); if (name >= 0) emit_str(name); else pl.lit(L_EMPTY_STR);
+              pl.lit(L_AN_TOOLUSE_CLOSE);
+            }
+          }
+          if (first) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }  // empty content: layout not pinned
+          pl.lit(L_ASST_CLOSE);
+        } else {
+          bool tfirst = true;
+          for (;;) {  // consecutive tool messages aggregate into one user message
+            Msg g2; int r2 = 4;
+            if (!tfirst) { if (d.ty(nx) == ']') break; r2 = scan_message(nx, g2); if (bad()) return; if (r2 != 4) break; nx = d.after(nx); }
+            const Msg& tm = tfirst ? g : g2;
+            if (!tfirst) pl.lit(L_COMMA);
+            tfirst = false;
+            const int c = tm.content;
+            pl.lit(L_AN_TR_OPEN);
+            int id = tm.tool_call_id; if (id >= 0 && is_null(id)) id = -1;
+            if (id >= 0) emit_str(id); else pl.lit(L_EMPTY_STR);
+            if (c < 0) { pend(AIGW_R_E500_ARGS); pl.lit(L_AN_TR_ERR_F); }
+            else if (is_str(c)) {
+              const bool ie = an_is_error(c);
+              if (bad()) return;
+              pl.lit(ie ? L_AN_TR_ERR_T : L_AN_TR_ERR_F);
+              an_text_block(c, false, false);
+            } else {
+              pl.lit(L_AN_TR_ERR_F);
+              if (d.ty(c + 1) == ']') { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+              bool first = true;
+              for (int q = c + 1; d.ty(q) != ']'; q = d.after(q)) {
+                Part p; if (!scan_part(q, p)) return;
+                if (p.text < 0 || cache_enabled(p.cache)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+                if (!first) pl.lit(L_COMMA); first = false;
+                an_text_block(p.text, false, false);
+              }
+            }
+            if (bad()) return;
+            pl.lit(L_AN_TR_CLOSE);
+          }
+          pl.lit(L_USER_CLOSE);
+        }
+        if (bad()) return;
+        e = nx;
+      }
+    }
+    if (mfirst) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }  // no messages: layout not pinned
+    pl.lit(L_RBRACK);
+    if (pl.nsys) { pl.lit(L_SYSTEM_OPEN); pl.flush_sys(); pl.lit(L_RBRACK); }
+    if (gcp && stream) pl.lit(L_AN_STREAM);
+    pl.lit(L_AN_VERSION);
+    if (P->version_len) {
+      for (uint32_t i = 0; i < P->version_len; i++) { const uint32_t c = (uint8_t)P->api_version[i]; if (c < 0x20 || c > 0x7f || c == '"' || c == '\\') { decline(AIGW_R_UNSUPPORTED_FIELD); return; } }
+      if (sc.n + P->version_len + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
+      for (uint32_t i = 0; i < P->version_len; i++) sc.p[sc.n + i] = (uint8_t)P->api_version[i];
+      pl.push(2, sc.n, P->version_len); sc.n += (P->version_len + 1u) & ~1u;
+    } else pl.lit(gcp ? L_AN_VER_GCP : L_AN_VER_AWS);
+    pl.lit(L_AN_END);
   }
 };
 
@@ -1318,6 +1532,7 @@ __global__ void __launch_bounds__(128, AIGW_WALK_BLOCKS) chat_walk_kernel(const 
       if (P.schema == AIGW_SCHEMA_AWS_BEDROCK) W.plan_bedrock(t, stream, path_len);
       else if (P.schema == AIGW_SCHEMA_OPENAI) { uint32_t fl = po.flags, bk = AIGW_BODY_BYTES; W.plan_passthrough(t, stream, path_len, fl, bk); po.flags = (uint8_t)(fl | (bk == AIGW_BODY_UNCHANGED ? 0x80u : 0u)); }
       else if (P.schema == AIGW_SCHEMA_AZURE_OPENAI) { uint32_t fl = po.flags, bk = AIGW_BODY_UNCHANGED; W.plan_azure(t, stream, path_len, fl, bk); po.flags = (uint8_t)(fl | 0x80u); }
+      else if (P.schema == AIGW_SCHEMA_GCP_ANTHROPIC || P.schema == AIGW_SCHEMA_AWS_ANTHROPIC) W.plan_anthropic(t, stream, P.schema == AIGW_SCHEMA_GCP_ANTHROPIC, path_len);
       else W.decline(AIGW_R_SCHEMA);
     }
     W.pl.flush();

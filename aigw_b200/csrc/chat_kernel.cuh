@@ -85,7 +85,28 @@ namespace aigw {
   X(L_MODEL_MEMBER, "\"model\":")                                                              \
   X(L_QUOTE, "\"")                                                                         \
   X(L_AZURE_PREFIX, "/openai/deployments/")                                                    \
-  X(L_AZURE_SUFFIX, "/chat/completions?api-version=")
+  X(L_AZURE_SUFFIX, "/chat/completions?api-version=")                                         \
+  X(L_AN_OPEN, "{\"max_tokens\":")                                                              \
+  X(L_AN_MSGS, ",\"messages\":[")                                                               \
+  X(L_AN_TEXT_CLOSE, ",\"type\":\"text\"}")                                                     \
+  X(L_AN_TEXT_CACHE_CLOSE, ",\"cache_control\":{\"type\":\"ephemeral\"},\"type\":\"text\"}")      \
+  X(L_AN_TOOLUSE_OPEN, "{\"id\":")                                                              \
+  X(L_AN_NAME, ",\"name\":")                                                                    \
+  X(L_AN_TOOLUSE_CLOSE, ",\"type\":\"tool_use\"}")                                              \
+  X(L_AN_TR_OPEN, "{\"tool_use_id\":")                                                          \
+  X(L_AN_TR_ERR_F, ",\"is_error\":false,\"content\":[")                                         \
+  X(L_AN_TR_ERR_T, ",\"is_error\":true,\"content\":[")                                          \
+  X(L_AN_TR_CLOSE, "],\"type\":\"tool_result\"}")                                               \
+  X(L_AN_STREAM, ",\"stream\":true")                                                            \
+  X(L_AN_VERSION, ",\"anthropic_version\":\"")                                                   \
+  X(L_AN_END, "\"}")                                                                            \
+  X(L_AN_GCP_PATH, "publishers/anthropic/models/")                                             \
+  X(L_AN_RAWPREDICT, ":rawPredict")                                                            \
+  X(L_AN_STREAMRAWPREDICT, ":streamRawPredict")                                                \
+  X(L_AN_INVOKE, "/invoke")                                                                    \
+  X(L_AN_INVOKE_STREAM, "/invoke-with-response-stream")                                        \
+  X(L_AN_VER_GCP, "vertex-2023-10-16")                                                         \
+  X(L_AN_VER_AWS, "bedrock-2023-05-31")
 
 enum LitId : int {
 #define X(name, text) name,
@@ -139,7 +160,7 @@ static constexpr int kSysCap = 64;
 template <int MAXD>
 struct Cls {
   static constexpr int kIn = MAXD + 16;                  // multiple of 16; slack for unaligned word reads
-  static constexpr int kTok = (MAXD / 8 + 63) / 64 * 64; // one token per 8 input bytes, else the body is declined
+  static constexpr int kTok = (MAXD / 8 < 512 ? 512 : (MAXD / 8 + 63) / 64 * 64); // ≈ one token per 8 input bytes, else the body is declined
   static constexpr int kOps = 160 + MAXD / 32;
   static constexpr int kScr = 256 + MAXD / 8;
   static constexpr int kWarpBytes = kIn + kTok * 6 + (kOps + kSysCap) * 4 + kOps * 4 + kScr;

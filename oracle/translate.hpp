@@ -310,6 +310,125 @@ inline TranslateResult request_body(std::string_view original, const ChatReq& r,
 }
 }  // namespace azure
 
+// ---------------------------------------------------------------- T4: OpenAI → Anthropic (GCP rawPredict / AWS InvokeModel)
+// internal/translator/anthropic_helper.go:131-221,265-569,661-747; openai_gcpanthropic.go:56-100; openai_awsanthropic.go:54-100.
+// The body layout is produced by anthropic-sdk-go v1.38.0 (MessageNewParams marshal), which is not in the tree.  Only
+// what the reference's goldens pin (tests/data-plane/testupstream_test.go:203,216,291,355,369,549) is restated:
+// max_tokens, messages (text / tool_use / tool_result blocks, cache_control {"type":"ephemeral"}), system, then the
+// sjson-appended "stream" (GCP) and "anthropic_version".  Every other field (temperature, top_p, stop_sequences, tools,
+// tool_choice, thinking, output_config) has no pinned position ⇒ status DECLINED ("parity unpinned"), never a guess.
+namespace anthropic {
+inline Error unpinned(const char* what) { return Error{DECLINED, std::string("parity unpinned: ") + what}; }
+
+inline void text_block(std::string& o, std::string_view text, bool cache) {
+  o += "{\"text\":"; oj::enc_str(o, text);
+  if (cache) o += ",\"cache_control\":{\"type\":\"ephemeral\"}";
+  o += ",\"type\":\"text\"}";
+}
+
+inline TranslateResult request_body(const ChatReq& r, const Value& root, bool gcp, const std::string& model_override, const std::string& api_version) {
+  TranslateResult res; res.stream = r.stream; res.model = r.model;
+  res.request_model = model_override.empty() ? r.model : model_override;
+  auto fail = [&](Error e) { res.err = e; return res; };
+  if (r.temperature) return fail(unpinned("temperature"));
+  if (r.top_p) return fail(unpinned("top_p"));
+  if (r.stop_is_string || r.stop_array) return fail(unpinned("stop_sequences"));
+  if (!r.tools.empty()) return fail(unpinned("tools"));
+  if (r.thinking != ChatReq::ThNone) return fail(unpinned("thinking"));
+  if (!r.reasoning_effort.empty()) return fail(unpinned("output_config.effort"));
+  if (r.response_format) return fail(unpinned("output_config.format"));
+  std::optional<int64_t> mt = r.max_completion_tokens ? r.max_completion_tokens : r.max_tokens;
+  std::string msgs, sys; bool mfirst = true, sfirst = true;
+  auto cache_raw_ok = [&](const CacheCtl& c) { return !c.present || true; };
+  (void)cache_raw_ok;
+  for (size_t i = 0; i < r.messages.size();) {
+    const Message& m = r.messages[i];
+    auto msep = [&] { if (!mfirst) msgs.push_back(','); mfirst = false; };
+    if (m.role == Message::System || m.role == Message::Developer) {  // one block per message, parts concatenated (:338-362)
+      std::string text; bool cache = false;
+      if (m.ck == Message::String) text = m.content_str;
+      else if (m.ck == Message::TextParts) for (auto& p : m.text_parts) { text += p.text; if (p.cache.ephemeral) cache = true; }
+      if (text.empty()) return fail(unpinned("empty system text block"));
+      if (!sfirst) sys.push_back(','); sfirst = false;
+      text_block(sys, text, cache);
+      i++; continue;
+    }
+    if (m.role == Message::User) {
+      std::string c;
+      if (m.ck == Message::None) return fail(internal("unsupported OpenAI content type: <nil>"));
+      if (m.ck == Message::String) { if (m.content_str.empty()) return fail(unpinned("nil content")); text_block(c, m.content_str, false); }
+      else {
+        if (m.user_parts.empty()) return fail(unpinned("empty content array"));
+        bool f = true;
+        for (auto& p : m.user_parts) {
+          if (p.k != UserPart::Text) return fail(unpinned("non-text content part"));
+          if (p.text.text.empty()) return fail(unpinned("empty text block"));
+          if (!f) c.push_back(','); f = false;
+          text_block(c, p.text.text, p.text.cache.ephemeral);
+        }
+      }
+      msep(); msgs += "{\"content\":[" + c + "],\"role\":\"user\"}"; i++; continue;
+    }
+    if (m.role == Message::Assistant) {
+      std::string c; bool f = true;
+      auto sep = [&] { if (!f) c.push_back(','); f = false; };
+      std::vector<AsstPart> parts;
+      if (m.ck == Message::String) { if (!m.content_str.empty()) { sep(); text_block(c, m.content_str, false); } }
+      else if (m.ck == Message::AsstParts || m.ck == Message::AsstSingle) parts = m.asst_parts;
+      for (auto& p : parts) {
+        if (p.type == "refusal") { if (p.refusal) { if (p.refusal->empty()) return fail(unpinned("empty text block")); sep(); text_block(c, *p.refusal, false); } }
+        else if (p.type == "text") { if (p.text) { if (p.text->empty()) return fail(unpinned("empty text block")); sep(); text_block(c, *p.text, p.cache.ephemeral); } }
+        else if (p.type == "thinking" || p.type == "redacted_thinking") return fail(unpinned("thinking blocks"));
+        else return fail(internal("content type not supported: " + p.type));
+      }
+      for (auto& tc : m.tool_calls) {
+        Value args; std::string perr;
+        if (!oj::parse(tc.arguments, args, perr) || !(args.is_obj() || args.is_null())) return fail(internal("failed to unmarshal tool call arguments: " + perr));
+        if (!tc.id) return fail(unpinned("nil tool call id (panics in the reference)"));
+        if (tc.cache.ephemeral) return fail(unpinned("cache_control on tool_use"));
+        sep(); c += "{\"id\":"; oj::enc_str(c, *tc.id); c += ",\"input\":";
+        if (args.is_null()) c += "null"; else oj::enc_any(c, args);
+        c += ",\"name\":"; oj::enc_str(c, tc.name); c += ",\"type\":\"tool_use\"}";
+      }
+      if (f) return fail(unpinned("empty assistant content"));
+      msep(); msgs += "{\"content\":[" + c + "],\"role\":\"assistant\"}"; i++; continue;
+    }
+    // tool: consecutive tool messages aggregate into one user message (:498-560)
+    std::string c; bool f = true;
+    while (i < r.messages.size() && r.messages[i].role_str == "tool") {
+      const Message& t = r.messages[i];
+      std::string blocks;
+      if (t.ck == Message::None) return fail(internal("unsupported ContentUnion value type: <nil>"));
+      if (t.ck == Message::String) { if (t.content_str.empty()) return fail(unpinned("nil tool result content")); text_block(blocks, t.content_str, false); }
+      else {
+        if (t.text_parts.empty()) return fail(unpinned("nil tool result content"));
+        bool bf = true;
+        for (auto& p : t.text_parts) { if (p.cache.ephemeral) return fail(unpinned("cache_control on tool_result")); if (p.text.empty()) return fail(unpinned("empty text block")); if (!bf) blocks.push_back(','); bf = false; text_block(blocks, p.text, false); }
+      }
+      bool is_error = false;
+      if (t.ck == Message::String) { Value cm; std::string pe; if (oj::parse(t.content_str, cm, pe) && cm.is_obj() && cm.get("error")) is_error = true; }
+      if (!f) c.push_back(','); f = false;
+      c += "{\"tool_use_id\":"; oj::enc_str(c, t.tool_call_id); c += is_error ? ",\"is_error\":true" : ",\"is_error\":false";
+      c += ",\"content\":[" + blocks + "],\"type\":\"tool_result\"}";
+      i++;
+    }
+    msep(); msgs += "{\"content\":[" + c + "],\"role\":\"user\"}";
+  }
+  if (mfirst) return fail(unpinned("no messages"));
+  std::string o = "{\"max_tokens\":" + std::to_string(mt.value_or(0)) + ",\"messages\":[" + msgs + "]";
+  if (!sys.empty()) o += ",\"system\":[" + sys + "]";
+  if (gcp && r.stream) o += ",\"stream\":true";
+  std::string ver = !api_version.empty() ? api_version : (gcp ? "vertex-2023-10-16" : "bedrock-2023-05-31");
+  o += ",\"anthropic_version\":"; sjson_stringify(o, ver); o += "}";
+  res.body_kind = BYTES; res.body = o;
+  std::string path = gcp ? "publishers/anthropic/models/" + res.request_model + (r.stream ? ":streamRawPredict" : ":rawPredict")
+                         : "/model/" + path_escape(res.request_model) + (r.stream ? "/invoke-with-response-stream" : "/invoke");
+  res.headers.push_back({":path", path});
+  res.headers.push_back({"content-length", std::to_string(o.size())});
+  return res;
+}
+}  // namespace anthropic
+
 enum Schema : int { SCHEMA_OPENAI = 0, SCHEMA_AWS_BEDROCK = 1, SCHEMA_AZURE_OPENAI = 2, SCHEMA_GCP_VERTEX = 3, SCHEMA_GCP_ANTHROPIC = 4, SCHEMA_AWS_ANTHROPIC = 5 };
 
 // ParseBody + GetTranslator + RequestBody for one /v1/chat/completions body
@@ -331,6 +450,8 @@ inline TranslateResult chat_translate(int schema, std::string_view body, const s
     case SCHEMA_AWS_BEDROCK: res = bedrock::request_body(r, model_override); break;
     case SCHEMA_OPENAI: res = openai_passthrough::request_body(cur, *curroot, r, prefix, model_override, force || has_mut); break;
     case SCHEMA_AZURE_OPENAI: res = azure::request_body(cur, r, prefix /* carries the api-version for this schema */, model_override, force || has_mut); break;
+    case SCHEMA_GCP_ANTHROPIC: res = anthropic::request_body(r, root, true, model_override, prefix /* api version */); break;
+    case SCHEMA_AWS_ANTHROPIC: res = anthropic::request_body(r, root, false, model_override, prefix /* api version */); break;
     default: res.err = Error{DECLINED, "schema not restated yet"}; break;
   }
   res.mutated_body = mutated; res.has_mutated = has_mut; res.model = r.model; res.stream = r.stream;
