@@ -5,6 +5,7 @@
 #include <chrono>
 #include <thread>
 
+#include "bedrock_stream.hpp"
 #include "stream.hpp"
 #include "translate.hpp"
 
@@ -109,6 +110,43 @@ int oracle_response_openai(const char* body, uint64_t len, const char* request_m
   return ok ? 0 : 1;
 }
 uint64_t oracle_eval_cost(int type, const oracle_usage* u) { TokenUsage t; t.input = u->input; t.output = u->output; t.total = u->total; t.cached = u->cached; t.cache_creation = u->cache_creation; t.reasoning = u->reasoning; t.mask = u->mask; return eval_cost(type, t); }
+
+// ---- S2: Bedrock eventstream → OpenAI SSE.  Replays ResponseBody over the given chunking; returns malloc'd output.
+char* oracle_bedrock_stream(const uint8_t* bytes, const uint64_t* chunk_off, uint32_t n_chunks, const char* request_model, const char* response_id,
+                            int64_t created, uint64_t* out_len, oracle_usage* usage) {
+  BedrockStreamState st; BedrockStreamCfg cfg; cfg.request_model = request_model ? request_model : ""; cfg.response_id = response_id ? response_id : ""; cfg.created = created;
+  std::string out; TokenUsage acc;
+  for (uint32_t c = 0; c < n_chunks; c++) {
+    TokenUsage u;
+    bedrock_stream_feed(st, cfg, std::string_view((const char*)bytes + chunk_off[c], chunk_off[c + 1] - chunk_off[c]), c + 1 == n_chunks, out, u);
+    acc.override_with(u);
+  }
+  if (n_chunks == 0) out += "data: [DONE]\n";
+  put(usage, acc); *out_len = out.size();
+  return dup(out);
+}
+double oracle_bedrock_stream_batch(const uint8_t* bytes, const uint64_t* stream_off, uint32_t n_streams, const char* request_model, const char* response_id, int64_t created,
+                                   int threads, uint64_t* total_out) {
+  std::atomic<uint32_t> next{0}; std::atomic<uint64_t> tot{0};
+  auto t0 = std::chrono::steady_clock::now();
+  auto work = [&] {
+    for (;;) {
+      uint32_t s = next.fetch_add(16); if (s >= n_streams) break;
+      uint32_t e = std::min(n_streams, s + 16);
+      for (; s < e; s++) {
+        BedrockStreamState st; BedrockStreamCfg cfg; cfg.request_model = request_model; cfg.response_id = response_id; cfg.created = created;
+        std::string out; TokenUsage u;
+        bedrock_stream_feed(st, cfg, std::string_view((const char*)bytes + stream_off[s], stream_off[s + 1] - stream_off[s]), true, out, u);
+        tot += out.size();
+      }
+    }
+  };
+  if (threads <= 1) work(); else { std::vector<std::thread> th; for (int t = 0; t < threads; t++) th.emplace_back(work); for (auto& t : th) t.join(); }
+  if (total_out) *total_out = tot.load();
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+void oracle_free(void* p) { free(p); }
+uint32_t oracle_crc32(const uint8_t* p, uint64_t n) { return crc32_ieee(p, n); }
 
 // float formatting probe for tests
 uint64_t oracle_fmt_f64(double v, char* buf, uint64_t cap) { std::string s; oj::enc_f64(s, v); uint64_t n = std::min<uint64_t>(cap, s.size()); memcpy(buf, s.data(), n); return s.size(); }

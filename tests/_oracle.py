@@ -50,6 +50,13 @@ def lib():
         _lib.oracle_response_openai.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.POINTER(Usage), C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
         _lib.oracle_eval_cost.argtypes = [C.c_int, C.POINTER(Usage)]
         _lib.oracle_eval_cost.restype = C.c_uint64
+        _lib.oracle_bedrock_stream.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(Usage)]
+        _lib.oracle_bedrock_stream.restype = C.c_void_p
+        _lib.oracle_free.argtypes = [C.c_void_p]
+        _lib.oracle_crc32.argtypes = [C.c_char_p, C.c_uint64]
+        _lib.oracle_crc32.restype = C.c_uint32
+        _lib.oracle_bedrock_stream_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p, C.c_char_p, C.c_int64, C.c_int, C.POINTER(C.c_uint64)]
+        _lib.oracle_bedrock_stream_batch.restype = C.c_double
         _lib.oracle_fmt_f64.argtypes = [C.c_double, C.c_char_p, C.c_uint64]
         _lib.oracle_fmt_f64.restype = C.c_uint64
     return _lib
@@ -114,3 +121,15 @@ def response_openai(body: bytes, request_model: bytes = b""):
 
 def eval_cost(cost_type: int, u: Usage) -> int:
     return lib().oracle_eval_cost(cost_type, C.byref(u))
+
+
+def bedrock_stream(data: bytes, chunk_sizes, request_model: bytes, response_id: bytes, created: int):
+    """Replay the Bedrock streaming ResponseBody over `chunk_sizes` (None = one chunk).  Returns (sse bytes, Usage)."""
+    import numpy as np
+    sizes = [len(data)] if chunk_sizes is None else list(chunk_sizes)
+    off = np.zeros(len(sizes) + 1, dtype=np.uint64); np.cumsum(sizes, out=off[1:])
+    assert int(off[-1]) == len(data)
+    n = C.c_uint64(0); u = Usage()
+    p = lib().oracle_bedrock_stream(data, off.ctypes.data, len(sizes), request_model, response_id, created, C.byref(n), C.byref(u))
+    out = C.string_at(p, n.value); lib().oracle_free(p)
+    return out, u

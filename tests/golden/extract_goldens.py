@@ -143,5 +143,21 @@ def main():
         json.dump(usage, f, indent=1)
 
 
+def bedrock_stream():
+    """internal/translator/openai_awsbedrock_test.go:1308-1391,1859: a real captured ConverseStream response (AWS eventstream
+    frames, base64) and the exact OpenAI SSE text the translator must produce for it (id "123", created 1731679200,
+    model "claude-sonnet-4"), fed one byte per call in the reference test."""
+    src = open(os.path.join(REF, "internal/translator/openai_awsbedrock_test.go"), encoding="utf-8").read()
+    m = re.search(r'const base64RealStreamingEvents = "([^"]+)"', src)
+    i = src.index("normalizedResults = append(normalizedResults, []byte(\"data: [DONE]")
+    j = src.index("`", i)
+    k = src.index("`", j + 1)
+    out = {"source": "internal/translator/openai_awsbedrock_test.go:1308-1391,1859", "eventstream_base64": m.group(1), "expected_sse": src[j + 1:k],
+           "response_id": "123", "created": 1731679200, "request_model": "claude-sonnet-4", "expect_output_tokens": 75, "expect_input_tokens": 386}
+    with open(os.path.join(OUT, "bedrock_stream_real.json"), "w", encoding="utf-8") as f:
+        json.dump(out, f, indent=1)
+
+
 if __name__ == "__main__":
     main()
+    bedrock_stream()

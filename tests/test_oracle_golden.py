@@ -78,3 +78,44 @@ def test_streaming_golden_usage_and_model():
                                    (1e-6, "0.000001"), (1e-7, "1e-7"), (0.5, "0.5"), (123456.789, "123456.789"), (-2.5e-9, "-2.5e-9"), (3.0e25, "3e+25")])
 def test_go_float_format(v, exp):
     assert O.fmt_f64(v) == exp
+
+
+def test_bedrock_real_stream_golden():
+    """internal/translator/openai_awsbedrock_test.go:1308-1391: the captured ConverseStream response, one byte per call,
+    must yield exactly the expected OpenAI SSE text; usage 386/75/461."""
+    import base64, zlib
+    g = json.load(open(os.path.join(G, "bedrock_stream_real.json"), encoding="utf-8"))
+    data = base64.b64decode(g["eventstream_base64"])
+    assert O.lib().oracle_crc32(data[:8], 8) == zlib.crc32(data[:8])
+    for sizes in (None, [1] * len(data), [7] * (len(data) // 7) + ([len(data) % 7] if len(data) % 7 else [])):
+        out, u = O.bedrock_stream(data, sizes, g["request_model"].encode(), g["response_id"].encode(), g["created"])
+        assert out.decode() == g["expected_sse"]
+        assert u.as_tuple() == (386, -1, -1, 75, 461, -1)
+
+
+def _encode_frames(lines):
+    """What the reference's fake upstream does (tests/internal/testupstreamlib/server.go:330-380): one frame per JSON line,
+    :event-type derived from the line's keys, then an "end" frame."""
+    import struct, zlib
+    def frame(headers, payload):
+        hb = b"".join(bytes([len(k)]) + k + b"\x07" + struct.pack(">H", len(v)) + v for k, v in headers)
+        total = 16 + len(hb) + len(payload)
+        pre = struct.pack(">II", total, len(hb)); pre += struct.pack(">I", zlib.crc32(pre))
+        msg = pre + hb + payload
+        return msg + struct.pack(">I", zlib.crc32(msg))
+    out = b""
+    for line in lines:
+        if not line: continue
+        d = json.loads(line)
+        et = "messageStart" if "role" in d else "contentBlockStart" if "start" in d else "contentBlockDelta" if "delta" in d else "messageStop" if "stopReason" in d else "metadata" if "usage" in d else "contentBlockStop" if "contentBlockIndex" in d else ""
+        out += frame([(b":event-type", et.encode())], line)
+    return out + frame([(b"event-type", b"end")], b"this-is-end")
+
+
+@pytest.mark.parametrize("name", ["aws - /v1/chat/completions - streaming with tool use", "aws-bedrock - /v1/chat/completions - streaming with thinking config"])
+def test_bedrock_stream_dataplane_goldens(name):
+    """tests/data-plane/testupstream_test.go:427-447,470-478 (exact text; created normalised to 123 by the test, id from x-amzn-requestid)."""
+    c = next(c for c in CASES if c["name"] == name)
+    data = _encode_frames([l.strip().encode() for l in c["responseBody"].split("\n")])
+    out, u = O.bedrock_stream(data, None, b"something", b"2bc5b090-a26c-4007-9467-ce5adc4ffa1d", 123)
+    assert out.decode() == c["expResponseBody"]
