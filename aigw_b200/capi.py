@@ -16,15 +16,24 @@ assert DocResult.itemsize == 32
 SseResult = np.dtype([("input", "<u4"), ("output", "<u4"), ("total", "<u4"), ("cached", "<u4"), ("cache_creation", "<u4"), ("reasoning", "<u4"),
                       ("mask", "<u4"), ("_pad", "<u4"), ("model_off", "<u8"), ("model_len", "<u4"), ("status", "<u4")])
 assert SseResult.itemsize == 48
+StreamResult = np.dtype([("out_off", "<u8"), ("out_len", "<u4"), ("status", "<u4"),
+                         ("input", "<u4"), ("output", "<u4"), ("total", "<u4"), ("cached", "<u4"), ("cache_creation", "<u4"), ("reasoning", "<u4"), ("mask", "<u4"), ("_pad", "<u4"),
+                         ("consumed", "<u8"), ("n_chunks", "<u4"), ("reason", "<u4")])
+assert StreamResult.itemsize == 64
 
 EXPORTS = ["aigw_version", "aigw_init", "aigw_destroy", "aigw_last_error", "aigw_device_sm_count", "aigw_host_alloc", "aigw_host_free",
            "aigw_device_alloc", "aigw_device_free", "aigw_memcpy_h2d", "aigw_memcpy_d2h", "aigw_memset_d", "aigw_sync",
-           "aigw_chat_translate_device", "aigw_chat_last_profile", "aigw_chat_translate_host", "aigw_sse_usage_device", "aigw_sse_usage_host", "aigw_response_usage_device", "aigw_response_usage_host", "aigw_usage_costs_device"]
+           "aigw_chat_translate_device", "aigw_chat_last_profile", "aigw_chat_translate_host", "aigw_sse_usage_device", "aigw_sse_usage_host", "aigw_response_usage_device", "aigw_response_usage_host", "aigw_usage_costs_device",
+           "aigw_bedrock_stream_device", "aigw_bedrock_stream_host"]
 
 
 class BackendCfg(C.Structure):
     _fields_ = [("schema", C.c_int32), ("cost_configured", C.c_int32), ("force_body_mutation", C.c_int32),
                 ("model_name_override", C.c_char_p), ("openai_prefix", C.c_char_p), ("api_version", C.c_char_p)]
+
+
+class BedrockStreamCfg(C.Structure):
+    _fields_ = [("created", C.c_int64), ("response_id", C.c_char_p), ("request_model", C.c_char_p)]
 
 
 class _BatchOut(C.Structure):
@@ -69,6 +78,10 @@ def load_library():
     L.aigw_response_usage_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     L.aigw_response_usage_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
     L.aigw_usage_costs_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.aigw_bedrock_stream_device.argtypes = [C.c_void_p, C.POINTER(BedrockStreamCfg), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    L.aigw_bedrock_stream_host.argtypes = [C.c_void_p, C.POINTER(BedrockStreamCfg), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
+                                           C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -198,6 +211,27 @@ class Context:
         self._check(self.L.aigw_sse_usage_host(self.h, bytes_arr.ctypes.data, chunk_off.ctypes.data, chunk_first.ctypes.data, n_streams, n_chunks,
                                                res.ctypes.data, C.byref(h2d), C.byref(d2h), C.byref(ms)), "sse_usage_host")
         return res, {"h2d_bytes": h2d.value, "d2h_bytes": d2h.value, "kernel_ms": ms.value}
+
+    # ---- Bedrock eventstream → OpenAI SSE
+    def bedrock_stream_host(self, bytes_arr, stream_off, request_model="", response_id="", created=0, out_capacity=None):
+        """streams = bytes_arr[stream_off[i]:stream_off[i+1]].  Returns (results, out bytes array, info)."""
+        n = len(stream_off) - 1
+        cfg = BedrockStreamCfg(created, response_id.encode(), request_model.encode())
+        cap = int(out_capacity if out_capacity is not None else 4 * len(bytes_arr) + 512 * n + 4096)
+        out = np.zeros(cap, dtype=np.uint8)
+        res = np.zeros(n, dtype=StreamResult)
+        used, h2d, d2h, ms = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_float(0)
+        so = np.ascontiguousarray(stream_off, dtype=np.uint64)
+        self._check(self.L.aigw_bedrock_stream_host(self.h, C.byref(cfg), bytes_arr.ctypes.data, so.ctypes.data, n, out.ctypes.data, cap, res.ctypes.data,
+                                                    C.byref(used), C.byref(h2d), C.byref(d2h), C.byref(ms)), "bedrock_stream_host")
+        return res, out, {"out_used": used.value, "h2d_bytes": h2d.value, "d2h_bytes": d2h.value, "kernel_ms": ms.value}
+
+    def bedrock_stream_device(self, d_bytes, d_stream_off, n_streams, total_bytes, d_out, out_capacity, d_res, d_used, request_model="", response_id="", created=0, timed=True):
+        cfg = BedrockStreamCfg(created, response_id.encode(), request_model.encode())
+        ms = C.c_float(0)
+        self._check(self.L.aigw_bedrock_stream_device(self.h, C.byref(cfg), d_bytes, d_stream_off, n_streams, total_bytes, d_out, out_capacity, d_res, d_used, None,
+                                                      C.byref(ms) if timed else None), "bedrock_stream_device")
+        return ms.value
 
     def response_usage_host(self, arena, offs, lens, cost_types=()):
         n = len(lens)

@@ -9,6 +9,7 @@
 
 #include "chat_kernel.cuh"
 #include "sse_kernel.cuh"
+#include "bedrock_stream_kernel.cuh"
 
 using namespace aigw;
 
@@ -47,6 +48,10 @@ struct aigw_ctx {
   uint64_t* d_sse_coff = nullptr; size_t sse_coff_cap = 0;
   uint32_t* d_sse_first = nullptr; size_t sse_first_cap = 0;
   aigw_sse_result* d_sse_res = nullptr; size_t sse_res_cap = 0;
+  // bedrock stream workspace (records + counts) and host-API buffers
+  uint8_t* d_bs_work = nullptr; size_t bs_work_cap = 0;
+  uint8_t* d_bs_out = nullptr; size_t bs_out_cap = 0;
+  unsigned long long* d_bs_used = nullptr; size_t bs_used_cap = 0;
 };
 
 static void fill_params(ChatParams& P, const aigw_backend_cfg* cfg) {
@@ -122,7 +127,7 @@ void aigw_destroy(aigw_ctx* ctx) {
   }
   cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_res); cudaFree(ctx->d_counters); cudaFree(ctx->d_work); cudaFree(ctx->d_used_arr); cudaFreeHost(ctx->h_used_arr);
   for (auto& e2 : ctx->stage_ev) cudaEventDestroy(e2);
-  cudaFree(ctx->d_sse_bytes); cudaFree(ctx->d_sse_coff); cudaFree(ctx->d_sse_first); cudaFree(ctx->d_sse_res);
+  cudaFree(ctx->d_sse_bytes); cudaFree(ctx->d_sse_coff); cudaFree(ctx->d_sse_first); cudaFree(ctx->d_sse_res); cudaFree(ctx->d_bs_work); cudaFree(ctx->d_bs_out); cudaFree(ctx->d_bs_used);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->s_compute); cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
   delete ctx;
@@ -302,6 +307,70 @@ int aigw_sse_usage_host(aigw_ctx* ctx, const uint8_t* bytes, const uint64_t* chu
   if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
   if (h2d_bytes) *h2d_bytes = nbytes + ((uint64_t)n_chunks + 1) * 8 + ((uint64_t)n_streams + 1) * 4;
   if (d2h_bytes) *d2h_bytes = (uint64_t)n_streams * sizeof(aigw_sse_result);
+  return 0;
+}
+
+// ------------------------------------------------------------------ S2: Bedrock eventstream → OpenAI SSE
+static bool plain_json_text(const char* s) { for (; *s; s++) { unsigned char c = (unsigned char)*s; if (c < 0x20 || c > 0x7e || c == '"' || c == '\\') return false; } return true; }
+static int fill_stream_params(aigw_ctx* ctx, BedrockStreamParams& P, const aigw_bedrock_stream_cfg* cfg) {
+  memset(P.id, 0, sizeof P.id); memset(P.model, 0, sizeof P.model); P.id_len = P.model_len = 0; P.created = cfg ? cfg->created : 0;
+  const char* id = cfg && cfg->response_id ? cfg->response_id : ""; const char* model = cfg && cfg->request_model ? cfg->request_model : "";
+  if (strlen(id) > sizeof P.id || strlen(model) > sizeof P.model || !plain_json_text(id) || !plain_json_text(model)) { ctx->err = "response_id/request_model need JSON escaping or exceed 128 bytes"; return -2; }
+  P.id_len = (uint32_t)strlen(id); memcpy(P.id, id, P.id_len); P.model_len = (uint32_t)strlen(model); memcpy(P.model, model, P.model_len);
+  return 0;
+}
+int aigw_bedrock_stream_device(aigw_ctx* ctx, const aigw_bedrock_stream_cfg* cfg, const uint8_t* d_bytes, const uint64_t* d_stream_off, uint32_t n_streams,
+                               uint64_t total_bytes, uint8_t* d_out, uint64_t out_capacity, aigw_stream_result* d_results, uint64_t* d_out_used,
+                               void* stream, float* kernel_ms) {
+  if (kernel_ms) *kernel_ms = 0;
+  if (n_streams == 0) return 0;
+  cudaSetDevice(ctx->device);
+  BedrockStreamParams P;
+  if (int rc = fill_stream_params(ctx, P, cfg)) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->s_compute;
+  ENSURE(ctx->d_bs_work, ctx->bs_work_cap, bedrock_work_bytes(total_bytes, n_streams), false);
+  P.bytes = d_bytes; P.stream_off = d_stream_off; P.n_streams = n_streams; P.out = d_out; P.out_capacity = out_capacity; P.results = d_results;
+  P.out_used = (unsigned long long*)d_out_used;
+  P.rec_count = (uint32_t*)ctx->d_bs_work;
+  P.recs = (BedrockRec*)(ctx->d_bs_work + (((size_t)n_streams * 4 + 255) & ~(size_t)255));
+  ctx->counter_next = (ctx->counter_next + 1) & ~1;   // two adjacent counters
+  P.next = ctx->d_counters + (ctx->counter_next & 255); ctx->counter_next += 2;
+  CK(cudaMemsetAsync(d_out_used, 0, sizeof(uint64_t), st));
+  if (kernel_ms) CK(cudaEventRecord(ctx->ev0, st));
+  CK(launch_bedrock_stream(P, ctx->sm_count, st));
+  if (kernel_ms) { CK(cudaEventRecord(ctx->ev1, st)); CK(cudaEventSynchronize(ctx->ev1)); CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1)); }
+  return 0;
+}
+int aigw_bedrock_stream_host(aigw_ctx* ctx, const aigw_bedrock_stream_cfg* cfg, const uint8_t* bytes, const uint64_t* stream_off, uint32_t n_streams,
+                             uint8_t* out, uint64_t out_capacity, aigw_stream_result* results, uint64_t* out_used,
+                             uint64_t* h2d_bytes, uint64_t* d2h_bytes, float* kernel_ms) {
+  if (out_used) *out_used = 0;
+  if (n_streams == 0) return 0;
+  cudaSetDevice(ctx->device);
+  const uint64_t base = stream_off[0], nbytes = stream_off[n_streams] - base;
+  if (base != 0) { ctx->err = "stream_off[0] must be 0"; return -2; }
+  ENSURE(ctx->d_sse_bytes, ctx->sse_bytes_cap, nbytes + 64, false);
+  ENSURE(ctx->d_sse_coff, ctx->sse_coff_cap, ((size_t)n_streams + 1) * 8, false);
+  ENSURE(ctx->d_sse_res, ctx->sse_res_cap, (size_t)n_streams * sizeof(aigw_stream_result), false);
+  ENSURE(ctx->d_bs_out, ctx->bs_out_cap, out_capacity + 64, false);
+  ENSURE(ctx->d_bs_used, ctx->bs_used_cap, 64, false);
+  cudaStream_t st = ctx->s_compute;
+  CK(cudaMemcpyAsync(ctx->d_sse_bytes, bytes, nbytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_sse_coff, stream_off, ((size_t)n_streams + 1) * 8, cudaMemcpyHostToDevice, st));
+  float ms = 0;
+  if (int rc = aigw_bedrock_stream_device(ctx, cfg, ctx->d_sse_bytes, ctx->d_sse_coff, n_streams, nbytes, ctx->d_bs_out, out_capacity,
+                                          (aigw_stream_result*)ctx->d_sse_res, (uint64_t*)ctx->d_bs_used, st, &ms)) return rc;
+  unsigned long long used = 0;
+  CK(cudaMemcpyAsync(&used, ctx->d_bs_used, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(results, ctx->d_sse_res, (size_t)n_streams * sizeof(aigw_stream_result), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (used > out_capacity) used = out_capacity;
+  CK(cudaMemcpyAsync(out, ctx->d_bs_out, used, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (out_used) *out_used = used;
+  if (kernel_ms) *kernel_ms = ms;
+  if (h2d_bytes) *h2d_bytes = nbytes + ((uint64_t)n_streams + 1) * 8;
+  if (d2h_bytes) *d2h_bytes = used + (uint64_t)n_streams * sizeof(aigw_stream_result) + 8;
   return 0;
 }
 

@@ -152,11 +152,11 @@ __global__ void __launch_bounds__(kWarps * 32) sse_usage_kernel(const __grid_con
           const int e = lstart[li];
           const uint8_t* q = tile + b; const int n = e - b;
           if (n >= 6 && q[0] == 'd' && q[1] == 'a' && q[2] == 't' && q[3] == 'a' && q[4] == ':' && q[5] == ' ') {
-            Capture cp; cp.int_set = 0; cp.obj_seen = 0; cp.span_set = 0; cp.weird = 0;
+            Capture cp; cp.int_set = 0; cp.obj_seen = 0; cp.span_set = 0; cp.span_esc = 0; cp.weird = 0; cp.big = 0;
 #pragma unroll
             for (int k = 0; k < 8; k++) cp.ints[k] = 0;
             const bool ok = walk(q + 6, n - 6, sch->nodes, sch->fields, sch->keys, N_ROOT, cp);
-            if (cp.weird) status = AIGW_DECLINED;
+            if (cp.weird || (cp.span_esc & 1u)) status = AIGW_DECLINED;
             if (ok) {
               const uint32_t seq = line_no + li + 1;
               if ((cp.span_set & 1u) && cp.span_len[0] > 0) { seq_m = seq; m_off = tile_base + (uint64_t)b + 6 + cp.span_off[0]; m_len = cp.span_len[0]; }
@@ -268,12 +268,12 @@ __global__ void __launch_bounds__(128) response_usage_kernel(const uint8_t* bodi
   const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= n) return;
   const uint8_t* p = bodies + offsets[d];
-  Capture cp; cp.int_set = 0; cp.obj_seen = 0; cp.span_set = 0; cp.weird = 0;
+  Capture cp; cp.int_set = 0; cp.obj_seen = 0; cp.span_set = 0; cp.span_esc = 0; cp.weird = 0; cp.big = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) cp.ints[k] = 0;
   const bool ok = walk(p, (int)lens[d], sch.nodes, sch.fields, sch.keys, R_ROOT, cp, /*allow_trailing=*/true);
   aigw_sse_result r; memset(&r, 0, sizeof r);
-  if (cp.weird) r.status = AIGW_DECLINED;
+  if (cp.weird || (cp.span_esc & 1u)) r.status = AIGW_DECLINED;
   else if (!ok) r.status = AIGW_INTERNAL;  // "failed to unmarshal body": the reference fails the request
   else {
     // resp.Usage is a value: the three counters are always set; details only when their object was present

@@ -17,14 +17,18 @@ struct Field { uint16_t koff; uint8_t klen; uint8_t node; };  // key bytes at ke
 struct Node { uint8_t kind; uint8_t cap; uint8_t f0; uint8_t nf; uint8_t elem; };
 
 // Capture sink: up to 8 integer captures (uint32 wrap), 2 span captures, "object present" bits.
-struct Capture {
+template <int NSPANS>
+struct CaptureT {
   uint32_t ints[8];
   uint32_t int_set;        // bit i: ints[i] was written
   uint32_t obj_seen;       // bit cap: a non-null object with that capture id was decoded
-  uint32_t span_off[2], span_len[2];
+  uint32_t span_off[NSPANS], span_len[NSPANS];
   uint32_t span_set;       // bit i
-  uint32_t weird;          // escape in a key or captured span, duplicate known key: caller must not trust the result
+  uint32_t span_esc;       // bit i: the captured string contains a backslash
+  uint32_t weird;          // escape in a key, duplicate known key, nesting too deep: caller must not trust the result
+  uint32_t big;            // a captured integer does not fit in 31 bits
 };
+using Capture = CaptureT<2>;
 
 __device__ __forceinline__ bool ws(uint32_t c) { return c == ' ' || c == '\n' || c == '\r' || c == '\t'; }
 __device__ __forceinline__ bool dig(uint32_t c) { return c - '0' < 10u; }
@@ -63,7 +67,7 @@ __device__ inline int scan_number(const uint8_t* p, int i, int n, bool& is_int, 
 }
 __device__ inline bool lit(const uint8_t* p, int i, int n, const char* w, int l) { if (i + l > n) return false; for (int k = 0; k < l; k++) if (p[i + k] != (uint8_t)w[k]) return false; return true; }
 // strconv.ParseInt(s, 10, 64) on -?digits: false on overflow.  out = low 32 bits (Go uint32(int) conversion).
-__device__ inline bool parse_i64(const uint8_t* p, int b, int e, uint32_t& low32) {
+__device__ inline bool parse_i64(const uint8_t* p, int b, int e, uint32_t& low32, bool* big = nullptr) {
   bool neg = p[b] == '-'; if (neg) b++;
   unsigned long long v = 0;
   for (int i = b; i < e; i++) {
@@ -73,6 +77,7 @@ __device__ inline bool parse_i64(const uint8_t* p, int b, int e, uint32_t& low32
   }
   if (neg) { if (v > 0x8000000000000000ull) return false; low32 = (uint32_t)(0ull - v); }
   else { if (v > 0x7FFFFFFFFFFFFFFFull) return false; low32 = (uint32_t)v; }
+  if (big) *big = neg ? v != 0 : (v >> 31) != 0;
   return true;
 }
 
@@ -133,7 +138,8 @@ __device__ inline int skip_any(const uint8_t* p, int i, int n) {
 }
 
 // Typed walk of p[0..n).  Returns true when json.Unmarshal into the schema's root type would succeed.
-__device__ inline bool walk(const uint8_t* p, int n, const Node* nodes, const Field* fields, const char* keys, int root, Capture& cap, bool allow_trailing = false) {
+template <class CAP>
+__device__ inline bool walk(const uint8_t* p, int n, const Node* nodes, const Field* fields, const char* keys, int root, CAP& cap, bool allow_trailing = false) {
   const int MAXD = 12;
   uint8_t st_node[MAXD]; uint32_t st_seen[MAXD];
   int sp = 0;
@@ -163,14 +169,14 @@ __device__ inline bool walk(const uint8_t* p, int n, const Node* nodes, const Fi
           for (int k = 0; k < L; k++) { uint32_t ch = q[k]; if (ch < 0x20) cap.weird = 1; bool ok = (ch - 'A' < 26u) || (ch - 'a' < 26u) || (ch - '0' < 10u) || ch == '+' || ch == '/' || (ch == '=' && k >= L - 2); if (!ok) return false; }
           if (L >= 2 && q[L - 2] == '=' && q[L - 1] != '=') return false;
         }
-        if (nd.cap != 0xff) { uint32_t s = nd.cap & 1; cap.span_off[s] = i + 1; cap.span_len[s] = j - i - 2; cap.span_set |= 1u << s; if (e) cap.weird = 1; }
+        if (nd.cap != 0xff) { const uint32_t s = nd.cap; cap.span_off[s] = i + 1; cap.span_len[s] = j - i - 2; cap.span_set |= 1u << s; if (e) cap.span_esc |= 1u << s; else cap.span_esc &= ~(1u << s); }
         i = j; break;
       }
       case K_INT: case K_FLOAT: case K_CREATED: {
         if (!(c == '-' || dig(c))) return false;
         bool ii; int ie; int j = scan_number(p, i, n, ii, ie); if (j < 0) return false;
         if (j < n && !delim(p[j])) return false;
-        if (nd.kind == K_INT) { if (!ii) return false; uint32_t v; if (!parse_i64(p, i, j, v)) return false; if (nd.cap != 0xff) { cap.ints[nd.cap] = v; cap.int_set |= 1u << nd.cap; } }
+        if (nd.kind == K_INT) { if (!ii) return false; uint32_t v; bool bg = false; if (!parse_i64(p, i, j, v, &bg)) return false; if (nd.cap != 0xff) { cap.ints[nd.cap] = v; cap.int_set |= 1u << nd.cap; if (bg) cap.big = 1; } }
         else if (nd.kind == K_CREATED) {  // integer part up to '.', exponent without '.' fails ParseInt
           if (!ii && (ie >= j || p[ie] != '.')) return false;
           uint32_t v; if (!parse_i64(p, i, ie, v)) return false;

@@ -153,6 +153,29 @@ int aigw_response_usage_host(aigw_ctx* ctx, const uint8_t* bodies, const uint64_
 int aigw_usage_costs_device(aigw_ctx* ctx, const aigw_sse_result* d_results, uint32_t n, const int32_t* d_cost_types, uint32_t n_costs,
                             uint64_t* d_costs, void* stream);
 
+/* ---- streamed Bedrock responses: AWS eventstream frames → OpenAI SSE text (S2) ----
+ * Replaces openAIToAWSBedrockTranslatorV1ChatCompletion.ResponseBody with stream=true
+ * (internal/translator/openai_awsbedrock.go:695-732: extractAmazonEventStreamEvents :829-852, convertEvent :858-1006,
+ * stop-reason map :601-621, usage arithmetic internal/metrics/metrics.go:292-307).  Stream s is the concatenation of every
+ * upstream response chunk of one request, bytes[stream_off[s] .. stream_off[s+1]); the SSE text the reference returns does
+ * not depend on where the chunk boundaries fell, so the result is the concatenation of all its ResponseBody mutations
+ * including the final "data: [DONE]\n" (end of stream).  Output of stream s: out[out_off .. out_off+out_len).
+ * `usage` is the Override merge over per-frame calls (latest set field wins).  A frame that fails the eventstream decoder
+ * (CRC, header layout) blocks the stream exactly as the reference's buffered decoder does: nothing after it is emitted,
+ * `consumed` (< stream length) tells where.  status: 0, or AIGW_DECLINED (reason: AIGW_R_UNSUPPORTED_FIELD = a string the
+ * encoder would re-escape / redactedContent / counters beyond 2^31; AIGW_R_TOO_LARGE = a frame above 8 KiB;
+ * AIGW_R_ARENA_FULL) — run the stock path for that stream.
+ * response_id / request_model (cfg) must not need JSON escaping (printable ASCII without '"' and '\\', ≤ 128 bytes);
+ * otherwise the call returns -2. */
+typedef struct aigw_stream_result { uint64_t out_off; uint32_t out_len; uint32_t status; aigw_usage usage; uint64_t consumed; uint32_t n_chunks; uint32_t reason; } aigw_stream_result; /* 64 bytes */
+typedef struct aigw_bedrock_stream_cfg { int64_t created; const char* response_id; const char* request_model; } aigw_bedrock_stream_cfg;
+int aigw_bedrock_stream_device(aigw_ctx* ctx, const aigw_bedrock_stream_cfg* cfg, const uint8_t* d_bytes, const uint64_t* d_stream_off, uint32_t n_streams,
+                               uint64_t total_bytes, uint8_t* d_out, uint64_t out_capacity, aigw_stream_result* d_results, uint64_t* d_out_used,
+                               void* stream, float* kernel_ms);
+int aigw_bedrock_stream_host(aigw_ctx* ctx, const aigw_bedrock_stream_cfg* cfg, const uint8_t* bytes, const uint64_t* stream_off, uint32_t n_streams,
+                             uint8_t* out /* host */, uint64_t out_capacity, aigw_stream_result* results /* host, n_streams */, uint64_t* out_used,
+                             uint64_t* h2d_bytes, uint64_t* d2h_bytes, float* kernel_ms);
+
 const char* aigw_version(void);
 
 #ifdef __cplusplus

@@ -183,3 +183,100 @@ def diverse_body(seed):
     if r.random() < 0.03:
         body = body[: r.randint(1, len(body) - 1)]  # truncated ⇒ malformed
     return body.encode("utf-8")
+
+
+# ---------------------------------------------------------------- Bedrock ConverseStream (AWS eventstream) corpora
+def es_frame(headers, payload: bytes, corrupt=None) -> bytes:
+    """One AWS eventstream message: [total u32][headers_len u32][prelude crc][headers][payload][message crc] (big endian, IEEE CRC-32).
+    headers: list of (name bytes, type int, value bytes); type 7 values get their u16 length prefix here."""
+    import struct, zlib
+    hb = b""
+    for k, t, v in headers:
+        hb += bytes([len(k)]) + k + bytes([t]) + (struct.pack(">H", len(v)) + v if t in (6, 7) else v)
+    total = 16 + len(hb) + len(payload)
+    pre = struct.pack(">II", total, len(hb))
+    pcrc = zlib.crc32(pre) ^ (1 if corrupt == "prelude" else 0)
+    msg = pre + struct.pack(">I", pcrc) + hb + payload
+    mcrc = zlib.crc32(msg) ^ (1 if corrupt == "message" else 0)
+    return msg + struct.pack(">I", mcrc)
+
+
+def es_event(event_type: str, payload: bytes, extra_headers=True, corrupt=None) -> bytes:
+    h = [(b":event-type", 7, event_type.encode())]
+    if extra_headers:
+        h += [(b":content-type", 7, b"application/json"), (b":message-type", 7, b"event")]
+    return es_frame(h, payload, corrupt)
+
+
+_WORDS = ["Hello", " world", "!", " The", " quick", " brown", " fox", "\\n", " \\\"quoted\\\"", " café", " 日本", " tab\\t", " back\\\\slash", " a", " of", " and", " 42", ".", ","]
+
+
+def bedrock_stream_bytes(rng, kind="plain") -> bytes:
+    """One ConverseStream response as eventstream bytes.  kind: plain | tools | reasoning | cache | odd (decoder / schema corner cases)."""
+    import json as _json
+    pad = lambda: '"p":"' + "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789"[: int(rng.integers(1, 40))] + '"'
+    fr = []
+    fr.append(es_event("messageStart", ('{' + pad() + ',"role":"assistant"}').encode()))
+    blk = 0
+    if kind == "reasoning":
+        for _ in range(int(rng.integers(1, 6))):
+            t = "".join(_WORDS[int(i)] for i in rng.integers(0, len(_WORDS), int(rng.integers(1, 8))))
+            fr.append(es_event("contentBlockDelta", ('{"contentBlockIndex":%d,"delta":{"reasoningContent":{"text":"%s"}},%s}' % (blk, t, pad())).encode()))
+        fr.append(es_event("contentBlockDelta", ('{"contentBlockIndex":%d,"delta":{"reasoningContent":{"signature":"c2lnbmF0dXJl%d"}},%s}' % (blk, int(rng.integers(0, 1000)), pad())).encode()))
+        fr.append(es_event("contentBlockStop", ('{"contentBlockIndex":%d,%s}' % (blk, pad())).encode())); blk += 1
+    for _ in range(int(rng.integers(1, 40))):
+        t = "".join(_WORDS[int(i)] for i in rng.integers(0, len(_WORDS), int(rng.integers(1, 10))))
+        fr.append(es_event("contentBlockDelta", ('{"contentBlockIndex":%d,"delta":{"text":"%s"},%s}' % (blk, t, pad())).encode()))
+    fr.append(es_event("contentBlockStop", ('{"contentBlockIndex":%d,%s}' % (blk, pad())).encode())); blk += 1
+    stop = "end_turn"
+    if kind == "tools":
+        for k in range(int(rng.integers(1, 4))):
+            fr.append(es_event("contentBlockStart", ('{"contentBlockIndex":%d,%s,"start":{"toolUse":{"name":"get_weather_%d","toolUseId":"tooluse_%08x"}}}' % (blk, pad(), k, int(rng.integers(0, 2**31)))).encode()))
+            args = _json.dumps({"location": "San Francisco, CA", "unit": "celsius", "n": k})
+            for i in range(0, len(args), 9):
+                fr.append(es_event("contentBlockDelta", ('{"contentBlockIndex":%d,"delta":{"toolUse":{"input":%s}},%s}' % (blk, _json.dumps(args[i:i + 9]), pad())).encode()))
+            fr.append(es_event("contentBlockStop", ('{"contentBlockIndex":%d,%s}' % (blk, pad())).encode())); blk += 1
+        stop = "tool_use"
+    else:
+        stop = ["end_turn", "max_tokens", "stop_sequence", "content_filtered", "guardrail_intervened"][int(rng.integers(0, 5))]
+    fr.append(es_event("messageStop", ('{%s,"stopReason":"%s"}' % (pad(), stop)).encode()))
+    usage = '"inputTokens":%d,"outputTokens":%d,"totalTokens":%d' % (int(rng.integers(0, 5000)), int(rng.integers(0, 3000)), int(rng.integers(0, 8000)))
+    if kind == "cache":
+        usage += ',"cacheReadInputTokens":%d,"cacheWriteInputTokens":%d' % (int(rng.integers(0, 3)) * 128, int(rng.integers(0, 3)) * 64)
+    tier = ',"serviceTier":{"type":"priority"}' if kind == "cache" and rng.integers(0, 2) else ""
+    fr.append(es_event("metadata", ('{"metrics":{"latencyMs":%d},%s,"usage":{%s}%s}' % (int(rng.integers(100, 9000)), pad(), usage, tier)).encode()))
+    if kind == "odd":
+        extras = [
+            es_event("metadata", b'{"usage":null}'), es_event("metadata", b'{"metrics":{"latencyMs":1}}'),
+            es_event("messageStart", b'{"role":null}'), es_event("messageStart", b'{"role":""}'), es_event("contentBlockDelta", b'{"delta":{}}'),
+            es_event("contentBlockDelta", b'{"delta":null}'), es_event("contentBlockStart", b'{"start":{}}'), es_event("contentBlockStart", b'{"start":{"toolUse":{}}}'),
+            es_event("contentBlockDelta", b'{"delta":{"text":""}}'), es_event("contentBlockDelta", b'{"delta":{"toolUse":{"input":null}}}'),
+            es_event("contentBlockDelta", b'{"delta":{"reasoningContent":{}}}'), es_event("contentBlockDelta", b'{"delta":{"reasoningContent":{"redactedContent":""}}}'),
+            es_event("somethingElse", b'{"a":1}'), es_event("contentBlockDelta", b'not json'), es_event("contentBlockDelta", b'{"delta":{"text":5}}'),
+            es_event("contentBlockDelta", b'{"contentBlockIndex":1.5,"delta":{"text":"x"}}'), es_event("messageStop", b'{"stopReason":null}'), es_event("messageStop", b'{}'),
+            es_event("contentBlockStop", b'null'), es_event("contentBlockStop", b'{}'), es_event("messageStop", b' {"stopReason" : "tool_use" } '),
+            es_frame([(b"x", 0, b""), (b"y", 1, b""), (b"b", 2, b"\x01"), (b"s", 3, b"\x00\x01"), (b"i", 4, b"\x00\x00\x00\x01"), (b"l", 5, b"\x00" * 8), (b"bin", 6, b"abc"),
+                      (b"ts", 8, b"\x00" * 8), (b"uuid", 9, b"\x00" * 16), (b":event-type", 7, b"contentBlockDelta")], b'{"delta":{"text":"typed headers"}}'),
+            es_frame([], b'{"eventType":"contentBlockDelta","delta":{"text":"type from payload"}}'),
+            es_frame([(b":event-type", 6, b"contentBlockDelta")], b'{"delta":{"text":"bytes-typed header is ignored"}}'),
+            es_event("metadata", b'{"usage":{"inputTokens":7,"outputTokens":0,"totalTokens":7,"cacheReadInputTokens":null,"cacheWriteInputTokens":0}}'),
+            es_event("metadata", b'{"usage":{},"serviceTier":{"type":""}}'),
+            es_event("contentBlockStart", b'{"start":{"toolUse":{"name":"f","toolUseId":"id1"}}}'), es_event("contentBlockStop", b'{}'), es_event("contentBlockStop", b'{}'),
+            es_event("contentBlockStart", b'{"start":{"toolUse":{"name":"g","toolUseId":"id2"}}}'), es_event("contentBlockDelta", b'{"delta":{"toolUse":{"input":"{}"}}}'),
+        ]
+        order = rng.permutation(len(extras))
+        k = int(rng.integers(3, len(extras)))
+        pos = sorted(int(x) for x in rng.integers(1, len(fr), k))
+        for j, p in zip(order[:k], reversed(pos)):
+            fr.insert(p, extras[int(j)])
+    return b"".join(fr)
+
+
+def bedrock_stream_corpus(n, seed=0, kinds=("plain", "tools", "reasoning", "cache")):
+    """n streams → (bytes array, stream_off u64[n+1], list of per-stream bytes)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    streams = [bedrock_stream_bytes(rng, kinds[i % len(kinds)]) for i in range(n)]
+    off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum([len(s) for s in streams], out=off[1:])
+    return np.frombuffer(b"".join(streams), dtype=np.uint8).copy(), off, streams
