@@ -36,6 +36,11 @@ class BedrockStreamCfg(C.Structure):
     _fields_ = [("created", C.c_int64), ("response_id", C.c_char_p), ("request_model", C.c_char_p)]
 
 
+class _StreamBatchOut(C.Structure):
+    _fields_ = [("results", C.c_void_p), ("out", C.c_void_p), ("out_used", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("gpu_launches", C.c_uint32), ("kernel_ms", C.c_float)]
+
+
 class _BatchOut(C.Structure):
     _fields_ = [("results", C.c_void_p), ("out", C.c_void_p), ("out_used", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("gpu_launches", C.c_uint32), ("kernel_ms", C.c_float)]
@@ -80,8 +85,7 @@ def load_library():
     L.aigw_usage_costs_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.aigw_bedrock_stream_device.argtypes = [C.c_void_p, C.POINTER(BedrockStreamCfg), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
-    L.aigw_bedrock_stream_host.argtypes = [C.c_void_p, C.POINTER(BedrockStreamCfg), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
-                                           C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_float)]
+    L.aigw_bedrock_stream_host.argtypes = [C.c_void_p, C.POINTER(BedrockStreamCfg), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(_StreamBatchOut)]
     _lib = L
     return L
 
@@ -213,18 +217,19 @@ class Context:
         return res, {"h2d_bytes": h2d.value, "d2h_bytes": d2h.value, "kernel_ms": ms.value}
 
     # ---- Bedrock eventstream → OpenAI SSE
-    def bedrock_stream_host(self, bytes_arr, stream_off, request_model="", response_id="", created=0, out_capacity=None):
-        """streams = bytes_arr[stream_off[i]:stream_off[i+1]].  Returns (results, out bytes array, info)."""
+    def bedrock_stream_host(self, bytes_arr, stream_off, request_model="", response_id="", created=0, out_capacity=0):
+        """streams = bytes_arr[stream_off[i]:stream_off[i+1]].  Returns (results view, out bytes view, info); the views alias
+        library-owned pinned memory and stay valid until the next host call on this context."""
         n = len(stream_off) - 1
         cfg = BedrockStreamCfg(created, response_id.encode(), request_model.encode())
-        cap = int(out_capacity if out_capacity is not None else 4 * len(bytes_arr) + 512 * n + 4096)
-        out = np.zeros(cap, dtype=np.uint8)
-        res = np.zeros(n, dtype=StreamResult)
-        used, h2d, d2h, ms = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_float(0)
         so = np.ascontiguousarray(stream_off, dtype=np.uint64)
-        self._check(self.L.aigw_bedrock_stream_host(self.h, C.byref(cfg), bytes_arr.ctypes.data, so.ctypes.data, n, out.ctypes.data, cap, res.ctypes.data,
-                                                    C.byref(used), C.byref(h2d), C.byref(d2h), C.byref(ms)), "bedrock_stream_host")
-        return res, out, {"out_used": used.value, "h2d_bytes": h2d.value, "d2h_bytes": d2h.value, "kernel_ms": ms.value}
+        bo = _StreamBatchOut()
+        self._check(self.L.aigw_bedrock_stream_host(self.h, C.byref(cfg), bytes_arr.ctypes.data, so.ctypes.data, n, int(out_capacity), C.byref(bo)), "bedrock_stream_host")
+        if n == 0:
+            return np.zeros(0, dtype=StreamResult), np.zeros(0, dtype=np.uint8), {"out_used": 0, "h2d_bytes": 0, "d2h_bytes": 0, "kernel_ms": 0.0, "gpu_launches": 0}
+        res = np.ctypeslib.as_array(C.cast(bo.results, C.POINTER(C.c_uint8)), shape=(n * StreamResult.itemsize,)).view(StreamResult)
+        out = np.ctypeslib.as_array(C.cast(bo.out, C.POINTER(C.c_uint8)), shape=(max(1, bo.out_used),))
+        return res, out, {"out_used": bo.out_used, "h2d_bytes": bo.h2d_bytes, "d2h_bytes": bo.d2h_bytes, "kernel_ms": bo.kernel_ms, "gpu_launches": bo.gpu_launches}
 
     def bedrock_stream_device(self, d_bytes, d_stream_off, n_streams, total_bytes, d_out, out_capacity, d_res, d_used, request_model="", response_id="", created=0, timed=True):
         cfg = BedrockStreamCfg(created, response_id.encode(), request_model.encode())

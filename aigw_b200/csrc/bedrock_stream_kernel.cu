@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kWarps * 32) bedrock_frames_kernel(const __gri
     s = __shfl_sync(FULLM, s, 0);
     if (s >= P.n_streams) break;
     const uint64_t sb = P.stream_off[s], se = P.stream_off[s + 1];
-    BedrockRec* recs = P.recs + (sb >> 5) + 2ull * s;
+    BedrockRec* recs = P.recs + ((sb - P.off_base) >> 5) + 2ull * s;
     const uint32_t rec_cap = (uint32_t)((se - sb) >> 5) + 2u;
     uint32_t nrec = 0, out_total = 0;
     uint32_t status = 0, reason = 0;
@@ -431,10 +431,11 @@ __global__ void __launch_bounds__(kWarps * 32) bedrock_frames_kernel(const __gri
         const uint32_t total = out_total + (uint32_t)(sizeof(L_DONE) - 1);
         const unsigned long long o = atomicAdd(P.out_used, (unsigned long long)((total + 15u) & ~15u));
         if (o + total > P.out_capacity) { r.status = AIGW_DECLINED; r.reason = AIGW_R_ARENA_FULL; nrec = 0; }
-        else { r.out_off = o; r.out_len = total; r.usage = usage; }
+        else { r.out_off = o + P.out_bias; r.out_len = total; r.usage = usage; }
       }
       P.results[s] = r;
       P.rec_count[s] = r.status ? 0xffffffffu : nrec;
+      P.out_pos[s] = r.out_off - P.out_bias;
     }
   }
 }
@@ -453,9 +454,9 @@ __global__ void __launch_bounds__(kEmitWarps * 32) bedrock_emit_kernel(const __g
     const uint32_t nrec = P.rec_count[s];
     if (nrec == 0xffffffffu) continue;
     const uint64_t sb = P.stream_off[s];
-    const BedrockRec* recs = P.recs + (sb >> 5) + 2ull * s;
+    const BedrockRec* recs = P.recs + ((sb - P.off_base) >> 5) + 2ull * s;
     const uint8_t* src = P.bytes + sb;
-    uint8_t* g = P.out + P.results[s].out_off;
+    uint8_t* g = P.out + P.out_pos[s];
     // warp flush of tile[a .. a+len) to g (a == g & 15, so 16-byte stores line up on both sides)
     auto flush = [&](uint32_t len) {
       const uint32_t a = (uint32_t)((uintptr_t)g & 15u);
@@ -498,8 +499,14 @@ __global__ void __launch_bounds__(kEmitWarps * 32) bedrock_emit_kernel(const __g
 
 }  // namespace
 
+static size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
 size_t bedrock_work_bytes(uint64_t total_bytes, uint32_t n_streams) {
-  return (size_t)((total_bytes >> 5) + 2ull * n_streams + 2) * sizeof(BedrockRec) + (size_t)n_streams * 4 + 256;
+  return (size_t)((total_bytes >> 5) + 2ull * n_streams + 2) * sizeof(BedrockRec) + up256((size_t)n_streams * 4) + up256((size_t)n_streams * 8) + 256;
+}
+void bedrock_work_layout(BedrockStreamParams& P, uint8_t* work, uint32_t n_streams) {
+  P.rec_count = (uint32_t*)work; work += up256((size_t)n_streams * 4);
+  P.out_pos = (uint64_t*)work; work += up256((size_t)n_streams * 8);
+  P.recs = (BedrockRec*)work;
 }
 
 cudaError_t launch_bedrock_stream(const BedrockStreamParams& P, int sm_count, cudaStream_t st) {

@@ -39,20 +39,24 @@ static_assert(sizeof(BedrockRec) == 48, "record layout");
 
 struct BedrockStreamParams {
   const uint8_t* bytes;
-  const uint64_t* stream_off;    // n_streams+1
+  const uint64_t* stream_off;    // n_streams+1 (absolute offsets into `bytes`)
+  uint64_t off_base;             // stream_off[0]: workspace slots are relative to it
+  uint64_t out_bias;             // added to the reported out_off (sub-batches of one host call share an arena)
   uint32_t n_streams;
   uint8_t* out; uint64_t out_capacity;
   aigw_stream_result* results;
   unsigned long long* out_used;
   unsigned int* next;            // two work counters (frames kernel, emit kernel)
-  BedrockRec* recs;              // slot of stream s starts at stream_off[s]/32 + 2*s
-  uint32_t* rec_count;           // n_streams
+  BedrockRec* recs;              // slot of stream s starts at (stream_off[s]-off_base)/32 + 2*s
+  uint32_t* rec_count;           // n_streams (0xffffffff: stream declined)
+  uint64_t* out_pos;             // n_streams: offset of the stream's text inside `out`
   long long created;
   uint32_t id_len, model_len;
   char id[128], model[128];      // response id / request model, already checked to need no JSON escaping
 };
 
 size_t bedrock_work_bytes(uint64_t total_bytes, uint32_t n_streams);
+void bedrock_work_layout(BedrockStreamParams& P, uint8_t* work, uint32_t n_streams);
 cudaError_t launch_bedrock_stream(const BedrockStreamParams& P, int sm_count, cudaStream_t st);
 
 }  // namespace aigw

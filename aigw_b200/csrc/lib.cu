@@ -50,8 +50,8 @@ struct aigw_ctx {
   aigw_sse_result* d_sse_res = nullptr; size_t sse_res_cap = 0;
   // bedrock stream workspace (records + counts) and host-API buffers
   uint8_t* d_bs_work = nullptr; size_t bs_work_cap = 0;
-  uint8_t* d_bs_out = nullptr; size_t bs_out_cap = 0;
-  unsigned long long* d_bs_used = nullptr; size_t bs_used_cap = 0;
+  uint64_t* d_bs_off[2] = {nullptr, nullptr}; size_t bs_off_cap[2] = {0, 0};
+  aigw_stream_result* h_sres = nullptr; size_t h_sres_cap = 0;
 };
 
 static void fill_params(ChatParams& P, const aigw_backend_cfg* cfg) {
@@ -127,7 +127,7 @@ void aigw_destroy(aigw_ctx* ctx) {
   }
   cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_res); cudaFree(ctx->d_counters); cudaFree(ctx->d_work); cudaFree(ctx->d_used_arr); cudaFreeHost(ctx->h_used_arr);
   for (auto& e2 : ctx->stage_ev) cudaEventDestroy(e2);
-  cudaFree(ctx->d_sse_bytes); cudaFree(ctx->d_sse_coff); cudaFree(ctx->d_sse_first); cudaFree(ctx->d_sse_res); cudaFree(ctx->d_bs_work); cudaFree(ctx->d_bs_out); cudaFree(ctx->d_bs_used);
+  cudaFree(ctx->d_sse_bytes); cudaFree(ctx->d_sse_coff); cudaFree(ctx->d_sse_first); cudaFree(ctx->d_sse_res); cudaFree(ctx->d_bs_work); cudaFree(ctx->d_bs_off[0]); cudaFree(ctx->d_bs_off[1]); cudaFreeHost(ctx->h_sres);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->s_compute); cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
   delete ctx;
@@ -329,10 +329,9 @@ int aigw_bedrock_stream_device(aigw_ctx* ctx, const aigw_bedrock_stream_cfg* cfg
   if (int rc = fill_stream_params(ctx, P, cfg)) return rc;
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->s_compute;
   ENSURE(ctx->d_bs_work, ctx->bs_work_cap, bedrock_work_bytes(total_bytes, n_streams), false);
-  P.bytes = d_bytes; P.stream_off = d_stream_off; P.n_streams = n_streams; P.out = d_out; P.out_capacity = out_capacity; P.results = d_results;
+  P.bytes = d_bytes; P.stream_off = d_stream_off; P.off_base = 0; P.out_bias = 0; P.n_streams = n_streams; P.out = d_out; P.out_capacity = out_capacity; P.results = d_results;
   P.out_used = (unsigned long long*)d_out_used;
-  P.rec_count = (uint32_t*)ctx->d_bs_work;
-  P.recs = (BedrockRec*)(ctx->d_bs_work + (((size_t)n_streams * 4 + 255) & ~(size_t)255));
+  bedrock_work_layout(P, ctx->d_bs_work, n_streams);
   ctx->counter_next = (ctx->counter_next + 1) & ~1;   // two adjacent counters
   P.next = ctx->d_counters + (ctx->counter_next & 255); ctx->counter_next += 2;
   CK(cudaMemsetAsync(d_out_used, 0, sizeof(uint64_t), st));
@@ -342,35 +341,76 @@ int aigw_bedrock_stream_device(aigw_ctx* ctx, const aigw_bedrock_stream_cfg* cfg
   return 0;
 }
 int aigw_bedrock_stream_host(aigw_ctx* ctx, const aigw_bedrock_stream_cfg* cfg, const uint8_t* bytes, const uint64_t* stream_off, uint32_t n_streams,
-                             uint8_t* out, uint64_t out_capacity, aigw_stream_result* results, uint64_t* out_used,
-                             uint64_t* h2d_bytes, uint64_t* d2h_bytes, float* kernel_ms) {
-  if (out_used) *out_used = 0;
+                             uint64_t out_capacity_hint, aigw_stream_batch_out* out) {
+  memset(out, 0, sizeof *out);
   if (n_streams == 0) return 0;
   cudaSetDevice(ctx->device);
-  const uint64_t base = stream_off[0], nbytes = stream_off[n_streams] - base;
-  if (base != 0) { ctx->err = "stream_off[0] must be 0"; return -2; }
-  ENSURE(ctx->d_sse_bytes, ctx->sse_bytes_cap, nbytes + 64, false);
-  ENSURE(ctx->d_sse_coff, ctx->sse_coff_cap, ((size_t)n_streams + 1) * 8, false);
-  ENSURE(ctx->d_sse_res, ctx->sse_res_cap, (size_t)n_streams * sizeof(aigw_stream_result), false);
-  ENSURE(ctx->d_bs_out, ctx->bs_out_cap, out_capacity + 64, false);
-  ENSURE(ctx->d_bs_used, ctx->bs_used_cap, 64, false);
-  cudaStream_t st = ctx->s_compute;
-  CK(cudaMemcpyAsync(ctx->d_sse_bytes, bytes, nbytes, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(ctx->d_sse_coff, stream_off, ((size_t)n_streams + 1) * 8, cudaMemcpyHostToDevice, st));
-  float ms = 0;
-  if (int rc = aigw_bedrock_stream_device(ctx, cfg, ctx->d_sse_bytes, ctx->d_sse_coff, n_streams, nbytes, ctx->d_bs_out, out_capacity,
-                                          (aigw_stream_result*)ctx->d_sse_res, (uint64_t*)ctx->d_bs_used, st, &ms)) return rc;
-  unsigned long long used = 0;
-  CK(cudaMemcpyAsync(&used, ctx->d_bs_used, 8, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(results, ctx->d_sse_res, (size_t)n_streams * sizeof(aigw_stream_result), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  if (used > out_capacity) used = out_capacity;
-  CK(cudaMemcpyAsync(out, ctx->d_bs_out, used, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  if (out_used) *out_used = used;
-  if (kernel_ms) *kernel_ms = ms;
-  if (h2d_bytes) *h2d_bytes = nbytes + ((uint64_t)n_streams + 1) * 8;
-  if (d2h_bytes) *d2h_bytes = used + (uint64_t)n_streams * sizeof(aigw_stream_result) + 8;
+  BedrockStreamParams P0;
+  if (int rc = fill_stream_params(ctx, P0, cfg)) return rc;
+  // sub-batches of ~64 MiB of stream bytes
+  constexpr uint64_t kChunk = 64ull << 20;
+  std::vector<uint32_t> cb; cb.push_back(0);
+  { uint64_t start = stream_off[0]; for (uint32_t i = 1; i < n_streams; i++) if (stream_off[i + 1] - start > kChunk) { cb.push_back(i); start = stream_off[i]; } cb.push_back(n_streams); }
+  const int nch = (int)cb.size() - 1;
+  const uint64_t total_in = stream_off[n_streams] - stream_off[0];
+  const double ratio = out_capacity_hint ? (double)out_capacity_hint / (double)(total_in + 1) : 2.0;
+  std::vector<uint64_t> out_cap(nch), out_base(nch);
+  uint64_t max_in = 0, total_cap = 0; uint32_t max_n = 0;
+  for (int c = 0; c < nch; c++) {
+    const uint64_t ib = stream_off[cb[c + 1]] - stream_off[cb[c]]; const uint32_t nd = cb[c + 1] - cb[c];
+    if (ib > max_in) max_in = ib; if (nd > max_n) max_n = nd;
+    out_cap[c] = ((uint64_t)((double)ib * ratio) + (uint64_t)nd * 64 + 4096 + 255) & ~255ull;
+    out_base[c] = total_cap; total_cap += out_cap[c];
+  }
+  const int nslots = nch < 2 ? 1 : 2;
+  for (int k = 0; k < nslots; k++) {
+    ENSURE(ctx->slot[k].d_in, ctx->slot[k].in_cap, max_in + 64, false);
+    ENSURE(ctx->d_bs_off[k], ctx->bs_off_cap[k], ((size_t)max_n + 1) * 8, false);
+  }
+  ENSURE(ctx->d_bs_work, ctx->bs_work_cap, bedrock_work_bytes(max_in, max_n), false);
+  ENSURE(ctx->h_out, ctx->h_out_cap, total_cap, true);
+  ENSURE(ctx->h_sres, ctx->h_sres_cap, (size_t)n_streams * sizeof(aigw_stream_result), true);
+  if ((size_t)nch > ctx->used_cap) {
+    cudaFree(ctx->d_used_arr); cudaFreeHost(ctx->h_used_arr); ctx->used_cap = 0;
+    const size_t cap = (size_t)nch + 64;
+    CK(cudaMalloc(&ctx->d_used_arr, cap * 8)); CK(cudaHostAlloc(&ctx->h_used_arr, cap * 8, cudaHostAllocDefault));
+    ctx->used_cap = cap;
+  }
+  uint8_t* dev_out = nullptr; aigw_stream_result* dev_res = nullptr;
+  CK(cudaHostGetDevicePointer((void**)&dev_out, ctx->h_out, 0));
+  CK(cudaHostGetDevicePointer((void**)&dev_res, ctx->h_sres, 0));
+  uint64_t h2d = 0;
+  CK(cudaMemsetAsync(ctx->d_used_arr, 0, (size_t)nch * 8, ctx->s_compute));
+  CK(cudaEventRecord(ctx->ev0, ctx->s_compute));
+  for (int c = 0; c < nch; c++) {
+    ChunkSlot& S = ctx->slot[c % nslots];
+    uint64_t* d_off = ctx->d_bs_off[c % nslots];
+    const uint32_t b = cb[c], e = cb[c + 1], nd = e - b;
+    const uint64_t ib = stream_off[e] - stream_off[b];
+    if (c >= nslots) CK(cudaStreamWaitEvent(ctx->s_h2d, S.ev_k1, 0));
+    CK(cudaMemcpyAsync(S.d_in, bytes + stream_off[b], ib, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaMemcpyAsync(d_off, stream_off + b, ((size_t)nd + 1) * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaEventRecord(S.ev_h2d, ctx->s_h2d));
+    h2d += ib + ((uint64_t)nd + 1) * 8;
+    CK(cudaStreamWaitEvent(ctx->s_compute, S.ev_h2d, 0));
+    BedrockStreamParams P = P0;
+    P.bytes = S.d_in - stream_off[b]; P.stream_off = d_off; P.off_base = stream_off[b]; P.n_streams = nd;
+    P.out = dev_out + out_base[c]; P.out_capacity = out_cap[c]; P.out_bias = out_base[c];
+    P.results = dev_res + b; P.out_used = ctx->d_used_arr + c;
+    bedrock_work_layout(P, ctx->d_bs_work, nd);
+    ctx->counter_next = (ctx->counter_next + 1) & ~1;
+    P.next = ctx->d_counters + (ctx->counter_next & 255); ctx->counter_next += 2;
+    CK(launch_bedrock_stream(P, ctx->sm_count, ctx->s_compute));
+    CK(cudaEventRecord(S.ev_k1, ctx->s_compute));
+    out->gpu_launches += 2;
+  }
+  CK(cudaEventRecord(ctx->ev1, ctx->s_compute));
+  CK(cudaMemcpyAsync(ctx->h_used_arr, ctx->d_used_arr, (size_t)nch * 8, cudaMemcpyDeviceToHost, ctx->s_compute));
+  CK(cudaStreamSynchronize(ctx->s_compute));
+  uint64_t d2h = (uint64_t)n_streams * sizeof(aigw_stream_result) + (uint64_t)nch * 8;
+  for (int c = 0; c < nch; c++) d2h += ctx->h_used_arr[c] < out_cap[c] ? ctx->h_used_arr[c] : out_cap[c];
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  out->results = ctx->h_sres; out->out = ctx->h_out; out->out_used = total_cap; out->h2d_bytes = h2d; out->d2h_bytes = d2h; out->kernel_ms = ms;
   return 0;
 }
 

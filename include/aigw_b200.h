@@ -172,9 +172,14 @@ typedef struct aigw_bedrock_stream_cfg { int64_t created; const char* response_i
 int aigw_bedrock_stream_device(aigw_ctx* ctx, const aigw_bedrock_stream_cfg* cfg, const uint8_t* d_bytes, const uint64_t* d_stream_off, uint32_t n_streams,
                                uint64_t total_bytes, uint8_t* d_out, uint64_t out_capacity, aigw_stream_result* d_results, uint64_t* d_out_used,
                                void* stream, float* kernel_ms);
+/* Host-buffer form: `bytes` is host memory (pinned from aigw_host_alloc for full PCIe rate).  The call splits the streams
+ * into sub-batches, overlaps each sub-batch's H2D copy with the kernels of the previous one, and the emit kernel writes
+ * the SSE text and the results straight into library-owned mapped pinned memory (no D2H copy).  `out->results[s].out_off`
+ * indexes `out->out`; both stay valid until the next host call on this ctx.  out_capacity_hint = 0 picks 2x input. */
+typedef struct aigw_stream_batch_out { const aigw_stream_result* results; const uint8_t* out; uint64_t out_used; uint64_t h2d_bytes, d2h_bytes;
+                                       uint32_t gpu_launches; float kernel_ms; } aigw_stream_batch_out;
 int aigw_bedrock_stream_host(aigw_ctx* ctx, const aigw_bedrock_stream_cfg* cfg, const uint8_t* bytes, const uint64_t* stream_off, uint32_t n_streams,
-                             uint8_t* out /* host */, uint64_t out_capacity, aigw_stream_result* results /* host, n_streams */, uint64_t* out_used,
-                             uint64_t* h2d_bytes, uint64_t* d2h_bytes, float* kernel_ms);
+                             uint64_t out_capacity_hint, aigw_stream_batch_out* out);
 
 const char* aigw_version(void);
 
