@@ -5,6 +5,7 @@
 #include <chrono>
 #include <thread>
 
+#include "bedrock_response.hpp"
 #include "bedrock_stream.hpp"
 #include "stream.hpp"
 #include "translate.hpp"
@@ -139,6 +140,29 @@ double oracle_bedrock_stream_batch(const uint8_t* bytes, const uint64_t* stream_
         bedrock_stream_feed(st, cfg, std::string_view((const char*)bytes + stream_off[s], stream_off[s + 1] - stream_off[s]), true, out, u);
         tot += out.size();
       }
+    }
+  };
+  if (threads <= 1) work(); else { std::vector<std::thread> th; for (int t = 0; t < threads; t++) th.emplace_back(work); for (auto& t : th) t.join(); }
+  if (total_out) *total_out = tot.load();
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+// ---- R1 (Bedrock): buffered Converse response → OpenAI ChatCompletionResponse.  Returns oracle::Status; *out is malloc'd.
+int oracle_bedrock_response(const char* body, uint64_t len, const char* request_model, const char* response_id, int64_t created, char** out, uint64_t* out_len, oracle_usage* usage) {
+  BedrockStreamCfg cfg; cfg.request_model = request_model ? request_model : ""; cfg.response_id = response_id ? response_id : ""; cfg.created = created;
+  std::string o; TokenUsage u; const Status st = bedrock_response(std::string_view(body, len), cfg, o, u);
+  put(usage, u); *out = dup(o); *out_len = o.size();
+  return (int)st;
+}
+double oracle_bedrock_response_batch(const uint8_t* bodies, const uint64_t* offsets, uint32_t n, int threads, uint64_t* total_out) {
+  std::atomic<uint32_t> next{0}; std::atomic<uint64_t> tot{0};
+  auto t0 = std::chrono::steady_clock::now();
+  auto work = [&] {
+    BedrockStreamCfg cfg; cfg.request_model = "m"; cfg.response_id = "r"; cfg.created = 7;
+    for (;;) {
+      uint32_t i = next.fetch_add(64); if (i >= n) break;
+      uint32_t e = std::min(n, i + 64); uint64_t loc = 0;
+      for (; i < e; i++) { std::string o; TokenUsage u; bedrock_response(std::string_view((const char*)bodies + offsets[i], offsets[i + 1] - offsets[i]), cfg, o, u); loc += o.size(); }
+      tot += loc;
     }
   };
   if (threads <= 1) work(); else { std::vector<std::thread> th; for (int t = 0; t < threads; t++) th.emplace_back(work); for (auto& t : th) t.join(); }

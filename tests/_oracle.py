@@ -133,3 +133,14 @@ def bedrock_stream(data: bytes, chunk_sizes, request_model: bytes, response_id: 
     p = lib().oracle_bedrock_stream(data, off.ctypes.data, len(sizes), request_model, response_id, created, C.byref(n), C.byref(u))
     out = C.string_at(p, n.value); lib().oracle_free(p)
     return out, u
+
+
+def bedrock_response(body: bytes, request_model: bytes, response_id: bytes, created: int):
+    """Buffered Bedrock Converse response → (status, OpenAI ChatCompletion JSON bytes, Usage)."""
+    p = C.c_char_p(); n = C.c_uint64(0); u = Usage()
+    L = lib()
+    L.oracle_bedrock_response.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(Usage)]
+    vp = C.c_void_p()
+    st = L.oracle_bedrock_response(body, len(body), request_model, response_id, created, C.byref(vp), C.byref(n), C.byref(u))
+    out = C.string_at(vp, n.value); L.oracle_free(vp)
+    return st, out, u

@@ -119,3 +119,44 @@ def test_bedrock_stream_dataplane_goldens(name):
     data = _encode_frames([l.strip().encode() for l in c["responseBody"].split("\n")])
     out, u = O.bedrock_stream(data, None, b"something", b"2bc5b090-a26c-4007-9467-ce5adc4ffa1d", 123)
     assert out.decode() == c["expResponseBody"]
+
+
+# ---------------------------------------------------------------- R1 (Bedrock): buffered Converse response → OpenAI JSON
+BEDROCK_RESP_CASES = [c for c in CASES if c.get("backend", "").startswith("aws") and "expResponseBody" in c and c.get("expPath", "").endswith("/converse")
+                      and "/v1/chat/completions" in c["name"]]
+
+
+def test_bedrock_response_goldens_found():
+    assert len(BEDROCK_RESP_CASES) >= 2
+
+
+@pytest.mark.parametrize("c", BEDROCK_RESP_CASES, ids=lambda c: c["name"])
+def test_bedrock_response_dataplane_goldens(c):
+    """tests/data-plane/testupstream_test.go:238-241,286-289 — the reference compares these with JSONEq after created → 123."""
+    model = json.loads(c["requestBody"])["model"]
+    rid = c["responseHeaders"].split(":", 1)[1]
+    st, out, u = O.bedrock_response(c["responseBody"].encode(), model.encode(), rid.encode(), 123)
+    assert st == 0
+    assert json.loads(out) == json.loads(c["expResponseBody"])
+    assert (u.input, u.output, u.total) == (10, 20, 30)
+
+
+def test_bedrock_response_struct_order_and_omits():
+    """openai.ChatCompletionResponse field order (internal/apischema/openai/openai.go:1269-1306,1365-1422) and omitempty/omitzero rules."""
+    body = (b'{"metrics":{"latencyMs":5},"output":{"message":{"content":[{"reasoningContent":{"reasoningText":{"text":"think","signature":"sig"}}},'
+            b'{"text":"hi"},{"text":"ignored"},{"toolUse":{"name":"f","input":{"b":1.50,"a":"x\\"y"},"toolUseId":"t1"}}],"role":"assistant"}},'
+            b'"stopReason":"tool_use","serviceTier":{"type":"priority"},"usage":{"inputTokens":5,"outputTokens":7,"totalTokens":12,"cacheReadInputTokens":3}}')
+    st, out, u = O.bedrock_response(body, b"m", b"rid", 9)
+    assert st == 0
+    assert out == (b'{"id":"rid","choices":[{"finish_reason":"tool_calls","index":0,"message":{"content":"hi","role":"assistant",'
+                   b'"tool_calls":[{"id":"t1","function":{"arguments":"{\\"a\\":\\"x\\\\\\"y\\",\\"b\\":1.5}","name":"f"},"type":"function"}],'
+                   b'"reasoning_content":{"reasoningContent":{"reasoningText":{"text":"think","signature":"sig"}}}}}],"created":9,"model":"m",'
+                   b'"service_tier":"priority","object":"chat.completion","usage":{"prompt_tokens":8,"completion_tokens":7,"total_tokens":15,"prompt_tokens_details":{"cached_tokens":3}}}')
+    assert (u.input, u.output, u.total, u.cached) == (8, 7, 15, 3)
+    # zero usage struct is omitted (omitzero); a missing role/content leaves "message":{}
+    st, out, _ = O.bedrock_response(b'{"output":{"message":{}},"usage":{"inputTokens":0,"outputTokens":0,"totalTokens":0}}', b"", b"", 1)
+    assert st == 0 and out == b'{"choices":[{"finish_reason":"stop","index":0,"message":{}}],"created":1,"object":"chat.completion"}'
+    # type errors fail the decode (INTERNAL = 3); nil Output is the reference's panic (DECLINED = 4)
+    assert O.bedrock_response(b'{"output":{"message":{"content":[{"text":5}]}}}', b"m", b"", 1)[0] == 3
+    assert O.bedrock_response(b'{"stopReason":"end_turn"}', b"m", b"", 1)[0] == 4
+    assert O.bedrock_response(b'not json', b"m", b"", 1)[0] == 3
