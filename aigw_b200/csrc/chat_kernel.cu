@@ -64,6 +64,20 @@ enum Vid : uint8_t {
   X("disabled", V_disabled) X("adaptive", V_adaptive) X("required", V_required) X("assistant", V_assistant) X("developer", V_developer) X("ephemeral", V_ephemeral) \
   X("redacted_thinking", V_redacted_thinking) X("image_url", V_image_url) X("input_audio", V_input_audio) X("file", V_file)
 
+// Response direction (P.schema >= AIGW_SCHEMA_RESP_AWS_BEDROCK): the index kernel loads this key table instead; ids share
+// the 6-bit field of the token word.  awsbedrock.ConverseResponse, internal/apischema/awsbedrock/awsbedrock.go:178-182,264-279,330-432.
+enum RKid : uint8_t {
+  RK_NONE = 0, RK_output, RK_message, RK_content, RK_role, RK_text, RK_toolUse, RK_toolUseId, RK_name, RK_input, RK_reasoningContent, RK_reasoningText,
+  RK_signature, RK_redactedContent, RK_stopReason, RK_usage, RK_inputTokens, RK_outputTokens, RK_totalTokens, RK_cacheReadInputTokens, RK_cacheWriteInputTokens,
+  RK_serviceTier, RK_type, RK_metrics, RK_latencyMs, RK_document, RK_image, RK_toolResult, RK_cachePoint, RK_COUNT
+};
+#define AIGW_RKEYS(X) \
+  X("output", RK_output) X("message", RK_message) X("content", RK_content) X("role", RK_role) X("text", RK_text) X("toolUse", RK_toolUse) X("toolUseId", RK_toolUseId) \
+  X("name", RK_name) X("input", RK_input) X("reasoningContent", RK_reasoningContent) X("reasoningText", RK_reasoningText) X("signature", RK_signature) \
+  X("redactedContent", RK_redactedContent) X("stopReason", RK_stopReason) X("usage", RK_usage) X("inputTokens", RK_inputTokens) X("outputTokens", RK_outputTokens) \
+  X("totalTokens", RK_totalTokens) X("cacheReadInputTokens", RK_cacheReadInputTokens) X("cacheWriteInputTokens", RK_cacheWriteInputTokens) X("serviceTier", RK_serviceTier) \
+  X("type", RK_type) X("metrics", RK_metrics) X("latencyMs", RK_latencyMs) X("document", RK_document) X("image", RK_image) X("toolResult", RK_toolResult) X("cachePoint", RK_cachePoint)
+
 static constexpr int kKeySlots = 128, kValSlots = 32, kMaxIdLen = 24;
 // slot = { six little-endian words of the string zero-padded to 24 bytes, len | id << 8 }
 struct IdSlot { uint32_t w[6]; uint32_t meta; };
@@ -92,6 +106,14 @@ constexpr IdTables make_id_tables() {
   return t;
 }
 __device__ __constant__ IdTables c_ids = make_id_tables();
+constexpr IdTables make_resp_id_tables() {
+  IdTables t{};
+#define X(lit, idv) id_insert(t.key, kKeySlots, lit, idv);
+  AIGW_RKEYS(X)
+#undef X
+  return t;
+}
+__device__ __constant__ IdTables c_ids_resp = make_resp_id_tables();
 
 // id of a short string (1 ≤ n ≤ kMaxIdLen) held in shared memory, against the key or the value table (also in shared
 // memory).  Straight-line code: seven aligned word loads, funnel shifts, length mask, multiplicative hash, ≤ 4 probes.
@@ -529,6 +551,247 @@ struct Walker {
       pl.lit(L_RBRACE, sys);
       if (with_cache && cache) { pl.lit(L_COMMA, sys); pl.lit(L_CACHEPOINT, sys); }
     }
+  }
+
+  // ---------------------------------------------------------------- response direction helpers
+  // decimal digits into scratch, as one op
+  __device__ void emit_dec(unsigned long long v, bool neg = false) {
+    char b[24]; int k = 0;
+    do { b[k++] = (char)('0' + v % 10ull); v /= 10ull; } while (v);
+    if (neg) b[k++] = '-';
+    if (sc.n + (uint32_t)k + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
+    for (int t = 0; t < k; t++) sc.p[sc.n + t] = (uint8_t)b[k - 1 - t];
+    pl.push(2, sc.n, (uint32_t)k); sc.n += ((uint32_t)k + 1u) & ~1u;
+  }
+  // configuration text (already known to need no JSON escaping) into scratch, as one op
+  __device__ void emit_cfg_text(const char* t, uint32_t n) {
+    if (sc.n + n + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
+    for (uint32_t i = 0; i < n; i++) sc.p[sc.n + i] = (uint8_t)t[i];
+    pl.push(2, sc.n, n); sc.n += (n + 1u) & ~1u;
+  }
+  // json.Marshal(map[string]any) of object `v`, then embedded in a JSON string: '"' and '\\' gain a backslash
+  // (bedrockToolUseToOpenAICalls, internal/translator/openai_awsbedrock.go:623-641).  The marshalled text is planned
+  // as ops first, then materialised into scratch with the escapes applied and replaced by one scratch op.
+  __device__ void emit_escaped_json(int v) {
+    if (pl.dry) { emit_any(d, pl, v); return; }
+    pl.flush();
+    const int n0 = pl.nops; const uint32_t olen0 = pl.olen;
+    emit_any(d, pl, v);
+    if (pl.err) return;
+    pl.flush();
+    const uint32_t start = sc.n;
+    for (int k = n0; k < pl.nops; k++) {
+      const uint32_t op = pl.ops[k], kind = op >> 30, l = (op >> 16) & 0x3fffu, off = op & 0xffffu;
+      const uint8_t* src = kind == 0 ? d.s + off : kind == 1 ? (const uint8_t*)c_lits.bytes + off : sc.p + off;
+      for (uint32_t i = 0; i < l; i++) {
+        const uint32_t c = src[i];
+        if (sc.n + 3 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
+        if (c == '"' || c == '\\') sc.p[sc.n++] = '\\';
+        sc.p[sc.n++] = (uint8_t)c;
+      }
+    }
+    pl.nops = n0; pl.olen = olen0;
+    const uint32_t total = sc.n - start;
+    if (total) pl.push(2, start, total);
+    sc.n = (sc.n + 1u) & ~1u;
+  }
+  // members of `obj` by response key id; `want` lists ids, `out` gets the value token (-1 absent or null)
+  __device__ bool rmembers(int obj, const uint8_t* want, int nw, int* out) {
+    for (int k = 0; k < nw; k++) out[k] = -1;
+    uint32_t seen = 0;
+    for (int m = obj + 1; d.ty(m) != '}'; m = d.after(m + 3)) {
+      const uint32_t id = d.id(m);
+      if (!id) continue;
+      for (int k = 0; k < nw; k++) if (want[k] == id) {
+        if (seen & (1u << k)) { decline(AIGW_R_DUP_KEY); return false; }
+        seen |= 1u << k;
+        out[k] = is_null(m + 3) ? -1 : m + 3;
+      }
+    }
+    return true;
+  }
+  // int64 struct field: 0 ok (value in `out`, must fit 31 bits here), 1 type error, 2 leave to the stock path
+  __device__ int rint(int v, uint32_t& out) {
+    out = 0;
+    if (v < 0) return 0;
+    if (!is_num(v)) return 1;
+    const uint32_t o = d.tok(v), e = d.scalar_end(v);
+    for (uint32_t i = o; i < e; i++) { const uint32_t c = d.s[i]; if (c == '.' || c == 'e' || c == 'E') return 1; }
+    if (d.s[o] == '-' || e - o > 10u) return 2;
+    unsigned long long x = 0;
+    for (uint32_t i = o; i < e; i++) x = x * 10ull + (d.s[i] - '0');
+    if (x >= 0x80000000ull) return 2;
+    out = (uint32_t)x;
+    return 0;
+  }
+  __device__ bool str_is(int v, const char* w, uint32_t wl) const {
+    if (d.str_len(v) != wl) return false;
+    const uint8_t* p = d.s + d.str_off(v);
+    for (uint32_t i = 0; i < wl; i++) if (p[i] != (uint8_t)w[i]) return false;
+    return true;
+  }
+
+  // Buffered Bedrock Converse response → openai.ChatCompletionResponse (internal/translator/openai_awsbedrock.go:734-824).
+  // terr: a known field has the wrong JSON type (the reference's decode fails: AIGW_INTERNAL); decline(): left to the stock path.
+  __device__ void plan_bedrock_response(uint32_t& path_len) {
+    bool terr = false, unsup = false;
+    if (is_null(0)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }      // zero struct: nil Output, the reference panics
+    if (!is_obj(0)) { decline(AIGW_R_E500_DECODE); return; }
+    static const uint8_t k_root[] = {RK_metrics, RK_output, RK_stopReason, RK_serviceTier, RK_usage};
+    int r[5]; if (!rmembers(0, k_root, 5, r)) return;
+    const int metrics = r[0], output = r[1], stop = r[2], tier_o = r[3], usage_o = r[4];
+    uint32_t tmp;
+    if (metrics >= 0) {
+      if (!is_obj(metrics)) terr = true;
+      else { static const uint8_t k[] = {RK_latencyMs}; int q[1]; if (!rmembers(metrics, k, 1, q)) return; const int rc = rint(q[0], tmp); if (rc == 1) terr = true; else if (rc == 2) unsup = true; }
+    }
+    if (stop >= 0 && !is_str(stop)) terr = true;
+    int tier = -1;
+    if (tier_o >= 0) {
+      if (!is_obj(tier_o)) terr = true;
+      else { static const uint8_t k[] = {RK_type}; int q[1]; if (!rmembers(tier_o, k, 1, q)) return; tier = q[0]; if (tier >= 0 && !is_str(tier)) terr = true; }
+    }
+    bool has_usage = false, has_rd = false, has_wr = false; uint32_t u_in = 0, u_out = 0, u_rd = 0, u_wr = 0;
+    if (usage_o >= 0) {
+      if (!is_obj(usage_o)) terr = true;
+      else {
+        has_usage = true;
+        static const uint8_t k[] = {RK_inputTokens, RK_outputTokens, RK_totalTokens, RK_cacheReadInputTokens, RK_cacheWriteInputTokens};
+        int q[5]; if (!rmembers(usage_o, k, 5, q)) return;
+        uint32_t* dst[5] = {&u_in, &u_out, &tmp, &u_rd, &u_wr};
+        for (int i = 0; i < 5; i++) { const int rc = rint(q[i], *dst[i]); if (rc == 1) terr = true; else if (rc == 2) unsup = true; }
+        has_rd = q[3] >= 0; has_wr = q[4] >= 0;
+      }
+    }
+    if (output >= 0 && !is_obj(output)) terr = true;
+    int role = -1, content = -1, text = -1, reason_blk = -1, n_tools = 0;
+    if (output >= 0 && is_obj(output)) {
+      static const uint8_t k[] = {RK_message}; int q[1]; if (!rmembers(output, k, 1, q)) return;
+      const int msg = q[0];
+      if (msg >= 0 && !is_obj(msg)) terr = true;
+      if (msg >= 0 && is_obj(msg)) {
+        static const uint8_t km[] = {RK_role, RK_content}; int qm[2]; if (!rmembers(msg, km, 2, qm)) return;
+        role = qm[0]; content = qm[1];
+        if (role >= 0 && !is_str(role)) terr = true;
+        if (content >= 0 && !is_arr(content)) { terr = true; content = -1; }
+      }
+    }
+    // first pass over the content blocks: types, first text, last reasoning block, number of tool calls
+    static const uint8_t kb[] = {RK_text, RK_toolUse, RK_reasoningContent, RK_document, RK_image, RK_toolResult, RK_cachePoint};
+    if (content >= 0) {
+      for (int e = content + 1; d.ty(e) != ']'; e = d.after(e)) {
+        if (is_null(e)) { unsup = true; continue; }                     // nil *ContentBlock is dereferenced by the reference
+        if (!is_obj(e)) { terr = true; continue; }
+        int q[7]; if (!rmembers(e, kb, 7, q)) return;
+        if (q[3] >= 0 || q[4] >= 0 || q[5] >= 0 || q[6] >= 0) unsup = true;
+        if (q[0] >= 0 && !is_str(q[0])) terr = true;
+        if (q[1] >= 0) {
+          if (!is_obj(q[1])) terr = true;
+          else {
+            static const uint8_t kt[] = {RK_name, RK_input, RK_toolUseId}; int t[3]; if (!rmembers(q[1], kt, 3, t)) return;
+            if ((t[0] >= 0 && !is_str(t[0])) || (t[2] >= 0 && !is_str(t[2])) || (t[1] >= 0 && !is_obj(t[1]))) terr = true;
+            n_tools++;
+          }
+        }
+        if (q[2] >= 0) {
+          if (!is_obj(q[2])) terr = true;
+          else {
+            static const uint8_t kr[] = {RK_reasoningText, RK_redactedContent}; int t[2]; if (!rmembers(q[2], kr, 2, t)) return;
+            if (t[0] >= 0) {
+              if (!is_obj(t[0])) terr = true;
+              else { static const uint8_t kx[] = {RK_text, RK_signature}; int x[2]; if (!rmembers(t[0], kx, 2, x)) return; if ((x[0] >= 0 && !is_str(x[0])) || (x[1] >= 0 && !is_str(x[1]))) terr = true; }
+            }
+            if (t[1] >= 0) { if (!is_str(t[1])) terr = true; else if (d.str_len(t[1]) > 0) unsup = true; }  // []byte is re-encoded: stock path
+          }
+        }
+        if (q[1] < 0 || !is_obj(q[1])) {
+          if (q[0] >= 0) { if (text < 0) text = q[0]; }
+          else if (q[2] >= 0) reason_blk = e;
+        }
+      }
+    }
+    if (terr) { decline(AIGW_R_E500_DECODE); return; }
+    if (output < 0 || unsup) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+    if (bad()) return;
+    // ---- usage record in front of the body (the slot request schemas use for :path)
+    const unsigned long long tin = (unsigned long long)u_in + u_rd + u_wr;
+    if (tin + u_out >= 0x80000000ull) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+    {
+      sc.n = (sc.n + 3u) & ~3u;
+      if (sc.n + 34 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
+      uint32_t* u = (uint32_t*)(sc.p + sc.n);
+      u[0] = has_usage ? (uint32_t)tin : 0u; u[1] = has_usage ? u_out : 0u; u[2] = has_usage ? (uint32_t)tin + u_out : 0u;
+      u[3] = has_rd ? u_rd : 0u; u[4] = has_wr ? u_wr : 0u; u[5] = 0u; u[6] = has_usage ? (7u | (has_rd ? 8u : 0u) | (has_wr ? 16u : 0u)) : 0u; u[7] = 0u;
+      pl.push(2, sc.n, 32); sc.n += 32;
+      path_len = 32;
+    }
+    // ---- body, fields in struct order (internal/apischema/openai/openai.go:1269-1306,1365-1422)
+    pl.lit(L_LBRACE);
+    if (P->rid_len) { pl.lit(L_R_ID_OPEN); emit_cfg_text(P->response_id, P->rid_len); pl.lit(L_R_QUOTE_COMMA); }
+    pl.lit(L_R_CHOICES);
+    {
+      int fr = L_R_FR_STOP;
+      if (stop >= 0) {
+        if (d.str_has_backslash(stop)) { decline(AIGW_R_ESCAPE); return; }
+        if (str_is(stop, "max_tokens", 10)) fr = L_R_FR_LENGTH; else if (str_is(stop, "content_filtered", 16)) fr = L_R_FR_FILTER; else if (str_is(stop, "tool_use", 8)) fr = L_R_FR_TOOLS;
+      }
+      pl.lit(fr);
+    }
+    pl.lit(L_R_MSG);
+    bool first = true;
+    if (text >= 0) { pl.lit(L_R_CONTENT); emit_str(text); first = false; }
+    if (role >= 0 && d.str_len(role) > 0) { if (!first) pl.lit(L_COMMA); first = false; pl.lit(L_R_ROLE); emit_str(role); }
+    if (n_tools) {
+      if (!first) pl.lit(L_COMMA); first = false;
+      pl.lit(L_R_TOOLCALLS);
+      bool tf = true;
+      for (int e = content + 1; d.ty(e) != ']'; e = d.after(e)) {
+        static const uint8_t k1[] = {RK_toolUse}; int q[1]; if (!rmembers(e, k1, 1, q)) return;
+        if (q[0] < 0) continue;
+        static const uint8_t kt[] = {RK_name, RK_input, RK_toolUseId}; int t[3]; if (!rmembers(q[0], kt, 3, t)) return;
+        if (!tf) pl.lit(L_COMMA); tf = false;
+        pl.lit(L_R_TC_ID); if (t[2] >= 0) emit_str(t[2]); else pl.lit(L_EMPTY_STR);
+        pl.lit(L_R_TC_ARGS);
+        if (t[1] >= 0) emit_escaped_json(t[1]); else pl.lit(L_NULL);
+        if (bad()) return;
+        pl.lit(L_R_TC_NAME); if (t[0] >= 0) emit_str(t[0]); else pl.lit(L_EMPTY_STR);
+        pl.lit(L_R_TC_END);
+      }
+      pl.lit(L_RBRACK);
+    }
+    if (reason_blk >= 0) {
+      if (!first) pl.lit(L_COMMA); first = false;
+      pl.lit(L_R_REASON);
+      static const uint8_t k1[] = {RK_reasoningContent}; int q[1]; if (!rmembers(reason_blk, k1, 1, q)) return;
+      static const uint8_t kr[] = {RK_reasoningText}; int t[1]; if (!rmembers(q[0], kr, 1, t)) return;
+      if (t[0] >= 0) {
+        static const uint8_t kx[] = {RK_text, RK_signature}; int x[2]; if (!rmembers(t[0], kx, 2, x)) return;
+        pl.lit(L_R_RTEXT); if (x[0] >= 0) emit_str(x[0]); else pl.lit(L_EMPTY_STR);
+        if (x[1] >= 0 && d.str_len(x[1]) > 0) { pl.lit(L_R_RSIG); emit_str(x[1]); }
+        pl.lit(L_RBRACE);
+      }
+      pl.lit(L_R_RBRACE2);
+    }
+    pl.lit(L_R_CREATED);
+    emit_dec(P->created < 0 ? 0ull - (unsigned long long)P->created : (unsigned long long)P->created, P->created < 0);
+    if (P->override_len) { pl.lit(L_R_MODEL); emit_cfg_text(P->override_model, P->override_len); pl.lit(L_R_QUOTE); }
+    if (tier >= 0 && d.str_len(tier) > 0) { pl.lit(L_R_TIER); emit_str(tier); }
+    pl.lit(L_R_OBJECT);
+    if (has_usage && (tin || u_out || has_rd || has_wr)) {   // Usage is omitzero: a zero struct is left out
+      pl.lit(L_R_USAGE);
+      bool uf = true;
+      auto num = [&](int lit, uint32_t v) { if (!v) return; if (!uf) pl.lit(L_COMMA); uf = false; pl.lit(lit); emit_dec(v); };
+      num(L_R_PROMPT, (uint32_t)tin); num(L_R_COMPLETION, u_out); num(L_R_TOTAL, (uint32_t)tin + u_out);
+      if (has_rd || has_wr) {
+        if (!uf) pl.lit(L_COMMA);
+        pl.lit(L_R_PTD); uf = true;
+        if (has_rd) num(L_R_CACHED, u_rd);
+        if (has_wr) num(L_R_CC, u_wr);
+        pl.lit(L_RBRACE);
+      }
+      pl.lit(L_RBRACE);
+    }
+    pl.lit(L_RBRACE);
   }
 
   struct Msg { int role_v, content, name, tool_calls, tool_call_id, refusal, audio; };
@@ -1287,7 +1550,10 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
   // CTA-shared tables: key/value id hash tables and the byte class LUT (0 scalar character, 1 whitespace, 2 structural)
   IdTables* s_ids = (IdTables*)smem;
   uint8_t* s_cls = smem + sizeof(IdTables);
-  for (uint32_t i = threadIdx.x; i < sizeof(IdTables) / 4; i += blockDim.x) ((uint32_t*)s_ids)[i] = ((const uint32_t*)&c_ids)[i];
+  {
+    const uint32_t* src = (const uint32_t*)(P.schema >= AIGW_SCHEMA_RESP_AWS_BEDROCK ? &c_ids_resp : &c_ids);
+    for (uint32_t i = threadIdx.x; i < sizeof(IdTables) / 4; i += blockDim.x) ((uint32_t*)s_ids)[i] = src[i];
+  }
   for (uint32_t c = threadIdx.x; c < 256; c += blockDim.x) s_cls[c] = is_ws(c) ? 1 : is_op(c) ? 2 : (c == '"' ? 3 : 0);
   __syncthreads();
   constexpr int kWarpBytes = C::kIn + C::kTok * 6;
@@ -1523,7 +1789,17 @@ __global__ void __launch_bounds__(128, AIGW_WALK_BLOCKS) chat_walk_kernel(const 
   int reason = validate_tokens(W.d);
   if (reason == AIGW_R_SYNTAX) reason = AIGW_R_E400_SYNTAX;
   uint32_t path_len = 0;
-  if (!reason) {
+  if (P.schema >= AIGW_SCHEMA_RESP_AWS_BEDROCK) {
+    // response direction: json.Decoder semantics differ from the request-side strictness (trailing bytes are fine, a syntax
+    // error is "failed to unmarshal body"), so anything the token grammar rejects goes to the stock path
+    if (reason) reason = AIGW_R_SYNTAX;
+    else {
+      W.plan_bedrock_response(path_len);
+      W.pl.flush();
+      reason = W.reason ? W.reason : W.pl.err;
+      if (!reason && W.pl.nops == 0) reason = AIGW_R_OPS;
+    }
+  } else if (!reason) {
     Walker::Top t;
     if (W.scan_top(t)) {
       const bool stream = t.stream >= 0 && W.d.ty(t.stream) == 't';

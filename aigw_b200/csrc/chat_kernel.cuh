@@ -106,7 +106,38 @@ namespace aigw {
   X(L_AN_INVOKE, "/invoke")                                                                    \
   X(L_AN_INVOKE_STREAM, "/invoke-with-response-stream")                                        \
   X(L_AN_VER_GCP, "vertex-2023-10-16")                                                         \
-  X(L_AN_VER_AWS, "bedrock-2023-05-31")
+  X(L_AN_VER_AWS, "bedrock-2023-05-31")                                                        \
+  X(L_R_ID_OPEN, "\"id\":\"")                                                                   \
+  X(L_R_QUOTE_COMMA, "\",")                                                                      \
+  X(L_R_QUOTE, "\"")                                                                             \
+  X(L_R_CHOICES, "\"choices\":[{\"finish_reason\":\"")                                           \
+  X(L_R_MSG, "\",\"index\":0,\"message\":{")                                                     \
+  X(L_R_CONTENT, "\"content\":")                                                                \
+  X(L_R_ROLE, "\"role\":")                                                                      \
+  X(L_R_TOOLCALLS, "\"tool_calls\":[")                                                          \
+  X(L_R_TC_ID, "{\"id\":")                                                                      \
+  X(L_R_TC_ARGS, ",\"function\":{\"arguments\":\"")                                              \
+  X(L_R_TC_NAME, "\",\"name\":")                                                                 \
+  X(L_R_TC_END, "},\"type\":\"function\"}")                                                     \
+  X(L_R_REASON, "\"reasoning_content\":{\"reasoningContent\":{")                                \
+  X(L_R_RTEXT, "\"reasoningText\":{\"text\":")                                                  \
+  X(L_R_RSIG, ",\"signature\":")                                                                \
+  X(L_R_RBRACE2, "}}")                                                                          \
+  X(L_R_CREATED, "}}],\"created\":")                                                            \
+  X(L_R_MODEL, ",\"model\":\"")                                                                  \
+  X(L_R_TIER, ",\"service_tier\":")                                                             \
+  X(L_R_OBJECT, ",\"object\":\"chat.completion\"")                                              \
+  X(L_R_USAGE, ",\"usage\":{")                                                                  \
+  X(L_R_PROMPT, "\"prompt_tokens\":")                                                           \
+  X(L_R_COMPLETION, "\"completion_tokens\":")                                                   \
+  X(L_R_TOTAL, "\"total_tokens\":")                                                             \
+  X(L_R_PTD, "\"prompt_tokens_details\":{")                                                     \
+  X(L_R_CACHED, "\"cached_tokens\":")                                                           \
+  X(L_R_CC, "\"cache_creation_input_tokens\":")                                                 \
+  X(L_R_FR_STOP, "stop")                                                                        \
+  X(L_R_FR_LENGTH, "length")                                                                    \
+  X(L_R_FR_FILTER, "content_filter")                                                            \
+  X(L_R_FR_TOOLS, "tool_calls")
 
 enum LitId : int {
 #define X(name, text) name,
@@ -117,7 +148,7 @@ enum LitId : int {
 
 struct alignas(16) LitTable {
   uint16_t off[L_COUNT + 1];
-  alignas(16) char bytes[1536];   // copied to shared memory with 32-bit loads
+  alignas(16) char bytes[2560];   // copied to shared memory with 32-bit loads
 };
 constexpr LitTable make_lit_table() {
   LitTable t{};
@@ -152,6 +183,9 @@ struct ChatParams {
   char api_version[64];
   char override_model[128];
   char openai_path[128];
+  long long created;      // response schemas: ChatCompletionResponse.created
+  uint16_t rid_len;       // response schemas: response id (x-amzn-requestid)
+  char response_id[128];
 };
 
 // size classes: MAXD bytes of input per document.  Per-warp shared memory:

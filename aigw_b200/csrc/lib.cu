@@ -54,6 +54,9 @@ struct aigw_ctx {
   aigw_stream_result* h_sres = nullptr; size_t h_sres_cap = 0;
 };
 
+// response bodies expand (escaped tool arguments, configuration text): plan them in a roomier size class
+static uint32_t resp_class_len(uint32_t max_len) { uint64_t m = (uint64_t)max_len * 4; if (m < 5120) m = 5120; if (m > 65536) m = max_len > 65536u ? max_len : 65536u; return (uint32_t)m; }
+
 static void fill_params(ChatParams& P, const aigw_backend_cfg* cfg) {
   P.schema = cfg ? cfg->schema : AIGW_SCHEMA_OPENAI;
   P.cost_configured = cfg ? cfg->cost_configured : 0;
@@ -72,6 +75,11 @@ static void fill_params(ChatParams& P, const aigw_backend_cfg* cfg) {
   std::string path = "/" + (pfx.empty() ? std::string() : pfx + "/") + "chat/completions";
   if (path.size() > sizeof P.openai_path) path.resize(sizeof P.openai_path);
   memcpy(P.openai_path, path.data(), path.size()); P.prefix_len = (uint16_t)path.size();
+  P.created = 0; P.rid_len = 0; memset(P.response_id, 0, sizeof P.response_id);
+  if (cfg && cfg->schema >= AIGW_SCHEMA_RESP_AWS_BEDROCK) {
+    P.created = cfg->created;
+    if (cfg->response_id) { size_t n = strlen(cfg->response_id); if (n > sizeof P.response_id) n = sizeof P.response_id; memcpy(P.response_id, cfg->response_id, n); P.rid_len = (uint16_t)n; }
+  }
 }
 
 static int ensure(aigw_ctx* ctx, void** p, size_t* cap, size_t want, bool host) {
@@ -155,7 +163,8 @@ int aigw_chat_translate_device(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const
   P.bodies = d_bodies; P.offsets = d_offsets; P.lens = d_lens; P.n = n; P.out = d_out; P.out_capacity = out_capacity;
   P.results = d_results; P.out_used = (unsigned long long*)d_out_used;
   P.next_doc = nullptr; P.out_bias = 0;
-  const uint32_t ml = max_len ? max_len : 65536u;
+  uint32_t ml = max_len ? max_len : 65536u;
+  if (cfg && cfg->schema >= AIGW_SCHEMA_RESP_AWS_BEDROCK) ml = resp_class_len(ml);
   {  // workspace for one sub-batch (≤ 128 Ki documents); the launcher loops over sub-batches
     const size_t sub = n < 131072u ? n : 131072u;
     ENSURE(ctx->d_work, ctx->work_cap, chat_work_bytes(ml, sub), false);
@@ -221,6 +230,7 @@ int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const u
       S.doc_cap = dc;
     }
   }
+  if (cfg && cfg->schema >= AIGW_SCHEMA_RESP_AWS_BEDROCK) max_len = resp_class_len(max_len);
   ENSURE(ctx->d_work, ctx->work_cap, chat_work_bytes(max_len, max_docs < 131072u ? max_docs : 131072u), false);
   ENSURE(ctx->h_out, ctx->h_out_cap, total_out_cap, true);
   ENSURE(ctx->h_res, ctx->h_res_cap, (size_t)n * sizeof(aigw_doc_result), true);

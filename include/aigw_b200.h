@@ -37,7 +37,14 @@ enum aigw_status { AIGW_OK = 0, AIGW_MALFORMED_400 = 1, AIGW_INVALID_422 = 2, AI
 enum aigw_body_kind { AIGW_BODY_UNCHANGED = 0, AIGW_BODY_BYTES = 1, AIGW_BODY_EMPTY = 2 };
 /* filterapi.APISchemaName (internal/filterapi/filterconfig.go:130-153) */
 enum aigw_schema { AIGW_SCHEMA_OPENAI = 0, AIGW_SCHEMA_AWS_BEDROCK = 1, AIGW_SCHEMA_AZURE_OPENAI = 2,
-                   AIGW_SCHEMA_GCP_VERTEX = 3, AIGW_SCHEMA_GCP_ANTHROPIC = 4, AIGW_SCHEMA_AWS_ANTHROPIC = 5 };
+                   AIGW_SCHEMA_GCP_VERTEX = 3, AIGW_SCHEMA_GCP_ANTHROPIC = 4, AIGW_SCHEMA_AWS_ANTHROPIC = 5,
+                   /* response direction (buffered upstream response → OpenAI ChatCompletionResponse), same entry points:
+                    * Translator.ResponseBody of the AWS Bedrock translator, internal/translator/openai_awsbedrock.go:734-824.
+                    * cfg: model_name_override = the request model reported back, response_id = x-amzn-requestid, created = unix
+                    * seconds (time.Now() in the reference).  The output record is [aigw_usage (32 bytes)][JSON body]:
+                    * path_len == 32 and the usage struct sits where request schemas put the :path.
+                    * status AIGW_INTERNAL = "failed to unmarshal body". */
+                   AIGW_SCHEMA_RESP_AWS_BEDROCK = 16 };
 
 /* Why a body was declined / rejected (diagnostics; stable numbering). */
 enum aigw_reason {
@@ -48,7 +55,7 @@ enum aigw_reason {
   /* definite reference errors, reported with the matching status (the shim builds the user-facing message):
    * 32..39 ⇒ AIGW_MALFORMED_400 (ParseBody), 40..47 ⇒ AIGW_INVALID_422 (translator), 48..55 ⇒ AIGW_INTERNAL */
   AIGW_R_E400_SYNTAX = 32, AIGW_R_E400_TYPE = 33, AIGW_R_E400_ROLE = 34, AIGW_R_E400_CONTENT = 35,
-  AIGW_R_E422_CONTENT = 40, AIGW_R_E500_ARGS = 48
+  AIGW_R_E422_CONTENT = 40, AIGW_R_E500_ARGS = 48, AIGW_R_E500_DECODE = 49
 };
 
 /* One record per body.  Output record layout in the arena at out_off: [path bytes][body bytes]. */
@@ -75,6 +82,8 @@ typedef struct aigw_backend_cfg {
   const char* model_name_override;
   const char* openai_prefix;   /* VersionedAPISchema.OpenAIPrefix(), default "v1" */
   const char* api_version;     /* VersionedAPISchema.Version (Azure api-version); may be NULL */
+  const char* response_id;     /* response schemas only; may be NULL */
+  int64_t created;             /* response schemas only */
 } aigw_backend_cfg;
 
 /* metrics.TokenUsage (internal/metrics/metrics.go:143-158): six u32 counters + "set" mask

@@ -7,6 +7,7 @@
 
 #include "bedrock_response.hpp"
 #include "bedrock_stream.hpp"
+#include "mutate.hpp"
 #include "stream.hpp"
 #include "translate.hpp"
 
@@ -162,6 +163,33 @@ double oracle_bedrock_response_batch(const uint8_t* bodies, const uint64_t* offs
       uint32_t i = next.fetch_add(64); if (i >= n) break;
       uint32_t e = std::min(n, i + 64); uint64_t loc = 0;
       for (; i < e; i++) { std::string o; TokenUsage u; bedrock_response(std::string_view((const char*)bodies + offsets[i], offsets[i + 1] - offsets[i]), cfg, o, u); loc += o.size(); }
+      tot += loc;
+    }
+  };
+  if (threads <= 1) work(); else { std::vector<std::thread> th; for (int t = 0; t < threads; t++) th.emplace_back(work); for (auto& t : th) t.join(); }
+  if (total_out) *total_out = tot.load();
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+// ---- B1: body mutation.  removes: n_rm NUL-terminated strings; sets: n_set (path, value) pairs.  Returns 0, or 1 = not restated.
+int oracle_body_mutate(const char* body, uint64_t len, const char* const* removes, uint32_t n_rm, const char* const* set_paths, const char* const* set_values, uint32_t n_set,
+                       char** out, uint64_t* out_len) {
+  std::vector<std::string> rm; for (uint32_t i = 0; i < n_rm; i++) rm.emplace_back(removes[i]);
+  std::vector<BodySet> st; for (uint32_t i = 0; i < n_set; i++) st.push_back({set_paths[i], set_values[i]});
+  std::string o; const int rc = body_mutate(std::string_view(body, len), rm, st, o);
+  *out = dup(o); *out_len = o.size();
+  return rc;
+}
+double oracle_body_mutate_batch(const uint8_t* bodies, const uint64_t* offsets, uint32_t n, const char* const* removes, uint32_t n_rm, const char* const* set_paths,
+                                const char* const* set_values, uint32_t n_set, int threads, uint64_t* total_out) {
+  std::vector<std::string> rm; for (uint32_t i = 0; i < n_rm; i++) rm.emplace_back(removes[i]);
+  std::vector<BodySet> st; for (uint32_t i = 0; i < n_set; i++) st.push_back({set_paths[i], set_values[i]});
+  std::atomic<uint32_t> next{0}; std::atomic<uint64_t> tot{0};
+  auto t0 = std::chrono::steady_clock::now();
+  auto work = [&] {
+    for (;;) {
+      uint32_t i = next.fetch_add(64); if (i >= n) break;
+      uint32_t e = std::min(n, i + 64); uint64_t loc = 0;
+      for (; i < e; i++) { std::string o; body_mutate(std::string_view((const char*)bodies + offsets[i], offsets[i + 1] - offsets[i]), rm, st, o); loc += o.size(); }
       tot += loc;
     }
   };

@@ -144,3 +144,16 @@ def bedrock_response(body: bytes, request_model: bytes, response_id: bytes, crea
     st = L.oracle_bedrock_response(body, len(body), request_model, response_id, created, C.byref(vp), C.byref(n), C.byref(u))
     out = C.string_at(vp, n.value); L.oracle_free(vp)
     return st, out, u
+
+
+def body_mutate(body: bytes, removes, sets):
+    """BodyMutator.Mutate: removes = [path str], sets = [(path, value)] → (rc, mutated bytes); rc 1 = not restated."""
+    L = lib()
+    rm = (C.c_char_p * max(1, len(removes)))(*[r.encode() for r in removes])
+    sp = (C.c_char_p * max(1, len(sets)))(*[p.encode() for p, _ in sets])
+    sv = (C.c_char_p * max(1, len(sets)))(*[v.encode() for _, v in sets])
+    L.oracle_body_mutate.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    vp = C.c_void_p(); n = C.c_uint64(0)
+    rc = L.oracle_body_mutate(body, len(body), rm, len(removes), sp, sv, len(sets), C.byref(vp), C.byref(n))
+    out = C.string_at(vp, n.value); L.oracle_free(vp)
+    return rc, out

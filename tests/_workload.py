@@ -280,3 +280,57 @@ def bedrock_stream_corpus(n, seed=0, kinds=("plain", "tools", "reasoning", "cach
     off = np.zeros(n + 1, dtype=np.uint64)
     np.cumsum([len(s) for s in streams], out=off[1:])
     return np.frombuffer(b"".join(streams), dtype=np.uint8).copy(), off, streams
+
+
+# ---------------------------------------------------------------- buffered Bedrock Converse responses (R1, Bedrock)
+def bedrock_response_body(rng, kind="plain") -> bytes:
+    import json as _json
+    words = ["Hello", "world", "the", "quick", "brown", "fox", "café", "日本", "line\nbreak", "quote\"d", "tab\tbed", "back\\slash", "42", "ok."]
+    txt = lambda k: " ".join(words[int(i)] for i in rng.integers(0, len(words), k))
+    blocks = []
+    if kind in ("reasoning",):
+        blocks.append({"reasoningContent": {"reasoningText": {"text": txt(int(rng.integers(3, 30))), "signature": "c2ln" + str(int(rng.integers(0, 999)))}}})
+    blocks.append({"text": txt(int(rng.integers(1, 120)))})
+    if rng.integers(0, 4) == 0:
+        blocks.append({"text": "second text block is ignored"})
+    stop = ["end_turn", "max_tokens", "stop_sequence", "content_filtered", "guardrail_intervened", None][int(rng.integers(0, 6))]
+    if kind == "tools":
+        for k in range(int(rng.integers(1, 4))):
+            blocks.append({"toolUse": {"toolUseId": "tooluse_%06x" % int(rng.integers(0, 2**24)), "name": "get_weather_%d" % k,
+                                       "input": {"location": txt(2), "unit": "celsius", "n": k, "ratio": 0.25 * k, "nested": {"z": [1, 2, {"y": None}], "a": True}}}})
+        stop = "tool_use"
+    usage = {"inputTokens": int(rng.integers(0, 9000)), "outputTokens": int(rng.integers(0, 4000)), "totalTokens": int(rng.integers(0, 13000))}
+    doc = {"metrics": {"latencyMs": int(rng.integers(10, 9000))}, "output": {"message": {"content": blocks, "role": "assistant"}}, "stopReason": stop, "usage": usage}
+    if kind == "cache":
+        usage["cacheReadInputTokens"] = int(rng.integers(0, 3)) * 100
+        if rng.integers(0, 2): usage["cacheWriteInputTokens"] = int(rng.integers(0, 3)) * 10
+        if rng.integers(0, 2): doc["serviceTier"] = {"type": ["priority", "default", ""][int(rng.integers(0, 3))]}
+    if rng.integers(0, 8) == 0:
+        del doc["metrics"]
+    return _json.dumps(doc, ensure_ascii=False, separators=(",", ":")).encode()
+
+
+BEDROCK_RESPONSE_ODD = [
+    b'{"output":{"message":{"content":[{"text":"a"}],"role":"assistant"}},"stopReason":"end_turn","usage":null}',
+    b'{"output":{"message":{"content":null,"role":null}},"stopReason":null}',
+    b'{"output":{"message":null}}', b'{"output":{}}', b'{"output":{"message":{}},"usage":{"inputTokens":0,"outputTokens":0,"totalTokens":0}}',
+    b'{"output":{"message":{"content":[],"role":""}},"usage":{"inputTokens":0,"outputTokens":0,"totalTokens":0,"cacheReadInputTokens":0}}',
+    b'{"output":{"message":{"content":[{"toolUse":{"name":null,"input":null,"toolUseId":null}}]}}}',
+    b'{"output":{"message":{"content":[{"toolUse":{}},{"toolUse":{"input":{}}}]}}}',
+    b'{"output":{"message":{"content":[{"toolUse":{"name":"f","input":{"q":"he said \\"hi\\"\\n","b":{"c":[1.50,2e0,-0]}},"toolUseId":"x"},"text":"both"}]}}}',
+    b'{"output":{"message":{"content":[{"reasoningContent":{}},{"reasoningContent":{"reasoningText":{}}},{"reasoningContent":{"reasoningText":{"text":"t","signature":""}}}]}}}',
+    b'{"output":{"message":{"content":[{"reasoningContent":{"reasoningText":{"text":"first"}}},{"text":"x"},{"reasoningContent":{"reasoningText":{"text":"last","signature":"s"}}}]}}}',
+    b'{"output":{"message":{"content":[{"reasoningContent":{"redactedContent":""}}]}}}',
+    b'{"output":{"message":{"content":[{"text":""}],"role":"assistant"}},"unknown":{"a":[1,2,{"b":null}]},"stopReason":"tool_use"}',
+    b' {"output" : {"message" : {"content" : [ {"text" : "spaced"} ] , "role" : "assistant"} } , "usage" : {"inputTokens" : 1 , "outputTokens" : 2 , "totalTokens" : 3} } ',
+    b'{"output":{"message":{"content":[{"text":"x"}]}},"serviceTier":{"type":"priority"},"usage":{"inputTokens":3,"outputTokens":4,"totalTokens":7,"cacheWriteInputTokens":5}}',
+    # decode errors (AIGW_INTERNAL)
+    b'{"output":{"message":{"content":[{"text":5}]}}}', b'{"output":{"message":{"content":{"text":"x"}}}}', b'{"output":[]}', b'{"output":{"message":{"role":7}}}',
+    b'{"output":{"message":{}},"usage":{"inputTokens":"1"}}', b'{"output":{"message":{}},"usage":{"inputTokens":1.5}}', b'{"output":{"message":{}},"stopReason":1}',
+    b'{"output":{"message":{"content":[{"toolUse":{"input":[1]}}]}}}', b'{"output":{"message":{"content":[{"toolUse":"x"}]}}}', b'{"output":{"message":{}},"metrics":{"latencyMs":"1"}}',
+    b'{"output":{"message":{"content":[{"reasoningContent":{"reasoningText":{"text":1}}}]}}}', b'{"output":{"message":{}},"serviceTier":{"type":1}}', b'[1]', b'"x"',
+    # left to the stock path (AIGW_DECLINED)
+    b'{"stopReason":"end_turn"}', b'{"output":null}', b'null', b'{"output":{"message":{"content":[null]}}}', b'{"output":{"message":{"content":[{"image":{"format":"png","source":{"bytes":"AAAA"}}}]}}}',
+    b'{"output":{"message":{"content":[{"reasoningContent":{"redactedContent":"AAAA"}}]}}}', b'{"output":{"message":{"content":[{"text":"caf\\u00e9"}]}}}',
+    b'{"output":{"message":{"content":[{"cachePoint":{"type":"default"}}]}}}', b'{"output":{"message":{}},"usage":{"inputTokens":4294967296}}',
+]

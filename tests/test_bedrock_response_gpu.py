@@ -1,0 +1,101 @@
+"""R1 (Bedrock) parity: buffered Converse response → OpenAI ChatCompletionResponse on the GPU vs the oracle and the reference's goldens."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import _oracle as O
+import _workload as W
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = json.load(open(os.path.join(HERE, "golden", "testupstream_cases.json"), encoding="utf-8"))["cases"]
+
+
+@pytest.fixture(scope="module")
+def gw():
+    from aigw_b200 import capi
+    g = capi.Context(0)
+    yield g
+    g.close()
+
+
+def run(gw, bodies, model="m", rid="r", created=7):
+    from aigw_b200 import capi
+    cfg = capi.Context.cfg("resp-aws-bedrock", model_override=model)
+    cfg.response_id = rid.encode() if rid else None
+    cfg.created = created
+    arena, offs, lens = capi.pack_bodies(bodies)
+    res, out, _ = gw.chat_translate_host(cfg, arena, offs, lens)
+    r = []
+    for i in range(len(bodies)):
+        x = res[i]
+        o = int(x["out_off"]); pl = int(x["path_len"]); bl = int(x["body_len"])
+        if x["status"] == 0:
+            assert pl == 32
+            u = tuple(int(v) for v in np.frombuffer(bytes(out[o:o + 32]), dtype="<u4")[:7])
+            r.append((0, bytes(out[o + pl:o + pl + bl]), u))
+        else:
+            r.append((int(x["status"]), b"", None))
+    return r
+
+
+def check(gw, bodies, model="m", rid="r", created=7, allow_decline=False):
+    got = run(gw, bodies, model, rid, created)
+    n_ok = 0
+    for b, (st, body, u) in zip(bodies, got):
+        est, eout, eu = O.bedrock_response(b, model.encode(), rid.encode(), created)
+        if st == 4 and est != 4:
+            assert allow_decline, (b[:200], est)
+            continue
+        assert st == est, (b[:300], st, est)
+        if st == 0:
+            assert body == eout, (b[:300], body, eout)
+            assert u == (eu.input, eu.output, eu.total, eu.cached, eu.cache_creation, eu.reasoning, eu.mask)
+            n_ok += 1
+    return n_ok
+
+
+@pytest.mark.parametrize("name", ["aws system role - /v1/chat/completions", "aws-bedrock - /v1/chat/completions - tool call results"])
+def test_dataplane_goldens(gw, name):
+    """tests/data-plane/testupstream_test.go:238-241,286-289 (JSONEq in the reference)."""
+    c = next(c for c in CASES if c["name"] == name)
+    model = json.loads(c["requestBody"])["model"]
+    rid = c["responseHeaders"].split(":", 1)[1]
+    (st, body, u), = run(gw, [c["responseBody"].encode()], model, rid, 123)
+    assert st == 0
+    assert json.loads(body) == json.loads(c["expResponseBody"])
+    assert u[:3] == (10, 20, 30)
+
+
+def test_parity_corpus(gw):
+    rng = np.random.default_rng(17)
+    bodies = [W.bedrock_response_body(rng, ["plain", "tools", "reasoning", "cache"][i % 4]) for i in range(3000)]
+    assert check(gw, bodies) == len(bodies)
+
+
+def test_parity_odd_bodies(gw):
+    n_ok = check(gw, list(W.BEDROCK_RESPONSE_ODD))
+    assert n_ok >= 14
+
+
+def test_empty_id_model_and_negative_created(gw):
+    rng = np.random.default_rng(3)
+    bodies = [W.bedrock_response_body(rng, ["plain", "tools"][i % 2]) for i in range(50)]
+    assert check(gw, bodies, model="", rid="", created=0) == 50
+    assert check(gw, bodies, model="anthropic.claude-3-sonnet-20240229-v1:0", rid="2bc5b090-a26c-4007-9467-ce5adc4ffa1d", created=-3) == 50
+
+
+def test_large_responses(gw):
+    """long completions (tens of KiB) and large tool inputs that overflow the scratch space decline instead of guessing"""
+    rng = np.random.default_rng(5)
+    bodies = []
+    for i in range(40):
+        d = json.loads(W.bedrock_response_body(rng, "tools"))
+        d["output"]["message"]["content"][0]["text"] = "x" * int(rng.integers(1000, 40000))
+        if i % 5 == 0:
+            d["output"]["message"]["content"][-1]["toolUse"]["input"]["blob"] = "y\"" * int(rng.integers(200, 6000))
+        bodies.append(json.dumps(d, separators=(",", ":")).encode())
+    n_ok = check(gw, bodies, allow_decline=True)
+    assert n_ok >= 30
