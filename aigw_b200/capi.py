@@ -20,11 +20,13 @@ StreamResult = np.dtype([("out_off", "<u8"), ("out_len", "<u4"), ("status", "<u4
                          ("input", "<u4"), ("output", "<u4"), ("total", "<u4"), ("cached", "<u4"), ("cache_creation", "<u4"), ("reasoning", "<u4"), ("mask", "<u4"), ("_pad", "<u4"),
                          ("consumed", "<u8"), ("n_chunks", "<u4"), ("reason", "<u4")])
 assert StreamResult.itemsize == 64
+MutResult = np.dtype([("out_off", "<u8"), ("out_len", "<u4"), ("status", "u1"), ("reason", "u1"), ("flags", "<u2")])
+assert MutResult.itemsize == 16
 
 EXPORTS = ["aigw_version", "aigw_init", "aigw_destroy", "aigw_last_error", "aigw_device_sm_count", "aigw_host_alloc", "aigw_host_free",
            "aigw_device_alloc", "aigw_device_free", "aigw_memcpy_h2d", "aigw_memcpy_d2h", "aigw_memset_d", "aigw_sync",
            "aigw_chat_translate_device", "aigw_chat_last_profile", "aigw_chat_translate_host", "aigw_sse_usage_device", "aigw_sse_usage_host", "aigw_response_usage_device", "aigw_response_usage_host", "aigw_usage_costs_device",
-           "aigw_bedrock_stream_device", "aigw_bedrock_stream_host"]
+           "aigw_bedrock_stream_device", "aigw_bedrock_stream_host", "aigw_body_mutate_device", "aigw_body_mutate_host"]
 
 
 class BackendCfg(C.Structure):
@@ -35,6 +37,22 @@ class BackendCfg(C.Structure):
 
 class BedrockStreamCfg(C.Structure):
     _fields_ = [("created", C.c_int64), ("response_id", C.c_char_p), ("request_model", C.c_char_p)]
+
+
+class BodyField(C.Structure):
+    _fields_ = [("path", C.c_char_p), ("value", C.c_char_p)]
+
+
+class BodyMutation(C.Structure):
+    _fields_ = [("remove", C.POINTER(C.c_char_p)), ("n_remove", C.c_uint32), ("set", C.POINTER(BodyField)), ("n_set", C.c_uint32)]
+
+
+def body_mutation(removes, sets):
+    """removes: [str]; sets: [(path, value)] → (BodyMutation, keepalive)."""
+    rm = (C.c_char_p * max(1, len(removes)))(*[r.encode() for r in removes])
+    st = (BodyField * max(1, len(sets)))(*[BodyField(p.encode(), v.encode()) for p, v in sets])
+    m = BodyMutation(C.cast(rm, C.POINTER(C.c_char_p)), len(removes), C.cast(st, C.POINTER(BodyField)), len(sets))
+    return m, (rm, st)
 
 
 class _StreamBatchOut(C.Structure):
@@ -86,6 +104,9 @@ def load_library():
     L.aigw_usage_costs_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.aigw_bedrock_stream_device.argtypes = [C.c_void_p, C.POINTER(BedrockStreamCfg), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    L.aigw_body_mutate_device.argtypes = [C.c_void_p, C.POINTER(BodyMutation), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    L.aigw_body_mutate_host.argtypes = [C.c_void_p, C.POINTER(BodyMutation), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(_StreamBatchOut)]
     L.aigw_bedrock_stream_host.argtypes = [C.c_void_p, C.POINTER(BedrockStreamCfg), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(_StreamBatchOut)]
     _lib = L
     return L
@@ -216,6 +237,31 @@ class Context:
         self._check(self.L.aigw_sse_usage_host(self.h, bytes_arr.ctypes.data, chunk_off.ctypes.data, chunk_first.ctypes.data, n_streams, n_chunks,
                                                res.ctypes.data, C.byref(h2d), C.byref(d2h), C.byref(ms)), "sse_usage_host")
         return res, {"h2d_bytes": h2d.value, "d2h_bytes": d2h.value, "kernel_ms": ms.value}
+
+    # ---- body mutation
+    def body_mutate_host(self, removes, sets, arena, offs, lens):
+        """Returns (results view, out view, info); views alias library-owned pinned memory until the next host call."""
+        m, keep = body_mutation(removes, sets)
+        n = len(lens)
+        bo = _StreamBatchOut()
+        self._check(self.L.aigw_body_mutate_host(self.h, C.byref(m), arena.ctypes.data, offs.ctypes.data, lens.ctypes.data, n, C.byref(bo)), "body_mutate_host")
+        if n == 0:
+            return np.zeros(0, dtype=MutResult), np.zeros(0, dtype=np.uint8), {"out_used": 0, "kernel_ms": 0.0}
+        res = np.ctypeslib.as_array(C.cast(bo.results, C.POINTER(C.c_uint8)), shape=(n * MutResult.itemsize,)).view(MutResult)
+        out = np.ctypeslib.as_array(C.cast(bo.out, C.POINTER(C.c_uint8)), shape=(max(1, bo.out_used),))
+        return res, out, {"out_used": bo.out_used, "h2d_bytes": bo.h2d_bytes, "d2h_bytes": bo.d2h_bytes, "kernel_ms": bo.kernel_ms, "gpu_launches": bo.gpu_launches}
+
+    def body_mutate(self, removes, sets, bodies):
+        """Convenience for tests: list of bytes → list of (status, reason, mutated bytes, unchanged flag)."""
+        arena, offs, lens = pack_bodies(bodies)
+        res, out, _ = self.body_mutate_host(removes, sets, arena, offs, lens)
+        return [(int(r["status"]), int(r["reason"]), bytes(out[int(r["out_off"]):int(r["out_off"]) + int(r["out_len"])]) if r["status"] == 0 else b"", bool(r["flags"] & 1)) for r in res]
+
+    def body_mutate_device(self, removes, sets, d_bodies, d_offs, d_lens, n, max_len, d_out, out_cap, d_res, d_used, timed=True):
+        m, keep = body_mutation(removes, sets)
+        ms = C.c_float(0)
+        self._check(self.L.aigw_body_mutate_device(self.h, C.byref(m), d_bodies, d_offs, d_lens, n, max_len, d_out, out_cap, d_res, d_used, None, C.byref(ms) if timed else None), "body_mutate_device")
+        return ms.value
 
     # ---- Bedrock eventstream → OpenAI SSE
     def bedrock_stream_host(self, bytes_arr, stream_off, request_model="", response_id="", created=0, out_capacity=0):

@@ -10,6 +10,7 @@
 #include "chat_kernel.cuh"
 #include "sse_kernel.cuh"
 #include "bedrock_stream_kernel.cuh"
+#include "mutate_kernel.cuh"
 
 using namespace aigw;
 
@@ -52,6 +53,7 @@ struct aigw_ctx {
   uint8_t* d_bs_work = nullptr; size_t bs_work_cap = 0;
   uint64_t* d_bs_off[2] = {nullptr, nullptr}; size_t bs_off_cap[2] = {0, 0};
   aigw_stream_result* h_sres = nullptr; size_t h_sres_cap = 0;
+  aigw_mut_result* h_mres = nullptr; size_t h_mres_cap = 0;
 };
 
 // response bodies expand (escaped tool arguments, configuration text): plan them in a roomier size class
@@ -135,7 +137,7 @@ void aigw_destroy(aigw_ctx* ctx) {
   }
   cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_res); cudaFree(ctx->d_counters); cudaFree(ctx->d_work); cudaFree(ctx->d_used_arr); cudaFreeHost(ctx->h_used_arr);
   for (auto& e2 : ctx->stage_ev) cudaEventDestroy(e2);
-  cudaFree(ctx->d_sse_bytes); cudaFree(ctx->d_sse_coff); cudaFree(ctx->d_sse_first); cudaFree(ctx->d_sse_res); cudaFree(ctx->d_bs_work); cudaFree(ctx->d_bs_off[0]); cudaFree(ctx->d_bs_off[1]); cudaFreeHost(ctx->h_sres);
+  cudaFree(ctx->d_sse_bytes); cudaFree(ctx->d_sse_coff); cudaFree(ctx->d_sse_first); cudaFree(ctx->d_sse_res); cudaFree(ctx->d_bs_work); cudaFree(ctx->d_bs_off[0]); cudaFree(ctx->d_bs_off[1]); cudaFreeHost(ctx->h_sres); cudaFreeHost(ctx->h_mres);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->s_compute); cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
   delete ctx;
@@ -421,6 +423,141 @@ int aigw_bedrock_stream_host(aigw_ctx* ctx, const aigw_bedrock_stream_cfg* cfg, 
   for (int c = 0; c < nch; c++) d2h += ctx->h_used_arr[c] < out_cap[c] ? ctx->h_used_arr[c] : out_cap[c];
   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   out->results = ctx->h_sres; out->out = ctx->h_out; out->out_used = total_cap; out->h2d_bytes = h2d; out->d2h_bytes = d2h; out->kernel_ms = ms;
+  return 0;
+}
+
+// ------------------------------------------------------------------ B1: body mutation
+static bool mut_path_ok(const char* p) {
+  bool digits = true;
+  for (const char* q = p; *q; q++) {
+    const unsigned char c = (unsigned char)*q;
+    if (c == '.' || c == '*' || c == '?' || c == '#' || c == '|' || c == ':' || c == '\\' || c == '@' || c < 0x21 || c > 0x7e || c == '"') return false;
+    if (c < '0' || c > '9') digits = false;
+  }
+  return !digits && strcmp(p, "-1") != 0;
+}
+// isJSONValue (internal/bodymutator/body_mutator.go:33-75)
+static bool mut_is_json_value(const std::string& value) {
+  size_t b = 0, e = value.size();
+  auto sp = [](unsigned char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\v' || c == '\f' || c == '\r' || c == 0x85 || c == 0xA0; };
+  while (b < e && sp((unsigned char)value[b])) b++;
+  while (e > b && sp((unsigned char)value[e - 1])) e--;
+  const std::string v = value.substr(b, e - b);
+  if (!v.empty() && v.front() == '"' && v.back() == '"') return true;
+  if (v == "0" || v == "true" || v == "false" || v == "null") return true;
+  if (!v.empty()) {
+    const char f = v[0];
+    if ((f >= '0' && f <= '9') || f == '-' || f == '+') {
+      bool num = true;
+      for (char c : v) if ((c < '0' || c > '9') && c != '.' && c != '-' && c != '+' && c != 'e' && c != 'E') { num = false; break; }
+      if (num) return true;
+    }
+  }
+  if (!v.empty() && v.front() == '{' && v.back() == '}') return true;
+  if (!v.empty() && v.front() == '[' && v.back() == ']') return true;
+  return false;
+}
+// fold the configured remove / set lists into per-key actions (see mutate_kernel.cuh)
+static int fill_mutate_params(aigw_ctx* ctx, MutateParams& P, const aigw_body_mutation* m) {
+  memset(P.keys, 0, sizeof P.keys); memset(P.text, 0, sizeof P.text); P.n_keys = 0;
+  P.text[kMutTextCap - 4] = ',';
+  struct K { std::string name, raw; bool remove = false, set = false; };
+  std::vector<K> keys;
+  auto find = [&](const char* name) -> K* { for (auto& k : keys) if (k.name == name) return &k; return nullptr; };
+  for (uint32_t i = 0; m && i < m->n_set; i++) {
+    const char* path = m->set[i].path; const char* val = m->set[i].value ? m->set[i].value : "";
+    if (!path || !*path) continue;
+    if (!mut_path_ok(path)) { ctx->err = std::string("body mutation path is not a plain top-level key: ") + path; return -2; }
+    std::string raw;
+    if (mut_is_json_value(val)) raw = val;
+    else {   // sjson.SetBytes of a Go string: plain quoting when nothing needs escaping
+      for (const char* q = val; *q; q++) { const unsigned char c = (unsigned char)*q; if (c < ' ' || c > 0x7f || c == '"' || c == '\\') { ctx->err = std::string("body mutation value needs JSON escaping: ") + path; return -2; } }
+      raw = std::string("\"") + val + "\"";
+    }
+    K* k = find(path);
+    if (!k) { keys.push_back(K{}); k = &keys.back(); k->name = path; }
+    k->set = true; k->raw = raw;
+  }
+  for (uint32_t i = 0; m && i < m->n_remove; i++) {
+    const char* path = m->remove[i];
+    if (!path || !*path) continue;
+    if (!mut_path_ok(path)) { ctx->err = std::string("body mutation path is not a plain top-level key: ") + path; return -2; }
+    K* k = find(path);
+    if (!k) { keys.push_back(K{}); k = &keys.back(); k->name = path; }
+    k->remove = true;
+  }
+  if (keys.size() > (size_t)kMutMaxKeys) { ctx->err = "more than 16 distinct body mutation keys"; return -2; }
+  size_t o = 0;
+  for (size_t i = 0; i < keys.size(); i++) {
+    const K& k = keys[i]; MutateKey& mk = P.keys[i];
+    const std::string memb = "\"" + k.name + "\":" + k.raw;
+    if (o + k.name.size() + memb.size() + 8 > (size_t)kMutTextCap - 8) { ctx->err = "body mutation text exceeds 3 KiB"; return -2; }
+    mk.name_off = (uint16_t)o; mk.name_len = (uint16_t)k.name.size(); memcpy(P.text + o, k.name.data(), k.name.size()); o += (k.name.size() + 3) & ~(size_t)3;
+    mk.memb_off = (uint16_t)o; mk.memb_len = (uint16_t)memb.size(); memcpy(P.text + o, memb.data(), memb.size());
+    mk.val_off = (uint16_t)(o + k.name.size() + 3); mk.val_len = (uint16_t)k.raw.size();
+    o += (memb.size() + 3) & ~(size_t)3;
+    mk.remove = k.remove; mk.set = k.set;
+  }
+  P.n_keys = (uint32_t)keys.size();
+  return 0;
+}
+int aigw_body_mutate_device(aigw_ctx* ctx, const aigw_body_mutation* m, const uint8_t* d_bodies, const uint64_t* d_offsets, const uint32_t* d_lens, uint32_t n,
+                            uint32_t max_len, uint8_t* d_out, uint64_t out_capacity, aigw_mut_result* d_results, uint64_t* d_out_used, void* stream, float* kernel_ms) {
+  if (kernel_ms) *kernel_ms = 0;
+  if (n == 0) return 0;
+  cudaSetDevice(ctx->device);
+  MutateParams P;
+  if (int rc = fill_mutate_params(ctx, P, m)) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->s_compute;
+  P.bodies = d_bodies; P.offsets = d_offsets; P.lens = d_lens; P.n = n; P.out = d_out; P.out_capacity = out_capacity; P.out_bias = 0; P.results = d_results;
+  P.out_used = (unsigned long long*)d_out_used;
+  P.next = ctx->d_counters + (ctx->counter_next++ & 255);
+  CK(cudaMemsetAsync(P.next, 0, sizeof(unsigned int), st));
+  CK(cudaMemsetAsync(d_out_used, 0, sizeof(uint64_t), st));
+  if (kernel_ms) CK(cudaEventRecord(ctx->ev0, st));
+  CK(launch_body_mutate(P, max_len ? max_len : 65536u, ctx->sm_count, st));
+  if (kernel_ms) { CK(cudaEventRecord(ctx->ev1, st)); CK(cudaEventSynchronize(ctx->ev1)); CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1)); }
+  return 0;
+}
+int aigw_body_mutate_host(aigw_ctx* ctx, const aigw_body_mutation* m, const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n,
+                          aigw_mut_batch_out* out) {
+  memset(out, 0, sizeof *out);
+  if (n == 0) return 0;
+  cudaSetDevice(ctx->device);
+  MutateParams P;
+  if (int rc = fill_mutate_params(ctx, P, m)) return rc;
+  uint32_t max_len = 0; uint64_t extra = 0;
+  for (uint32_t i = 0; i < n; i++) if (lens[i] > max_len) max_len = lens[i];
+  for (uint32_t k = 0; k < P.n_keys; k++) extra += P.keys[k].memb_len + 2;
+  const uint64_t lo = offsets[0], nbytes = offsets[n - 1] + lens[n - 1] - lo;
+  const uint64_t out_cap = (nbytes + (uint64_t)n * (extra + 32) + 4096 + 255) & ~255ull;
+  ChunkSlot& S = ctx->slot[0];
+  ENSURE(S.d_in, S.in_cap, nbytes + 64, false);
+  if (S.doc_cap < n) { cudaFree(S.d_off); cudaFree(S.d_len); S.doc_cap = 0; const size_t dc = (size_t)n + n / 8 + 16; CK(cudaMalloc(&S.d_off, dc * 8)); CK(cudaMalloc(&S.d_len, dc * 4)); S.doc_cap = dc; }
+  ENSURE(ctx->h_out, ctx->h_out_cap, out_cap, true);
+  ENSURE(ctx->h_mres, ctx->h_mres_cap, (size_t)n * sizeof(aigw_mut_result), true);
+  if (ctx->used_cap < 1) { CK(cudaMalloc(&ctx->d_used_arr, 64 * 8)); CK(cudaHostAlloc(&ctx->h_used_arr, 64 * 8, cudaHostAllocDefault)); ctx->used_cap = 64; }
+  uint8_t* dev_out = nullptr; aigw_mut_result* dev_res = nullptr;
+  CK(cudaHostGetDevicePointer((void**)&dev_out, ctx->h_out, 0));
+  CK(cudaHostGetDevicePointer((void**)&dev_res, ctx->h_mres, 0));
+  cudaStream_t st = ctx->s_compute;
+  CK(cudaMemcpyAsync(S.d_in, bodies + lo, nbytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(S.d_off, offsets, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(S.d_len, lens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  P.bodies = S.d_in - lo; P.offsets = S.d_off; P.lens = S.d_len; P.n = n; P.out = dev_out; P.out_capacity = out_cap; P.out_bias = 0; P.results = dev_res;
+  P.out_used = ctx->d_used_arr;
+  P.next = ctx->d_counters + (ctx->counter_next++ & 255);
+  CK(cudaMemsetAsync(P.next, 0, sizeof(unsigned int), st));
+  CK(cudaMemsetAsync(ctx->d_used_arr, 0, 8, st));
+  CK(cudaEventRecord(ctx->ev0, st));
+  CK(launch_body_mutate(P, max_len, ctx->sm_count, st));
+  CK(cudaEventRecord(ctx->ev1, st));
+  CK(cudaMemcpyAsync(ctx->h_used_arr, ctx->d_used_arr, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  const uint64_t used = ctx->h_used_arr[0] < out_cap ? ctx->h_used_arr[0] : out_cap;
+  out->results = ctx->h_mres; out->out = ctx->h_out; out->out_used = used; out->h2d_bytes = nbytes + (uint64_t)n * 12; out->d2h_bytes = used + (uint64_t)n * sizeof(aigw_mut_result) + 8;
+  out->gpu_launches = 1; out->kernel_ms = ms;
   return 0;
 }
 

@@ -190,6 +190,25 @@ typedef struct aigw_stream_batch_out { const aigw_stream_result* results; const 
 int aigw_bedrock_stream_host(aigw_ctx* ctx, const aigw_bedrock_stream_cfg* cfg, const uint8_t* bytes, const uint64_t* stream_off, uint32_t n_streams,
                              uint64_t out_capacity_hint, aigw_stream_batch_out* out);
 
+/* ---- route/backend body mutation (B1) ----
+ * Replaces BodyMutator.Mutate (internal/bodymutator/body_mutator.go:77-119; config type internal/filterapi/filterconfig.go:258-277)
+ * as applyBodyMutation (internal/extproc/util.go:107-131) runs it on the translated body, or on the original body when the
+ * translator returned none: sjson.DeleteBytes for every `remove`, then sjson.SetRawBytes (values isJSONValue accepts) or
+ * SetBytes (plain strings) for every `set`, in configuration order, top-level keys only.
+ * Result i: out[out_off .. out_off+out_len) (16-byte aligned records), flags bit0 = bytes identical to the input.
+ * status AIGW_DECLINED (stock path) for: a delete in a body with whitespace between top-level members (the surviving
+ * whitespace would depend on which comma sjson removes), duplicate top-level keys that are edited, escaped keys, more than
+ * 128 top-level members, bodies above 64 KiB.  The call returns -2 for paths that are not plain top-level keys
+ * ('.', '*', '?', '#', '|', ':', '@', '\\', all-digit) and for plain-string values that would need JSON escaping. */
+typedef struct aigw_body_field { const char* path; const char* value; } aigw_body_field;
+typedef struct aigw_body_mutation { const char* const* remove; uint32_t n_remove; const aigw_body_field* set; uint32_t n_set; } aigw_body_mutation;
+typedef struct aigw_mut_result { uint64_t out_off; uint32_t out_len; uint8_t status; uint8_t reason; uint16_t flags; } aigw_mut_result; /* 16 bytes */
+typedef struct aigw_mut_batch_out { const aigw_mut_result* results; const uint8_t* out; uint64_t out_used; uint64_t h2d_bytes, d2h_bytes; uint32_t gpu_launches; float kernel_ms; } aigw_mut_batch_out;
+int aigw_body_mutate_device(aigw_ctx* ctx, const aigw_body_mutation* m, const uint8_t* d_bodies, const uint64_t* d_offsets, const uint32_t* d_lens, uint32_t n,
+                            uint32_t max_len, uint8_t* d_out, uint64_t out_capacity, aigw_mut_result* d_results, uint64_t* d_out_used, void* stream, float* kernel_ms);
+int aigw_body_mutate_host(aigw_ctx* ctx, const aigw_body_mutation* m, const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n,
+                          aigw_mut_batch_out* out);
+
 const char* aigw_version(void);
 
 #ifdef __cplusplus
