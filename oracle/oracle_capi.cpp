@@ -7,6 +7,7 @@
 
 #include "bedrock_response.hpp"
 #include "bedrock_stream.hpp"
+#include "embeddings.hpp"
 #include "mutate.hpp"
 #include "stream.hpp"
 #include "translate.hpp"
@@ -37,6 +38,17 @@ void oracle_chat_translate(int schema, const char* body, uint64_t len, const cha
   out->model = dup(r.model); out->model_len = r.model.size();
   out->err = dup(r.err.msg); out->err_len = r.err.msg.size();
   out->mutated = dup(r.mutated_body); out->mutated_len = r.mutated_body.size();
+}
+void oracle_embeddings_translate(int schema, const char* body, uint64_t len, const char* model_override, const char* prefix, int force, oracle_result* out) {
+  TranslateResult r = embeddings_translate(schema, std::string_view(body, len), model_override ? model_override : "", prefix ? prefix : "", force != 0);
+  memset(out, 0, sizeof *out);
+  out->status = r.err.status; out->body_kind = r.body_kind; out->stream = 0; out->has_mutated = 0;
+  std::string path; for (auto& h : r.headers) if (h.name == ":path") path = h.value;
+  out->body = dup(r.body); out->body_len = r.body.size();
+  out->path = dup(path); out->path_len = path.size();
+  out->model = dup(r.model); out->model_len = r.model.size();
+  out->err = dup(r.err.msg); out->err_len = r.err.msg.size();
+  out->mutated = dup(""); out->mutated_len = 0;
 }
 void oracle_result_free(oracle_result* r) { free(r->body); free(r->path); free(r->model); free(r->err); free(r->mutated); memset(r, 0, sizeof *r); }
 

@@ -157,3 +157,17 @@ def body_mutate(body: bytes, removes, sets):
     rc = L.oracle_body_mutate(body, len(body), rm, len(removes), sp, sv, len(sets), C.byref(vp), C.byref(n))
     out = C.string_at(vp, n.value); L.oracle_free(vp)
     return rc, out
+
+
+def embeddings_translate(schema, body: bytes, model_override="", prefix="v1", force=False) -> Translated:
+    r = _Result()
+    lib().oracle_embeddings_translate(SCHEMA[schema] if isinstance(schema, str) else schema, body, len(body), model_override.encode(), prefix.encode(), int(force), C.byref(r))
+    t = Translated()
+    t.status, t.body_kind, t.stream = r.status, r.body_kind, False
+    t.body = C.string_at(r.body, r.body_len)
+    t.path = C.string_at(r.path, r.path_len).decode()
+    t.model = C.string_at(r.model, r.model_len)
+    t.err = C.string_at(r.err, r.err_len).decode("utf-8", "replace")
+    t.mutated = None
+    lib().oracle_result_free(C.byref(r))
+    return t

@@ -198,3 +198,54 @@ def test_body_mutation_unit_vectors():
     assert O.body_mutate(b' {"a":1 } ', [], [("b", "x y")])[1] == b'{"a":1 ,"b":"x y"}'
     assert O.body_mutate(b'{"a":1,"a":2}', ["a"], [("a", "9")])[1] == b'{"a":9}'
     assert O.body_mutate(b'{"a":1}', [], [("a.b", "1")])[0] == 1
+
+
+# ---------------------------------------------------------------- /v1/embeddings (P3, T1, T6)
+EMB_CASES = [c for c in CASES if c.get("path") == "/v1/embeddings" and "requestBody" in c]
+
+
+@pytest.mark.parametrize("c", [c for c in EMB_CASES if "expRequestBody" in c], ids=lambda c: c["name"])
+def test_embeddings_vertex_goldens(c):
+    """tests/data-plane/testupstream_test.go:782-852: bytes.Equal on the translated predict request."""
+    t = O.embeddings_translate("gcp-vertexai", c["requestBody"].encode())
+    assert t.status == 0 and t.body.decode() == c["expRequestBody"]
+    assert c["expPath"].endswith("/" + t.path)
+
+
+@pytest.mark.parametrize("c", [c for c in EMB_CASES if "expRequestBody" not in c and c["backend"] in ("openai", "azure-openai")], ids=lambda c: c["name"])
+def test_embeddings_passthrough_goldens(c):
+    t = O.embeddings_translate(c["backend"], c["requestBody"].encode(), prefix="v1" if c["backend"] == "openai" else "2025-01-01-preview")
+    assert t.status == 0 and t.body_kind == 0
+    assert t.path.split("?")[0] == c["expPath"]
+
+
+def test_embeddings_union_rules():
+    """internal/apischema/openai/union.go:71-147 accept/reject rules and the Vertex mapping (openai_gcpvertexai_embeddings.go:46-132)."""
+    E = lambda b, s="gcp-vertexai", **k: O.embeddings_translate(s, b, **k)
+    assert E(b'{"model":"m","input":null}').status == 1
+    assert E(b'{"model":"m","input":5}').status == 1
+    assert E(b'{"model":"m","input":[null]}').status == 1
+    assert E(b'{"model":"m","input":["a",5]}').status == 1
+    assert E(b'{"model":"m","input":{"content":""}}').status == 1
+    assert E(b'{"model":"m","input":{"task_type":"X"}}').status == 1
+    assert E(b'{"model":"m","input":[{"content":"a"},{"content":[]}]}').status == 1
+    assert E(b'{"model":5,"input":"a"}').status == 1
+    assert E(b'{"model":"m","input":"a","dimensions":1.5}').status == 1
+    assert E(b'{"model":"m","input":[1,2,3]}').status == 3           # Vertex: unsupported input type
+    assert E(b'{"model":"m","input":[[1,2],[3]]}').status == 3
+    assert E(b'{"model":"m","input":[1,2,3]}', "openai").status == 0
+    assert E(b'{"model":"m","input":[1,"a"]}', "openai").status == 1
+    assert E(b'{"model":"m"}').status == 3 and E(b'{"model":"m"}', "openai").status == 0
+    assert E(b'{"model":"m","input":[]}').body == b'{"instances":null,"parameters":{}}'
+    assert E(b'{"model":"m","input":["a",null]}').body == b'{"instances":[{"content":"a"},{"content":""}],"parameters":{}}'
+    assert E(b'{"model":"m","input":{"content":["a","b"],"task_type":"RETRIEVAL_DOCUMENT","title":"T"}}').body == \
+        b'{"instances":[{"content":"a","task_type":"RETRIEVAL_DOCUMENT","title":"T"},{"content":"b","task_type":"RETRIEVAL_DOCUMENT","title":"T"}],"parameters":{}}'
+    assert E(b'{"model":"m","input":{"content":"a","task_type":"RETRIEVAL_QUERY","title":"dropped"}}').body == b'{"instances":[{"content":"a","task_type":"RETRIEVAL_QUERY"}],"parameters":{}}'
+    assert E(b'{"model":"m","input":[{"content":"a","task_type":"RETRIEVAL_DOCUMENT","title":"T"}],"task_type":"CLUSTERING","auto_truncate":true,"dimensions":8}').body == \
+        b'{"instances":[{"content":"a","task_type":"CLUSTERING","title":"T"}],"parameters":{"auto_truncate":true,"outputDimensionality":8}}'
+    t = E(b'{"model":"m","input":"x"}', model_override="text-embedding-005")
+    assert t.path == "publishers/google/models/text-embedding-005:predict" and t.model == b"m"
+    t = E(b'{"input":"x","model":"m"}', "openai", model_override="big")
+    assert t.body == b'{"input":"x","model":"big"}' and t.path == "/v1/embeddings"
+    t = E(b'{"input":"x","model":"m"}', "azure-openai", model_override="dep", prefix="2024-10-21")
+    assert t.body == b'{"input":"x","model":"dep"}' and t.path == "/openai/deployments/dep/embeddings?api-version=2024-10-21"
