@@ -37,10 +37,11 @@ enum Kid : uint8_t {
   K_guided_choice, K_guided_regex, K_guided_json, K_TOP_END,
   K_role = K_TOP_END, K_content, K_name, K_tool_calls, K_tool_call_id, K_refusal, K_type, K_text, K_cache_control, K_ttl, K_signature, K_redactedContent,
   K_id, K_function, K_arguments, K_description, K_strict, K_parameters, K_google_search, K_budget_tokens, K_includeThoughts, K_include_usage,
+  K_input, K_encoding_format, K_dimensions, K_auto_truncate, K_task_type, K_title,   // /v1/embeddings
   K_COUNT
 };
 static_assert(K_TOP_END <= 63, "top-level seen mask is 64 bits");
-static_assert(K_COUNT <= 63, "ids are 6 bits in the token word");
+static_assert(K_COUNT <= 64, "ids are 6 bits in the token word");
 enum Vid : uint8_t {
   V_NONE = 0, V_user, V_assistant, V_system, V_developer, V_tool, V_text, V_refusal, V_thinking, V_redacted_thinking, V_ephemeral,
   V_enabled, V_disabled, V_adaptive, V_auto, V_required, V_image_url, V_input_audio, V_file
@@ -58,13 +59,14 @@ enum Vid : uint8_t {
   X("guided_choice", K_guided_choice) X("budget_tokens", K_budget_tokens) X("google_search", K_google_search) X("include_usage", K_include_usage) X("stream_options", K_stream_options) \
   X("safetySettings", K_safetySettings) X("response_format", K_response_format) X("redactedContent", K_redactedContent) X("includeThoughts", K_includeThoughts) \
   X("presence_penalty", K_presence_penalty) X("reasoning_effort", K_reasoning_effort) X("generationConfig", K_generationConfig) X("frequency_penalty", K_frequency_penalty) \
-  X("web_search_options", K_web_search_options) X("parallel_tool_calls", K_parallel_tool_calls) X("max_completion_tokens", K_max_completion_tokens)
+  X("web_search_options", K_web_search_options) X("parallel_tool_calls", K_parallel_tool_calls) X("max_completion_tokens", K_max_completion_tokens) \
+  X("input", K_input) X("encoding_format", K_encoding_format) X("dimensions", K_dimensions) X("auto_truncate", K_auto_truncate) X("task_type", K_task_type) X("title", K_title)
 #define AIGW_VALS(X) \
   X("user", V_user) X("tool", V_tool) X("text", V_text) X("auto", V_auto) X("system", V_system) X("refusal", V_refusal) X("enabled", V_enabled) X("thinking", V_thinking) \
   X("disabled", V_disabled) X("adaptive", V_adaptive) X("required", V_required) X("assistant", V_assistant) X("developer", V_developer) X("ephemeral", V_ephemeral) \
   X("redacted_thinking", V_redacted_thinking) X("image_url", V_image_url) X("input_audio", V_input_audio) X("file", V_file)
 
-// Response direction (P.schema >= AIGW_SCHEMA_RESP_AWS_BEDROCK): the index kernel loads this key table instead; ids share
+// Response direction ((P.schema & 48) == AIGW_SCHEMA_RESP_AWS_BEDROCK): the index kernel loads this key table instead; ids share
 // the 6-bit field of the token word.  awsbedrock.ConverseResponse, internal/apischema/awsbedrock/awsbedrock.go:178-182,264-279,330-432.
 enum RKid : uint8_t {
   RK_NONE = 0, RK_output, RK_message, RK_content, RK_role, RK_text, RK_toolUse, RK_toolUseId, RK_name, RK_input, RK_reasoningContent, RK_reasoningText,
@@ -105,6 +107,18 @@ constexpr IdTables make_id_tables() {
 #undef X
   return t;
 }
+// the device lookup probes at most 6 slots: every inserted string must sit within 6 of its home slot
+constexpr int id_max_probe(const IdSlot* tab, int slots) {
+  int worst = 0;
+  for (int sl = 0; sl < slots; sl++) {
+    if (!tab[sl].meta) continue;
+    const int home = (int)(id_hash(tab[sl].w, tab[sl].meta & 0xffu) & (uint32_t)(slots - 1));
+    const int dist = (sl - home + slots) & (slots - 1);
+    if (dist > worst) worst = dist;
+  }
+  return worst + 1;
+}
+static_assert(id_max_probe(make_id_tables().key, kKeySlots) <= 6 && id_max_probe(make_id_tables().val, kValSlots) <= 6, "id hash table needs more than 6 probes");
 __device__ __constant__ IdTables c_ids = make_id_tables();
 constexpr IdTables make_resp_id_tables() {
   IdTables t{};
@@ -113,6 +127,7 @@ constexpr IdTables make_resp_id_tables() {
 #undef X
   return t;
 }
+static_assert(id_max_probe(make_resp_id_tables().key, kKeySlots) <= 6, "response id hash table needs more than 6 probes");
 __device__ __constant__ IdTables c_ids_resp = make_resp_id_tables();
 
 // id of a short string (1 ≤ n ≤ kMaxIdLen) held in shared memory, against the key or the value table (also in shared
@@ -792,6 +807,174 @@ struct Walker {
       pl.lit(L_RBRACE);
     }
     pl.lit(L_RBRACE);
+  }
+
+  // ---------------------------------------------------------------- /v1/embeddings (P3 + T1 + T6)
+  // EmbeddingsEndpointSpec.ParseBody (internal/endpointspec/endpointspec.go:231-240; input union internal/apischema/openai/union.go:71-147,
+  // EmbeddingInputItem / EmbeddingContent internal/apischema/openai/openai.go:316-375) followed by the OpenAI / Azure passthrough
+  // (internal/translator/openai_embeddings.go:38-59, openai_azureopenai_embeddings.go:36-61) or the Vertex predict request
+  // (internal/translator/openai_gcpvertexai_embeddings.go:46-180, internal/apischema/gcp/gcp.go:45-76).
+  struct EmbItem { int content, task, title; };
+  // Go int / int64 struct field: a number with a fraction or exponent fails the decode (400); other spellings strconv would
+  // not print back (leading '-0', > 18 digits) are left to the stock path
+  __device__ bool emb_int(int v) {
+    if (!is_num(v)) { decline(AIGW_R_E400_TYPE); return false; }
+    const uint32_t o = d.tok(v), e = d.scalar_end(v);
+    for (uint32_t i = o; i < e; i++) { const uint32_t c = d.s[i]; if (c == '.' || c == 'e' || c == 'E') { decline(AIGW_R_E400_TYPE); return false; } }
+    if (!canon_number(d.s + o, e - o, true)) { decline(AIGW_R_NUMBER); return false; }
+    return true;
+  }
+  // one EmbeddingInputItem: returns false after decline(); `empty` = EmbeddingContent.IsEmpty()
+  __device__ bool scan_emb_item(int e, EmbItem& it, bool& empty) {
+    it.content = it.task = it.title = -1; empty = true;
+    if (is_null(e)) return true;
+    if (!is_obj(e)) { decline(AIGW_R_E400_TYPE); return false; }
+    uint32_t seen = 0; int content_raw = -1;
+    for (int m = e + 1; d.ty(m) != '}'; m = d.after(m + 3)) {
+      int slot;
+      switch (d.id(m)) { case K_content: slot = 0; break; case K_task_type: slot = 1; break; case K_title: slot = 2; break; default: slot = -1; }
+      if (slot < 0) continue;
+      if (seen & (1u << slot)) { decline(AIGW_R_DUP_KEY); return false; }
+      seen |= 1u << slot;
+      const int v = m + 3;
+      if (slot == 0) content_raw = v; else if (!is_null(v)) { if (!is_str(v)) { decline(AIGW_R_E400_TYPE); return false; } if (slot == 1) it.task = v; else it.title = v; }
+    }
+    if (content_raw >= 0) {
+      if (is_null(content_raw)) empty = true;                  // decodes as the empty string
+      else if (is_str(content_raw)) { it.content = content_raw; empty = d.str_len(content_raw) == 0; }
+      else if (is_arr(content_raw)) {
+        it.content = content_raw; empty = d.ty(content_raw + 1) == ']';
+        for (int q = content_raw + 1; d.ty(q) != ']'; q = d.after(q)) if (!is_str(q) && !is_null(q)) { decline(AIGW_R_E400_CONTENT); return false; }
+      } else { decline(AIGW_R_E400_CONTENT); return false; }
+    }
+    return true;
+  }
+  __device__ bool str_eq_lit(int v, const char* w, uint32_t wl) const {
+    if (d.str_has_backslash(v) || d.str_len(v) != wl) return false;
+    const uint8_t* p = d.s + d.str_off(v);
+    for (uint32_t i = 0; i < wl; i++) if (p[i] != (uint8_t)w[i]) return false;
+    return true;
+  }
+  // one gcp.Instance: {"content":C[,"task_type":T][,"title":X]}
+  __device__ void emit_instance(int content /* string token or -1 = "" */, int task, int title, bool& first) {
+    if (!first) pl.lit(L_COMMA); first = false;
+    pl.lit(L_EM_CONTENT); if (content >= 0) emit_str(content); else pl.lit(L_EMPTY_STR);
+    if (task >= 0 && d.str_len(task) > 0) { pl.lit(L_EM_TASK); emit_str(task); }
+    if (title >= 0) { pl.lit(L_EM_TITLE); emit_str(title); }
+    pl.lit(L_RBRACE);
+  }
+  __device__ void emit_item_instances(const EmbItem& it, int global_task, bool& first) {
+    // Title is kept only with the ITEM's task_type == RETRIEVAL_DOCUMENT; a request-level task_type then overrides the type
+    const bool keep_title = it.task >= 0 && it.title >= 0 && d.str_len(it.title) > 0 && str_eq_lit(it.task, "RETRIEVAL_DOCUMENT", 18);
+    const int task = global_task >= 0 ? global_task : it.task;
+    const int title = keep_title ? it.title : -1;
+    if (is_str(it.content)) emit_instance(it.content, task, title, first);
+    else for (int q = it.content + 1; d.ty(q) != ']'; q = d.after(q)) emit_instance(is_null(q) ? -1 : q, task, title, first);
+  }
+  __device__ void plan_embeddings(uint32_t& path_len, uint32_t& model_off, uint32_t& model_len, uint32_t& body_kind) {
+    const int base = P->schema & 15;
+    body_kind = AIGW_BODY_UNCHANGED;
+    int input = -1, model_raw = -1, model = -1, dims = -1, autot = -1, gtask = -1;
+    bool has_input = false;
+    if (!is_null(0)) {
+      if (!is_obj(0)) { decline(AIGW_R_E400_TYPE); return; }
+      uint32_t seen = 0;
+      for (int m = 1; d.ty(m) != '}'; m = d.after(m + 3)) {
+        int slot;
+        switch (d.id(m)) { case K_input: slot = 0; break; case K_model: slot = 1; break; case K_encoding_format: slot = 2; break; case K_dimensions: slot = 3; break; case K_user: slot = 4; break;
+          case K_auto_truncate: slot = 5; break; case K_task_type: slot = 6; break; default: slot = -1; }
+        if (slot < 0) continue;
+        if (seen & (1u << slot)) { decline(AIGW_R_DUP_KEY); return; }
+        seen |= 1u << slot;
+        const int v = m + 3; const bool nul = is_null(v);
+        switch (slot) {
+          case 0: input = v; has_input = true; break;
+          case 1: model_raw = v; if (!nul) { if (!is_str(v)) { decline(AIGW_R_E400_TYPE); return; } model = v; } break;
+          case 2: case 4: if (!nul && !is_str(v)) { decline(AIGW_R_E400_TYPE); return; } break;
+          case 3: if (!nul) { if (!emb_int(v)) return; dims = v; } break;
+          case 5: if (!nul) { if (!is_bool(v)) { decline(AIGW_R_E400_TYPE); return; } autot = v; } break;
+          case 6: if (!nul) { if (!is_str(v)) { decline(AIGW_R_E400_TYPE); return; } if (d.str_len(v) > 0) gtask = v; } break;  // "" overrides nothing
+        }
+      }
+    }
+    // ---- the input union: 0 none, 1 string, 2 []string, 3 item, 4 []item, 5 ints / int arrays
+    int kind = 0;
+    if (has_input) {
+      if (is_str(input)) kind = 1;
+      else if (is_obj(input)) { EmbItem it; bool empty; if (!scan_emb_item(input, it, empty)) return; if (empty) { decline(AIGW_R_E400_CONTENT); return; } kind = 3; }
+      else if (is_arr(input)) {
+        const int f = input + 1;
+        if (d.ty(f) == ']') kind = 2;
+        else if (is_str(f)) { kind = 2; for (int q = f; d.ty(q) != ']'; q = d.after(q)) if (!is_str(q) && !is_null(q)) { decline(AIGW_R_E400_TYPE); return; } }
+        else if (is_obj(f)) { kind = 4; for (int q = f; d.ty(q) != ']'; q = d.after(q)) { EmbItem it; bool empty; if (!scan_emb_item(q, it, empty)) return; if (empty) { decline(AIGW_R_E400_CONTENT); return; } } }
+        else if (is_arr(f)) {
+          kind = 5;
+          for (int q = f; d.ty(q) != ']'; q = d.after(q)) {
+            if (is_null(q)) continue;
+            if (!is_arr(q)) { decline(AIGW_R_E400_TYPE); return; }
+            for (int x = q + 1; d.ty(x) != ']'; x = d.after(x)) if (!is_null(x) && !emb_int(x)) return;
+          }
+        } else if (is_num(f)) { kind = 5; for (int q = f; d.ty(q) != ']'; q = d.after(q)) if (!is_null(q) && !emb_int(q)) return; }
+        else { decline(AIGW_R_E400_TYPE); return; }
+      } else { decline(AIGW_R_E400_TYPE); return; }
+    }
+    if (bad()) return;
+    if (model >= 0) { if (d.str_has_backslash(model)) { decline(AIGW_R_ESCAPE); return; } model_off = d.str_off(model); model_len = d.str_len(model); }
+    const bool need_model = P->override_len != 0;
+    if (need_model) for (uint32_t i = 0; i < P->override_len; i++) { const uint32_t c = (uint8_t)P->override_model[i]; if (c < 0x20 || c > 0x7f || c == '"' || c == '\\') { decline(AIGW_R_UNSUPPORTED_FIELD); return; } }
+    // ---- :path
+    if (base == AIGW_SCHEMA_OPENAI) emit_cfg_text(P->openai_path, P->prefix_len);
+    else {
+      pl.lit(base == AIGW_SCHEMA_AZURE_OPENAI ? L_EM_AZ_PATH1 : L_EM_GOOGLE_PATH);
+      if (need_model) emit_cfg_text(P->override_model, P->override_len); else if (model >= 0) pl.src(d, d.str_off(model), d.str_len(model));
+      if (base == AIGW_SCHEMA_AZURE_OPENAI) { pl.lit(L_EM_AZ_PATH2); emit_cfg_text(P->api_version, P->version_len); } else pl.lit(L_EM_PREDICT);
+    }
+    if (bad()) return;
+    path_len = pl.olen;
+    if (base != AIGW_SCHEMA_GCP_VERTEX) {
+      // sjson.SetBytesOptions(original, "model", override): splice the first "model" value, or append the member at the root
+      if (!need_model) { if (P->force_mutation) { pl.src(d, 0, d.len); body_kind = AIGW_BODY_BYTES; } return; }
+      body_kind = AIGW_BODY_BYTES;
+      if (is_null(0)) { pl.lit(L_LBRACE); pl.lit(L_MODEL_MEMBER); pl.lit(L_QUOTE); emit_cfg_text(P->override_model, P->override_len); pl.lit(L_QUOTE); pl.lit(L_RBRACE); return; }
+      const int root_close = d.jmp[0];
+      if (model_raw >= 0) {
+        const uint32_t b = d.tok(model_raw), e = is_str(model_raw) ? d.tok(model_raw + 1) + 1u : d.scalar_end(model_raw);
+        pl.src(d, 0, b); pl.lit(L_QUOTE); emit_cfg_text(P->override_model, P->override_len); pl.lit(L_QUOTE); pl.src(d, e, d.len - e);
+      } else {
+        const uint32_t o = d.tok(0), c = d.tok(root_close);
+        pl.src(d, o, c - o); if (root_close != 1) pl.lit(L_COMMA); pl.lit(L_MODEL_MEMBER); pl.lit(L_QUOTE); emit_cfg_text(P->override_model, P->override_len); pl.lit(L_QUOTE); pl.lit(L_RBRACE);
+      }
+      return;
+    }
+    // ---- Vertex: gcp.PredictRequest{instances, parameters}
+    if (kind == 0 || kind == 5) { pend(AIGW_R_E500_ARGS); return; }   // "unsupported input type for embedding"
+    body_kind = AIGW_BODY_BYTES;
+    pl.lit(L_EM_OPEN);
+    {
+      bool first = true;
+      bool any = false;
+      if (kind == 1) any = true;
+      else if (kind == 2) any = d.ty(input + 1) != ']';
+      else any = true;
+      if (!any) pl.lit(L_NULL);
+      else {
+        pl.lit(L_LBRACK);
+        if (kind == 1) emit_instance(input, gtask, -1, first);
+        else if (kind == 2) { for (int q = input + 1; d.ty(q) != ']'; q = d.after(q)) emit_instance(is_null(q) ? -1 : q, gtask, -1, first); }
+        else if (kind == 3) { EmbItem it; bool e2; scan_emb_item(input, it, e2); emit_item_instances(it, gtask, first); }
+        else { for (int q = input + 1; d.ty(q) != ']'; q = d.after(q)) { EmbItem it; bool e2; scan_emb_item(q, it, e2); emit_item_instances(it, gtask, first); } }
+        pl.lit(L_RBRACK);
+      }
+    }
+    pl.lit(L_EM_PARAMS);
+    bool pf = true;
+    if (autot >= 0 && d.ty(autot) == 't') { pl.lit(L_EM_AUTOTRUNC); pf = false; }
+    if (dims >= 0) {
+      const uint32_t o = d.tok(dims), e = d.scalar_end(dims);
+      bool pos = d.s[o] != '-'; if (pos) { pos = false; for (uint32_t i = o; i < e; i++) if (d.s[i] != '0') pos = true; }
+      if (pos) { if (!pf) pl.lit(L_COMMA); pl.lit(L_EM_DIMS); pl.src(d, o, e - o); }
+    }
+    pl.lit(L_EM_END);
   }
 
   struct Msg { int role_v, content, name, tool_calls, tool_call_id, refusal, audio; };
@@ -1551,7 +1734,7 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
   IdTables* s_ids = (IdTables*)smem;
   uint8_t* s_cls = smem + sizeof(IdTables);
   {
-    const uint32_t* src = (const uint32_t*)(P.schema >= AIGW_SCHEMA_RESP_AWS_BEDROCK ? &c_ids_resp : &c_ids);
+    const uint32_t* src = (const uint32_t*)((P.schema & 48) == AIGW_SCHEMA_RESP_AWS_BEDROCK ? &c_ids_resp : &c_ids);
     for (uint32_t i = threadIdx.x; i < sizeof(IdTables) / 4; i += blockDim.x) ((uint32_t*)s_ids)[i] = src[i];
   }
   for (uint32_t c = threadIdx.x; c < 256; c += blockDim.x) s_cls[c] = is_ws(c) ? 1 : is_op(c) ? 2 : (c == '"' ? 3 : 0);
@@ -1789,7 +1972,7 @@ __global__ void __launch_bounds__(128, AIGW_WALK_BLOCKS) chat_walk_kernel(const 
   int reason = validate_tokens(W.d);
   if (reason == AIGW_R_SYNTAX) reason = AIGW_R_E400_SYNTAX;
   uint32_t path_len = 0;
-  if (P.schema >= AIGW_SCHEMA_RESP_AWS_BEDROCK) {
+  if ((P.schema & 48) == AIGW_SCHEMA_RESP_AWS_BEDROCK) {
     // response direction: json.Decoder semantics differ from the request-side strictness (trailing bytes are fine, a syntax
     // error is "failed to unmarshal body"), so anything the token grammar rejects goes to the stock path
     if (reason) reason = AIGW_R_SYNTAX;
@@ -1797,6 +1980,15 @@ __global__ void __launch_bounds__(128, AIGW_WALK_BLOCKS) chat_walk_kernel(const 
       W.plan_bedrock_response(path_len);
       W.pl.flush();
       reason = W.reason ? W.reason : W.pl.err;
+      if (!reason && W.pl.nops == 0) reason = AIGW_R_OPS;
+    }
+  } else if (P.schema & AIGW_SCHEMA_EMBEDDINGS) {
+    if (!reason) {
+      uint32_t mo = 0, mlen = 0, bk = AIGW_BODY_UNCHANGED;
+      W.plan_embeddings(path_len, mo, mlen, bk);
+      po.model_off = mo; po.model_len = (uint16_t)mlen; po.flags = bk == AIGW_BODY_UNCHANGED ? 0x80u : 0u;
+      W.pl.flush();
+      reason = W.reason ? W.reason : W.pl.err ? W.pl.err : W.pending;
       if (!reason && W.pl.nops == 0) reason = AIGW_R_OPS;
     }
   } else if (!reason) {

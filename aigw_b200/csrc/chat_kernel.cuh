@@ -137,7 +137,19 @@ namespace aigw {
   X(L_R_FR_STOP, "stop")                                                                        \
   X(L_R_FR_LENGTH, "length")                                                                    \
   X(L_R_FR_FILTER, "content_filter")                                                            \
-  X(L_R_FR_TOOLS, "tool_calls")
+  X(L_R_FR_TOOLS, "tool_calls")                                                                \
+  X(L_EM_OPEN, "{\"instances\":")                                                               \
+  X(L_EM_CONTENT, "{\"content\":")                                                              \
+  X(L_EM_TASK, ",\"task_type\":")                                                               \
+  X(L_EM_TITLE, ",\"title\":")                                                                  \
+  X(L_EM_PARAMS, ",\"parameters\":{")                                                           \
+  X(L_EM_AUTOTRUNC, "\"auto_truncate\":true")                                                   \
+  X(L_EM_DIMS, "\"outputDimensionality\":")                                                     \
+  X(L_EM_END, "}}")                                                                             \
+  X(L_EM_GOOGLE_PATH, "publishers/google/models/")                                              \
+  X(L_EM_PREDICT, ":predict")                                                                   \
+  X(L_EM_AZ_PATH1, "/openai/deployments/")                                                      \
+  X(L_EM_AZ_PATH2, "/embeddings?api-version=")
 
 enum LitId : int {
 #define X(name, text) name,

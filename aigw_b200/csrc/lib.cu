@@ -74,11 +74,11 @@ static void fill_params(ChatParams& P, const aigw_backend_cfg* cfg) {
   std::string pfx = (cfg && cfg->openai_prefix) ? cfg->openai_prefix : "v1";
   while (!pfx.empty() && pfx.front() == '/') pfx.erase(0, 1);
   while (!pfx.empty() && pfx.back() == '/') pfx.pop_back();
-  std::string path = "/" + (pfx.empty() ? std::string() : pfx + "/") + "chat/completions";
+  std::string path = "/" + (pfx.empty() ? std::string() : pfx + "/") + ((cfg && (cfg->schema & AIGW_SCHEMA_EMBEDDINGS)) ? "embeddings" : "chat/completions");
   if (path.size() > sizeof P.openai_path) path.resize(sizeof P.openai_path);
   memcpy(P.openai_path, path.data(), path.size()); P.prefix_len = (uint16_t)path.size();
   P.created = 0; P.rid_len = 0; memset(P.response_id, 0, sizeof P.response_id);
-  if (cfg && cfg->schema >= AIGW_SCHEMA_RESP_AWS_BEDROCK) {
+  if (cfg && (cfg->schema & 48) == AIGW_SCHEMA_RESP_AWS_BEDROCK) {
     P.created = cfg->created;
     if (cfg->response_id) { size_t n = strlen(cfg->response_id); if (n > sizeof P.response_id) n = sizeof P.response_id; memcpy(P.response_id, cfg->response_id, n); P.rid_len = (uint16_t)n; }
   }
@@ -166,7 +166,7 @@ int aigw_chat_translate_device(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const
   P.results = d_results; P.out_used = (unsigned long long*)d_out_used;
   P.next_doc = nullptr; P.out_bias = 0;
   uint32_t ml = max_len ? max_len : 65536u;
-  if (cfg && cfg->schema >= AIGW_SCHEMA_RESP_AWS_BEDROCK) ml = resp_class_len(ml);
+  if (cfg && (cfg->schema & 48) == AIGW_SCHEMA_RESP_AWS_BEDROCK) ml = resp_class_len(ml);
   {  // workspace for one sub-batch (≤ 128 Ki documents); the launcher loops over sub-batches
     const size_t sub = n < 131072u ? n : 131072u;
     ENSURE(ctx->d_work, ctx->work_cap, chat_work_bytes(ml, sub), false);
@@ -232,7 +232,7 @@ int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const u
       S.doc_cap = dc;
     }
   }
-  if (cfg && cfg->schema >= AIGW_SCHEMA_RESP_AWS_BEDROCK) max_len = resp_class_len(max_len);
+  if (cfg && (cfg->schema & 48) == AIGW_SCHEMA_RESP_AWS_BEDROCK) max_len = resp_class_len(max_len);
   ENSURE(ctx->d_work, ctx->work_cap, chat_work_bytes(max_len, max_docs < 131072u ? max_docs : 131072u), false);
   ENSURE(ctx->h_out, ctx->h_out_cap, total_out_cap, true);
   ENSURE(ctx->h_res, ctx->h_res_cap, (size_t)n * sizeof(aigw_doc_result), true);

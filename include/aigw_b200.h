@@ -44,7 +44,12 @@ enum aigw_schema { AIGW_SCHEMA_OPENAI = 0, AIGW_SCHEMA_AWS_BEDROCK = 1, AIGW_SCH
                     * seconds (time.Now() in the reference).  The output record is [aigw_usage (32 bytes)][JSON body]:
                     * path_len == 32 and the usage struct sits where request schemas put the :path.
                     * status AIGW_INTERNAL = "failed to unmarshal body". */
-                   AIGW_SCHEMA_RESP_AWS_BEDROCK = 16 };
+                   AIGW_SCHEMA_RESP_AWS_BEDROCK = 16,
+                   /* /v1/embeddings requests (EmbeddingsEndpointSpec.ParseBody, internal/endpointspec/endpointspec.go:231-240, then the
+                    * OpenAI / Azure passthrough translators internal/translator/openai_embeddings.go:38-59,
+                    * openai_azureopenai_embeddings.go:36-61 or the Vertex predict translator openai_gcpvertexai_embeddings.go:46-180):
+                    * AIGW_SCHEMA_EMBEDDINGS | base schema.  openai_prefix / api_version / model_name_override as for chat. */
+                   AIGW_SCHEMA_EMBEDDINGS = 32, AIGW_SCHEMA_EMB_OPENAI = 32, AIGW_SCHEMA_EMB_AZURE_OPENAI = 34, AIGW_SCHEMA_EMB_GCP_VERTEX = 35 };
 
 /* Why a body was declined / rejected (diagnostics; stable numbering). */
 enum aigw_reason {
