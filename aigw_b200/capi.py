@@ -26,7 +26,8 @@ assert MutResult.itemsize == 16
 EXPORTS = ["aigw_version", "aigw_init", "aigw_destroy", "aigw_last_error", "aigw_device_sm_count", "aigw_host_alloc", "aigw_host_free",
            "aigw_device_alloc", "aigw_device_free", "aigw_memcpy_h2d", "aigw_memcpy_d2h", "aigw_memset_d", "aigw_sync",
            "aigw_chat_translate_device", "aigw_chat_last_profile", "aigw_chat_translate_host", "aigw_sse_usage_device", "aigw_sse_usage_host", "aigw_response_usage_device", "aigw_response_usage_host", "aigw_usage_costs_device",
-           "aigw_bedrock_stream_device", "aigw_bedrock_stream_host", "aigw_body_mutate_device", "aigw_body_mutate_host"]
+           "aigw_bedrock_stream_device", "aigw_bedrock_stream_host", "aigw_body_mutate_device", "aigw_body_mutate_host",
+           "aigw_batcher_start", "aigw_batcher_translate", "aigw_batcher_get_stats", "aigw_batcher_stop"]
 
 
 class BackendCfg(C.Structure):
@@ -104,6 +105,11 @@ def load_library():
     L.aigw_usage_costs_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.aigw_bedrock_stream_device.argtypes = [C.c_void_p, C.POINTER(BedrockStreamCfg), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    L.aigw_batcher_start.argtypes = [C.c_void_p, C.POINTER(BackendCfg), C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
+    L.aigw_batcher_translate.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.aigw_batcher_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+    L.aigw_batcher_stop.argtypes = [C.c_void_p]
+    L.aigw_batcher_stop.restype = None
     L.aigw_body_mutate_device.argtypes = [C.c_void_p, C.POINTER(BodyMutation), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
     L.aigw_body_mutate_host.argtypes = [C.c_void_p, C.POINTER(BodyMutation), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(_StreamBatchOut)]
@@ -237,6 +243,30 @@ class Context:
         self._check(self.L.aigw_sse_usage_host(self.h, bytes_arr.ctypes.data, chunk_off.ctypes.data, chunk_first.ctypes.data, n_streams, n_chunks,
                                                res.ctypes.data, C.byref(h2d), C.byref(d2h), C.byref(ms)), "sse_usage_host")
         return res, {"h2d_bytes": h2d.value, "d2h_bytes": d2h.value, "kernel_ms": ms.value}
+
+    # ---- request batcher (synchronous single-request call, thread safe)
+    def batcher_start(self, cfg, max_batch=256, window_us=50):
+        h = C.c_void_p()
+        self._check(self.L.aigw_batcher_start(self.h, C.byref(cfg), max_batch, window_us, C.byref(h)), "batcher_start")
+        return h
+
+    def batcher_translate(self, b, body: bytes, out_cap=1 << 17):
+        """→ (rc, status, reason, path bytes, body bytes, body_kind).  Releases the GIL while it waits."""
+        out = C.create_string_buffer(out_cap)
+        res = np.zeros(1, dtype=DocResult)
+        rc = self.L.aigw_batcher_translate(b, body, len(body), out, out_cap, res.ctypes.data)
+        r = res[0]
+        pl, bl = int(r["path_len"]), int(r["body_len"])
+        ok = rc == 0 and r["status"] == AIGW_OK
+        return rc, int(r["status"]), int(r["reason"]), out.raw[:pl] if ok else b"", out.raw[pl:pl + bl] if ok else b"", int(r["body_kind"])
+
+    def batcher_stats(self, b):
+        st = np.zeros(1, dtype=np.dtype([("batches", "<u8"), ("requests", "<u8"), ("max_batch_seen", "<u4"), ("_pad", "<u4")]))
+        self.L.aigw_batcher_get_stats(b, st.ctypes.data)
+        return {k: int(st[0][k]) for k in ("batches", "requests", "max_batch_seen")}
+
+    def batcher_stop(self, b):
+        self.L.aigw_batcher_stop(b)
 
     # ---- body mutation
     def body_mutate_host(self, removes, sets, arena, offs, lens):

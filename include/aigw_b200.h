@@ -214,6 +214,19 @@ int aigw_body_mutate_device(aigw_ctx* ctx, const aigw_body_mutation* m, const ui
 int aigw_body_mutate_host(aigw_ctx* ctx, const aigw_body_mutation* m, const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n,
                           aigw_mut_batch_out* out);
 
+/* ---- per-GPU request batcher: the synchronous single-request call for the cgo shim ----
+ * The reference translates one request per goroutine (internal/extproc/processor_impl.go:211-398); a GPU wants batches.
+ * aigw_batcher_translate is called concurrently from any number of threads, blocks until its request has been through ONE
+ * aigw_chat_translate_host call shared with the requests that arrived within `window_us` of the batch's first one (or until
+ * `max_batch` are queued), and returns the request's own record in `out` (`[:path][body]`, res->out_off == 0).
+ * Return: 0, a CUDA error code if the batch failed, -4 if `out_cap` is too small, -5 after stop.  `cfg` strings are copied. */
+typedef struct aigw_batcher aigw_batcher;
+typedef struct aigw_batcher_stats { uint64_t batches, requests; uint32_t max_batch_seen, _pad; } aigw_batcher_stats;
+int  aigw_batcher_start(aigw_ctx* ctx, const aigw_backend_cfg* cfg, uint32_t max_batch, uint32_t window_us, aigw_batcher** out);
+int  aigw_batcher_translate(aigw_batcher* b, const uint8_t* body, uint32_t len, uint8_t* out, uint32_t out_cap, aigw_doc_result* res);
+int  aigw_batcher_get_stats(aigw_batcher* b, aigw_batcher_stats* s);
+void aigw_batcher_stop(aigw_batcher* b);
+
 const char* aigw_version(void);
 
 #ifdef __cplusplus
