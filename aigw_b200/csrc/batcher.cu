@@ -20,14 +20,13 @@
 #include "../../include/aigw_b200.h"
 
 namespace {
-constexpr int kFan = 4;
-constexpr size_t kTreeFrom = 0, kTreeRoots = 0;   // a wake tree (each woken ticket waking kFan more) was measured: same median, worse tails than waking every ticket from the batcher thread, so it is off
+// (A wake tree — each woken ticket waking four more — was measured: same median, worse tails than waking every ticket
+// from the batcher thread, so the batcher wakes them all itself.)
 struct Ticket {
   const uint8_t* body; uint32_t len;
   uint8_t* out; uint32_t out_cap;
   // filled by the batcher thread before the wake
   const aigw_doc_result* src_res = nullptr; const uint8_t* src_out = nullptr; int batch_rc = 0;
-  Ticket* child[kFan] = {nullptr, nullptr, nullptr, nullptr};
   std::atomic<uint32_t>* pending = nullptr;
   bool woken = false;
   std::mutex m; std::condition_variable cv;
@@ -71,7 +70,6 @@ struct aigw_batcher {
     for (size_t i = 0; i < n; i++) {
       Ticket* t = batch[i];
       t->batch_rc = rc; t->src_res = bo ? bo->results + i : nullptr; t->src_out = bo ? bo->out : nullptr; t->pending = &pending;
-      for (int c = 0; c < kFan; c++) { const size_t k = kTreeFrom + (i - 0) * kFan + 1 + c; t->child[c] = (i >= kTreeRoots || k >= n) ? nullptr : nullptr; }
     }
     for (size_t i = 0; i < n; i++) wake(batch[i]);
     // the output arena belongs to the next GPU call only after every ticket has copied its record
@@ -120,7 +118,6 @@ int aigw_batcher_translate(aigw_batcher* b, const uint8_t* body, uint32_t len, u
   }
   b->cv.notify_one();
   { std::unique_lock<std::mutex> lk(t.m); t.cv.wait(lk, [&] { return t.woken; }); }
-  for (int c = 0; c < kFan; c++) if (t.child[c]) wake(t.child[c]);   // pass the wake on before doing our own copy
   int rc = t.batch_rc;
   aigw_doc_result r; memset(&r, 0, sizeof r);
   if (!rc) {
