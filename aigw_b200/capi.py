@@ -27,7 +27,7 @@ EXPORTS = ["aigw_version", "aigw_init", "aigw_destroy", "aigw_last_error", "aigw
            "aigw_device_alloc", "aigw_device_free", "aigw_memcpy_h2d", "aigw_memcpy_d2h", "aigw_memset_d", "aigw_sync",
            "aigw_chat_translate_device", "aigw_chat_last_profile", "aigw_chat_translate_host", "aigw_sse_usage_device", "aigw_sse_usage_host", "aigw_response_usage_device", "aigw_response_usage_host", "aigw_usage_costs_device",
            "aigw_bedrock_stream_device", "aigw_bedrock_stream_host", "aigw_body_mutate_device", "aigw_body_mutate_host",
-           "aigw_batcher_start", "aigw_batcher_translate", "aigw_batcher_get_stats", "aigw_batcher_stop"]
+           "aigw_sha256_device", "aigw_chat_body_sha256_device", "aigw_sha256_host", "aigw_batcher_start", "aigw_batcher_translate", "aigw_batcher_get_stats", "aigw_batcher_stop"]
 
 
 class BackendCfg(C.Structure):
@@ -105,6 +105,9 @@ def load_library():
     L.aigw_usage_costs_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.aigw_bedrock_stream_device.argtypes = [C.c_void_p, C.POINTER(BedrockStreamCfg), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    L.aigw_sha256_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    L.aigw_chat_body_sha256_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    L.aigw_sha256_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     L.aigw_batcher_start.argtypes = [C.c_void_p, C.POINTER(BackendCfg), C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
     L.aigw_batcher_translate.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
     L.aigw_batcher_get_stats.argtypes = [C.c_void_p, C.c_void_p]
@@ -243,6 +246,23 @@ class Context:
         self._check(self.L.aigw_sse_usage_host(self.h, bytes_arr.ctypes.data, chunk_off.ctypes.data, chunk_first.ctypes.data, n_streams, n_chunks,
                                                res.ctypes.data, C.byref(h2d), C.byref(d2h), C.byref(ms)), "sse_usage_host")
         return res, {"h2d_bytes": h2d.value, "d2h_bytes": d2h.value, "kernel_ms": ms.value}
+
+    # ---- SigV4 payload hash
+    def sha256_host(self, arena, offs, lens):
+        n = len(lens)
+        dig = np.zeros((n, 32), dtype=np.uint8)
+        self._check(self.L.aigw_sha256_host(self.h, arena.ctypes.data, offs.ctypes.data, lens.ctypes.data, n, dig.ctypes.data), "sha256_host")
+        return dig
+
+    def sha256_device(self, d_bytes, d_off, d_len, n, d_dig, timed=True):
+        ms = C.c_float(0)
+        self._check(self.L.aigw_sha256_device(self.h, d_bytes, d_off, d_len, n, d_dig, None, C.byref(ms) if timed else None), "sha256_device")
+        return ms.value
+
+    def chat_body_sha256_device(self, d_out, d_res, n, d_dig, timed=True):
+        ms = C.c_float(0)
+        self._check(self.L.aigw_chat_body_sha256_device(self.h, d_out, d_res, n, d_dig, None, C.byref(ms) if timed else None), "chat_body_sha256_device")
+        return ms.value
 
     # ---- request batcher (synchronous single-request call, thread safe)
     def batcher_start(self, cfg, max_batch=256, window_us=50):

@@ -11,6 +11,7 @@
 #include "sse_kernel.cuh"
 #include "bedrock_stream_kernel.cuh"
 #include "mutate_kernel.cuh"
+#include "sha256_kernel.cuh"
 
 using namespace aigw;
 
@@ -558,6 +559,43 @@ int aigw_body_mutate_host(aigw_ctx* ctx, const aigw_body_mutation* m, const uint
   const uint64_t used = ctx->h_used_arr[0] < out_cap ? ctx->h_used_arr[0] : out_cap;
   out->results = ctx->h_mres; out->out = ctx->h_out; out->out_used = used; out->h2d_bytes = nbytes + (uint64_t)n * 12; out->d2h_bytes = used + (uint64_t)n * sizeof(aigw_mut_result) + 8;
   out->gpu_launches = 1; out->kernel_ms = ms;
+  return 0;
+}
+
+// ------------------------------------------------------------------ SigV4 payload hash
+static int sha_common(aigw_ctx* ctx, const uint8_t* d_bytes, const uint64_t* d_off, const uint32_t* d_len, const aigw_doc_result* d_res, uint32_t n, uint8_t* d_dig, void* stream, float* kernel_ms) {
+  if (kernel_ms) *kernel_ms = 0;
+  if (n == 0) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->s_compute;
+  if (kernel_ms) CK(cudaEventRecord(ctx->ev0, st));
+  CK(launch_sha256(d_bytes, d_off, d_len, d_res, n, d_dig, st));
+  if (kernel_ms) { CK(cudaEventRecord(ctx->ev1, st)); CK(cudaEventSynchronize(ctx->ev1)); CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1)); }
+  return 0;
+}
+int aigw_sha256_device(aigw_ctx* ctx, const uint8_t* d_bytes, const uint64_t* d_off, const uint32_t* d_len, uint32_t n, uint8_t* d_digests, void* stream, float* kernel_ms) {
+  return sha_common(ctx, d_bytes, d_off, d_len, nullptr, n, d_digests, stream, kernel_ms);
+}
+int aigw_chat_body_sha256_device(aigw_ctx* ctx, const uint8_t* d_out, const aigw_doc_result* d_results, uint32_t n, uint8_t* d_digests, void* stream, float* kernel_ms) {
+  return sha_common(ctx, d_out, nullptr, nullptr, d_results, n, d_digests, stream, kernel_ms);
+}
+int aigw_sha256_host(aigw_ctx* ctx, const uint8_t* bytes, const uint64_t* off, const uint32_t* len, uint32_t n, uint8_t* digests) {
+  if (n == 0) return 0;
+  cudaSetDevice(ctx->device);
+  uint64_t lo = ~0ull, hi = 0;
+  for (uint32_t i = 0; i < n; i++) { if (off[i] < lo) lo = off[i]; if (off[i] + len[i] > hi) hi = off[i] + len[i]; }
+  const uint64_t nbytes = hi - lo;
+  ChunkSlot& S = ctx->slot[0];
+  ENSURE(S.d_in, S.in_cap, nbytes + 64, false);
+  if (S.doc_cap < n) { cudaFree(S.d_off); cudaFree(S.d_len); S.doc_cap = 0; const size_t dc = (size_t)n + n / 8 + 16; CK(cudaMalloc(&S.d_off, dc * 8)); CK(cudaMalloc(&S.d_len, dc * 4)); S.doc_cap = dc; }
+  ENSURE(ctx->d_sse_res, ctx->sse_res_cap, (size_t)n * 32, false);
+  cudaStream_t st = ctx->s_compute;
+  CK(cudaMemcpyAsync(S.d_in, bytes + lo, nbytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(S.d_off, off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(S.d_len, len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CK(launch_sha256(S.d_in - lo, S.d_off, S.d_len, nullptr, n, (uint8_t*)ctx->d_sse_res, st));
+  CK(cudaMemcpyAsync(digests, ctx->d_sse_res, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return 0;
 }
 

@@ -227,6 +227,16 @@ int  aigw_batcher_translate(aigw_batcher* b, const uint8_t* body, uint32_t len, 
 int  aigw_batcher_get_stats(aigw_batcher* b, aigw_batcher_stats* s);
 void aigw_batcher_stop(aigw_batcher* b);
 
+/* ---- SigV4 payload hash ----
+ * Replaces `sha256.Sum256(body)` of the AWS signer (internal/backendauth/aws.go:93-117) for the bodies the translate pass just
+ * produced: digests[i] (32 bytes, the raw digest; the shim hex-encodes it for x-amz-content-sha256) of message i.
+ * aigw_sha256_device: message i = d_bytes[d_off[i] .. d_off[i]+d_len[i]).
+ * aigw_chat_body_sha256_device: message i = the body of translate record i in d_out (zero digest when the record is not
+ * AIGW_OK / AIGW_BODY_BYTES).  aigw_sha256_host copies the messages in, hashes, copies the digests out. */
+int aigw_sha256_device(aigw_ctx* ctx, const uint8_t* d_bytes, const uint64_t* d_off, const uint32_t* d_len, uint32_t n, uint8_t* d_digests, void* stream, float* kernel_ms);
+int aigw_chat_body_sha256_device(aigw_ctx* ctx, const uint8_t* d_out, const aigw_doc_result* d_results, uint32_t n, uint8_t* d_digests, void* stream, float* kernel_ms);
+int aigw_sha256_host(aigw_ctx* ctx, const uint8_t* bytes, const uint64_t* off, const uint32_t* len, uint32_t n, uint8_t* digests /* host, 32*n */);
+
 const char* aigw_version(void);
 
 #ifdef __cplusplus

@@ -7,6 +7,7 @@
 
 #include "bedrock_response.hpp"
 #include "bedrock_stream.hpp"
+#include "sha256.hpp"
 #include "embeddings.hpp"
 #include "mutate.hpp"
 #include "stream.hpp"
@@ -207,6 +208,15 @@ double oracle_body_mutate_batch(const uint8_t* bodies, const uint64_t* offsets, 
   };
   if (threads <= 1) work(); else { std::vector<std::thread> th; for (int t = 0; t < threads; t++) th.emplace_back(work); for (auto& t : th) t.join(); }
   if (total_out) *total_out = tot.load();
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+// ---- SigV4 payload hash
+void oracle_sha256(const uint8_t* p, uint64_t n, uint8_t* out32) { sha256(p, (size_t)n, out32); }
+double oracle_sha256_batch(const uint8_t* bytes, const uint64_t* offsets, const uint32_t* lens, uint32_t n, int threads, uint8_t* digests) {
+  std::atomic<uint32_t> next{0};
+  auto t0 = std::chrono::steady_clock::now();
+  auto work = [&] { for (;;) { uint32_t i = next.fetch_add(64); if (i >= n) break; uint32_t e = std::min(n, i + 64); for (; i < e; i++) sha256(bytes + offsets[i], lens[i], digests + 32ull * i); } };
+  if (threads <= 1) work(); else { std::vector<std::thread> th; for (int t = 0; t < threads; t++) th.emplace_back(work); for (auto& t : th) t.join(); }
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 void oracle_free(void* p) { free(p); }

@@ -171,3 +171,10 @@ def embeddings_translate(schema, body: bytes, model_override="", prefix="v1", fo
     t.mutated = None
     lib().oracle_result_free(C.byref(r))
     return t
+
+
+def sha256(data: bytes) -> bytes:
+    out = C.create_string_buffer(32)
+    L = lib(); L.oracle_sha256.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p]
+    L.oracle_sha256(data, len(data), out)
+    return out.raw

@@ -5,6 +5,7 @@ reference compares expRequestBody with bytes.Equal, so equality here is byte-exa
 import json
 import os
 
+import numpy as np
 import pytest
 
 import _oracle as O
@@ -249,3 +250,22 @@ def test_embeddings_union_rules():
     assert t.body == b'{"input":"x","model":"big"}' and t.path == "/v1/embeddings"
     t = E(b'{"input":"x","model":"m"}', "azure-openai", model_override="dep", prefix="2024-10-21")
     assert t.body == b'{"input":"x","model":"dep"}' and t.path == "/openai/deployments/dep/embeddings?api-version=2024-10-21"
+
+
+# ---------------------------------------------------------------- SigV4 payload hash (internal/backendauth/aws.go:93-117)
+def test_sha256_known_answers():
+    """FIPS 180-4 / NIST CAVP known answers, then hashlib on lengths around every padding boundary."""
+    import hashlib
+    kat = {
+        b"abc": "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad",
+        b"": "e3b0c44298fc1c149afbf4c8996fb92427ae41e4649b934ca495991b7852b855",
+        b"abcdbcdecdefdefgefghfghighijhijkijkljklmklmnlmnomnopnopq": "248d6a61d20638b8e5c026930c3e6039a33ce45964ff2167f6ecedd419db06c1",
+        b"abcdefghbcdefghicdefghijdefghijkefghijklfghijklmghijklmnhijklmnoijklmnopjklmnopqklmnopqrlmnopqrsmnopqrstnopqrstu": "cf5b16a778af8380036ce59e7b0492370b249b11e8f07a51afac45037afee9d1",
+        b"a" * 1000000: "cdc76e5c9914fb9281a1c7e284d73e67f1809a48a497200e046d39ccc7112cd0",
+    }
+    for m, h in kat.items():
+        assert O.sha256(m).hex() == h
+    rng = np.random.default_rng(1)
+    for n in list(range(0, 200)) + [4095, 4096, 4097, 65535, 65536]:
+        m = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert O.sha256(m) == hashlib.sha256(m).digest()
