@@ -857,11 +857,11 @@ struct Walker {
   }
   // one gcp.Instance: {"content":C[,"task_type":T][,"title":X]}
   __device__ void emit_instance(int content /* string token or -1 = "" */, int task, int title, bool& first) {
-    if (!first) pl.lit(L_COMMA); first = false;
-    pl.lit(L_EM_CONTENT); if (content >= 0) emit_str(content); else pl.lit(L_EMPTY_STR);
+    // the closing brace of an instance is emitted with the opening of the next one (one literal op instead of three)
+    pl.lit(first ? L_EM_CONTENT : L_EM_NEXT); first = false;
+    if (content >= 0) emit_str(content); else pl.lit(L_EMPTY_STR);
     if (task >= 0 && d.str_len(task) > 0) { pl.lit(L_EM_TASK); emit_str(task); }
     if (title >= 0) { pl.lit(L_EM_TITLE); emit_str(title); }
-    pl.lit(L_RBRACE);
   }
   __device__ void emit_item_instances(const EmbItem& it, int global_task, bool& first) {
     // Title is kept only with the ITEM's task_type == RETRIEVAL_DOCUMENT; a request-level task_type then overrides the type
@@ -963,7 +963,7 @@ struct Walker {
         else if (kind == 2) { for (int q = input + 1; d.ty(q) != ']'; q = d.after(q)) emit_instance(is_null(q) ? -1 : q, gtask, -1, first); }
         else if (kind == 3) { EmbItem it; bool e2; scan_emb_item(input, it, e2); emit_item_instances(it, gtask, first); }
         else { for (int q = input + 1; d.ty(q) != ']'; q = d.after(q)) { EmbItem it; bool e2; scan_emb_item(q, it, e2); emit_item_instances(it, gtask, first); } }
-        pl.lit(L_RBRACK);
+        pl.lit(L_EM_LAST);
       }
     }
     pl.lit(L_EM_PARAMS);
@@ -1751,7 +1751,7 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
     if (lane == 0) li = atomicAdd(counter, 1u);
     li = __shfl_sync(FULL, li, 0);
     if (li >= ndocs) break;
-    const uint32_t doc = doc0 + li;
+    const uint32_t doc = P.doc_map ? P.doc_map[doc0 + li] : doc0 + li;
     const uint32_t len = P.lens[doc];
     const uint8_t* g = P.bodies + P.offsets[doc];
     if (len > (uint32_t)MAXD || len == 0) {
@@ -1956,7 +1956,7 @@ __global__ void __launch_bounds__(128, AIGW_WALK_BLOCKS) chat_walk_kernel(const 
   if (tid >= ndocs) return;
   const WorkPtrs wp = carve<MAXD>(work, ndocs);
   const uint32_t li = wp.perm[tid];  // shape-sorted order
-  const uint32_t doc = doc0 + li;
+  const uint32_t doc = P.doc_map ? P.doc_map[doc0 + li] : doc0 + li;
   const uint32_t nt_word = wp.ntok[li];
   PlanOut po; po.nops = 0; po.olen = 0; po.path_len = 0; po.model_off = 0; po.model_len = 0; po.flags = 0; po.reason = 0;
   if (nt_word & 0x80000000u) { po.reason = (uint8_t)(nt_word & 0xff); wp.plan[li] = po; return; }
@@ -2034,7 +2034,7 @@ __global__ void __launch_bounds__(WARPS * 32) chat_emit_kernel(const __grid_cons
     if (lane == 0) li = atomicAdd(counter, 1u);
     li = __shfl_sync(FULL, li, 0);
     if (li >= ndocs) break;
-    const uint32_t doc = doc0 + li;
+    const uint32_t doc = P.doc_map ? P.doc_map[doc0 + li] : doc0 + li;
     const uint32_t len = P.lens[doc];
     const PlanOut po = wp.plan[li];
     aigw_doc_result res = blank_result(len);

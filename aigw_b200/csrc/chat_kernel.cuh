@@ -149,7 +149,9 @@ namespace aigw {
   X(L_EM_GOOGLE_PATH, "publishers/google/models/")                                              \
   X(L_EM_PREDICT, ":predict")                                                                   \
   X(L_EM_AZ_PATH1, "/openai/deployments/")                                                      \
-  X(L_EM_AZ_PATH2, "/embeddings?api-version=")
+  X(L_EM_AZ_PATH2, "/embeddings?api-version=")                                                 \
+  X(L_EM_NEXT, "},{\"content\":")                                                               \
+  X(L_EM_LAST, "}]")
 
 enum LitId : int {
 #define X(name, text) name,
@@ -186,6 +188,7 @@ struct ChatParams {
   unsigned long long* out_used;  // bump allocator
   unsigned int* next_doc;        // work counter
   uint64_t out_bias;             // added to every out_off (host pipeline: chunk base in the host arena)
+  const uint32_t* doc_map;       // optional: unit i of the launch is document doc_map[first + i] (size-class bucketing)
   int schema;
   int cost_configured;
   int force_mutation;

@@ -3,6 +3,7 @@
 // CUDA streams; everything computed is computed by the kernels in this directory — there is no
 // CPU fallback anywhere in this library.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -22,6 +23,7 @@ static constexpr int kSlots = 3;
 struct ChunkSlot {
   uint8_t* d_in = nullptr; size_t in_cap = 0;
   uint64_t* d_off = nullptr; uint32_t* d_len = nullptr; size_t doc_cap = 0;
+  uint32_t* d_map = nullptr; size_t map_cap = 0;   // size-class bucketing: documents of the chunk grouped by class
   uint8_t* d_out = nullptr; size_t out_cap = 0;
   aigw_doc_result* d_res = nullptr;
   unsigned long long* d_used = nullptr;   // device bump counter
@@ -55,6 +57,7 @@ struct aigw_ctx {
   uint64_t* d_bs_off[2] = {nullptr, nullptr}; size_t bs_off_cap[2] = {0, 0};
   aigw_stream_result* h_sres = nullptr; size_t h_sres_cap = 0;
   aigw_mut_result* h_mres = nullptr; size_t h_mres_cap = 0;
+  std::vector<uint32_t> h_map;   // size-class bucketing scratch (host)
 };
 
 // response bodies expand (escaped tool arguments, configuration text): plan them in a roomier size class
@@ -156,24 +159,27 @@ int aigw_memcpy_d2h(aigw_ctx* ctx, void* dst, const void* src, size_t bytes) { C
 int aigw_memset_d(aigw_ctx* ctx, void* dst, int v, size_t bytes) { CK(cudaMemset(dst, v, bytes)); return 0; }
 int aigw_sync(aigw_ctx* ctx) { CK(cudaDeviceSynchronize()); return 0; }
 
-int aigw_chat_translate_device(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const uint8_t* d_bodies, const uint64_t* d_offsets,
-                               const uint32_t* d_lens, uint32_t n, uint32_t max_len, uint8_t* d_out, uint64_t out_capacity,
-                               aigw_doc_result* d_results, uint64_t* d_out_used, void* stream, float* kernel_ms) {
+static int chat_translate_device_impl(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const uint8_t* d_bodies, const uint64_t* d_offsets,
+                                      const uint32_t* d_lens, const uint32_t* d_doc_map, uint32_t first, uint32_t n, uint32_t max_len, uint8_t* d_out, uint64_t out_capacity,
+                                      aigw_doc_result* d_results, uint64_t* d_out_used, void* stream, float* kernel_ms) {
   if (n == 0) { if (kernel_ms) *kernel_ms = 0; return 0; }
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->s_compute;
   ChatParams P;
   fill_params(P, cfg);
   P.bodies = d_bodies; P.offsets = d_offsets; P.lens = d_lens; P.n = n; P.out = d_out; P.out_capacity = out_capacity;
   P.results = d_results; P.out_used = (unsigned long long*)d_out_used;
-  P.next_doc = nullptr; P.out_bias = 0;
+  P.next_doc = nullptr; P.out_bias = 0; P.doc_map = d_doc_map;
   uint32_t ml = max_len ? max_len : 65536u;
   if (cfg && (cfg->schema & 48) == AIGW_SCHEMA_RESP_AWS_BEDROCK) ml = resp_class_len(ml);
   {  // workspace for one sub-batch (≤ 128 Ki documents); the launcher loops over sub-batches
     const size_t sub = n < 131072u ? n : 131072u;
-    ENSURE(ctx->d_work, ctx->work_cap, chat_work_bytes(ml, sub), false);
+    size_t need = chat_work_bytes(ml, sub);
+    const size_t cap = (size_t)3 << 30, floor1 = chat_work_bytes(ml, 1024);
+    if (need > cap) need = cap > floor1 ? cap : floor1;
+    ENSURE(ctx->d_work, ctx->work_cap, need, false);
   }
   if (kernel_ms) CK(cudaEventRecord(ctx->ev0, st));
-  CK(launch_chat_translate(P, ml, ctx->sm_count, st, ctx->d_work, ctx->work_cap, ctx->d_counters, &ctx->last_launches, kernel_ms ? ctx->stage_ev : nullptr, 64));
+  CK(launch_chat_translate(P, ml, ctx->sm_count, st, ctx->d_work, ctx->work_cap, ctx->d_counters, &ctx->last_launches, kernel_ms ? ctx->stage_ev : nullptr, 64, first));
   if (kernel_ms) {
     CK(cudaEventRecord(ctx->ev1, st)); CK(cudaEventSynchronize(ctx->ev1)); CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
     ctx->stage_ms[0] = ctx->stage_ms[1] = ctx->stage_ms[2] = 0;
@@ -181,6 +187,17 @@ int aigw_chat_translate_device(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const
     for (int sb = 0; sb < nsb && 4 * sb + 3 < 64; sb++) for (int k = 0; k < 3; k++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->stage_ev[4 * sb + k], ctx->stage_ev[4 * sb + k + 1]); ctx->stage_ms[k] += ms; }
   }
   return 0;
+}
+
+int aigw_chat_translate_device(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const uint8_t* d_bodies, const uint64_t* d_offsets,
+                               const uint32_t* d_lens, uint32_t n, uint32_t max_len, uint8_t* d_out, uint64_t out_capacity,
+                               aigw_doc_result* d_results, uint64_t* d_out_used, void* stream, float* kernel_ms) {
+  return chat_translate_device_impl(ctx, cfg, d_bodies, d_offsets, d_lens, nullptr, 0, n, max_len, d_out, out_capacity, d_results, d_out_used, stream, kernel_ms);
+}
+int aigw_chat_translate_device_mapped(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const uint8_t* d_bodies, const uint64_t* d_offsets, const uint32_t* d_lens,
+                                      const uint32_t* d_doc_map, uint32_t first, uint32_t count, uint32_t max_len, uint8_t* d_out, uint64_t out_capacity,
+                                      aigw_doc_result* d_results, uint64_t* d_out_used, void* stream, float* kernel_ms) {
+  return chat_translate_device_impl(ctx, cfg, d_bodies, d_offsets, d_lens, d_doc_map, first, count, max_len, d_out, out_capacity, d_results, d_out_used, stream, kernel_ms);
 }
 
 /* per-stage CUDA-event times (index, walk, emit) and launch count of the last timed aigw_chat_translate_device call */
@@ -233,8 +250,18 @@ int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const u
       S.doc_cap = dc;
     }
   }
-  if (cfg && (cfg->schema & 48) == AIGW_SCHEMA_RESP_AWS_BEDROCK) max_len = resp_class_len(max_len);
-  ENSURE(ctx->d_work, ctx->work_cap, chat_work_bytes(max_len, max_docs < 131072u ? max_docs : 131072u), false);
+  const bool resp_dir = cfg && (cfg->schema & 48) == AIGW_SCHEMA_RESP_AWS_BEDROCK;
+  if (resp_dir) max_len = resp_class_len(max_len);
+  // size classes (the kernels' shared-memory footprints, chat_kernel.cu launch_chat_translate)
+  static const uint32_t kClsMax[6] = {2048, 5120, 9216, 17408, 33792, 65536};
+  auto cls_of = [&](uint32_t len) { const uint32_t l = resp_dir ? resp_class_len(len) : len; int k = 0; while (k < 5 && l > kClsMax[k]) k++; return k; };
+  {
+    size_t need = chat_work_bytes(max_len, max_docs < 131072u ? max_docs : 131072u);
+    const size_t cap = (size_t)3 << 30;   // the launcher walks a class in sub-batches that fit the workspace
+    const size_t floor1 = chat_work_bytes(max_len, 1024);
+    if (need > cap) need = cap > floor1 ? cap : floor1;
+    ENSURE(ctx->d_work, ctx->work_cap, need, false);
+  }
   ENSURE(ctx->h_out, ctx->h_out_cap, total_out_cap, true);
   ENSURE(ctx->h_res, ctx->h_res_cap, (size_t)n * sizeof(aigw_doc_result), true);
   if ((size_t)nch > ctx->used_cap) {
@@ -258,6 +285,23 @@ int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const u
     CK(cudaMemcpyAsync(S.d_in, bodies + offsets[b], in_bytes[c] - 16, cudaMemcpyHostToDevice, ctx->s_h2d));
     CK(cudaMemcpyAsync(S.d_off, offsets + b, (size_t)nd * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
     CK(cudaMemcpyAsync(S.d_len, lens + b, (size_t)nd * 4, cudaMemcpyHostToDevice, ctx->s_h2d));
+    // size-class bucketing: a chunk whose documents span several classes is launched class by class over a document map,
+    // so that a few large bodies do not force the small ones into the large class's shared-memory footprint
+    uint32_t cls_cnt[6] = {0, 0, 0, 0, 0, 0};
+    for (uint32_t i = b; i < e; i++) cls_cnt[cls_of(lens[i])]++;
+    int n_cls = 0, top_cls = 0; for (int k = 0; k < 6; k++) if (cls_cnt[k]) { n_cls++; top_cls = k; }
+    static const bool no_bucketing = getenv("AIGW_NO_BUCKETING") != nullptr;   // A/B switch for tools/bench_zipf.py
+    if (no_bucketing) n_cls = 1;
+    uint32_t cls_start[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (n_cls > 1) {
+      for (int k = 0; k < 6; k++) cls_start[k + 1] = cls_start[k] + cls_cnt[k];
+      ctx->h_map.resize(nd);
+      uint32_t cur[6]; for (int k = 0; k < 6; k++) cur[k] = cls_start[k];
+      for (uint32_t i = b; i < e; i++) ctx->h_map[cur[cls_of(lens[i])]++] = i;
+      ENSURE(S.d_map, S.map_cap, (size_t)nd * 4, false);
+      CK(cudaMemcpyAsync(S.d_map, ctx->h_map.data(), (size_t)nd * 4, cudaMemcpyHostToDevice, ctx->s_h2d));   // pageable source: staged before the call returns
+      h2d += (uint64_t)nd * 4;
+    }
     CK(cudaEventRecord(S.ev_h2d, ctx->s_h2d));
     h2d += in_bytes[c] - 16 + (uint64_t)nd * 12;
     CK(cudaStreamWaitEvent(ctx->s_compute, S.ev_h2d, 0));
@@ -265,12 +309,22 @@ int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const u
     P.bodies = S.d_in - offsets[b];  // absolute offsets index straight into the chunk
     P.offsets = S.d_off - b; P.lens = S.d_len - b; P.n = nd;
     P.out = dev_out + out_base[c]; P.out_capacity = out_cap[c];
-    P.results = dev_res; P.out_used = ctx->d_used_arr + c; P.next_doc = nullptr; P.out_bias = out_base[c];
-    // documents keep their global index: kernels address offsets/lens/results with doc0 + i
-    int nl = 0;
-    CK(launch_chat_translate_range(P, b, nd, max_len, ctx->sm_count, ctx->s_compute, ctx->d_work, ctx->work_cap, ctx->d_counters, &nl));
+    P.results = dev_res; P.out_used = ctx->d_used_arr + c; P.next_doc = nullptr; P.out_bias = out_base[c]; P.doc_map = nullptr;
+    // documents keep their global index: kernels address offsets/lens/results with doc0 + i (or doc_map[i])
+    if (n_cls <= 1) {
+      int nl = 0;
+      CK(launch_chat_translate_range(P, b, nd, kClsMax[top_cls], ctx->sm_count, ctx->s_compute, ctx->d_work, ctx->work_cap, ctx->d_counters, &nl));
+      out->gpu_launches += nl;
+    } else {
+      P.doc_map = S.d_map;
+      for (int k = 0; k < 6; k++) {
+        if (!cls_cnt[k]) continue;
+        int nl = 0;
+        CK(launch_chat_translate_range(P, cls_start[k], cls_cnt[k], kClsMax[k], ctx->sm_count, ctx->s_compute, ctx->d_work, ctx->work_cap, ctx->d_counters, &nl));
+        out->gpu_launches += nl;
+      }
+    }
     CK(cudaEventRecord(S.ev_k1, ctx->s_compute));
-    out->gpu_launches += nl;
   }
   CK(cudaEventRecord(ctx->ev1, ctx->s_compute));
   CK(cudaMemcpyAsync(ctx->h_used_arr, ctx->d_used_arr, (size_t)nch * 8, cudaMemcpyDeviceToHost, ctx->s_compute));

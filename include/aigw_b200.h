@@ -125,6 +125,13 @@ int aigw_chat_translate_device(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const
 
 /* CUDA-event time of the three stages (index, walk, emit) and the launch count of the last aigw_chat_translate_device
  * call that passed kernel_ms != NULL. */
+/* Same, over a document map: unit i of the call is document d_doc_map[first + i] (offsets / lens / results keep the document's
+ * own index).  Callers with mixed body sizes group documents by size class (≤ 2048, 5120, 9216, 17408, 33792, 65536 bytes) and
+ * make one call per class with that class's max_len, so small bodies are not run with the large class's shared-memory
+ * footprint; aigw_chat_translate_host does this itself per 256 MiB chunk. */
+int aigw_chat_translate_device_mapped(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const uint8_t* d_bodies, const uint64_t* d_offsets, const uint32_t* d_lens,
+                                      const uint32_t* d_doc_map, uint32_t first, uint32_t count, uint32_t max_len, uint8_t* d_out, uint64_t out_capacity,
+                                      aigw_doc_result* d_results, uint64_t* d_out_used, void* stream, float* kernel_ms);
 int aigw_chat_last_profile(aigw_ctx* ctx, float stage_ms[3], int* launches);
 
 /* ---- same, HOST buffers (the call the cgo shim makes) ----
