@@ -7,6 +7,7 @@
 
 #include "bedrock_response.hpp"
 #include "bedrock_stream.hpp"
+#include "cel.hpp"
 #include "sha256.hpp"
 #include "embeddings.hpp"
 #include "mutate.hpp"
@@ -218,6 +219,14 @@ double oracle_sha256_batch(const uint8_t* bytes, const uint64_t* offsets, const 
   auto work = [&] { for (;;) { uint32_t i = next.fetch_add(64); if (i >= n) break; uint32_t e = std::min(n, i + 64); for (; i < e; i++) sha256(bytes + offsets[i], lens[i], digests + 32ull * i); } };
   if (threads <= 1) work(); else { std::vector<std::thread> th; for (int t = 0; t < threads; t++) th.emplace_back(work); for (auto& t : th) t.join(); }
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+// ---- CEL cost expressions.  compile: 0 ok / 1 unsupported or compile error / 2 rejected by the sanity evaluation
+void* oracle_cel_compile(const char* expr, int* rc) { auto* p = new cel::Program(); std::string err; *rc = cel::compile(expr, *p, err); if (*rc) { delete p; return nullptr; } return p; }
+void oracle_cel_free(void* p) { delete (cel::Program*)p; }
+// evaluate: returns 0 and the cost, or the error class (1 integer overflow, 2 unsigned overflow, 3 divide by zero, 4 modulus by zero, 5 negative result)
+int oracle_cel_eval(void* p, const char* model, const char* backend, const char* route, const uint32_t tok[6], uint64_t* out) {
+  cel::Vars v; v.model = model; v.backend = backend; v.route = route; for (int k = 0; k < 6; k++) v.tok[k] = tok[k];
+  *out = 0; return cel::evaluate(*(cel::Program*)p, v, *out);
 }
 void oracle_free(void* p) { free(p); }
 uint32_t oracle_crc32(const uint8_t* p, uint64_t n) { return crc32_ieee(p, n); }

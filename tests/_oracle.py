@@ -178,3 +178,22 @@ def sha256(data: bytes) -> bytes:
     L = lib(); L.oracle_sha256.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p]
     L.oracle_sha256(data, len(data), out)
     return out.raw
+
+
+class Cel:
+    """llmcostcel.NewProgram / EvaluateProgram.  rc: 0 ok, 1 unsupported / compile error, 2 rejected by the sanity evaluation."""
+    def __init__(self, expr: str):
+        L = lib(); L.oracle_cel_compile.restype = C.c_void_p; L.oracle_cel_compile.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
+        rc = C.c_int(0)
+        self.h = L.oracle_cel_compile(expr.encode(), C.byref(rc)); self.rc = rc.value
+
+    def eval(self, model, backend, route, inp, cached, cache_creation, out, total, reasoning):
+        """→ (error class, cost); tokens in the order of EvaluateProgram's arguments"""
+        L = lib(); L.oracle_cel_eval.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32 * 6, C.POINTER(C.c_uint64)]
+        tok = (C.c_uint32 * 6)(inp, cached, cache_creation, out, total, reasoning); v = C.c_uint64(0)
+        e = L.oracle_cel_eval(self.h, model.encode(), backend.encode(), route.encode(), tok, C.byref(v))
+        return e, v.value
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_cel_free.argtypes = [C.c_void_p]; lib().oracle_cel_free(self.h)

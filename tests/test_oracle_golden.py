@@ -269,3 +269,39 @@ def test_sha256_known_answers():
     for n in list(range(0, 200)) + [4095, 4096, 4097, 65535, 65536]:
         m = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
         assert O.sha256(m) == hashlib.sha256(m).digest()
+
+
+# ---------------------------------------------------------------- CEL cost expressions (internal/llmcostcel/cel_test.go:15-90)
+def test_cel_reference_vectors():
+    assert O.Cel("1 +").rc == 1
+    assert O.Cel("1 + 1").rc == 0 and O.Cel("uint(1) + uint(1)").rc == 0
+    p = O.Cel("model == 'cool_model' ?  (input_tokens - cached_input_tokens - cache_creation_input_tokens) * output_tokens  : total_tokens")
+    assert p.rc == 0
+    assert p.eval("cool_model", "cool_backend", "cool_route", 200, 100, 1, 2, 3, 0) == (0, 198)
+    assert p.eval("not_cool_model", "cool_backend", "cool_route", 200, 100, 1, 2, 3, 0) == (0, 3)
+    assert O.Cel("uint(1)-uint(1200)").rc == 2                                   # "unsigned integer overflow" in NewProgram's sanity evaluation
+    p = O.Cel("int(input_tokens) - int(output_tokens)"); assert p.rc == 0
+    assert p.eval("cool_model", "cool_backend", "cool_route", 100, 0, 0, 2000, 3, 0)[0] == 5   # "result is negative (-1900)"
+    p = O.Cel("input_tokens - output_tokens"); assert p.rc == 0
+    assert p.eval("cool_model", "cool_backend", "cool_route", 100, 0, 0, 2000, 3, 0)[0] == 2   # "unsigned integer overflow"
+    assert O.Cel("output_tokens + reasoning_tokens").eval("m", "b", "r", 0, 0, 0, 100, 0, 50) == (0, 150)
+    assert O.Cel("model == 'cool_model' ?  input_tokens * output_tokens : total_tokens").eval("cool_model", "b", "r", 100, 0, 0, 2, 3, 0) == (0, 200)
+    # examples/token_ratelimit/token_ratelimit.yaml:49-65
+    p = O.Cel("input_tokens == uint(3) ? 100000000 : 0"); assert p.rc == 0
+    assert p.eval("m", "b", "r", 3, 0, 0, 0, 0, 0) == (0, 100000000) and p.eval("m", "b", "r", 4, 0, 0, 0, 0, 0) == (0, 0)
+
+
+def test_cel_subset_rules():
+    assert O.Cel("input_tokens * 2").rc == 1            # uint * int: no matching overload
+    assert O.Cel("input_tokens * 2u").rc == 0
+    assert O.Cel("input_tokens < 5 ? 1 : 0").rc == 1 and O.Cel("input_tokens < 5u ? 1 : 0").rc == 0 and O.Cel("input_tokens < 5u").rc == 2
+    assert O.Cel("model == backend ? 1 : 0").rc == 0 and O.Cel("model").rc == 2 and O.Cel("true").rc == 2
+    assert O.Cel("1u / input_tokens").rc == 2            # divide by zero under the sanity evaluation
+    assert O.Cel("model.startsWith('gpt')").rc == 1 and O.Cel("1.5 * 2.0").rc == 1 and O.Cel("size(model)").rc == 1
+    assert O.Cel("false && 1u / input_tokens > 0u ? 1 : 2").eval("m", "b", "r", 0, 0, 0, 0, 0, 0) == (0, 2)    # error absorbed by false &&
+    assert O.Cel("1u / (input_tokens + 1u) > 0u && false ? 1 : 2").eval("m", "b", "r", 0, 0, 0, 0, 0, 0) == (0, 2)
+    assert O.Cel("(backend == 'aws' || route_name != 'r1') && !(model == \"x\") ? 10u : 20u").eval("m", "aws", "r1", 0, 0, 0, 0, 0, 0) == (0, 10)
+    assert O.Cel("9223372036854775807 + int(input_tokens)").eval("m", "b", "r", 1, 0, 0, 0, 0, 0)[0] == 1
+    assert O.Cel("18446744073709551615u * (input_tokens + 1u)").eval("m", "b", "r", 1, 0, 0, 0, 0, 0)[0] == 2
+    assert O.Cel("100u % input_tokens == 0u ? 1 : 0").rc == 2
+    assert O.Cel("0x10 + -3").eval("m", "b", "r", 0, 0, 0, 0, 0, 0) == (0, 13)
