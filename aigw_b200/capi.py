@@ -27,7 +27,7 @@ EXPORTS = ["aigw_version", "aigw_init", "aigw_destroy", "aigw_last_error", "aigw
            "aigw_device_alloc", "aigw_device_free", "aigw_memcpy_h2d", "aigw_memcpy_d2h", "aigw_memset_d", "aigw_sync",
            "aigw_chat_translate_device", "aigw_chat_translate_device_mapped", "aigw_chat_last_profile", "aigw_chat_translate_host", "aigw_sse_usage_device", "aigw_sse_usage_host", "aigw_response_usage_device", "aigw_response_usage_host", "aigw_usage_costs_device",
            "aigw_bedrock_stream_device", "aigw_bedrock_stream_host", "aigw_body_mutate_device", "aigw_body_mutate_host",
-           "aigw_sha256_device", "aigw_chat_body_sha256_device", "aigw_sha256_host", "aigw_batcher_start", "aigw_batcher_translate", "aigw_batcher_get_stats", "aigw_batcher_stop"]
+           "aigw_cost_compile", "aigw_cost_program_free", "aigw_usage_costs_cel_device", "aigw_usage_costs_cel_host", "aigw_sha256_device", "aigw_chat_body_sha256_device", "aigw_sha256_host", "aigw_batcher_start", "aigw_batcher_translate", "aigw_batcher_get_stats", "aigw_batcher_stop"]
 
 
 class BackendCfg(C.Structure):
@@ -107,6 +107,13 @@ def load_library():
     L.aigw_usage_costs_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.aigw_bedrock_stream_device.argtypes = [C.c_void_p, C.POINTER(BedrockStreamCfg), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    L.aigw_cost_compile.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.aigw_cost_program_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.aigw_cost_program_free.restype = None
+    L.aigw_usage_costs_cel_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p]
+    L.aigw_usage_costs_cel_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p,
+                                            C.c_void_p, C.c_void_p]
     L.aigw_sha256_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
     L.aigw_chat_body_sha256_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
     L.aigw_sha256_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
@@ -254,6 +261,31 @@ class Context:
         self._check(self.L.aigw_sse_usage_host(self.h, bytes_arr.ctypes.data, chunk_off.ctypes.data, chunk_first.ctypes.data, n_streams, n_chunks,
                                                res.ctypes.data, C.byref(h2d), C.byref(d2h), C.byref(ms)), "sse_usage_host")
         return res, {"h2d_bytes": h2d.value, "d2h_bytes": d2h.value, "kernel_ms": ms.value}
+
+    # ---- CEL cost expressions
+    def cost_compile(self, expr: str):
+        """→ (rc, handle): rc 0 ok, -2 outside the subset / type error, -3 the reference's NewProgram refuses it"""
+        h = C.c_void_p()
+        rc = self.L.aigw_cost_compile(self.h, expr.encode(), C.byref(h))
+        return rc, (h if rc == 0 else None)
+
+    def cost_free(self, prog):
+        self.L.aigw_cost_program_free(self.h, prog)
+
+    def usage_costs_cel_host(self, usages, progs, models=None, model="", backend="", route=""):
+        """usages: SseResult array; progs: handles; models: optional list of bytes (per record) → (costs[n, p] u64, errs[n, p] u8)"""
+        n, k = len(usages), len(progs)
+        arr = (C.c_void_p * k)(*[p.value for p in progs])
+        costs = np.zeros((n, k), dtype=np.uint64); errs = np.zeros((n, k), dtype=np.uint8)
+        if models is not None:
+            mb = np.frombuffer(b"".join(models) + b"\0", dtype=np.uint8).copy()
+            ml = np.array([len(m) for m in models], dtype=np.uint32); mo = np.concatenate([[0], np.cumsum(ml)[:-1]]).astype(np.uint32)
+            self._check(self.L.aigw_usage_costs_cel_host(self.h, usages.ctypes.data, n, arr, k, mb.ctypes.data, len(mb), mo.ctypes.data, ml.ctypes.data, model.encode(), backend.encode(), route.encode(),
+                                                          costs.ctypes.data, errs.ctypes.data), "usage_costs_cel_host")
+        else:
+            self._check(self.L.aigw_usage_costs_cel_host(self.h, usages.ctypes.data, n, arr, k, None, 0, None, None, model.encode(), backend.encode(), route.encode(), costs.ctypes.data, errs.ctypes.data),
+                        "usage_costs_cel_host")
+        return costs, errs
 
     # ---- SigV4 payload hash
     def sha256_host(self, arena, offs, lens):

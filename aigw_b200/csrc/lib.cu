@@ -13,8 +13,11 @@
 #include "bedrock_stream_kernel.cuh"
 #include "mutate_kernel.cuh"
 #include "sha256_kernel.cuh"
+#include "cel_kernel.cuh"
 
 using namespace aigw;
+
+struct aigw_cost_program { aigw::CelProgramHost h; };
 
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(_e); return (int)_e; } } while (0)
 
@@ -649,6 +652,80 @@ int aigw_sha256_host(aigw_ctx* ctx, const uint8_t* bytes, const uint64_t* off, c
   CK(cudaMemcpyAsync(S.d_len, len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
   CK(launch_sha256(S.d_in - lo, S.d_off, S.d_len, nullptr, n, (uint8_t*)ctx->d_sse_res, st));
   CK(cudaMemcpyAsync(digests, ctx->d_sse_res, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ------------------------------------------------------------------ CEL cost expressions
+int aigw_cost_compile(aigw_ctx* ctx, const char* expr, aigw_cost_program** out) {
+  *out = nullptr;
+  cudaSetDevice(ctx->device);
+  aigw_cost_program* p = new aigw_cost_program();
+  std::string err;
+  const int rc = cel_compile(expr ? expr : "", p->h, err);
+  if (rc) { ctx->err = std::string(rc == 1 ? "CEL expression outside the compiled subset: " : "CEL expression rejected: ") + err; delete p; return rc == 1 ? -2 : -3; }
+  std::vector<CelInstr> padded(p->h.code); padded.resize(kCelMaxInstr, CelInstr{});
+  if (cudaMalloc(&p->h.d_code, sizeof(CelInstr) * kCelMaxInstr) != cudaSuccess || cudaMalloc(&p->h.d_strings, p->h.strings.size() + 16) != cudaSuccess) { ctx->err = "cudaMalloc"; delete p; return (int)cudaErrorMemoryAllocation; }
+  CK(cudaMemcpy(p->h.d_code, padded.data(), sizeof(CelInstr) * kCelMaxInstr, cudaMemcpyHostToDevice));
+  if (!p->h.strings.empty()) CK(cudaMemcpy(p->h.d_strings, p->h.strings.data(), p->h.strings.size(), cudaMemcpyHostToDevice));
+  *out = p;
+  return 0;
+}
+void aigw_cost_program_free(aigw_ctx* ctx, aigw_cost_program* p) { if (!p) return; cudaSetDevice(ctx->device); cudaFree(p->h.d_code); cudaFree(p->h.d_strings); delete p; }
+
+static int cel_fill(aigw_ctx* ctx, CelLaunch& L, aigw_cost_program* const* progs, uint32_t n_progs, const char* model, const char* backend, const char* route) {
+  if (n_progs > (uint32_t)kCelMaxProgs) { ctx->err = "more than 8 CEL programs per call"; return -2; }
+  memset(&L.cs, 0, sizeof L.cs);
+  auto put = [&](char* dst, uint32_t& len, const char* src) -> bool { const size_t l = src ? strlen(src) : 0; if (l >= (size_t)kCelStrCap) return false; if (l) memcpy(dst, src, l); len = (uint32_t)l; return true; };
+  if (!put(L.cs.model, L.cs.model_len, model) || !put(L.cs.backend, L.cs.backend_len, backend) || !put(L.cs.route, L.cs.route_len, route)) { ctx->err = "model / backend / route_name longer than 255 bytes"; return -2; }
+  L.n_progs = n_progs;
+  for (uint32_t p = 0; p < n_progs; p++) {
+    const CelProgramHost& h = progs[p]->h;
+    L.code[p] = h.d_code; L.strings[p] = h.d_strings; L.result_is_int[p] = h.result_is_int;
+    uint32_t bits = 0;
+    for (size_t k = 0; k < h.sites.size(); k++) {   // string comparisons that do not involve the per-record model
+      const CelHostSite& st = h.sites[k];
+      auto str = [&](uint8_t kind, uint32_t off, uint32_t len) { return kind == 0 ? h.strings.substr(off, len) : kind == 1 ? std::string(L.cs.backend, L.cs.backend_len) : std::string(L.cs.route, L.cs.route_len); };
+      if ((str(st.lk, st.loff, st.llen) == str(st.rk, st.roff, st.rlen)) != st.negate) bits |= 1u << k;
+    }
+    L.host_bits[p] = bits;
+  }
+  return 0;
+}
+int aigw_usage_costs_cel_device(aigw_ctx* ctx, const aigw_sse_result* d_results, uint32_t n, aigw_cost_program* const* progs, uint32_t n_progs,
+                                const uint8_t* d_model_bytes, const uint32_t* d_model_off, const uint32_t* d_model_len, const char* model, const char* backend,
+                                const char* route_name, uint64_t* d_costs, uint8_t* d_errs, void* stream) {
+  if (n == 0 || n_progs == 0) return 0;
+  cudaSetDevice(ctx->device);
+  CelLaunch L;
+  if (int rc = cel_fill(ctx, L, progs, n_progs, model, backend, route_name)) return rc;
+  L.results = d_results; L.n = n; L.model_bytes = d_model_bytes; L.model_off = d_model_off; L.model_len = d_model_len;
+  L.costs = (unsigned long long*)d_costs; L.errs = d_errs;
+  CK(launch_cel(L, stream ? (cudaStream_t)stream : ctx->s_compute));
+  return 0;
+}
+int aigw_usage_costs_cel_host(aigw_ctx* ctx, const aigw_sse_result* results, uint32_t n, aigw_cost_program* const* progs, uint32_t n_progs,
+                              const uint8_t* model_bytes, uint64_t model_bytes_len, const uint32_t* model_off, const uint32_t* model_len, const char* model,
+                              const char* backend, const char* route_name, uint64_t* costs, uint8_t* errs) {
+  if (n == 0 || n_progs == 0) return 0;
+  cudaSetDevice(ctx->device);
+  const size_t nres = (size_t)n * sizeof(aigw_sse_result), nout = (size_t)n * n_progs;
+  ENSURE(ctx->d_sse_res, ctx->sse_res_cap, nres, false);
+  ENSURE(ctx->d_sse_coff, ctx->sse_coff_cap, nout * 9 + 64, false);
+  ENSURE(ctx->d_sse_bytes, ctx->sse_bytes_cap, model_bytes_len + (size_t)n * 8 + 64, false);
+  cudaStream_t st = ctx->s_compute;
+  CK(cudaMemcpyAsync(ctx->d_sse_res, results, nres, cudaMemcpyHostToDevice, st));
+  uint32_t* d_off = nullptr; uint32_t* d_len = nullptr;
+  if (model_off && model_len) {
+    d_off = (uint32_t*)ctx->d_sse_bytes; d_len = d_off + n;
+    uint8_t* d_mb = (uint8_t*)(d_len + n);
+    CK(cudaMemcpyAsync(d_off, model_off, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_len, model_len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_mb, model_bytes, model_bytes_len, cudaMemcpyHostToDevice, st));
+    if (int rc = aigw_usage_costs_cel_device(ctx, ctx->d_sse_res, n, progs, n_progs, d_mb, d_off, d_len, model, backend, route_name, (uint64_t*)ctx->d_sse_coff, (uint8_t*)ctx->d_sse_coff + nout * 8, st)) return rc;
+  } else if (int rc = aigw_usage_costs_cel_device(ctx, ctx->d_sse_res, n, progs, n_progs, nullptr, nullptr, nullptr, model, backend, route_name, (uint64_t*)ctx->d_sse_coff, (uint8_t*)ctx->d_sse_coff + nout * 8, st)) return rc;
+  CK(cudaMemcpyAsync(costs, ctx->d_sse_coff, nout * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(errs, (uint8_t*)ctx->d_sse_coff + nout * 8, nout, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return 0;
 }

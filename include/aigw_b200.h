@@ -244,6 +244,27 @@ int aigw_sha256_device(aigw_ctx* ctx, const uint8_t* d_bytes, const uint64_t* d_
 int aigw_chat_body_sha256_device(aigw_ctx* ctx, const uint8_t* d_out, const aigw_doc_result* d_results, uint32_t n, uint8_t* d_digests, void* stream, float* kernel_ms);
 int aigw_sha256_host(aigw_ctx* ctx, const uint8_t* bytes, const uint64_t* off, const uint32_t* len, uint32_t n, uint8_t* digests /* host, 32*n */);
 
+/* ---- CEL cost expressions (C2 / SURVEY §8f rank 2) ----
+ * Replaces llmcostcel.NewProgram / EvaluateProgram (internal/llmcostcel/cel.go:55-99) as evalCost calls them
+ * (internal/extproc/processor_impl.go:728-751) for the typed subset cost expressions use: model / backend / route_name with
+ * == and !=, the six uint token counters, int / uint / bool / string literals, checked + - * / %, same-type comparisons,
+ * ! && || (CEL error absorption), ?:, int() and uint().
+ * aigw_cost_compile: 0; -2 = outside the subset or a type error (keep evaluating it with cel-go); -3 = the reference's
+ * NewProgram refuses the expression (result not an integer, or its sanity evaluation with zero counters fails).
+ * aigw_usage_costs_cel_*: costs[i * n_progs + p] and errs[i * n_progs + p] (0, or 1 "integer overflow", 2 "unsigned integer
+ * overflow", 3 "divide by zero", 4 "modulus by zero", 5 "result is negative": EvaluateProgram returns an error) for usage
+ * record i.  The request model (x-ai-eg-model) is per record when model_off / model_len are given (spans in model_bytes),
+ * else `model` for all; backend and route_name are per call.  Strings are limited to 255 bytes. */
+typedef struct aigw_cost_program aigw_cost_program;
+int  aigw_cost_compile(aigw_ctx* ctx, const char* expr, aigw_cost_program** out);
+void aigw_cost_program_free(aigw_ctx* ctx, aigw_cost_program* p);
+int  aigw_usage_costs_cel_device(aigw_ctx* ctx, const aigw_sse_result* d_results, uint32_t n, aigw_cost_program* const* progs, uint32_t n_progs,
+                                 const uint8_t* d_model_bytes, const uint32_t* d_model_off, const uint32_t* d_model_len, const char* model, const char* backend,
+                                 const char* route_name, uint64_t* d_costs, uint8_t* d_errs, void* stream);
+int  aigw_usage_costs_cel_host(aigw_ctx* ctx, const aigw_sse_result* results, uint32_t n, aigw_cost_program* const* progs, uint32_t n_progs,
+                               const uint8_t* model_bytes, uint64_t model_bytes_len, const uint32_t* model_off, const uint32_t* model_len, const char* model,
+                               const char* backend, const char* route_name, uint64_t* costs, uint8_t* errs);
+
 const char* aigw_version(void);
 
 #ifdef __cplusplus
