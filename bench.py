@@ -96,6 +96,24 @@ def cpu_oracle_rate(arena, offs, lens, n_sample, threads):
     return n / sec, n, int(tot.value)
 
 
+def host_cores():
+    """threads the CPU legs may really use: the scheduler affinity mask, further limited by a cgroup CPU quota when one is set
+    (a box can show 128 logical CPUs and still be capped; oversubscribing a quota only adds throttling)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q[0] != "max":
+            n = max(1, min(n, int(float(q[0]) / float(q[1]) + 0.5)))
+    except Exception:
+        try:
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0:
+                n = max(1, min(n, int(quota / period + 0.5)))
+        except Exception:
+            pass
+    return n
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -107,7 +125,7 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
-    ncpu = os.cpu_count() or 1
+    ncpu = host_cores()
     import _workload as W
     import __graft_entry__ as entry
 

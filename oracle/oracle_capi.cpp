@@ -1,6 +1,8 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see ojson.hpp header).
 // C entry points so tests/, smoke() and bench.py's cpu_baseline / --impl reference legs can
 // drive the restatement through ctypes.  Built by oracle/Makefile into oracle/liboracle.so.
+#include <malloc.h>
+
 #include <atomic>
 #include <chrono>
 #include <thread>
@@ -15,6 +17,14 @@
 #include "translate.hpp"
 
 using namespace oracle;
+
+// The batch helpers run one worker per host thread.  glibc's defaults return freed memory to the kernel and map large blocks
+// eagerly, which serialises 128 workers on the process's mm lock (observed: 0.4–2.0 M bodies/s run to run on the bench box);
+// keeping freed memory in the arenas makes the CPU baseline both faster and repeatable — closer to Go's per-P allocator caches.
+__attribute__((constructor)) static void oracle_tune_allocator() {
+  if (getenv("ORACLE_NO_MALLOPT")) return;
+  mallopt(M_MMAP_THRESHOLD, 1 << 30); mallopt(M_TRIM_THRESHOLD, 1 << 30);
+}
 
 extern "C" {
 
