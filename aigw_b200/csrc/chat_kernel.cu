@@ -17,7 +17,7 @@ static_assert(make_lit_table().off[L_COUNT] + 24 <= sizeof(LitTable::bytes), "li
 
 #define FULL 0xffffffffu
 #ifndef AIGW_WALK_BLOCKS
-#define AIGW_WALK_BLOCKS 4
+#define AIGW_WALK_BLOCKS 6
 #endif
 
 // ------------------------------------------------------------------ small device helpers
