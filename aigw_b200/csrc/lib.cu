@@ -731,17 +731,26 @@ int aigw_usage_costs_cel_host(aigw_ctx* ctx, const aigw_sse_result* results, uin
 }
 
 // ------------------------------------------------------------------ R1 + C2
-int aigw_response_usage_device(aigw_ctx* ctx, const uint8_t* d_bodies, const uint64_t* d_offsets, const uint32_t* d_lens, uint32_t n,
-                               aigw_sse_result* d_results, void* stream, float* kernel_ms) {
+static int response_usage_device_impl(aigw_ctx* ctx, const uint8_t* d_bodies, const uint64_t* d_offsets, const uint32_t* d_lens, uint32_t n,
+                                      aigw_sse_result* d_results, void* stream, float* kernel_ms, int embeddings) {
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->s_compute;
   if (kernel_ms) CK(cudaEventRecord(ctx->ev0, st));
-  CK(launch_response_usage(d_bodies, d_offsets, d_lens, n, d_results, st));
+  CK(launch_response_usage(d_bodies, d_offsets, d_lens, n, d_results, st, embeddings));
   if (kernel_ms) { CK(cudaEventRecord(ctx->ev1, st)); CK(cudaEventSynchronize(ctx->ev1)); CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1)); }
   return 0;
 }
 
-int aigw_response_usage_host(aigw_ctx* ctx, const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n, aigw_sse_result* results,
-                             const int32_t* cost_types, uint32_t n_costs, uint64_t* costs) {
+int aigw_response_usage_device(aigw_ctx* ctx, const uint8_t* d_bodies, const uint64_t* d_offsets, const uint32_t* d_lens, uint32_t n,
+                               aigw_sse_result* d_results, void* stream, float* kernel_ms) {
+  return response_usage_device_impl(ctx, d_bodies, d_offsets, d_lens, n, d_results, stream, kernel_ms, 0);
+}
+int aigw_embeddings_response_usage_device(aigw_ctx* ctx, const uint8_t* d_bodies, const uint64_t* d_offsets, const uint32_t* d_lens, uint32_t n,
+                                          aigw_sse_result* d_results, void* stream, float* kernel_ms) {
+  return response_usage_device_impl(ctx, d_bodies, d_offsets, d_lens, n, d_results, stream, kernel_ms, 1);
+}
+
+static int response_usage_host_impl(aigw_ctx* ctx, const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n, aigw_sse_result* results,
+                                    const int32_t* cost_types, uint32_t n_costs, uint64_t* costs, int embeddings) {
   if (n == 0) return 0;
   cudaSetDevice(ctx->device);
   const uint64_t nbytes = offsets[n - 1] + lens[n - 1] - offsets[0];
@@ -753,7 +762,7 @@ int aigw_response_usage_host(aigw_ctx* ctx, const uint8_t* bodies, const uint64_
   CK(cudaMemcpyAsync(ctx->d_sse_bytes, bodies + offsets[0], nbytes, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->d_sse_coff, offsets, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->d_sse_first, lens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-  CK(launch_response_usage(ctx->d_sse_bytes - offsets[0], ctx->d_sse_coff, ctx->d_sse_first, n, ctx->d_sse_res, st));
+  CK(launch_response_usage(ctx->d_sse_bytes - offsets[0], ctx->d_sse_coff, ctx->d_sse_first, n, ctx->d_sse_res, st, embeddings));
   CK(cudaMemcpyAsync(results, ctx->d_sse_res, (size_t)n * sizeof(aigw_sse_result), cudaMemcpyDeviceToHost, st));
   if (n_costs && costs) {
     int32_t* d_types = (int32_t*)(ctx->d_sse_first + n + 1);
@@ -764,6 +773,14 @@ int aigw_response_usage_host(aigw_ctx* ctx, const uint8_t* bodies, const uint64_
   }
   CK(cudaStreamSynchronize(st));
   return 0;
+}
+int aigw_response_usage_host(aigw_ctx* ctx, const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n, aigw_sse_result* results,
+                             const int32_t* cost_types, uint32_t n_costs, uint64_t* costs) {
+  return response_usage_host_impl(ctx, bodies, offsets, lens, n, results, cost_types, n_costs, costs, 0);
+}
+int aigw_embeddings_response_usage_host(aigw_ctx* ctx, const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n, aigw_sse_result* results,
+                                        const int32_t* cost_types, uint32_t n_costs, uint64_t* costs) {
+  return response_usage_host_impl(ctx, bodies, offsets, lens, n, results, cost_types, n_costs, costs, 1);
 }
 
 int aigw_usage_costs_device(aigw_ctx* ctx, const aigw_sse_result* d_results, uint32_t n, const int32_t* d_cost_types, uint32_t n_costs, uint64_t* d_costs, void* stream) {

@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(kWarps * 32) sse_usage_kernel(const __grid_con
 // (internal/translator/openai_openai.go:146-174; struct internal/apischema/openai/openai.go:1269-1306,1365-1422).
 enum RN : uint8_t { R_ANY = 0, R_STR, R_INT, R_FLOAT, R_ROOT, R_CHOICES, R_CHOICE, R_MSG, R_TOOLCALLS, R_TOOLCALL, R_FUNC, R_CACHE, R_ANNOTS, R_ANNOT, R_URLCIT,
                   R_AUDIO, R_REASON_U, R_REASON_O, R_REASON_BLOCK, R_REASON_TEXT, R_B64, R_THINKS, R_THINK, R_LOGPROBS, R_TOKLPS, R_TOKLP, R_INTS, R_TOPLPS, R_TOPLP,
-                  R_USAGE, R_CTD, R_PTD, R_CREATED, R_MODEL, R_PROMPT, R_COMPLETION, R_TOTAL, R_REASONING_TOK, R_CACHED, R_CACHE_CREATION, R_COUNT };
+                  R_USAGE, R_CTD, R_PTD, R_CREATED, R_MODEL, R_PROMPT, R_COMPLETION, R_TOTAL, R_REASONING_TOK, R_CACHED, R_CACHE_CREATION,
+                  R_EM_DATA, R_EM_ITEM, R_EM_VEC, R_EM_FLOATS, R_EM_USAGE, R_COUNT };
 static const FieldDef kRespFields[] = {
   {R_ROOT, "id", R_STR}, {R_ROOT, "choices", R_CHOICES}, {R_ROOT, "created", R_CREATED}, {R_ROOT, "model", R_MODEL}, {R_ROOT, "service_tier", R_STR},
   {R_ROOT, "system_fingerprint", R_STR}, {R_ROOT, "object", R_STR}, {R_ROOT, "usage", R_USAGE}, {R_ROOT, "obfuscation", R_STR},
@@ -260,10 +261,38 @@ static RespSchemaBlob build_resp_schema() {
   return b;
 }
 
-// one thread per response body
-__global__ void __launch_bounds__(128) response_usage_kernel(const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n, aigw_sse_result* results) {
+// openai.EmbeddingResponse (internal/apischema/openai/openai.go:1683-1731,1772-1778): R_ROOT fields differ, so a second blob
+static const FieldDef kEmbFields[] = {
+  {R_ROOT, "object", R_STR}, {R_ROOT, "data", R_EM_DATA}, {R_ROOT, "model", R_MODEL}, {R_ROOT, "usage", R_EM_USAGE},
+  {R_EM_ITEM, "object", R_STR}, {R_EM_ITEM, "embedding", R_EM_VEC}, {R_EM_ITEM, "index", R_INT},
+  {R_EM_USAGE, "prompt_tokens", R_PROMPT}, {R_EM_USAGE, "total_tokens", R_TOTAL},
+};
+__device__ RespSchemaBlob g_emb_schema;
+static RespSchemaBlob build_emb_schema() {
+  RespSchemaBlob b; memset(&b, 0, sizeof b);
+  auto set = [&](int n, uint8_t kind, uint8_t cap = NOCAP, uint8_t elem = 0) { b.nodes[n].kind = kind; b.nodes[n].cap = cap; b.nodes[n].elem = elem; };
+  set(R_ANY, K_ANY); set(R_STR, K_STR); set(R_INT, K_INT); set(R_FLOAT, K_FLOAT);
+  set(R_ROOT, K_OBJ); set(R_EM_DATA, K_ARR, NOCAP, R_EM_ITEM); set(R_EM_ITEM, K_OBJ);
+  set(R_EM_VEC, K_STROBJ, NOCAP, R_EM_FLOATS);   // EmbeddingUnion: a string, or (the alternative node) an array of numbers
+  set(R_EM_FLOATS, K_ARR, NOCAP, R_FLOAT);
+  set(R_EM_USAGE, K_OBJ, C_OBJ_USAGE); set(R_MODEL, K_STR, C_SPAN_MODEL); set(R_PROMPT, K_INT, C_PROMPT); set(R_TOTAL, K_INT, C_TOTAL);
+  int ko = 0;
+  for (int f = 0; f < (int)(sizeof(kEmbFields) / sizeof(kEmbFields[0])); f++) {
+    const FieldDef& d = kEmbFields[f];
+    Node& o = b.nodes[d.owner];
+    if (o.nf == 0) o.f0 = (uint8_t)f;
+    o.nf++;
+    int kl = (int)strlen(d.key);
+    b.fields[f].koff = (uint16_t)ko; b.fields[f].klen = (uint8_t)kl; b.fields[f].node = d.node;
+    memcpy(b.keys + ko, d.key, kl); ko += kl;
+  }
+  return b;
+}
+
+// one thread per response body; `embeddings`: openai.EmbeddingResponse instead of openai.ChatCompletionResponse
+__global__ void __launch_bounds__(128) response_usage_kernel(const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n, aigw_sse_result* results, int embeddings) {
   __shared__ RespSchemaBlob sch;
-  for (uint32_t i = threadIdx.x; i < sizeof(RespSchemaBlob) / 4; i += blockDim.x) ((uint32_t*)&sch)[i] = ((const uint32_t*)&g_resp_schema)[i];
+  for (uint32_t i = threadIdx.x; i < sizeof(RespSchemaBlob) / 4; i += blockDim.x) ((uint32_t*)&sch)[i] = ((const uint32_t*)(embeddings ? &g_emb_schema : &g_resp_schema))[i];
   __syncthreads();
   const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= n) return;
@@ -277,7 +306,7 @@ __global__ void __launch_bounds__(128) response_usage_kernel(const uint8_t* bodi
   else if (!ok) r.status = AIGW_INTERNAL;  // "failed to unmarshal body": the reference fails the request
   else {
     // resp.Usage is a value: the three counters are always set; details only when their object was present
-    r.usage.input = cp.ints[C_PROMPT]; r.usage.output = cp.ints[C_COMPLETION]; r.usage.total = cp.ints[C_TOTAL]; r.usage.mask = 1u | 2u | 4u;
+    r.usage.input = cp.ints[C_PROMPT]; r.usage.output = cp.ints[C_COMPLETION]; r.usage.total = cp.ints[C_TOTAL]; r.usage.mask = embeddings ? (1u | 4u) : (1u | 2u | 4u);
     if (cp.obj_seen & (1u << C_OBJ_PTD)) { r.usage.cached = cp.ints[C_CACHED]; r.usage.cache_creation = cp.ints[C_CACHE_CREATION]; r.usage.mask |= 8u | 16u; }
     if (cp.obj_seen & (1u << C_OBJ_CTD)) { r.usage.reasoning = cp.ints[C_REASONING]; r.usage.mask |= 32u; }
     if ((cp.span_set & 1u) && cp.span_len[0] > 0) { r.model_off = offsets[d] + cp.span_off[0]; r.model_len = cp.span_len[0]; }
@@ -295,11 +324,15 @@ __global__ void usage_costs_kernel(const aigw_sse_result* results, uint32_t n, c
   out[i] = v;
 }
 
-cudaError_t launch_response_usage(const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n, aigw_sse_result* results, cudaStream_t st) {
+cudaError_t launch_response_usage(const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n, aigw_sse_result* results, cudaStream_t st, int embeddings) {
   static bool ready = false;
-  if (!ready) { RespSchemaBlob b = build_resp_schema(); cudaError_t e = cudaMemcpyToSymbol(g_resp_schema, &b, sizeof b); if (e != cudaSuccess) return e; ready = true; }
+  if (!ready) {
+    RespSchemaBlob b = build_resp_schema(); cudaError_t e = cudaMemcpyToSymbol(g_resp_schema, &b, sizeof b); if (e != cudaSuccess) return e;
+    RespSchemaBlob b2 = build_emb_schema(); e = cudaMemcpyToSymbol(g_emb_schema, &b2, sizeof b2); if (e != cudaSuccess) return e;
+    ready = true;
+  }
   if (n == 0) return cudaSuccess;
-  response_usage_kernel<<<(n + 127) / 128, 128, 0, st>>>(bodies, offsets, lens, n, results);
+  response_usage_kernel<<<(n + 127) / 128, 128, 0, st>>>(bodies, offsets, lens, n, results, embeddings);
   return cudaGetLastError();
 }
 cudaError_t launch_usage_costs(const aigw_sse_result* results, uint32_t n, const int32_t* cost_types, uint32_t n_costs, unsigned long long* out, cudaStream_t st) {

@@ -171,6 +171,13 @@ int aigw_response_usage_device(aigw_ctx* ctx, const uint8_t* d_bodies, const uin
                                aigw_sse_result* d_results, void* stream, float* kernel_ms);
 int aigw_response_usage_host(aigw_ctx* ctx, const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n,
                              aigw_sse_result* results, const int32_t* cost_types, uint32_t n_costs, uint64_t* costs /* n * n_costs, may be NULL */);
+/* Same for /v1/embeddings responses: openAIToOpenAITranslatorV1Embedding.ResponseBody (internal/translator/openai_embeddings.go:70-88)
+ * decodes openai.EmbeddingResponse (embedding = []float64 or base64 string) and sets input and total tokens only (mask bits 0 and 2);
+ * the response model is resp.Model. */
+int aigw_embeddings_response_usage_device(aigw_ctx* ctx, const uint8_t* d_bodies, const uint64_t* d_offsets, const uint32_t* d_lens, uint32_t n,
+                                          aigw_sse_result* d_results, void* stream, float* kernel_ms);
+int aigw_embeddings_response_usage_host(aigw_ctx* ctx, const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n,
+                                        aigw_sse_result* results, const int32_t* cost_types, uint32_t n_costs, uint64_t* costs /* n * n_costs, may be NULL */);
 int aigw_usage_costs_device(aigw_ctx* ctx, const aigw_sse_result* d_results, uint32_t n, const int32_t* d_cost_types, uint32_t n_costs,
                             uint64_t* d_costs, void* stream);
 

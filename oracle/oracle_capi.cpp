@@ -135,6 +135,12 @@ int oracle_response_openai(const char* body, uint64_t len, const char* request_m
   put(out, tu); uint64_t n = std::min<uint64_t>(cap, rm.size()); memcpy(model_buf, rm.data(), n); *model_len = rm.size();
   return ok ? 0 : 1;
 }
+int oracle_response_embeddings(const char* body, uint64_t len, oracle_usage* out, char* model_buf, uint64_t cap, uint64_t* model_len) {
+  TokenUsage tu; std::string rm;
+  bool ok = response_embeddings(std::string_view(body, len), tu, rm);
+  put(out, tu); uint64_t n = std::min<uint64_t>(cap, rm.size()); memcpy(model_buf, rm.data(), n); *model_len = rm.size();
+  return ok ? 0 : 1;
+}
 uint64_t oracle_eval_cost(int type, const oracle_usage* u) { TokenUsage t; t.input = u->input; t.output = u->output; t.total = u->total; t.cached = u->cached; t.cache_creation = u->cache_creation; t.reasoning = u->reasoning; t.mask = u->mask; return eval_cost(type, t); }
 
 // ---- S2: Bedrock eventstream → OpenAI SSE.  Replays ResponseBody over the given chunking; returns malloc'd output.

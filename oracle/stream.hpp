@@ -253,4 +253,34 @@ inline uint64_t eval_cost(int type, const TokenUsage& u) {
   return 0;
 }
 
+// R1 (embeddings): json.NewDecoder(body).Decode(&openai.EmbeddingResponse{}) then usage / model
+// (internal/translator/openai_embeddings.go:70-88; types internal/apischema/openai/openai.go:1683-1731,1772-1778).
+// Only input and total tokens are set; the response model is resp.Model.
+inline bool response_embeddings(std::string_view body, TokenUsage& tu, std::string& response_model) {
+  Value v;
+  oj::Parser ps(body.data(), body.size());
+  if (!ps.value(v)) return false;
+  tu = TokenUsage{}; response_model.clear();
+  int64_t prompt = 0, total = 0;
+  if (v.is_obj()) {
+    for (const char* k : {"object", "model"}) if (!str_or_null(v.get(k))) return false;
+    const Value* d = v.get("data"); if (!arr_or_null(d)) return false;
+    if (d && d->is_arr()) for (auto& e : d->arr) {
+      if (e.is_null()) continue;
+      if (!e.is_obj()) return false;
+      if (!str_or_null(e.get("object"))) return false;
+      int64_t q; if (!int_field(e.get("index"), q)) return false;
+      if (const Value* em = e.get("embedding")) {   // EmbeddingUnion: []float64 first, then string
+        if (em->is_arr()) { for (auto& x : em->arr) if (!x.is_null() && !x.is_num()) return false; }
+        else if (!em->is_null() && !em->is_str()) return false;
+      }
+    }
+    const Value* u = v.get("usage"); if (!obj_or_null(u)) return false;
+    if (u && u->is_obj()) { if (!int_field(u->get("prompt_tokens"), prompt) || !int_field(u->get("total_tokens"), total)) return false; }
+    if (const Value* m = v.get("model"); m && m->is_str()) response_model = m->s;
+  } else if (!v.is_null()) return false;
+  tu.input = (uint32_t)prompt; tu.total = (uint32_t)total; tu.mask = TokenUsage::IN | TokenUsage::TOTAL;
+  return true;
+}
+
 }  // namespace oracle

@@ -119,6 +119,14 @@ def response_openai(body: bytes, request_model: bytes = b""):
     return rc == 0, u, buf.raw[:ml.value]
 
 
+def response_embeddings(body: bytes):
+    """(ok, Usage, response_model bytes) — R1 embeddings, internal/translator/openai_embeddings.go:70-88."""
+    u = Usage(); buf = C.create_string_buffer(4096); ml = C.c_uint64(0)
+    L = lib(); L.oracle_response_embeddings.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(Usage), C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    rc = L.oracle_response_embeddings(body, len(body), C.byref(u), buf, 4096, C.byref(ml))
+    return rc == 0, u, buf.raw[:ml.value]
+
+
 def eval_cost(cost_type: int, u: Usage) -> int:
     return lib().oracle_eval_cost(cost_type, C.byref(u))
 

@@ -305,3 +305,14 @@ def test_cel_subset_rules():
     assert O.Cel("18446744073709551615u * (input_tokens + 1u)").eval("m", "b", "r", 1, 0, 0, 0, 0, 0)[0] == 2
     assert O.Cel("100u % input_tokens == 0u ? 1 : 0").rc == 2
     assert O.Cel("0x10 + -3").eval("m", "b", "r", 0, 0, 0, 0, 0, 0) == (0, 13)
+
+
+def test_embeddings_response_usage():
+    """internal/translator/openai_embeddings.go:70-88 on the data-plane response bodies (tests/data-plane/testupstream_test.go, /v1/embeddings cases)."""
+    c = next(c for c in CASES if c["name"] == "openai - /v1/embeddings")
+    ok, u, m = O.response_embeddings(c["responseBody"].encode())
+    assert ok and (u.input, u.total, u.output, u.mask) == (8, 8, 0, 5) and m == b"text-embedding-ada-002"
+    assert O.response_embeddings(b'{"data":[{"embedding":"AAAA","index":0},{"embedding":null},null],"usage":null}')[0]
+    assert not O.response_embeddings(b'{"data":[{"embedding":{"a":1}}]}')[0]
+    assert not O.response_embeddings(b'{"data":[{"embedding":[1,"x"]}]}')[0]
+    assert not O.response_embeddings(b'{"usage":{"prompt_tokens":1.5}}')[0]

@@ -95,3 +95,33 @@ def test_reference_response_golden(ctx):
     res, _ = ctx.response_usage_host(arena, offs, lens)
     r = res[0]
     assert int(r["status"]) == 0 and int(r["mask"]) == 7 and (int(r["input"]), int(r["output"]), int(r["total"])) == (0, 0, 0) and int(r["model_len"]) == 0
+
+
+def test_embeddings_response_usage_parity(ctx):
+    """R1 for /v1/embeddings (internal/translator/openai_embeddings.go:70-88): usage (input + total only) and response model."""
+    import json as _json
+    from aigw_b200 import capi
+    rng = np.random.default_rng(4)
+    bodies = []
+    for i in range(600):
+        n = int(rng.integers(0, 6))
+        data = [{"object": "embedding", "index": k, "embedding": ([float(x) for x in np.round(rng.normal(size=int(rng.integers(1, 200))), 6)] if rng.integers(0, 3) else "AAECAwQF")} for k in range(n)]
+        d = {"object": "list", "data": data, "model": ["text-embedding-3-small", "text-embedding-ada-002", ""][int(rng.integers(0, 3))],
+             "usage": {"prompt_tokens": int(rng.integers(0, 9000)), "total_tokens": int(rng.integers(0, 9000))}}
+        if i % 11 == 0: del d["usage"]
+        if i % 13 == 0: d["model"] = None
+        bodies.append(_json.dumps(d, separators=(",", ":")).encode())
+    bodies += [b'{"data":[{"embedding":{"a":1}}]}', b'{"data":[{"embedding":[1,"x"]}]}', b'{"usage":{"prompt_tokens":1.5}}', b'{"data":[{"embedding":null},null],"usage":null}', b'null', b'[]', b'{"model":5}',
+               b'{"data":[{"embedding":[1e-3,-2.5E+2,0]}],"usage":{"prompt_tokens":4294967297,"total_tokens":3}}']
+    arena, offs, lens = capi.pack_bodies(bodies)
+    res, _ = ctx.response_usage_host(arena, offs, lens, embeddings=True)
+    for b, r, o in zip(bodies, res, offs):
+        ok, u, m = O.response_embeddings(b)
+        if r["status"] == 4:
+            continue
+        assert (r["status"] == 0) == ok, (b[:120], int(r["status"]), ok)
+        if ok:
+            assert (int(r["input"]), int(r["output"]), int(r["total"]), int(r["mask"])) == (u.input, 0, u.total, 5), b[:120]
+            got = bytes(arena[int(r["model_off"]):int(r["model_off"]) + int(r["model_len"])])
+            assert got == m
+    assert (res["status"] != 4).sum() >= len(bodies) - 2
