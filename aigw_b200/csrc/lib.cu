@@ -579,43 +579,84 @@ int aigw_body_mutate_device(aigw_ctx* ctx, const aigw_body_mutation* m, const ui
 }
 int aigw_body_mutate_host(aigw_ctx* ctx, const aigw_body_mutation* m, const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n,
                           aigw_mut_batch_out* out) {
+  // Same pipeline as aigw_chat_translate_host: 256 MiB chunks, the H2D copy of chunk c+1 overlaps the kernel of chunk c, the
+  // kernel stores records and results straight into mapped pinned host memory, one synchronisation at the end.
   memset(out, 0, sizeof *out);
   if (n == 0) return 0;
   cudaSetDevice(ctx->device);
-  MutateParams P;
-  if (int rc = fill_mutate_params(ctx, P, m)) return rc;
-  uint32_t max_len = 0; uint64_t extra = 0;
-  for (uint32_t i = 0; i < n; i++) if (lens[i] > max_len) max_len = lens[i];
-  for (uint32_t k = 0; k < P.n_keys; k++) extra += P.keys[k].memb_len + 2;
-  const uint64_t lo = offsets[0], nbytes = offsets[n - 1] + lens[n - 1] - lo;
-  const uint64_t out_cap = (nbytes + (uint64_t)n * (extra + 32) + 4096 + 255) & ~255ull;
-  ChunkSlot& S = ctx->slot[0];
-  ENSURE(S.d_in, S.in_cap, nbytes + 64, false);
-  if (S.doc_cap < n) { cudaFree(S.d_off); cudaFree(S.d_len); S.doc_cap = 0; const size_t dc = (size_t)n + n / 8 + 16; CK(cudaMalloc(&S.d_off, dc * 8)); CK(cudaMalloc(&S.d_len, dc * 4)); S.doc_cap = dc; }
-  ENSURE(ctx->h_out, ctx->h_out_cap, out_cap, true);
+  MutateParams P0;
+  if (int rc = fill_mutate_params(ctx, P0, m)) return rc;
+  uint64_t extra = 0;
+  for (uint32_t k = 0; k < P0.n_keys; k++) extra += P0.keys[k].memb_len + 2;
+  const uint64_t kChunkBytes = 256ull << 20;
+  std::vector<uint32_t> cb; cb.push_back(0);
+  uint32_t max_len = 0;
+  {
+    uint64_t start = offsets[0];
+    for (uint32_t i = 0; i < n; i++) {
+      const uint64_t end = offsets[i] + lens[i];
+      if (end - start > kChunkBytes && i > cb.back()) { cb.push_back(i); start = offsets[i]; }
+      if (lens[i] > max_len) max_len = lens[i];
+    }
+    cb.push_back(n);
+  }
+  const int nch = (int)cb.size() - 1;
+  std::vector<uint64_t> in_bytes(nch), out_cap(nch), out_base(nch);
+  uint64_t max_in = 0, total_cap = 0; uint32_t max_docs = 0;
+  for (int c = 0; c < nch; c++) {
+    const uint32_t b = cb[c], e = cb[c + 1];
+    const uint64_t ib = offsets[e - 1] + lens[e - 1] - offsets[b];
+    in_bytes[c] = ib; if (ib > max_in) max_in = ib; if (e - b > max_docs) max_docs = e - b;
+    out_cap[c] = (ib + (uint64_t)(e - b) * (extra + 32) + 4096 + 255) & ~255ull;
+    out_base[c] = total_cap; total_cap += out_cap[c];
+  }
+  const int nslots = nch < 2 ? 1 : 2;
+  for (int k = 0; k < nslots; k++) {
+    ChunkSlot& S = ctx->slot[k];
+    ENSURE(S.d_in, S.in_cap, max_in + 64, false);
+    if (S.doc_cap < max_docs) { cudaFree(S.d_off); cudaFree(S.d_len); S.doc_cap = 0; const size_t dc = (size_t)max_docs + max_docs / 8 + 16; CK(cudaMalloc(&S.d_off, dc * 8)); CK(cudaMalloc(&S.d_len, dc * 4)); S.doc_cap = dc; }
+  }
+  ENSURE(ctx->h_out, ctx->h_out_cap, total_cap, true);
   ENSURE(ctx->h_mres, ctx->h_mres_cap, (size_t)n * sizeof(aigw_mut_result), true);
-  if (ctx->used_cap < 1) { CK(cudaMalloc(&ctx->d_used_arr, 64 * 8)); CK(cudaHostAlloc(&ctx->h_used_arr, 64 * 8, cudaHostAllocDefault)); ctx->used_cap = 64; }
+  if ((size_t)nch > ctx->used_cap) {
+    cudaFree(ctx->d_used_arr); cudaFreeHost(ctx->h_used_arr); ctx->used_cap = 0;
+    const size_t cap = (size_t)nch + 64;
+    CK(cudaMalloc(&ctx->d_used_arr, cap * 8)); CK(cudaHostAlloc(&ctx->h_used_arr, cap * 8, cudaHostAllocDefault));
+    ctx->used_cap = cap;
+  }
   uint8_t* dev_out = nullptr; aigw_mut_result* dev_res = nullptr;
   CK(cudaHostGetDevicePointer((void**)&dev_out, ctx->h_out, 0));
   CK(cudaHostGetDevicePointer((void**)&dev_res, ctx->h_mres, 0));
-  cudaStream_t st = ctx->s_compute;
-  CK(cudaMemcpyAsync(S.d_in, bodies + lo, nbytes, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(S.d_off, offsets, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(S.d_len, lens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-  P.bodies = S.d_in - lo; P.offsets = S.d_off; P.lens = S.d_len; P.n = n; P.out = dev_out; P.out_capacity = out_cap; P.out_bias = 0; P.results = dev_res;
-  P.out_used = ctx->d_used_arr;
-  P.next = ctx->d_counters + (ctx->counter_next++ & 255);
-  CK(cudaMemsetAsync(P.next, 0, sizeof(unsigned int), st));
-  CK(cudaMemsetAsync(ctx->d_used_arr, 0, 8, st));
-  CK(cudaEventRecord(ctx->ev0, st));
-  CK(launch_body_mutate(P, max_len, ctx->sm_count, st));
-  CK(cudaEventRecord(ctx->ev1, st));
-  CK(cudaMemcpyAsync(ctx->h_used_arr, ctx->d_used_arr, 8, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  uint64_t h2d = 0;
+  CK(cudaMemsetAsync(ctx->d_used_arr, 0, (size_t)nch * 8, ctx->s_compute));
+  CK(cudaEventRecord(ctx->ev0, ctx->s_compute));
+  for (int c = 0; c < nch; c++) {
+    ChunkSlot& S = ctx->slot[c % nslots];
+    const uint32_t b = cb[c], e = cb[c + 1], nd = e - b;
+    if (c >= nslots) CK(cudaStreamWaitEvent(ctx->s_h2d, S.ev_k1, 0));
+    CK(cudaMemcpyAsync(S.d_in, bodies + offsets[b], in_bytes[c], cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaMemcpyAsync(S.d_off, offsets + b, (size_t)nd * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaMemcpyAsync(S.d_len, lens + b, (size_t)nd * 4, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaEventRecord(S.ev_h2d, ctx->s_h2d));
+    h2d += in_bytes[c] + (uint64_t)nd * 12;
+    CK(cudaStreamWaitEvent(ctx->s_compute, S.ev_h2d, 0));
+    MutateParams P = P0;
+    P.bodies = S.d_in - offsets[b]; P.offsets = S.d_off; P.lens = S.d_len; P.n = nd;
+    P.out = dev_out + out_base[c]; P.out_capacity = out_cap[c]; P.out_bias = out_base[c]; P.results = dev_res + b;
+    P.out_used = ctx->d_used_arr + c;
+    P.next = ctx->d_counters + (ctx->counter_next++ & 255);
+    CK(cudaMemsetAsync(P.next, 0, sizeof(unsigned int), ctx->s_compute));
+    CK(launch_body_mutate(P, max_len, ctx->sm_count, ctx->s_compute));
+    CK(cudaEventRecord(S.ev_k1, ctx->s_compute));
+    out->gpu_launches += 1;
+  }
+  CK(cudaEventRecord(ctx->ev1, ctx->s_compute));
+  CK(cudaMemcpyAsync(ctx->h_used_arr, ctx->d_used_arr, (size_t)nch * 8, cudaMemcpyDeviceToHost, ctx->s_compute));
+  CK(cudaStreamSynchronize(ctx->s_compute));
+  uint64_t d2h = (uint64_t)n * sizeof(aigw_mut_result) + (uint64_t)nch * 8;
+  for (int c = 0; c < nch; c++) d2h += ctx->h_used_arr[c] < out_cap[c] ? ctx->h_used_arr[c] : out_cap[c];
   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-  const uint64_t used = ctx->h_used_arr[0] < out_cap ? ctx->h_used_arr[0] : out_cap;
-  out->results = ctx->h_mres; out->out = ctx->h_out; out->out_used = used; out->h2d_bytes = nbytes + (uint64_t)n * 12; out->d2h_bytes = used + (uint64_t)n * sizeof(aigw_mut_result) + 8;
-  out->gpu_launches = 1; out->kernel_ms = ms;
+  out->results = ctx->h_mres; out->out = ctx->h_out; out->out_used = total_cap; out->h2d_bytes = h2d; out->d2h_bytes = d2h; out->kernel_ms = ms;
   return 0;
 }
 

@@ -24,7 +24,8 @@ buf = np.tile(arr, reps)
 soff = np.concatenate([[0], np.tile(np.diff(off.astype(np.int64)), reps).cumsum()]).astype(np.uint64)
 nbytes = int(soff[-1])
 frames = sum(s.count(b":event-type") for s in streams) * reps
-ncpu = os.cpu_count()
+from bench import host_cores
+ncpu = host_cores()   # affinity mask ∩ cgroup CPU quota
 ns = min(a.cpu_streams, n)
 tot = C.c_uint64(0)
 L = O.lib(); L.oracle_bedrock_stream_batch.restype = C.c_double

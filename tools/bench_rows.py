@@ -18,7 +18,8 @@ ap.add_argument("--cpu-n", type=int, default=200_000)
 ap.add_argument("--rows", default="r1,b1")
 a = ap.parse_args()
 ctx = A.Context(0)
-ncpu = os.cpu_count()
+from bench import host_cores
+ncpu = host_cores()   # affinity mask ∩ cgroup CPU quota
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 L = O.lib()
 

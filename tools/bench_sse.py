@@ -20,7 +20,8 @@ a = ap.parse_args()
 ctx = A.Context(0)
 buf, coff, cfirst = W.sse_corpus(4, 0, a.streams, chunks=a.chunks)
 nbytes = int(coff[-1]); nchunks = len(coff) - 1
-ncpu = os.cpu_count()
+from bench import host_cores
+ncpu = host_cores()   # affinity mask ∩ cgroup CPU quota
 # CPU oracle (chunk-by-chunk replay) on a bounded sample
 ns = min(a.cpu_streams, a.streams)
 outu = np.zeros(ns, dtype=np.dtype([(k, "<u4") for k in ("input", "output", "total", "cached", "cache_creation", "reasoning", "mask")]))
