@@ -73,9 +73,12 @@ static SchemaBlob build_schema() {
 }
 
 // ------------------------------------------------------------------ kernel
+__device__ __forceinline__ uint32_t nib_ff(uint32_t m) { return ((m & 0x08040201u) * 0x01010101u) >> 24; }   // 0xFF per byte → 4-bit mask
 static constexpr int kTile = 8192;       // bytes of a stream staged per warp
 static constexpr int kMaxLines = 512;    // line-start slots per tile
 static constexpr int kWarps = 4;
+static constexpr int kMaxCand = 64;
+static constexpr int kWarpBytes = kTile + 32 + kMaxLines * 2 + kMaxLines / 8 + kMaxCand * 2;
 
 struct LineOut { uint32_t seq; uint32_t v[6]; uint32_t flags; uint32_t model_off, model_len; };
 
@@ -86,8 +89,10 @@ __global__ void __launch_bounds__(kWarps * 32) sse_usage_kernel(const __grid_con
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t FULLM = 0xffffffffu;
-  uint8_t* tile = smem + ((sizeof(SchemaBlob) + 15) & ~15u) + (size_t)warp * (kTile + 16 + kMaxLines * 2);
-  uint16_t* lstart = (uint16_t*)(tile + kTile + 16);
+  uint8_t* tile = smem + ((sizeof(SchemaBlob) + 15) & ~15u) + (size_t)warp * kWarpBytes;
+  uint16_t* lstart = (uint16_t*)(tile + kTile + 32);
+  uint32_t* s_need = (uint32_t*)(lstart + kMaxLines);   // bit per line: the typed walk is needed
+  uint16_t* s_cand = (uint16_t*)(s_need + kMaxLines / 32);   // positions of `"usage"` / `\u` candidates of the tile
 
   for (;;) {
     uint32_t s = 0;
@@ -102,7 +107,10 @@ __global__ void __launch_bounds__(kWarps * 32) sse_usage_kernel(const __grid_con
     uint32_t status = 0;
     uint32_t line_no = 0;
     uint64_t pos = sb;         // next unread stream byte
-    uint32_t carry = 0;        // bytes of an unfinished line at tile[0..carry)
+    uint32_t carry = 0;        // bytes of an unfinished line at tile[t0..t0+carry)
+    // the tile's data starts at t0 < 16, kept such that tile + t0 + carry and the next source byte have the same alignment
+    // modulo 16: every 16-byte load from global memory is then a 16-byte store to shared memory
+    uint32_t t0 = (uint32_t)((uintptr_t)(P.bytes + sb) & 15u);
     while (pos < se || carry) {
       // ---- stage the next tile after the carry
       uint32_t room = kTile - carry;
@@ -112,29 +120,73 @@ __global__ void __launch_bounds__(kWarps * 32) sse_usage_kernel(const __grid_con
         // global → shared; source alignment is arbitrary, so align the 16-byte loads on the source
         const uint8_t* g = P.bytes + pos;
         uint32_t head = (uint32_t)((16 - ((uintptr_t)g & 15)) & 15); if (head > take) head = take;
-        for (uint32_t i = lane; i < head; i += 32) tile[carry + i] = g[i];
+        uint8_t* dst = tile + t0 + carry;
+        for (uint32_t i = lane; i < head; i += 32) dst[i] = g[i];
         const uint32_t body = (take - head) & ~15u;
         const uint4* g4 = (const uint4*)(g + head);
-        for (uint32_t i = lane; i < (body >> 4); i += 32) {
-          uint4 v = __ldg(g4 + i);
-          uint8_t* d = tile + carry + head + (i << 4);
-          if ((((uintptr_t)d) & 15) == 0) *(uint4*)d = v;
-          else { const uint8_t* b = (const uint8_t*)&v; for (int k = 0; k < 16; k++) d[k] = b[k]; }
-        }
-        for (uint32_t i = head + body + lane; i < take; i += 32) tile[carry + i] = g[i];
+        uint4* d4 = (uint4*)(dst + head);
+        for (uint32_t i = lane; i < (body >> 4); i += 32) d4[i] = __ldg(g4 + i);
+        for (uint32_t i = head + body + lane; i < take; i += 32) dst[i] = g[i];
       }
       __syncwarp();
       const uint32_t filled = carry + take;
-      const uint64_t tile_base = pos - carry;  // stream offset of tile[0]
+      const uint64_t tile_base = pos - carry - t0;  // stream offset of tile[0]
       pos += take;
-      // ---- newline positions
+      // ---- newline positions and walk candidates, 16 bytes per lane per step (SIMD-in-register byte compares)
       uint32_t nlines = 0; bool overflow = false;
-      for (uint32_t b = 0; b < filled; b += 32) {
-        const uint32_t i = b + lane;
-        const bool nl = i < filled && tile[i] == '\n';
-        const uint32_t m = __ballot_sync(FULLM, nl);
-        if (nl) { const uint32_t k = nlines + __popc(m & ((1u << lane) - 1u)); if (k < kMaxLines) lstart[k] = (uint16_t)i; else overflow = true; }
-        nlines += __popc(m);
+      uint32_t ncand = 0;
+      if (lane < kMaxLines / 32) s_need[lane] = 0;
+      {
+        const uint32_t lo = t0, hi = t0 + filled;
+        for (uint32_t cb0 = 0; cb0 < hi; cb0 += 512u) {
+          const uint32_t off = cb0 + ((uint32_t)lane << 4);
+          uint32_t mn = 0, mq = 0, mb = 0, mu = 0;
+          if (off < hi) {
+            const uint4 v = *(const uint4*)(tile + off);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              mn |= nib_ff(__vcmpeq4(w[j], 0x0a0a0a0au)) << (4 * j);
+              mq |= nib_ff(__vcmpeq4(w[j], 0x22222222u)) << (4 * j);
+              mb |= nib_ff(__vcmpeq4(w[j], 0x5c5c5c5cu)) << (4 * j);
+              mu |= nib_ff(__vcmpeq4(w[j], 0x75757575u)) << (4 * j);
+            }
+            // bytes of this chunk inside [lo, hi)
+            uint32_t vm = 0xffffu;
+            if (off < lo) vm &= lo - off >= 16u ? 0u : (0xffffu << (lo - off));
+            if (off + 16u > hi) vm &= (1u << (hi - off)) - 1u;
+            mn &= vm;
+            const uint32_t next_u = tile[off + 16] == 'u' ? 0x8000u : 0u;
+            uint32_t cand = (mq | mb) & ((mu >> 1) | next_u) & vm;
+            // `"u…`: keep only a full `"usage"`
+            uint32_t cq = cand & mq;
+            while (cq) {
+              const int j = __ffs(cq) - 1; cq &= cq - 1;
+              const uint8_t* q = tile + off + j;
+              if (!(off + j + 6 < hi && q[2] == 's' && q[3] == 'a' && q[4] == 'g' && q[5] == 'e' && q[6] == '"')) cand &= ~(1u << j);
+            }
+            mq = cand;   // reuse: surviving candidates
+          } else mq = 0;
+          // newlines → lstart (warp scan of the per-lane counts)
+          const uint32_t cnt = __popc(mn);
+          uint32_t incl = cnt;
+#pragma unroll
+          for (int sft = 1; sft < 32; sft <<= 1) { const uint32_t t = __shfl_up_sync(FULLM, incl, sft); if (lane >= sft) incl += t; }
+          uint32_t k = nlines + incl - cnt;
+          while (mn) { const int j = __ffs(mn) - 1; mn &= mn - 1; if (k < kMaxLines) lstart[k] = (uint16_t)(off + j); else overflow = true; k++; }
+          nlines += __shfl_sync(FULLM, incl, 31);
+          // candidate positions → list (resolved to lines once lstart is complete)
+          const uint32_t cm = __ballot_sync(FULLM, mq != 0);
+          if (cm) {
+            const uint32_t c2 = __popc(mq);
+            uint32_t in2 = c2;
+#pragma unroll
+            for (int sft = 1; sft < 32; sft <<= 1) { const uint32_t t = __shfl_up_sync(FULLM, in2, sft); if (lane >= sft) in2 += t; }
+            uint32_t kk = ncand + in2 - c2;
+            while (mq) { const int j = __ffs(mq) - 1; mq &= mq - 1; if (kk < kMaxCand) s_cand[kk] = (uint16_t)(off + j); kk++; }
+            ncand += __shfl_sync(FULLM, in2, 31);
+          }
+        }
       }
       overflow = __any_sync(FULLM, overflow);
       __syncwarp();
@@ -144,43 +196,87 @@ __global__ void __launch_bounds__(kWarps * 32) sse_usage_kernel(const __grid_con
         carry = filled; continue;
       }
       if (overflow) { status = AIGW_DECLINED; break; }
-      // ---- one lane per complete line
+      __syncwarp();
+      const bool cand_overflow = ncand > (uint32_t)kMaxCand;   // too many candidates to list: walk every line of this tile
+      if (!cand_overflow) {
+        for (uint32_t c = lane; c < ncand; c += 32) {
+          const uint32_t p = s_cand[c];
+          uint32_t lo2 = 0, hi2 = nlines;   // first line whose newline lies behind p
+          while (lo2 < hi2) { const uint32_t mid = (lo2 + hi2) >> 1; if (lstart[mid] > p) hi2 = mid; else lo2 = mid + 1; }
+          if (lo2 < nlines) atomicOr(&s_need[lo2 >> 5], 1u << (lo2 & 31));
+        }
+      }
+      __syncwarp();
+      // ---- which lines need the typed walk?
+      // A line changes the usage only if it decodes AND carries a top-level "usage" member; it changes the response model
+      // only if it is the LAST decodable line with a non-empty model.  So a line is walked when it contains the bytes
+      // `"usage"` (keys are matched case-sensitively, internal/json/json.go) or a `\u` escape (which could spell that key),
+      // or when it is one of the last two `data: ` lines of the tile (model candidates).  If neither candidate yields a model
+      // the whole tile is walked again without the filter, so the result is the reference's for every input.
+      uint32_t cand1 = 0xffffffffu, cand2 = 0xffffffffu;   // the tile's last and second-to-last data line
       for (uint32_t l0 = 0; l0 < nlines; l0 += 32) {
         const uint32_t li = l0 + lane;
-        if (li < nlines) {
-          const int b = li == 0 ? 0 : lstart[li - 1] + 1;
-          const int e = lstart[li];
-          const uint8_t* q = tile + b; const int n = e - b;
-          if (n >= 6 && q[0] == 'd' && q[1] == 'a' && q[2] == 't' && q[3] == 'a' && q[4] == ':' && q[5] == ' ') {
-            Capture cp; cp.int_set = 0; cp.obj_seen = 0; cp.span_set = 0; cp.span_esc = 0; cp.weird = 0; cp.big = 0;
+        bool isd = false;
+        if (li < nlines) { const int b = li == 0 ? (int)t0 : lstart[li - 1] + 1; const int e = lstart[li]; const uint8_t* q = tile + b; isd = e - b >= 6 && q[0] == 'd' && q[1] == 'a' && q[2] == 't' && q[3] == 'a' && q[4] == ':' && q[5] == ' '; }
+        const uint32_t m = __ballot_sync(FULLM, isd);
+        if (m) {   // groups ascend, so this group's top two data lines supersede the earlier candidates
+          const uint32_t hi = 31u - __clz(m), m2 = m & ~(1u << hi);
+          cand2 = m2 ? l0 + (31u - __clz(m2)) : cand1;
+          cand1 = l0 + hi;
+        }
+      }
+      for (int pass = 0; pass < 2; pass++) {
+        const bool walk_all = pass == 1;
+        uint32_t model_found = 0;
+        for (uint32_t l0 = 0; l0 < nlines; l0 += 32) {
+          const uint32_t li = l0 + lane;
+          if (li < nlines) {
+            const int b = li == 0 ? (int)t0 : lstart[li - 1] + 1;
+            const int e = lstart[li];
+            const uint8_t* q = tile + b; const int n = e - b;
+            if (n >= 6 && q[0] == 'd' && q[1] == 'a' && q[2] == 't' && q[3] == 'a' && q[4] == ':' && q[5] == ' ') {
+              const bool need = walk_all || cand_overflow || li == cand1 || li == cand2 || ((s_need[li >> 5] >> (li & 31)) & 1u);
+              if (need) {
+                Capture cp; cp.int_set = 0; cp.obj_seen = 0; cp.span_set = 0; cp.span_esc = 0; cp.weird = 0; cp.big = 0;
 #pragma unroll
-            for (int k = 0; k < 8; k++) cp.ints[k] = 0;
-            const bool ok = walk(q + 6, n - 6, sch->nodes, sch->fields, sch->keys, N_ROOT, cp);
-            if (cp.weird || (cp.span_esc & 1u)) status = AIGW_DECLINED;
-            if (ok) {
-              const uint32_t seq = line_no + li + 1;
-              if ((cp.span_set & 1u) && cp.span_len[0] > 0) { seq_m = seq; m_off = tile_base + (uint64_t)b + 6 + cp.span_off[0]; m_len = cp.span_len[0]; }
-              if (cp.obj_seen & (1u << C_OBJ_USAGE)) {
-                seq_u = seq; v_in = cp.ints[C_PROMPT]; v_out = cp.ints[C_COMPLETION]; v_tot = cp.ints[C_TOTAL];
-                if (cp.obj_seen & (1u << C_OBJ_PTD)) { seq_p = seq; v_cached = cp.ints[C_CACHED]; v_cc = cp.ints[C_CACHE_CREATION]; }
-                if (cp.obj_seen & (1u << C_OBJ_CTD)) { seq_c = seq; v_reason = cp.ints[C_REASONING]; }
+                for (int k = 0; k < 8; k++) cp.ints[k] = 0;
+                const bool ok = walk(q + 6, n - 6, sch->nodes, sch->fields, sch->keys, N_ROOT, cp);
+                if (cp.weird || (cp.span_esc & 1u)) status = AIGW_DECLINED;
+                if (ok) {
+                  const uint32_t seq = line_no + li + 1;
+                  if ((cp.span_set & 1u) && cp.span_len[0] > 0) { if (seq >= seq_m) { seq_m = seq; m_off = tile_base + (uint64_t)b + 6 + cp.span_off[0]; m_len = cp.span_len[0]; } if (li == cand1 || li == cand2) model_found = 1; }
+                  if (cp.obj_seen & (1u << C_OBJ_USAGE)) {
+                    if (seq >= seq_u) { seq_u = seq; v_in = cp.ints[C_PROMPT]; v_out = cp.ints[C_COMPLETION]; v_tot = cp.ints[C_TOTAL]; }
+                    if ((cp.obj_seen & (1u << C_OBJ_PTD)) && seq >= seq_p) { seq_p = seq; v_cached = cp.ints[C_CACHED]; v_cc = cp.ints[C_CACHE_CREATION]; }
+                    if ((cp.obj_seen & (1u << C_OBJ_CTD)) && seq >= seq_c) { seq_c = seq; v_reason = cp.ints[C_REASONING]; }
+                  }
+                }
               }
             }
           }
         }
+        // a candidate that decoded with a non-empty model is the tile's last such line (only the other, later candidate could
+        // follow it, and it was walked too); otherwise walk every line of the tile
+        if (walk_all || cand1 == 0xffffffffu || __any_sync(FULLM, model_found)) break;
       }
       __syncwarp();
       line_no += nlines;
-      // ---- carry the unterminated tail to the front of the tile
+      // ---- carry the unterminated tail to the front of the tile, at the offset that keeps the staging aligned
       const uint32_t last = (uint32_t)lstart[nlines - 1] + 1;
-      const uint32_t rem = filled - last;
-      for (uint32_t b = 0; b < rem; b += 32) {
-        const uint32_t i = b + lane;
-        uint8_t c = 0; if (i < rem) c = tile[last + i];
-        __syncwarp();
-        if (i < rem) tile[i] = c;
+      const uint32_t rem = t0 + filled - last;
+      const uint32_t nt0 = (uint32_t)(((uintptr_t)(P.bytes + pos) - rem) & 15u);
+      if (rem && nt0 != last) {
+        const uint32_t nchunk = (rem + 31u) >> 5;
+        for (uint32_t k = 0; k < nchunk; k++) {
+          const uint32_t ck = nt0 <= last ? k : nchunk - 1u - k;   // ascending when moving down, descending when moving up
+          const uint32_t i = (ck << 5) + lane;
+          uint8_t c = 0; if (i < rem) c = tile[last + i];
+          __syncwarp();
+          if (i < rem) tile[nt0 + i] = c;
+          __syncwarp();
+        }
       }
-      __syncwarp();
+      t0 = nt0;
       carry = rem;
       if (pos >= se) break;
     }
@@ -344,7 +440,7 @@ cudaError_t launch_usage_costs(const aigw_sse_result* results, uint32_t n, const
 
 cudaError_t launch_sse_usage(const SseParams& P, int sm_count, cudaStream_t st) {
   static bool ready = false; static int bps = 1;
-  const size_t smem = ((sizeof(SchemaBlob) + 15) & ~15u) + (size_t)kWarps * (kTile + 16 + kMaxLines * 2);
+  const size_t smem = ((sizeof(SchemaBlob) + 15) & ~15u) + (size_t)kWarps * kWarpBytes;
   if (!ready) {
     SchemaBlob b = build_schema();
     cudaError_t e = cudaMemcpyToSymbol(g_schema, &b, sizeof b);

@@ -2,6 +2,7 @@
 chunk-by-chunk replay of extractUsageFromBufferEvent + Override."""
 import ctypes as C
 import json
+import random
 import os
 
 import numpy as np
@@ -112,3 +113,44 @@ def test_adversarial_lines(ctx):
         exp, emodel = _oracle_stream(chunks)
         if st == 0:
             assert tup == exp and model == emodel, (b"".join(chunks), tup, exp, model, emodel)
+
+
+def test_line_filter_is_exact(ctx):
+    """the kernel walks only lines that can matter (a `"usage"` member, a \\u escape, the last two data lines of a tile):
+    streams built to defeat that shortcut must still give the reference's usage and response model"""
+    rng = random.Random(7)
+    def chunk(model, content="x", usage=None, extra=""):
+        d = {"id": "c", "object": "chat.completion.chunk", "created": 1, "model": model, "choices": [{"index": 0, "delta": {"content": content}}]}
+        if usage is not None: d["usage"] = usage
+        return ("data: " + json.dumps(d, separators=(",", ":")) + extra + "\n\n").encode()
+    U = lambda a, b: {"prompt_tokens": a, "completion_tokens": b, "total_tokens": a + b}
+    streams = []
+    # usage line early with model A, later valid lines with model B, then an invalid tail
+    streams.append([chunk("A", usage=U(1, 2)), chunk("B"), chunk("B"), b"data: {not json}\n\n", b"data: [DONE]\n\n"])
+    # last data lines valid but with an empty model; an earlier line carries it
+    streams.append([chunk("M1"), chunk(""), chunk(""), b"data: [DONE]\n\n"])
+    # the word usage inside content (escaped quotes), a key spelled with \u escapes, a usage member that is null
+    streams.append([chunk("m", content='he said "usage" twice'), b'data: {"model":"m","us\\u0061ge":{"prompt_tokens":9,"completion_tokens":1,"total_tokens":10}}\n\n', chunk("m", usage=None), b"data: [DONE]\n\n"])
+    # two usage lines, the later one wins field by field; model switches after the last usage line
+    streams.append([chunk("a", usage=U(5, 6)), chunk("a", usage={"prompt_tokens": 7, "completion_tokens": 8, "total_tokens": 15, "prompt_tokens_details": {"cached_tokens": 3}}), chunk("zz"), b"data: [DONE]\n\n"])
+    # many tiles: long streams whose only valid model-bearing line sits far from the tile ends
+    long = [chunk("first")] + [b"data: {broken\n\n"] * 400 + [chunk("mid", usage=U(2, 3))] + [b": comment\n\n"] * 300 + [b"data: {broken\n\n"] * 3
+    streams.append(long)
+    # random mixtures
+    for _ in range(200):
+        s = []
+        for _ in range(rng.randint(1, 60)):
+            r = rng.random()
+            if r < 0.6: s.append(chunk(rng.choice(["a", "b", "", "gpt-4o"]), content="t" * rng.randint(0, 200)))
+            elif r < 0.7: s.append(chunk(rng.choice(["a", "b"]), usage=U(rng.randint(0, 99), rng.randint(0, 99))))
+            elif r < 0.8: s.append(b"data: {oops\n\n")
+            elif r < 0.9: s.append(b"event: ping\n\n")
+            else: s.append(chunk("esc", content="caf\\u00e9"))
+        streams.append(s)
+    got = _gpu_streams(ctx, streams)
+    for s, g in zip(streams, got):
+        exp_u, exp_m = _oracle_stream(s)
+        if g[0] == 4:
+            continue
+        assert g[0] == 0 and g[1] == exp_u and g[2] == exp_m, (b"".join(s)[:300], g, exp_u, exp_m)
+    assert sum(1 for g in got if g[0] == 0) >= len(streams) - 60
