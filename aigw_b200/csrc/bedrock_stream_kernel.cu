@@ -204,8 +204,8 @@ __global__ void __launch_bounds__(kWarps * 32) bedrock_frames_kernel(const __gri
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t FULLM = 0xffffffffu;
-  uint8_t* tile = (uint8_t*)(crc_tab + 256) + (size_t)warp * (kTile + 16 + kMaxFrames * 2);
-  uint16_t* fstart = (uint16_t*)(tile + kTile + 16);
+  uint8_t* tile = (uint8_t*)(crc_tab + 256) + (size_t)warp * (kTile + 32 + kMaxFrames * 2);
+  uint16_t* fstart = (uint16_t*)(tile + kTile + 32);
 
   for (;;) {
     uint32_t s = 0;
@@ -221,6 +221,8 @@ __global__ void __launch_bounds__(kWarps * 32) bedrock_frames_kernel(const __gri
     uint32_t role_off = 0, role_len = 0, tool_index = 0; bool active_tool = false;
     aigw_usage usage; memset(&usage, 0, sizeof usage);
     uint64_t pos = sb; uint32_t carry = 0; bool blocked = false;
+    // data lives at tile[t0 .. t0+filled), t0 < 16 chosen so that shared and global addresses agree modulo 16 (aligned 16-byte staging)
+    uint32_t t0 = (uint32_t)((uintptr_t)(P.bytes + sb) & 15u);
     uint64_t consumed = 0;
     while (!blocked && !status && (pos < se)) {
       const uint32_t room = kTile - carry;
@@ -228,26 +230,24 @@ __global__ void __launch_bounds__(kWarps * 32) bedrock_frames_kernel(const __gri
       {
         const uint8_t* g = P.bytes + pos;
         uint32_t head = (uint32_t)((16 - ((uintptr_t)g & 15)) & 15); if (head > take) head = take;
-        for (uint32_t i = lane; i < head; i += 32) tile[carry + i] = g[i];
+        uint8_t* dst = tile + t0 + carry;
+        for (uint32_t i = lane; i < head; i += 32) dst[i] = g[i];
         const uint32_t body = (take - head) & ~15u;
         const uint4* g4 = (const uint4*)(g + head);
-        for (uint32_t i = lane; i < (body >> 4); i += 32) {
-          uint4 v = __ldg(g4 + i);
-          uint8_t* d = tile + carry + head + (i << 4);
-          if ((((uintptr_t)d) & 15) == 0) *(uint4*)d = v;
-          else { const uint8_t* b = (const uint8_t*)&v; for (int k = 0; k < 16; k++) d[k] = b[k]; }
-        }
-        for (uint32_t i = head + body + lane; i < take; i += 32) tile[carry + i] = g[i];
+        uint4* d4 = (uint4*)(dst + head);
+        for (uint32_t i = lane; i < (body >> 4); i += 32) d4[i] = __ldg(g4 + i);
+        for (uint32_t i = head + body + lane; i < take; i += 32) dst[i] = g[i];
       }
       __syncwarp();
       const uint32_t filled = carry + take;
-      const uint32_t tile_rel = (uint32_t)(pos - carry - sb);  // stream-relative offset of tile[0]
+      const uint32_t tile_rel = (uint32_t)(pos - carry - sb) - t0;  // stream-relative offset of tile[0] (wraps consistently)
       pos += take;
       // ---- lane 0: frame chain (prelude length + prelude CRC), eventstream decoder order of checks
       uint32_t nf = 0, end = 0, chain = 0;  // chain: 0 ran out of bytes, 1 blocked by a bad prelude, 2 frame larger than the tile
       if (lane == 0) {
-        uint32_t i = 0;
-        while (i + 12 <= filled) {
+        uint32_t i = t0;
+        const uint32_t hi = t0 + filled;
+        while (i + 12 <= hi) {
           const uint8_t* f = tile + i;
           const uint32_t total = be32(f), hlen = be32(f + 4);
           uint32_t c = 0xffffffffu;
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kWarps * 32) bedrock_frames_kernel(const __gri
           if (~c != be32(f + 8)) { chain = 1; break; }
           if (hlen > 128u * 1024u || total < 16u || hlen > total - 16u || total - hlen - 16u > 16u * 1024u * 1024u) { chain = 1; break; }
           if (total > (uint32_t)kTile) { chain = 2; break; }
-          if (i + total > filled) break;
+          if (i + total > hi) break;
           fstart[nf++] = (uint16_t)i; i += total;
         }
         end = i;
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(kWarps * 32) bedrock_frames_kernel(const __gri
         const uint32_t livem = badm ? ((1u << (__ffs(badm) - 1)) - 1u) : FULLM;
         const bool live = have && ((livem >> lane) & 1u);
         if (!live) { kind = KD_NONE; has_usage = false; decl = 0; }
-        if (badm) { blocked = true; consumed = (uint64_t)tile_rel + fstart[f0 + __ffs(badm) - 1]; }
+        if (badm) { blocked = true; consumed = (uint64_t)(uint32_t)(tile_rel + fstart[f0 + __ffs(badm) - 1]); }
         if (__any_sync(FULLM, decl != 0)) { status = AIGW_DECLINED; reason = AIGW_R_UNSUPPORTED_FIELD; break; }
         // ---- stream state in event order: role of the latest messageStart, tool-call index
         const uint32_t startm = __ballot_sync(FULLM, kind == KD_MSGSTART);
@@ -407,19 +407,25 @@ __global__ void __launch_bounds__(kWarps * 32) bedrock_frames_kernel(const __gri
         out_total += ol;
       }
       if (blocked || status) break;
-      if (chain == 1) { blocked = true; consumed = (uint64_t)tile_rel + end; break; }
+      if (chain == 1) { blocked = true; consumed = (uint64_t)(uint32_t)(tile_rel + end); break; }
       if (chain == 2) { status = AIGW_DECLINED; reason = AIGW_R_TOO_LARGE; break; }
-      // ---- carry the incomplete frame to the front of the tile
-      const uint32_t rem = filled - end;
-      consumed = (uint64_t)tile_rel + end;
-      if (end) {
-        for (uint32_t b = 0; b < rem; b += 32) {
-          const uint32_t i = b + lane;
-          uint8_t c = 0; if (i < rem) c = tile[end + i];
-          __syncwarp();
-          if (i < rem) tile[i] = c;
+      // ---- carry the incomplete frame to the front of the tile, at the offset that keeps the staging aligned
+      const uint32_t rem = t0 + filled - end;
+      consumed = (uint64_t)(uint32_t)(tile_rel + end);
+      if (end != t0) {
+        const uint32_t nt0 = (uint32_t)(((uintptr_t)(P.bytes + pos) - rem) & 15u);
+        if (rem && nt0 != end) {
+          const uint32_t nchunk = (rem + 31u) >> 5;
+          for (uint32_t k = 0; k < nchunk; k++) {
+            const uint32_t ck = nt0 <= end ? k : nchunk - 1u - k;
+            const uint32_t i = (ck << 5) + lane;
+            uint8_t c = 0; if (i < rem) c = tile[end + i];
+            __syncwarp();
+            if (i < rem) tile[nt0 + i] = c;
+            __syncwarp();
+          }
         }
-        __syncwarp();
+        t0 = nt0;
       }
       carry = rem;
     }
@@ -511,7 +517,7 @@ void bedrock_work_layout(BedrockStreamParams& P, uint8_t* work, uint32_t n_strea
 
 cudaError_t launch_bedrock_stream(const BedrockStreamParams& P, int sm_count, cudaStream_t st) {
   static bool ready = false; static int bps_a = 1, bps_b = 1;
-  const size_t smem_a = ((sizeof(BedrockSchema) + 15) & ~15u) + 1024 + (size_t)kWarps * (kTile + 16 + kMaxFrames * 2);
+  const size_t smem_a = ((sizeof(BedrockSchema) + 15) & ~15u) + 1024 + (size_t)kWarps * (kTile + 32 + kMaxFrames * 2);
   const size_t smem_b = (size_t)kEmitWarps * (kOutTile + 32);
   if (!ready) {
     BedrockSchema b = build_schema();
