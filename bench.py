@@ -96,6 +96,10 @@ def cpu_oracle_rate(arena, offs, lens, n_sample, threads):
     return n / sec, n, int(tot.value)
 
 
+# DRAM traffic per body of the three stages, from the ncu --set full captures named in profiles/r01_chat_final.md
+NCU_DRAM_BYTES_PER_BODY = 16860
+
+
 def host_cores():
     """threads the CPU legs may really use: the scheduler affinity mask, further limited by a cgroup CPU quota when one is set
     (a box can show 128 logical CPUs and still be capped; oversubscribing a quota only adds throttling)"""
@@ -255,7 +259,9 @@ def main():
                            "bodies_per_gpu_per_step": n, "mean_in_bytes": float(lens.mean()), "mean_out_bytes": out_bytes / max(1, n_ok), "accepted": n_ok, "declined": n - n_ok,
                            "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB in + {out_bytes / 1e6:.0f} MB out per step vs 126 MB L2)", "sharding": "hash(request-id)→device, no collective",
                            "wall_ms_per_step_incl_launch": wall_max / a.steps * 1e3},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_BODY * n, "peak_source": peak_src,
+                             "traffic_source": "ncu --set full captures of one 131072-body launch of each stage (profiles/r01_chat_final.md): dram read+write per body "
+                                               "index 4.50 KB + walk 3.03 KB + emit 9.33 KB = 16.86 KB, i.e. 2.0x the algorithmic 8.25 KB (the body is read by index and again by emit)",
                              "kernel": "chat_index_kernel + chat_walk_kernel + chat_emit_kernel (the three stages of one translate pass)",
                              "algorithmic_bytes_per_step": alg_bytes, "avg_step_ms": dev_s / a.steps * 1e3,
                              "stage_ms_per_step": {"index": stage[0] / a.steps, "walk": stage[1] / a.steps, "emit": stage[2] / a.steps},
