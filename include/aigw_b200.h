@@ -95,7 +95,10 @@ typedef struct aigw_backend_cfg {
  * (bit0 input, bit1 output, bit2 total, bit3 cached, bit4 cache_creation, bit5 reasoning). */
 typedef struct aigw_usage { uint32_t input, output, total, cached, cache_creation, reasoning, mask, _pad; } aigw_usage;
 
-/* ---- lifecycle ---- */
+/* ---- lifecycle ----
+ * One context per GPU and per calling thread: a context owns its streams, pinned arenas and workspaces and is NOT thread-safe;
+ * the views a host-buffer call returns (results / out pointers) stay valid until the next host-buffer call on that context.
+ * aigw_batcher_* is the one entry point meant to be called concurrently. */
 int  aigw_init(int device, aigw_ctx** ctx);          /* returns 0, or a CUDA error code; never falls back */
 void aigw_destroy(aigw_ctx* ctx);
 const char* aigw_last_error(aigw_ctx* ctx);
