@@ -1840,11 +1840,11 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
         while (o) {
           const int j = __ffs(o) - 1; o &= o - 1;
           const uint32_t c = s_in[base + j];
-          // 128-bit bitmaps: whitespace {09,0A,0D,20}, structural {2C,3A,5B,5D,7B,7D}
-          const uint64_t lo = c < 64u, sel = 1ull << (c & 63u);
-          const bool ws_ = lo && (sel & 0x0000000100002600ull);
-          const bool op_ = c < 128u && (sel & (lo ? 0x0400100000000000ull : 0x2800000028000000ull));
-          if (op_) mtok |= 1u << j; else if (!ws_) msc |= 1u << j;
+          // class LUT in shared memory: 0 scalar character, 1 whitespace, 2 structural (quotes never reach this loop)
+          const uint32_t cl = s_cls[c];
+          const uint32_t bit = 1u << j;
+          mtok |= cl == 2u ? bit : 0u;
+          msc |= cl == 0u ? bit : 0u;
         }
       }
       {
