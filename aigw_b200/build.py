@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libaigw_b200.so")
-SOURCES = ["lib.cu", "chat_kernel.cu", "sse_kernel.cu", "bedrock_stream_kernel.cu", "mutate_kernel.cu", "batcher.cu", "sha256_kernel.cu", "cel_kernel.cu"]
+SOURCES = ["lib.cu", "chat_kernel.cu", "chat_walk.cu", "sse_kernel.cu", "bedrock_stream_kernel.cu", "mutate_kernel.cu", "batcher.cu", "sha256_kernel.cu", "cel_kernel.cu"]
 
 
 def nvcc():
@@ -20,7 +20,7 @@ def needs_build():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "aigw_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))] + [os.path.join(HERE, "..", "include", "aigw_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

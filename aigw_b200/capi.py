@@ -25,7 +25,7 @@ assert MutResult.itemsize == 16
 
 EXPORTS = ["aigw_version", "aigw_init", "aigw_destroy", "aigw_last_error", "aigw_device_sm_count", "aigw_host_alloc", "aigw_host_free",
            "aigw_device_alloc", "aigw_device_free", "aigw_memcpy_h2d", "aigw_memcpy_d2h", "aigw_memset_d", "aigw_sync",
-           "aigw_chat_translate_device", "aigw_chat_translate_device_mapped", "aigw_chat_last_profile", "aigw_chat_translate_host", "aigw_sse_usage_device", "aigw_sse_usage_host", "aigw_response_usage_device", "aigw_response_usage_host", "aigw_embeddings_response_usage_device", "aigw_embeddings_response_usage_host", "aigw_usage_costs_device",
+           "aigw_chat_translate_device", "aigw_chat_translate_device_mapped", "aigw_chat_last_profile", "aigw_chat_set_profile", "aigw_chat_translate_host", "aigw_sse_usage_device", "aigw_sse_usage_host", "aigw_response_usage_device", "aigw_response_usage_host", "aigw_embeddings_response_usage_device", "aigw_embeddings_response_usage_host", "aigw_usage_costs_device",
            "aigw_bedrock_stream_device", "aigw_bedrock_stream_host", "aigw_body_mutate_device", "aigw_body_mutate_host",
            "aigw_cost_compile", "aigw_cost_program_free", "aigw_usage_costs_cel_device", "aigw_usage_costs_cel_host", "aigw_sha256_device", "aigw_chat_body_sha256_device", "aigw_sha256_host", "aigw_batcher_start", "aigw_batcher_translate", "aigw_batcher_get_stats", "aigw_batcher_stop"]
 
@@ -98,6 +98,7 @@ def load_library():
     L.aigw_chat_translate_device_mapped.argtypes = [C.c_void_p, C.POINTER(BackendCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
                                                     C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
     L.aigw_chat_last_profile.argtypes = [C.c_void_p, C.POINTER(C.c_float * 3), C.POINTER(C.c_int)]
+    L.aigw_chat_set_profile.argtypes = [C.c_void_p, C.c_int]
     L.aigw_chat_translate_host.argtypes = [C.c_void_p, C.POINTER(BackendCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(_BatchOut)]
     L.aigw_sse_usage_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
     L.aigw_sse_usage_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64),
@@ -247,6 +248,9 @@ class Context:
         self._check(self.L.aigw_chat_translate_device_mapped(self.h, C.byref(cfg), d_bodies, d_offs, d_lens, d_map, first, count, max_len, d_out, out_cap, d_res, d_used, None,
                                                             C.byref(ms) if timed else None), "chat_translate_device_mapped")
         return ms.value
+
+    def chat_set_profile(self, on):
+        self.L.aigw_chat_set_profile(self.h, 1 if on else 0)
 
     def chat_last_profile(self):
         ms = (C.c_float * 3)()

@@ -215,13 +215,20 @@ struct Cls {
   static constexpr int kWarpBytes = kIn + kTok * 6 + (kOps + kSysCap) * 4 + kOps * 4 + kScr;
 };
 
-// Workspace: chat_work_bytes(max_len, docs_per_sub_batch) bytes hold one sub-batch of intermediates; the launcher
-// walks P.n documents in sub-batches that fit `work_cap` (3 launches per sub-batch).  `counters`: ≥ 64 device uints.
+// Workspace: chat_work_bytes(max_len, docs_per_sub_batch) bytes hold one sub-batch of intermediates; the launcher walks P.n
+// documents in sub-batches (4 launches each).  With `aux` (two extra streams + events, owned by the context) consecutive
+// sub-batches alternate between the two streams and two halves of the workspace: chat_work_bytes_for(max_len, n) is the size
+// that lets a call of n documents do so.  `stage_events` (profiling) forces one stream with the stages back to back.
+// Per-device kernel attributes are configured on first use of each (device, size class).
+static constexpr int kMaxDevices = 16;
+static constexpr int kChatStreams = 4;
+struct ChatAux { cudaStream_t s[kChatStreams]; cudaEvent_t fork, join[kChatStreams]; };
 size_t chat_work_bytes(uint32_t max_len, size_t ndocs);
-cudaError_t launch_chat_translate(const ChatParams& P, uint32_t max_len, int sm_count, cudaStream_t st, uint8_t* work, size_t work_cap,
-                                  unsigned int* counters, int* launches, cudaEvent_t* stage_events, int stage_event_cap, uint32_t first = 0);
+size_t chat_work_bytes_for(uint32_t max_len, size_t n);
+cudaError_t launch_chat_translate(const ChatParams& P, uint32_t max_len, int device, int sm_count, cudaStream_t st, uint8_t* work, size_t work_cap, const ChatAux* aux, int* launches,
+                                  cudaEvent_t* stage_events, int stage_event_cap, uint32_t first = 0);
 // documents [first, first+count): offsets / lens / results are indexed with the global document number
-cudaError_t launch_chat_translate_range(const ChatParams& P, uint32_t first, uint32_t count, uint32_t max_len, int sm_count, cudaStream_t st, uint8_t* work,
-                                        size_t work_cap, unsigned int* counters, int* launches);
+cudaError_t launch_chat_translate_range(const ChatParams& P, uint32_t first, uint32_t count, uint32_t max_len, int device, int sm_count, cudaStream_t st, uint8_t* work,
+                                        size_t work_cap, const ChatAux* aux, int* launches);
 
 }  // namespace aigw

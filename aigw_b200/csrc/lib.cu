@@ -50,6 +50,8 @@ struct aigw_ctx {
   uint8_t* d_work = nullptr; size_t work_cap = 0;
   unsigned long long* d_used_arr = nullptr; unsigned long long* h_used_arr = nullptr; size_t used_cap = 0;  // per-chunk bump counters
   cudaEvent_t stage_ev[64]; float stage_ms[3] = {0, 0, 0}; int last_launches = 0;
+  bool profile_stages = false;   // aigw_chat_set_profile: next device calls run the stages back to back on one stream and time them
+  ChatAux aux{};                 // two extra streams: sub-batches of one call alternate between them
   // sse host-API device buffers
   uint8_t* d_sse_bytes = nullptr; size_t sse_bytes_cap = 0;
   uint64_t* d_sse_coff = nullptr; size_t sse_coff_cap = 0;
@@ -117,19 +119,23 @@ int aigw_init(int device, aigw_ctx** out) {
   if (e != cudaSuccess) { delete ctx; return (int)e; }
   ctx->sm_count = prop.multiProcessorCount;
   if (prop.major < 10) { fprintf(stderr, "aigw_init: device %d is sm_%d%d; this library is built for sm_100a only\n", device, prop.major, prop.minor); delete ctx; return (int)cudaErrorNoKernelImageForDevice; }
-  cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
-  cudaMalloc(&ctx->d_counters, 256 * sizeof(unsigned int));
-  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
-  for (auto& e2 : ctx->stage_ev) cudaEventCreate(&e2);
+  // every allocation is checked on its own: a half-built context is destroyed, never returned
+  auto fail = [&](const char* what, cudaError_t err) { fprintf(stderr, "aigw_init: %s: %s\n", what, cudaGetErrorString(err)); aigw_destroy(ctx); return (int)err; };
+#define INIT_CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return fail(#x, _e); } while (0)
+  INIT_CK(cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
+  INIT_CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+  INIT_CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+  for (int k = 0; k < kChatStreams; k++) { INIT_CK(cudaStreamCreateWithFlags(&ctx->aux.s[k], cudaStreamNonBlocking)); INIT_CK(cudaEventCreateWithFlags(&ctx->aux.join[k], cudaEventDisableTiming)); }
+  INIT_CK(cudaEventCreateWithFlags(&ctx->aux.fork, cudaEventDisableTiming));
+  INIT_CK(cudaMalloc(&ctx->d_counters, 256 * sizeof(unsigned int)));
+  INIT_CK(cudaEventCreate(&ctx->ev0)); INIT_CK(cudaEventCreate(&ctx->ev1));
+  for (auto& e2 : ctx->stage_ev) INIT_CK(cudaEventCreate(&e2));
   for (auto& s : ctx->slot) {
-    cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming); cudaEventCreate(&s.ev_k0); cudaEventCreate(&s.ev_k1);
-    cudaEventCreateWithFlags(&s.ev_ctr, cudaEventDisableTiming); cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming);
-    cudaMalloc(&s.d_used, 8); cudaMalloc(&s.d_next, 4); cudaHostAlloc(&s.h_used, 8, cudaHostAllocDefault);
+    INIT_CK(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming)); INIT_CK(cudaEventCreate(&s.ev_k0)); INIT_CK(cudaEventCreate(&s.ev_k1));
+    INIT_CK(cudaEventCreateWithFlags(&s.ev_ctr, cudaEventDisableTiming)); INIT_CK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    INIT_CK(cudaMalloc(&s.d_used, 8)); INIT_CK(cudaMalloc(&s.d_next, 4)); INIT_CK(cudaHostAlloc(&s.h_used, 8, cudaHostAllocDefault));
   }
-  e = cudaGetLastError();
-  if (e != cudaSuccess) { fprintf(stderr, "aigw_init: %s\n", cudaGetErrorString(e)); delete ctx; return (int)e; }
+#undef INIT_CK
   *out = ctx;
   return 0;
 }
@@ -147,25 +153,28 @@ void aigw_destroy(aigw_ctx* ctx) {
   cudaFree(ctx->d_sse_bytes); cudaFree(ctx->d_sse_coff); cudaFree(ctx->d_sse_first); cudaFree(ctx->d_sse_res); cudaFree(ctx->d_bs_work); cudaFree(ctx->d_bs_off[0]); cudaFree(ctx->d_bs_off[1]); cudaFreeHost(ctx->h_sres); cudaFreeHost(ctx->h_mres);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->s_compute); cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
+  for (int k = 0; k < kChatStreams; k++) { if (ctx->aux.s[k]) cudaStreamDestroy(ctx->aux.s[k]); if (ctx->aux.join[k]) cudaEventDestroy(ctx->aux.join[k]); }
+  if (ctx->aux.fork) cudaEventDestroy(ctx->aux.fork);
   delete ctx;
 }
 
 const char* aigw_last_error(aigw_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 int aigw_device_sm_count(aigw_ctx* ctx) { return ctx->sm_count; }
 
-void* aigw_host_alloc(aigw_ctx* ctx, size_t bytes) { void* p = nullptr; if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { ctx->err = "cudaHostAlloc failed"; return nullptr; } return p; }
+void* aigw_host_alloc(aigw_ctx* ctx, size_t bytes) { void* p = nullptr; cudaSetDevice(ctx->device); if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { ctx->err = "cudaHostAlloc failed"; return nullptr; } return p; }
 void aigw_host_free(aigw_ctx*, void* p) { cudaFreeHost(p); }
-void* aigw_device_alloc(aigw_ctx* ctx, size_t bytes) { void* p = nullptr; if (cudaMalloc(&p, bytes) != cudaSuccess) { ctx->err = "cudaMalloc failed"; return nullptr; } return p; }
-void aigw_device_free(aigw_ctx*, void* p) { cudaFree(p); }
-int aigw_memcpy_h2d(aigw_ctx* ctx, void* dst, const void* src, size_t bytes) { CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); return 0; }
-int aigw_memcpy_d2h(aigw_ctx* ctx, void* dst, const void* src, size_t bytes) { CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return 0; }
-int aigw_memset_d(aigw_ctx* ctx, void* dst, int v, size_t bytes) { CK(cudaMemset(dst, v, bytes)); return 0; }
-int aigw_sync(aigw_ctx* ctx) { CK(cudaDeviceSynchronize()); return 0; }
+void* aigw_device_alloc(aigw_ctx* ctx, size_t bytes) { void* p = nullptr; cudaSetDevice(ctx->device); if (cudaMalloc(&p, bytes) != cudaSuccess) { ctx->err = "cudaMalloc failed"; return nullptr; } return p; }
+void aigw_device_free(aigw_ctx* ctx, void* p) { cudaSetDevice(ctx->device); cudaFree(p); }
+int aigw_memcpy_h2d(aigw_ctx* ctx, void* dst, const void* src, size_t bytes) { CK(cudaSetDevice(ctx->device)); CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); return 0; }
+int aigw_memcpy_d2h(aigw_ctx* ctx, void* dst, const void* src, size_t bytes) { CK(cudaSetDevice(ctx->device)); CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return 0; }
+int aigw_memset_d(aigw_ctx* ctx, void* dst, int v, size_t bytes) { CK(cudaSetDevice(ctx->device)); CK(cudaMemset(dst, v, bytes)); return 0; }
+int aigw_sync(aigw_ctx* ctx) { CK(cudaSetDevice(ctx->device)); CK(cudaDeviceSynchronize()); return 0; }
 
 static int chat_translate_device_impl(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const uint8_t* d_bodies, const uint64_t* d_offsets,
                                       const uint32_t* d_lens, const uint32_t* d_doc_map, uint32_t first, uint32_t n, uint32_t max_len, uint8_t* d_out, uint64_t out_capacity,
                                       aigw_doc_result* d_results, uint64_t* d_out_used, void* stream, float* kernel_ms) {
   if (n == 0) { if (kernel_ms) *kernel_ms = 0; return 0; }
+  CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->s_compute;
   ChatParams P;
   fill_params(P, cfg);
@@ -174,20 +183,22 @@ static int chat_translate_device_impl(aigw_ctx* ctx, const aigw_backend_cfg* cfg
   P.next_doc = nullptr; P.out_bias = 0; P.doc_map = d_doc_map;
   uint32_t ml = max_len ? max_len : 65536u;
   if (cfg && (cfg->schema & 48) == AIGW_SCHEMA_RESP_AWS_BEDROCK) ml = resp_class_len(ml);
-  {  // workspace for one sub-batch (≤ 128 Ki documents); the launcher loops over sub-batches
-    const size_t sub = n < 131072u ? n : 131072u;
-    size_t need = chat_work_bytes(ml, sub);
+  const bool stages = ctx->profile_stages && kernel_ms;
+  {  // workspace: two sub-batches in flight (one per auxiliary stream); profiling runs one large sub-batch at a time
+    size_t need = chat_work_bytes_for(ml, n);
     const size_t cap = (size_t)3 << 30, floor1 = chat_work_bytes(ml, 1024);
     if (need > cap) need = cap > floor1 ? cap : floor1;
     ENSURE(ctx->d_work, ctx->work_cap, need, false);
   }
   if (kernel_ms) CK(cudaEventRecord(ctx->ev0, st));
-  CK(launch_chat_translate(P, ml, ctx->sm_count, st, ctx->d_work, ctx->work_cap, ctx->d_counters, &ctx->last_launches, kernel_ms ? ctx->stage_ev : nullptr, 64, first));
+  CK(launch_chat_translate(P, ml, ctx->device, ctx->sm_count, st, ctx->d_work, ctx->work_cap, &ctx->aux, &ctx->last_launches, stages ? ctx->stage_ev : nullptr, 64, first));
   if (kernel_ms) {
     CK(cudaEventRecord(ctx->ev1, st)); CK(cudaEventSynchronize(ctx->ev1)); CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
-    ctx->stage_ms[0] = ctx->stage_ms[1] = ctx->stage_ms[2] = 0;
-    const int nsb = ctx->last_launches / 6;
-    for (int sb = 0; sb < nsb && 4 * sb + 3 < 64; sb++) for (int k = 0; k < 3; k++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->stage_ev[4 * sb + k], ctx->stage_ev[4 * sb + k + 1]); ctx->stage_ms[k] += ms; }
+    if (stages) {
+      ctx->stage_ms[0] = ctx->stage_ms[1] = ctx->stage_ms[2] = 0;
+      const int nsb = ctx->last_launches / 4;
+      for (int sb = 0; sb < nsb && 4 * sb + 3 < 64; sb++) for (int k = 0; k < 3; k++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->stage_ev[4 * sb + k], ctx->stage_ev[4 * sb + k + 1]); ctx->stage_ms[k] += ms; }
+    }
   }
   return 0;
 }
@@ -203,7 +214,9 @@ int aigw_chat_translate_device_mapped(aigw_ctx* ctx, const aigw_backend_cfg* cfg
   return chat_translate_device_impl(ctx, cfg, d_bodies, d_offsets, d_lens, d_doc_map, first, count, max_len, d_out, out_capacity, d_results, d_out_used, stream, kernel_ms);
 }
 
-/* per-stage CUDA-event times (index, walk, emit) and launch count of the last timed aigw_chat_translate_device call */
+int aigw_chat_set_profile(aigw_ctx* ctx, int on) { ctx->profile_stages = on != 0; return 0; }
+
+/* per-stage CUDA-event times (index, walk, emit) of the last profiled call and the launch count of the last device call */
 int aigw_chat_last_profile(aigw_ctx* ctx, float stage_ms[3], int* launches) {
   for (int k = 0; k < 3; k++) stage_ms[k] = ctx->stage_ms[k];
   if (launches) *launches = ctx->last_launches;
@@ -259,7 +272,7 @@ int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const u
   static const uint32_t kClsMax[6] = {2048, 5120, 9216, 17408, 33792, 65536};
   auto cls_of = [&](uint32_t len) { const uint32_t l = resp_dir ? resp_class_len(len) : len; int k = 0; while (k < 5 && l > kClsMax[k]) k++; return k; };
   {
-    size_t need = chat_work_bytes(max_len, max_docs < 131072u ? max_docs : 131072u);
+    size_t need = chat_work_bytes_for(max_len, max_docs);
     const size_t cap = (size_t)3 << 30;   // the launcher walks a class in sub-batches that fit the workspace
     const size_t floor1 = chat_work_bytes(max_len, 1024);
     if (need > cap) need = cap > floor1 ? cap : floor1;
@@ -316,14 +329,14 @@ int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const u
     // documents keep their global index: kernels address offsets/lens/results with doc0 + i (or doc_map[i])
     if (n_cls <= 1) {
       int nl = 0;
-      CK(launch_chat_translate_range(P, b, nd, kClsMax[top_cls], ctx->sm_count, ctx->s_compute, ctx->d_work, ctx->work_cap, ctx->d_counters, &nl));
+      CK(launch_chat_translate_range(P, b, nd, kClsMax[top_cls], ctx->device, ctx->sm_count, ctx->s_compute, ctx->d_work, ctx->work_cap, &ctx->aux, &nl));
       out->gpu_launches += nl;
     } else {
       P.doc_map = S.d_map;
       for (int k = 0; k < 6; k++) {
         if (!cls_cnt[k]) continue;
         int nl = 0;
-        CK(launch_chat_translate_range(P, cls_start[k], cls_cnt[k], kClsMax[k], ctx->sm_count, ctx->s_compute, ctx->d_work, ctx->work_cap, ctx->d_counters, &nl));
+        CK(launch_chat_translate_range(P, cls_start[k], cls_cnt[k], kClsMax[k], ctx->device, ctx->sm_count, ctx->s_compute, ctx->d_work, ctx->work_cap, &ctx->aux, &nl));
         out->gpu_launches += nl;
       }
     }

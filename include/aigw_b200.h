@@ -126,8 +126,6 @@ int aigw_chat_translate_device(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const
                                const uint32_t* d_lens, uint32_t n, uint32_t max_len, uint8_t* d_out, uint64_t out_capacity,
                                aigw_doc_result* d_results, uint64_t* d_out_used, void* stream, float* kernel_ms);
 
-/* CUDA-event time of the three stages (index, walk, emit) and the launch count of the last aigw_chat_translate_device
- * call that passed kernel_ms != NULL. */
 /* Same, over a document map: unit i of the call is document d_doc_map[first + i] (offsets / lens / results keep the document's
  * own index).  Callers with mixed body sizes group documents by size class (≤ 2048, 5120, 9216, 17408, 33792, 65536 bytes) and
  * make one call per class with that class's max_len, so small bodies are not run with the large class's shared-memory
@@ -135,6 +133,11 @@ int aigw_chat_translate_device(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const
 int aigw_chat_translate_device_mapped(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const uint8_t* d_bodies, const uint64_t* d_offsets, const uint32_t* d_lens,
                                       const uint32_t* d_doc_map, uint32_t first, uint32_t count, uint32_t max_len, uint8_t* d_out, uint64_t out_capacity,
                                       aigw_doc_result* d_results, uint64_t* d_out_used, void* stream, float* kernel_ms);
+/* Stage profiling.  A device call normally splits its documents into L2-sized sub-batches that alternate between two internal
+ * streams (the walk of one runs under the index / emit of the other), so per-stage times do not exist.  After
+ * aigw_chat_set_profile(ctx, 1), calls that pass kernel_ms != NULL run the stages back to back on one stream and
+ * aigw_chat_last_profile returns their CUDA-event times (index, walk, emit) and the launch count of the last call. */
+int aigw_chat_set_profile(aigw_ctx* ctx, int on);
 int aigw_chat_last_profile(aigw_ctx* ctx, float stage_ms[3], int* launches);
 
 /* ---- same, HOST buffers (the call the cgo shim makes) ----
