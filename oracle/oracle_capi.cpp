@@ -9,6 +9,7 @@
 
 #include "bedrock_response.hpp"
 #include "bedrock_stream.hpp"
+#include "anthropic_stream.hpp"
 #include "cel.hpp"
 #include "sha256.hpp"
 #include "embeddings.hpp"
@@ -199,6 +200,25 @@ double oracle_bedrock_response_batch(const uint8_t* bodies, const uint64_t* offs
   if (threads <= 1) work(); else { std::vector<std::thread> th; for (int t = 0; t < threads; t++) th.emplace_back(work); for (auto& t : th) t.join(); }
   if (total_out) *total_out = tot.load();
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+// ---- S3 / R1 (Anthropic): SSE events → OpenAI SSE, per ResponseBody call; buffered Message → ChatCompletionResponse
+struct AnthropicHandle { AnthropicStreamState st; AnthropicStreamCfg cfg; };
+void* oracle_anthropic_open(const char* request_model, int64_t created) { auto* h = new AnthropicHandle(); h->cfg.request_model = request_model ? request_model : ""; h->cfg.created = created; return h; }
+void oracle_anthropic_close(void* h) { delete (AnthropicHandle*)h; }
+// returns oracle::Status of this call; *out (malloc'd) = the body mutation of this call; usage = the TokenUsage the call returns
+int oracle_anthropic_feed(void* hv, const char* chunk, uint64_t len, int eos, char** out, uint64_t* out_len, oracle_usage* usage) {
+  auto* h = (AnthropicHandle*)hv; std::string o; TokenUsage u;
+  const Status s = anthropic_stream_feed(h->st, h->cfg, std::string_view(chunk, len), eos != 0, o, u);
+  if (s != OK) o.clear();
+  put(usage, u); *out = dup(o); *out_len = o.size();
+  return (int)s;
+}
+int oracle_anthropic_response(const char* body, uint64_t len, const char* request_model, int64_t created, char** out, uint64_t* out_len, oracle_usage* usage, char* model_buf, uint64_t cap, uint64_t* model_len) {
+  AnthropicStreamCfg cfg; cfg.request_model = request_model ? request_model : ""; cfg.created = created;
+  std::string o, rm; TokenUsage u; const Status s = anthropic_response(std::string_view(body, len), cfg, o, u, rm);
+  put(usage, u); *out = dup(o); *out_len = o.size();
+  uint64_t n = std::min<uint64_t>(cap, rm.size()); memcpy(model_buf, rm.data(), n); *model_len = rm.size();
+  return (int)s;
 }
 // ---- B1: body mutation.  removes: n_rm NUL-terminated strings; sets: n_set (path, value) pairs.  Returns 0, or 1 = not restated.
 int oracle_body_mutate(const char* body, uint64_t len, const char* const* removes, uint32_t n_rm, const char* const* set_paths, const char* const* set_values, uint32_t n_set,

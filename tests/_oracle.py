@@ -205,3 +205,32 @@ class Cel:
     def __del__(self):
         if getattr(self, "h", None):
             lib().oracle_cel_free.argtypes = [C.c_void_p]; lib().oracle_cel_free(self.h)
+
+
+class AnthropicStream:
+    """anthropicStreamParser.Process per call (S3): feed(chunk, eos) → (status, body mutation bytes, Usage)."""
+    def __init__(self, request_model: bytes, created: int):
+        L = lib(); L.oracle_anthropic_open.restype = C.c_void_p; L.oracle_anthropic_open.argtypes = [C.c_char_p, C.c_int64]
+        L.oracle_anthropic_feed.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(Usage)]
+        L.oracle_anthropic_close.argtypes = [C.c_void_p]
+        self.h = L.oracle_anthropic_open(request_model, created)
+
+    def feed(self, chunk: bytes, eos: bool):
+        vp = C.c_void_p(); n = C.c_uint64(0); u = Usage()
+        st = lib().oracle_anthropic_feed(self.h, chunk, len(chunk), int(eos), C.byref(vp), C.byref(n), C.byref(u))
+        out = C.string_at(vp, n.value); lib().oracle_free(vp)
+        return st, out, u
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_anthropic_close(self.h); self.h = None
+
+
+def anthropic_response(body: bytes, request_model: bytes, created: int):
+    """Buffered anthropic.Message → (status, ChatCompletionResponse JSON bytes, Usage, response model)."""
+    L = lib()
+    L.oracle_anthropic_response.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(Usage), C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    vp = C.c_void_p(); n = C.c_uint64(0); u = Usage(); buf = C.create_string_buffer(4096); ml = C.c_uint64(0)
+    st = L.oracle_anthropic_response(body, len(body), request_model, created, C.byref(vp), C.byref(n), C.byref(u), buf, 4096, C.byref(ml))
+    out = C.string_at(vp, n.value); L.oracle_free(vp)
+    return st, out, u, buf.raw[:ml.value]

@@ -316,3 +316,71 @@ def test_embeddings_response_usage():
     assert not O.response_embeddings(b'{"data":[{"embedding":{"a":1}}]}')[0]
     assert not O.response_embeddings(b'{"data":[{"embedding":[1,"x"]}]}')[0]
     assert not O.response_embeddings(b'{"usage":{"prompt_tokens":1.5}}')[0]
+
+
+# ---------------------------------------------------------------- S3 / R1 (Anthropic): SSE → OpenAI SSE, Message → ChatCompletion
+ANTHROPIC_STREAM_CASES = ["gcp-anthropicai - /v1/chat/completions - streaming", "gcp-anthropicai - /v1/chat/completions - streaming tool use"]
+
+
+def _sse_blocks(body: str):
+    """the fake upstream's chunking: one write per event block (tests/internal/testupstreamlib/server.go:284-300)"""
+    return [b.encode() + b"\n\n" for b in body.split("\n\n") if b.strip()]
+
+
+@pytest.mark.parametrize("name", ANTHROPIC_STREAM_CASES)
+@pytest.mark.parametrize("chunking", ["blocks", "whole", "bytes"])
+def test_anthropic_stream_dataplane_goldens(name, chunking):
+    """tests/data-plane/testupstream_test.go:575,637 (exact text; created normalised to 123); the result must not depend on the chunking"""
+    c = next(c for c in CASES if c["name"] == name)
+    blocks = _sse_blocks(c["responseBody"])
+    whole = b"".join(blocks)
+    chunks = blocks if chunking == "blocks" else [whole] if chunking == "whole" else [whole[i:i + 1] for i in range(len(whole))]
+    st = O.AnthropicStream(b"claude-3-sonnet", 123)
+    out = b""
+    for i, ch in enumerate(chunks):
+        s, o, u = st.feed(ch, False)
+        assert s == O.OK
+        out += o
+    s, o, u = st.feed(b"", True)
+    assert s == O.OK
+    out += o
+    assert out.decode() == c["expResponseBody"]
+    want = {"gcp-anthropicai - /v1/chat/completions - streaming": (25, 10, 0, 12, 37, -1), "gcp-anthropicai - /v1/chat/completions - streaming tool use": (50, 0, 0, 20, 70, -1)}[name]
+    assert u.as_tuple() == want
+
+
+def test_anthropic_stream_rules():
+    st = O.AnthropicStream(b"m", 7)
+    # ping / unknown events are ignored without a decode; an event without data is ignored
+    s, o, u = st.feed(b"event: ping\ndata: not json\n\nevent: message_start\n\n", False)
+    assert s == O.OK and o == b""
+    # thinking block start emits an empty content with the role; thinking_delta reads delta.text (absent ⇒ "")
+    s, o, u = st.feed(b'event: content_block_start\ndata: {"content_block":{"type":"thinking"}}\n\nevent: content_block_delta\ndata: {"delta":{"type":"thinking_delta","thinking":"x"}}\n\n', False)
+    assert o == (b'data: {"choices":[{"index":0,"delta":{"content":"","role":"assistant"}}],"model":"m","object":"chat.completion.chunk"}\n\n'
+                 b'data: {"choices":[{"index":0,"delta":{"content":""}}],"model":"m","object":"chat.completion.chunk"}\n\n')
+    # input_json_delta without an open tool is a stream error; the stream stays failed
+    s, o, u = st.feed(b'event: content_block_delta\ndata: {"delta":{"type":"input_json_delta","partial_json":"{"}}\n\n', False)
+    assert s == O.INTERNAL
+    assert st.feed(b"", True)[0] == O.INTERNAL
+    # invalid stop reason / error event / bad JSON
+    for ev in (b'event: message_delta\ndata: {"delta":{"stop_reason":"weird"}}\n\nevent: message_stop\ndata: {}\n\n', b'event: error\ndata: {"error":{"type":"overloaded_error","message":"x"}}\n\n',
+               b'event: message_stop\ndata: {\n\n'):
+        assert O.AnthropicStream(b"m", 7).feed(ev, False)[0] == O.INTERNAL
+    # no usage and no choices: only [DONE]; trailing partial event is handled at end of stream
+    s, o, u = O.AnthropicStream(b"m", 7).feed(b'event: message_stop\ndata: {}', True)
+    assert s == O.OK and o == b'data: {"choices":[{"index":0,"delta":{},"finish_reason":"stop"}],"model":"m","object":"chat.completion.chunk"}\n\ndata: [DONE]\n\n'
+
+
+def test_anthropic_response_goldens():
+    """buffered GCP Anthropic responses (JSONEq in the reference, tests/data-plane/testupstream_test.go:1473-1482)"""
+    n = 0
+    for c in CASES:
+        if c.get("backend") != "gcp-anthropicai" or c.get("responseType") or "expResponseBody" not in c or "/v1/chat/completions" not in c["name"] or "error" in c["name"] or "missing" in c["name"]:
+            continue
+        st, out, u, model = O.anthropic_response(c["responseBody"].encode(), json.loads(c["requestBody"])["model"].encode(), 123)
+        assert st == O.OK, c["name"]
+        got = json.loads(out); exp = json.loads(c["expResponseBody"])
+        got["created"] = exp.get("created", got["created"])
+        assert got == exp, c["name"]
+        n += 1
+    assert n >= 2
