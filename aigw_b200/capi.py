@@ -16,6 +16,21 @@ assert DocResult.itemsize == 32
 SseResult = np.dtype([("input", "<u4"), ("output", "<u4"), ("total", "<u4"), ("cached", "<u4"), ("cache_creation", "<u4"), ("reasoning", "<u4"),
                       ("mask", "<u4"), ("_pad", "<u4"), ("model_off", "<u8"), ("model_len", "<u4"), ("status", "<u4")])
 assert SseResult.itemsize == 48
+ChunkResult = np.dtype([("out_off", "<u8"), ("out_len", "<u4"), ("status", "u1"), ("body_kind", "u1"), ("reason", "u1"), ("_pad", "u1"),
+                        ("input", "<u4"), ("output", "<u4"), ("total", "<u4"), ("cached", "<u4"), ("cache_creation", "<u4"), ("reasoning", "<u4"), ("mask", "<u4"), ("_upad", "<u4"),
+                        ("model_len", "<u4"), ("carry_len", "<u4"), ("_reserved", "<u8")])
+assert ChunkResult.itemsize == 64
+STREAM_KIND = {"openai": 0, "aws-bedrock": 1, "gcp-anthropicai": 2}
+
+
+class StreamCfg(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("created", C.c_int64), ("request_model", C.c_char_p), ("response_id", C.c_char_p)]
+
+
+class ChunkIn(C.Structure):
+    _fields_ = [("handle", C.c_uint64), ("bytes", C.c_void_p), ("len", C.c_uint32), ("eos", C.c_uint32)]
+
+
 StreamResult = np.dtype([("out_off", "<u8"), ("out_len", "<u4"), ("status", "<u4"),
                          ("input", "<u4"), ("output", "<u4"), ("total", "<u4"), ("cached", "<u4"), ("cache_creation", "<u4"), ("reasoning", "<u4"), ("mask", "<u4"), ("_pad", "<u4"),
                          ("consumed", "<u8"), ("n_chunks", "<u4"), ("reason", "<u4")])
@@ -23,7 +38,8 @@ assert StreamResult.itemsize == 64
 MutResult = np.dtype([("out_off", "<u8"), ("out_len", "<u4"), ("status", "u1"), ("reason", "u1"), ("flags", "<u2")])
 assert MutResult.itemsize == 16
 
-EXPORTS = ["aigw_version", "aigw_init", "aigw_destroy", "aigw_last_error", "aigw_device_sm_count", "aigw_host_alloc", "aigw_host_free",
+EXPORTS = ["aigw_stream_open", "aigw_stream_open_batch", "aigw_stream_chunks", "aigw_stream_chunk", "aigw_stream_close", "aigw_stream_close_batch",
+           "aigw_version", "aigw_init", "aigw_destroy", "aigw_last_error", "aigw_device_sm_count", "aigw_host_alloc", "aigw_host_free",
            "aigw_device_alloc", "aigw_device_free", "aigw_memcpy_h2d", "aigw_memcpy_d2h", "aigw_memset_d", "aigw_sync",
            "aigw_chat_translate_device", "aigw_chat_translate_device_mapped", "aigw_chat_last_profile", "aigw_chat_set_profile", "aigw_chat_translate_host", "aigw_sse_usage_device", "aigw_sse_usage_host", "aigw_response_usage_device", "aigw_response_usage_host", "aigw_embeddings_response_usage_device", "aigw_embeddings_response_usage_host", "aigw_usage_costs_device",
            "aigw_bedrock_stream_device", "aigw_bedrock_stream_host", "aigw_body_mutate_device", "aigw_body_mutate_host",
@@ -257,6 +273,53 @@ class Context:
         nl = C.c_int(0)
         self.L.aigw_chat_last_profile(self.h, C.byref(ms), C.byref(nl))
         return {"index_ms": ms[0], "walk_ms": ms[1], "emit_ms": ms[2], "launches": nl.value}
+
+    # ---- stateful per-chunk response streams
+    def stream_open(self, kind, request_model=b"", response_id=b"", created=0, n=1):
+        cfg = StreamCfg(STREAM_KIND[kind] if isinstance(kind, str) else kind, 0, created, request_model, response_id)
+        hs = (C.c_uint64 * n)()
+        self.L.aigw_stream_open_batch.argtypes = [C.c_void_p, C.POINTER(StreamCfg), C.c_uint32, C.c_void_p]
+        self._check(self.L.aigw_stream_open_batch(self.h, C.byref(cfg), n, hs), "stream_open_batch")
+        return list(hs)
+
+    def stream_chunks(self, handles, chunks, eos):
+        """one ResponseBody call per listed stream; returns a list of dicts (status, body_kind, reason, body, model, usage tuple, carry_len)"""
+        n = len(handles)
+        arr = (ChunkIn * n)()
+        keep = []
+        for i in range(n):
+            b = bytes(chunks[i]); buf = C.create_string_buffer(b, len(b)) if b else None; keep.append(buf)
+            arr[i].handle = handles[i]; arr[i].bytes = C.cast(buf, C.c_void_p).value if buf is not None else None; arr[i].len = len(b); arr[i].eos = 1 if eos[i] else 0
+        res = np.zeros(n, dtype=ChunkResult)
+        arena = C.c_void_p()
+        self.L.aigw_stream_chunks.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]
+        self._check(self.L.aigw_stream_chunks(self.h, arr, n, res.ctypes.data, C.byref(arena)), "stream_chunks")
+        out = []
+        for r in res:
+            tot = int(r["out_len"]) + int(r["model_len"])
+            raw = C.string_at(arena.value + int(r["out_off"]), tot) if tot else b""
+            m = int(r["mask"])
+            usage = (int(r["input"]) if m & 1 else -1, int(r["cached"]) if m & 8 else -1, int(r["cache_creation"]) if m & 16 else -1,
+                     int(r["output"]) if m & 2 else -1, int(r["total"]) if m & 4 else -1, int(r["reasoning"]) if m & 32 else -1)
+            out.append({"status": int(r["status"]), "body_kind": int(r["body_kind"]), "reason": int(r["reason"]), "body": raw[: int(r["out_len"])], "model": raw[int(r["out_len"]):],
+                        "usage": usage, "carry_len": int(r["carry_len"])})
+        return out
+
+    def stream_chunk(self, handle, chunk, eos):
+        b = bytes(chunk); out = C.create_string_buffer(1 << 20); res = np.zeros(1, dtype=ChunkResult)
+        self.L.aigw_stream_chunk.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p]
+        self._check(self.L.aigw_stream_chunk(self.h, handle, b, len(b), 1 if eos else 0, out, 1 << 20, res.ctypes.data), "stream_chunk")
+        r = res[0]; m = int(r["mask"])
+        usage = (int(r["input"]) if m & 1 else -1, int(r["cached"]) if m & 8 else -1, int(r["cache_creation"]) if m & 16 else -1,
+                 int(r["output"]) if m & 2 else -1, int(r["total"]) if m & 4 else -1, int(r["reasoning"]) if m & 32 else -1)
+        raw = out.raw[: int(r["out_len"]) + int(r["model_len"])]
+        return {"status": int(r["status"]), "body_kind": int(r["body_kind"]), "reason": int(r["reason"]), "body": raw[: int(r["out_len"])], "model": raw[int(r["out_len"]):], "usage": usage,
+                "carry_len": int(r["carry_len"])}
+
+    def stream_close(self, handles):
+        arr = (C.c_uint64 * len(handles))(*handles)
+        self.L.aigw_stream_close_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        return self.L.aigw_stream_close_batch(self.h, arr, len(handles))
 
     # ---- SSE usage
     def sse_usage_host(self, bytes_arr, chunk_off, chunk_first):

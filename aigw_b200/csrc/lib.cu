@@ -14,6 +14,9 @@
 #include "mutate_kernel.cuh"
 #include "sha256_kernel.cuh"
 #include "cel_kernel.cuh"
+#include "stream_kernel.cuh"
+
+#include <mutex>
 
 using namespace aigw;
 
@@ -22,6 +25,7 @@ struct aigw_cost_program { aigw::CelProgramHost h; };
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(_e); return (int)_e; } } while (0)
 
 static constexpr int kSlots = 3;
+static bool plain_json_text(const char* s) { for (; *s; s++) { unsigned char c = (unsigned char)*s; if (c < 0x20 || c > 0x7e || c == '"' || c == '\\') return false; } return true; }
 
 struct ChunkSlot {
   uint8_t* d_in = nullptr; size_t in_cap = 0;
@@ -63,6 +67,18 @@ struct aigw_ctx {
   aigw_stream_result* h_sres = nullptr; size_t h_sres_cap = 0;
   aigw_mut_result* h_mres = nullptr; size_t h_mres_cap = 0;
   std::vector<uint32_t> h_map;   // size-class bucketing scratch (host)
+  // ---- stateful response streams (aigw_stream_*): device-resident slots + per-call staging
+  struct StreamPool {
+    std::mutex mu;
+    StreamSlot* d_slots = nullptr; uint32_t cap = 0;
+    std::vector<uint32_t> free_list, carry, gen, stamp; std::vector<uint8_t> open; uint32_t call_no = 0;
+    uint8_t* h_in = nullptr; size_t h_in_cap = 0; uint8_t* d_in = nullptr; size_t d_in_cap = 0;
+    StreamStep* h_steps = nullptr; size_t h_steps_cap = 0; StreamStep* d_steps = nullptr; size_t d_steps_cap = 0;
+    aigw_chunk_result* d_res = nullptr; size_t d_res_cap = 0; aigw_chunk_result* h_res = nullptr; size_t h_res_cap = 0;
+    uint8_t* d_out = nullptr; size_t d_out_cap = 0; uint8_t* d_packed = nullptr; size_t d_packed_cap = 0; uint8_t* h_packed = nullptr; size_t h_packed_cap = 0;
+    unsigned long long* d_used = nullptr; unsigned long long* h_used = nullptr;
+    uint8_t* d_tmpl = nullptr; uint32_t* d_ids = nullptr; size_t d_ids_cap = 0; uint32_t* h_ids = nullptr; size_t h_ids_cap = 0;
+  } sp;
 };
 
 // response bodies expand (escaped tool arguments, configuration text): plan them in a roomier size class
@@ -153,6 +169,11 @@ void aigw_destroy(aigw_ctx* ctx) {
   cudaFree(ctx->d_sse_bytes); cudaFree(ctx->d_sse_coff); cudaFree(ctx->d_sse_first); cudaFree(ctx->d_sse_res); cudaFree(ctx->d_bs_work); cudaFree(ctx->d_bs_off[0]); cudaFree(ctx->d_bs_off[1]); cudaFreeHost(ctx->h_sres); cudaFreeHost(ctx->h_mres);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->s_compute); cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
+  {
+    auto& sp = ctx->sp;
+    cudaFree(sp.d_slots); cudaFreeHost(sp.h_in); cudaFree(sp.d_in); cudaFreeHost(sp.h_steps); cudaFree(sp.d_steps); cudaFree(sp.d_res); cudaFreeHost(sp.h_res);
+    cudaFree(sp.d_out); cudaFree(sp.d_packed); cudaFreeHost(sp.h_packed); cudaFree(sp.d_used); cudaFreeHost(sp.h_used); cudaFree(sp.d_tmpl); cudaFree(sp.d_ids); cudaFreeHost(sp.h_ids);
+  }
   for (int k = 0; k < kChatStreams; k++) { if (ctx->aux.s[k]) cudaStreamDestroy(ctx->aux.s[k]); if (ctx->aux.join[k]) cudaEventDestroy(ctx->aux.join[k]); }
   if (ctx->aux.fork) cudaEventDestroy(ctx->aux.fork);
   delete ctx;
@@ -393,8 +414,138 @@ int aigw_sse_usage_host(aigw_ctx* ctx, const uint8_t* bytes, const uint64_t* chu
   return 0;
 }
 
+// ------------------------------------------------------------------ stateful per-chunk response streams
+static int stream_pool_grow(aigw_ctx* ctx, uint32_t want) {
+  auto& sp = ctx->sp;
+  if (want <= sp.cap) return 0;
+  uint32_t ncap = sp.cap ? sp.cap : 1024u;
+  while (ncap < want) ncap *= 2;
+  if (ncap > (1u << 22)) { ctx->err = "too many open streams"; return -3; }
+  StreamSlot* nd = nullptr;
+  CK(cudaMalloc(&nd, (size_t)ncap * sizeof(StreamSlot)));
+  if (sp.d_slots) { CK(cudaMemcpyAsync(nd, sp.d_slots, (size_t)sp.cap * sizeof(StreamSlot), cudaMemcpyDeviceToDevice, ctx->s_compute)); CK(cudaStreamSynchronize(ctx->s_compute)); cudaFree(sp.d_slots); }
+  sp.d_slots = nd;
+  sp.carry.resize(ncap, 0); sp.gen.resize(ncap, 0); sp.stamp.resize(ncap, 0); sp.open.resize(ncap, 0);
+  for (uint32_t i = ncap; i-- > sp.cap;) sp.free_list.push_back(i);
+  sp.cap = ncap;
+  return 0;
+}
+static bool stream_handle_ok(aigw_ctx* ctx, uint64_t h, uint32_t& slot) {
+  auto& sp = ctx->sp;
+  const uint32_t lo = (uint32_t)h; if (lo == 0 || lo > sp.cap) return false;
+  slot = lo - 1;
+  return sp.open[slot] && sp.gen[slot] == (uint32_t)(h >> 32);
+}
+
+int aigw_stream_open_batch(aigw_ctx* ctx, const aigw_stream_cfg* cfg, uint32_t n, uint64_t* handles) {
+  if (!cfg || (n && !handles)) return -2;
+  if (n == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  auto& sp = ctx->sp;
+  std::lock_guard<std::mutex> lk(sp.mu);
+  const char* model = cfg->request_model ? cfg->request_model : ""; const char* id = cfg->response_id ? cfg->response_id : "";
+  if (cfg->kind < AIGW_STREAM_OPENAI || cfg->kind > AIGW_STREAM_GCP_ANTHROPIC || strlen(model) > 160 || strlen(id) > 160 || !plain_json_text(model) || !plain_json_text(id)) {
+    ctx->err = "stream cfg: unknown kind, or request_model / response_id need JSON escaping or exceed 160 bytes"; return -2;
+  }
+  if (sp.free_list.size() < n) { const int rc = stream_pool_grow(ctx, sp.cap + (uint32_t)(n - sp.free_list.size())); if (rc) return rc; }
+  std::vector<uint8_t> tmpl(kStreamHdrBytes, 0);
+  StreamSlot* t = (StreamSlot*)tmpl.data();   // header part only
+  t->kind = (uint32_t)cfg->kind; t->beg = t->end = 0; t->flags = 0; t->tool_index = cfg->kind == AIGW_STREAM_GCP_ANTHROPIC ? -1 : 0; t->active_index = -1;
+  t->created = cfg->created; t->model_len = (uint32_t)strlen(model); memcpy(t->model, model, t->model_len);
+  if (cfg->kind == AIGW_STREAM_AWS_BEDROCK) { t->id_len = (uint32_t)strlen(id); memcpy(t->id, id, t->id_len); t->flags |= SF_HAVE_CREATED; }
+  if (!sp.d_tmpl) CK(cudaMalloc(&sp.d_tmpl, kStreamHdrBytes));
+  ENSURE(sp.d_ids, sp.d_ids_cap, (size_t)n * 4, false);
+  ENSURE(sp.h_ids, sp.h_ids_cap, (size_t)n * 4, true);
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t slot = sp.free_list.back(); sp.free_list.pop_back();
+    sp.open[slot] = 1; sp.gen[slot]++; sp.carry[slot] = 0;
+    sp.h_ids[i] = slot; handles[i] = ((uint64_t)sp.gen[slot] << 32) | (uint64_t)(slot + 1);
+  }
+  cudaStream_t st = ctx->s_compute;
+  CK(cudaMemcpyAsync(sp.d_tmpl, tmpl.data(), kStreamHdrBytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(sp.d_ids, sp.h_ids, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CK(launch_stream_init(sp.d_slots, sp.d_ids, n, sp.d_tmpl, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+int aigw_stream_open(aigw_ctx* ctx, const aigw_stream_cfg* cfg, uint64_t* handle) { return aigw_stream_open_batch(ctx, cfg, 1, handle); }
+
+int aigw_stream_close_batch(aigw_ctx* ctx, const uint64_t* handles, uint32_t n) {
+  auto& sp = ctx->sp;
+  std::lock_guard<std::mutex> lk(sp.mu);
+  int rc = 0;
+  for (uint32_t i = 0; i < n; i++) { uint32_t slot; if (!stream_handle_ok(ctx, handles[i], slot)) { rc = -2; continue; } sp.open[slot] = 0; sp.free_list.push_back(slot); }
+  return rc;
+}
+int aigw_stream_close(aigw_ctx* ctx, uint64_t handle) { return aigw_stream_close_batch(ctx, &handle, 1); }
+
+static int stream_chunks_locked(aigw_ctx* ctx, const aigw_chunk_in* in, uint32_t n, aigw_chunk_result* results, const uint8_t** arena) {
+  auto& sp = ctx->sp;
+  if (arena) *arena = nullptr;
+  if (n == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  ENSURE(sp.h_steps, sp.h_steps_cap, (size_t)n * sizeof(StreamStep), true);
+  sp.call_no++;
+  uint64_t in_bytes = 0, out_bytes = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t slot;
+    if (!stream_handle_ok(ctx, in[i].handle, slot) || (in[i].len && !in[i].bytes)) { ctx->err = "aigw_stream_chunks: bad handle"; return -2; }
+    if (sp.stamp[slot] == sp.call_no) { ctx->err = "aigw_stream_chunks: a stream appears twice in one call"; return -2; }
+    sp.stamp[slot] = sp.call_no;
+    StreamStep& s = sp.h_steps[i];
+    s.slot = slot; s.len = in[i].len; s.eos = in[i].eos ? 1u : 0u;
+    s.in_off = in_bytes; in_bytes += ((uint64_t)in[i].len + 15u) & ~15ull;
+    // output bound: every unit of input (≥ 20 bytes) yields at most one chunk of ≤ 96 + id + model + its own text
+    const uint64_t oc = 16ull * ((uint64_t)sp.carry[slot] + in[i].len) + 1024u;
+    s.out_cap = (uint32_t)(oc > 0x7fffffffull ? 0x7fffffffull : oc);
+    s.out_off = out_bytes; out_bytes += ((uint64_t)s.out_cap + 15u) & ~15ull;
+  }
+  ENSURE(sp.h_in, sp.h_in_cap, in_bytes + 16, true);
+  ENSURE(sp.d_in, sp.d_in_cap, in_bytes + 16, false);
+  ENSURE(sp.d_steps, sp.d_steps_cap, (size_t)n * sizeof(StreamStep), false);
+  ENSURE(sp.d_res, sp.d_res_cap, (size_t)n * sizeof(aigw_chunk_result), false);
+  ENSURE(sp.h_res, sp.h_res_cap, (size_t)n * sizeof(aigw_chunk_result), true);
+  ENSURE(sp.d_out, sp.d_out_cap, out_bytes + 16, false);
+  ENSURE(sp.d_packed, sp.d_packed_cap, out_bytes + 16, false);
+  if (!sp.d_used) { CK(cudaMalloc(&sp.d_used, 8)); CK(cudaHostAlloc(&sp.h_used, 8, cudaHostAllocDefault)); }
+  for (uint32_t i = 0; i < n; i++) if (in[i].len) memcpy(sp.h_in + sp.h_steps[i].in_off, in[i].bytes, in[i].len);   // no caller pointer is retained
+  cudaStream_t st = ctx->s_compute;
+  CK(cudaMemcpyAsync(sp.d_in, sp.h_in, in_bytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(sp.d_steps, sp.h_steps, (size_t)n * sizeof(StreamStep), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(sp.d_used, 0, 8, st));
+  StreamParams P; P.slots = sp.d_slots; P.in = sp.d_in; P.out = sp.d_out; P.packed = sp.d_packed; P.packed_used = sp.d_used; P.packed_cap = sp.d_packed_cap; P.steps = sp.d_steps; P.results = sp.d_res; P.n = n;
+  CK(launch_stream_steps(P, st));
+  CK(cudaMemcpyAsync(sp.h_res, sp.d_res, (size_t)n * sizeof(aigw_chunk_result), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(sp.h_used, sp.d_used, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const uint64_t used = *sp.h_used < sp.d_packed_cap ? *sp.h_used : sp.d_packed_cap;
+  if (used) {
+    ENSURE(sp.h_packed, sp.h_packed_cap, used + 16, true);
+    CK(cudaMemcpyAsync(sp.h_packed, sp.d_packed, used, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  for (uint32_t i = 0; i < n; i++) { results[i] = sp.h_res[i]; sp.carry[sp.h_steps[i].slot] = sp.h_res[i].carry_len; }
+  if (arena) *arena = sp.h_packed;
+  return 0;
+}
+int aigw_stream_chunks(aigw_ctx* ctx, const aigw_chunk_in* in, uint32_t n, aigw_chunk_result* results, const uint8_t** arena) {
+  std::lock_guard<std::mutex> lk(ctx->sp.mu);
+  return stream_chunks_locked(ctx, in, n, results, arena);
+}
+int aigw_stream_chunk(aigw_ctx* ctx, uint64_t handle, const uint8_t* bytes, uint32_t len, int eos, uint8_t* out, uint32_t out_cap, aigw_chunk_result* res) {
+  std::lock_guard<std::mutex> lk(ctx->sp.mu);
+  aigw_chunk_in in; in.handle = handle; in.bytes = bytes; in.len = len; in.eos = eos ? 1u : 0u;
+  const uint8_t* arena = nullptr;
+  const int rc = stream_chunks_locked(ctx, &in, 1, res, &arena);
+  if (rc) return rc;
+  const uint32_t tot = res->out_len + res->model_len;
+  if (tot > out_cap) return -4;
+  if (tot) memcpy(out, arena + res->out_off, tot);
+  res->out_off = 0;
+  return 0;
+}
+
 // ------------------------------------------------------------------ S2: Bedrock eventstream → OpenAI SSE
-static bool plain_json_text(const char* s) { for (; *s; s++) { unsigned char c = (unsigned char)*s; if (c < 0x20 || c > 0x7e || c == '"' || c == '\\') return false; } return true; }
 static int fill_stream_params(aigw_ctx* ctx, BedrockStreamParams& P, const aigw_bedrock_stream_cfg* cfg) {
   memset(P.id, 0, sizeof P.id); memset(P.model, 0, sizeof P.model); P.id_len = P.model_len = 0; P.created = cfg ? cfg->created : 0;
   const char* id = cfg && cfg->response_id ? cfg->response_id : ""; const char* model = cfg && cfg->request_model ? cfg->request_model : "";

@@ -1,4 +1,5 @@
 // See mutate_kernel.cuh.  sm_100a only.
+#include "device_once.cuh"
 #include "mutate_kernel.cuh"
 
 namespace aigw {
@@ -269,15 +270,20 @@ __global__ void __launch_bounds__(WARPS * 32) body_mutate_kernel(const __grid_co
 
 template <int MAXD, int WARPS>
 cudaError_t launch_cls(const MutateParams& P, int sm_count, cudaStream_t st) {
-  static bool ready = false; static int bps = 1;
+  static DeviceOnce once;
   const size_t smem = kMutTextCap + 256 + (size_t)WARPS * Lay<MAXD>::kWarpBytes;
-  if (!ready) {
-    cudaError_t e = cudaFuncSetAttribute(body_mutate_kernel<MAXD, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, body_mutate_kernel<MAXD, WARPS>, WARPS * 32, smem)) != cudaSuccess) return e;
-    if (bps < 1) bps = 1;
-    ready = true;
+  int* v = nullptr;
+  {
+    const cudaError_t e0 = device_once(once, &v, [&](int* val) {
+      cudaError_t e = cudaFuncSetAttribute(body_mutate_kernel<MAXD, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&val[0], body_mutate_kernel<MAXD, WARPS>, WARPS * 32, smem)) != cudaSuccess) return e;
+      if (val[0] < 1) val[0] = 1;
+      return cudaSuccess;
+    });
+    if (e0 != cudaSuccess) return e0;
   }
+  const int bps = v[0];
   long long want = ((long long)P.n + WARPS - 1) / WARPS, grid = (long long)sm_count * bps;
   if (want < grid) grid = want;
   if (grid < 1) grid = 1;

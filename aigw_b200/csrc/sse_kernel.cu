@@ -2,75 +2,13 @@
 #include <cstring>
 #include <vector>
 
+#include "device_once.cuh"
 #include "sse_kernel.cuh"
-#include "tjson.cuh"
+#include "sse_schema.cuh"
 
 namespace aigw {
-using namespace tj;
 
-// ------------------------------------------------------------------ schema: ChatCompletionResponseChunk
-// (internal/apischema/openai/openai.go:1497-1565 chunk/choice/delta, :2064-2083 Usage, :1464-1495 details,
-//  :1323-1361 logprobs, :1424-1443 annotations, :1875-1879 StreamReasoningContent, :1789-1807 created)
-enum Cap : uint8_t { C_PROMPT = 0, C_COMPLETION = 1, C_TOTAL = 2, C_REASONING = 3, C_CACHED = 4, C_CACHE_CREATION = 5,
-                     C_OBJ_USAGE = 0, C_OBJ_CTD = 1, C_OBJ_PTD = 2, C_SPAN_MODEL = 0, NOCAP = 0xff };
-enum N : uint8_t { N_ANY = 0, N_STR, N_INT, N_FLOAT, N_ROOT, N_CHOICES, N_CHOICE, N_DELTA, N_TOOLCALLS, N_TOOLCALL, N_FUNC, N_ANNOTS, N_ANNOT, N_URLCIT,
-                   N_REASON, N_B64, N_LOGPROBS, N_TOKLPS, N_TOKLP, N_INTS, N_TOPLPS, N_TOPLP, N_USAGE, N_CTD, N_PTD, N_CREATED, N_MODEL,
-                   N_PROMPT, N_COMPLETION, N_TOTAL, N_REASONING_TOK, N_CACHED, N_CACHE_CREATION, N_COUNT };
-
-struct FieldDef { uint8_t owner; const char* key; uint8_t node; };
-static const FieldDef kFields[] = {
-  {N_ROOT, "id", N_STR}, {N_ROOT, "choices", N_CHOICES}, {N_ROOT, "created", N_CREATED}, {N_ROOT, "model", N_MODEL}, {N_ROOT, "service_tier", N_STR},
-  {N_ROOT, "system_fingerprint", N_STR}, {N_ROOT, "object", N_STR}, {N_ROOT, "usage", N_USAGE}, {N_ROOT, "obfuscation", N_STR},
-  {N_CHOICE, "index", N_INT}, {N_CHOICE, "delta", N_DELTA}, {N_CHOICE, "logprobs", N_LOGPROBS}, {N_CHOICE, "finish_reason", N_STR},
-  {N_DELTA, "content", N_STR}, {N_DELTA, "role", N_STR}, {N_DELTA, "tool_calls", N_TOOLCALLS}, {N_DELTA, "annotations", N_ANNOTS}, {N_DELTA, "reasoning_content", N_REASON},
-  {N_TOOLCALL, "index", N_INT}, {N_TOOLCALL, "id", N_STR}, {N_TOOLCALL, "function", N_FUNC}, {N_TOOLCALL, "type", N_STR},
-  {N_FUNC, "arguments", N_STR}, {N_FUNC, "name", N_STR},
-  {N_ANNOT, "type", N_STR}, {N_ANNOT, "url_citation", N_URLCIT},
-  {N_URLCIT, "end_index", N_INT}, {N_URLCIT, "start_index", N_INT}, {N_URLCIT, "url", N_STR}, {N_URLCIT, "title", N_STR},
-  {N_REASON, "text", N_STR}, {N_REASON, "signature", N_STR}, {N_REASON, "redactedContent", N_B64},
-  {N_LOGPROBS, "content", N_TOKLPS}, {N_LOGPROBS, "refusal", N_TOKLPS},
-  {N_TOKLP, "token", N_STR}, {N_TOKLP, "bytes", N_INTS}, {N_TOKLP, "logprob", N_FLOAT}, {N_TOKLP, "top_logprobs", N_TOPLPS},
-  {N_TOPLP, "token", N_STR}, {N_TOPLP, "bytes", N_INTS}, {N_TOPLP, "logprob", N_FLOAT},
-  {N_USAGE, "prompt_tokens", N_PROMPT}, {N_USAGE, "completion_tokens", N_COMPLETION}, {N_USAGE, "total_tokens", N_TOTAL},
-  {N_USAGE, "completion_tokens_details", N_CTD}, {N_USAGE, "prompt_tokens_details", N_PTD},
-  {N_CTD, "text_tokens", N_INT}, {N_CTD, "accepted_prediction_tokens", N_INT}, {N_CTD, "audio_tokens", N_INT}, {N_CTD, "reasoning_tokens", N_REASONING_TOK}, {N_CTD, "rejected_prediction_tokens", N_INT},
-  {N_PTD, "text_tokens", N_INT}, {N_PTD, "audio_tokens", N_INT}, {N_PTD, "cached_tokens", N_CACHED}, {N_PTD, "cache_creation_input_tokens", N_CACHE_CREATION},
-};
-static constexpr int kNumFields = sizeof(kFields) / sizeof(kFields[0]);
-
-struct alignas(16) SchemaBlob {
-  Node nodes[N_COUNT];
-  Field fields[64];
-  char keys[768];
-};
-static_assert(kNumFields <= 64, "field table too small");
 __device__ SchemaBlob g_schema;
-
-static SchemaBlob build_schema() {
-  SchemaBlob b; memset(&b, 0, sizeof b);
-  auto set = [&](int n, uint8_t kind, uint8_t cap = NOCAP, uint8_t elem = 0) { b.nodes[n].kind = kind; b.nodes[n].cap = cap; b.nodes[n].elem = elem; };
-  set(N_ANY, K_ANY); set(N_STR, K_STR); set(N_INT, K_INT); set(N_FLOAT, K_FLOAT);
-  set(N_ROOT, K_OBJ); set(N_CHOICES, K_ARR, NOCAP, N_CHOICE); set(N_CHOICE, K_OBJ); set(N_DELTA, K_OBJ);
-  set(N_TOOLCALLS, K_ARR, NOCAP, N_TOOLCALL); set(N_TOOLCALL, K_OBJ); set(N_FUNC, K_OBJ);
-  set(N_ANNOTS, K_ARR, NOCAP, N_ANNOT); set(N_ANNOT, K_OBJ); set(N_URLCIT, K_OBJ); set(N_REASON, K_OBJ); set(N_B64, K_B64);
-  set(N_LOGPROBS, K_OBJ); set(N_TOKLPS, K_ARR, NOCAP, N_TOKLP); set(N_TOKLP, K_OBJ); set(N_INTS, K_ARR, NOCAP, N_INT);
-  set(N_TOPLPS, K_ARR, NOCAP, N_TOPLP); set(N_TOPLP, K_OBJ);
-  set(N_USAGE, K_OBJ, C_OBJ_USAGE); set(N_CTD, K_OBJ, C_OBJ_CTD); set(N_PTD, K_OBJ, C_OBJ_PTD);
-  set(N_CREATED, K_CREATED); set(N_MODEL, K_STR, C_SPAN_MODEL);
-  set(N_PROMPT, K_INT, C_PROMPT); set(N_COMPLETION, K_INT, C_COMPLETION); set(N_TOTAL, K_INT, C_TOTAL);
-  set(N_REASONING_TOK, K_INT, C_REASONING); set(N_CACHED, K_INT, C_CACHED); set(N_CACHE_CREATION, K_INT, C_CACHE_CREATION);
-  int ko = 0;
-  for (int f = 0; f < kNumFields; f++) {
-    const FieldDef& d = kFields[f];
-    Node& o = b.nodes[d.owner];
-    if (o.nf == 0) o.f0 = (uint8_t)f;   // fields of one owner are contiguous in kFields
-    o.nf++;
-    int kl = (int)strlen(d.key);
-    b.fields[f].koff = (uint16_t)ko; b.fields[f].klen = (uint8_t)kl; b.fields[f].node = d.node;
-    memcpy(b.keys + ko, d.key, kl); ko += kl;
-  }
-  return b;
-}
 
 // ------------------------------------------------------------------ kernel
 __device__ __forceinline__ uint32_t nib_ff(uint32_t m) { return ((m & 0x08040201u) * 0x01010101u) >> 24; }   // 0xFF per byte → 4-bit mask
@@ -421,11 +359,13 @@ __global__ void usage_costs_kernel(const aigw_sse_result* results, uint32_t n, c
 }
 
 cudaError_t launch_response_usage(const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n, aigw_sse_result* results, cudaStream_t st, int embeddings) {
-  static bool ready = false;
-  if (!ready) {
-    RespSchemaBlob b = build_resp_schema(); cudaError_t e = cudaMemcpyToSymbol(g_resp_schema, &b, sizeof b); if (e != cudaSuccess) return e;
-    RespSchemaBlob b2 = build_emb_schema(); e = cudaMemcpyToSymbol(g_emb_schema, &b2, sizeof b2); if (e != cudaSuccess) return e;
-    ready = true;
+  static DeviceOnce once;
+  {
+    const cudaError_t e0 = device_once(once, nullptr, [&](int*) {
+      RespSchemaBlob b = build_resp_schema(); cudaError_t e = cudaMemcpyToSymbol(g_resp_schema, &b, sizeof b); if (e != cudaSuccess) return e;
+      RespSchemaBlob b2 = build_emb_schema(); return cudaMemcpyToSymbol(g_emb_schema, &b2, sizeof b2);
+    });
+    if (e0 != cudaSuccess) return e0;
   }
   if (n == 0) return cudaSuccess;
   response_usage_kernel<<<(n + 127) / 128, 128, 0, st>>>(bodies, offsets, lens, n, results, embeddings);
@@ -439,19 +379,22 @@ cudaError_t launch_usage_costs(const aigw_sse_result* results, uint32_t n, const
 }
 
 cudaError_t launch_sse_usage(const SseParams& P, int sm_count, cudaStream_t st) {
-  static bool ready = false; static int bps = 1;
+  static DeviceOnce once;
   const size_t smem = ((sizeof(SchemaBlob) + 15) & ~15u) + (size_t)kWarps * kWarpBytes;
-  if (!ready) {
-    SchemaBlob b = build_schema();
-    cudaError_t e = cudaMemcpyToSymbol(g_schema, &b, sizeof b);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(sse_usage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sse_usage_kernel, kWarps * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (bps < 1) bps = 1;
-    ready = true;
+  int* v = nullptr;
+  {
+    const cudaError_t e0 = device_once(once, &v, [&](int* val) {
+      SchemaBlob b = build_schema();
+      cudaError_t e = cudaMemcpyToSymbol(g_schema, &b, sizeof b);
+      if (e != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(sse_usage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&val[0], sse_usage_kernel, kWarps * 32, smem)) != cudaSuccess) return e;
+      if (val[0] < 1) val[0] = 1;
+      return cudaSuccess;
+    });
+    if (e0 != cudaSuccess) return e0;
   }
+  const int bps = v[0];
   long long want = ((long long)P.n_streams + kWarps - 1) / kWarps;
   long long grid = (long long)sm_count * bps;
   if (want < grid) grid = want;

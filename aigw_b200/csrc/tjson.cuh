@@ -153,7 +153,11 @@ __device__ inline bool walk(const uint8_t* p, int n, const Node* nodes, const Fi
     uint32_t c = p[i];
     if (nd.kind == K_STROBJ) { if (c == '"' || c == 'n') nd.kind = K_STR; else { node = nd.elem; nd = nodes[node]; } }
     bool descend = false;
-    if (nd.kind == K_ANY) { i = skip_any(p, i, n); if (i < 0) return false; }
+    if (nd.kind == K_ANY) {
+      const int j = skip_any(p, i, n); if (j < 0) return false;
+      if (nd.cap != 0xff) { const uint32_t s = nd.cap; cap.span_off[s] = i; cap.span_len[s] = j - i; cap.span_set |= 1u << s; }   // raw value (quotes included for strings)
+      i = j;
+    }
     else if (c == 'n') {
       if (!lit(p, i, n, "null", 4)) return false;
       i += 4;

@@ -215,6 +215,41 @@ typedef struct aigw_stream_batch_out { const aigw_stream_result* results; const 
 int aigw_bedrock_stream_host(aigw_ctx* ctx, const aigw_bedrock_stream_cfg* cfg, const uint8_t* bytes, const uint64_t* stream_off, uint32_t n_streams,
                              uint64_t out_capacity_hint, aigw_stream_batch_out* out);
 
+/* ---- stateful per-chunk response streams (aigw_stream_open / chunk / close) ----
+ * Replaces Translator.ResponseBody(headers, body, endOfStream) as the reference calls it once per upstream chunk
+ * (internal/translator/translator.go:41-76): the undecoded tail (partial SSE line / eventstream frame / SSE event) and the
+ * parser state (role, tool-call index, accumulated usage, message id) stay on the DEVICE between calls, exactly what the
+ * reference carries in its translator object (openai_openai.go:131-145,179-193; openai_awsbedrock.go:695-732,829-852;
+ * anthropic_helper.go:787-919).  Kinds:
+ *   AIGW_STREAM_OPENAI         OpenAI / Azure passthrough: usage scan only, body UNCHANGED (openai_openai.go:179-215)
+ *   AIGW_STREAM_AWS_BEDROCK    AWS eventstream → OpenAI SSE (openai_awsbedrock.go:695-1006)
+ *   AIGW_STREAM_GCP_ANTHROPIC  Anthropic SSE → OpenAI SSE (anthropic_helper.go:787-1162; openai_gcpanthropic.go:237-244)
+ * aigw_stream_chunks processes one ResponseBody call for each of n streams in ONE batch (a stream may appear once per call;
+ * calls on one context are serialised by the library).  Result i: the call's body mutation is
+ * arena[out_off .. out_off+out_len) (body_kind BYTES, or EMPTY when the call produced nothing; UNCHANGED for the passthrough
+ * kind), followed by model_len bytes of responseModel; `usage` is the TokenUsage that call returns (the processor merges it
+ * with Override); the arena stays valid until the next stream call on the context.  status: AIGW_OK; AIGW_INTERNAL = the
+ * reference returns an error (stream failure); AIGW_DECLINED = outside the GPU path (reason: AIGW_R_UNSUPPORTED_FIELD,
+ * AIGW_R_TOO_LARGE carry above 15.6 KB, AIGW_R_OUT_SPACE, AIGW_R_ARENA_FULL) — both are sticky for the stream.
+ * cfg strings must not need JSON escaping (printable ASCII without '"' and '\\', ≤ 160 bytes), else -2. */
+enum aigw_stream_kind { AIGW_STREAM_OPENAI = 0, AIGW_STREAM_AWS_BEDROCK = 1, AIGW_STREAM_GCP_ANTHROPIC = 2 };
+typedef struct aigw_stream_cfg { int32_t kind; int32_t _pad; int64_t created; const char* request_model; const char* response_id; } aigw_stream_cfg;
+typedef struct aigw_chunk_in { uint64_t handle; const uint8_t* bytes; uint32_t len; uint32_t eos; } aigw_chunk_in;
+typedef struct aigw_chunk_result {
+  uint64_t out_off; uint32_t out_len; uint8_t status, body_kind, reason, _pad;
+  aigw_usage usage;
+  uint32_t model_len;    /* responseModel bytes follow the body bytes in the arena */
+  uint32_t carry_len;    /* undecoded tail kept on the device for the next call */
+  uint64_t _reserved;
+} aigw_chunk_result;     /* 64 bytes */
+int aigw_stream_open(aigw_ctx* ctx, const aigw_stream_cfg* cfg, uint64_t* handle);
+int aigw_stream_open_batch(aigw_ctx* ctx, const aigw_stream_cfg* cfg, uint32_t n, uint64_t* handles);   /* n streams with the same cfg */
+int aigw_stream_chunks(aigw_ctx* ctx, const aigw_chunk_in* in, uint32_t n, aigw_chunk_result* results /* host, n */, const uint8_t** arena);
+/* one chunk of one stream; the mutation is copied to out (≥ out_len + model_len bytes, else -4) */
+int aigw_stream_chunk(aigw_ctx* ctx, uint64_t handle, const uint8_t* bytes, uint32_t len, int eos, uint8_t* out, uint32_t out_cap, aigw_chunk_result* res);
+int aigw_stream_close(aigw_ctx* ctx, uint64_t handle);
+int aigw_stream_close_batch(aigw_ctx* ctx, const uint64_t* handles, uint32_t n);
+
 /* ---- route/backend body mutation (B1) ----
  * Replaces BodyMutator.Mutate (internal/bodymutator/body_mutator.go:77-119; config type internal/filterapi/filterconfig.go:258-277)
  * as applyBodyMutation (internal/extproc/util.go:107-131) runs it on the translated body, or on the original body when the

@@ -201,6 +201,15 @@ double oracle_bedrock_response_batch(const uint8_t* bodies, const uint64_t* offs
   if (total_out) *total_out = tot.load();
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
+// stateful form of the Bedrock stream oracle: one ResponseBody call per feed
+struct BedrockHandle { BedrockStreamState st; BedrockStreamCfg cfg; };
+void* oracle_bedrock_open(const char* request_model, const char* response_id, int64_t created) { auto* h = new BedrockHandle(); h->cfg.request_model = request_model ? request_model : ""; h->cfg.response_id = response_id ? response_id : ""; h->cfg.created = created; return h; }
+void oracle_bedrock_close(void* h) { delete (BedrockHandle*)h; }
+void oracle_bedrock_feed(void* hv, const char* chunk, uint64_t len, int eos, char** out, uint64_t* out_len, oracle_usage* usage) {
+  auto* h = (BedrockHandle*)hv; std::string o; TokenUsage u;
+  bedrock_stream_feed(h->st, h->cfg, std::string_view(chunk, len), eos != 0, o, u);
+  put(usage, u); *out = dup(o); *out_len = o.size();
+}
 // ---- S3 / R1 (Anthropic): SSE events → OpenAI SSE, per ResponseBody call; buffered Message → ChatCompletionResponse
 struct AnthropicHandle { AnthropicStreamState st; AnthropicStreamCfg cfg; };
 void* oracle_anthropic_open(const char* request_model, int64_t created) { auto* h = new AnthropicHandle(); h->cfg.request_model = request_model ? request_model : ""; h->cfg.created = created; return h; }

@@ -234,3 +234,22 @@ def anthropic_response(body: bytes, request_model: bytes, created: int):
     st = L.oracle_anthropic_response(body, len(body), request_model, created, C.byref(vp), C.byref(n), C.byref(u), buf, 4096, C.byref(ml))
     out = C.string_at(vp, n.value); L.oracle_free(vp)
     return st, out, u, buf.raw[:ml.value]
+
+
+class BedrockStream:
+    """Bedrock ResponseBody(stream) per call (S2): feed(chunk, eos) → (body mutation bytes, Usage of the call)."""
+    def __init__(self, request_model: bytes, response_id: bytes, created: int):
+        L = lib(); L.oracle_bedrock_open.restype = C.c_void_p; L.oracle_bedrock_open.argtypes = [C.c_char_p, C.c_char_p, C.c_int64]
+        L.oracle_bedrock_feed.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(Usage)]
+        L.oracle_bedrock_close.argtypes = [C.c_void_p]
+        self.h = L.oracle_bedrock_open(request_model, response_id, created)
+
+    def feed(self, chunk: bytes, eos: bool):
+        vp = C.c_void_p(); n = C.c_uint64(0); u = Usage()
+        lib().oracle_bedrock_feed(self.h, chunk, len(chunk), int(eos), C.byref(vp), C.byref(n), C.byref(u))
+        out = C.string_at(vp, n.value); lib().oracle_free(vp)
+        return out, u
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_bedrock_close(self.h); self.h = None

@@ -1,0 +1,247 @@
+"""Stateful per-chunk stream ABI (aigw_stream_open / chunks / close) on the GPU vs the oracle and the reference's own protocol tests:
+TestExtractUsageFromBufferEvent feed by feed (internal/translator/openai_openai_test.go:424-480), the real AWS capture fed ONE BYTE PER
+CALL (internal/translator/openai_awsbedrock_test.go:1315-1316,1338-1390), the Anthropic streaming goldens
+(tests/data-plane/testupstream_test.go:575,637) under several chunkings."""
+import base64
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import _oracle as O
+import _workload as W
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = json.load(open(os.path.join(HERE, "golden", "testupstream_cases.json"), encoding="utf-8"))["cases"]
+OKS, INTERNAL, DECLINED = 0, 3, 4
+UNCHANGED, BYTES, EMPTY = 0, 1, 2
+
+
+@pytest.fixture(scope="module")
+def gw():
+    from aigw_b200 import capi
+    g = capi.Context(0)
+    yield g
+    g.close()
+
+
+# ---------------------------------------------------------------- S1: OpenAI usage scan
+def test_openai_usage_reference_vectors_feed_by_feed(gw):
+    cases = json.load(open(os.path.join(HERE, "golden", "sse_usage_cases.json"), encoding="utf-8"))["cases"]
+    for c in cases:
+        (h,) = gw.stream_open("openai", b"req-model")
+        for feed, exp in zip(c["feeds"], c["exp"]):
+            r = gw.stream_chunk(h, feed.encode(), False)
+            assert r["status"] == OKS and r["body_kind"] == UNCHANGED and r["body"] == b"", c["name"]
+            assert list(r["usage"]) == exp, c["name"]
+        if c.get("buffered_empty"):
+            assert r["carry_len"] == 0, c["name"]
+        gw.stream_close([h])
+
+
+def test_openai_usage_batch_vs_oracle(gw):
+    """256 streams advance together, one call per round, random chunk boundaries; every call's usage / model / carry equal the oracle's"""
+    buf, coff, cfirst = W.sse_corpus(4, 0, 256, chunks=24)
+    raw = bytes(buf)
+    rng = random.Random(7)
+    streams = []
+    for s in range(256):
+        data = raw[int(coff[int(cfirst[s])]):int(coff[int(cfirst[s + 1])])]
+        cuts = sorted(rng.sample(range(1, len(data)), min(11, len(data) - 1)))
+        streams.append([data[a:b] for a, b in zip([0] + cuts, cuts + [len(data)])])
+    hs = gw.stream_open("openai", b"req-model", n=256)
+    orc = [O.SSEStream() for _ in range(256)]
+    for rnd in range(max(len(s) for s in streams)):
+        idx = [i for i in range(256) if rnd < len(streams[i])]
+        got = gw.stream_chunks([hs[i] for i in idx], [streams[i][rnd] for i in idx], [False] * len(idx))
+        for i, g in zip(idx, got):
+            u = orc[i].feed(streams[i][rnd])
+            assert g["status"] == OKS
+            assert g["usage"] == u.as_tuple(), (i, rnd)
+            assert g["model"] == (orc[i].model() or b"req-model")
+            assert g["carry_len"] == orc[i].buffered()
+    gw.stream_close(hs)
+
+
+# ---------------------------------------------------------------- S2: Bedrock eventstream
+def test_bedrock_real_capture_one_byte_per_call(gw):
+    g = json.load(open(os.path.join(HERE, "golden", "bedrock_stream_real.json"), encoding="utf-8"))
+    data = base64.b64decode(g["eventstream_base64"])
+    (h,) = gw.stream_open("aws-bedrock", g["request_model"].encode(), g["response_id"].encode(), g["created"])
+    orc = O.BedrockStream(g["request_model"].encode(), g["response_id"].encode(), g["created"])
+    out = b""; last_usage = None
+    for i in range(len(data)):
+        r = gw.stream_chunk(h, data[i:i + 1], False)
+        o, u = orc.feed(data[i:i + 1], False)
+        assert r["status"] == OKS and r["body"] == o, i
+        assert r["body_kind"] == (BYTES if o else EMPTY)
+        assert r["usage"] == u.as_tuple(), i
+        if u.mask:
+            last_usage = r["usage"]
+        out += r["body"]
+    r = gw.stream_chunk(h, b"", True)
+    assert r["body"] == b"data: [DONE]\n" and r["carry_len"] == 0
+    out += r["body"]
+    got = [l for l in out.decode().split("\n") if l.strip()]
+    want = [l.strip() for l in g["expected_sse"].split("\n") if l.strip()]
+    if want[-1] != "data: [DONE]":
+        want.append("data: [DONE]")
+    assert got == want
+    assert last_usage[0] == g["expect_input_tokens"] and last_usage[3] == g["expect_output_tokens"]
+    gw.stream_close([h])
+
+
+def test_bedrock_corpus_random_chunking_vs_oracle(gw):
+    _, _, streams = W.bedrock_stream_corpus(96, seed=5)
+    rng = random.Random(11)
+    parts = []
+    for data in streams:
+        k = rng.randint(1, 9)
+        cuts = sorted(rng.sample(range(1, len(data)), min(k, len(data) - 1)))
+        parts.append([data[a:b] for a, b in zip([0] + cuts, cuts + [len(data)])])
+    n = len(streams)
+    hs = gw.stream_open("aws-bedrock", b"model-x", b"req-1", 1700000000, n=n)
+    orc = [O.BedrockStream(b"model-x", b"req-1", 1700000000) for _ in range(n)]
+    whole = [b""] * n
+    for rnd in range(max(len(p) for p in parts)):
+        idx = [i for i in range(n) if rnd < len(parts[i])]
+        eos = [rnd == len(parts[i]) - 1 for i in idx]
+        got = gw.stream_chunks([hs[i] for i in idx], [parts[i][rnd] for i in idx], eos)
+        for i, e, g in zip(idx, eos, got):
+            o, u = orc[i].feed(parts[i][rnd], e)
+            assert g["status"] == OKS, (i, rnd, g["reason"])
+            assert g["body"] == o and g["usage"] == u.as_tuple() and g["model"] == b"model-x"
+            whole[i] += g["body"]
+    for i, data in enumerate(streams):
+        ref, _ = O.bedrock_stream(data, None, b"model-x", b"req-1", 1700000000)
+        assert whole[i] == ref
+    gw.stream_close(hs)
+
+
+# ---------------------------------------------------------------- S3: Anthropic SSE
+ANTHROPIC_STREAM_CASES = ["gcp-anthropicai - /v1/chat/completions - streaming", "gcp-anthropicai - /v1/chat/completions - streaming tool use"]
+
+
+def _blocks(body):
+    return [b.encode() + b"\n\n" for b in body.split("\n\n") if b.strip()]
+
+
+@pytest.mark.parametrize("name", ANTHROPIC_STREAM_CASES)
+@pytest.mark.parametrize("chunking", ["blocks", "whole", "bytes", "random"])
+def test_anthropic_stream_goldens(gw, name, chunking):
+    c = next(c for c in CASES if c["name"] == name)
+    blocks = _blocks(c["responseBody"]); whole = b"".join(blocks)
+    if chunking == "blocks": chunks = blocks
+    elif chunking == "whole": chunks = [whole]
+    elif chunking == "bytes": chunks = [whole[i:i + 1] for i in range(len(whole))]
+    else:
+        rng = random.Random(3); cuts = sorted(rng.sample(range(1, len(whole)), 17)); chunks = [whole[a:b] for a, b in zip([0] + cuts, cuts + [len(whole)])]
+    (h,) = gw.stream_open("gcp-anthropicai", b"claude-3-sonnet", b"", 123)
+    orc = O.AnthropicStream(b"claude-3-sonnet", 123)
+    out = b""
+    for ch in chunks + [None]:
+        eos = ch is None
+        r = gw.stream_chunk(h, ch or b"", eos)
+        s, o, u = orc.feed(ch or b"", eos)
+        assert r["status"] == s == OKS
+        assert r["body"] == o and r["usage"] == u.as_tuple() and r["model"] == b"claude-3-sonnet"
+        out += r["body"]
+    assert out.decode() == c["expResponseBody"]
+    gw.stream_close([h])
+
+
+def _an_event(rng, kind):
+    text = rng.choice(["Hello", " world", "a\\nb", "q\\\"uote", "café", "x" * rng.randint(1, 200), ""])
+    if kind == "start": return 'event: message_start\ndata: {"type":"message_start","message":{"id":"msg_%d","role":"assistant","usage":{"input_tokens":%d,"cache_read_input_tokens":%d}}}' % (rng.randint(1, 99), rng.randint(0, 500), rng.choice([0, 0, 7]))
+    if kind == "text_start": return 'event: content_block_start\ndata: {"type":"content_block_start","index":0,"content_block":{"type":"text","text":""}}'
+    if kind == "thinking_start": return 'event: content_block_start\ndata: {"type":"content_block_start","index":0,"content_block":{"type":"thinking","thinking":""}}'
+    if kind == "text": return 'event: content_block_delta\ndata:  {"type":"content_block_delta","index":0,"delta":{"type":"text_delta","text":"%s"}} ' % text
+    if kind == "thinking": return 'event: content_block_delta\ndata: {"type":"content_block_delta","delta":{"type":"thinking_delta","thinking":"%s"}}' % text
+    if kind == "tool_start": return 'event: content_block_start\ndata: {"type":"content_block_start","index":1,"content_block":{"type":"tool_use","id":"toolu_%d","name":"fn_%d","input":{}}}' % (rng.randint(1, 9), rng.randint(1, 9))
+    if kind == "tool_delta": return 'event: content_block_delta\ndata: {"type":"content_block_delta","index":1,"delta":{"type":"input_json_delta","partial_json":"{\\"k\\":%d"}}' % rng.randint(0, 9)
+    if kind == "block_stop": return 'event: content_block_stop\ndata: {"type":"content_block_stop","index":0}'
+    if kind == "ping": return 'event: ping\ndata: {"type": "ping"}'
+    if kind == "delta": return 'event: message_delta\ndata: {"type":"message_delta","delta":{"stop_reason":"%s"},"usage":{"output_tokens":%d}}' % (rng.choice(["end_turn", "max_tokens", "tool_use", "stop_sequence", "refusal"]), rng.randint(0, 300))
+    if kind == "stop": return 'event: message_stop\ndata: {"type":"message_stop"}'
+    raise AssertionError(kind)
+
+
+def test_anthropic_corpus_vs_oracle(gw):
+    rng = random.Random(21)
+    n = 128
+    streams = []
+    for _ in range(n):
+        ev = ["start"]
+        for _b in range(rng.randint(1, 3)):
+            t = rng.choice(["text", "tool", "thinking"])
+            if t == "text": ev += ["text_start"] + ["text"] * rng.randint(1, 6) + ["block_stop"]
+            elif t == "thinking": ev += ["thinking_start"] + ["thinking"] * rng.randint(1, 3) + ["block_stop"]
+            else: ev += ["tool_start"] + ["tool_delta"] * rng.randint(0, 3) + ["block_stop"]
+            if rng.random() < 0.3: ev.append("ping")
+        ev += ["delta", "stop"]
+        data = "".join(_an_event(rng, k) + "\n\n" for k in ev).encode()
+        if rng.random() < 0.3: data = data[:-2]   # last event without the blank line: handled at end of stream
+        cuts = sorted(rng.sample(range(1, len(data)), min(rng.randint(0, 12), len(data) - 1)))
+        streams.append([data[a:b] for a, b in zip([0] + cuts, cuts + [len(data)])])
+    hs = gw.stream_open("gcp-anthropicai", b"claude-x", b"", 99, n=n)
+    orc = [O.AnthropicStream(b"claude-x", 99) for _ in range(n)]
+    dead = [False] * n; n_ok = 0
+    for rnd in range(max(len(p) for p in streams) + 1):
+        idx = [i for i in range(n) if rnd <= len(streams[i])]
+        chunks = [streams[i][rnd] if rnd < len(streams[i]) else b"" for i in idx]
+        eos = [rnd == len(streams[i]) for i in idx]
+        got = gw.stream_chunks([hs[i] for i in idx], chunks, eos)
+        for i, ch, e, g in zip(idx, chunks, eos, got):
+            s, o, u = orc[i].feed(ch, e)
+            assert g["status"] == s, (i, rnd, g["reason"], ch)
+            if s == OKS:
+                assert g["body"] == o and g["usage"] == u.as_tuple(), (i, rnd)
+                n_ok += e
+            else:
+                dead[i] = True
+    assert n_ok >= n * 0.6   # "café"-free streams translate; a raw UTF-8 é is fine too, only \uXXXX / control escapes decline
+    gw.stream_close(hs)
+
+
+def test_anthropic_error_paths(gw):
+    def run(events, eos_last=True):
+        (h,) = gw.stream_open("gcp-anthropicai", b"m", b"", 7)
+        orc = O.AnthropicStream(b"m", 7)
+        res = []
+        for k, ev in enumerate(events):
+            e = eos_last and k == len(events) - 1
+            r = gw.stream_chunk(h, ev, e); s, o, u = orc.feed(ev, e)
+            assert r["status"] == s, (ev, r["reason"])
+            if s == OKS: assert r["body"] == o
+            res.append(r)
+        gw.stream_close([h])
+        return res
+    r = run([b'event: ping\ndata: not json\n\nevent: message_start\n\n', b'event: content_block_delta\ndata: {"delta":{"type":"input_json_delta","partial_json":"{"}}\n\n', b""])
+    assert [x["status"] for x in r] == [OKS, INTERNAL, INTERNAL]
+    assert run([b'event: message_delta\ndata: {"delta":{"stop_reason":"weird"}}\n\nevent: message_stop\ndata: {}\n\n'])[0]["status"] == INTERNAL
+    assert run([b'event: error\ndata: {"error":{"type":"overloaded_error","message":"x"}}\n\n'])[0]["status"] == INTERNAL
+    assert run([b'event: message_stop\ndata: {\n\n'])[0]["status"] == INTERNAL
+    assert run([b'event: message_stop\ndata: {}'])[0]["body"] == b'data: {"choices":[{"index":0,"delta":{},"finish_reason":"stop"}],"model":"m","object":"chat.completion.chunk"}\n\ndata: [DONE]\n\n'
+    # unpinned inputs decline on both sides: wrong types, non-empty tool input, \u escapes in echoed text
+    assert run([b'event: message_start\ndata: {"message":{"id":5}}\n\n'])[0]["status"] == DECLINED
+    assert run([b'event: content_block_start\ndata: {"content_block":{"type":"tool_use","id":"a","name":"b","input":{"x":1}}}\n\n'])[0]["status"] == DECLINED
+
+
+def test_stream_handle_rules(gw):
+    (h,) = gw.stream_open("openai", b"m")
+    with pytest.raises(Exception):
+        gw.stream_chunks([h, h], [b"a", b"b"], [False, False])   # one ResponseBody call per stream per batch
+    gw.stream_close([h])
+    with pytest.raises(Exception):
+        gw.stream_chunk(h, b"data: {}\n", False)                # closed handle
+    with pytest.raises(Exception):
+        gw.stream_open("openai", b'needs"escaping')
+    # a carry above the slot capacity declines the stream (sticky)
+    (h,) = gw.stream_open("openai", b"m")
+    r = gw.stream_chunk(h, b"x" * 9000, False); assert r["status"] == OKS and r["carry_len"] == 9000
+    r = gw.stream_chunk(h, b"y" * 9000, False); assert r["status"] == DECLINED and r["reason"] == 1
+    r = gw.stream_chunk(h, b"\n", False); assert r["status"] == DECLINED
+    gw.stream_close([h])
