@@ -72,30 +72,34 @@ enum Vid : uint8_t {
 enum RKid : uint8_t {
   RK_NONE = 0, RK_output, RK_message, RK_content, RK_role, RK_text, RK_toolUse, RK_toolUseId, RK_name, RK_input, RK_reasoningContent, RK_reasoningText,
   RK_signature, RK_redactedContent, RK_stopReason, RK_usage, RK_inputTokens, RK_outputTokens, RK_totalTokens, RK_cacheReadInputTokens, RK_cacheWriteInputTokens,
-  RK_serviceTier, RK_type, RK_metrics, RK_latencyMs, RK_document, RK_image, RK_toolResult, RK_cachePoint, RK_COUNT
+  RK_serviceTier, RK_type, RK_metrics, RK_latencyMs, RK_document, RK_image, RK_toolResult, RK_cachePoint,
+  // anthropic.Message (buffered GCP / AWS Anthropic responses)
+  RK_id, RK_model, RK_stop_reason, RK_thinking, RK_data, RK_input_tokens, RK_output_tokens, RK_cache_read_input_tokens, RK_cache_creation_input_tokens, RK_COUNT
 };
 #define AIGW_RKEYS(X) \
   X("output", RK_output) X("message", RK_message) X("content", RK_content) X("role", RK_role) X("text", RK_text) X("toolUse", RK_toolUse) X("toolUseId", RK_toolUseId) \
   X("name", RK_name) X("input", RK_input) X("reasoningContent", RK_reasoningContent) X("reasoningText", RK_reasoningText) X("signature", RK_signature) \
   X("redactedContent", RK_redactedContent) X("stopReason", RK_stopReason) X("usage", RK_usage) X("inputTokens", RK_inputTokens) X("outputTokens", RK_outputTokens) \
   X("totalTokens", RK_totalTokens) X("cacheReadInputTokens", RK_cacheReadInputTokens) X("cacheWriteInputTokens", RK_cacheWriteInputTokens) X("serviceTier", RK_serviceTier) \
-  X("type", RK_type) X("metrics", RK_metrics) X("latencyMs", RK_latencyMs) X("document", RK_document) X("image", RK_image) X("toolResult", RK_toolResult) X("cachePoint", RK_cachePoint)
+  X("type", RK_type) X("metrics", RK_metrics) X("latencyMs", RK_latencyMs) X("document", RK_document) X("image", RK_image) X("toolResult", RK_toolResult) X("cachePoint", RK_cachePoint) \
+  X("id", RK_id) X("model", RK_model) X("stop_reason", RK_stop_reason) X("thinking", RK_thinking) X("data", RK_data) X("input_tokens", RK_input_tokens) X("output_tokens", RK_output_tokens) \
+  X("cache_read_input_tokens", RK_cache_read_input_tokens) X("cache_creation_input_tokens", RK_cache_creation_input_tokens)
 
-static constexpr int kKeySlots = 128, kValSlots = 32, kMaxIdLen = 24;
-// slot = { six little-endian words of the string zero-padded to 24 bytes, len | id << 8 }
-struct IdSlot { uint32_t w[6]; uint32_t meta; };
+static constexpr int kKeySlots = 128, kValSlots = 32, kMaxIdLen = 28, kIdWords = 7;
+// slot = { seven little-endian words of the string zero-padded to 28 bytes, len | id << 8 }
+struct IdSlot { uint32_t w[kIdWords]; uint32_t meta; };
 struct alignas(16) IdTables { IdSlot key[kKeySlots]; IdSlot val[kValSlots]; };
 __host__ __device__ constexpr uint32_t id_hash(const uint32_t* v, uint32_t n) {
-  uint32_t h = v[0] * 0x9E3779B1u ^ v[1] * 0x85EBCA77u ^ v[2] * 0xC2B2AE3Du ^ v[3] * 0x27D4EB2Fu ^ v[4] * 0x165667B1u ^ v[5] * 0x2545F491u;
+  uint32_t h = v[0] * 0x9E3779B1u ^ v[1] * 0x85EBCA77u ^ v[2] * 0xC2B2AE3Du ^ v[3] * 0x27D4EB2Fu ^ v[4] * 0x165667B1u ^ v[5] * 0x2545F491u ^ v[6] * 0x7FEB352Du;
   h ^= h >> 15; h += n * 0x9E3779B1u; h ^= h >> 13;
   return h;
 }
 constexpr void id_insert(IdSlot* tab, int slots, const char* lit, int idv) {
-  uint32_t v[6] = {0, 0, 0, 0, 0, 0};
+  uint32_t v[kIdWords] = {0, 0, 0, 0, 0, 0, 0};
   int n = 0; while (lit[n]) { v[n >> 2] |= (uint32_t)(uint8_t)lit[n] << ((n & 3) * 8); n++; }
   int sl = id_hash(v, (uint32_t)n) & (slots - 1);
   while (tab[sl].meta) sl = (sl + 1) & (slots - 1);
-  for (int k = 0; k < 6; k++) tab[sl].w[k] = v[k];
+  for (int k = 0; k < kIdWords; k++) tab[sl].w[k] = v[k];
   tab[sl].meta = (uint32_t)n | ((uint32_t)idv << 8);
 }
 constexpr IdTables make_id_tables() {
@@ -137,12 +141,12 @@ __device__ __forceinline__ uint32_t lookup_id(const IdTables* T, const uint8_t* 
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
   const uint32_t sh = (a & 3u) * 8u;
   const uint32_t* wp = (const uint32_t*)(p - (a & 3u));
-  uint32_t x[7];
+  uint32_t x[kIdWords + 1];
 #pragma unroll
-  for (int k = 0; k < 7; k++) x[k] = wp[k];
-  uint32_t v[6];
+  for (int k = 0; k < kIdWords + 1; k++) x[k] = wp[k];
+  uint32_t v[kIdWords];
 #pragma unroll
-  for (int k = 0; k < 6; k++) {
+  for (int k = 0; k < kIdWords; k++) {
     const uint32_t rem = n > 4u * k ? n - 4u * k : 0u;
     const uint32_t m = rem >= 4u ? 0xffffffffu : ((1u << (8u * rem)) - 1u);
     v[k] = __funnelshift_r(x[k], x[k + 1], sh) & m;
@@ -155,7 +159,7 @@ __device__ __forceinline__ uint32_t lookup_id(const IdTables* T, const uint8_t* 
   for (int probe = 0; probe < 6; probe++) {
     const IdSlot e = tab[sl];
     if (e.meta == 0) return 0;
-    if ((e.meta & 0xffu) == n && e.w[0] == v[0] && e.w[1] == v[1] && e.w[2] == v[2] && e.w[3] == v[3] && e.w[4] == v[4] && e.w[5] == v[5]) return e.meta >> 8;
+    if ((e.meta & 0xffu) == n && e.w[0] == v[0] && e.w[1] == v[1] && e.w[2] == v[2] && e.w[3] == v[3] && e.w[4] == v[4] && e.w[5] == v[5] && e.w[6] == v[6]) return e.meta >> 8;
     sl = (sl + 1) & mask;
   }
   return 0;

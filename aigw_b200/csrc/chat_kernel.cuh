@@ -138,6 +138,10 @@ namespace aigw {
   X(L_R_FR_LENGTH, "length")                                                                    \
   X(L_R_FR_FILTER, "content_filter")                                                            \
   X(L_R_FR_TOOLS, "tool_calls")                                                                \
+  X(L_R_Q_ASSISTANT, "\"assistant\"")                                                          \
+  X(L_R_Q_USER, "\"user\"")                                                                    \
+  X(L_R_MODEL_KEY, ",\"model\":")                                                              \
+  X(L_R_ID_KEY, "\"id\":")                                                                     \
   X(L_EM_OPEN, "{\"instances\":")                                                               \
   X(L_EM_CONTENT, "{\"content\":")                                                              \
   X(L_EM_TASK, ",\"task_type\":")                                                               \

@@ -656,6 +656,106 @@ struct Walker {
     pl.lit(L_RBRACE);
   }
 
+  // Buffered anthropic.Message → openai.ChatCompletionResponse (internal/translator/openai_gcpanthropic.go:246-278 and
+  // messageToChatCompletion, anthropic_helper.go:1165-1255).  A known field of the wrong JSON type is left to the stock path
+  // (the SDK's decoder is lenient in ways no reference test pins); strings are echoed raw (the index kernel admits only escapes
+  // the encoder reproduces byte for byte).
+  __device__ void plan_anthropic_response(uint32_t& path_len, uint32_t& model_off, uint32_t& model_len) {
+    if (!is_obj(0)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }   // null decodes to a zero Message, other shapes are the SDK decoder's business: stock path
+    static const uint8_t k_root[] = {RK_id, RK_model, RK_stop_reason, RK_role, RK_usage, RK_content};
+    int r[6]; if (!rmembers(0, k_root, 6, r)) return;
+    const int id = r[0], model = r[1], stop = r[2], role = r[3], usage_o = r[4], content = r[5];
+    bool unp = false;
+    for (int k = 0; k < 4; k++) if (r[k] >= 0 && !is_str(r[k])) unp = true;
+    uint32_t u_in = 0, u_out = 0, u_rd = 0, u_cr = 0;
+    if (usage_o >= 0) {
+      if (!is_obj(usage_o)) unp = true;
+      else {
+        static const uint8_t k[] = {RK_input_tokens, RK_output_tokens, RK_cache_read_input_tokens, RK_cache_creation_input_tokens};
+        int q[4]; if (!rmembers(usage_o, k, 4, q)) return;
+        uint32_t* dst[4] = {&u_in, &u_out, &u_rd, &u_cr};
+        for (int i = 0; i < 4; i++) if (rint(q[i], *dst[i]) != 0) unp = true;
+      }
+    }
+    if (content >= 0 && !is_arr(content)) unp = true;
+    static const uint8_t kb[] = {RK_type, RK_text, RK_id, RK_name, RK_input, RK_thinking, RK_signature, RK_data};
+    int text = -1, think_blk = -1, n_tools = 0; bool redacted = false;
+    if (content >= 0 && is_arr(content)) {
+      for (int e = content + 1; d.ty(e) != ']'; e = d.after(e)) {
+        if (!is_obj(e)) { unp = true; continue; }
+        int q[8]; if (!rmembers(e, kb, 8, q)) return;
+        for (int k = 0; k < 8; k++) if (k != 4 && q[k] >= 0 && !is_str(q[k])) unp = true;
+        if (unp || q[0] < 0) continue;
+        if (d.str_has_backslash(q[0])) { unp = true; continue; }
+        if (str_is(q[0], "tool_use", 8)) { if (q[2] >= 0 && d.str_len(q[2]) > 0) n_tools++; }
+        else if (str_is(q[0], "text", 4)) { if (q[1] >= 0 && d.str_len(q[1]) > 0 && text < 0) text = q[1]; }
+        else if (str_is(q[0], "thinking", 8)) { if (q[5] >= 0 && d.str_len(q[5]) > 0) { think_blk = e; redacted = false; } }
+        else if (str_is(q[0], "redacted_thinking", 17)) { if (q[7] >= 0 && d.str_len(q[7]) > 0) redacted = true; }
+      }
+    }
+    if (unp || redacted) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }   // redactedContent is a re-encoded []byte: stock path
+    if (bad()) return;
+    // finish reason / role (errors of the reference)
+    int fr = -1;
+    if (stop >= 0) {
+      if (d.str_has_backslash(stop)) { decline(AIGW_R_ESCAPE); return; }
+      if (str_is(stop, "end_turn", 8) || str_is(stop, "stop_sequence", 13) || str_is(stop, "pause_turn", 10)) fr = L_R_FR_STOP;
+      else if (str_is(stop, "max_tokens", 10)) fr = L_R_FR_LENGTH; else if (str_is(stop, "tool_use", 8)) fr = L_R_FR_TOOLS; else if (str_is(stop, "refusal", 7)) fr = L_R_FR_FILTER;
+    }
+    int role_lit = -1;
+    if (role >= 0) { if (d.str_has_backslash(role)) { decline(AIGW_R_ESCAPE); return; } if (str_is(role, "assistant", 9)) role_lit = L_R_Q_ASSISTANT; else if (str_is(role, "user", 4)) role_lit = L_R_Q_USER; }
+    if (fr < 0 || role_lit < 0) { decline(AIGW_R_E500_DECODE); return; }   // "received invalid stop reason" / "invalid anthropic role"
+    const unsigned long long tin = (unsigned long long)u_in + u_rd + u_cr;
+    if (tin + u_out >= 0x80000000ull) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+    if (model >= 0 && d.str_len(model) > 0) { model_off = d.str_off(model); model_len = d.str_len(model); }
+    {
+      sc.n = (sc.n + 3u) & ~3u;
+      if (sc.n + 34 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
+      uint32_t* u = (uint32_t*)(sc.p + sc.n);
+      u[0] = (uint32_t)tin; u[1] = u_out; u[2] = (uint32_t)tin + u_out; u[3] = u_rd; u[4] = u_cr; u[5] = 0u; u[6] = 1u | 2u | 4u | 8u | 16u; u[7] = 0u;
+      pl.push(2, sc.n, 32); sc.n += 32;
+      path_len = 32;
+    }
+    pl.lit(L_LBRACE);
+    if (id >= 0 && d.str_len(id) > 0) { pl.lit(L_R_ID_KEY); emit_str(id); pl.lit(L_COMMA); }
+    pl.lit(L_R_CHOICES); pl.lit(fr); pl.lit(L_R_MSG);
+    if (text >= 0) { pl.lit(L_R_CONTENT); emit_str(text); pl.lit(L_COMMA); }
+    pl.lit(L_R_ROLE); pl.lit(role_lit);
+    if (n_tools) {
+      pl.lit(L_COMMA); pl.lit(L_R_TOOLCALLS);
+      bool tf = true;
+      for (int e = content + 1; d.ty(e) != ']'; e = d.after(e)) {
+        int q[8]; if (!rmembers(e, kb, 8, q)) return;
+        if (q[0] < 0 || !str_is(q[0], "tool_use", 8) || q[2] < 0 || d.str_len(q[2]) == 0) continue;
+        if (!tf) pl.lit(L_COMMA); tf = false;
+        pl.lit(L_R_TC_ID); emit_str(q[2]); pl.lit(L_R_TC_ARGS);
+        if (q[4] >= 0) emit_escaped_json(q[4]); else pl.lit(L_NULL);
+        if (bad()) return;
+        pl.lit(L_R_TC_NAME); if (q[3] >= 0) emit_str(q[3]); else pl.lit(L_EMPTY_STR);
+        pl.lit(L_R_TC_END);
+      }
+      pl.lit(L_RBRACK);
+    }
+    if (think_blk >= 0) {
+      int q[8]; if (!rmembers(think_blk, kb, 8, q)) return;
+      pl.lit(L_COMMA); pl.lit(L_R_REASON); pl.lit(L_R_RTEXT); emit_str(q[5]);
+      if (q[6] >= 0 && d.str_len(q[6]) > 0) { pl.lit(L_R_RSIG); emit_str(q[6]); }
+      pl.lit(L_RBRACE); pl.lit(L_R_RBRACE2);
+    }
+    pl.lit(L_R_CREATED);
+    emit_dec(P->created < 0 ? 0ull - (unsigned long long)P->created : (unsigned long long)P->created, P->created < 0);
+    if (model_len) { pl.lit(L_R_MODEL_KEY); emit_str(model); }
+    else if (P->override_len) { pl.lit(L_R_MODEL); emit_cfg_text(P->override_model, P->override_len); pl.lit(L_R_QUOTE); }
+    pl.lit(L_R_OBJECT); pl.lit(L_R_USAGE);
+    bool uf = true;
+    auto num = [&](int lit, uint32_t v) { if (!v) return; if (!uf) pl.lit(L_COMMA); uf = false; pl.lit(lit); emit_dec(v); };
+    num(L_R_PROMPT, (uint32_t)tin); num(L_R_COMPLETION, u_out); num(L_R_TOTAL, (uint32_t)tin + u_out);
+    if (!uf) pl.lit(L_COMMA);
+    pl.lit(L_R_PTD); uf = true;
+    num(L_R_CACHED, u_rd); num(L_R_CC, u_cr);
+    pl.lit(L_RBRACE); pl.lit(L_RBRACE); pl.lit(L_RBRACE);
+  }
+
   // ---------------------------------------------------------------- /v1/embeddings (P3 + T1 + T6)
   // EmbeddingsEndpointSpec.ParseBody (internal/endpointspec/endpointspec.go:231-240; input union internal/apischema/openai/union.go:71-147,
   // EmbeddingInputItem / EmbeddingContent internal/apischema/openai/openai.go:316-375) followed by the OpenAI / Azure passthrough
@@ -1540,7 +1640,8 @@ __device__ void walk_one(const ChatParams& P, uint32_t doc0, const WorkPtrs& wp,
     // error is "failed to unmarshal body"), so anything the token grammar rejects goes to the stock path
     if (reason) reason = AIGW_R_SYNTAX;
     else {
-      W.plan_bedrock_response(path_len);
+      if ((P.schema & 15) == AIGW_SCHEMA_GCP_ANTHROPIC) { uint32_t mo = 0, mlen = 0; W.plan_anthropic_response(path_len, mo, mlen); po.model_off = mo; po.model_len = (uint16_t)mlen; }
+      else W.plan_bedrock_response(path_len);
       W.pl.flush();
       reason = W.reason ? W.reason : W.pl.err;
       if (!reason && W.pl.nops == 0) reason = AIGW_R_OPS;

@@ -103,7 +103,7 @@ static void fill_params(ChatParams& P, const aigw_backend_cfg* cfg) {
   if (path.size() > sizeof P.openai_path) path.resize(sizeof P.openai_path);
   memcpy(P.openai_path, path.data(), path.size()); P.prefix_len = (uint16_t)path.size();
   P.created = 0; P.rid_len = 0; memset(P.response_id, 0, sizeof P.response_id);
-  if (cfg && (cfg->schema & 48) == AIGW_SCHEMA_RESP_AWS_BEDROCK) {
+  if (cfg && (cfg->schema & 48) == AIGW_SCHEMA_RESP_AWS_BEDROCK) {   // response direction (any backend)
     P.created = cfg->created;
     if (cfg->response_id) { size_t n = strlen(cfg->response_id); if (n > sizeof P.response_id) n = sizeof P.response_id; memcpy(P.response_id, cfg->response_id, n); P.rid_len = (uint16_t)n; }
   }

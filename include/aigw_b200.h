@@ -45,6 +45,12 @@ enum aigw_schema { AIGW_SCHEMA_OPENAI = 0, AIGW_SCHEMA_AWS_BEDROCK = 1, AIGW_SCH
                     * path_len == 32 and the usage struct sits where request schemas put the :path.
                     * status AIGW_INTERNAL = "failed to unmarshal body". */
                    AIGW_SCHEMA_RESP_AWS_BEDROCK = 16,
+                   /* buffered anthropic.Message → OpenAI ChatCompletionResponse: Translator.ResponseBody of the GCP / AWS Anthropic
+                    * translators (internal/translator/openai_gcpanthropic.go:237-278, messageToChatCompletion anthropic_helper.go:1165-1255).
+                    * cfg: model_name_override = the request model (used when the response carries no model), created.  Record layout as
+                    * above; aigw_doc_result.model_off / model_len = the response's own "model" string (responseModel) when present.
+                    * AIGW_INTERNAL = decode error / invalid stop reason / invalid role. */
+                   AIGW_SCHEMA_RESP_ANTHROPIC = 20,
                    /* /v1/embeddings requests (EmbeddingsEndpointSpec.ParseBody, internal/endpointspec/endpointspec.go:231-240, then the
                     * OpenAI / Azure passthrough translators internal/translator/openai_embeddings.go:38-59,
                     * openai_azureopenai_embeddings.go:36-61 or the Vertex predict translator openai_gcpvertexai_embeddings.go:46-180):
