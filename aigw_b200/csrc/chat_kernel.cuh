@@ -155,6 +155,28 @@ namespace aigw {
   X(L_EM_AZ_PATH1, "/openai/deployments/")                                                      \
   X(L_EM_AZ_PATH2, "/embeddings?api-version=")                                                 \
   X(L_EM_NEXT, "},{\"content\":")                                                               \
+  X(L_GEM_GENERATE, ":generateContent")                                                        \
+  X(L_GEM_STREAM, ":streamGenerateContent?alt=sse")                                            \
+  X(L_GEM_CONTENTS, "{\"contents\":")                                                          \
+  X(L_GEM_PARTS_OPEN, "{\"parts\":[")                                                          \
+  X(L_GEM_MODEL_EMPTY, "{\"role\":\"model\"}")                                                 \
+  X(L_GEM_MODEL_CLOSE, "],\"role\":\"model\"}")                                                \
+  X(L_GEM_TOOLS, ",\"tools\":")                                                                \
+  X(L_GEM_DECLS_OPEN, "[{\"functionDeclarations\":[")                                          \
+  X(L_GEM_DECLS_CLOSE, "]}]")                                                                  \
+  X(L_GEM_NAME, "\"name\":")                                                                   \
+  X(L_GEM_PARAMS, "\"parameters\":")                                                           \
+  X(L_GEM_PARAMS_JS, "\"parametersJsonSchema\":")                                              \
+  X(L_GEM_GENCFG, ",\"generation_config\":{")                                                  \
+  X(L_GEM_CANDIDATES, "\"candidateCount\":")                                                   \
+  X(L_GEM_FREQ, "\"frequencyPenalty\":")                                                       \
+  X(L_GEM_LOGPROBS, "\"logprobs\":")                                                           \
+  X(L_GEM_MAXOUT, "\"maxOutputTokens\":")                                                      \
+  X(L_GEM_PRES, "\"presencePenalty\":")                                                        \
+  X(L_GEM_RESP_LOGPROBS, "\"responseLogprobs\":true")                                          \
+  X(L_GEM_SEED, "\"seed\":")                                                                   \
+  X(L_GEM_SYS_OPEN, ",\"system_instruction\":{\"parts\":[")                                    \
+  X(L_GEM_SYS_CLOSE, "]}")                                                                     \
   X(L_EM_LAST, "}]")
 
 enum LitId : int {
@@ -166,7 +188,7 @@ enum LitId : int {
 
 struct alignas(16) LitTable {
   uint16_t off[L_COUNT + 1];
-  alignas(16) char bytes[2560];   // copied to shared memory with 32-bit loads
+  alignas(16) char bytes[3072];   // copied to shared memory with 32-bit loads
 };
 constexpr LitTable make_lit_table() {
   LitTable t{};

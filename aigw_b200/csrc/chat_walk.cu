@@ -1087,11 +1087,13 @@ struct Walker {
 
   struct Top { int model, messages, temperature, top_p, max_tokens, mct, stop, stream, stream_options, tools, tool_choice, thinking, service_tier;
                int model_raw, so_raw; /* value tokens even when null; -1 when the key is absent */
-               int reasoning_effort; };
+               int reasoning_effort;
+               int n, seed, top_logprobs, logprobs, freq_pen, pres_pen; /* Gemini generation_config */ };
 
   // top-level member scan with type checks for every known field (endpointspec.go:102-105)
   __device__ bool scan_top(Top& t) {
     t.model = t.messages = t.temperature = t.top_p = t.max_tokens = t.mct = t.stop = t.stream = t.stream_options = t.tools = t.tool_choice = t.thinking = t.service_tier = t.model_raw = t.so_raw = t.reasoning_effort = -1;
+    t.n = t.seed = t.top_logprobs = t.logprobs = t.freq_pen = t.pres_pen = -1;
     if (d.nt == 0 || !is_obj(0)) { decline(d.nt && is_null(0) ? AIGW_R_ROOT : AIGW_R_E400_TYPE); return false; }
     uint64_t seen = 0;
     for (int k = 1; d.ty(k) != '}'; k = d.after(k + 3)) {
@@ -1109,9 +1111,9 @@ struct Walker {
         case K_service_tier: t.service_tier = v; break;
         case K_reasoning_effort: if (!check_scalar_type(v, 0)) return false; t.reasoning_effort = v; break;
         case K_verbosity: case K_user: case K_guided_regex: if (!check_scalar_type(v, 0)) return false; break;
-        case K_logprobs: case K_parallel_tool_calls: if (!check_scalar_type(v, 1)) return false; break;
-        case K_top_logprobs: case K_seed: case K_n: if (!check_scalar_type(v, 2)) return false; break;
-        case K_frequency_penalty: case K_presence_penalty: if (!check_scalar_type(v, 3)) return false; break;
+        case K_logprobs: case K_parallel_tool_calls: if (!check_scalar_type(v, 1)) return false; if (id == K_logprobs) t.logprobs = v; break;
+        case K_top_logprobs: case K_seed: case K_n: if (!check_scalar_type(v, 2)) return false; if (id == K_n) t.n = v; else if (id == K_seed) t.seed = v; else t.top_logprobs = v; break;
+        case K_frequency_penalty: case K_presence_penalty: if (!check_scalar_type(v, 3)) return false; if (id == K_frequency_penalty) t.freq_pen = v; else t.pres_pen = v; break;
         case K_guided_json: break;  // json.RawMessage: anything
         default: decline(AIGW_R_UNSUPPORTED_FIELD); return false;  // modalities, audio, prediction, response_format, logit_bias, …: stock path
       }
@@ -1456,6 +1458,187 @@ struct Walker {
     return false;
   }
 
+  // ---- OpenAI → GCP Vertex AI Gemini (openai_gcpvertexai.go:93-126,512-580; gemini_helper.go:52-122,144-339,401-474,609-734).
+  // The layout the reference's goldens pin (testupstream_test.go:313,327,341,510) plus generation_config in genai's field order;
+  // FunctionCall / FunctionResponse parts, media parts, tool_choice, thinking and schemas beyond the restated subset are declined.
+  __device__ bool rm_contains(const Top& t, const char* needle, uint32_t n) {
+    if (!P->override_len) return model_contains(t.model, needle, n);
+    const char* p = P->override_model; const uint32_t L = P->override_len;
+    for (uint32_t i = 0; i + n <= L; i++) { uint32_t k = 0; while (k < n && p[i + k] == needle[k]) k++; if (k == n) return true; }
+    return false;
+  }
+  // float32 field: the literal is echoed when it has at most 6 significant digits (then float32 → shortest decimal gives it back)
+  __device__ void emit_f32_field(int v) {
+    const uint32_t e = d.scalar_end(v), o = d.tok(v);
+    const uint32_t l = canon_number(d.s + o, e - o, false);
+    if (!l) { decline(AIGW_R_NUMBER); return; }
+    uint32_t sig = 0; bool lead = true;
+    for (uint32_t i = o; i < o + l; i++) { const uint32_t c = d.s[i]; if (c - '0' < 10u) { if (c != '0') lead = false; if (!lead) sig++; } }
+    if (sig > 6) { decline(AIGW_R_NUMBER); return; }
+    pl.src(d, o, l);
+  }
+  // int32 field; zero = true when the value is 0 (omitempty fields)
+  __device__ bool emit_i32_field(int v, bool& zero, bool dry_only) {
+    const uint32_t e = d.scalar_end(v), o = d.tok(v);
+    const uint32_t l = canon_number(d.s + o, e - o, true);
+    if (!l || l > 9u + (d.s[o] == '-' ? 1u : 0u)) { decline(AIGW_R_NUMBER); return false; }
+    zero = (l == 1 && d.s[o] == '0');
+    if (!dry_only && !zero) pl.src(d, o, l);
+    return true;
+  }
+  // JSON schema subset whose conversion is a sorted re-marshal: {type, description: string; properties: {name: schema}; items: schema; required, enum: [string]}
+  __device__ bool gem_schema_ok(int root) {
+    int stack[24]; int sp = 0; stack[sp++] = root;
+    int guard = 0;
+    while (sp) {
+      const int o = stack[--sp];
+      if (!is_obj(o)) return false;
+      for (int m = o + 1; d.ty(m) != '}'; m = d.after(m + 3)) {
+        if (++guard > 512 || d.str_has_backslash(m)) return false;
+        const int v = m + 3;
+        if (str_eq_lit(m, "type", 4) || str_eq_lit(m, "description", 11)) { if (!is_str(v)) return false; }
+        else if (str_eq_lit(m, "properties", 10)) {
+          if (!is_obj(v)) return false;
+          for (int q = v + 1; d.ty(q) != '}'; q = d.after(q + 3)) { if (sp >= 24) return false; stack[sp++] = q + 3; }
+        } else if (str_eq_lit(m, "items", 5)) { if (sp >= 24) return false; stack[sp++] = v; }
+        else if (str_eq_lit(m, "required", 8) || str_eq_lit(m, "enum", 4)) { if (!is_arr(v)) return false; for (int q = v + 1; d.ty(q) != ']'; q = d.after(q)) if (!is_str(q)) return false; }
+        else return false;
+      }
+    }
+    return true;
+  }
+  __device__ void gem_text_part(int str_tok, bool& first, bool sys) {
+    if (!first) pl.lit(L_COMMA, sys); first = false;
+    pl.lit(L_TEXT_OPEN, sys); emit_str(str_tok, sys); pl.lit(L_RBRACE, sys);
+  }
+  __device__ void plan_gemini(const Top& t, bool stream, uint32_t& path_len) {
+    { uint32_t pl0 = 0; pl.dry = true; plan_bedrock(t, stream, pl0); pl.dry = false; pl.nsys = 0; sc.n = 0; }
+    if (bad()) return;
+    pending = 0;   // Bedrock's translator errors do not apply
+    if (t.tool_choice >= 0 || t.thinking >= 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+    if (t.reasoning_effort >= 0 && d.str_len(t.reasoning_effort) > 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+    // ":path"
+    pl.lit(L_EM_GOOGLE_PATH); emit_model(t, false); pl.lit(stream ? L_GEM_STREAM : L_GEM_GENERATE);
+    path_len = pl.olen;
+    if (bad()) return;
+    pl.lit(L_GEM_CONTENTS);
+    bool any_content = false, pending_open = false, pfirst = true, sys_first = true;
+    auto content_sep = [&] { if (!any_content) { pl.lit(L_LBRACK); any_content = true; } else pl.lit(L_COMMA); };
+    auto flush_user = [&] { if (pending_open) { pl.lit(L_USER_CLOSE); pending_open = false; pfirst = true; } };
+    if (t.messages >= 0) {
+      for (int e = t.messages + 1; d.ty(e) != ']'; e = d.after(e)) {
+        Msg g; const int role = scan_message(e, g);
+        if (bad()) return;
+        const int c = g.content;
+        if (role == 2 || role == 3) {
+          if (c < 0 || is_null(c)) { pend(AIGW_R_E422_CONTENT); continue; }
+          if (is_str(c)) { if (d.str_len(c) > 0) gem_text_part(c, sys_first, true); }
+          else { for (int q = c + 1; d.ty(q) != ']'; q = d.after(q)) { Part p; if (!scan_part(q, p)) return; if (p.text >= 0 && d.str_len(p.text) > 0) gem_text_part(p.text, sys_first, true); } }
+        } else if (role == 0) {
+          if (c < 0 || is_null(c)) { pend(AIGW_R_E422_CONTENT); continue; }
+          if (is_str(c)) { if (d.str_len(c) > 0) { if (!pending_open) { content_sep(); pl.lit(L_GEM_PARTS_OPEN); pending_open = true; } gem_text_part(c, pfirst, false); } }
+          else {
+            for (int q = c + 1; d.ty(q) != ']'; q = d.after(q)) {
+              Part p; if (!scan_part(q, p)) return;
+              if (p.text < 0 || d.str_len(p.text) == 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }   // Part{} layout: stock path
+              if (!pending_open) { content_sep(); pl.lit(L_GEM_PARTS_OPEN); pending_open = true; }
+              gem_text_part(p.text, pfirst, false);
+            }
+          }
+        } else if (role == 4) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }    // FunctionResponse part
+        else {
+          flush_user();
+          if (g.tool_calls >= 0 && !is_null(g.tool_calls) && d.ty(g.tool_calls + 1) != ']') { decline(AIGW_R_UNSUPPORTED_FIELD); return; }   // FunctionCall part
+          // does the message yield any part?
+          bool has_parts = false;
+          if (c >= 0 && !is_null(c)) {
+            if (is_str(c)) has_parts = d.str_len(c) > 0;
+            else if (is_arr(c)) {
+              for (int q = c + 1; d.ty(q) != ']'; q = d.after(q)) {
+                Part p; if (!scan_part(q, p)) return;
+                if (p.type < 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+                const uint32_t ty = d.id(p.type);
+                if (ty == V_text) { if (p.text >= 0 && d.str_len(p.text) > 0) has_parts = true; }
+                else if (ty != V_refusal) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }   // thought parts and unknown types
+              }
+            } else { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+          }
+          content_sep();
+          if (!has_parts) pl.lit(L_GEM_MODEL_EMPTY);
+          else {
+            pl.lit(L_GEM_PARTS_OPEN);
+            bool first = true;
+            if (is_str(c)) gem_text_part(c, first, false);
+            else for (int q = c + 1; d.ty(q) != ']'; q = d.after(q)) { Part p; if (!scan_part(q, p)) return; if (d.id(p.type) == V_text && p.text >= 0 && d.str_len(p.text) > 0) gem_text_part(p.text, first, false); }
+            pl.lit(L_GEM_MODEL_CLOSE);
+          }
+        }
+        if (bad()) return;
+      }
+    }
+    flush_user();
+    pl.lit(any_content ? L_RBRACK : L_NULL);
+    // tools
+    pl.lit(L_GEM_TOOLS);
+    bool any_decl = false;
+    if (t.tools >= 0) {
+      const bool json_schema = rm_contains(t, "gemini", 6) && (rm_contains(t, "2.5", 3) || rm_contains(t, "3", 1));
+      for (int e = t.tools + 1; d.ty(e) != ']'; e = d.after(e)) {
+        const int ty = find(e, K_type), fn = find(e, K_function);
+        if (bad()) return;
+        if (ty < 0 || !str_eq_lit(ty, "function", 8)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+        if (fn < 0) continue;
+        const int nm = find(fn, K_name), ds = find(fn, K_description), pr = find(fn, K_parameters);
+        if (bad()) return;
+        pl.lit(any_decl ? L_COMMA : L_GEM_DECLS_OPEN); any_decl = true;
+        pl.lit(L_LBRACE);
+        bool f = true;
+        if (ds >= 0 && d.str_len(ds) > 0) { pl.lit(L_DESC); emit_str(ds); f = false; }
+        if (nm >= 0 && d.str_len(nm) > 0) { if (!f) pl.lit(L_COMMA); pl.lit(L_GEM_NAME); emit_str(nm); f = false; }
+        if (pr >= 0) {
+          const bool empty_obj = is_obj(pr) && d.ty(pr + 1) == '}';
+          if (json_schema) { if (!empty_obj) { if (!f) pl.lit(L_COMMA); pl.lit(L_GEM_PARAMS_JS); emit_any(d, pl, pr); } }
+          else {
+            if (!is_obj(pr)) { pend(AIGW_R_E422_CONTENT); }
+            else if (!empty_obj) { if (!gem_schema_ok(pr)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; } if (!f) pl.lit(L_COMMA); pl.lit(L_GEM_PARAMS); emit_any(d, pl, pr); }
+          }
+          if (bad()) return;
+        }
+        pl.lit(L_RBRACE);
+      }
+    }
+    pl.lit(any_decl ? L_GEM_DECLS_CLOSE : L_NULL);
+    // generation_config, genai.GenerationConfig field order
+    pl.lit(L_GEM_GENCFG);
+    bool gf = true; bool zero = false;
+    auto sep = [&] { if (!gf) pl.lit(L_COMMA); gf = false; };
+    if (t.n >= 0) { if (!emit_i32_field(t.n, zero, true)) return; if (!zero) { sep(); pl.lit(L_GEM_CANDIDATES); emit_i32_field(t.n, zero, false); } }
+    if (t.freq_pen >= 0) { sep(); pl.lit(L_GEM_FREQ); emit_f32_field(t.freq_pen); }
+    if (t.top_logprobs >= 0) { if (!emit_i32_field(t.top_logprobs, zero, true)) return; sep(); pl.lit(L_GEM_LOGPROBS); if (zero) pl.lit(L_ZERO); else emit_i32_field(t.top_logprobs, zero, false); }
+    { const int mt = t.mct >= 0 ? t.mct : t.max_tokens; if (mt >= 0) { if (!emit_i32_field(mt, zero, true)) return; if (!zero) { sep(); pl.lit(L_GEM_MAXOUT); emit_i32_field(mt, zero, false); } } }
+    if (t.pres_pen >= 0) { sep(); pl.lit(L_GEM_PRES); emit_f32_field(t.pres_pen); }
+    if (t.logprobs >= 0 && d.ty(t.logprobs) == 't') { sep(); pl.lit(L_GEM_RESP_LOGPROBS); }
+    if (t.seed >= 0) { if (!emit_i32_field(t.seed, zero, true)) return; sep(); pl.lit(L_GEM_SEED); if (zero) pl.lit(L_ZERO); else emit_i32_field(t.seed, zero, false); }
+    if (t.stop >= 0) {
+      const int s = t.stop;
+      if (is_str(s)) { sep(); pl.lit(L_STOPSEQ); emit_str(s); pl.lit(L_RBRACK); }
+      else if (is_arr(s)) {
+        if (d.ty(s + 1) != ']') {
+          sep(); pl.lit(L_STOPSEQ);
+          bool sf = true;
+          for (int e = s + 1; d.ty(e) != ']'; e = d.after(e)) { if (!is_str(e)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; } if (!sf) pl.lit(L_COMMA); sf = false; emit_str(e); }
+          pl.lit(L_RBRACK);
+        }
+      } else { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+    }
+    if (t.temperature >= 0) { sep(); pl.lit(L_TEMP); emit_f32_field(t.temperature); }
+    if (t.top_p >= 0) { sep(); pl.lit(L_TOPP); emit_f32_field(t.top_p); }
+    pl.lit(L_RBRACE);
+    if (bad()) return;
+    if (pl.nsys) { pl.lit(L_GEM_SYS_OPEN); pl.flush_sys(); pl.lit(L_GEM_SYS_CLOSE); }
+    pl.lit(L_RBRACE);
+  }
+
   // ---- OpenAI → Anthropic messages API behind GCP rawPredict / AWS InvokeModel (anthropic_helper.go:455-569,661-747;
   // openai_gcpanthropic.go:56-100; openai_awsanthropic.go:54-100).  Only the layout the reference's goldens pin is
   // produced (testupstream_test.go:203,216,291,355,369,549); fields whose position the SDK decides are declined.
@@ -1665,6 +1848,7 @@ __device__ void walk_one(const ChatParams& P, uint32_t doc0, const WorkPtrs& wp,
       else if (P.schema == AIGW_SCHEMA_OPENAI) { uint32_t fl = po.flags, bk = AIGW_BODY_BYTES; W.plan_passthrough(t, stream, path_len, fl, bk); po.flags = (uint8_t)(fl | (bk == AIGW_BODY_UNCHANGED ? 0x80u : 0u)); }
       else if (P.schema == AIGW_SCHEMA_AZURE_OPENAI) { uint32_t fl = po.flags, bk = AIGW_BODY_UNCHANGED; W.plan_azure(t, stream, path_len, fl, bk); po.flags = (uint8_t)(fl | 0x80u); }
       else if (P.schema == AIGW_SCHEMA_GCP_ANTHROPIC || P.schema == AIGW_SCHEMA_AWS_ANTHROPIC) W.plan_anthropic(t, stream, P.schema == AIGW_SCHEMA_GCP_ANTHROPIC, path_len);
+      else if (P.schema == AIGW_SCHEMA_GCP_VERTEX) W.plan_gemini(t, stream, path_len);
       else W.decline(AIGW_R_SCHEMA);
     }
     W.pl.flush();

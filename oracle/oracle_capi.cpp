@@ -10,6 +10,8 @@
 #include "bedrock_response.hpp"
 #include "bedrock_stream.hpp"
 #include "anthropic_stream.hpp"
+#include "gemini.hpp"
+namespace oracle { TranslateResult gemini_request_body(const ChatReq& r, const std::string& model_override) { return gemini::request_body(r, model_override); } }
 #include "cel.hpp"
 #include "sha256.hpp"
 #include "embeddings.hpp"

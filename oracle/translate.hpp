@@ -429,6 +429,8 @@ inline TranslateResult request_body(const ChatReq& r, const Value& root, bool gc
 }
 }  // namespace anthropic
 
+TranslateResult gemini_request_body(const ChatReq& r, const std::string& model_override);   // gemini.hpp
+
 enum Schema : int { SCHEMA_OPENAI = 0, SCHEMA_AWS_BEDROCK = 1, SCHEMA_AZURE_OPENAI = 2, SCHEMA_GCP_VERTEX = 3, SCHEMA_GCP_ANTHROPIC = 4, SCHEMA_AWS_ANTHROPIC = 5 };
 
 // ParseBody + GetTranslator + RequestBody for one /v1/chat/completions body
@@ -452,6 +454,7 @@ inline TranslateResult chat_translate(int schema, std::string_view body, const s
     case SCHEMA_AZURE_OPENAI: res = azure::request_body(cur, r, prefix /* carries the api-version for this schema */, model_override, force || has_mut); break;
     case SCHEMA_GCP_ANTHROPIC: res = anthropic::request_body(r, root, true, model_override, prefix /* api version */); break;
     case SCHEMA_AWS_ANTHROPIC: res = anthropic::request_body(r, root, false, model_override, prefix /* api version */); break;
+    case SCHEMA_GCP_VERTEX: res = gemini_request_body(r, model_override); break;
     default: res.err = Error{DECLINED, "schema not restated yet"}; break;
   }
   res.mutated_body = mutated; res.has_mutated = has_mut; res.model = r.model; res.stream = r.stream;

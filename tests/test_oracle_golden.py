@@ -384,3 +384,40 @@ def test_anthropic_response_goldens():
         assert got == exp, c["name"]
         n += 1
     assert n >= 2
+
+
+# ---------------------------------------------------------------- T3: OpenAI → Gemini request
+def _gemini_cases():
+    for c in CASES:
+        if c.get("backend") == "gcp-vertexai" and "/v1/chat/completions" in c["name"] and "expRequestBody" in c:
+            yield c
+
+
+@pytest.mark.parametrize("case", list(_gemini_cases()), ids=lambda c: c["name"])
+def test_gemini_request_goldens(case):
+    """tests/data-plane/testupstream_test.go:313,327,341,510 — byte-exact (the fake upstream compares with bytes.Equal)"""
+    t = O.chat_translate("gcp-vertexai", case["requestBody"].encode(), cost_configured=True)
+    assert t.status == O.OK, t.err
+    assert t.body == case["expRequestBody"].encode()
+    assert "/v1/projects/gcp-project-name/locations/gcp-region/" + t.path == case["expPath"] + ("?alt=sse" if ":stream" in case["expPath"] else "")
+
+
+def test_gemini_request_rules():
+    tr = lambda b, **kw: O.chat_translate("gcp-vertexai", json.dumps(b).encode(), **kw)
+    t = tr({"model": "gemini-1.5-pro", "messages": [{"role": "system", "content": "S"}, {"role": "user", "content": "a"}, {"role": "user", "content": [{"type": "text", "text": "b"}]},
+                                                     {"role": "assistant", "content": "c"}, {"role": "user", "content": "d"}],
+            "temperature": 0.7, "top_p": 0.95, "max_tokens": 100, "stop": ["x", "y"], "n": 2, "seed": 7})
+    assert t.status == O.OK
+    assert t.body == (b'{"contents":[{"parts":[{"text":"a"},{"text":"b"}],"role":"user"},{"parts":[{"text":"c"}],"role":"model"},{"parts":[{"text":"d"}],"role":"user"}],"tools":null,'
+                      b'"generation_config":{"candidateCount":2,"maxOutputTokens":100,"seed":7,"stopSequences":["x","y"],"temperature":0.7,"topP":0.95},"system_instruction":{"parts":[{"text":"S"}]}}')
+    # float32 narrowing of temperature / top_p (gemini_helper.go:612-619)
+    t = tr({"model": "g", "messages": [], "temperature": 0.123456789, "top_p": 1})
+    assert b'"temperature":0.12345679,"topP":1}' in t.body
+    # gemini 2.5 / 3 models take the raw JSON schema (sorted keys), older ones the converted subset
+    tools = [{"type": "function", "function": {"name": "f", "parameters": {"type": "object", "additionalProperties": False, "properties": {}}}}]
+    assert tr({"model": "gemini-2.5-pro", "messages": [], "tools": tools}).body == b'{"contents":null,"tools":[{"functionDeclarations":[{"name":"f","parametersJsonSchema":{"additionalProperties":false,"properties":{},"type":"object"}}]}],"generation_config":{}}'
+    assert tr({"model": "gemini-1.5-pro", "messages": [], "tools": tools}).status == O.DECLINED
+    for body in ({"model": "g", "messages": [{"role": "tool", "content": "x", "tool_call_id": "t"}]}, {"model": "g", "messages": [], "tool_choice": "auto"},
+                 {"model": "g", "messages": [{"role": "user", "content": [{"type": "image_url", "image_url": {"url": "http://x"}}]}]}):
+        assert tr(body).status == O.DECLINED
+    assert tr({"model": "g", "messages": [], "stream": True}).path == "publishers/google/models/g:streamGenerateContent?alt=sse"
