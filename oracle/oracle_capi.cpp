@@ -11,6 +11,7 @@
 #include "bedrock_stream.hpp"
 #include "anthropic_stream.hpp"
 #include "gemini.hpp"
+#include "gemini_stream.hpp"
 namespace oracle { TranslateResult gemini_request_body(const ChatReq& r, const std::string& model_override) { return gemini::request_body(r, model_override); } }
 #include "cel.hpp"
 #include "sha256.hpp"
@@ -227,6 +228,24 @@ int oracle_anthropic_feed(void* hv, const char* chunk, uint64_t len, int eos, ch
 int oracle_anthropic_response(const char* body, uint64_t len, const char* request_model, int64_t created, char** out, uint64_t* out_len, oracle_usage* usage, char* model_buf, uint64_t cap, uint64_t* model_len) {
   AnthropicStreamCfg cfg; cfg.request_model = request_model ? request_model : ""; cfg.created = created;
   std::string o, rm; TokenUsage u; const Status s = anthropic_response(std::string_view(body, len), cfg, o, u, rm);
+  put(usage, u); *out = dup(o); *out_len = o.size();
+  uint64_t n = std::min<uint64_t>(cap, rm.size()); memcpy(model_buf, rm.data(), n); *model_len = rm.size();
+  return (int)s;
+}
+// ---- S4 / R1 (Gemini)
+struct GeminiHandle { GeminiStreamState st; GeminiCfg cfg; };
+void* oracle_gemini_open(const char* request_model) { auto* h = new GeminiHandle(); h->cfg.request_model = request_model ? request_model : ""; return h; }
+void oracle_gemini_close(void* h) { delete (GeminiHandle*)h; }
+int oracle_gemini_feed(void* hv, const char* chunk, uint64_t len, int eos, char** out, uint64_t* out_len, oracle_usage* usage, uint64_t* buffered) {
+  auto* h = (GeminiHandle*)hv; std::string o; TokenUsage u;
+  const Status s = gemini_stream_feed(h->st, h->cfg, std::string_view(chunk, len), eos != 0, o, u);
+  if (s != OK) o.clear();
+  put(usage, u); *out = dup(o); *out_len = o.size(); if (buffered) *buffered = h->st.buffered.size();
+  return (int)s;
+}
+int oracle_gemini_response(const char* body, uint64_t len, const char* request_model, char** out, uint64_t* out_len, oracle_usage* usage, char* model_buf, uint64_t cap, uint64_t* model_len) {
+  GeminiCfg cfg; cfg.request_model = request_model ? request_model : "";
+  std::string o, rm; TokenUsage u; const Status s = gemini_response(std::string_view(body, len), cfg, o, u, rm);
   put(usage, u); *out = dup(o); *out_len = o.size();
   uint64_t n = std::min<uint64_t>(cap, rm.size()); memcpy(model_buf, rm.data(), n); *model_len = rm.size();
   return (int)s;

@@ -253,3 +253,32 @@ class BedrockStream:
     def __del__(self):
         if getattr(self, "h", None):
             lib().oracle_bedrock_close(self.h); self.h = None
+
+
+class GeminiStream:
+    """Gemini handleStreamingResponse per call (S4): feed(chunk, eos) → (status, body mutation bytes, Usage, buffered length)."""
+    def __init__(self, request_model: bytes):
+        L = lib(); L.oracle_gemini_open.restype = C.c_void_p; L.oracle_gemini_open.argtypes = [C.c_char_p]
+        L.oracle_gemini_feed.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(Usage), C.POINTER(C.c_uint64)]
+        L.oracle_gemini_close.argtypes = [C.c_void_p]
+        self.h = L.oracle_gemini_open(request_model)
+
+    def feed(self, chunk: bytes, eos: bool):
+        vp = C.c_void_p(); n = C.c_uint64(0); u = Usage(); bl = C.c_uint64(0)
+        st = lib().oracle_gemini_feed(self.h, chunk, len(chunk), int(eos), C.byref(vp), C.byref(n), C.byref(u), C.byref(bl))
+        out = C.string_at(vp, n.value); lib().oracle_free(vp)
+        return st, out, u, bl.value
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_gemini_close(self.h); self.h = None
+
+
+def gemini_response(body: bytes, request_model: bytes):
+    """Buffered genai.GenerateContentResponse → (status, ChatCompletionResponse JSON bytes, Usage, response model)."""
+    L = lib()
+    L.oracle_gemini_response.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(Usage), C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    vp = C.c_void_p(); n = C.c_uint64(0); u = Usage(); buf = C.create_string_buffer(4096); ml = C.c_uint64(0)
+    st = L.oracle_gemini_response(body, len(body), request_model, C.byref(vp), C.byref(n), C.byref(u), buf, 4096, C.byref(ml))
+    out = C.string_at(vp, n.value); L.oracle_free(vp)
+    return st, out, u, buf.raw[:ml.value]
