@@ -423,6 +423,259 @@ __device__ void step_bedrock(StreamSlot& S, const StreamStep& st, uint8_t* out, 
   if (wn + S.model_len <= st.out_cap) { for (uint32_t k = 0; k < S.model_len; k++) out[wn + k] = (uint8_t)S.model[k]; R.model_len = S.model_len; }
 }
 
+// ------------------------------------------------------------------ S4 / R1: Gemini GenerateContentResponse → OpenAI
+// (handleStreamingResponse / parseGCPStreamingChunks / convertGCPChunkToOpenAI, internal/translator/openai_gcpvertexai.go:202-337,390-482;
+//  buffered: ResponseBody :139-198, geminiCandidatesToOpenAIChoices gemini_helper.go:741-828; usage :942-958; finish reasons :836-868)
+static constexpr int kGemCands = 2, kGemTexts = 8;
+struct GemCand { uint32_t null_, has_content, ntext; uint32_t toff[kGemTexts], tlen[kGemTexts]; uint32_t tthought; uint32_t fin_off, fin_len; };
+struct GemResp { uint32_t id_off, id_len, mv_off, mv_len, has_time, has_usage, ncand; long long created; uint32_t prompt, cand, total, cached, thoughts; GemCand c[kGemCands]; };
+
+__device__ __forceinline__ int skipws(const uint8_t* p, int i, int n) { while (i < n && ws(p[i])) i++; return i; }
+// object member iteration over syntactically valid JSON: i = position after '{' or after the previous value; false at '}'
+__device__ bool next_member(const uint8_t* p, int& i, int n, int& ks, int& kl, bool& kesc, int& vs, int& ve) {
+  i = skipws(p, i, n);
+  if (p[i] == ',') i = skipws(p, i + 1, n);
+  if (p[i] == '}') { i++; return false; }
+  kesc = false; const int e = scan_string(p, i, n, kesc);
+  ks = i + 1; kl = e - i - 2;
+  i = skipws(p, e, n); i = skipws(p, i + 1, n);   // ':'
+  vs = i; ve = skip_any(p, i, n); i = ve;
+  return true;
+}
+__device__ bool next_elem(const uint8_t* p, int& i, int n, int& vs, int& ve) {
+  i = skipws(p, i, n);
+  if (p[i] == ',') i = skipws(p, i + 1, n);
+  if (p[i] == ']') { i++; return false; }
+  vs = i; ve = skip_any(p, i, n); i = ve;
+  return true;
+}
+__device__ __forceinline__ bool is_null_at(const uint8_t* p, int vs) { return p[vs] == 'n'; }
+// RFC 3339 → Unix seconds
+__device__ bool rfc3339_unix(const uint8_t* s, int n, long long& out) {
+  auto dig = [&](int i) { return i < n && s[i] - '0' < 10u; };
+  auto num = [&](int i, int k, int& v) { v = 0; for (int t = 0; t < k; t++) { if (!dig(i + t)) return false; v = v * 10 + (s[i + t] - '0'); } return true; };
+  int Y, M, D, h, m, sec;
+  if (n < 20 || !num(0, 4, Y) || s[4] != '-' || !num(5, 2, M) || s[7] != '-' || !num(8, 2, D) || (s[10] != 'T' && s[10] != 't') || !num(11, 2, h) || s[13] != ':' || !num(14, 2, m) || s[16] != ':' || !num(17, 2, sec)) return false;
+  int i = 19;
+  if (i < n && s[i] == '.') { i++; if (!dig(i)) return false; while (dig(i)) i++; }
+  int off = 0;
+  if (i < n && (s[i] == 'Z' || s[i] == 'z')) i++;
+  else { int oh, om; if (i + 6 > n || (s[i] != '+' && s[i] != '-') || !num(i + 1, 2, oh) || s[i + 3] != ':' || !num(i + 4, 2, om)) return false; off = (oh * 60 + om) * 60 * (s[i] == '-' ? -1 : 1); i += 6; }
+  if (i != n || M < 1 || M > 12 || D < 1 || D > 31 || h > 23 || m > 59 || sec > 59) return false;
+  const long long y = Y - (M <= 2); const long long era = (y >= 0 ? y : y - 399) / 400; const long long yoe = y - era * 400;
+  const long long doy = (153 * (M + (M > 2 ? -3 : 9)) + 2) / 5 + D - 1; const long long doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+  out = (era * 146097 + doe - 719468) * 86400 + h * 3600 + m * 60 + sec - off;
+  return true;
+}
+// 0 decoded, 1 not decodable (syntax / trailing bytes), 2 unpinned (stock path)
+__device__ int gem_decode(const uint8_t* p, int n, GemResp& g, bool buffered) {
+  memset(&g, 0, sizeof g);
+  int i = skipws(p, 0, n);
+  const int root_end = skip_any(p, i, n);
+  if (root_end < 0) return 1;
+  if (!buffered && skipws(p, root_end, n) != n) return 1;
+  if (p[i] == 'n') return 0;
+  if (p[i] != '{') return 2;
+  bool unp = false;
+  auto str_span = [&](int vs, int ve, uint32_t& off, uint32_t& len) { if (is_null_at(p, vs)) return; if (p[vs] != '"') { unp = true; return; } off = vs + 1; len = ve - vs - 2; if (!canonical(p + off, len)) unp = true; };
+  auto u31 = [&](int vs, int ve, uint32_t& out) { if (is_null_at(p, vs)) return; bool ii; int ie; if (!(p[vs] == '-' || dig(p[vs])) || scan_number(p, vs, n, ii, ie) != ve || !ii) { unp = true; return; } uint32_t v; bool big = false; if (!parse_i64(p, vs, ve, v, &big) || big) { unp = true; return; } out = v; };
+  int ks, kl, vs, ve; bool kesc;
+  i++;
+  while (next_member(p, i, n, ks, kl, kesc, vs, ve)) {
+    if (kesc) { unp = true; continue; }
+    const uint8_t* k = p + ks;
+    if (EQ(k, kl, "responseId")) str_span(vs, ve, g.id_off, g.id_len);
+    else if (EQ(k, kl, "modelVersion")) str_span(vs, ve, g.mv_off, g.mv_len);
+    else if (EQ(k, kl, "createTime")) { if (!is_null_at(p, vs)) { if (p[vs] != '"' || !rfc3339_unix(p + vs + 1, ve - vs - 2, g.created)) unp = true; else g.has_time = 1; } }
+    else if (EQ(k, kl, "usageMetadata")) {
+      if (is_null_at(p, vs)) continue;
+      if (p[vs] != '{') { unp = true; continue; }
+      g.has_usage = 1;
+      int j = vs + 1, ks2, kl2, vs2, ve2; bool ke2;
+      while (next_member(p, j, n, ks2, kl2, ke2, vs2, ve2)) {
+        const uint8_t* q = p + ks2;
+        if (EQ(q, kl2, "promptTokenCount")) u31(vs2, ve2, g.prompt); else if (EQ(q, kl2, "candidatesTokenCount")) u31(vs2, ve2, g.cand); else if (EQ(q, kl2, "totalTokenCount")) u31(vs2, ve2, g.total);
+        else if (EQ(q, kl2, "cachedContentTokenCount")) u31(vs2, ve2, g.cached); else if (EQ(q, kl2, "thoughtsTokenCount")) u31(vs2, ve2, g.thoughts);
+      }
+    } else if (EQ(k, kl, "candidates")) {
+      if (is_null_at(p, vs)) continue;
+      if (p[vs] != '[') { unp = true; continue; }
+      int j = vs + 1, cs, ce;
+      while (next_elem(p, j, n, cs, ce)) {
+        if (g.ncand >= (uint32_t)kGemCands) { unp = true; continue; }
+        GemCand& c = g.c[g.ncand++];
+        if (is_null_at(p, cs)) { c.null_ = 1; continue; }
+        if (p[cs] != '{') { unp = true; continue; }
+        int a = cs + 1, ks2, kl2, vs2, ve2; bool ke2;
+        while (next_member(p, a, n, ks2, kl2, ke2, vs2, ve2)) {
+          const uint8_t* q = p + ks2;
+          if (EQ(q, kl2, "finishReason")) { str_span(vs2, ve2, c.fin_off, c.fin_len); }
+          else if (buffered && (EQ(q, kl2, "safetyRatings") || EQ(q, kl2, "groundingMetadata") || EQ(q, kl2, "logprobsResult"))) { if (!is_null_at(p, vs2)) unp = true; }
+          else if (EQ(q, kl2, "content")) {
+            if (is_null_at(p, vs2)) continue;
+            if (p[vs2] != '{') { unp = true; continue; }
+            c.has_content = 1;
+            int b = vs2 + 1, ks3, kl3, vs3, ve3; bool ke3;
+            while (next_member(p, b, n, ks3, kl3, ke3, vs3, ve3)) {
+              if (!EQ(p + ks3, kl3, "parts") || is_null_at(p, vs3)) continue;
+              if (p[vs3] != '[') { unp = true; continue; }
+              int e = vs3 + 1, ps, pe;
+              while (next_elem(p, e, n, ps, pe)) {
+                if (is_null_at(p, ps)) continue;
+                if (p[ps] != '{') { unp = true; continue; }
+                uint32_t toff = 0, tlen = 0; bool thought = false;
+                int f = ps + 1, ks4, kl4, vs4, ve4; bool ke4;
+                while (next_member(p, f, n, ks4, kl4, ke4, vs4, ve4)) {
+                  const uint8_t* r = p + ks4;
+                  if (EQ(r, kl4, "text")) str_span(vs4, ve4, toff, tlen);
+                  else if (EQ(r, kl4, "thought")) { if (p[vs4] == 't') thought = true; else if (p[vs4] != 'f' && !is_null_at(p, vs4)) unp = true; }
+                  else if (EQ(r, kl4, "functionCall") || EQ(r, kl4, "thoughtSignature")) { if (!is_null_at(p, vs4)) unp = true; }
+                }
+                if (tlen) { if (c.ntext >= (uint32_t)kGemTexts) unp = true; else { c.toff[c.ntext] = toff; c.tlen[c.ntext] = tlen; if (thought) c.tthought |= 1u << c.ntext; c.ntext++; } }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  return unp ? 2 : 0;
+}
+__device__ void gem_finish(Wr& w, const uint8_t* p, const GemCand& c, bool always) {
+  const uint8_t* q = p + c.fin_off; const uint32_t l = c.fin_len;
+  const char* fr; uint32_t fl;
+  if (l == 0) { fr = ""; fl = 0; }
+  else if (EQ(q, l, "STOP")) { fr = "stop"; fl = 4; } else if (EQ(q, l, "MAX_TOKENS")) { fr = "length"; fl = 6; }
+  else if (EQ(q, l, "SAFETY") || EQ(q, l, "BLOCKLIST") || EQ(q, l, "PROHIBITED_CONTENT") || EQ(q, l, "SPII") || EQ(q, l, "IMAGE_SAFETY") || EQ(q, l, "IMAGE_PROHIBITED_CONTENT")) { fr = "content_filter"; fl = 14; }
+  else if (EQ(q, l, "RECITATION") || EQ(q, l, "IMAGE_RECITATION")) { fr = "recitation"; fl = 10; } else if (EQ(q, l, "MALFORMED_FUNCTION_CALL")) { fr = "malformed_function_call"; fl = 23; }
+  else if (EQ(q, l, "UNEXPECTED_TOOL_CALL")) { fr = "unexpected_tool_call"; fl = 20; } else if (EQ(q, l, "LANGUAGE")) { fr = "language"; fl = 8; } else if (EQ(q, l, "NO_IMAGE")) { fr = "no_image"; fl = 8; }
+  else { fr = "error"; fl = 5; }
+  if (always) { WL(w, "{\"finish_reason\":\""); w.lit(fr, fl); w.ch('"'); }
+  else if (fl) { WL(w, ",\"finish_reason\":\""); w.lit(fr, fl); w.ch('"'); }
+}
+__device__ void gem_usage(Wr& w, const GemResp& g) {
+  bool f = true;
+  auto num = [&](const char* k, uint32_t kl, uint32_t v) { if (!v) return; if (!f) w.ch(','); f = false; w.lit(k, kl); w.dec(v); };
+  w.ch('{'); num("\"prompt_tokens\":", 16, g.prompt); num("\"completion_tokens\":", 20, g.cand + g.thoughts); num("\"total_tokens\":", 15, g.total);
+  if (!f) w.ch(',');
+  WL(w, "\"completion_tokens_details\":{"); if (g.thoughts) { WL(w, "\"reasoning_tokens\":"); w.dec(g.thoughts); }
+  WL(w, "},\"prompt_tokens_details\":{"); if (g.cached) { WL(w, "\"cached_tokens\":"); w.dec(g.cached); }
+  WL(w, "}}");
+}
+__device__ void gem_texts(Wr& w, const uint8_t* p, const GemCand& c, bool thought) { for (uint32_t k = 0; k < c.ntext; k++) if ((((c.tthought >> k) & 1u) != 0) == thought) w.raw(p + c.toff[k], c.tlen[k]); }
+__device__ bool gem_has(const GemCand& c, bool thought) { for (uint32_t k = 0; k < c.ntext; k++) if ((((c.tthought >> k) & 1u) != 0) == thought) return true; return false; }
+
+__device__ void gem_stream_chunk(StreamSlot& S, Wr& w, const uint8_t* p, const GemResp& g) {
+  auto head = [&] { WL(w, "data: {"); if (g.id_len) { WL(w, "\"id\":\""); w.raw(p + g.id_off, g.id_len); WL(w, "\","); } };
+  auto tail = [&] { if (g.has_time) { WL(w, ",\"created\":"); w.sdec(g.created); } if (S.model_len) { WL(w, ",\"model\":\""); w.raw((const uint8_t*)S.model, S.model_len); w.ch('"'); } WL(w, ",\"object\":\"chat.completion.chunk\""); };
+  head(); WL(w, "\"choices\":[");
+  bool cf = true;
+  for (uint32_t ci = 0; ci < g.ncand; ci++) {
+    const GemCand& c = g.c[ci];
+    if (c.null_) continue;
+    if (!cf) w.ch(','); cf = false;
+    WL(w, "{\"index\":"); w.dec(ci); WL(w, ",\"delta\":{");
+    if (c.has_content) {
+      if (gem_has(c, false)) { WL(w, "\"content\":\""); gem_texts(w, p, c, false); WL(w, "\","); }
+      WL(w, "\"role\":\"assistant\"");
+      if (gem_has(c, true)) { WL(w, ",\"reasoning_content\":{\"text\":\""); gem_texts(w, p, c, true); WL(w, "\"}"); }
+    }
+    w.ch('}'); gem_finish(w, p, c, false); w.ch('}');
+  }
+  w.ch(']'); tail(); WL(w, "}\n\n");
+  if (g.has_usage && g.prompt > 0) { head(); WL(w, "\"choices\":[]"); tail(); WL(w, ",\"usage\":"); gem_usage(w, g); WL(w, "}\n\n"); }
+}
+
+__device__ void step_gemini(StreamSlot& S, const StreamStep& st, uint8_t* out, aigw_chunk_result& R) {
+  uint8_t* b = S.buf; const uint32_t n = S.end; const uint32_t old_len = S._r0;   // carry length before this call's append
+  Wr w{out, 0, st.out_cap, 0};
+  aigw_usage u; memset(&u, 0, sizeof u);
+  int status = 0;
+  if (n) {
+    if (S.stop_reason == 0) {   // delimiter not detected yet: CRLFCRLF, LFLF, CRCR in that order of preference
+      bool crlf = false, lf = false, cr = false;
+      for (uint32_t i = 0; i + 1 < n; i++) { if (b[i] == '\n' && b[i + 1] == '\n') lf = true; if (b[i] == '\r' && b[i + 1] == '\r') cr = true; if (i + 3 < n && b[i] == '\r' && b[i + 1] == '\n' && b[i + 2] == '\r' && b[i + 3] == '\n') crlf = true; }
+      S.stop_reason = crlf ? 1u : lf ? 2u : cr ? 3u : 0u;
+    }
+    const uint32_t dk = S.stop_reason, dl = dk == 1 ? 4u : dk ? 2u : 0u;
+    uint32_t pos = 0; bool touched = false; uint32_t nb_off = 0, nb_len = old_len;   // the new bufferedBody as a span of b
+    for (;;) {
+      uint32_t cut = n; 
+      if (dk) for (uint32_t i = pos; i + dl <= n; i++) { const bool m = dk == 1 ? (b[i] == '\r' && b[i + 1] == '\n' && b[i + 2] == '\r' && b[i + 3] == '\n') : dk == 2 ? (b[i] == '\n' && b[i + 1] == '\n') : (b[i] == '\r' && b[i + 1] == '\r'); if (m) { cut = i; break; } }
+      const uint8_t* part = b + pos; uint32_t pl = cut - pos;
+      trim_space(part, pl);
+      if (pl) {
+        if (prefix(part, pl, "data: ", 6)) { part += 6; pl -= 6; }
+        GemResp g;
+        const int rc = gem_decode(part, (int)pl, g, false);
+        if (rc == 2) { status = AIGW_DECLINED; break; }
+        touched = true;
+        if (rc == 1) { nb_off = (uint32_t)(part - b); nb_len = pl; }
+        else {
+          nb_len = 0;
+          gem_stream_chunk(S, w, part, g);
+          if (g.has_usage && g.prompt > 0) { u.input = g.prompt; u.output = g.cand; u.total = g.total; u.cached = g.cached; u.reasoning = g.thoughts; u.mask = 1u | 2u | 4u | 8u | 32u; }
+        }
+      }
+      if (cut >= n) break;
+      pos = cut + dl;
+    }
+    if (!status) {
+      if (!touched) { nb_off = 0; nb_len = old_len; }
+      for (uint32_t k = 0; k < nb_len; k++) b[k] = b[nb_off + k];   // bufferedBody := the (trimmed, prefix-stripped) undecodable part; forward copy, nb_off ≥ 0
+      S.beg = 0; S.end = nb_len;
+    }
+  }
+  if (!status && st.eos) WL(w, "data: [DONE]\n");
+  if (!status && w.ovf) status = AIGW_DECLINED;
+  if (status) { S.flags |= SF_DEAD; S.dead_status = (uint32_t)status; S.dead_reason = w.ovf ? AIGW_R_OUT_SPACE : AIGW_R_UNSUPPORTED_FIELD; R.status = (uint8_t)status; R.reason = (uint8_t)S.dead_reason; return; }
+  R.usage = u; R.out_len = w.n; R.body_kind = w.n ? AIGW_BODY_BYTES : AIGW_BODY_EMPTY;
+  if (w.n + S.model_len <= st.out_cap) { for (uint32_t k = 0; k < S.model_len; k++) out[w.n + k] = (uint8_t)S.model[k]; R.model_len = S.model_len; }
+}
+
+// buffered response: the body accumulates in the slot; the last call (eos) converts it
+__device__ void step_gemini_buffered(StreamSlot& S, const StreamStep& st, uint8_t* out, aigw_chunk_result& R) {
+  if (!st.eos) { R.body_kind = AIGW_BODY_EMPTY; return; }
+  const uint8_t* b = S.buf; const int n = (int)S.end;
+  Wr w{out, 0, st.out_cap, 0};
+  GemResp g;
+  const int rc = gem_decode(b, n, g, true);
+  int status = rc == 1 ? AIGW_INTERNAL : rc == 2 ? AIGW_DECLINED : 0;   // "error decoding GCP response"
+  if (!status) for (uint32_t ci = 0; ci < g.ncand; ci++) if (!g.c[ci].null_ && !g.c[ci].has_content) status = AIGW_DECLINED;
+  if (!status) {
+    w.ch('{');
+    if (g.id_len) { WL(w, "\"id\":\""); w.raw(b + g.id_off, g.id_len); WL(w, "\","); }
+    WL(w, "\"choices\":[");
+    bool cf = true;
+    for (uint32_t ci = 0; ci < g.ncand; ci++) {
+      const GemCand& c = g.c[ci];
+      if (c.null_) continue;
+      if (!cf) w.ch(','); cf = false;
+      gem_finish(w, b, c, true); WL(w, ",\"index\":"); w.dec(ci); WL(w, ",\"message\":{");
+      if (gem_has(c, false)) { WL(w, "\"content\":\""); gem_texts(w, b, c, false); WL(w, "\","); }
+      WL(w, "\"role\":\"assistant\"");
+      if (gem_has(c, true)) { WL(w, ",\"reasoning_content\":\""); gem_texts(w, b, c, true); w.ch('"'); }
+      WL(w, "}}");
+    }
+    w.ch(']');
+    if (g.has_time) { WL(w, ",\"created\":"); w.sdec(g.created); }
+    const uint8_t* m = g.mv_len ? b + g.mv_off : (const uint8_t*)S.model; const uint32_t ml = g.mv_len ? g.mv_len : S.model_len;
+    if (ml) { WL(w, ",\"model\":\""); w.raw(m, ml); w.ch('"'); }
+    WL(w, ",\"object\":\"chat.completion\"");
+    if (g.has_usage) { WL(w, ",\"usage\":"); gem_usage(w, g); }
+    w.ch('}');
+    if (w.ovf) status = AIGW_DECLINED;
+    else {
+      R.usage.input = g.prompt; R.usage.output = g.cand + g.thoughts; R.usage.total = g.total; R.usage.mask = 7u;
+      if (g.has_usage) { R.usage.cached = g.cached; R.usage.reasoning = g.thoughts; R.usage.mask |= 8u | 32u; }
+      R.out_len = w.n; R.body_kind = AIGW_BODY_BYTES;
+      if (w.n + ml <= st.out_cap) { for (uint32_t k = 0; k < ml; k++) out[w.n + k] = m[k]; R.model_len = ml; }
+      S.beg = S.end;
+    }
+  }
+  if (status) { S.flags |= SF_DEAD; S.dead_status = (uint32_t)status; S.dead_reason = w.ovf ? AIGW_R_OUT_SPACE : AIGW_R_UNSUPPORTED_FIELD; R.status = (uint8_t)status; R.reason = (uint8_t)S.dead_reason; }
+}
+
 // ------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(128) stream_init_kernel(StreamSlot* slots, const uint32_t* slot_ids, uint32_t n, const uint8_t* tmpl) {
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -438,6 +691,7 @@ __global__ void __launch_bounds__(128) stream_append_kernel(const __grid_constan
   StreamSlot& S = P.slots[st.slot];
   if (S.flags & SF_DEAD) return;
   const uint32_t beg = S.beg, end = S.end, n = end - beg;
+  if (lane == 0) S._r0 = n;   // carry length before this call (the Gemini step restates bufferedBody from it)
   if (beg) {   // move the carry to the front (reads of one batch complete before its writes; later batches read further right)
     for (uint32_t i0 = 0; i0 < n; i0 += 32) {
       const uint32_t i = i0 + lane;
@@ -471,6 +725,8 @@ __global__ void __launch_bounds__(64) stream_step_kernel(const __grid_constant__
       case AIGW_STREAM_OPENAI: step_openai(S, st, out, R); break;
       case AIGW_STREAM_AWS_BEDROCK: step_bedrock(S, st, out, R); break;
       case AIGW_STREAM_GCP_ANTHROPIC: step_anthropic(S, st, out, R); break;
+      case AIGW_STREAM_GCP_GEMINI: step_gemini(S, st, out, R); break;
+      case AIGW_STREAM_GCP_GEMINI_BUFFERED: step_gemini_buffered(S, st, out, R); break;
       default: R.status = AIGW_DECLINED; R.reason = AIGW_R_SCHEMA; break;
     }
   }

@@ -245,3 +245,115 @@ def test_stream_handle_rules(gw):
     r = gw.stream_chunk(h, b"y" * 9000, False); assert r["status"] == DECLINED and r["reason"] == 1
     r = gw.stream_chunk(h, b"\n", False); assert r["status"] == DECLINED
     gw.stream_close([h])
+
+
+# ---------------------------------------------------------------- S4 / R1: Gemini
+def _gemini_sse(body):
+    return [b"data: " + l.encode() + b"\n\n" for l in body.split("\n") if l.strip()]
+
+
+@pytest.mark.parametrize("chunking", ["events", "whole", "bytes", "random"])
+def test_gemini_stream_golden_and_chunkings(gw, chunking):
+    """tests/data-plane/testupstream_test.go:523 byte-exact for event-aligned chunkings; for cuts inside an event the reference's own
+    (chunking dependent) TrimSpace'd carry is reproduced call by call against the oracle"""
+    c = next(c for c in CASES if c["name"] == "gcp-vertexai - /v1/chat/completions - streaming")
+    ev = _gemini_sse(c["responseBody"]); whole = b"".join(ev)
+    if chunking == "events": chunks = ev
+    elif chunking == "whole": chunks = [whole]
+    elif chunking == "bytes": chunks = [whole[i:i + 1] for i in range(len(whole))]
+    else:
+        rng = random.Random(9); cuts = sorted(rng.sample(range(1, len(whole)), 23)); chunks = [whole[a:b] for a, b in zip([0] + cuts, cuts + [len(whole)])]
+    (h,) = gw.stream_open("gcp-vertexai", b"gemini-1.5-pro")
+    orc = O.GeminiStream(b"gemini-1.5-pro")
+    out = b""
+    for ch in chunks + [None]:
+        eos = ch is None
+        r = gw.stream_chunk(h, ch or b"", eos)
+        s, o, u, bl = orc.feed(ch or b"", eos)
+        assert r["status"] == s == OKS
+        assert r["body"] == o and r["usage"] == u.as_tuple() and r["carry_len"] == bl, (chunking, ch)
+        out += r["body"]
+    if chunking in ("events", "whole"):
+        assert out.decode().replace('"created":1731661200', '"created":123') == c["expResponseBody"]
+    gw.stream_close([h])
+
+
+def _gemini_chunk(rng, last=False):
+    parts = []
+    for _ in range(rng.randint(0, 3)):
+        p = {"text": rng.choice(["Hello", " world ", "a\nb", 'q"uote', "café", "", "x" * rng.randint(1, 120)])}
+        if rng.random() < 0.2: p["thought"] = True
+        parts.append(p)
+    cand = {"content": {"parts": parts, "role": "model"}}
+    if rng.random() < 0.1: cand = {}
+    if last or rng.random() < 0.1: cand["finishReason"] = rng.choice(["STOP", "MAX_TOKENS", "SAFETY", "RECITATION", "OTHER", "LANGUAGE"])
+    d = {"responseId": "r_%d" % rng.randint(0, 99), "candidates": [cand]}
+    if rng.random() < 0.7: d["createTime"] = rng.choice(["2024-11-15T09:00:00Z", "2025-07-11T22:15:44.956335Z", "2030-01-02T03:04:05+02:00"])
+    if last: d["usageMetadata"] = {"promptTokenCount": rng.randint(0, 50), "candidatesTokenCount": rng.randint(0, 90), "totalTokenCount": rng.randint(0, 200), **({"thoughtsTokenCount": 5} if rng.random() < 0.3 else {}),
+                                   **({"cachedContentTokenCount": 3} if rng.random() < 0.3 else {})}
+    return json.dumps(d, ensure_ascii=False, separators=(",", ":")).encode()
+
+
+def test_gemini_stream_corpus_vs_oracle(gw):
+    rng = random.Random(17)
+    n = 96
+    streams = []
+    for s in range(n):
+        delim = rng.choice([b"\n\n", b"\n\n", b"\r\n\r\n", b"\r\r"])
+        k = rng.randint(1, 8)
+        data = b"".join((b"data: " if rng.random() < 0.9 else b"") + _gemini_chunk(rng, last=(i == k - 1)) + delim for i in range(k))
+        cuts = sorted(rng.sample(range(1, len(data)), min(rng.choice([0, 0, 3, 9]), len(data) - 1)))
+        # half of the streams are cut only at event boundaries (what the upstream does)
+        if s % 2 == 0:
+            cuts = [i + len(delim) for i in range(len(data)) if data.startswith(delim, i)][:-1]
+        streams.append([data[a:b] for a, b in zip([0] + cuts, cuts + [len(data)])])
+    hs = gw.stream_open("gcp-vertexai", b"gemini-x", n=n)
+    orc = [O.GeminiStream(b"gemini-x") for _ in range(n)]
+    for rnd in range(max(len(p) for p in streams) + 1):
+        idx = [i for i in range(n) if rnd <= len(streams[i])]
+        chunks = [streams[i][rnd] if rnd < len(streams[i]) else b"" for i in idx]
+        eos = [rnd == len(streams[i]) for i in idx]
+        got = gw.stream_chunks([hs[i] for i in idx], chunks, eos)
+        for i, ch, e, g in zip(idx, chunks, eos, got):
+            s, o, u, bl = orc[i].feed(ch, e)
+            assert g["status"] == s == OKS, (i, rnd, g["reason"], ch)
+            assert g["body"] == o and g["usage"] == u.as_tuple() and g["carry_len"] == bl, (i, rnd, ch)
+    gw.stream_close(hs)
+
+
+def _gemini_buffered(gw, body, model):
+    (h,) = gw.stream_open("gcp-vertexai-buffered", model)
+    half = len(body) // 2
+    r0 = gw.stream_chunk(h, body[:half], False)
+    assert r0["status"] == OKS and r0["body"] == b""
+    r = gw.stream_chunk(h, body[half:], True)
+    gw.stream_close([h])
+    return r
+
+
+def test_gemini_buffered_response(gw):
+    n = 0
+    for c in CASES:
+        if c.get("backend") != "gcp-vertexai" or c.get("responseType") or "expResponseBody" not in c or "/v1/chat/completions" not in c["name"] or "error" in c["name"]:
+            continue
+        model = json.loads(c["requestBody"])["model"].encode()
+        r = _gemini_buffered(gw, c["responseBody"].encode(), model)
+        st, out, u, rm = O.gemini_response(c["responseBody"].encode(), model)
+        assert r["status"] == st, c["name"]
+        if st == OKS:
+            assert r["body"] == out and r["usage"] == u.as_tuple() and r["model"] == rm
+            got = json.loads(r["body"]); exp = json.loads(c["expResponseBody"]); got.pop("created", None); exp.pop("created", None)
+            assert got == exp
+            n += 1
+    assert n >= 2
+    rng = random.Random(23)
+    for _ in range(200):
+        body = _gemini_chunk(rng, last=True)
+        if rng.random() < 0.5: body = body[:-1] + b',"modelVersion":"gemini-2.0-flash-001"}'
+        r = _gemini_buffered(gw, body, b"gemini-req")
+        st, out, u, rm = O.gemini_response(body, b"gemini-req")
+        assert r["status"] == st, body
+        if st == OKS:
+            assert r["body"] == out and r["usage"] == u.as_tuple() and r["model"] == rm, body
+    for bad, want in ((b'{"candidates":[', INTERNAL), (b'{"candidates":[{"content":{"parts":[{"functionCall":{"name":"f","args":{}}}]}}]}', DECLINED), (b'{"candidates":5}', DECLINED)):
+        assert _gemini_buffered(gw, bad, b"m")["status"] == want == O.gemini_response(bad, b"m")[0]
