@@ -166,6 +166,45 @@ __device__ __forceinline__ uint32_t lookup_id(const IdTables* T, const uint8_t* 
 }
 
 
+__device__ __forceinline__ int hex_val(uint32_t c) { if (c - '0' < 10u) return (int)(c - '0'); c |= 0x20u; if (c - 'a' < 6u) return (int)(c - 'a') + 10; return -1; }
+
+// id of a string that contains escapes: the lookup runs on the DECODED bytes (a key spelled "mod\u0065l" is the model member for
+// the reference's decoder).  Decoded strings longer than kMaxIdLen, malformed escapes and escapes that decode to non-ASCII
+// (no table entry has any) give 0.
+static __device__ uint32_t lookup_id_escaped(const IdTables* T, const uint8_t* p, uint32_t n, bool key) {
+  uint32_t v[kIdWords];
+#pragma unroll
+  for (int k = 0; k < kIdWords; k++) v[k] = 0;
+  uint32_t m = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t c = p[i];
+    if (c == '\\') {
+      if (++i >= n) return 0;
+      const uint32_t e = p[i];
+      if (e == 'n') c = '\n'; else if (e == 't') c = '\t'; else if (e == 'r') c = '\r'; else if (e == 'b') c = 8; else if (e == 'f') c = 12; else if (e == '"' || e == '\\' || e == '/') c = e;
+      else if (e == 'u') { if (i + 4 >= n) return 0; int h = 0; for (int k = 1; k <= 4; k++) { const int x = hex_val(p[i + k]); if (x < 0) return 0; h = h * 16 + x; } if (h >= 0x80) return 0; c = (uint32_t)h; i += 4; }
+      else return 0;
+    }
+    if (m >= (uint32_t)kMaxIdLen) return 0;
+    v[m >> 2] |= c << ((m & 3u) * 8u);
+    m++;
+  }
+  if (m == 0) return 0;
+  const uint32_t h = id_hash(v, m);
+  const IdSlot* tab = key ? T->key : T->val;
+  const uint32_t mask = key ? (kKeySlots - 1) : (kValSlots - 1);
+  uint32_t sl = h & mask;
+  for (int probe = 0; probe < 6; probe++) {
+    const IdSlot e = tab[sl];
+    if (e.meta == 0) return 0;
+    bool same = (e.meta & 0xffu) == m;
+    for (int k = 0; k < kIdWords; k++) same = same && e.w[k] == v[k];
+    if (same) return e.meta >> 8;
+    sl = (sl + 1) & mask;
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------ workspace shared by the three stages
 struct PlanOut { uint32_t nops, olen, path_len, model_off; uint16_t model_len; uint8_t flags, reason; };  // 20 bytes
 static constexpr int kBins = 1024;

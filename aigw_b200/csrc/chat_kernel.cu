@@ -74,11 +74,13 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
   if (threadIdx.x == 0) { for (int w = 0; w < WARPS; w++) mbar_init(&s_bar[w], 1); mbar_fence_init(); }
   __syncthreads();
   constexpr int kHdr = (int)((sizeof(IdTables) + 8 * WARPS + 15) & ~(size_t)15);
-  constexpr int kWarpBytes = C::kIn + C::kTok * 6;
+  constexpr int kNcBytes = ((MAXD / 1024 + 1) * 4 + 15) & ~15;   // one word per round: lanes (32-byte blocks) that hold a valid escape the encoder rewrites
+  constexpr int kWarpBytes = C::kIn + C::kTok * 6 + kNcBytes;
   uint8_t* wb = smem + kHdr + (size_t)warp * kWarpBytes;
   uint8_t* s_in = wb;
   uint32_t* s_tw = (uint32_t*)(wb + C::kIn);
   uint16_t* s_bs = (uint16_t*)(s_tw + C::kTok);   // running backslash count in front of each token; later overlaid by the lookup list
+  uint32_t* s_nc = (uint32_t*)(wb + C::kIn + C::kTok * 6);
   uint64_t* bar = &s_bar[warp];
   const WorkPtrs wp = carve(work, ndocs, layout_of<MAXD>());
   uint32_t phase = 0;
@@ -169,9 +171,15 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
       ps &= valid;
       // ps: bit set from an opening quote up to the byte before its closing quote
       if (mctl & ps) flags |= 1u;
-      {
-        uint32_t e = esc & ps;
-        while (e) { const int j = __ffs(e) - 1; e &= e - 1; const uint32_t c = s_in[base + j]; if (!(c == '"' || c == '\\' || c == 'n' || c == 'r' || c == 't')) flags |= 2u; }
+      {  // escaped characters: \" \\ \n \r \t are what the encoder writes back; \/ \b \f \uXXXX are valid but re-spelled (marked per
+         // 32-byte block, re-escaped by the walk when the string is echoed); anything else is not JSON
+        uint32_t e = esc & ps; bool nc = false;
+        while (e) {
+          const int j = __ffs(e) - 1; e &= e - 1; const uint32_t c = s_in[base + j];
+          if (!(c == '"' || c == '\\' || c == 'n' || c == 'r' || c == 't')) { if (c == '/' || c == 'b' || c == 'f' || c == 'u') nc = true; else flags |= 2u; }
+        }
+        const uint32_t ncm = __ballot_sync(FULL, nc);
+        if (lane == 0) s_nc[r] = ncm;
       }
       // bytes outside strings: structural characters are tokens, everything that is neither structural nor whitespace is a
       // scalar character (a control character other than \t \n \r lands there and fails the scalar grammar in the walk)
@@ -247,7 +255,21 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
         if (isq && ((qbase + __popc(qm & lt)) & 1u) == 0 && i + 1 < ntok) {
           const uint32_t o = (w & 0xffffu) + 1u, n = (s_tw[i + 1] & 0xffffu) - o;
           const bool esc = s_bs[i + 1] != s_bs[i];
-          if (esc) s_tw[i] = w | (1u << 30);
+          if (esc) {
+            // bit 31: some block the string touches holds a re-spelled escape (conservative: the walk re-checks byte by byte)
+            uint32_t ncf = 0;
+            const uint32_t b0k = o >> 5, b1k = (o + n) >> 5;
+            for (uint32_t wk = b0k >> 5; wk <= (b1k >> 5); wk++) {
+              uint32_t m = s_nc[wk];
+              if (wk == (b0k >> 5)) m &= ~0u << (b0k & 31u);
+              if (wk == (b1k >> 5)) m &= (b1k & 31u) == 31u ? ~0u : ((2u << (b1k & 31u)) - 1u);
+              ncf |= m;
+            }
+            // ids are looked up on the decoded bytes, so an escaped spelling of a key or of an enumerated value keeps its meaning
+            uint32_t id = 0;
+            if (n <= 6u * (uint32_t)kMaxIdLen) { const bool is_key = i + 2 < ntok && ((s_tw[i + 2] >> 16) & 0xffu) == ':'; id = lookup_id_escaped(s_ids, s_in + o, n, is_key); }
+            s_tw[i] = w | (1u << 30) | (ncf ? (1u << 31) : 0u) | (id << 24);
+          }
           want = !esc && n >= 1u && n <= (uint32_t)kMaxIdLen;
         }
         __syncwarp();
@@ -513,7 +535,7 @@ static cudaError_t launch_cls(const ChatParams& P, uint32_t first, int device, i
                               int* launches) {
   using C = Cls<MAXD>;
   constexpr size_t hdr1 = (sizeof(IdTables) + 8 * WARPS + 15) & ~(size_t)15, hdr3 = (sizeof(LitTable::bytes) + 8 * WARPS + 15) & ~(size_t)15;
-  const size_t smem1 = hdr1 + (size_t)(C::kIn + C::kTok * 6) * WARPS;
+  const size_t smem1 = hdr1 + (size_t)(C::kIn + C::kTok * 6 + (((MAXD / 1024 + 1) * 4 + 15) & ~15)) * WARPS;
   const size_t smem3 = hdr3 + (size_t)EmitSmem<MAXD>::kWarpBytes * WARPS;
   static ClsConfig cfgs[kMaxDevices];
   static std::mutex mu;

@@ -231,7 +231,7 @@ struct ChatParams {
 
 // size classes: MAXD bytes of input per document.  Per-warp shared memory:
 //   in[kIn] | tpos u16[kTok] | jmp u16[kTok] | tty u8[kTok] | tkid u8[kTok] | ops u32[kOps+kSys] | pre u32[kOps] | scr[kScr]
-static constexpr int kSysCap = 64;
+static constexpr int kSysCap = 192;   // system-message ops parked until the messages array is closed (a re-spelled escape run costs two ops)
 template <int MAXD>
 struct Cls {
   static constexpr int kIn = MAXD + 16;                  // multiple of 16; slack for unaligned word reads

@@ -32,6 +32,7 @@ struct Doc {
   __device__ __forceinline__ uint32_t str_off(int i) const { return tok(i) + 1u; }
   __device__ __forceinline__ uint32_t str_len(int i) const { return tok(i + 1) - tok(i) - 1u; }
   __device__ __forceinline__ bool str_has_backslash(int i) const { return (tw[i] >> 30) & 1u; }
+  __device__ __forceinline__ bool str_nc(int i) const { return (tw[i] >> 31) & 1u; }   // may hold an escape the encoder re-spells (\/ \b \f \uXXXX)
   __device__ uint32_t scalar_end(int i) const {
     const uint32_t w = tw[i];
     const uint32_t l = (w >> 24) & 0x3fu;
@@ -234,7 +235,7 @@ __device__ void emit_any(const Doc& d, Plan& pl, int root, bool sys = false) {
     if (need_value) {
       need_value = false;
       const uint32_t c = d.ty(vi);
-      if (c == '"') pl.src(d, d.tok(vi), (uint32_t)d.tok(vi + 1) - d.tok(vi) + 1u, sys);
+      if (c == '"') { if (d.str_nc(vi)) { pl.err = AIGW_R_ESCAPE; return; } pl.src(d, d.tok(vi), (uint32_t)d.tok(vi + 1) - d.tok(vi) + 1u, sys); }
       else if (c == '[') {
         pl.src(d, d.tok(vi), 1, sys);
         if (d.ty(vi + 1) == ']') pl.src(d, d.tok(vi + 1), 1, sys);
@@ -335,7 +336,60 @@ struct Walker {
   __device__ __forceinline__ bool is_num(int v) const { const uint32_t c = d.ty(v); return c == '-' || is_digit(c); }
   __device__ __forceinline__ bool is_null(int v) const { return d.ty(v) == 'n'; }
 
-  __device__ __forceinline__ void emit_str(int v, bool sys = false) { pl.src(d, d.tok(v), (uint32_t)d.tok(v + 1) - d.tok(v) + 1u, sys); }
+  __device__ __forceinline__ void emit_str(int v, bool sys = false) {
+    if (d.str_nc(v)) emit_str_respelled(v, sys);
+    else pl.src(d, d.tok(v), (uint32_t)d.tok(v + 1) - d.tok(v) + 1u, sys);
+  }
+  // Echo of a string that holds escapes the reference's encoder spells differently after its decode (sonic / encoding-json: the
+  // oracle's enc_str): backslash-slash becomes a plain slash, backslash-b / backslash-f become the six-byte u-escapes of 0x08 / 0x0c,
+  // a u-escape becomes the character itself (UTF-8; surrogate pairs joined) except for control characters (the two-byte escapes
+  // of newline, carriage return, tab, or a lower-case u-escape), the quote and the backslash.  Unchanged stretches stay input ops,
+  // each run of rewritten escapes becomes one scratch op.  Lone surrogates and malformed hex are left to the stock path.
+  __device__ void emit_str_respelled(int v, bool sys) {
+    const uint32_t q0 = d.tok(v), q1 = d.tok(v + 1);
+    const uint8_t* s = d.s;
+    uint32_t seg = q0, i = q0 + 1, run_start = sc.n;
+    bool in_run = false;
+    auto put = [&](uint32_t kind, uint32_t off, uint32_t len) { if (!len) return; if (sys) pl.push_sys(kind, off, len); else pl.push(kind, off, len); };
+    while (i < q1) {
+      const uint32_t c = s[i];
+      const uint32_t e = c == '\\' ? s[i + 1] : 0u;
+      if (c != '\\' || e == '"' || e == '\\' || e == 'n' || e == 'r' || e == 't') {
+        if (in_run) { put(2, run_start, sc.n - run_start); in_run = false; seg = i; }
+        i += c == '\\' ? 2u : 1u;
+        continue;
+      }
+      if (!in_run) { put(d.kind, seg, i - seg); in_run = true; run_start = sc.n; }
+      if (sc.n + 8 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
+      uint8_t* o = sc.p + sc.n;
+      uint32_t cp, used;
+      if (e == '/') { cp = '/'; used = 2; }
+      else if (e == 'b') { cp = 8; used = 2; }
+      else if (e == 'f') { cp = 12; used = 2; }
+      else {  // 'u' (the index kernel admits no other escape)
+        if (i + 6 > q1) { decline(AIGW_R_ESCAPE); return; }
+        int h = 0; for (int k = 2; k < 6; k++) { const int x = hex_val(s[i + k]); if (x < 0) { decline(AIGW_R_ESCAPE); return; } h = h * 16 + x; }
+        cp = (uint32_t)h; used = 6;
+        if (cp >= 0xD800u && cp < 0xDC00u) {
+          if (i + 12 > q1 || s[i + 6] != '\\' || s[i + 7] != 'u') { decline(AIGW_R_ESCAPE); return; }
+          int l = 0; for (int k = 8; k < 12; k++) { const int x = hex_val(s[i + k]); if (x < 0) { decline(AIGW_R_ESCAPE); return; } l = l * 16 + x; }
+          if (l < 0xDC00 || l >= 0xE000) { decline(AIGW_R_ESCAPE); return; }
+          cp = 0x10000u + ((cp - 0xD800u) << 10) + ((uint32_t)l - 0xDC00u); used = 12;
+        } else if (cp >= 0xDC00u && cp < 0xE000u) { decline(AIGW_R_ESCAPE); return; }
+      }
+      uint32_t w = 0;
+      if (cp == '"' || cp == '\\') { o[0] = '\\'; o[1] = (uint8_t)cp; w = 2; }
+      else if (cp == 10u || cp == 13u || cp == 9u) { o[0] = '\\'; o[1] = cp == 10u ? 'n' : cp == 13u ? 'r' : 't'; w = 2; }
+      else if (cp < 0x20u) { const char* hx = "0123456789abcdef"; o[0] = '\\'; o[1] = 'u'; o[2] = '0'; o[3] = '0'; o[4] = hx[cp >> 4]; o[5] = hx[cp & 15u]; w = 6; }
+      else if (cp < 0x80u) { o[0] = (uint8_t)cp; w = 1; }
+      else if (cp < 0x800u) { o[0] = (uint8_t)(0xC0u | (cp >> 6)); o[1] = (uint8_t)(0x80u | (cp & 63u)); w = 2; }
+      else if (cp < 0x10000u) { o[0] = (uint8_t)(0xE0u | (cp >> 12)); o[1] = (uint8_t)(0x80u | ((cp >> 6) & 63u)); o[2] = (uint8_t)(0x80u | (cp & 63u)); w = 3; }
+      else { o[0] = (uint8_t)(0xF0u | (cp >> 18)); o[1] = (uint8_t)(0x80u | ((cp >> 12) & 63u)); o[2] = (uint8_t)(0x80u | ((cp >> 6) & 63u)); o[3] = (uint8_t)(0x80u | (cp & 63u)); w = 4; }
+      sc.n += w; i += used;
+    }
+    if (in_run) { put(2, run_start, sc.n - run_start); seg = q1; }
+    put(d.kind, seg, q1 + 1u - seg);
+  }
 
   // value token of member `key` in object `obj`, -1 when absent or null; duplicates decline
   __device__ int find(int obj, uint32_t key) {
@@ -962,6 +1016,7 @@ struct Walker {
 
   // ---- tool call arguments: JSON text inside a JSON string → map[string]any → marshal
   __device__ void emit_arguments(int v) {
+    if (d.str_nc(v)) { decline(AIGW_R_ESCAPE); return; }   // the unescape below knows the five canonical escapes only
     const uint32_t off = d.str_off(v), n = d.str_len(v);
     if (sc.n + n + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
     uint8_t* dst = sc.p + sc.n; uint32_t w = 0;
@@ -1435,6 +1490,7 @@ struct Walker {
   }
   // is_error of a tool result: the content string decodes to a JSON object that has an "error" key (anthropic_helper.go:531-539)
   __device__ bool an_is_error(int v) {
+    if (d.str_nc(v)) { decline(AIGW_R_ESCAPE); return false; }
     const uint32_t off = d.str_off(v), n = d.str_len(v);
     const uint8_t* p = d.s + off;
     uint32_t k = 0; while (k < n && (p[k] == ' ')) k++;
@@ -1675,7 +1731,7 @@ struct Walker {
             pl.lit(L_TEXT_OPEN, true); pl.lit(L_QUOTE, true);
             for (int q = c + 1; d.ty(q) != ']'; q = d.after(q)) {
               Part p; if (!scan_part(q, p)) return;
-              if (p.text >= 0) { pl.src(d, d.str_off(p.text), d.str_len(p.text), true); total += d.str_len(p.text); }
+              if (p.text >= 0) { if (d.str_nc(p.text)) { decline(AIGW_R_ESCAPE); return; } pl.src(d, d.str_off(p.text), d.str_len(p.text), true); total += d.str_len(p.text); }
               if (cache_simple(p.cache)) cache = true;
               if (bad()) return;
             }
