@@ -38,7 +38,7 @@ assert StreamResult.itemsize == 64
 MutResult = np.dtype([("out_off", "<u8"), ("out_len", "<u4"), ("status", "u1"), ("reason", "u1"), ("flags", "<u2")])
 assert MutResult.itemsize == 16
 
-EXPORTS = ["aigw_stream_open", "aigw_stream_open_batch", "aigw_stream_chunks", "aigw_stream_chunk", "aigw_stream_close", "aigw_stream_close_batch",
+EXPORTS = ["aigw_bind_numa", "aigw_stream_open", "aigw_stream_open_batch", "aigw_stream_chunks", "aigw_stream_chunks_soa", "aigw_stream_chunk", "aigw_stream_close", "aigw_stream_close_batch",
            "aigw_version", "aigw_init", "aigw_destroy", "aigw_last_error", "aigw_device_sm_count", "aigw_host_alloc", "aigw_host_free",
            "aigw_device_alloc", "aigw_device_free", "aigw_memcpy_h2d", "aigw_memcpy_d2h", "aigw_memset_d", "aigw_sync",
            "aigw_chat_translate_device", "aigw_chat_translate_device_mapped", "aigw_chat_last_profile", "aigw_chat_set_profile", "aigw_chat_translate_host", "aigw_sse_usage_device", "aigw_sse_usage_host", "aigw_response_usage_device", "aigw_response_usage_host", "aigw_embeddings_response_usage_device", "aigw_embeddings_response_usage_host", "aigw_usage_costs_device",
@@ -304,6 +304,15 @@ class Context:
             out.append({"status": int(r["status"]), "body_kind": int(r["body_kind"]), "reason": int(r["reason"]), "body": raw[: int(r["out_len"])], "model": raw[int(r["out_len"]):],
                         "usage": usage, "carry_len": int(r["carry_len"])})
         return out
+
+    def stream_chunks_soa(self, handles_arr, base_arr, off_arr, len_arr, eos_arr=None):
+        """numpy-array driver: returns (ChunkResult array, arena address)"""
+        n = len(handles_arr)
+        res = np.zeros(n, dtype=ChunkResult); arena = C.c_void_p()
+        self.L.aigw_stream_chunks_soa.argtypes = [C.c_void_p] * 6 + [C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]
+        self._check(self.L.aigw_stream_chunks_soa(self.h, handles_arr.ctypes.data, base_arr.ctypes.data, off_arr.ctypes.data, len_arr.ctypes.data,
+                                                  eos_arr.ctypes.data if eos_arr is not None else None, n, res.ctypes.data, C.byref(arena)), "stream_chunks_soa")
+        return res, arena.value
 
     def stream_chunk(self, handle, chunk, eos):
         b = bytes(chunk); out = C.create_string_buffer(1 << 20); res = np.zeros(1, dtype=ChunkResult)

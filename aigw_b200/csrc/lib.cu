@@ -3,6 +3,7 @@
 // CUDA streams; everything computed is computed by the kernels in this directory — there is no
 // CPU fallback anywhere in this library.
 #include <cstdio>
+#include <sched.h>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -179,6 +180,33 @@ void aigw_destroy(aigw_ctx* ctx) {
   delete ctx;
 }
 
+// Bind the calling thread (and the threads it starts later) to the CPUs of the NUMA node the GPU hangs off, so that pinned
+// arenas allocated afterwards are node-local (first touch) and the copy engines do not cross the socket interconnect
+// (8 ranks on one host lost 4x end to end with unbound ranks).  Returns the node, or -1 when it cannot be determined.
+int aigw_bind_numa(int device) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return -1;
+  for (char* c = bus; *c; c++) if (*c >= 'A' && *c <= 'F') *c = (char)(*c - 'A' + 'a');
+  char path[128]; snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE* f = fopen(path, "r"); if (!f) return -1;
+  int node = -1; if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f);
+  if (node < 0) return -1;
+  snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+  f = fopen(path, "r"); if (!f) return -1;
+  char list[4096] = {0}; if (!fgets(list, sizeof list, f)) { fclose(f); return -1; } fclose(f);
+  cpu_set_t want; CPU_ZERO(&want);
+  for (char* p = list; *p;) {
+    char* end; long a = strtol(p, &end, 10); if (end == p) break; long b = a;
+    if (*end == '-') { p = end + 1; b = strtol(p, &end, 10); }
+    for (long c = a; c <= b && c < CPU_SETSIZE; c++) CPU_SET((int)c, &want);
+    p = *end == ',' ? end + 1 : end; if (*end != ',' ) break;
+  }
+  cpu_set_t cur; CPU_ZERO(&cur);
+  if (sched_getaffinity(0, sizeof cur, &cur) == 0) { cpu_set_t both; CPU_AND(&both, &cur, &want); if (CPU_COUNT(&both) > 0) want = both; }
+  if (CPU_COUNT(&want) == 0 || sched_setaffinity(0, sizeof want, &want) != 0) return -1;
+  return node;
+}
+
 const char* aigw_last_error(aigw_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 int aigw_device_sm_count(aigw_ctx* ctx) { return ctx->sm_count; }
 
@@ -246,12 +274,16 @@ int aigw_chat_last_profile(aigw_ctx* ctx, float stage_ms[3], int* launches) {
 
 int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const uint8_t* bodies, const uint64_t* offsets,
                              const uint32_t* lens, uint32_t n, aigw_batch_out* out) {
-  // Pipeline: H2D DMA of chunk c+1 (copy engine) overlaps the three kernels of chunk c, whose emit stage stores the
-  // output records and the per-body results directly into mapped pinned host memory (posted PCIe writes, 512 B per
-  // warp store).  No device→host copy and no host synchronisation until the end of the call.
+  // Three-stage pipeline over 256 MiB chunks, both PCIe directions busy at once:
+  //   copy engine A   H2D of chunk c+1                               (s_h2d)
+  //   SMs             index / sort / walk / emit of chunk c → device (s_compute)
+  //   copy engine B   D2H of chunk c-1: exactly the bytes the emit stage produced + the chunk's result table (s_d2h)
+  // The host runs one chunk behind the GPU (it waits for chunk c-1's byte count while chunk c's kernels are queued).
+  // AIGW_HOST_ZEROCOPY=1 restores the round-1 variant (emit stores straight into mapped host memory) for A/B runs.
   memset(out, 0, sizeof *out);
   if (n == 0) return 0;
-  cudaSetDevice(ctx->device);
+  CK(cudaSetDevice(ctx->device));
+  static const bool zero_copy = getenv("AIGW_HOST_ZEROCOPY") != nullptr;
   const uint64_t kChunkBytes = 256ull << 20;
   std::vector<uint32_t> cb;  // chunk begin doc index
   cb.push_back(0);
@@ -266,7 +298,7 @@ int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const u
     cb.push_back(n);
   }
   const int nch = (int)cb.size() - 1;
-  uint64_t max_in = 0; uint32_t max_docs = 0;
+  uint64_t max_in = 0, max_out = 0; uint32_t max_docs = 0;
   std::vector<uint64_t> in_bytes(nch), out_cap(nch), out_base(nch);
   uint64_t total_out_cap = 0;
   for (int c = 0; c < nch; c++) {
@@ -274,16 +306,18 @@ int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const u
     const uint64_t ib = offsets[e - 1] + (((uint64_t)lens[e - 1] + 15u) & ~15ull) - offsets[b] + 16;
     in_bytes[c] = ib; if (ib > max_in) max_in = ib; if (e - b > max_docs) max_docs = e - b;
     out_cap[c] = ((ib + ib / 4 + (uint64_t)(e - b) * 528 + 255) & ~255ull);
+    if (out_cap[c] > max_out) max_out = out_cap[c];
     out_base[c] = total_out_cap; total_out_cap += out_cap[c];
   }
-  const int nslots = nch < 2 ? 1 : 2;
+  const int nslots = nch < kSlots ? nch : kSlots;
   for (int s = 0; s < nslots; s++) {
     ChunkSlot& S = ctx->slot[s];
     ENSURE(S.d_in, S.in_cap, max_in + 64, false);
+    if (!zero_copy) { ENSURE(S.d_out, S.out_cap, max_out + 64, false); }
     if (S.doc_cap < max_docs) {
-      cudaFree(S.d_off); cudaFree(S.d_len); S.doc_cap = 0;
+      cudaFree(S.d_off); cudaFree(S.d_len); cudaFree(S.d_res); S.doc_cap = 0;
       const size_t dc = max_docs + max_docs / 8 + 16;
-      CK(cudaMalloc(&S.d_off, dc * 8)); CK(cudaMalloc(&S.d_len, dc * 4));
+      CK(cudaMalloc(&S.d_off, dc * 8)); CK(cudaMalloc(&S.d_len, dc * 4)); CK(cudaMalloc(&S.d_res, dc * sizeof(aigw_doc_result)));
       S.doc_cap = dc;
     }
   }
@@ -307,18 +341,33 @@ int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const u
     CK(cudaMalloc(&ctx->d_used_arr, cap * 8)); CK(cudaHostAlloc(&ctx->h_used_arr, cap * 8, cudaHostAllocDefault));
     ctx->used_cap = cap;
   }
-  uint8_t* dev_out = nullptr; aigw_doc_result* dev_res = nullptr;  // device views of the pinned arenas
-  CK(cudaHostGetDevicePointer((void**)&dev_out, ctx->h_out, 0));
-  CK(cudaHostGetDevicePointer((void**)&dev_res, ctx->h_res, 0));
+  uint8_t* dev_out = nullptr; aigw_doc_result* dev_res = nullptr;  // device views of the pinned arenas (zero-copy variant)
+  if (zero_copy) { CK(cudaHostGetDevicePointer((void**)&dev_out, ctx->h_out, 0)); CK(cudaHostGetDevicePointer((void**)&dev_res, ctx->h_res, 0)); }
 
   ChatParams P0; fill_params(P0, cfg);
-  uint64_t h2d = 0;
+  uint64_t h2d = 0, d2h = (uint64_t)n * sizeof(aigw_doc_result) + (uint64_t)nch * 8;
   CK(cudaMemsetAsync(ctx->d_used_arr, 0, (size_t)nch * 8, ctx->s_compute));
   CK(cudaEventRecord(ctx->ev0, ctx->s_compute));
+  auto drain = [&](int k) -> int {   // chunk k's kernels are done: move exactly what they produced
+    ChunkSlot& S = ctx->slot[k % nslots];
+    CK(cudaEventSynchronize(S.ev_k1));
+    const uint64_t used = ctx->h_used_arr[k] < out_cap[k] ? ctx->h_used_arr[k] : out_cap[k];
+    d2h += used;
+    if (!zero_copy) {
+      const uint32_t b = cb[k], nd = cb[k + 1] - b;
+      if (used) CK(cudaMemcpyAsync(ctx->h_out + out_base[k], S.d_out, used, cudaMemcpyDeviceToHost, ctx->s_d2h));
+      CK(cudaMemcpyAsync(ctx->h_res + b, S.d_res, (size_t)nd * sizeof(aigw_doc_result), cudaMemcpyDeviceToHost, ctx->s_d2h));
+      CK(cudaEventRecord(S.ev_done, ctx->s_d2h));
+    }
+    return 0;
+  };
   for (int c = 0; c < nch; c++) {
     ChunkSlot& S = ctx->slot[c % nslots];
     const uint32_t b = cb[c], e = cb[c + 1], nd = e - b;
-    if (c >= nslots) CK(cudaStreamWaitEvent(ctx->s_h2d, S.ev_k1, 0));  // the slot's previous chunk has been consumed
+    if (c >= nslots) {
+      CK(cudaStreamWaitEvent(ctx->s_h2d, S.ev_k1, 0));                       // the slot's input has been consumed
+      if (!zero_copy) CK(cudaStreamWaitEvent(ctx->s_compute, S.ev_done, 0));   // the slot's output has left the device
+    }
     CK(cudaMemcpyAsync(S.d_in, bodies + offsets[b], in_bytes[c] - 16, cudaMemcpyHostToDevice, ctx->s_h2d));
     CK(cudaMemcpyAsync(S.d_off, offsets + b, (size_t)nd * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
     CK(cudaMemcpyAsync(S.d_len, lens + b, (size_t)nd * 4, cudaMemcpyHostToDevice, ctx->s_h2d));
@@ -327,7 +376,7 @@ int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const u
     uint32_t cls_cnt[6] = {0, 0, 0, 0, 0, 0};
     for (uint32_t i = b; i < e; i++) cls_cnt[cls_of(lens[i])]++;
     int n_cls = 0, top_cls = 0; for (int k = 0; k < 6; k++) if (cls_cnt[k]) { n_cls++; top_cls = k; }
-    static const bool no_bucketing = getenv("AIGW_NO_BUCKETING") != nullptr;   // A/B switch for tools/bench_zipf.py
+    static const bool no_bucketing = getenv("AIGW_NO_BUCKETING") != nullptr;   // A/B switch for the Zipf bench
     if (no_bucketing) n_cls = 1;
     uint32_t cls_start[7] = {0, 0, 0, 0, 0, 0, 0};
     if (n_cls > 1) {
@@ -345,8 +394,8 @@ int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const u
     ChatParams P = P0;
     P.bodies = S.d_in - offsets[b];  // absolute offsets index straight into the chunk
     P.offsets = S.d_off - b; P.lens = S.d_len - b; P.n = nd;
-    P.out = dev_out + out_base[c]; P.out_capacity = out_cap[c];
-    P.results = dev_res; P.out_used = ctx->d_used_arr + c; P.next_doc = nullptr; P.out_bias = out_base[c]; P.doc_map = nullptr;
+    P.out = zero_copy ? dev_out + out_base[c] : S.d_out; P.out_capacity = out_cap[c];
+    P.results = zero_copy ? dev_res : S.d_res - b; P.out_used = ctx->d_used_arr + c; P.next_doc = nullptr; P.out_bias = out_base[c]; P.doc_map = nullptr;
     // documents keep their global index: kernels address offsets/lens/results with doc0 + i (or doc_map[i])
     if (n_cls <= 1) {
       int nl = 0;
@@ -361,13 +410,14 @@ int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const u
         out->gpu_launches += nl;
       }
     }
+    CK(cudaMemcpyAsync(ctx->h_used_arr + c, ctx->d_used_arr + c, 8, cudaMemcpyDeviceToHost, ctx->s_compute));
     CK(cudaEventRecord(S.ev_k1, ctx->s_compute));
+    if (c >= 1) { const int rc = drain(c - 1); if (rc) return rc; }
   }
   CK(cudaEventRecord(ctx->ev1, ctx->s_compute));
-  CK(cudaMemcpyAsync(ctx->h_used_arr, ctx->d_used_arr, (size_t)nch * 8, cudaMemcpyDeviceToHost, ctx->s_compute));
+  { const int rc = drain(nch - 1); if (rc) return rc; }
+  CK(cudaStreamSynchronize(ctx->s_d2h));
   CK(cudaStreamSynchronize(ctx->s_compute));
-  uint64_t d2h = (uint64_t)n * sizeof(aigw_doc_result) + (uint64_t)nch * 8;
-  for (int c = 0; c < nch; c++) d2h += ctx->h_used_arr[c] < out_cap[c] ? ctx->h_used_arr[c] : out_cap[c];
   float ms_total = 0; cudaEventElapsedTime(&ms_total, ctx->ev0, ctx->ev1);
   out->results = ctx->h_res; out->out = ctx->h_out; out->out_used = total_out_cap; out->h2d_bytes = h2d; out->d2h_bytes = d2h; out->kernel_ms = ms_total;
   return 0;
@@ -531,6 +581,14 @@ static int stream_chunks_locked(aigw_ctx* ctx, const aigw_chunk_in* in, uint32_t
 int aigw_stream_chunks(aigw_ctx* ctx, const aigw_chunk_in* in, uint32_t n, aigw_chunk_result* results, const uint8_t** arena) {
   std::lock_guard<std::mutex> lk(ctx->sp.mu);
   return stream_chunks_locked(ctx, in, n, results, arena);
+}
+/* structure-of-arrays form: chunk i of the call = base[off[i] .. off[i]+len[i]) for stream handles[i] (batch drivers, bench config 4) */
+int aigw_stream_chunks_soa(aigw_ctx* ctx, const uint64_t* handles, const uint8_t* base, const uint64_t* off, const uint32_t* len, const uint8_t* eos, uint32_t n,
+                           aigw_chunk_result* results, const uint8_t** arena) {
+  std::lock_guard<std::mutex> lk(ctx->sp.mu);
+  std::vector<aigw_chunk_in> in(n);
+  for (uint32_t i = 0; i < n; i++) { in[i].handle = handles[i]; in[i].bytes = base + off[i]; in[i].len = len[i]; in[i].eos = eos ? eos[i] : 0u; }
+  return stream_chunks_locked(ctx, in.data(), n, results, arena);
 }
 int aigw_stream_chunk(aigw_ctx* ctx, uint64_t handle, const uint8_t* bytes, uint32_t len, int eos, uint8_t* out, uint32_t out_cap, aigw_chunk_result* res) {
   std::lock_guard<std::mutex> lk(ctx->sp.mu);

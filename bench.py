@@ -1,22 +1,20 @@
 #!/usr/bin/env python3
-"""bench.py — BASELINE.json's metric on its config #2:
-    "1M OpenAI→AWS Bedrock Converse body translate, 4 KB bodies, 1×B200"
+"""bench.py — BASELINE.json's metric.  `--config` selects the BASELINE config (default 2, the one the metric is quoted on):
 
-One step = one pass of the hot path (parse → validate → translate → emit) over a batch of synthetic
-ChatCompletion bodies.  Per GPU the batch is --bodies (default 1,000,000; weak scaling: every rank gets
-its own 1 M shard, seeded by rank).  Printed (rank 0, one JSON line):
+  1  128 OpenAI ChatCompletion bodies (2 KB, 4 messages): passthrough translate + usage count, per-call latency shape
+  2  1 M OpenAI→AWS Bedrock Converse body translate, 4 KB bodies, per GPU                      (headline; the driver's run)
+  4  SSE streamed response parse through the per-chunk stream ABI: streams x 256 chunks x 80 B, usage extract
+  5  mixed-provider fan-out: OpenAI / Gemini / Anthropic / Bedrock translate, Zipf(1.2) body size 1-64 KB, requests routed to
+     a device by hash64(request-id) % n_gpus
+  (3, embeddings + BPE count, is not built: the line says so.)
 
-  value      bodies/s, whole job, inputs already resident in HBM (device API; CUDA-event time)
-  e2e        bodies/s through the host-buffer C-ABI call: pinned host arena → H2D → kernel → D2H, all in
-             the timed region (the call the cgo shim makes)
-  roofline   HBM roofline of the translate kernel: algorithmic bytes (input body + output record)
-             ÷ CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the oracle (CPU restatement of the reference Go path) on this box's host cores,
-             bounded sample, rank 0 / N=1 only
-  p50_added_us  submit→complete latency of a single-body call through the host API
-
---impl reference times the CPU restatement alone (the reference is Go; no Go toolchain exists in the
-image, so the restatement — pinned by the reference's goldens — stands in as kind "port").
+One step = one pass of the hot path over a batch of synthetic bodies.  Printed (rank 0, one JSON line):
+  value      units/s, whole job, inputs already resident in HBM (device API; CUDA-event time)
+  e2e        the same through the host-buffer C-ABI call; the timed region includes the multi-threaded copy of the bodies
+             into the library's pinned arena, H2D, kernels, D2H and the copy of the produced bytes out of the pinned arena
+  roofline   HBM roofline of the translate pass: algorithmic bytes (input + output) ÷ CUDA-event duration vs MEASURED_PEAKS.json
+  cpu_baseline  the oracle (CPU restatement of the reference Go path) on this box's host cores, bounded sample, rank 0 / N=1
+--impl reference times the CPU restatement alone on the same config (the reference is Go; no Go toolchain exists in the image).
 """
 import argparse
 import ctypes as C
@@ -35,6 +33,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "extproc bodies/sec, 4 KB ChatCompletion translate (OpenAI→AWS Bedrock Converse)"
 SEED = 2
+WORKLOAD2 = "configs[1]: OpenAI→AWS Bedrock Converse translate, 4 KB bodies (4096±32 B, 4–8 messages, 10% tool use), seed 2"
 
 
 def hbm_peak():
@@ -45,6 +44,16 @@ def hbm_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """DRAM read+write bytes per body of the three stages, from the committed ncu --set full capture of this round
+    (profiles/r02_traffic.json, written by tools/ncu_traffic.py from gpurun_out/*.ncu-rep); None when absent."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -86,23 +95,8 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_rate(arena, offs, lens, n_sample, threads):
-    import _oracle as O
-    n = min(n_sample, len(lens))
-    status = np.zeros(n, dtype=np.int32); olen = np.zeros(n, dtype=np.uint32); tot = C.c_uint64(0)
-    L = O.lib()
-    sec = L.oracle_chat_translate_batch(1, arena.ctypes.data, offs.ctypes.data, n, 0, threads, status.ctypes.data, olen.ctypes.data, C.byref(tot))
-    assert (status == 0).all()
-    return n / sec, n, int(tot.value)
-
-
-# DRAM traffic per body of the three stages, from the ncu --set full captures named in profiles/r01_chat_final.md
-NCU_DRAM_BYTES_PER_BODY = 16860
-
-
 def host_cores():
-    """threads the CPU legs may really use: the scheduler affinity mask, further limited by a cgroup CPU quota when one is set
-    (a box can show 128 logical CPUs and still be capped; oversubscribing a quota only adds throttling)"""
+    """threads the CPU legs may really use: the scheduler affinity mask, further limited by a cgroup CPU quota when one is set"""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     try:
         q = open("/sys/fs/cgroup/cpu.max").read().split()
@@ -118,46 +112,72 @@ def host_cores():
     return n
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--bodies", type=int, default=int(os.environ.get("AIGW_BENCH_BODIES", 1_000_000)), help="bodies per GPU per step")
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=400_000)
-    ap.add_argument("--skip-e2e", action="store_true")
-    a = ap.parse_args()
-    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
-    ncpu = host_cores()
+def build_checker():
+    """oracle + workload generator only (the reference arm must not map the product library)"""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    import _workload as W
+    W.lib()
+
+
+def cpu_oracle_rate(schema, arena, offs, n_sample, threads):
+    import _oracle as O
+    status = np.zeros(n_sample, dtype=np.int32); olen = np.zeros(n_sample, dtype=np.uint32); tot = C.c_uint64(0)
+    sec = O.lib().oracle_chat_translate_batch(schema, arena.ctypes.data, offs.ctypes.data, n_sample, 0, threads, status.ctypes.data, olen.ctypes.data, C.byref(tot))
+    return n_sample / sec, status
+
+
+def config2_dict(n):
+    return {"workload": WORKLOAD2, "bodies_per_gpu_per_step": n, "sharding": "hash(request-id)→device, no collective"}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(a, ncpu):
+    """the reference's own CPU implementation of the path.  It is Go and cannot be built here, so the restatement (oracle, kind
+    "port") is timed with every usable host thread on a bounded sample of the SAME workload (config and metric identical)."""
+    import _workload as W
+    build_checker()
+    n = a.bodies
+    sample = min(n, a.cpu_sample)
+    arena, offs, lens = W.chat_corpus(SEED, 0, sample, threads=ncpu)
+    times = []
+    for s in range(a.warmup + a.steps):
+        rate, status = cpu_oracle_rate(1, arena, offs, sample, ncpu)
+        assert (status == 0).all()
+        if s >= a.warmup:
+            times.append(sample / rate)
+    val = sample * a.steps / float(np.sum(times))
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": "bodies/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                      "ms_per_step": 1e3 * n / val, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                      "config": config2_dict(n),
+                      "cpu_baseline": {"value": val, "unit": "bodies/s", "cores": ncpu, "kind": "port",
+                                       "sample": f"first {sample} bodies of the {n}-body step per timed step x {a.steps} steps, {ncpu} threads; ms_per_step is extrapolated to the full step"},
+                      "e2e": {"value": val, "unit": "bodies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------------------------------ config 2 (headline)
+def escaped_corpus(arena, offs, lens, count):
+    """accept-rate corpus: the first `count` workload bodies, every tenth re-serialised the way ASCII-only JSON encoders write them
+    (non-ASCII characters as \\uXXXX, slashes escaped in half of those)"""
+    out = []
+    for i in range(count):
+        b = bytes(arena[int(offs[i]):int(offs[i]) + int(lens[i])])
+        if i % 10 == 0:
+            b = json.dumps(json.loads(b), ensure_ascii=True, separators=(",", ":")).encode()
+            if i % 20 == 0:
+                b = b.replace(b"/", b"\\/")
+        out.append(b)
+    return out
+
+
+def run_config2(a, rank, world, local, ncpu):
+    import _oracle as O
     import _workload as W
     import __graft_entry__ as entry
-
-    if a.impl == "reference":
-        # reference arm: the reference's own CPU implementation of the path.  It is Go and cannot be built here,
-        # so the restatement (oracle, kind "port") is timed with every host thread.  Rank 0 only.
-        if rank != 0:
-            return
-        entry.build()
-        n = min(a.bodies, 400_000)
-        arena, offs, lens = W.chat_corpus(SEED, 0, n, threads=ncpu)
-        times = []
-        for s in range(a.warmup + a.steps):
-            rate, nn, tot = cpu_oracle_rate(arena, offs, lens, n, ncpu)
-            if s >= a.warmup:
-                times.append(nn / rate)
-        t = float(np.sum(times))
-        val = n * a.steps / t
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": "bodies/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-                          "ms_per_step": 1e3 * t / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                          "config": {"workload": "configs[1]: OpenAI→AWS Bedrock Converse translate, 4 KB bodies", "bodies_per_step": n, "seed": SEED,
-                                     "note": "CPU restatement of the reference Go path (oracle); bounded sample of the 1M-body workload"},
-                          "cpu_baseline": {"value": val, "unit": "bodies/s", "cores": ncpu, "kind": "port", "sample": f"{n} bodies/step x {a.steps} steps, {ncpu} threads"},
-                          "e2e": {"value": val, "unit": "bodies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return
-
     entry.build()
     import aigw_b200 as A
+    from aigw_b200 import capi
+    node = A.load_library().aigw_bind_numa(local)      # this rank's threads and pinned arenas stay on the GPU's NUMA node
+    ncpu_local = host_cores()
     dist = None
     if world > 1:
         import torch
@@ -166,23 +186,23 @@ def main():
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     ctx = A.Context(local)
     n = a.bodies
-    # ---- synthetic shard for this rank, generated straight into a pinned arena
-    lens = W.chat_lens(SEED, rank * n, n, threads=ncpu)
+    # ---- synthetic shard for this rank (the bodies a shim would hold in Go memory) and the pinned arena the library reads
+    lens = W.chat_lens(SEED, rank * n, n, threads=ncpu_local)
     offs = W.chat_offsets(lens)
     in_bytes = int(offs[-1]) + 16
+    src = np.full(in_bytes, 0x20, dtype=np.uint8)
+    W.chat_fill(SEED, rank * n, n, src, offs, lens, threads=ncpu_local)
     arena, arena_ptr = ctx.host_array(in_bytes)
-    arena[-16:] = 0x20
-    W.chat_fill(SEED, rank * n, n, arena, offs, lens, threads=ncpu)
+    arena[:] = src
     max_len = int(lens.max())
     cfg = ctx.cfg("aws-bedrock")
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload, all host threads and 1 thread
     cpu = None
     if rank == 0 and world == 1:
-        r1, n1, _ = cpu_oracle_rate(arena, offs, lens, max(2000, min(a.cpu_sample // 8, 50_000)), 1)
-        rN, nN, _ = cpu_oracle_rate(arena, offs, lens, a.cpu_sample, ncpu)
-        rN2, _, _ = cpu_oracle_rate(arena, offs, lens, a.cpu_sample, ncpu)
-        cpu = {"value": max(rN, rN2), "unit": "bodies/s", "cores": ncpu, "kind": "port", "sample": f"first {nN} bodies of the workload, {ncpu} threads (1 thread: {r1:.0f} bodies/s on {n1})",
+        r1, _ = cpu_oracle_rate(1, src, offs, max(2000, min(a.cpu_sample // 8, 50_000)), 1)
+        rN = max(cpu_oracle_rate(1, src, offs, min(n, a.cpu_sample), ncpu)[0] for _ in range(2))
+        cpu = {"value": rN, "unit": "bodies/s", "cores": ncpu, "kind": "port", "sample": f"first {min(n, a.cpu_sample)} bodies of the workload, {ncpu} threads (1 thread: {r1:.0f} bodies/s)",
                "p50_us_per_body_1thread": 1e6 / r1}
 
     # ---- device-resident pass ("value")
@@ -202,7 +222,7 @@ def main():
         ctx.chat_translate_device(cfg, d_in, d_off, d_len, n, max_len, d_out, out_cap, d_res, d_used)
     sampler = ClockSampler(local); sampler.start()
     barrier()
-    t0 = time.perf_counter(); kms = []; stage = np.zeros(3); dev_launches = 0
+    t0 = time.perf_counter(); kms = []; dev_launches = 0
     for _ in range(a.steps):
         ctx.memset(d_used, 0, 8)
         kms.append(ctx.chat_translate_device(cfg, d_in, d_off, d_len, n, max_len, d_out, out_cap, d_res, d_used))
@@ -210,36 +230,60 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     dev_s = float(np.sum(kms)) / 1e3
-    # per-stage times: one extra pass outside the timed region with the stages serialised on one stream (the timed passes
-    # overlap the walk of one sub-batch with the index / emit of the next, so stage times do not exist there)
-    ctx.chat_set_profile(True); ctx.memset(d_used, 0, 8)
-    serial_ms = ctx.chat_translate_device(cfg, d_in, d_off, d_len, n, max_len, d_out, out_cap, d_res, d_used)
-    pr = ctx.chat_last_profile(); stage += np.array([pr["index_ms"], pr["walk_ms"], pr["emit_ms"]]) * a.steps
-    ctx.chat_set_profile(False); ctx.memset(d_used, 0, 8)
-    ctx.chat_translate_device(cfg, d_in, d_off, d_len, n, max_len, d_out, out_cap, d_res, d_used)
-    used = np.zeros(1, dtype=np.uint64); ctx.d2h(used, d_used)
     res = np.zeros(n, dtype=A.DocResult); ctx.d2h(res, d_res)
     n_ok = int((res["status"] == A.AIGW_OK).sum())
     out_bytes = int(res["body_len"].astype(np.uint64).sum() + res["path_len"].astype(np.uint64).sum())
     alg_bytes = int(lens.astype(np.uint64).sum()) + out_bytes  # bytes_in + bytes_out per body
+    # per-stage times: one extra pass outside the timed region with stage events (the stages already run back to back on one stream)
+    ctx.chat_set_profile(True); ctx.memset(d_used, 0, 8)
+    serial_ms = ctx.chat_translate_device(cfg, d_in, d_off, d_len, n, max_len, d_out, out_cap, d_res, d_used)
+    pr = ctx.chat_last_profile(); stage = [pr["index_ms"], pr["walk_ms"], pr["emit_ms"]]
+    ctx.chat_set_profile(False)
     for p in (d_in, d_off, d_len, d_out, d_res, d_used):
         ctx.dfree(p)
 
-    # ---- end-to-end through the host-buffer C-ABI call
-    e2e = None; p50 = None; launches = dev_launches
+    # ---- end to end through the host-buffer C-ABI call, copies into and out of the pinned arenas included
+    e2e = None; p50 = None; launches = dev_launches; checked = 0; accept = None
     if not a.skip_e2e:
+        WL = W.lib()
+        sink = np.empty(int(in_bytes * 1.1) + 4096, dtype=np.uint8)
+        def e2e_step():
+            WL.wl_memcpy_mt(C.c_void_p(arena.ctypes.data), C.c_void_p(src.ctypes.data), C.c_uint64(in_bytes), C.c_int(ncpu_local))
+            r2, o2, st = ctx.chat_translate_host(cfg, arena, offs, lens)
+            nout = min(int(st["d2h_bytes"]), len(sink), len(o2))     # the bytes the call produced (record table included), copied to caller memory
+            WL.wl_memcpy_mt(C.c_void_p(sink.ctypes.data), C.c_void_p(o2.ctypes.data), C.c_uint64(nout), C.c_int(ncpu_local))
+            return r2, o2, st
         for _ in range(max(1, min(a.warmup, 2))):
-            _, _, st = ctx.chat_translate_host(cfg, arena, offs, lens)
+            e2e_step()
         barrier()
         t1 = time.perf_counter(); e_launch = 0
         for _ in range(a.steps):
-            r2, o2, st = ctx.chat_translate_host(cfg, arena, offs, lens)
+            r2, o2, st = e2e_step()
             e_launch += st["gpu_launches"]
         barrier()
         e_wall = time.perf_counter() - t1
         assert int((r2["status"] == A.AIGW_OK).sum()) == n_ok
         e2e = {"wall_s": e_wall, "h2d": st["h2d_bytes"], "d2h": st["d2h_bytes"], "launches_per_step": e_launch // a.steps}
         launches += e_launch
+        # ---- parity of the timed outputs: 1 % of the bodies of the last step against the oracle, byte for byte
+        if rank == 0:
+            for i in range(0, n, 100):
+                t = O.chat_translate("aws-bedrock", bytes(arena[int(offs[i]):int(offs[i]) + int(lens[i])]))
+                x = r2[i]; o = int(x["out_off"]); pl = int(x["path_len"]); bl = int(x["body_len"])
+                assert int(x["status"]) == t.status == 0 and bytes(o2[o + pl:o + pl + bl]) == t.body and bytes(o2[o:o + pl]).decode() == t.path, i
+                checked += 1
+            # ---- accept rate on real-world spellings (report it next to the number)
+            esc = escaped_corpus(arena, offs, lens, min(n, 20_000))
+            got = ctx.chat_translate(cfg, esc)
+            ok = sum(1 for g in got if g["status"] == A.AIGW_OK)
+            for k in range(0, len(esc), 10):
+                t = O.chat_translate("aws-bedrock", esc[k])
+                if got[k]["status"] == A.AIGW_OK:
+                    assert t.status == 0 and got[k]["body"] == t.body, k
+            div = [W.diverse_body(s) for s in range(4000)]
+            gd = ctx.chat_translate(cfg, div)
+            accept = {"workload": n_ok / n, "escaped_corpus": ok / len(esc), "escaped_share_of_corpus": 0.1,
+                      "diverse_corpus_ok_or_reference_error": sum(1 for g in gd if g["status"] != A.AIGW_DECLINED) / len(div)}
         # p50 added latency: one 4 KB body, submit → complete
         one_a, one_o, one_l = arena[: int(offs[1]) + 16], offs[:2].copy(), lens[:1].copy()
         lat = []
@@ -260,24 +304,31 @@ def main():
         peak, peak_src = hbm_peak()
         step_s = dev_s_max / a.steps
         achieved = alg_bytes / (dev_s / a.steps) / 1e9
+        tr = ncu_traffic()
+        cfgd = config2_dict(n)
+        detail = {}
+        detail.update({"mean_in_bytes": float(lens.mean()), "mean_out_bytes": out_bytes / max(1, n_ok), "accepted": n_ok, "declined": n - n_ok,
+                     "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB in + {out_bytes / 1e6:.0f} MB out per step vs 126 MB L2)",
+                     "wall_ms_per_step_incl_launch": wall_max / a.steps * 1e3, "numa_node": node, "host_threads": ncpu_local})
         line = {"metric": METRIC, "value": tot_bodies / step_s, "unit": "bodies/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "configs[1]: OpenAI→AWS Bedrock Converse translate, 4 KB bodies (4096±32 B, 4–8 messages, 10% tool use), seed 2",
-                           "bodies_per_gpu_per_step": n, "mean_in_bytes": float(lens.mean()), "mean_out_bytes": out_bytes / max(1, n_ok), "accepted": n_ok, "declined": n - n_ok,
-                           "l2": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB in + {out_bytes / 1e6:.0f} MB out per step vs 126 MB L2)", "sharding": "hash(request-id)→device, no collective",
-                           "wall_ms_per_step_incl_launch": wall_max / a.steps * 1e3},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_BODY * n, "peak_source": peak_src,
-                             "traffic_source": "ncu --set full captures of one 131072-body launch of each stage (profiles/r01_chat_final.md): dram read+write per body "
-                                               "index 4.50 KB + walk 3.03 KB + emit 9.33 KB = 16.86 KB, i.e. 2.0x the algorithmic 8.25 KB (the body is read by index and again by emit)",
+                "config": cfgd, "config_detail": detail,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": (tr["bytes_per_body"] * n) if tr else None, "peak_source": peak_src,
+                             "traffic_source": (tr["source"] if tr else "no ncu capture committed for this round"),
                              "kernel": "chat_index_kernel + chat_walk_kernel + chat_emit_kernel (the three stages of one translate pass)",
                              "algorithmic_bytes_per_step": alg_bytes, "avg_step_ms": dev_s / a.steps * 1e3,
-                             "stage_ms_serialised": {"index": stage[0] / a.steps, "walk": stage[1] / a.steps, "emit": stage[2] / a.steps, "sum_one_stream": serial_ms},
+                             "stage_ms_profiled_pass": {"index": stage[0], "walk": stage[1], "emit": stage[2], "sum": serial_ms},
                              "launches_per_step": dev_launches // max(1, a.steps)},
                 "gpu_launches": launches, "clocks": clocks}
         if e2e:
             line["e2e"] = {"value": tot_bodies * a.steps / e_wall_max, "unit": "bodies/s", "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
-                           "launches_per_step": e2e["launches_per_step"], "pcie_gbs_each_way": [e2e["h2d"] * a.steps / e_wall_max / 1e9, e2e["d2h"] * a.steps / e_wall_max / 1e9]}
+                           "launches_per_step": e2e["launches_per_step"], "pcie_gbs_each_way": [e2e["h2d"] * a.steps / e_wall_max / 1e9, e2e["d2h"] * a.steps / e_wall_max / 1e9],
+                           "includes": "multi-threaded copy of the bodies into the pinned arena, H2D, kernels, D2H, copy of the produced bytes out of the pinned arena",
+                           "outputs_checked_vs_oracle": checked}
             line["p50_added_us"] = p50
+            if accept:
+                line["accept_rate"] = accept
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
@@ -285,6 +336,219 @@ def main():
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ config 1
+def run_config1(a, local, ncpu):
+    """128 bodies x 2 KB, passthrough translate + response usage: the reference's own CPU-runnable case; latency shape"""
+    import _workload as W
+    import __graft_entry__ as entry
+    entry.build()
+    import aigw_b200 as A
+    ctx = A.Context(local)
+    arena, offs, lens = W.chat_corpus(1, 0, 128, target=2048, jitter=16)
+    pin, pp = ctx.host_array(len(arena)); pin[:] = arena
+    cfg = ctx.cfg("openai", cost_configured=True)
+    resp = [b'{"id":"x","object":"chat.completion","model":"gpt-4o-mini","choices":[{"index":0,"message":{"role":"assistant","content":"ok"},"finish_reason":"stop"}],"usage":{"prompt_tokens":%d,"completion_tokens":%d,"total_tokens":%d}}' % (i, 2 * i, 3 * i) for i in range(128)]
+    from aigw_b200 import capi
+    ra, ro, rl = capi.pack_bodies(resp)
+    lat = []
+    for k in range(a.warmup + a.steps * 20):
+        t = time.perf_counter()
+        res, out, st = ctx.chat_translate_host(cfg, pin, offs[:128].copy(), lens)
+        ru = ctx.response_usage_host(ra, ro, rl)
+        dt = time.perf_counter() - t
+        if k >= a.warmup:
+            lat.append(dt)
+    assert (res["status"] == 0).all()
+    r1, _ = cpu_oracle_rate(0, arena, offs, 128, 1)
+    med = float(np.median(lat))
+    print(json.dumps({"metric": "extproc bodies/sec, 2 KB ChatCompletion passthrough translate + usage count (128-body call)", "value": 128 / med, "unit": "bodies/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
+                      "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                      "config": {"workload": "configs[0]: 128 OpenAI ChatCompletion bodies, 2 KB, 4 messages, passthrough + response usage, host buffers", "calls_timed": len(lat)},
+                      "e2e": {"value": 128 / med, "unit": "bodies/s", "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"])},
+                      "p50_call_us": med * 1e6, "cpu_baseline": {"value": r1, "unit": "bodies/s", "cores": 1, "kind": "port", "sample": "the same 128 bodies, 1 thread"}}))
+    ctx.host_free(pp); ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ config 4
+def run_config4(a, rank, world, local, ncpu):
+    """streams x 256 chunks x 80 B through aigw_stream_chunks (one ResponseBody call per stream per round), OpenAI usage extract"""
+    import _oracle as O
+    import _workload as W
+    import __graft_entry__ as entry
+    entry.build()
+    import aigw_b200 as A
+    A.load_library().aigw_bind_numa(local)
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    ctx = A.Context(local)
+    ns, chunks = a.streams, 256
+    buf, coff, cfirst = W.sse_corpus(4, rank * ns, ns, chunks=chunks)
+    nbytes = int(coff[-1])
+    lens_all = (coff[1:] - coff[:-1]).astype(np.uint32)
+    def one_pass(check):
+        hs = np.array(ctx.stream_open("openai", b"gpt-4o-mini", n=ns), dtype=np.uint64)
+        last = None
+        for r in range(chunks):
+            idx = cfirst[:-1].astype(np.int64) + r
+            res, arena = ctx.stream_chunks_soa(hs, buf, coff[idx].copy(), lens_all[idx].copy())
+            if check and r >= chunks - 3:
+                m = res["mask"] != 0
+                if last is None: last = np.zeros(ns, dtype=res.dtype)
+                last[m] = res[m]
+        ctx.stream_close([int(h) for h in hs])
+        return last
+    for _ in range(max(1, a.warmup // 3)):
+        one_pass(False)
+    ctx.sync()
+    if dist is not None: dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        last = one_pass(True)
+    ctx.sync()
+    if dist is not None: dist.barrier()
+    wall = time.perf_counter() - t0
+    # parity on a sample: the usage of the final calls equals the oracle's replay
+    nsamp = min(ns, 2000)
+    outu = np.zeros(nsamp, dtype=np.dtype([(k, "<u4") for k in ("input", "output", "total", "cached", "cache_creation", "reasoning", "mask")]))
+    sec = O.lib().oracle_sse_batch(buf.ctypes.data, coff.ctypes.data, cfirst.ctypes.data, nsamp, ncpu, outu.ctypes.data)
+    assert (last["input"][:nsamp] == outu["input"]).all() and (last["total"][:nsamp] == outu["total"]).all()
+    wall_max = wall
+    if dist is not None:
+        import torch
+        t = torch.tensor([wall], dtype=torch.float64, device=f"cuda:{local}"); dist.all_reduce(t, op=dist.ReduceOp.MAX); wall_max = float(t.item())
+    if rank == 0:
+        val = ns * chunks * world * a.steps / wall_max
+        print(json.dumps({"metric": "SSE chunks/sec through the per-chunk stream ABI, OpenAI usage extract", "value": val, "unit": "chunks/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                          "ms_per_step": wall_max / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": f"configs[3]: {ns} streams/GPU x {chunks} chunk calls x ~80 B, 20% ragged chunking, seed 4; every round is one aigw_stream_chunks call over all streams",
+                                     "bytes_per_gpu": nbytes},
+                          "e2e": {"value": val, "unit": "chunks/s", "h2d_bytes_per_step": nbytes + ns * chunks * 32, "d2h_bytes_per_step": ns * chunks * 64},
+                          "cpu_baseline": {"value": nsamp * chunks / sec, "unit": "chunks/s", "cores": ncpu, "kind": "port", "sample": f"{nsamp} streams replayed chunk by chunk, {ncpu} threads"}}))
+    ctx.close()
+    if dist is not None: dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ config 5
+def run_config5(a, rank, world, local, ncpu):
+    """mixed-provider fan-out: every request has an id; device = hash64(id) % n_gpus (aigw_b200/shard.py); each rank translates the
+    requests that hash to it, grouped by backend schema (one host-buffer call per backend)"""
+    import _oracle as O
+    import _workload as W
+    import __graft_entry__ as entry
+    entry.build()
+    import aigw_b200 as A
+    from aigw_b200 import capi, shard
+    A.load_library().aigw_bind_numa(local)
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    ctx = A.Context(local)
+    total = a.bodies * world
+    rng = np.random.default_rng(5 + rank)
+    k = np.arange(1, 65); p = k ** -1.2; p /= p.sum()
+    # request ids 0..total-1; this rank owns the ids whose hash64 lands on it (aigw_b200/shard.py, FNV-1a 64 as the cgo shim would)
+    ids = np.arange(total, dtype=np.uint64)
+    dev = shard.devices_for_requests(ids, world)
+    owner = dev[:: max(1, total // 65536)]
+    mine = ids[dev == rank]
+    assert shard.device_for_request(int(mine[0]).to_bytes(8, "little"), world) == rank   # the scalar and the vectorised hash agree
+    kb = rng.choice(k, size=len(mine), p=p)
+    backend = rng.integers(0, 4, size=len(mine))
+    names = ["openai", "gcp-vertexai", "gcp-anthropicai", "aws-bedrock"]
+    pools = {}
+    for t in sorted(set(int(x) for x in kb)):
+        m = min(int((kb == t).sum()), 256)
+        arena, offs, lens = W.chat_corpus(5, 0, m, target=min(t * 1024, 62000), jitter=max(16, t * 16))
+        pools[t] = [bytes(arena[int(offs[i]):int(offs[i]) + int(lens[i])]) for i in range(m)]
+    groups = []
+    for bi, name in enumerate(names):
+        sel = np.nonzero(backend == bi)[0]
+        bodies = [pools[int(kb[j])][int(j) % len(pools[int(kb[j])])] for j in sel]
+        arena, offs, lens = capi.pack_bodies(bodies)
+        pin, pp = ctx.host_array(len(arena) + 64); pin[: len(arena)] = arena
+        groups.append((name, ctx.cfg(name), pin, offs[: len(bodies)].copy(), lens, bodies))
+    def step():
+        acc = 0
+        for name, cfg, pin, offs, lens, bodies in groups:
+            res, out, st = ctx.chat_translate_host(cfg, pin, offs, lens)
+            acc += int((res["status"] == 0).sum())
+        return acc, None
+    for _ in range(a.warmup):
+        step()
+    ctx.sync()
+    if dist is not None: dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        acc, outs = step()
+    ctx.sync()
+    if dist is not None: dist.barrier()
+    wall = time.perf_counter() - t0
+    # sampled parity per backend (a host call's views are valid until the next call on the context: check right after each)
+    for name, cfg, pin, offs, lens, bodies in groups:
+        res, out, st = ctx.chat_translate_host(cfg, pin, offs, lens)
+        for i in range(0, len(bodies), max(1, len(bodies) // 100)):
+            t = O.chat_translate(name, bodies[i], prefix="" if "anthropic" in name else "v1")
+            if int(res[i]["status"]) == 0:
+                o = int(res[i]["out_off"]) + int(res[i]["path_len"])
+                got = bytes(out[o:o + int(res[i]["body_len"])])
+                assert t.status == 0 and got == (t.body if t.body_kind == 1 else b""), (name, i, t.status, len(got), len(t.body))
+    wall_max = wall; acc_all = acc
+    if dist is not None:
+        import torch
+        t = torch.tensor([wall, -float(acc)], dtype=torch.float64, device=f"cuda:{local}"); dist.all_reduce(t, op=dist.ReduceOp.MAX); wall_max = float(t[0].item())
+        t2 = torch.tensor([float(acc)], dtype=torch.float64, device=f"cuda:{local}"); dist.all_reduce(t2, op=dist.ReduceOp.SUM); acc_all = int(t2.item())
+    if rank == 0:
+        nb = sum(len(g[5]) for g in groups)
+        mean_in = float(np.mean([len(b) for g in groups for b in g[5][:2000]]))
+        print(json.dumps({"metric": "extproc bodies/sec, mixed-provider translate (OpenAI / Gemini / Anthropic / Bedrock), Zipf 1-64 KB", "value": total * a.steps / wall_max, "unit": "bodies/s", "n_gpus": world,
+                          "steps": a.steps, "warmup": a.warmup, "ms_per_step": wall_max / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": "configs[4]: 4-target mix, body size clamp(1 KB x Zipf(1.2), 1 KB, 64 KB), seed 5, device = hash64(request-id) % n_gpus", "bodies_rank0_per_step": nb, "bodies_total_per_step": total,
+                                     "mean_in_bytes": mean_in, "accepted_share": acc_all / total, "hash_balance_sample": np.bincount(owner, minlength=world).tolist()},
+                          "e2e": {"value": total * a.steps / wall_max, "unit": "bodies/s", "h2d_bytes_per_step": int(sum(int(g[4].sum()) for g in groups)), "d2h_bytes_per_step": None}}))
+    ctx.close()
+    if dist is not None: dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
+    ap.add_argument("--bodies", type=int, default=int(os.environ.get("AIGW_BENCH_BODIES", 0)), help="bodies per GPU per step (config 2: 1,000,000; config 5: 1,250,000)")
+    ap.add_argument("--streams", type=int, default=100_000, help="config 4: streams per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=400_000)
+    ap.add_argument("--skip-e2e", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    ncpu = host_cores()
+    if a.bodies <= 0:
+        a.bodies = 1_250_000 if a.config == 5 else 1_000_000
+    if a.impl == "reference":
+        if rank == 0:
+            run_reference(a, ncpu)
+        return
+    if a.config == 1:
+        if rank == 0: run_config1(a, local, ncpu)
+    elif a.config == 2:
+        run_config2(a, rank, world, local, ncpu)
+    elif a.config == 3:
+        if rank == 0:
+            print(json.dumps({"metric": "embeddings requests/sec with BPE token count", "unavailable": "configs[2] (68.7 KB requests + GPU BPE count) is not built this round: bodies above 64 KiB need 32-bit token positions; see DESIGN.md §7"}))
+    elif a.config == 4:
+        run_config4(a, rank, world, local, ncpu)
+    else:
+        run_config5(a, rank, world, local, ncpu)
 
 
 if __name__ == "__main__":

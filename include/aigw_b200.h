@@ -108,6 +108,9 @@ typedef struct aigw_usage { uint32_t input, output, total, cached, cache_creatio
 int  aigw_init(int device, aigw_ctx** ctx);          /* returns 0, or a CUDA error code; never falls back */
 void aigw_destroy(aigw_ctx* ctx);
 const char* aigw_last_error(aigw_ctx* ctx);
+/* Bind the calling thread to the CPUs of the GPU's NUMA node (call before aigw_init / aigw_host_alloc so that pinned arenas are
+ * node-local); returns the node or -1.  One process (or one batcher thread) per GPU, as SURVEY.md §8e lays it out. */
+int  aigw_bind_numa(int device);
 int  aigw_device_sm_count(aigw_ctx* ctx);
 
 /* ---- pinned arenas (the Go shim copies request bodies straight into these) ---- */
@@ -255,6 +258,9 @@ typedef struct aigw_chunk_result {
 int aigw_stream_open(aigw_ctx* ctx, const aigw_stream_cfg* cfg, uint64_t* handle);
 int aigw_stream_open_batch(aigw_ctx* ctx, const aigw_stream_cfg* cfg, uint32_t n, uint64_t* handles);   /* n streams with the same cfg */
 int aigw_stream_chunks(aigw_ctx* ctx, const aigw_chunk_in* in, uint32_t n, aigw_chunk_result* results /* host, n */, const uint8_t** arena);
+/* structure-of-arrays form of aigw_stream_chunks: chunk i = base[off[i] .. off[i]+len[i]), eos may be NULL (all 0) */
+int aigw_stream_chunks_soa(aigw_ctx* ctx, const uint64_t* handles, const uint8_t* base, const uint64_t* off, const uint32_t* len, const uint8_t* eos, uint32_t n,
+                           aigw_chunk_result* results /* host, n */, const uint8_t** arena);
 /* one chunk of one stream; the mutation is copied to out (≥ out_len + model_len bytes, else -4) */
 int aigw_stream_chunk(aigw_ctx* ctx, uint64_t handle, const uint8_t* bytes, uint32_t len, int eos, uint8_t* out, uint32_t out_cap, aigw_chunk_result* res);
 int aigw_stream_close(aigw_ctx* ctx, uint64_t handle);

@@ -151,6 +151,13 @@ void wl_chat_fill(uint64_t seed, uint64_t first, uint32_t n, uint32_t target, ui
   for (int t = 0; t < threads; t++) { uint32_t b = t * per, e = b + per > n ? n : b + per; if (b < e) th.emplace_back(work, b, e); }
   for (auto& t : th) t.join();
 }
+// multi-threaded memcpy (the bench's stand-in for the goroutines that copy bodies into / results out of the pinned arenas)
+void wl_memcpy_mt(uint8_t* dst, const uint8_t* src, uint64_t n, int threads) {
+  if (threads <= 1 || n < (1u << 20)) { memcpy(dst, src, n); return; }
+  std::vector<std::thread> th; const uint64_t per = ((n + threads - 1) / threads + 4095) & ~4095ull;
+  for (int t = 0; t < threads; t++) { const uint64_t b = (uint64_t)t * per; if (b >= n) break; const uint64_t l = b + per > n ? n - b : per; th.emplace_back([=] { memcpy(dst + b, src + b, l); }); }
+  for (auto& t : th) t.join();
+}
 // SSE: returns total bytes; chunk_off has n*chunks+1 entries (absolute byte offsets); out may be NULL to size
 uint64_t wl_sse_fill(uint64_t seed, uint64_t first, uint32_t n, int chunks, int chunk_bytes, uint8_t* out, uint64_t cap, uint64_t* chunk_off) {
   std::string s; std::vector<uint32_t> ends; uint64_t pos = 0; uint64_t c = 0;
