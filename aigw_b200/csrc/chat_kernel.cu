@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
     uint32_t carry_esc = 0, carry_str = 0, carry_sc = 0;
     uint32_t ntok = 0, bs_run = 0;
     uint32_t flags = 0;  // bit0 ctrl in string, bit1 bad escape, bit2 token overflow
+    uint32_t any_nc = 0; // some round holds a valid escape the encoder re-spells (warp-uniform)
     for (uint32_t r = 0; r < rounds; r++) {
       const uint32_t rbase = r << 10;
       const uint32_t base = rbase + (lane << 5);
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
         }
         const uint32_t ncm = __ballot_sync(FULL, nc);
         if (lane == 0) s_nc[r] = ncm;
+        any_nc |= ncm;
       }
       // bytes outside strings: structural characters are tokens, everything that is neither structural nor whitespace is a
       // scalar character (a control character other than \t \n \r lands there and fails the scalar grammar in the walk)
@@ -256,18 +258,20 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
           const uint32_t o = (w & 0xffffu) + 1u, n = (s_tw[i + 1] & 0xffffu) - o;
           const bool esc = s_bs[i + 1] != s_bs[i];
           if (esc) {
-            // bit 31: some block the string touches holds a re-spelled escape (conservative: the walk re-checks byte by byte)
-            uint32_t ncf = 0;
-            const uint32_t b0k = o >> 5, b1k = (o + n) >> 5;
-            for (uint32_t wk = b0k >> 5; wk <= (b1k >> 5); wk++) {
-              uint32_t m = s_nc[wk];
-              if (wk == (b0k >> 5)) m &= ~0u << (b0k & 31u);
-              if (wk == (b1k >> 5)) m &= (b1k & 31u) == 31u ? ~0u : ((2u << (b1k & 31u)) - 1u);
-              ncf |= m;
+            uint32_t ncf = 0, id = 0;
+            if (any_nc) {   // only documents that hold a re-spelled escape pay for the per-string questions
+              // bit 31: some block the string touches holds a re-spelled escape (conservative: the walk re-checks byte by byte)
+              const uint32_t b0k = o >> 5, b1k = (o + n) >> 5;
+              for (uint32_t wk = b0k >> 5; wk <= (b1k >> 5); wk++) {
+                uint32_t m = s_nc[wk];
+                if (wk == (b0k >> 5)) m &= ~0u << (b0k & 31u);
+                if (wk == (b1k >> 5)) m &= (b1k & 31u) == 31u ? ~0u : ((2u << (b1k & 31u)) - 1u);
+                ncf |= m;
+              }
+              // ids are looked up on the decoded bytes, so an escaped spelling of a key or of an enumerated value keeps its meaning
+              // (a string whose escapes are all canonical cannot equal a table entry: none contains such a character)
+              if (ncf && n <= 6u * (uint32_t)kMaxIdLen) { const bool is_key = i + 2 < ntok && ((s_tw[i + 2] >> 16) & 0xffu) == ':'; id = lookup_id_escaped(s_ids, s_in + o, n, is_key); }
             }
-            // ids are looked up on the decoded bytes, so an escaped spelling of a key or of an enumerated value keeps its meaning
-            uint32_t id = 0;
-            if (n <= 6u * (uint32_t)kMaxIdLen) { const bool is_key = i + 2 < ntok && ((s_tw[i + 2] >> 16) & 0xffu) == ':'; id = lookup_id_escaped(s_ids, s_in + o, n, is_key); }
             s_tw[i] = w | (1u << 30) | (ncf ? (1u << 31) : 0u) | (id << 24);
           }
           want = !esc && n >= 1u && n <= (uint32_t)kMaxIdLen;

@@ -1,1948 +1,26 @@
-// K2 of the chat translate pass: JSON grammar + bracket matching over the token list, then the schema walk that plans the
-// output as copy ops.  One thread per document; compiled once for every size class (slot sizes are kernel arguments).
-// See chat_kernel.cuh for the design and chat_kernel.cu for the index / emit stages.  sm_100a only.
+// K2 launcher: picks the walk kernel of the schema's group (chat_walk_g*.cu, one translation unit per group).
 #include "chat_internal.cuh"
-
-#include <cstdlib>
 
 namespace aigw {
 
-// ------------------------------------------------------------------ token view of one JSON text
-// token word = pos(16) | byte at pos(8) | id(6) | esc(1): id = key id (string followed by ':'), value id (other
-// strings), or the scalar's length (numbers / literals; 63 = longer); esc = the string contains a backslash.
-struct Doc {
-  const uint8_t* s;   // bytes
-  uint32_t len;       // valid bytes
-  const uint32_t* tw; // token words
-  uint16_t* jmp;
-  int nt;
-  uint32_t kind;      // op source kind: 0 input, 2 scratch
-
-  __device__ __forceinline__ uint32_t ty(int i) const { return (tw[i] >> 16) & 0xffu; }
-  __device__ __forceinline__ uint32_t tok(int i) const { return tw[i] & 0xffffu; }
-  __device__ __forceinline__ uint32_t id(int i) const { return (tw[i] >> 24) & 0x3fu; }
-  __device__ __forceinline__ int next(int i) const {
-    const uint32_t b = ty(i);
-    if (b == '{' || b == '[') return jmp[i] + 1;
-    if (b == '"') return i + 2;
-    return i + 1;
-  }
-  // member / element iteration: after value v, the next key or element (or the closing token)
-  __device__ __forceinline__ int after(int v) const { int nx = next(v); if (ty(nx) == ',') nx++; return nx; }
-  __device__ __forceinline__ uint32_t str_off(int i) const { return tok(i) + 1u; }
-  __device__ __forceinline__ uint32_t str_len(int i) const { return tok(i + 1) - tok(i) - 1u; }
-  __device__ __forceinline__ bool str_has_backslash(int i) const { return (tw[i] >> 30) & 1u; }
-  __device__ __forceinline__ bool str_nc(int i) const { return (tw[i] >> 31) & 1u; }   // may hold an escape the encoder re-spells (\/ \b \f \uXXXX)
-  __device__ uint32_t scalar_end(int i) const {
-    const uint32_t w = tw[i];
-    const uint32_t l = (w >> 24) & 0x3fu;
-    uint32_t p = w & 0xffffu;
-    if (l && l < 63u) return p + l;
-    while (p < len) { const uint32_t c = s[p]; if (is_ws(c) || is_op(c) || c == '"') break; p++; }
-    return p;
-  }
-};
-
-// JSON scalar grammar: number | true | false | null
-__device__ bool scalar_valid(const uint8_t* p, uint32_t n) {
-  if (n == 0) return false;
-  const uint32_t c = p[0];
-  if (c == 't') return n == 4 && p[1] == 'r' && p[2] == 'u' && p[3] == 'e';
-  if (c == 'f') return n == 5 && p[1] == 'a' && p[2] == 'l' && p[3] == 's' && p[4] == 'e';
-  if (c == 'n') return n == 4 && p[1] == 'u' && p[2] == 'l' && p[3] == 'l';
-  uint32_t i = 0;
-  if (p[i] == '-') { i++; if (i >= n) return false; }
-  if (p[i] == '0') i++;
-  else if (p[i] >= '1' && p[i] <= '9') { while (i < n && is_digit(p[i])) i++; }
-  else return false;
-  if (i < n && p[i] == '.') { i++; if (i >= n || !is_digit(p[i])) return false; while (i < n && is_digit(p[i])) i++; }
-  if (i < n && (p[i] == 'e' || p[i] == 'E')) {
-    i++; if (i < n && (p[i] == '+' || p[i] == '-')) i++;
-    if (i >= n || !is_digit(p[i])) return false;
-    while (i < n && is_digit(p[i])) i++;
-  }
-  return i == n;
-}
-
-// Stage 3: grammar check + bracket matching over the token list (single lane).  0 ok, else aigw_reason.
-__device__ int validate_tokens(Doc& d) {
-  const int MAXDEPTH = 48;
-  uint16_t open_idx[MAXDEPTH];
-  uint64_t isobj = 0;
-  int depth = 0;
-  // state: 0 value expected, 1 key or '}', 2 key, 3 ':', 4 ',' or close, 5 value or ']', 6 done
-  int st = 0;
-  int i = 0;
-  const int nt = d.nt;
-  while (i < nt) {
-    const uint32_t b = d.ty(i);
-    if (st == 6) return AIGW_R_SYNTAX;
-    if (b == '"') {
-      if (i + 1 >= nt || d.ty(i + 1) != '"') return AIGW_R_SYNTAX;
-      if (st == 1 || st == 2) st = 3;
-      else if (st == 0 || st == 5) st = depth ? 4 : 6;
-      else return AIGW_R_SYNTAX;
-      i += 2; continue;
-    }
-    if (b == '{' || b == '[') {
-      if (!(st == 0 || st == 5)) return AIGW_R_SYNTAX;
-      if (depth >= MAXDEPTH) return AIGW_R_DEPTH;
-      open_idx[depth] = (uint16_t)i;
-      if (b == '{') { isobj |= (1ull << depth); st = 1; } else { isobj &= ~(1ull << depth); st = 5; }
-      depth++; i++; continue;
-    }
-    if (b == '}' || b == ']') {
-      if (depth == 0) return AIGW_R_SYNTAX;
-      const bool obj = (isobj >> (depth - 1)) & 1;
-      if (b == '}') { if (!obj || !(st == 1 || st == 4)) return AIGW_R_SYNTAX; }
-      else { if (obj || !(st == 5 || st == 4)) return AIGW_R_SYNTAX; }
-      depth--;
-      d.jmp[open_idx[depth]] = (uint16_t)i;
-      st = depth ? 4 : 6; i++; continue;
-    }
-    if (b == ':') { if (st != 3) return AIGW_R_SYNTAX; st = 0; i++; continue; }
-    if (b == ',') {
-      if (st != 4) return AIGW_R_SYNTAX;
-      st = ((isobj >> (depth - 1)) & 1) ? 2 : 0; i++; continue;
-    }
-    if (!(st == 0 || st == 5)) return AIGW_R_SYNTAX;
-    const uint32_t e = d.scalar_end(i);
-    if (!scalar_valid(d.s + d.tok(i), e - d.tok(i))) return AIGW_R_SYNTAX;
-    st = depth ? 4 : 6; i++;
-  }
-  return st == 6 ? 0 : AIGW_R_SYNTAX;
-}
-
-// ------------------------------------------------------------------ copy-op plan
-// op = kind(2) | len(14) | off(16); kind 0 input bytes, 1 literal table, 2 scratch.
-// The op being extended is held in registers (ckind/coff/clen) and written when the next one starts.
-// "System" ops (emitted after the messages array) are parked in ops[cap .. cap+kSysCap).
-struct Plan {
-  uint32_t* ops;
-  int nops, nsys, cap;
-  uint32_t ckind, coff, clen;  // clen == 0 ⇒ nothing pending
-  uint32_t olen;
-  int err;
-  bool dry;  // validate only: count nothing, store nothing
-
-  __device__ __forceinline__ void flush() {
-    if (clen) {
-      if (nops >= cap) { err = AIGW_R_OPS; clen = 0; return; }
-      ops[nops++] = (ckind << 30) | (clen << 16) | coff;
-      clen = 0;
-    }
-  }
-  __device__ void push(uint32_t kind, uint32_t off, uint32_t len) {
-    if (dry) return;
-    olen += len;
-    if (clen && kind == ckind && coff + clen == off && clen + len <= 16383u) { clen += len; return; }
-    while (len) {
-      flush();
-      const uint32_t l = len < 16383u ? len : 16383u;
-      ckind = kind; coff = off; clen = l;
-      off += l; len -= l;
-    }
-  }
-  __device__ void push_sys(uint32_t kind, uint32_t off, uint32_t len) {
-    if (dry) { nsys = 1; return; }
-    while (len) {
-      const uint32_t l = len < 16383u ? len : 16383u;
-      if (nsys >= kSysCap) { err = AIGW_R_OPS; return; }
-      ops[cap + nsys++] = (kind << 30) | (l << 16) | off;
-      off += l; len -= l;
-    }
-  }
-  __device__ __forceinline__ void lit(int id, bool sys = false) {
-    const uint32_t o = c_lits.off[id], l = c_lits.off[id + 1] - o;
-    if (sys) push_sys(1, o, l); else push(1, o, l);
-  }
-  __device__ __forceinline__ void src(const Doc& d, uint32_t off, uint32_t len, bool sys = false) {
-    if (sys) push_sys(d.kind, off, len); else push(d.kind, off, len);
-  }
-  __device__ void flush_sys() {
-    if (dry) { nsys = 0; return; }
-    for (int k = 0; k < nsys; k++) { const uint32_t p = ops[cap + k]; push(p >> 30, p & 0xffffu, (p >> 16) & 0x3fffu); }
-    nsys = 0;
-  }
-};
-
-struct Scratch { uint8_t* p; uint32_t n, cap; };
-
-// ------------------------------------------------------------------ canonical scalars
-// A JSON number literal that strconv would print back digit-for-digit once trailing fractional
-// zeros are dropped: -?(0|[1-9]\d*)(\.\d+)? , ≤ 15 significant digits, |v| ≥ 1e-6 unless zero.
-// Returns the emitted length (a prefix of the literal), 0 when not canonical.
-__device__ uint32_t canon_number(const uint8_t* p, uint32_t n, bool integer_only) {
-  uint32_t i = 0;
-  bool neg = false;
-  if (p[0] == '-') { neg = true; i = 1; }
-  const uint32_t int_start = i;
-  while (i < n && is_digit(p[i])) i++;
-  const uint32_t int_digits = i - int_start;
-  if (int_digits == 0) return 0;
-  const bool int_zero = (int_digits == 1 && p[int_start] == '0');
-  if (i == n) {
-    if (integer_only) { if (int_digits > 18) return 0; if (neg && int_zero) return 0; return n; }
-    if (int_digits > 15) return 0;
-    return n;  // "-0" prints "-0" for a float64
-  }
-  if (integer_only || p[i] != '.') return 0;
-  const uint32_t dot = i; i++;
-  const uint32_t frac_start = i;
-  while (i < n && is_digit(p[i])) i++;
-  if (i != n) return 0;
-  uint32_t fe = n;
-  while (fe > frac_start && p[fe - 1] == '0') fe--;
-  const uint32_t frac_digits = fe - frac_start;
-  if (frac_digits == 0) return dot;  // "1.0" → "1", "-0.0" → "-0"
-  uint32_t sig;
-  if (int_zero) {
-    uint32_t z = 0; while (frac_start + z < fe && p[frac_start + z] == '0') z++;
-    if (z > 5) return 0;  // < 1e-6 switches strconv to exponent form
-    sig = frac_digits - z;
-  } else sig = int_digits + frac_digits;
-  if (sig > 15) return 0;
-  return fe;
-}
-
-// ------------------------------------------------------------------ generic canonical re-serialisation
-// Go: decode into interface{} / map[string]any, then marshal ⇒ compact, keys sorted, numbers via float64.
-__device__ int cmp_keys(const Doc& d, int a, int b) {
-  const uint8_t* pa = d.s + d.str_off(a); const uint32_t la = d.str_len(a);
-  const uint8_t* pb = d.s + d.str_off(b); const uint32_t lb = d.str_len(b);
-  const uint32_t m = la < lb ? la : lb;
-  for (uint32_t k = 0; k < m; k++) { if (pa[k] != pb[k]) return pa[k] < pb[k] ? -1 : 1; }
-  return la == lb ? 0 : (la < lb ? -1 : 1);
-}
-
-__device__ void emit_scalar_any(const Doc& d, Plan& pl, int vi, bool sys) {
-  const uint32_t c = d.ty(vi);
-  const uint32_t e = d.scalar_end(vi), o = d.tok(vi);
-  if (c == 't' || c == 'f' || c == 'n') { pl.src(d, o, e - o, sys); return; }
-  const uint32_t l = canon_number(d.s + o, e - o, false);
-  if (!l) { pl.err = AIGW_R_NUMBER; return; }
-  pl.src(d, o, l, sys);
-}
-
-__device__ void emit_any(const Doc& d, Plan& pl, int root, bool sys = false) {
-  const int MAXF = 24;
-  int f_open[MAXF]; int f_state[MAXF];  // array: current element token; object: last emitted key token (-1 none)
-  int sp = 0;
-  int vi = root;
-  bool need_value = true;
-  for (;;) {
-    if (pl.err) return;
-    if (need_value) {
-      need_value = false;
-      const uint32_t c = d.ty(vi);
-      if (c == '"') { if (d.str_nc(vi)) { pl.err = AIGW_R_ESCAPE; return; } pl.src(d, d.tok(vi), (uint32_t)d.tok(vi + 1) - d.tok(vi) + 1u, sys); }
-      else if (c == '[') {
-        pl.src(d, d.tok(vi), 1, sys);
-        if (d.ty(vi + 1) == ']') pl.src(d, d.tok(vi + 1), 1, sys);
-        else {
-          if (sp >= MAXF) { pl.err = AIGW_R_DEPTH; return; }
-          f_open[sp] = vi; f_state[sp] = vi + 1; sp++;
-          vi = vi + 1; need_value = true; continue;
-        }
-      } else if (c == '{') {
-        pl.src(d, d.tok(vi), 1, sys);
-        if (sp >= MAXF) { pl.err = AIGW_R_DEPTH; return; }
-        f_open[sp] = vi; f_state[sp] = -1; sp++;
-      } else emit_scalar_any(d, pl, vi, sys);
-    }
-    if (sp == 0) return;
-    const int open = f_open[sp - 1];
-    if (d.ty(open) == '[') {
-      const int nx = d.next(f_state[sp - 1]);
-      pl.src(d, d.tok(nx), 1, sys);  // ',' or ']'
-      if (d.ty(nx) == ',') { f_state[sp - 1] = nx + 1; vi = nx + 1; need_value = true; }
-      else sp--;
-    } else {
-      const int last = f_state[sp - 1];
-      int best = -1, cnt = 0;
-      for (int m = open + 1; d.ty(m) != '}'; m = d.after(m + 3)) {
-        if (d.str_has_backslash(m)) { pl.err = AIGW_R_ESCAPE; return; }
-        const int c1 = last < 0 ? 1 : cmp_keys(d, m, last);
-        if (c1 == 0 && m != last) { pl.err = AIGW_R_DUP_KEY; return; }
-        if (c1 > 0 && (best < 0 || cmp_keys(d, m, best) < 0)) best = m;
-        if (++cnt > 64) { pl.err = AIGW_R_UNSUPPORTED_FIELD; return; }
-      }
-      if (best < 0) { pl.src(d, d.tok(d.jmp[open]), 1, sys); sp--; continue; }
-      if (last >= 0) pl.lit(L_COMMA, sys);
-      const uint32_t ko = d.tok(best), kc = d.tok(best + 1), colon = d.tok(best + 2);
-      if (colon == kc + 1u) pl.src(d, ko, colon + 1u - ko, sys);
-      else { pl.src(d, ko, kc + 1u - ko, sys); pl.lit(L_COLON, sys); }
-      f_state[sp - 1] = best;
-      vi = best + 3; need_value = true;
-    }
-  }
-}
-
-// Sequential tokenizer for a scratch-resident JSON text (tool-call arguments after unescaping).
-// `base` is added to every position.  Returns number of tokens, or -reason.
-__device__ int tokenize_seq(const uint8_t* s, uint32_t len, uint32_t base, uint32_t* tw, int cap) {
-  int nt = 0; uint32_t i = 0;
-  while (i < len) {
-    const uint32_t c = s[i];
-    if (is_ws(c)) { i++; continue; }
-    if (nt + 2 > cap) return -AIGW_R_TOKENS;
-    if (c == '"') {
-      const int open = nt;
-      tw[nt++] = (base + i) | ((uint32_t)'"' << 16); i++;
-      uint32_t esc = 0;
-      for (;;) {
-        if (i >= len) return -AIGW_R_SYNTAX;
-        const uint32_t ch = s[i];
-        if (ch == '"') break;
-        if (ch < 0x20) return -AIGW_R_CTRL_IN_STRING;
-        if (ch == '\\') {
-          if (i + 1 >= len) return -AIGW_R_SYNTAX;
-          const uint32_t e = s[i + 1];
-          if (!(e == '"' || e == '\\' || e == 'n' || e == 'r' || e == 't')) return -AIGW_R_ESCAPE;
-          esc = 1; i += 2; continue;
-        }
-        i++;
-      }
-      tw[open] |= esc << 30;
-      tw[nt++] = (base + i) | ((uint32_t)'"' << 16); i++; continue;
-    }
-    const uint32_t start = i;
-    if (is_op(c)) { tw[nt++] = (base + i) | (c << 16); i++; continue; }
-    while (i < len && !is_ws(s[i]) && !is_op(s[i]) && s[i] != '"') i++;
-    const uint32_t l = i - start;
-    tw[nt++] = (base + start) | (c << 16) | ((l < 63u ? l : 63u) << 24);
-  }
-  return nt;
-}
-
-// ------------------------------------------------------------------ schema walk
-struct Walker {
-  Doc d;
-  Plan pl;
-  Scratch sc;
-  uint32_t* tw_tail; uint16_t* jmp_tail; int tail_cap;  // free token space for nested documents
-  const ChatParams* P;
-  int reason;
-  int pending;  // first translator-side error (422 / internal): reported only if the rest of the body neither declines nor fails ParseBody
-
-  __device__ __forceinline__ void decline(int r) { if (!reason) reason = r; }
-  __device__ __forceinline__ void pend(int r) { if (!pending) pending = r; }
-  __device__ __forceinline__ bool bad() const { return reason != 0 || pl.err != 0; }
-
-  __device__ __forceinline__ bool is_str(int v) const { return d.ty(v) == '"'; }
-  __device__ __forceinline__ bool is_obj(int v) const { return d.ty(v) == '{'; }
-  __device__ __forceinline__ bool is_arr(int v) const { return d.ty(v) == '['; }
-  __device__ __forceinline__ bool is_bool(int v) const { const uint32_t c = d.ty(v); return c == 't' || c == 'f'; }
-  __device__ __forceinline__ bool is_num(int v) const { const uint32_t c = d.ty(v); return c == '-' || is_digit(c); }
-  __device__ __forceinline__ bool is_null(int v) const { return d.ty(v) == 'n'; }
-
-  __device__ __forceinline__ void emit_str(int v, bool sys = false) {
-    if (d.str_nc(v)) emit_str_respelled(v, sys);
-    else pl.src(d, d.tok(v), (uint32_t)d.tok(v + 1) - d.tok(v) + 1u, sys);
-  }
-  // Echo of a string that holds escapes the reference's encoder spells differently after its decode (sonic / encoding-json: the
-  // oracle's enc_str): backslash-slash becomes a plain slash, backslash-b / backslash-f become the six-byte u-escapes of 0x08 / 0x0c,
-  // a u-escape becomes the character itself (UTF-8; surrogate pairs joined) except for control characters (the two-byte escapes
-  // of newline, carriage return, tab, or a lower-case u-escape), the quote and the backslash.  Unchanged stretches stay input ops,
-  // each run of rewritten escapes becomes one scratch op.  Lone surrogates and malformed hex are left to the stock path.
-  __device__ void emit_str_respelled(int v, bool sys) {
-    const uint32_t q0 = d.tok(v), q1 = d.tok(v + 1);
-    const uint8_t* s = d.s;
-    uint32_t seg = q0, i = q0 + 1, run_start = sc.n;
-    bool in_run = false;
-    auto put = [&](uint32_t kind, uint32_t off, uint32_t len) { if (!len) return; if (sys) pl.push_sys(kind, off, len); else pl.push(kind, off, len); };
-    while (i < q1) {
-      const uint32_t c = s[i];
-      const uint32_t e = c == '\\' ? s[i + 1] : 0u;
-      if (c != '\\' || e == '"' || e == '\\' || e == 'n' || e == 'r' || e == 't') {
-        if (in_run) { put(2, run_start, sc.n - run_start); in_run = false; seg = i; }
-        i += c == '\\' ? 2u : 1u;
-        continue;
-      }
-      if (!in_run) { put(d.kind, seg, i - seg); in_run = true; run_start = sc.n; }
-      if (sc.n + 8 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
-      uint8_t* o = sc.p + sc.n;
-      uint32_t cp, used;
-      if (e == '/') { cp = '/'; used = 2; }
-      else if (e == 'b') { cp = 8; used = 2; }
-      else if (e == 'f') { cp = 12; used = 2; }
-      else {  // 'u' (the index kernel admits no other escape)
-        if (i + 6 > q1) { decline(AIGW_R_ESCAPE); return; }
-        int h = 0; for (int k = 2; k < 6; k++) { const int x = hex_val(s[i + k]); if (x < 0) { decline(AIGW_R_ESCAPE); return; } h = h * 16 + x; }
-        cp = (uint32_t)h; used = 6;
-        if (cp >= 0xD800u && cp < 0xDC00u) {
-          if (i + 12 > q1 || s[i + 6] != '\\' || s[i + 7] != 'u') { decline(AIGW_R_ESCAPE); return; }
-          int l = 0; for (int k = 8; k < 12; k++) { const int x = hex_val(s[i + k]); if (x < 0) { decline(AIGW_R_ESCAPE); return; } l = l * 16 + x; }
-          if (l < 0xDC00 || l >= 0xE000) { decline(AIGW_R_ESCAPE); return; }
-          cp = 0x10000u + ((cp - 0xD800u) << 10) + ((uint32_t)l - 0xDC00u); used = 12;
-        } else if (cp >= 0xDC00u && cp < 0xE000u) { decline(AIGW_R_ESCAPE); return; }
-      }
-      uint32_t w = 0;
-      if (cp == '"' || cp == '\\') { o[0] = '\\'; o[1] = (uint8_t)cp; w = 2; }
-      else if (cp == 10u || cp == 13u || cp == 9u) { o[0] = '\\'; o[1] = cp == 10u ? 'n' : cp == 13u ? 'r' : 't'; w = 2; }
-      else if (cp < 0x20u) { const char* hx = "0123456789abcdef"; o[0] = '\\'; o[1] = 'u'; o[2] = '0'; o[3] = '0'; o[4] = hx[cp >> 4]; o[5] = hx[cp & 15u]; w = 6; }
-      else if (cp < 0x80u) { o[0] = (uint8_t)cp; w = 1; }
-      else if (cp < 0x800u) { o[0] = (uint8_t)(0xC0u | (cp >> 6)); o[1] = (uint8_t)(0x80u | (cp & 63u)); w = 2; }
-      else if (cp < 0x10000u) { o[0] = (uint8_t)(0xE0u | (cp >> 12)); o[1] = (uint8_t)(0x80u | ((cp >> 6) & 63u)); o[2] = (uint8_t)(0x80u | (cp & 63u)); w = 3; }
-      else { o[0] = (uint8_t)(0xF0u | (cp >> 18)); o[1] = (uint8_t)(0x80u | ((cp >> 12) & 63u)); o[2] = (uint8_t)(0x80u | ((cp >> 6) & 63u)); o[3] = (uint8_t)(0x80u | (cp & 63u)); w = 4; }
-      sc.n += w; i += used;
-    }
-    if (in_run) { put(2, run_start, sc.n - run_start); seg = q1; }
-    put(d.kind, seg, q1 + 1u - seg);
-  }
-
-  // value token of member `key` in object `obj`, -1 when absent or null; duplicates decline
-  __device__ int find(int obj, uint32_t key) {
-    int r = -1;
-    for (int m = obj + 1; d.ty(m) != '}'; m = d.after(m + 3)) {
-      if (d.id(m) == key) { if (r >= 0) { decline(AIGW_R_DUP_KEY); return -1; } r = m + 3; }
-    }
-    if (r >= 0 && is_null(r)) return -1;
-    return r;
-  }
-  // cache_control: object whose "type" == "ephemeral" (anthropic_helper.go:261-263)
-  __device__ bool cache_enabled(int cc) {
-    if (cc < 0) return false;
-    if (!is_obj(cc)) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
-    int t = -1, ttl = -1;
-    for (int m = cc + 1; d.ty(m) != '}'; m = d.after(m + 3)) {
-      const uint32_t k = d.id(m);
-      if (k == K_type) { if (t >= 0) { decline(AIGW_R_DUP_KEY); return false; } t = m + 3; }
-      else if (k == K_ttl) { if (ttl >= 0) { decline(AIGW_R_DUP_KEY); return false; } ttl = m + 3; }
-    }
-    if (ttl >= 0 && !is_null(ttl) && !is_str(ttl)) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
-    if (t < 0 || is_null(t)) return false;
-    if (!is_str(t)) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
-    return d.id(t) == V_ephemeral;
-  }
-  __device__ void emit_num_field(int v, bool integer) {
-    const uint32_t e = d.scalar_end(v), o = d.tok(v);
-    if (!is_num(v)) { decline(AIGW_R_E400_TYPE); return; }
-    const uint32_t l = canon_number(d.s + o, e - o, integer);
-    if (!l) { decline(AIGW_R_NUMBER); return; }
-    pl.src(d, o, l);
-  }
-  __device__ bool check_scalar_type(int v, int kind /*0 str,1 bool,2 int,3 float*/) {
-    if (v < 0) return true;
-    bool ok;
-    if (kind == 0) ok = is_str(v);
-    else if (kind == 1) ok = is_bool(v);
-    else {
-      ok = is_num(v);
-      if (ok && kind == 2) { const uint32_t e = d.scalar_end(v), o = d.tok(v); ok = canon_number(d.s + o, e - o, true) != 0; if (!ok) { decline(AIGW_R_NUMBER); return false; } }
-    }
-    if (!ok) decline(AIGW_R_E400_TYPE);
-    return ok;
-  }
-
-  // one {"type":…,"text":…,"cache_control":…} element: fields by id in one pass (null ⇒ absent)
-  struct Part { int type, text, cache, refusal, signature, redacted; };
-  __device__ bool scan_part(int e, Part& p) {
-    p.type = p.text = p.cache = p.refusal = p.signature = p.redacted = -1;
-    uint32_t seen = 0;
-    for (int m = e + 1; d.ty(m) != '}'; m = d.after(m + 3)) {
-      int slot;
-      switch (d.id(m)) { case K_type: slot = 0; break; case K_text: slot = 1; break; case K_cache_control: slot = 2; break; case K_refusal: slot = 3; break;
-        case K_signature: slot = 4; break; case K_redactedContent: slot = 5; break; default: slot = -1; }
-      if (slot < 0) continue;
-      if (seen & (1u << slot)) { decline(AIGW_R_DUP_KEY); return false; }
-      seen |= 1u << slot;
-      const int v = is_null(m + 3) ? -1 : m + 3;
-      switch (slot) { case 0: p.type = v; break; case 1: p.text = v; break; case 2: p.cache = v; break; case 3: p.refusal = v; break; case 4: p.signature = v; break; case 5: p.redacted = v; break; }
-    }
-    return true;
-  }
-
-  // text part list for system / developer / tool messages (ChatCompletionContentPartTextParam)
-  __device__ void emit_text_parts(int arr, bool with_cache, bool sys, bool& first) {
-    for (int e = arr + 1; d.ty(e) != ']'; e = d.after(e)) {
-      if (!is_obj(e)) { decline(is_null(e) ? AIGW_R_CONTENT : AIGW_R_E400_TYPE); return; }  // null element = zero struct in the reference
-      Part p; if (!scan_part(e, p)) return;
-      if ((p.text >= 0 && !is_str(p.text)) || (p.type >= 0 && !is_str(p.type))) { decline(AIGW_R_E400_TYPE); return; }
-      const bool cache = cache_enabled(p.cache);
-      if (bad()) return;
-      if (!first) pl.lit(L_COMMA, sys); first = false;
-      pl.lit(L_TEXT_OPEN, sys);
-      if (p.text >= 0) emit_str(p.text, sys); else pl.lit(L_EMPTY_STR, sys);
-      pl.lit(L_RBRACE, sys);
-      if (with_cache && cache) { pl.lit(L_COMMA, sys); pl.lit(L_CACHEPOINT, sys); }
-    }
-  }
-
-  // ---------------------------------------------------------------- response direction helpers
-  // decimal digits into scratch, as one op
-  __device__ void emit_dec(unsigned long long v, bool neg = false) {
-    char b[24]; int k = 0;
-    do { b[k++] = (char)('0' + v % 10ull); v /= 10ull; } while (v);
-    if (neg) b[k++] = '-';
-    if (sc.n + (uint32_t)k + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
-    for (int t = 0; t < k; t++) sc.p[sc.n + t] = (uint8_t)b[k - 1 - t];
-    pl.push(2, sc.n, (uint32_t)k); sc.n += ((uint32_t)k + 1u) & ~1u;
-  }
-  // configuration text (already known to need no JSON escaping) into scratch, as one op
-  __device__ void emit_cfg_text(const char* t, uint32_t n) {
-    if (sc.n + n + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
-    for (uint32_t i = 0; i < n; i++) sc.p[sc.n + i] = (uint8_t)t[i];
-    pl.push(2, sc.n, n); sc.n += (n + 1u) & ~1u;
-  }
-  // json.Marshal(map[string]any) of object `v`, then embedded in a JSON string: '"' and '\\' gain a backslash
-  // (bedrockToolUseToOpenAICalls, internal/translator/openai_awsbedrock.go:623-641).  The marshalled text is planned
-  // as ops first, then materialised into scratch with the escapes applied and replaced by one scratch op.
-  __device__ void emit_escaped_json(int v) {
-    if (pl.dry) { emit_any(d, pl, v); return; }
-    pl.flush();
-    const int n0 = pl.nops; const uint32_t olen0 = pl.olen;
-    emit_any(d, pl, v);
-    if (pl.err) return;
-    pl.flush();
-    const uint32_t start = sc.n;
-    for (int k = n0; k < pl.nops; k++) {
-      const uint32_t op = pl.ops[k], kind = op >> 30, l = (op >> 16) & 0x3fffu, off = op & 0xffffu;
-      const uint8_t* src = kind == 0 ? d.s + off : kind == 1 ? (const uint8_t*)c_lits.bytes + off : sc.p + off;
-      for (uint32_t i = 0; i < l; i++) {
-        const uint32_t c = src[i];
-        if (sc.n + 3 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
-        if (c == '"' || c == '\\') sc.p[sc.n++] = '\\';
-        sc.p[sc.n++] = (uint8_t)c;
-      }
-    }
-    pl.nops = n0; pl.olen = olen0;
-    const uint32_t total = sc.n - start;
-    if (total) pl.push(2, start, total);
-    sc.n = (sc.n + 1u) & ~1u;
-  }
-  // members of `obj` by response key id; `want` lists ids, `out` gets the value token (-1 absent or null)
-  __device__ bool rmembers(int obj, const uint8_t* want, int nw, int* out) {
-    for (int k = 0; k < nw; k++) out[k] = -1;
-    uint32_t seen = 0;
-    for (int m = obj + 1; d.ty(m) != '}'; m = d.after(m + 3)) {
-      const uint32_t id = d.id(m);
-      if (!id) continue;
-      for (int k = 0; k < nw; k++) if (want[k] == id) {
-        if (seen & (1u << k)) { decline(AIGW_R_DUP_KEY); return false; }
-        seen |= 1u << k;
-        out[k] = is_null(m + 3) ? -1 : m + 3;
-      }
-    }
-    return true;
-  }
-  // int64 struct field: 0 ok (value in `out`, must fit 31 bits here), 1 type error, 2 leave to the stock path
-  __device__ int rint(int v, uint32_t& out) {
-    out = 0;
-    if (v < 0) return 0;
-    if (!is_num(v)) return 1;
-    const uint32_t o = d.tok(v), e = d.scalar_end(v);
-    for (uint32_t i = o; i < e; i++) { const uint32_t c = d.s[i]; if (c == '.' || c == 'e' || c == 'E') return 1; }
-    if (d.s[o] == '-' || e - o > 10u) return 2;
-    unsigned long long x = 0;
-    for (uint32_t i = o; i < e; i++) x = x * 10ull + (d.s[i] - '0');
-    if (x >= 0x80000000ull) return 2;
-    out = (uint32_t)x;
-    return 0;
-  }
-  __device__ bool str_is(int v, const char* w, uint32_t wl) const {
-    if (d.str_len(v) != wl) return false;
-    const uint8_t* p = d.s + d.str_off(v);
-    for (uint32_t i = 0; i < wl; i++) if (p[i] != (uint8_t)w[i]) return false;
-    return true;
-  }
-
-  // Buffered Bedrock Converse response → openai.ChatCompletionResponse (internal/translator/openai_awsbedrock.go:734-824).
-  // terr: a known field has the wrong JSON type (the reference's decode fails: AIGW_INTERNAL); decline(): left to the stock path.
-  __device__ void plan_bedrock_response(uint32_t& path_len) {
-    bool terr = false, unsup = false;
-    if (is_null(0)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }      // zero struct: nil Output, the reference panics
-    if (!is_obj(0)) { decline(AIGW_R_E500_DECODE); return; }
-    static const uint8_t k_root[] = {RK_metrics, RK_output, RK_stopReason, RK_serviceTier, RK_usage};
-    int r[5]; if (!rmembers(0, k_root, 5, r)) return;
-    const int metrics = r[0], output = r[1], stop = r[2], tier_o = r[3], usage_o = r[4];
-    uint32_t tmp;
-    if (metrics >= 0) {
-      if (!is_obj(metrics)) terr = true;
-      else { static const uint8_t k[] = {RK_latencyMs}; int q[1]; if (!rmembers(metrics, k, 1, q)) return; const int rc = rint(q[0], tmp); if (rc == 1) terr = true; else if (rc == 2) unsup = true; }
-    }
-    if (stop >= 0 && !is_str(stop)) terr = true;
-    int tier = -1;
-    if (tier_o >= 0) {
-      if (!is_obj(tier_o)) terr = true;
-      else { static const uint8_t k[] = {RK_type}; int q[1]; if (!rmembers(tier_o, k, 1, q)) return; tier = q[0]; if (tier >= 0 && !is_str(tier)) terr = true; }
-    }
-    bool has_usage = false, has_rd = false, has_wr = false; uint32_t u_in = 0, u_out = 0, u_rd = 0, u_wr = 0;
-    if (usage_o >= 0) {
-      if (!is_obj(usage_o)) terr = true;
-      else {
-        has_usage = true;
-        static const uint8_t k[] = {RK_inputTokens, RK_outputTokens, RK_totalTokens, RK_cacheReadInputTokens, RK_cacheWriteInputTokens};
-        int q[5]; if (!rmembers(usage_o, k, 5, q)) return;
-        uint32_t* dst[5] = {&u_in, &u_out, &tmp, &u_rd, &u_wr};
-        for (int i = 0; i < 5; i++) { const int rc = rint(q[i], *dst[i]); if (rc == 1) terr = true; else if (rc == 2) unsup = true; }
-        has_rd = q[3] >= 0; has_wr = q[4] >= 0;
-      }
-    }
-    if (output >= 0 && !is_obj(output)) terr = true;
-    int role = -1, content = -1, text = -1, reason_blk = -1, n_tools = 0;
-    if (output >= 0 && is_obj(output)) {
-      static const uint8_t k[] = {RK_message}; int q[1]; if (!rmembers(output, k, 1, q)) return;
-      const int msg = q[0];
-      if (msg >= 0 && !is_obj(msg)) terr = true;
-      if (msg >= 0 && is_obj(msg)) {
-        static const uint8_t km[] = {RK_role, RK_content}; int qm[2]; if (!rmembers(msg, km, 2, qm)) return;
-        role = qm[0]; content = qm[1];
-        if (role >= 0 && !is_str(role)) terr = true;
-        if (content >= 0 && !is_arr(content)) { terr = true; content = -1; }
-      }
-    }
-    // first pass over the content blocks: types, first text, last reasoning block, number of tool calls
-    static const uint8_t kb[] = {RK_text, RK_toolUse, RK_reasoningContent, RK_document, RK_image, RK_toolResult, RK_cachePoint};
-    if (content >= 0) {
-      for (int e = content + 1; d.ty(e) != ']'; e = d.after(e)) {
-        if (is_null(e)) { unsup = true; continue; }                     // nil *ContentBlock is dereferenced by the reference
-        if (!is_obj(e)) { terr = true; continue; }
-        int q[7]; if (!rmembers(e, kb, 7, q)) return;
-        if (q[3] >= 0 || q[4] >= 0 || q[5] >= 0 || q[6] >= 0) unsup = true;
-        if (q[0] >= 0 && !is_str(q[0])) terr = true;
-        if (q[1] >= 0) {
-          if (!is_obj(q[1])) terr = true;
-          else {
-            static const uint8_t kt[] = {RK_name, RK_input, RK_toolUseId}; int t[3]; if (!rmembers(q[1], kt, 3, t)) return;
-            if ((t[0] >= 0 && !is_str(t[0])) || (t[2] >= 0 && !is_str(t[2])) || (t[1] >= 0 && !is_obj(t[1]))) terr = true;
-            n_tools++;
-          }
-        }
-        if (q[2] >= 0) {
-          if (!is_obj(q[2])) terr = true;
-          else {
-            static const uint8_t kr[] = {RK_reasoningText, RK_redactedContent}; int t[2]; if (!rmembers(q[2], kr, 2, t)) return;
-            if (t[0] >= 0) {
-              if (!is_obj(t[0])) terr = true;
-              else { static const uint8_t kx[] = {RK_text, RK_signature}; int x[2]; if (!rmembers(t[0], kx, 2, x)) return; if ((x[0] >= 0 && !is_str(x[0])) || (x[1] >= 0 && !is_str(x[1]))) terr = true; }
-            }
-            if (t[1] >= 0) { if (!is_str(t[1])) terr = true; else if (d.str_len(t[1]) > 0) unsup = true; }  // []byte is re-encoded: stock path
-          }
-        }
-        if (q[1] < 0 || !is_obj(q[1])) {
-          if (q[0] >= 0) { if (text < 0) text = q[0]; }
-          else if (q[2] >= 0) reason_blk = e;
-        }
-      }
-    }
-    if (terr) { decline(AIGW_R_E500_DECODE); return; }
-    if (output < 0 || unsup) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-    if (bad()) return;
-    // ---- usage record in front of the body (the slot request schemas use for :path)
-    const unsigned long long tin = (unsigned long long)u_in + u_rd + u_wr;
-    if (tin + u_out >= 0x80000000ull) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-    {
-      sc.n = (sc.n + 3u) & ~3u;
-      if (sc.n + 34 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
-      uint32_t* u = (uint32_t*)(sc.p + sc.n);
-      u[0] = has_usage ? (uint32_t)tin : 0u; u[1] = has_usage ? u_out : 0u; u[2] = has_usage ? (uint32_t)tin + u_out : 0u;
-      u[3] = has_rd ? u_rd : 0u; u[4] = has_wr ? u_wr : 0u; u[5] = 0u; u[6] = has_usage ? (7u | (has_rd ? 8u : 0u) | (has_wr ? 16u : 0u)) : 0u; u[7] = 0u;
-      pl.push(2, sc.n, 32); sc.n += 32;
-      path_len = 32;
-    }
-    // ---- body, fields in struct order (internal/apischema/openai/openai.go:1269-1306,1365-1422)
-    pl.lit(L_LBRACE);
-    if (P->rid_len) { pl.lit(L_R_ID_OPEN); emit_cfg_text(P->response_id, P->rid_len); pl.lit(L_R_QUOTE_COMMA); }
-    pl.lit(L_R_CHOICES);
-    {
-      int fr = L_R_FR_STOP;
-      if (stop >= 0) {
-        if (d.str_has_backslash(stop)) { decline(AIGW_R_ESCAPE); return; }
-        if (str_is(stop, "max_tokens", 10)) fr = L_R_FR_LENGTH; else if (str_is(stop, "content_filtered", 16)) fr = L_R_FR_FILTER; else if (str_is(stop, "tool_use", 8)) fr = L_R_FR_TOOLS;
-      }
-      pl.lit(fr);
-    }
-    pl.lit(L_R_MSG);
-    bool first = true;
-    if (text >= 0) { pl.lit(L_R_CONTENT); emit_str(text); first = false; }
-    if (role >= 0 && d.str_len(role) > 0) { if (!first) pl.lit(L_COMMA); first = false; pl.lit(L_R_ROLE); emit_str(role); }
-    if (n_tools) {
-      if (!first) pl.lit(L_COMMA); first = false;
-      pl.lit(L_R_TOOLCALLS);
-      bool tf = true;
-      for (int e = content + 1; d.ty(e) != ']'; e = d.after(e)) {
-        static const uint8_t k1[] = {RK_toolUse}; int q[1]; if (!rmembers(e, k1, 1, q)) return;
-        if (q[0] < 0) continue;
-        static const uint8_t kt[] = {RK_name, RK_input, RK_toolUseId}; int t[3]; if (!rmembers(q[0], kt, 3, t)) return;
-        if (!tf) pl.lit(L_COMMA); tf = false;
-        pl.lit(L_R_TC_ID); if (t[2] >= 0) emit_str(t[2]); else pl.lit(L_EMPTY_STR);
-        pl.lit(L_R_TC_ARGS);
-        if (t[1] >= 0) emit_escaped_json(t[1]); else pl.lit(L_NULL);
-        if (bad()) return;
-        pl.lit(L_R_TC_NAME); if (t[0] >= 0) emit_str(t[0]); else pl.lit(L_EMPTY_STR);
-        pl.lit(L_R_TC_END);
-      }
-      pl.lit(L_RBRACK);
-    }
-    if (reason_blk >= 0) {
-      if (!first) pl.lit(L_COMMA); first = false;
-      pl.lit(L_R_REASON);
-      static const uint8_t k1[] = {RK_reasoningContent}; int q[1]; if (!rmembers(reason_blk, k1, 1, q)) return;
-      static const uint8_t kr[] = {RK_reasoningText}; int t[1]; if (!rmembers(q[0], kr, 1, t)) return;
-      if (t[0] >= 0) {
-        static const uint8_t kx[] = {RK_text, RK_signature}; int x[2]; if (!rmembers(t[0], kx, 2, x)) return;
-        pl.lit(L_R_RTEXT); if (x[0] >= 0) emit_str(x[0]); else pl.lit(L_EMPTY_STR);
-        if (x[1] >= 0 && d.str_len(x[1]) > 0) { pl.lit(L_R_RSIG); emit_str(x[1]); }
-        pl.lit(L_RBRACE);
-      }
-      pl.lit(L_R_RBRACE2);
-    }
-    pl.lit(L_R_CREATED);
-    emit_dec(P->created < 0 ? 0ull - (unsigned long long)P->created : (unsigned long long)P->created, P->created < 0);
-    if (P->override_len) { pl.lit(L_R_MODEL); emit_cfg_text(P->override_model, P->override_len); pl.lit(L_R_QUOTE); }
-    if (tier >= 0 && d.str_len(tier) > 0) { pl.lit(L_R_TIER); emit_str(tier); }
-    pl.lit(L_R_OBJECT);
-    if (has_usage && (tin || u_out || has_rd || has_wr)) {   // Usage is omitzero: a zero struct is left out
-      pl.lit(L_R_USAGE);
-      bool uf = true;
-      auto num = [&](int lit, uint32_t v) { if (!v) return; if (!uf) pl.lit(L_COMMA); uf = false; pl.lit(lit); emit_dec(v); };
-      num(L_R_PROMPT, (uint32_t)tin); num(L_R_COMPLETION, u_out); num(L_R_TOTAL, (uint32_t)tin + u_out);
-      if (has_rd || has_wr) {
-        if (!uf) pl.lit(L_COMMA);
-        pl.lit(L_R_PTD); uf = true;
-        if (has_rd) num(L_R_CACHED, u_rd);
-        if (has_wr) num(L_R_CC, u_wr);
-        pl.lit(L_RBRACE);
-      }
-      pl.lit(L_RBRACE);
-    }
-    pl.lit(L_RBRACE);
-  }
-
-  // Buffered anthropic.Message → openai.ChatCompletionResponse (internal/translator/openai_gcpanthropic.go:246-278 and
-  // messageToChatCompletion, anthropic_helper.go:1165-1255).  A known field of the wrong JSON type is left to the stock path
-  // (the SDK's decoder is lenient in ways no reference test pins); strings are echoed raw (the index kernel admits only escapes
-  // the encoder reproduces byte for byte).
-  __device__ void plan_anthropic_response(uint32_t& path_len, uint32_t& model_off, uint32_t& model_len) {
-    if (!is_obj(0)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }   // null decodes to a zero Message, other shapes are the SDK decoder's business: stock path
-    static const uint8_t k_root[] = {RK_id, RK_model, RK_stop_reason, RK_role, RK_usage, RK_content};
-    int r[6]; if (!rmembers(0, k_root, 6, r)) return;
-    const int id = r[0], model = r[1], stop = r[2], role = r[3], usage_o = r[4], content = r[5];
-    bool unp = false;
-    for (int k = 0; k < 4; k++) if (r[k] >= 0 && !is_str(r[k])) unp = true;
-    uint32_t u_in = 0, u_out = 0, u_rd = 0, u_cr = 0;
-    if (usage_o >= 0) {
-      if (!is_obj(usage_o)) unp = true;
-      else {
-        static const uint8_t k[] = {RK_input_tokens, RK_output_tokens, RK_cache_read_input_tokens, RK_cache_creation_input_tokens};
-        int q[4]; if (!rmembers(usage_o, k, 4, q)) return;
-        uint32_t* dst[4] = {&u_in, &u_out, &u_rd, &u_cr};
-        for (int i = 0; i < 4; i++) if (rint(q[i], *dst[i]) != 0) unp = true;
-      }
-    }
-    if (content >= 0 && !is_arr(content)) unp = true;
-    static const uint8_t kb[] = {RK_type, RK_text, RK_id, RK_name, RK_input, RK_thinking, RK_signature, RK_data};
-    int text = -1, think_blk = -1, n_tools = 0; bool redacted = false;
-    if (content >= 0 && is_arr(content)) {
-      for (int e = content + 1; d.ty(e) != ']'; e = d.after(e)) {
-        if (!is_obj(e)) { unp = true; continue; }
-        int q[8]; if (!rmembers(e, kb, 8, q)) return;
-        for (int k = 0; k < 8; k++) if (k != 4 && q[k] >= 0 && !is_str(q[k])) unp = true;
-        if (unp || q[0] < 0) continue;
-        if (d.str_has_backslash(q[0])) { unp = true; continue; }
-        if (str_is(q[0], "tool_use", 8)) { if (q[2] >= 0 && d.str_len(q[2]) > 0) n_tools++; }
-        else if (str_is(q[0], "text", 4)) { if (q[1] >= 0 && d.str_len(q[1]) > 0 && text < 0) text = q[1]; }
-        else if (str_is(q[0], "thinking", 8)) { if (q[5] >= 0 && d.str_len(q[5]) > 0) { think_blk = e; redacted = false; } }
-        else if (str_is(q[0], "redacted_thinking", 17)) { if (q[7] >= 0 && d.str_len(q[7]) > 0) redacted = true; }
-      }
-    }
-    if (unp || redacted) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }   // redactedContent is a re-encoded []byte: stock path
-    if (bad()) return;
-    // finish reason / role (errors of the reference)
-    int fr = -1;
-    if (stop >= 0) {
-      if (d.str_has_backslash(stop)) { decline(AIGW_R_ESCAPE); return; }
-      if (str_is(stop, "end_turn", 8) || str_is(stop, "stop_sequence", 13) || str_is(stop, "pause_turn", 10)) fr = L_R_FR_STOP;
-      else if (str_is(stop, "max_tokens", 10)) fr = L_R_FR_LENGTH; else if (str_is(stop, "tool_use", 8)) fr = L_R_FR_TOOLS; else if (str_is(stop, "refusal", 7)) fr = L_R_FR_FILTER;
-    }
-    int role_lit = -1;
-    if (role >= 0) { if (d.str_has_backslash(role)) { decline(AIGW_R_ESCAPE); return; } if (str_is(role, "assistant", 9)) role_lit = L_R_Q_ASSISTANT; else if (str_is(role, "user", 4)) role_lit = L_R_Q_USER; }
-    if (fr < 0 || role_lit < 0) { decline(AIGW_R_E500_DECODE); return; }   // "received invalid stop reason" / "invalid anthropic role"
-    const unsigned long long tin = (unsigned long long)u_in + u_rd + u_cr;
-    if (tin + u_out >= 0x80000000ull) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-    if (model >= 0 && d.str_len(model) > 0) { model_off = d.str_off(model); model_len = d.str_len(model); }
-    {
-      sc.n = (sc.n + 3u) & ~3u;
-      if (sc.n + 34 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
-      uint32_t* u = (uint32_t*)(sc.p + sc.n);
-      u[0] = (uint32_t)tin; u[1] = u_out; u[2] = (uint32_t)tin + u_out; u[3] = u_rd; u[4] = u_cr; u[5] = 0u; u[6] = 1u | 2u | 4u | 8u | 16u; u[7] = 0u;
-      pl.push(2, sc.n, 32); sc.n += 32;
-      path_len = 32;
-    }
-    pl.lit(L_LBRACE);
-    if (id >= 0 && d.str_len(id) > 0) { pl.lit(L_R_ID_KEY); emit_str(id); pl.lit(L_COMMA); }
-    pl.lit(L_R_CHOICES); pl.lit(fr); pl.lit(L_R_MSG);
-    if (text >= 0) { pl.lit(L_R_CONTENT); emit_str(text); pl.lit(L_COMMA); }
-    pl.lit(L_R_ROLE); pl.lit(role_lit);
-    if (n_tools) {
-      pl.lit(L_COMMA); pl.lit(L_R_TOOLCALLS);
-      bool tf = true;
-      for (int e = content + 1; d.ty(e) != ']'; e = d.after(e)) {
-        int q[8]; if (!rmembers(e, kb, 8, q)) return;
-        if (q[0] < 0 || !str_is(q[0], "tool_use", 8) || q[2] < 0 || d.str_len(q[2]) == 0) continue;
-        if (!tf) pl.lit(L_COMMA); tf = false;
-        pl.lit(L_R_TC_ID); emit_str(q[2]); pl.lit(L_R_TC_ARGS);
-        if (q[4] >= 0) emit_escaped_json(q[4]); else pl.lit(L_NULL);
-        if (bad()) return;
-        pl.lit(L_R_TC_NAME); if (q[3] >= 0) emit_str(q[3]); else pl.lit(L_EMPTY_STR);
-        pl.lit(L_R_TC_END);
-      }
-      pl.lit(L_RBRACK);
-    }
-    if (think_blk >= 0) {
-      int q[8]; if (!rmembers(think_blk, kb, 8, q)) return;
-      pl.lit(L_COMMA); pl.lit(L_R_REASON); pl.lit(L_R_RTEXT); emit_str(q[5]);
-      if (q[6] >= 0 && d.str_len(q[6]) > 0) { pl.lit(L_R_RSIG); emit_str(q[6]); }
-      pl.lit(L_RBRACE); pl.lit(L_R_RBRACE2);
-    }
-    pl.lit(L_R_CREATED);
-    emit_dec(P->created < 0 ? 0ull - (unsigned long long)P->created : (unsigned long long)P->created, P->created < 0);
-    if (model_len) { pl.lit(L_R_MODEL_KEY); emit_str(model); }
-    else if (P->override_len) { pl.lit(L_R_MODEL); emit_cfg_text(P->override_model, P->override_len); pl.lit(L_R_QUOTE); }
-    pl.lit(L_R_OBJECT); pl.lit(L_R_USAGE);
-    bool uf = true;
-    auto num = [&](int lit, uint32_t v) { if (!v) return; if (!uf) pl.lit(L_COMMA); uf = false; pl.lit(lit); emit_dec(v); };
-    num(L_R_PROMPT, (uint32_t)tin); num(L_R_COMPLETION, u_out); num(L_R_TOTAL, (uint32_t)tin + u_out);
-    if (!uf) pl.lit(L_COMMA);
-    pl.lit(L_R_PTD); uf = true;
-    num(L_R_CACHED, u_rd); num(L_R_CC, u_cr);
-    pl.lit(L_RBRACE); pl.lit(L_RBRACE); pl.lit(L_RBRACE);
-  }
-
-  // ---------------------------------------------------------------- /v1/embeddings (P3 + T1 + T6)
-  // EmbeddingsEndpointSpec.ParseBody (internal/endpointspec/endpointspec.go:231-240; input union internal/apischema/openai/union.go:71-147,
-  // EmbeddingInputItem / EmbeddingContent internal/apischema/openai/openai.go:316-375) followed by the OpenAI / Azure passthrough
-  // (internal/translator/openai_embeddings.go:38-59, openai_azureopenai_embeddings.go:36-61) or the Vertex predict request
-  // (internal/translator/openai_gcpvertexai_embeddings.go:46-180, internal/apischema/gcp/gcp.go:45-76).
-  struct EmbItem { int content, task, title; };
-  // Go int / int64 struct field: a number with a fraction or exponent fails the decode (400); other spellings strconv would
-  // not print back (leading '-0', > 18 digits) are left to the stock path
-  __device__ bool emb_int(int v) {
-    if (!is_num(v)) { decline(AIGW_R_E400_TYPE); return false; }
-    const uint32_t o = d.tok(v), e = d.scalar_end(v);
-    for (uint32_t i = o; i < e; i++) { const uint32_t c = d.s[i]; if (c == '.' || c == 'e' || c == 'E') { decline(AIGW_R_E400_TYPE); return false; } }
-    if (!canon_number(d.s + o, e - o, true)) { decline(AIGW_R_NUMBER); return false; }
-    return true;
-  }
-  // one EmbeddingInputItem: returns false after decline(); `empty` = EmbeddingContent.IsEmpty()
-  __device__ bool scan_emb_item(int e, EmbItem& it, bool& empty) {
-    it.content = it.task = it.title = -1; empty = true;
-    if (is_null(e)) return true;
-    if (!is_obj(e)) { decline(AIGW_R_E400_TYPE); return false; }
-    uint32_t seen = 0; int content_raw = -1;
-    for (int m = e + 1; d.ty(m) != '}'; m = d.after(m + 3)) {
-      int slot;
-      switch (d.id(m)) { case K_content: slot = 0; break; case K_task_type: slot = 1; break; case K_title: slot = 2; break; default: slot = -1; }
-      if (slot < 0) continue;
-      if (seen & (1u << slot)) { decline(AIGW_R_DUP_KEY); return false; }
-      seen |= 1u << slot;
-      const int v = m + 3;
-      if (slot == 0) content_raw = v; else if (!is_null(v)) { if (!is_str(v)) { decline(AIGW_R_E400_TYPE); return false; } if (slot == 1) it.task = v; else it.title = v; }
-    }
-    if (content_raw >= 0) {
-      if (is_null(content_raw)) empty = true;                  // decodes as the empty string
-      else if (is_str(content_raw)) { it.content = content_raw; empty = d.str_len(content_raw) == 0; }
-      else if (is_arr(content_raw)) {
-        it.content = content_raw; empty = d.ty(content_raw + 1) == ']';
-        for (int q = content_raw + 1; d.ty(q) != ']'; q = d.after(q)) if (!is_str(q) && !is_null(q)) { decline(AIGW_R_E400_CONTENT); return false; }
-      } else { decline(AIGW_R_E400_CONTENT); return false; }
-    }
-    return true;
-  }
-  __device__ bool str_eq_lit(int v, const char* w, uint32_t wl) const {
-    if (d.str_has_backslash(v) || d.str_len(v) != wl) return false;
-    const uint8_t* p = d.s + d.str_off(v);
-    for (uint32_t i = 0; i < wl; i++) if (p[i] != (uint8_t)w[i]) return false;
-    return true;
-  }
-  // one gcp.Instance: {"content":C[,"task_type":T][,"title":X]}
-  __device__ void emit_instance(int content /* string token or -1 = "" */, int task, int title, bool& first) {
-    // the closing brace of an instance is emitted with the opening of the next one (one literal op instead of three)
-    pl.lit(first ? L_EM_CONTENT : L_EM_NEXT); first = false;
-    if (content >= 0) emit_str(content); else pl.lit(L_EMPTY_STR);
-    if (task >= 0 && d.str_len(task) > 0) { pl.lit(L_EM_TASK); emit_str(task); }
-    if (title >= 0) { pl.lit(L_EM_TITLE); emit_str(title); }
-  }
-  __device__ void emit_item_instances(const EmbItem& it, int global_task, bool& first) {
-    // Title is kept only with the ITEM's task_type == RETRIEVAL_DOCUMENT; a request-level task_type then overrides the type
-    const bool keep_title = it.task >= 0 && it.title >= 0 && d.str_len(it.title) > 0 && str_eq_lit(it.task, "RETRIEVAL_DOCUMENT", 18);
-    const int task = global_task >= 0 ? global_task : it.task;
-    const int title = keep_title ? it.title : -1;
-    if (is_str(it.content)) emit_instance(it.content, task, title, first);
-    else for (int q = it.content + 1; d.ty(q) != ']'; q = d.after(q)) emit_instance(is_null(q) ? -1 : q, task, title, first);
-  }
-  __device__ void plan_embeddings(uint32_t& path_len, uint32_t& model_off, uint32_t& model_len, uint32_t& body_kind) {
-    const int base = P->schema & 15;
-    body_kind = AIGW_BODY_UNCHANGED;
-    int input = -1, model_raw = -1, model = -1, dims = -1, autot = -1, gtask = -1;
-    bool has_input = false;
-    if (!is_null(0)) {
-      if (!is_obj(0)) { decline(AIGW_R_E400_TYPE); return; }
-      uint32_t seen = 0;
-      for (int m = 1; d.ty(m) != '}'; m = d.after(m + 3)) {
-        int slot;
-        switch (d.id(m)) { case K_input: slot = 0; break; case K_model: slot = 1; break; case K_encoding_format: slot = 2; break; case K_dimensions: slot = 3; break; case K_user: slot = 4; break;
-          case K_auto_truncate: slot = 5; break; case K_task_type: slot = 6; break; default: slot = -1; }
-        if (slot < 0) continue;
-        if (seen & (1u << slot)) { decline(AIGW_R_DUP_KEY); return; }
-        seen |= 1u << slot;
-        const int v = m + 3; const bool nul = is_null(v);
-        switch (slot) {
-          case 0: input = v; has_input = true; break;
-          case 1: model_raw = v; if (!nul) { if (!is_str(v)) { decline(AIGW_R_E400_TYPE); return; } model = v; } break;
-          case 2: case 4: if (!nul && !is_str(v)) { decline(AIGW_R_E400_TYPE); return; } break;
-          case 3: if (!nul) { if (!emb_int(v)) return; dims = v; } break;
-          case 5: if (!nul) { if (!is_bool(v)) { decline(AIGW_R_E400_TYPE); return; } autot = v; } break;
-          case 6: if (!nul) { if (!is_str(v)) { decline(AIGW_R_E400_TYPE); return; } if (d.str_len(v) > 0) gtask = v; } break;  // "" overrides nothing
-        }
-      }
-    }
-    // ---- the input union: 0 none, 1 string, 2 []string, 3 item, 4 []item, 5 ints / int arrays
-    int kind = 0;
-    if (has_input) {
-      if (is_str(input)) kind = 1;
-      else if (is_obj(input)) { EmbItem it; bool empty; if (!scan_emb_item(input, it, empty)) return; if (empty) { decline(AIGW_R_E400_CONTENT); return; } kind = 3; }
-      else if (is_arr(input)) {
-        const int f = input + 1;
-        if (d.ty(f) == ']') kind = 2;
-        else if (is_str(f)) { kind = 2; for (int q = f; d.ty(q) != ']'; q = d.after(q)) if (!is_str(q) && !is_null(q)) { decline(AIGW_R_E400_TYPE); return; } }
-        else if (is_obj(f)) { kind = 4; for (int q = f; d.ty(q) != ']'; q = d.after(q)) { EmbItem it; bool empty; if (!scan_emb_item(q, it, empty)) return; if (empty) { decline(AIGW_R_E400_CONTENT); return; } } }
-        else if (is_arr(f)) {
-          kind = 5;
-          for (int q = f; d.ty(q) != ']'; q = d.after(q)) {
-            if (is_null(q)) continue;
-            if (!is_arr(q)) { decline(AIGW_R_E400_TYPE); return; }
-            for (int x = q + 1; d.ty(x) != ']'; x = d.after(x)) if (!is_null(x) && !emb_int(x)) return;
-          }
-        } else if (is_num(f)) { kind = 5; for (int q = f; d.ty(q) != ']'; q = d.after(q)) if (!is_null(q) && !emb_int(q)) return; }
-        else { decline(AIGW_R_E400_TYPE); return; }
-      } else { decline(AIGW_R_E400_TYPE); return; }
-    }
-    if (bad()) return;
-    if (model >= 0) { if (d.str_has_backslash(model)) { decline(AIGW_R_ESCAPE); return; } model_off = d.str_off(model); model_len = d.str_len(model); }
-    const bool need_model = P->override_len != 0;
-    if (need_model) for (uint32_t i = 0; i < P->override_len; i++) { const uint32_t c = (uint8_t)P->override_model[i]; if (c < 0x20 || c > 0x7f || c == '"' || c == '\\') { decline(AIGW_R_UNSUPPORTED_FIELD); return; } }
-    // ---- :path
-    if (base == AIGW_SCHEMA_OPENAI) emit_cfg_text(P->openai_path, P->prefix_len);
-    else {
-      pl.lit(base == AIGW_SCHEMA_AZURE_OPENAI ? L_EM_AZ_PATH1 : L_EM_GOOGLE_PATH);
-      if (need_model) emit_cfg_text(P->override_model, P->override_len); else if (model >= 0) pl.src(d, d.str_off(model), d.str_len(model));
-      if (base == AIGW_SCHEMA_AZURE_OPENAI) { pl.lit(L_EM_AZ_PATH2); emit_cfg_text(P->api_version, P->version_len); } else pl.lit(L_EM_PREDICT);
-    }
-    if (bad()) return;
-    path_len = pl.olen;
-    if (base != AIGW_SCHEMA_GCP_VERTEX) {
-      // sjson.SetBytesOptions(original, "model", override): splice the first "model" value, or append the member at the root
-      if (!need_model) { if (P->force_mutation) { pl.src(d, 0, d.len); body_kind = AIGW_BODY_BYTES; } return; }
-      body_kind = AIGW_BODY_BYTES;
-      if (is_null(0)) { pl.lit(L_LBRACE); pl.lit(L_MODEL_MEMBER); pl.lit(L_QUOTE); emit_cfg_text(P->override_model, P->override_len); pl.lit(L_QUOTE); pl.lit(L_RBRACE); return; }
-      const int root_close = d.jmp[0];
-      if (model_raw >= 0) {
-        const uint32_t b = d.tok(model_raw), e = is_str(model_raw) ? d.tok(model_raw + 1) + 1u : d.scalar_end(model_raw);
-        pl.src(d, 0, b); pl.lit(L_QUOTE); emit_cfg_text(P->override_model, P->override_len); pl.lit(L_QUOTE); pl.src(d, e, d.len - e);
-      } else {
-        const uint32_t o = d.tok(0), c = d.tok(root_close);
-        pl.src(d, o, c - o); if (root_close != 1) pl.lit(L_COMMA); pl.lit(L_MODEL_MEMBER); pl.lit(L_QUOTE); emit_cfg_text(P->override_model, P->override_len); pl.lit(L_QUOTE); pl.lit(L_RBRACE);
-      }
-      return;
-    }
-    // ---- Vertex: gcp.PredictRequest{instances, parameters}
-    if (kind == 0 || kind == 5) { pend(AIGW_R_E500_ARGS); return; }   // "unsupported input type for embedding"
-    body_kind = AIGW_BODY_BYTES;
-    pl.lit(L_EM_OPEN);
-    {
-      bool first = true;
-      bool any = false;
-      if (kind == 1) any = true;
-      else if (kind == 2) any = d.ty(input + 1) != ']';
-      else any = true;
-      if (!any) pl.lit(L_NULL);
-      else {
-        pl.lit(L_LBRACK);
-        if (kind == 1) emit_instance(input, gtask, -1, first);
-        else if (kind == 2) { for (int q = input + 1; d.ty(q) != ']'; q = d.after(q)) emit_instance(is_null(q) ? -1 : q, gtask, -1, first); }
-        else if (kind == 3) { EmbItem it; bool e2; scan_emb_item(input, it, e2); emit_item_instances(it, gtask, first); }
-        else { for (int q = input + 1; d.ty(q) != ']'; q = d.after(q)) { EmbItem it; bool e2; scan_emb_item(q, it, e2); emit_item_instances(it, gtask, first); } }
-        pl.lit(L_EM_LAST);
-      }
-    }
-    pl.lit(L_EM_PARAMS);
-    bool pf = true;
-    if (autot >= 0 && d.ty(autot) == 't') { pl.lit(L_EM_AUTOTRUNC); pf = false; }
-    if (dims >= 0) {
-      const uint32_t o = d.tok(dims), e = d.scalar_end(dims);
-      bool pos = d.s[o] != '-'; if (pos) { pos = false; for (uint32_t i = o; i < e; i++) if (d.s[i] != '0') pos = true; }
-      if (pos) { if (!pf) pl.lit(L_COMMA); pl.lit(L_EM_DIMS); pl.src(d, o, e - o); }
-    }
-    pl.lit(L_EM_END);
-  }
-
-  struct Msg { int role_v, content, name, tool_calls, tool_call_id, refusal, audio; };
-  // role: 0 user 1 assistant 2 system 3 developer 4 tool
-  __device__ int scan_message(int m, Msg& g) {
-    g.role_v = g.content = g.name = g.tool_calls = g.tool_call_id = g.refusal = g.audio = -1;
-    if (!is_obj(m)) { decline(AIGW_R_E400_ROLE); return -1; }
-    uint32_t seen = 0;
-    for (int k = m + 1; d.ty(k) != '}'; k = d.after(k + 3)) {
-      const int v = k + 3;
-      int which;
-      switch (d.id(k)) { case K_role: which = 0; break; case K_content: which = 1; break; case K_name: which = 2; break; case K_tool_calls: which = 3; break;
-        case K_tool_call_id: which = 4; break; case K_refusal: which = 5; break; case K_audio: which = 6; break; default: which = -1; }
-      if (which < 0) continue;
-      if (seen & (1u << which)) { decline(AIGW_R_DUP_KEY); return -1; }
-      seen |= 1u << which;
-      switch (which) { case 0: g.role_v = v; break; case 1: g.content = v; break; case 2: g.name = v; break; case 3: g.tool_calls = v; break;
-        case 4: g.tool_call_id = v; break; case 5: g.refusal = v; break; case 6: g.audio = v; break; }
-    }
-    if (g.role_v < 0 || !is_str(g.role_v)) { decline(AIGW_R_E400_ROLE); return -1; }
-    switch (d.id(g.role_v)) { case V_user: return 0; case V_assistant: return 1; case V_system: return 2; case V_developer: return 3; case V_tool: return 4; default: break; }
-    decline(AIGW_R_E400_ROLE); return -1;
-  }
-
-  // ---- Bedrock: tool result block for one tool message (openai_awsbedrock.go:451-486)
-  __device__ void bedrock_tool_result(const Msg& g) {
-    pl.lit(L_TOOLRESULT_OPEN);
-    if (g.content < 0) pend(AIGW_R_E422_CONTENT);   // absent ⇒ 422 "message 'content' must be a string or an array"
-    else if (is_str(g.content)) { pl.lit(L_TEXT_OPEN); emit_str(g.content); pl.lit(L_RBRACE); }
-    else if (is_arr(g.content)) { bool first = true; emit_text_parts(g.content, false, false, first); }
-    else { decline(AIGW_R_E400_CONTENT); return; }  // null / number / object: ContentUnion rejects it
-    pl.lit(L_TOOLRESULT_MID);
-    int id = g.tool_call_id;
-    if (id >= 0 && is_null(id)) id = -1;
-    if (id >= 0) { if (!is_str(id)) { decline(AIGW_R_E400_TYPE); return; } emit_str(id); } else pl.lit(L_EMPTY_STR);
-    pl.lit(L_TOOLRESULT_CLOSE);
-  }
-
-  // ---- tool call arguments: JSON text inside a JSON string → map[string]any → marshal
-  __device__ void emit_arguments(int v) {
-    if (d.str_nc(v)) { decline(AIGW_R_ESCAPE); return; }   // the unescape below knows the five canonical escapes only
-    const uint32_t off = d.str_off(v), n = d.str_len(v);
-    if (sc.n + n + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
-    uint8_t* dst = sc.p + sc.n; uint32_t w = 0;
-    const uint8_t* p = d.s + off;
-    for (uint32_t i = 0; i < n; i++) {
-      uint32_t c = p[i];
-      if (c == '\\') { const uint32_t e = p[++i]; c = e == 'n' ? '\n' : e == 'r' ? '\r' : e == 't' ? '\t' : e; }
-      dst[w++] = (uint8_t)c;
-    }
-    const uint32_t base = sc.n; sc.n += (w + 1u) & ~1u;
-    const int nt = tokenize_seq(dst, w, base, tw_tail, tail_cap);
-    if (nt == 0 || nt == -AIGW_R_SYNTAX) { pend(AIGW_R_E500_ARGS); pl.lit(L_NULL); return; }
-    if (nt < 0) { decline(-nt); return; }
-    Doc a; a.s = sc.p; a.len = base + w; a.tw = tw_tail; a.jmp = jmp_tail; a.nt = nt; a.kind = 2;
-    { const int vr = validate_tokens(a); if (vr == AIGW_R_SYNTAX) { pend(AIGW_R_E500_ARGS); pl.lit(L_NULL); return; } if (vr) { decline(vr); return; } }
-    const uint32_t c0 = a.ty(0);
-    if (c0 == 'n') { pl.lit(L_NULL); return; }
-    if (c0 != '{') { pend(AIGW_R_E500_ARGS); pl.lit(L_NULL); return; }  // not a map: "failed to unmarshal tool call arguments"
-    emit_any(a, pl, 0);
-  }
-
-  // ---- Bedrock assistant content blocks (openai_awsbedrock.go:309-419)
-  __device__ void bedrock_asst_part(int e, bool& first) {
-    if (!is_obj(e)) { decline(is_null(e) ? AIGW_R_CONTENT : AIGW_R_E400_CONTENT); return; }
-    Part p; if (!scan_part(e, p)) return;
-    if ((p.type >= 0 && !is_str(p.type)) || (p.text >= 0 && !is_str(p.text)) || (p.refusal >= 0 && !is_str(p.refusal)) || (p.signature >= 0 && !is_str(p.signature))) { decline(AIGW_R_E400_TYPE); return; }
-    if (p.redacted >= 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-    const bool cache = cache_enabled(p.cache);
-    if (bad()) return;
-    if (p.type < 0) return;  // type "" matches no case
-    bool emitted = false;
-    const uint32_t ty = d.id(p.type);
-    if (ty == V_text) { if (p.text >= 0) { if (!first) pl.lit(L_COMMA); first = false; pl.lit(L_TEXT_OPEN); emit_str(p.text); pl.lit(L_RBRACE); emitted = true; } }
-    else if (ty == V_refusal) { if (p.refusal >= 0) { if (!first) pl.lit(L_COMMA); first = false; pl.lit(L_TEXT_OPEN); emit_str(p.refusal); pl.lit(L_RBRACE); emitted = true; } }
-    else if (ty == V_thinking) {
-      if (p.text >= 0) {
-        if (!first) pl.lit(L_COMMA); first = false;
-        pl.lit(L_REASON_OPEN); emit_str(p.text);
-        if (p.signature >= 0 && d.str_len(p.signature) > 0) { pl.lit(L_REASON_SIG); emit_str(p.signature); }
-        pl.lit(L_REASON_CLOSE); emitted = true;
-      }
-    }
-    if (emitted && cache) { pl.lit(L_COMMA); pl.lit(L_CACHEPOINT); }
-  }
-
-  __device__ void bedrock_assistant(const Msg& g) {
-    pl.lit(L_MSG_CONTENT_OPEN);
-    bool first = true;
-    const int c = g.content;
-    if (c >= 0 && !is_null(c)) {
-      if (is_str(c)) { if (d.str_len(c) > 0) { pl.lit(L_TEXT_OPEN); emit_str(c); pl.lit(L_RBRACE); first = false; } }
-      else if (is_arr(c)) { for (int e = c + 1; d.ty(e) != ']'; e = d.after(e)) { bedrock_asst_part(e, first); if (bad()) return; } }
-      else if (is_obj(c)) bedrock_asst_part(c, first);
-      else { decline(AIGW_R_E400_CONTENT); return; }
-    }
-    if (g.audio >= 0 && !is_null(g.audio)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-    if (g.name >= 0 && !is_null(g.name) && !is_str(g.name)) { decline(AIGW_R_E400_TYPE); return; }
-    if (g.refusal >= 0 && !is_null(g.refusal) && !is_str(g.refusal)) { decline(AIGW_R_E400_TYPE); return; }
-    const int tcs = g.tool_calls;
-    if (tcs >= 0 && !is_null(tcs)) {
-      if (!is_arr(tcs)) { decline(AIGW_R_E400_TYPE); return; }
-      for (int e = tcs + 1; d.ty(e) != ']'; e = d.after(e)) {
-        if (!is_obj(e)) { decline(is_null(e) ? AIGW_R_TOOL : AIGW_R_E400_TYPE); return; }
-        const int id = find(e, K_id), fn = find(e, K_function), ty = find(e, K_type);
-        (void)cache_enabled(find(e, K_cache_control));
-        if (bad()) return;
-        if (id < 0) { decline(AIGW_R_TOOL); return; }  // nil id panics in the reference
-        if (!is_str(id)) { decline(AIGW_R_E400_TYPE); return; }
-        if (ty >= 0 && !is_str(ty)) { decline(AIGW_R_E400_TYPE); return; }
-        int name = -1, args = -1;
-        if (fn >= 0) { if (!is_obj(fn)) { decline(AIGW_R_E400_TYPE); return; } name = find(fn, K_name); args = find(fn, K_arguments); }
-        if (bad()) return;
-        if ((name >= 0 && !is_str(name)) || (args >= 0 && !is_str(args))) { decline(AIGW_R_E400_TYPE); return; }
-        if (args < 0) pend(AIGW_R_E500_ARGS);  // "" fails to unmarshal in the reference
-        if (!first) pl.lit(L_COMMA); first = false;
-        pl.lit(L_TOOLUSE_OPEN);
-        if (name >= 0) emit_str(name); else pl.lit(L_EMPTY_STR);
-        pl.lit(L_TOOLUSE_INPUT);
-        if (args >= 0) emit_arguments(args); else pl.lit(L_NULL);
-        if (bad()) return;
-        pl.lit(L_TOOLUSE_ID); emit_str(id);
-        pl.lit(L_TOOLRESULT_CLOSE);
-      }
-    }
-    pl.lit(L_ASST_CLOSE);
-  }
-
-  __device__ void bedrock_user(const Msg& g) {
-    const int c = g.content;
-    if (g.name >= 0 && !is_null(g.name) && !is_str(g.name)) { decline(AIGW_R_E400_TYPE); return; }
-    if (c < 0) { pend(AIGW_R_E422_CONTENT); return; }  // absent ⇒ 422 "unexpected content type for user message"
-    if (is_null(c)) { pl.lit(L_MSG_TEXT_OPEN); pl.lit(L_EMPTY_STR); pl.lit(L_USER_CLOSE1); return; }
-    if (is_str(c)) { pl.lit(L_MSG_TEXT_OPEN); emit_str(c); pl.lit(L_USER_CLOSE1); return; }
-    if (!is_arr(c)) { decline(AIGW_R_E400_CONTENT); return; }
-    pl.lit(L_MSG_CONTENT_OPEN);
-    bool first = true;
-    for (int e = c + 1; d.ty(e) != ']'; e = d.after(e)) {
-      if (!is_obj(e)) { decline(AIGW_R_E400_CONTENT); return; }
-      Part p; if (!scan_part(e, p)) return;
-      if (p.type < 0 || !is_str(p.type)) { decline(AIGW_R_E400_CONTENT); return; }  // no type / unknown type
-      if (d.id(p.type) != V_text) {  // image_url / input_audio / file are valid but left to the stock path; anything else is unknown
-        const uint32_t tv = d.id(p.type);
-        decline((tv == V_image_url || tv == V_input_audio || tv == V_file || d.str_has_backslash(p.type)) ? AIGW_R_CONTENT : AIGW_R_E400_CONTENT); return;
-      }
-      if (p.text >= 0 && !is_str(p.text)) { decline(AIGW_R_E400_TYPE); return; }
-      const bool cache = cache_enabled(p.cache);
-      if (bad()) return;
-      if (!first) pl.lit(L_COMMA); first = false;
-      pl.lit(L_TEXT_OPEN); if (p.text >= 0) emit_str(p.text); else pl.lit(L_EMPTY_STR); pl.lit(L_RBRACE);
-      if (cache) { pl.lit(L_COMMA); pl.lit(L_CACHEPOINT); }
-    }
-    pl.lit(L_USER_CLOSE);
-  }
-
-  __device__ void bedrock_system(const Msg& g, bool& sys_first) {
-    const int c = g.content;
-    if (g.name >= 0 && !is_null(g.name) && !is_str(g.name)) { decline(AIGW_R_E400_TYPE); return; }
-    if (c < 0) { pend(AIGW_R_E422_CONTENT); return; }
-    if (is_str(c)) { if (!sys_first) pl.lit(L_COMMA, true); sys_first = false; pl.lit(L_TEXT_OPEN, true); emit_str(c, true); pl.lit(L_RBRACE, true); }
-    else if (is_arr(c)) emit_text_parts(c, true, true, sys_first);
-    else decline(AIGW_R_E400_CONTENT);
-  }
-
-  struct Top { int model, messages, temperature, top_p, max_tokens, mct, stop, stream, stream_options, tools, tool_choice, thinking, service_tier;
-               int model_raw, so_raw; /* value tokens even when null; -1 when the key is absent */
-               int reasoning_effort;
-               int n, seed, top_logprobs, logprobs, freq_pen, pres_pen; /* Gemini generation_config */ };
-
-  // top-level member scan with type checks for every known field (endpointspec.go:102-105)
-  __device__ bool scan_top(Top& t) {
-    t.model = t.messages = t.temperature = t.top_p = t.max_tokens = t.mct = t.stop = t.stream = t.stream_options = t.tools = t.tool_choice = t.thinking = t.service_tier = t.model_raw = t.so_raw = t.reasoning_effort = -1;
-    t.n = t.seed = t.top_logprobs = t.logprobs = t.freq_pen = t.pres_pen = -1;
-    if (d.nt == 0 || !is_obj(0)) { decline(d.nt && is_null(0) ? AIGW_R_ROOT : AIGW_R_E400_TYPE); return false; }
-    uint64_t seen = 0;
-    for (int k = 1; d.ty(k) != '}'; k = d.after(k + 3)) {
-      const int v = k + 3;
-      const uint32_t id = d.id(k);
-      if (id == K_NONE || id >= K_TOP_END) continue;
-      if (seen & (1ull << id)) { decline(AIGW_R_DUP_KEY); return false; }
-      seen |= 1ull << id;
-      if (id == K_model) t.model_raw = v; else if (id == K_stream_options) t.so_raw = v;
-      if (is_null(v)) continue;
-      switch (id) {
-        case K_model: t.model = v; break; case K_messages: t.messages = v; break; case K_max_tokens: t.max_tokens = v; break; case K_max_completion_tokens: t.mct = v; break;
-        case K_temperature: t.temperature = v; break; case K_top_p: t.top_p = v; break; case K_tools: t.tools = v; break; case K_tool_choice: t.tool_choice = v; break;
-        case K_thinking: t.thinking = v; break; case K_stop: t.stop = v; break; case K_stream: t.stream = v; break; case K_stream_options: t.stream_options = v; break;
-        case K_service_tier: t.service_tier = v; break;
-        case K_reasoning_effort: if (!check_scalar_type(v, 0)) return false; t.reasoning_effort = v; break;
-        case K_verbosity: case K_user: case K_guided_regex: if (!check_scalar_type(v, 0)) return false; break;
-        case K_logprobs: case K_parallel_tool_calls: if (!check_scalar_type(v, 1)) return false; if (id == K_logprobs) t.logprobs = v; break;
-        case K_top_logprobs: case K_seed: case K_n: if (!check_scalar_type(v, 2)) return false; if (id == K_n) t.n = v; else if (id == K_seed) t.seed = v; else t.top_logprobs = v; break;
-        case K_frequency_penalty: case K_presence_penalty: if (!check_scalar_type(v, 3)) return false; if (id == K_frequency_penalty) t.freq_pen = v; else t.pres_pen = v; break;
-        case K_guided_json: break;  // json.RawMessage: anything
-        default: decline(AIGW_R_UNSUPPORTED_FIELD); return false;  // modalities, audio, prediction, response_format, logit_bias, …: stock path
-      }
-    }
-    if (t.model >= 0 && (!is_str(t.model) || d.str_has_backslash(t.model))) { decline(is_str(t.model) ? AIGW_R_ESCAPE : AIGW_R_E400_TYPE); return false; }
-    if (t.messages >= 0 && !is_arr(t.messages)) { decline(AIGW_R_E400_TYPE); return false; }
-    if (t.stream >= 0 && !is_bool(t.stream)) { decline(AIGW_R_E400_TYPE); return false; }
-    if (t.service_tier >= 0 && !is_str(t.service_tier)) { decline(AIGW_R_E400_TYPE); return false; }
-    if (t.tools >= 0 && !is_arr(t.tools)) { decline(AIGW_R_E400_TYPE); return false; }
-    if (t.stream_options >= 0) {
-      if (!is_obj(t.stream_options)) { decline(AIGW_R_E400_TYPE); return false; }
-      const int iu = find(t.stream_options, K_include_usage);
-      if (iu >= 0 && !is_bool(iu)) { decline(AIGW_R_E400_TYPE); return false; }
-    }
-    if (t.temperature >= 0 && !is_num(t.temperature)) { decline(AIGW_R_E400_TYPE); return false; }
-    if (t.top_p >= 0 && !is_num(t.top_p)) { decline(AIGW_R_E400_TYPE); return false; }
-    if (t.max_tokens >= 0 && !check_scalar_type(t.max_tokens, 2)) return false;
-    if (t.mct >= 0 && !check_scalar_type(t.mct, 2)) return false;
-    return !bad();
-  }
-
-  __device__ bool model_contains(int mv, const char* needle, uint32_t n) {
-    if (mv < 0) return false;
-    const uint8_t* p = d.s + d.str_off(mv); const uint32_t L = d.str_len(mv);
-    for (uint32_t i = 0; i + n <= L; i++) { uint32_t k = 0; while (k < n && p[i + k] == (uint8_t)needle[k]) k++; if (k == n) return true; }
-    return false;
-  }
-
-  // ":path" = /model/{url.PathEscape(model)}/converse[-stream]  (openai_awsbedrock.go:94-109,155)
-  __device__ void emit_bedrock_path(const Top& t, bool stream) {
-    pl.lit(L_PATH_MODEL);
-    const uint8_t* mp; uint32_t ml;
-    if (P->override_len) { mp = (const uint8_t*)P->override_model; ml = P->override_len; }
-    else if (t.model >= 0) { mp = d.s + d.str_off(t.model); ml = d.str_len(t.model); }
-    else { mp = nullptr; ml = 0; }
-    bool clean = true;
-    for (uint32_t i = 0; i < ml; i++) {
-      const uint32_t c = mp[i];
-      const bool keep = (c - 'a' < 26u) || (c - 'A' < 26u) || (c - '0' < 10u) || c == '-' || c == '_' || c == '.' || c == '~' || c == '$' || c == '&' || c == '+' || c == ':' || c == '=' || c == '@';
-      if (!keep) { clean = false; break; }
-    }
-    if (clean && !P->override_len) { if (ml) pl.src(d, d.str_off(t.model), ml); }
-    else {
-      if (sc.n + 3 * ml + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
-      uint8_t* o = sc.p + sc.n; uint32_t w = 0;
-      for (uint32_t i = 0; i < ml; i++) {
-        const uint32_t c = mp[i];
-        const bool keep = (c - 'a' < 26u) || (c - 'A' < 26u) || (c - '0' < 10u) || c == '-' || c == '_' || c == '.' || c == '~' || c == '$' || c == '&' || c == '+' || c == ':' || c == '=' || c == '@';
-        if (keep) o[w++] = (uint8_t)c;
-        else { const char* hx = "0123456789ABCDEF"; o[w++] = '%'; o[w++] = hx[c >> 4]; o[w++] = hx[c & 15]; }
-      }
-      pl.push(2, sc.n, w); sc.n += (w + 1u) & ~1u;
-    }
-    pl.lit(L_PATH_CONVERSE);
-    if (stream) pl.lit(L_PATH_STREAM);
-  }
-
-  // ---- OpenAI → AWS Bedrock Converse (openai_awsbedrock.go:91-159)
-  __device__ void plan_bedrock(const Top& t, bool stream, uint32_t& path_len) {
-    emit_bedrock_path(t, stream);
-    path_len = pl.olen;
-    if (bad()) return;
-    pl.lit(L_LBRACE);
-    if (t.thinking >= 0) {  // openai.go:911-945, openai_awsbedrock.go:57-78
-      const int th = t.thinking;
-      if (!is_obj(th)) { decline(AIGW_R_E400_TYPE); return; }
-      const int ty = find(th, K_type);
-      if (ty < 0 || !is_str(ty)) { decline(AIGW_R_E400_TYPE); return; }
-      const uint32_t tv = d.id(ty);
-      if (tv == V_enabled) {
-        const int bt = find(th, K_budget_tokens), it = find(th, K_includeThoughts);
-        if (it >= 0 && !is_bool(it)) { decline(AIGW_R_E400_TYPE); return; }
-        pl.lit(L_ADDL_EN_PRE);
-        if (bt >= 0) emit_num_field(bt, true); else pl.lit(L_ZERO);
-        pl.lit(L_ADDL_EN_POST);
-      } else if (tv == V_disabled) pl.lit(L_ADDL_DIS);
-      else if (tv == V_adaptive) {}
-      else { decline(AIGW_R_E400_TYPE); return; }
-      if (bad()) return;
-    }
-    pl.lit(L_INF_OPEN);
-    bool f = true;
-    const int mt = t.mct >= 0 ? t.mct : t.max_tokens;  // cmp.Or(MaxCompletionTokens, MaxTokens)
-    if (mt >= 0) { pl.lit(L_MAXTOK); emit_num_field(mt, true); f = false; }
-    if (t.stop >= 0) {
-      const int s = t.stop;
-      if (is_str(s)) { if (!f) pl.lit(L_COMMA); f = false; pl.lit(L_STOPSEQ); emit_str(s); pl.lit(L_RBRACK); }
-      else if (is_arr(s)) {
-        if (d.ty(s + 1) != ']') {
-          if (!f) pl.lit(L_COMMA); f = false; pl.lit(L_STOPSEQ);
-          bool sf = true;
-          for (int e = s + 1; d.ty(e) != ']'; e = d.after(e)) { if (!is_str(e)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; } if (!sf) pl.lit(L_COMMA); sf = false; emit_str(e); }
-          pl.lit(L_RBRACK);
-        }
-      } else { decline(AIGW_R_UNSUPPORTED_FIELD); return; }  // stop of another type: openai-go union behaviour is not pinned
-    }
-    if (t.temperature >= 0) { if (!f) pl.lit(L_COMMA); f = false; pl.lit(L_TEMP); emit_num_field(t.temperature, false); }
-    if (t.top_p >= 0) { if (!f) pl.lit(L_COMMA); f = false; pl.lit(L_TOPP); emit_num_field(t.top_p, false); }
-    pl.lit(L_INF_CLOSE_MSGS);
-    if (bad()) return;
-    // messages (openai_awsbedrock.go:489-585)
-    bool mfirst = true, sys_first = true;
-    if (t.messages >= 0) {
-      int e = t.messages + 1;
-      while (d.ty(e) != ']') {
-        Msg g; const int role = scan_message(e, g);
-        if (bad()) return;
-        int nx = d.after(e);
-        if (role == 2 || role == 3) { bedrock_system(g, sys_first); e = nx; if (bad()) return; continue; }
-        if (!mfirst) pl.lit(L_COMMA); mfirst = false;
-        if (role == 0) bedrock_user(g);
-        else if (role == 1) bedrock_assistant(g);
-        else {
-          pl.lit(L_MSG_CONTENT_OPEN);
-          bedrock_tool_result(g);
-          if (bad()) return;
-          while (d.ty(nx) != ']') {  // coalesce the following tool messages (openai_awsbedrock.go:559-575)
-            Msg g2; const int r2 = scan_message(nx, g2);
-            if (bad()) return;
-            if (r2 != 4) break;
-            pl.lit(L_COMMA); bedrock_tool_result(g2);
-            if (bad()) return;
-            nx = d.after(nx);
-          }
-          pl.lit(L_USER_CLOSE);
-        }
-        if (bad()) return;
-        e = nx;
-      }
-    }
-    pl.lit(L_RBRACK);
-    if (pl.nsys) { pl.lit(L_SYSTEM_OPEN); pl.flush_sys(); pl.lit(L_RBRACK); }
-    if (t.service_tier >= 0 && d.str_len(t.service_tier) > 0) { pl.lit(L_SERVICE_TIER); emit_str(t.service_tier); pl.lit(L_RBRACE); }
-    // tool_choice decodes (and can fail) whether or not tools are present (openai.go:1194-1210)
-    int tc_kind = 0, tc_name = -1;  // 1 auto, 2 any, 3 tool{name}
-    if (t.tool_choice >= 0) {
-      const int tc = t.tool_choice;
-      if (is_str(tc)) {
-        const uint32_t tv = d.id(tc);
-        if (tv == V_auto) tc_kind = 1;
-        else if (tv == V_required) tc_kind = 2;
-        else if (model_contains(t.model, "anthropic", 9) && model_contains(t.model, "claude", 6)) { tc_kind = 3; tc_name = tc; }
-      } else if (is_obj(tc)) {
-        const int ty = find(tc, K_type), fn = find(tc, K_function);
-        if (ty >= 0 && !is_str(ty)) { decline(AIGW_R_E400_TYPE); return; }
-        if (fn >= 0) { if (!is_obj(fn)) { decline(AIGW_R_E400_TYPE); return; } tc_name = find(fn, K_name); if (tc_name >= 0 && !is_str(tc_name)) { decline(AIGW_R_E400_TYPE); return; } }
-        if (bad()) return;
-        tc_kind = 3;
-      } else { decline(AIGW_R_E400_TYPE); return; }
-    }
-    // tools (openai_awsbedrock.go:162-226)
-    if (t.tools >= 0 && d.ty(t.tools + 1) != ']') {
-      pl.lit(L_TOOLCFG_OPEN);
-      if (tc_kind == 1) pl.lit(L_TOOLCHOICE_AUTO);
-      else if (tc_kind == 2) pl.lit(L_TOOLCHOICE_ANY);
-      else if (tc_kind == 3) { pl.lit(L_TOOLCHOICE_TOOL); if (tc_name >= 0) emit_str(tc_name); else pl.lit(L_EMPTY_STR); pl.lit(L_TOOLCHOICE_TOOL_END); }
-      pl.lit(L_TOOLS_OPEN);
-      bool tf = true;
-      for (int e = t.tools + 1; d.ty(e) != ']'; e = d.after(e)) {
-        if (!is_obj(e)) { decline(is_null(e) ? AIGW_R_TOOL : AIGW_R_E400_TYPE); return; }
-        const int ty = find(e, K_type), fn = find(e, K_function), gs = find(e, K_google_search);
-        if (ty >= 0 && !is_str(ty)) { decline(AIGW_R_E400_TYPE); return; }
-        if (gs >= 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-        if (bad()) return;
-        if (fn >= 0) {
-          if (!is_obj(fn)) { decline(AIGW_R_E400_TYPE); return; }
-          const int nm = find(fn, K_name), ds = find(fn, K_description), st = find(fn, K_strict), pr = find(fn, K_parameters);
-          const bool cache = cache_enabled(find(fn, K_cache_control));
-          if (bad()) return;
-          if ((nm >= 0 && !is_str(nm)) || (ds >= 0 && !is_str(ds)) || (st >= 0 && !is_bool(st))) { decline(AIGW_R_E400_TYPE); return; }
-          if (!tf) pl.lit(L_COMMA); tf = false;
-          pl.lit(L_TOOLSPEC_OPEN);
-          if (ds >= 0 && d.str_len(ds) > 0) { pl.lit(L_DESC); emit_str(ds); pl.lit(L_COMMA); }
-          pl.lit(L_INPUTSCHEMA);
-          if (pr >= 0) emit_any(d, pl, pr); else pl.lit(L_NULL);
-          if (bad()) return;
-          pl.lit(L_NAME); if (nm >= 0) emit_str(nm); else pl.lit(L_EMPTY_STR); pl.lit(L_RBRACE);
-          if (cache) pl.lit(L_TOOL_CACHE);
-          pl.lit(L_RBRACE);
-        }
-      }
-      pl.lit(L_TOOLS_CLOSE);
-    }
-    pl.lit(L_RBRACE);
-  }
-
-  // ---- OpenAI → OpenAI passthrough (openai_openai.go:55-84) on top of ParseBody's forced include_usage
-  // (endpointspec.go:107-123).  Edits follow tidwall/sjson `set`: an existing value is spliced in place, a missing key is
-  // appended before the closing brace of the deepest existing object, and a rebuilt root loses the bytes outside its braces.
-  __device__ void plan_passthrough(const Top& t, bool stream, uint32_t& path_len, uint32_t& out_flags, uint32_t& body_kind) {
-    // validation = the Bedrock walk with the plan in dry mode (its accept set ⊆ ParseBody's)
-    { uint32_t pl0 = 0; pl.dry = true; plan_bedrock(t, stream, pl0); pl.dry = false; pl.nsys = 0; sc.n = 0; }
-    if (bad()) return;
-    if (pending) { decline(AIGW_R_CONTENT); return; }  // 422 / internal errors belong to the Bedrock translator; here the body is merely outside the fast path
-    // ":path" = path.Join("/", prefix, "chat/completions")
-    {
-      const uint32_t n = P->prefix_len;
-      if (sc.n + n + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
-      for (uint32_t i = 0; i < n; i++) sc.p[sc.n + i] = (uint8_t)P->openai_path[i];
-      pl.push(2, sc.n, n); sc.n += (n + 1u) & ~1u;
-    }
-    path_len = pl.olen;
-    // which edits?
-    bool inc_true = false; int iu_raw = -1;
-    if (t.stream_options >= 0) {
-      for (int m = t.stream_options + 1; d.ty(m) != '}'; m = d.after(m + 3)) if (d.id(m) == K_include_usage) { iu_raw = m + 3; break; }
-      inc_true = iu_raw >= 0 && d.ty(iu_raw) == 't';
-    }
-    const bool need_usage = stream && P->cost_configured && !inc_true;
-    const bool need_model = P->override_len != 0;
-    if (need_model) for (uint32_t i = 0; i < P->override_len; i++) { const uint32_t c = (uint8_t)P->override_model[i]; if (c < 0x20 || c > 0x7f || c == '"' || c == '\\') { decline(AIGW_R_UNSUPPORTED_FIELD); return; } }
-    if (need_usage) out_flags |= 2u;
-    if (!need_usage && !need_model) {
-      if (P->force_mutation) { pl.src(d, 0, d.len); body_kind = AIGW_BODY_BYTES; } else body_kind = AIGW_BODY_UNCHANGED;
-      return;
-    }
-    body_kind = AIGW_BODY_BYTES;
-    const int root_close = d.jmp[0];
-    const bool root_empty = root_close == 1;
-    // edit A (usage) and edit B (model): [a_b, a_e) replaced or insertion at a_b == a_e
-    uint32_t a_b = 0xffffffffu, a_e = 0; int a_kind = 0;  // 1 replace with true, 2 append member in stream_options, 3 replace with object, 4 append at root
-    bool a_comma = false;
-    if (need_usage) {
-      if (iu_raw >= 0) { a_kind = 1; a_b = d.tok(iu_raw); a_e = d.scalar_end(iu_raw); }
-      else if (t.stream_options >= 0) { a_kind = 2; const int cl = d.jmp[t.stream_options]; a_b = a_e = d.tok(cl); a_comma = cl != t.stream_options + 1; }
-      else if (t.so_raw >= 0) { a_kind = 3; a_b = d.tok(t.so_raw); a_e = d.scalar_end(t.so_raw); }
-      else { a_kind = 4; a_b = a_e = d.tok(root_close); a_comma = !root_empty; }
-    }
-    uint32_t b_b = 0xffffffffu, b_e = 0; int b_kind = 0;  // 1 replace value, 2 append at root
-    if (need_model) {
-      if (t.model_raw >= 0) { b_kind = 1; b_b = d.tok(t.model_raw); b_e = is_str(t.model_raw) ? d.tok(t.model_raw + 1) + 1u : d.scalar_end(t.model_raw); }
-      else { b_kind = 2; b_b = b_e = d.tok(root_close); }
-    }
-    const bool drop_outside = a_kind == 4 || b_kind == 2;
-    uint32_t cur = drop_outside ? d.tok(0) : 0u;
-    const uint32_t end = drop_outside ? d.tok(root_close) + 1u : d.len;
-    // override literal into scratch
-    uint32_t ov_off = 0;
-    if (need_model) {
-      const uint32_t n = P->override_len;
-      if (sc.n + n + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
-      ov_off = sc.n; for (uint32_t i = 0; i < n; i++) sc.p[sc.n + i] = (uint8_t)P->override_model[i];
-      sc.n += (n + 1u) & ~1u;
-    }
-    for (int pass = 0; pass < 2; pass++) {
-      // the earlier edit first; at equal positions (both root appends) usage goes first, as in the reference's call order
-      const bool do_a = pass == 0 ? (a_kind && (!b_kind || a_b <= b_b)) : (a_kind && b_kind && a_b > b_b);
-      const bool do_b = pass == 0 ? (b_kind && !do_a) : (b_kind && a_kind && a_b <= b_b);
-      if (do_a) {
-        pl.src(d, cur, a_b - cur); cur = a_e;
-        if (a_kind == 1) pl.lit(L_TRUE);
-        else if (a_kind == 2) { if (a_comma) pl.lit(L_COMMA); pl.lit(L_INCLUDE_USAGE_MEMBER); }
-        else if (a_kind == 3) pl.lit(L_INCLUDE_USAGE_OBJ);
-        else { if (a_comma) pl.lit(L_COMMA); pl.lit(L_STREAMOPT_APPEND); }
-      } else if (do_b) {
-        pl.src(d, cur, b_b - cur); cur = b_e;
-        if (b_kind == 2) { if (!root_empty || a_kind == 4) pl.lit(L_COMMA); pl.lit(L_MODEL_MEMBER); }
-        pl.lit(L_QUOTE); pl.push(2, ov_off, P->override_len); pl.lit(L_QUOTE);
-      }
-    }
-    pl.src(d, cur, end - cur);
-  }
-
-  // ---- OpenAI → Azure OpenAI (openai_azureopenai.go:37-62): the body is never rewritten; ":path" carries the deployment
-  // (= request model or the override, NOT path-escaped) and the api-version.
-  __device__ void plan_azure(const Top& t, bool stream, uint32_t& path_len, uint32_t& out_flags, uint32_t& body_kind) {
-    { uint32_t pl0 = 0; pl.dry = true; plan_bedrock(t, stream, pl0); pl.dry = false; pl.nsys = 0; sc.n = 0; }
-    if (bad()) return;
-    if (pending) { decline(AIGW_R_CONTENT); return; }
-    if (stream && P->cost_configured) {  // ParseBody's forced include_usage still marks the request (endpointspec.go:107-123)
-      int iu = -1;
-      if (t.stream_options >= 0) iu = find(t.stream_options, K_include_usage);
-      if (!(iu >= 0 && d.ty(iu) == 't')) out_flags |= 2u;
-    }
-    pl.lit(L_AZURE_PREFIX);
-    if (P->override_len) {
-      const uint32_t n = P->override_len;
-      if (sc.n + n + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
-      for (uint32_t i = 0; i < n; i++) sc.p[sc.n + i] = (uint8_t)P->override_model[i];
-      pl.push(2, sc.n, n); sc.n += (n + 1u) & ~1u;
-    } else if (t.model >= 0) pl.src(d, d.str_off(t.model), d.str_len(t.model));
-    pl.lit(L_AZURE_SUFFIX);
-    {
-      const uint32_t n = P->version_len;
-      if (sc.n + n + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
-      for (uint32_t i = 0; i < n; i++) sc.p[sc.n + i] = (uint8_t)P->api_version[i];
-      pl.push(2, sc.n, n); sc.n += (n + 1u) & ~1u;
-    }
-    path_len = pl.olen;
-    body_kind = AIGW_BODY_UNCHANGED;
-  }
-
-  // raw model bytes (override or request model) appended as-is (GCP paths) or url.PathEscape'd (AWS paths)
-  __device__ void emit_model(const Top& t, bool escape) {
-    const uint8_t* mp; uint32_t ml;
-    if (P->override_len) { mp = (const uint8_t*)P->override_model; ml = P->override_len; }
-    else if (t.model >= 0) { mp = d.s + d.str_off(t.model); ml = d.str_len(t.model); }
-    else return;
-    if (sc.n + 3 * ml + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
-    uint8_t* o = sc.p + sc.n; uint32_t w = 0;
-    for (uint32_t i = 0; i < ml; i++) {
-      const uint32_t c = mp[i];
-      const bool keep = !escape || (c - 'a' < 26u) || (c - 'A' < 26u) || (c - '0' < 10u) || c == '-' || c == '_' || c == '.' || c == '~' || c == '$' || c == '&' || c == '+' || c == ':' || c == '=' || c == '@';
-      if (keep) o[w++] = (uint8_t)c;
-      else { const char* hx = "0123456789ABCDEF"; o[w++] = '%'; o[w++] = hx[c >> 4]; o[w++] = hx[c & 15]; }
-    }
-    pl.push(2, sc.n, w); sc.n += (w + 1u) & ~1u;
-  }
-
-  // {"text":S[,"cache_control":{"type":"ephemeral"}],"type":"text"}; empty text has no pinned layout ⇒ decline
-  __device__ void an_text_block(int str_tok, bool cache, bool sys) {
-    if (d.str_len(str_tok) == 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-    pl.lit(L_TEXT_OPEN, sys); emit_str(str_tok, sys); pl.lit(cache ? L_AN_TEXT_CACHE_CLOSE : L_AN_TEXT_CLOSE, sys);
-  }
-  __device__ bool cache_simple(int cc) {  // cache_control limited to {"type":…}: a ttl has no pinned position
-    if (cc < 0) return false;
-    for (int m = cc + 1; d.ty(m) != '}'; m = d.after(m + 3)) if (d.id(m) == K_ttl && !is_null(m + 3)) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
-    return cache_enabled(cc);
-  }
-  // is_error of a tool result: the content string decodes to a JSON object that has an "error" key (anthropic_helper.go:531-539)
-  __device__ bool an_is_error(int v) {
-    if (d.str_nc(v)) { decline(AIGW_R_ESCAPE); return false; }
-    const uint32_t off = d.str_off(v), n = d.str_len(v);
-    const uint8_t* p = d.s + off;
-    uint32_t k = 0; while (k < n && (p[k] == ' ')) k++;
-    if (k >= n || (p[k] != '{' && p[k] != '\\')) return false;  // cannot be an object
-    if (sc.n + n + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return false; }
-    uint8_t* dst = sc.p + sc.n; uint32_t w = 0;
-    for (uint32_t i = 0; i < n; i++) { uint32_t c = p[i]; if (c == '\\') { const uint32_t e = p[++i]; c = e == 'n' ? '\n' : e == 'r' ? '\r' : e == 't' ? '\t' : e; } dst[w++] = (uint8_t)c; }
-    const uint32_t base = sc.n;  // scratch is only borrowed: nothing emitted references it
-    const int nt = tokenize_seq(dst, w, base, tw_tail, tail_cap);
-    if (nt == 0 || nt == -AIGW_R_SYNTAX) return false;
-    if (nt < 0) { decline(-nt); return false; }
-    Doc a; a.s = sc.p; a.len = base + w; a.tw = tw_tail; a.jmp = jmp_tail; a.nt = nt; a.kind = 2;
-    const int vr = validate_tokens(a);
-    if (vr == AIGW_R_SYNTAX) return false;
-    if (vr) { decline(vr); return false; }
-    if (a.ty(0) != '{') return false;
-    for (int m = 1; a.ty(m) != '}'; m = a.after(m + 3)) {
-      if (a.str_has_backslash(m)) { decline(AIGW_R_ESCAPE); return false; }
-      if (a.str_len(m) == 5) { const uint8_t* q = a.s + a.str_off(m); if (q[0] == 'e' && q[1] == 'r' && q[2] == 'r' && q[3] == 'o' && q[4] == 'r') return true; }
-    }
-    return false;
-  }
-
-  // ---- OpenAI → GCP Vertex AI Gemini (openai_gcpvertexai.go:93-126,512-580; gemini_helper.go:52-122,144-339,401-474,609-734).
-  // The layout the reference's goldens pin (testupstream_test.go:313,327,341,510) plus generation_config in genai's field order;
-  // FunctionCall / FunctionResponse parts, media parts, tool_choice, thinking and schemas beyond the restated subset are declined.
-  __device__ bool rm_contains(const Top& t, const char* needle, uint32_t n) {
-    if (!P->override_len) return model_contains(t.model, needle, n);
-    const char* p = P->override_model; const uint32_t L = P->override_len;
-    for (uint32_t i = 0; i + n <= L; i++) { uint32_t k = 0; while (k < n && p[i + k] == needle[k]) k++; if (k == n) return true; }
-    return false;
-  }
-  // float32 field: the literal is echoed when it has at most 6 significant digits (then float32 → shortest decimal gives it back)
-  __device__ void emit_f32_field(int v) {
-    const uint32_t e = d.scalar_end(v), o = d.tok(v);
-    const uint32_t l = canon_number(d.s + o, e - o, false);
-    if (!l) { decline(AIGW_R_NUMBER); return; }
-    uint32_t sig = 0; bool lead = true;
-    for (uint32_t i = o; i < o + l; i++) { const uint32_t c = d.s[i]; if (c - '0' < 10u) { if (c != '0') lead = false; if (!lead) sig++; } }
-    if (sig > 6) { decline(AIGW_R_NUMBER); return; }
-    pl.src(d, o, l);
-  }
-  // int32 field; zero = true when the value is 0 (omitempty fields)
-  __device__ bool emit_i32_field(int v, bool& zero, bool dry_only) {
-    const uint32_t e = d.scalar_end(v), o = d.tok(v);
-    const uint32_t l = canon_number(d.s + o, e - o, true);
-    if (!l || l > 9u + (d.s[o] == '-' ? 1u : 0u)) { decline(AIGW_R_NUMBER); return false; }
-    zero = (l == 1 && d.s[o] == '0');
-    if (!dry_only && !zero) pl.src(d, o, l);
-    return true;
-  }
-  // JSON schema subset whose conversion is a sorted re-marshal: {type, description: string; properties: {name: schema}; items: schema; required, enum: [string]}
-  __device__ bool gem_schema_ok(int root) {
-    int stack[24]; int sp = 0; stack[sp++] = root;
-    int guard = 0;
-    while (sp) {
-      const int o = stack[--sp];
-      if (!is_obj(o)) return false;
-      for (int m = o + 1; d.ty(m) != '}'; m = d.after(m + 3)) {
-        if (++guard > 512 || d.str_has_backslash(m)) return false;
-        const int v = m + 3;
-        if (str_eq_lit(m, "type", 4) || str_eq_lit(m, "description", 11)) { if (!is_str(v)) return false; }
-        else if (str_eq_lit(m, "properties", 10)) {
-          if (!is_obj(v)) return false;
-          for (int q = v + 1; d.ty(q) != '}'; q = d.after(q + 3)) { if (sp >= 24) return false; stack[sp++] = q + 3; }
-        } else if (str_eq_lit(m, "items", 5)) { if (sp >= 24) return false; stack[sp++] = v; }
-        else if (str_eq_lit(m, "required", 8) || str_eq_lit(m, "enum", 4)) { if (!is_arr(v)) return false; for (int q = v + 1; d.ty(q) != ']'; q = d.after(q)) if (!is_str(q)) return false; }
-        else return false;
-      }
-    }
-    return true;
-  }
-  __device__ void gem_text_part(int str_tok, bool& first, bool sys) {
-    if (!first) pl.lit(L_COMMA, sys); first = false;
-    pl.lit(L_TEXT_OPEN, sys); emit_str(str_tok, sys); pl.lit(L_RBRACE, sys);
-  }
-  __device__ void plan_gemini(const Top& t, bool stream, uint32_t& path_len) {
-    { uint32_t pl0 = 0; pl.dry = true; plan_bedrock(t, stream, pl0); pl.dry = false; pl.nsys = 0; sc.n = 0; }
-    if (bad()) return;
-    pending = 0;   // Bedrock's translator errors do not apply
-    if (t.tool_choice >= 0 || t.thinking >= 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-    if (t.reasoning_effort >= 0 && d.str_len(t.reasoning_effort) > 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-    // ":path"
-    pl.lit(L_EM_GOOGLE_PATH); emit_model(t, false); pl.lit(stream ? L_GEM_STREAM : L_GEM_GENERATE);
-    path_len = pl.olen;
-    if (bad()) return;
-    pl.lit(L_GEM_CONTENTS);
-    bool any_content = false, pending_open = false, pfirst = true, sys_first = true;
-    auto content_sep = [&] { if (!any_content) { pl.lit(L_LBRACK); any_content = true; } else pl.lit(L_COMMA); };
-    auto flush_user = [&] { if (pending_open) { pl.lit(L_USER_CLOSE); pending_open = false; pfirst = true; } };
-    if (t.messages >= 0) {
-      for (int e = t.messages + 1; d.ty(e) != ']'; e = d.after(e)) {
-        Msg g; const int role = scan_message(e, g);
-        if (bad()) return;
-        const int c = g.content;
-        if (role == 2 || role == 3) {
-          if (c < 0 || is_null(c)) { pend(AIGW_R_E422_CONTENT); continue; }
-          if (is_str(c)) { if (d.str_len(c) > 0) gem_text_part(c, sys_first, true); }
-          else { for (int q = c + 1; d.ty(q) != ']'; q = d.after(q)) { Part p; if (!scan_part(q, p)) return; if (p.text >= 0 && d.str_len(p.text) > 0) gem_text_part(p.text, sys_first, true); } }
-        } else if (role == 0) {
-          if (c < 0 || is_null(c)) { pend(AIGW_R_E422_CONTENT); continue; }
-          if (is_str(c)) { if (d.str_len(c) > 0) { if (!pending_open) { content_sep(); pl.lit(L_GEM_PARTS_OPEN); pending_open = true; } gem_text_part(c, pfirst, false); } }
-          else {
-            for (int q = c + 1; d.ty(q) != ']'; q = d.after(q)) {
-              Part p; if (!scan_part(q, p)) return;
-              if (p.text < 0 || d.str_len(p.text) == 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }   // Part{} layout: stock path
-              if (!pending_open) { content_sep(); pl.lit(L_GEM_PARTS_OPEN); pending_open = true; }
-              gem_text_part(p.text, pfirst, false);
-            }
-          }
-        } else if (role == 4) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }    // FunctionResponse part
-        else {
-          flush_user();
-          if (g.tool_calls >= 0 && !is_null(g.tool_calls) && d.ty(g.tool_calls + 1) != ']') { decline(AIGW_R_UNSUPPORTED_FIELD); return; }   // FunctionCall part
-          // does the message yield any part?
-          bool has_parts = false;
-          if (c >= 0 && !is_null(c)) {
-            if (is_str(c)) has_parts = d.str_len(c) > 0;
-            else if (is_arr(c)) {
-              for (int q = c + 1; d.ty(q) != ']'; q = d.after(q)) {
-                Part p; if (!scan_part(q, p)) return;
-                if (p.type < 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-                const uint32_t ty = d.id(p.type);
-                if (ty == V_text) { if (p.text >= 0 && d.str_len(p.text) > 0) has_parts = true; }
-                else if (ty != V_refusal) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }   // thought parts and unknown types
-              }
-            } else { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-          }
-          content_sep();
-          if (!has_parts) pl.lit(L_GEM_MODEL_EMPTY);
-          else {
-            pl.lit(L_GEM_PARTS_OPEN);
-            bool first = true;
-            if (is_str(c)) gem_text_part(c, first, false);
-            else for (int q = c + 1; d.ty(q) != ']'; q = d.after(q)) { Part p; if (!scan_part(q, p)) return; if (d.id(p.type) == V_text && p.text >= 0 && d.str_len(p.text) > 0) gem_text_part(p.text, first, false); }
-            pl.lit(L_GEM_MODEL_CLOSE);
-          }
-        }
-        if (bad()) return;
-      }
-    }
-    flush_user();
-    pl.lit(any_content ? L_RBRACK : L_NULL);
-    // tools
-    pl.lit(L_GEM_TOOLS);
-    bool any_decl = false;
-    if (t.tools >= 0) {
-      const bool json_schema = rm_contains(t, "gemini", 6) && (rm_contains(t, "2.5", 3) || rm_contains(t, "3", 1));
-      for (int e = t.tools + 1; d.ty(e) != ']'; e = d.after(e)) {
-        const int ty = find(e, K_type), fn = find(e, K_function);
-        if (bad()) return;
-        if (ty < 0 || !str_eq_lit(ty, "function", 8)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-        if (fn < 0) continue;
-        const int nm = find(fn, K_name), ds = find(fn, K_description), pr = find(fn, K_parameters);
-        if (bad()) return;
-        pl.lit(any_decl ? L_COMMA : L_GEM_DECLS_OPEN); any_decl = true;
-        pl.lit(L_LBRACE);
-        bool f = true;
-        if (ds >= 0 && d.str_len(ds) > 0) { pl.lit(L_DESC); emit_str(ds); f = false; }
-        if (nm >= 0 && d.str_len(nm) > 0) { if (!f) pl.lit(L_COMMA); pl.lit(L_GEM_NAME); emit_str(nm); f = false; }
-        if (pr >= 0) {
-          const bool empty_obj = is_obj(pr) && d.ty(pr + 1) == '}';
-          if (json_schema) { if (!empty_obj) { if (!f) pl.lit(L_COMMA); pl.lit(L_GEM_PARAMS_JS); emit_any(d, pl, pr); } }
-          else {
-            if (!is_obj(pr)) { pend(AIGW_R_E422_CONTENT); }
-            else if (!empty_obj) { if (!gem_schema_ok(pr)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; } if (!f) pl.lit(L_COMMA); pl.lit(L_GEM_PARAMS); emit_any(d, pl, pr); }
-          }
-          if (bad()) return;
-        }
-        pl.lit(L_RBRACE);
-      }
-    }
-    pl.lit(any_decl ? L_GEM_DECLS_CLOSE : L_NULL);
-    // generation_config, genai.GenerationConfig field order
-    pl.lit(L_GEM_GENCFG);
-    bool gf = true; bool zero = false;
-    auto sep = [&] { if (!gf) pl.lit(L_COMMA); gf = false; };
-    if (t.n >= 0) { if (!emit_i32_field(t.n, zero, true)) return; if (!zero) { sep(); pl.lit(L_GEM_CANDIDATES); emit_i32_field(t.n, zero, false); } }
-    if (t.freq_pen >= 0) { sep(); pl.lit(L_GEM_FREQ); emit_f32_field(t.freq_pen); }
-    if (t.top_logprobs >= 0) { if (!emit_i32_field(t.top_logprobs, zero, true)) return; sep(); pl.lit(L_GEM_LOGPROBS); if (zero) pl.lit(L_ZERO); else emit_i32_field(t.top_logprobs, zero, false); }
-    { const int mt = t.mct >= 0 ? t.mct : t.max_tokens; if (mt >= 0) { if (!emit_i32_field(mt, zero, true)) return; if (!zero) { sep(); pl.lit(L_GEM_MAXOUT); emit_i32_field(mt, zero, false); } } }
-    if (t.pres_pen >= 0) { sep(); pl.lit(L_GEM_PRES); emit_f32_field(t.pres_pen); }
-    if (t.logprobs >= 0 && d.ty(t.logprobs) == 't') { sep(); pl.lit(L_GEM_RESP_LOGPROBS); }
-    if (t.seed >= 0) { if (!emit_i32_field(t.seed, zero, true)) return; sep(); pl.lit(L_GEM_SEED); if (zero) pl.lit(L_ZERO); else emit_i32_field(t.seed, zero, false); }
-    if (t.stop >= 0) {
-      const int s = t.stop;
-      if (is_str(s)) { sep(); pl.lit(L_STOPSEQ); emit_str(s); pl.lit(L_RBRACK); }
-      else if (is_arr(s)) {
-        if (d.ty(s + 1) != ']') {
-          sep(); pl.lit(L_STOPSEQ);
-          bool sf = true;
-          for (int e = s + 1; d.ty(e) != ']'; e = d.after(e)) { if (!is_str(e)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; } if (!sf) pl.lit(L_COMMA); sf = false; emit_str(e); }
-          pl.lit(L_RBRACK);
-        }
-      } else { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-    }
-    if (t.temperature >= 0) { sep(); pl.lit(L_TEMP); emit_f32_field(t.temperature); }
-    if (t.top_p >= 0) { sep(); pl.lit(L_TOPP); emit_f32_field(t.top_p); }
-    pl.lit(L_RBRACE);
-    if (bad()) return;
-    if (pl.nsys) { pl.lit(L_GEM_SYS_OPEN); pl.flush_sys(); pl.lit(L_GEM_SYS_CLOSE); }
-    pl.lit(L_RBRACE);
-  }
-
-  // ---- OpenAI → Anthropic messages API behind GCP rawPredict / AWS InvokeModel (anthropic_helper.go:455-569,661-747;
-  // openai_gcpanthropic.go:56-100; openai_awsanthropic.go:54-100).  Only the layout the reference's goldens pin is
-  // produced (testupstream_test.go:203,216,291,355,369,549); fields whose position the SDK decides are declined.
-  __device__ void plan_anthropic(const Top& t, bool stream, bool gcp, uint32_t& path_len) {
-    { uint32_t pl0 = 0; pl.dry = true; plan_bedrock(t, stream, pl0); pl.dry = false; pl.nsys = 0; sc.n = 0; }
-    if (bad()) return;
-    pending = 0;  // Bedrock's translator errors do not apply; this translator's own are found below
-    if (t.temperature >= 0 || t.top_p >= 0 || t.stop >= 0 || t.thinking >= 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-    if (t.tools >= 0 && d.ty(t.tools + 1) != ']') { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-    if (t.reasoning_effort >= 0 && d.str_len(t.reasoning_effort) > 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-    // ":path"
-    if (gcp) { pl.lit(L_AN_GCP_PATH); emit_model(t, false); pl.lit(stream ? L_AN_STREAMRAWPREDICT : L_AN_RAWPREDICT); }
-    else { pl.lit(L_PATH_MODEL); emit_model(t, true); pl.lit(stream ? L_AN_INVOKE_STREAM : L_AN_INVOKE); }
-    path_len = pl.olen;
-    if (bad()) return;
-    pl.lit(L_AN_OPEN);
-    const int mt = t.mct >= 0 ? t.mct : t.max_tokens;
-    if (mt >= 0) emit_num_field(mt, true); else pl.lit(L_ZERO);
-    pl.lit(L_AN_MSGS);
-    bool mfirst = true, sys_first = true;
-    if (t.messages >= 0) {
-      int e = t.messages + 1;
-      while (d.ty(e) != ']') {
-        Msg g; const int role = scan_message(e, g);
-        if (bad()) return;
-        int nx = d.after(e);
-        if (role == 2 || role == 3) {  // one system block per message; text parts are concatenated into one string
-          const int c = g.content;
-          if (c < 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-          if (!sys_first) pl.lit(L_COMMA, true); sys_first = false;
-          if (is_str(c)) an_text_block(c, false, true);
-          else {
-            bool cache = false; uint32_t total = 0;
-            pl.lit(L_TEXT_OPEN, true); pl.lit(L_QUOTE, true);
-            for (int q = c + 1; d.ty(q) != ']'; q = d.after(q)) {
-              Part p; if (!scan_part(q, p)) return;
-              if (p.text >= 0) { if (d.str_nc(p.text)) { decline(AIGW_R_ESCAPE); return; } pl.src(d, d.str_off(p.text), d.str_len(p.text), true); total += d.str_len(p.text); }
-              if (cache_simple(p.cache)) cache = true;
-              if (bad()) return;
-            }
-            if (total == 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-            pl.lit(L_QUOTE, true); pl.lit(cache ? L_AN_TEXT_CACHE_CLOSE : L_AN_TEXT_CLOSE, true);
-          }
-          if (bad()) return;
-          e = nx; continue;
-        }
-        if (!mfirst) pl.lit(L_COMMA); mfirst = false;
-        pl.lit(L_MSG_CONTENT_OPEN);
-        if (role == 0) {
-          const int c = g.content;
-          if (c < 0) { pend(AIGW_R_E500_ARGS); }  // "unsupported OpenAI content type: <nil>"
-          else if (is_null(c)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-          else if (is_str(c)) an_text_block(c, false, false);
-          else {
-            if (d.ty(c + 1) == ']') { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-            bool first = true;
-            for (int q = c + 1; d.ty(q) != ']'; q = d.after(q)) {
-              Part p; if (!scan_part(q, p)) return;
-              if (p.text < 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-              const bool cache = cache_simple(p.cache);
-              if (bad()) return;
-              if (!first) pl.lit(L_COMMA); first = false;
-              an_text_block(p.text, cache, false);
-            }
-          }
-          if (bad()) return;
-          pl.lit(L_USER_CLOSE);
-        } else if (role == 1) {
-          bool first = true;
-          const int c = g.content;
-          if (c >= 0 && !is_null(c)) {
-            if (is_str(c)) { if (d.str_len(c) > 0) { an_text_block(c, false, false); first = false; } }
-            else {
-              const bool arr = is_arr(c);
-              for (int q = arr ? c + 1 : c; arr ? d.ty(q) != ']' : q == c; q = arr ? d.after(q) : -1) {
-                Part p; if (!scan_part(q, p)) return;
-                if (p.type < 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-                const uint32_t ty = d.id(p.type);
-                int src = -1; bool cache = false;
-                if (ty == V_text) { src = p.text; cache = cache_simple(p.cache); }
-                else if (ty == V_refusal) src = p.refusal;
-                else { decline(AIGW_R_UNSUPPORTED_FIELD); return; }  // thinking blocks, unknown types
-                if (bad()) return;
-                if (src >= 0) { if (!first) pl.lit(L_COMMA); first = false; an_text_block(src, cache, false); if (bad()) return; }
-                if (!arr) break;
-              }
-            }
-          }
-          const int tcs = g.tool_calls;
-          if (tcs >= 0 && !is_null(tcs)) {
-            for (int q = tcs + 1; d.ty(q) != ']'; q = d.after(q)) {
-              const int id = find(q, K_id), fn = find(q, K_function);
-              if (cache_enabled(find(q, K_cache_control))) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-              int name = -1, args = -1;
-              if (fn >= 0) { name = find(fn, K_name); args = find(fn, K_arguments); }
-              if (bad()) return;
-              if (id < 0) { decline(AIGW_R_TOOL); return; }
-              if (args < 0) pend(AIGW_R_E500_ARGS);
-              if (!first) pl.lit(L_COMMA); first = false;
-              pl.lit(L_AN_TOOLUSE_OPEN); emit_str(id); pl.lit(L_TOOLUSE_INPUT);
-              if (args >= 0) emit_arguments(args); else pl.lit(L_NULL);
-              if (bad()) return;
-              pl.lit(L_AN_NAME); if (name >= 0) emit_str(name); else pl.lit(L_EMPTY_STR);
-              pl.lit(L_AN_TOOLUSE_CLOSE);
-            }
-          }
-          if (first) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }  // empty content: layout not pinned
-          pl.lit(L_ASST_CLOSE);
-        } else {
-          bool tfirst = true;
-          for (;;) {  // consecutive tool messages aggregate into one user message
-            Msg g2; int r2 = 4;
-            if (!tfirst) { if (d.ty(nx) == ']') break; r2 = scan_message(nx, g2); if (bad()) return; if (r2 != 4) break; nx = d.after(nx); }
-            const Msg& tm = tfirst ? g : g2;
-            if (!tfirst) pl.lit(L_COMMA);
-            tfirst = false;
-            const int c = tm.content;
-            pl.lit(L_AN_TR_OPEN);
-            int id = tm.tool_call_id; if (id >= 0 && is_null(id)) id = -1;
-            if (id >= 0) emit_str(id); else pl.lit(L_EMPTY_STR);
-            if (c < 0) { pend(AIGW_R_E500_ARGS); pl.lit(L_AN_TR_ERR_F); }
-            else if (is_str(c)) {
-              const bool ie = an_is_error(c);
-              if (bad()) return;
-              pl.lit(ie ? L_AN_TR_ERR_T : L_AN_TR_ERR_F);
-              an_text_block(c, false, false);
-            } else {
-              pl.lit(L_AN_TR_ERR_F);
-              if (d.ty(c + 1) == ']') { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-              bool first = true;
-              for (int q = c + 1; d.ty(q) != ']'; q = d.after(q)) {
-                Part p; if (!scan_part(q, p)) return;
-                if (p.text < 0 || cache_enabled(p.cache)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-                if (!first) pl.lit(L_COMMA); first = false;
-                an_text_block(p.text, false, false);
-              }
-            }
-            if (bad()) return;
-            pl.lit(L_AN_TR_CLOSE);
-          }
-          pl.lit(L_USER_CLOSE);
-        }
-        if (bad()) return;
-        e = nx;
-      }
-    }
-    if (mfirst) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }  // no messages: layout not pinned
-    pl.lit(L_RBRACK);
-    if (pl.nsys) { pl.lit(L_SYSTEM_OPEN); pl.flush_sys(); pl.lit(L_RBRACK); }
-    if (gcp && stream) pl.lit(L_AN_STREAM);
-    pl.lit(L_AN_VERSION);
-    if (P->version_len) {
-      for (uint32_t i = 0; i < P->version_len; i++) { const uint32_t c = (uint8_t)P->api_version[i]; if (c < 0x20 || c > 0x7f || c == '"' || c == '\\') { decline(AIGW_R_UNSUPPORTED_FIELD); return; } }
-      if (sc.n + P->version_len + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
-      for (uint32_t i = 0; i < P->version_len; i++) sc.p[sc.n + i] = (uint8_t)P->api_version[i];
-      pl.push(2, sc.n, P->version_len); sc.n += (P->version_len + 1u) & ~1u;
-    } else pl.lit(gcp ? L_AN_VER_GCP : L_AN_VER_AWS);
-    pl.lit(L_AN_END);
-  }
-};
-
-// ---- K2: validate + schema walk, one thread per document
-__device__ void walk_one(const ChatParams& P, uint32_t doc0, const WorkPtrs& wp, const WorkLayout& C, uint32_t li) {
-  const uint32_t doc = P.doc_map ? P.doc_map[doc0 + li] : doc0 + li;
-  const uint32_t nt_word = wp.ntok[li];
-  PlanOut po; po.nops = 0; po.olen = 0; po.path_len = 0; po.model_off = 0; po.model_len = 0; po.flags = 0; po.reason = 0;
-  if (nt_word & 0x80000000u) { po.reason = (uint8_t)(nt_word & 0xff); wp.plan[li] = po; return; }
-  const uint32_t ntok = nt_word;
-  Walker W;
-  W.d.s = P.bodies + P.offsets[doc]; W.d.len = P.lens[doc];
-  W.d.tw = wp.tw + (size_t)li * C.kTok; W.d.jmp = wp.jmp + (size_t)li * C.kTok;
-  W.d.nt = (int)ntok; W.d.kind = 0;
-  W.pl.ops = wp.ops + (size_t)li * (C.kOps + kSysCap); W.pl.nops = 0; W.pl.nsys = 0; W.pl.cap = (int)C.kOps; W.pl.clen = 0; W.pl.ckind = 0; W.pl.coff = 0; W.pl.olen = 0; W.pl.err = 0; W.pl.dry = false;
-  W.sc.p = wp.scr + (size_t)li * C.kScr; W.sc.n = 0; W.sc.cap = C.kScr - 20u;
-  W.tw_tail = (uint32_t*)W.d.tw + ntok; W.jmp_tail = W.d.jmp + ntok; W.tail_cap = (int)C.kTok - (int)ntok;
-  W.P = &P; W.reason = 0; W.pending = 0;
-  int reason = validate_tokens(W.d);
-  if (reason == AIGW_R_SYNTAX) reason = AIGW_R_E400_SYNTAX;
-  uint32_t path_len = 0;
-  if ((P.schema & 48) == AIGW_SCHEMA_RESP_AWS_BEDROCK) {
-    // response direction: json.Decoder semantics differ from the request-side strictness (trailing bytes are fine, a syntax
-    // error is "failed to unmarshal body"), so anything the token grammar rejects goes to the stock path
-    if (reason) reason = AIGW_R_SYNTAX;
-    else {
-      if ((P.schema & 15) == AIGW_SCHEMA_GCP_ANTHROPIC) { uint32_t mo = 0, mlen = 0; W.plan_anthropic_response(path_len, mo, mlen); po.model_off = mo; po.model_len = (uint16_t)mlen; }
-      else W.plan_bedrock_response(path_len);
-      W.pl.flush();
-      reason = W.reason ? W.reason : W.pl.err;
-      if (!reason && W.pl.nops == 0) reason = AIGW_R_OPS;
-    }
-  } else if (P.schema & AIGW_SCHEMA_EMBEDDINGS) {
-    if (!reason) {
-      uint32_t mo = 0, mlen = 0, bk = AIGW_BODY_UNCHANGED;
-      W.plan_embeddings(path_len, mo, mlen, bk);
-      po.model_off = mo; po.model_len = (uint16_t)mlen; po.flags = bk == AIGW_BODY_UNCHANGED ? 0x80u : 0u;
-      W.pl.flush();
-      reason = W.reason ? W.reason : W.pl.err ? W.pl.err : W.pending;
-      if (!reason && W.pl.nops == 0) reason = AIGW_R_OPS;
-    }
-  } else if (!reason) {
-    Walker::Top t;
-    if (W.scan_top(t)) {
-      const bool stream = t.stream >= 0 && W.d.ty(t.stream) == 't';
-      if (t.model >= 0) { po.model_off = W.d.str_off(t.model); po.model_len = (uint16_t)W.d.str_len(t.model); }
-      po.flags = stream ? 1u : 0u;
-      if (P.schema == AIGW_SCHEMA_AWS_BEDROCK) W.plan_bedrock(t, stream, path_len);
-      else if (P.schema == AIGW_SCHEMA_OPENAI) { uint32_t fl = po.flags, bk = AIGW_BODY_BYTES; W.plan_passthrough(t, stream, path_len, fl, bk); po.flags = (uint8_t)(fl | (bk == AIGW_BODY_UNCHANGED ? 0x80u : 0u)); }
-      else if (P.schema == AIGW_SCHEMA_AZURE_OPENAI) { uint32_t fl = po.flags, bk = AIGW_BODY_UNCHANGED; W.plan_azure(t, stream, path_len, fl, bk); po.flags = (uint8_t)(fl | 0x80u); }
-      else if (P.schema == AIGW_SCHEMA_GCP_ANTHROPIC || P.schema == AIGW_SCHEMA_AWS_ANTHROPIC) W.plan_anthropic(t, stream, P.schema == AIGW_SCHEMA_GCP_ANTHROPIC, path_len);
-      else if (P.schema == AIGW_SCHEMA_GCP_VERTEX) W.plan_gemini(t, stream, path_len);
-      else W.decline(AIGW_R_SCHEMA);
-    }
-    W.pl.flush();
-    reason = W.reason ? W.reason : W.pl.err ? W.pl.err : W.pending;
-    if (!reason && W.pl.nops == 0) reason = AIGW_R_OPS;
-  }
-  po.reason = (uint8_t)reason; po.nops = (uint32_t)W.pl.nops; po.olen = W.pl.olen; po.path_len = path_len;
-  wp.plan[li] = po;
-}
-
-
-// Persistent grid: every warp pulls groups of 32 shape-sorted documents from a counter, heaviest (most tokens) first, so the
-// launch has no wave quantisation and its tail is made of the lightest documents.
-template <int BLOCKS>
-__global__ void __launch_bounds__(128, BLOCKS) chat_walk_kernel(const __grid_constant__ ChatParams P, uint32_t doc0, uint32_t ndocs, uint8_t* work, const WorkLayout C) {
-  const WorkPtrs wp = carve(work, ndocs, C);
-  const int lane = threadIdx.x & 31;
-  const uint32_t ngroups = (ndocs + 31u) >> 5;
-  for (;;) {
-    uint32_t grp = 0;
-    if (lane == 0) grp = atomicAdd(wp.c_walk, 1u);
-    grp = __shfl_sync(0xffffffffu, grp, 0);
-    if (grp >= ngroups) break;
-    const uint32_t tid = grp * 32u + (uint32_t)lane;
-    if (tid < ndocs) walk_one(P, doc0, wp, C, wp.perm[ndocs - 1u - tid]);
-    __syncwarp();
-  }
-}
+#define AIGW_WALK_DECL(g) cudaError_t launch_chat_walk_g##g(const ChatParams&, uint32_t, uint32_t, uint8_t*, const WorkLayout&, cudaStream_t, int);
+AIGW_WALK_DECL(0) AIGW_WALK_DECL(1) AIGW_WALK_DECL(2) AIGW_WALK_DECL(3) AIGW_WALK_DECL(4) AIGW_WALK_DECL(5) AIGW_WALK_DECL(6)
+#undef AIGW_WALK_DECL
 
 cudaError_t launch_chat_walk(const ChatParams& P, uint32_t doc0, uint32_t ndocs, uint8_t* work, const WorkLayout& layout, cudaStream_t st) {
-  static const int variant = getenv("AIGW_WALK_VARIANT") ? atoi(getenv("AIGW_WALK_VARIANT")) : 0;   // experiment: 1 = 8 blocks / SM (64 registers)
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   { static int sm_cache[kMaxDevices] = {0}; if (dev >= 0 && dev < kMaxDevices) { if (!sm_cache[dev]) cudaDeviceGetAttribute(&sm_cache[dev], cudaDevAttrMultiProcessorCount, dev); sms = sm_cache[dev] ? sm_cache[dev] : 148; } }
-  const unsigned want = (ndocs + 127) / 128;
-  if (variant & 1) { const unsigned cap = (unsigned)sms * 8u; chat_walk_kernel<8><<<want < cap ? want : cap, 128, 0, st>>>(P, doc0, ndocs, work, layout); }
-  else { const unsigned cap = (unsigned)sms * AIGW_WALK_BLOCKS; chat_walk_kernel<AIGW_WALK_BLOCKS><<<want < cap ? want : cap, 128, 0, st>>>(P, doc0, ndocs, work, layout); }
-  return cudaGetLastError();
+  const uint32_t s = P.schema;
+  if ((s & 48u) == (uint32_t)AIGW_SCHEMA_RESP_AWS_BEDROCK)
+    return (s & 15u) == (uint32_t)AIGW_SCHEMA_GCP_ANTHROPIC ? launch_chat_walk_g5(P, doc0, ndocs, work, layout, st, sms) : launch_chat_walk_g4(P, doc0, ndocs, work, layout, st, sms);
+  if (s & (uint32_t)AIGW_SCHEMA_EMBEDDINGS) return launch_chat_walk_g6(P, doc0, ndocs, work, layout, st, sms);
+  switch (s) {
+    case AIGW_SCHEMA_AWS_BEDROCK: return launch_chat_walk_g0(P, doc0, ndocs, work, layout, st, sms);
+    case AIGW_SCHEMA_GCP_ANTHROPIC: case AIGW_SCHEMA_AWS_ANTHROPIC: return launch_chat_walk_g2(P, doc0, ndocs, work, layout, st, sms);
+    case AIGW_SCHEMA_GCP_VERTEX: return launch_chat_walk_g3(P, doc0, ndocs, work, layout, st, sms);
+    default: return launch_chat_walk_g1(P, doc0, ndocs, work, layout, st, sms);   // OpenAI / Azure; a schema without a planner declines every document with AIGW_R_SCHEMA
+  }
 }
 
 }  // namespace aigw
