@@ -18,7 +18,7 @@ static_assert(make_lit_table().off[L_COUNT] + 24 <= sizeof(LitTable::bytes), "li
 
 #define FULL 0xffffffffu
 #ifndef AIGW_WALK_BLOCKS
-#define AIGW_WALK_BLOCKS 6
+#define AIGW_WALK_BLOCKS 4
 #endif
 
 // ------------------------------------------------------------------ small device helpers
@@ -234,6 +234,6 @@ __host__ __device__ inline WorkPtrs carve(uint8_t* base, size_t ndocs, const Wor
 }
 
 // K2 (chat_walk.cu): validate + schema walk, one thread per document of the sub-batch
-cudaError_t launch_chat_walk(const ChatParams& P, uint32_t doc0, uint32_t ndocs, uint8_t* work, const WorkLayout& layout, cudaStream_t st);
+cudaError_t launch_chat_walk(const ChatParams& P, uint32_t doc0, uint32_t ndocs, uint8_t* work, const WorkLayout& layout, cudaStream_t st, int blocks_per_sm = 0);   // 0: AIGW_WALK_BLOCKS
 
 }  // namespace aigw

@@ -562,9 +562,57 @@ static cudaError_t launch_cls(const ChatParams& P, uint32_t first, int device, i
     }
   }
   // stage timing (ev) needs the stages back to back on one stream; otherwise sub-batches rotate over the auxiliary streams
-  static const int env_streams = getenv("AIGW_CHAT_STREAMS") ? atoi(getenv("AIGW_CHAT_STREAMS")) : 1;   // > 1: sub-batches rotate over auxiliary streams (measured: no gain)
+  static const int env_streams = getenv("AIGW_CHAT_STREAMS") ? atoi(getenv("AIGW_CHAT_STREAMS")) : 1;   // > 1: sub-batches rotate over auxiliary streams
   static const int env_idx_ctas = getenv("AIGW_IDX_CTAS") ? atoi(getenv("AIGW_IDX_CTAS")) : 0;      // experiments: cap resident CTAs per SM
   static const int env_emit_ctas = getenv("AIGW_EMIT_CTAS") ? atoi(getenv("AIGW_EMIT_CTAS")) : 0;
+  static const int env_walk_ctas = getenv("AIGW_WALK_CTAS") ? atoi(getenv("AIGW_WALK_CTAS")) : 0;
+  static const int env_pipe = getenv("AIGW_CHAT_PIPE") ? atoi(getenv("AIGW_CHAT_PIPE")) : 0;
+  // ---- stage-pipelined mode: one stream per STAGE, sub-batches flow index -> walk -> emit through a ring of workspaces, so in
+  // the steady state one index, one walk and one emit kernel (of three consecutive sub-batches) are resident on every SM at
+  // once.  The walk is latency-bound (IPC 0.4) while index and emit are bound by the integer issue rate, so sharing an SM costs
+  // each little; every kernel's grid is capped so that the three fit together (registers: 3x128x80 + 2x128x54 + 2x128x56).
+  if (env_pipe && aux && !ev && P.n > 4096) {
+    const int ic = env_idx_ctas > 0 ? env_idx_ctas : 2, wc = env_walk_ctas > 0 ? env_walk_ctas : 3, ec = env_emit_ctas > 0 ? env_emit_ctas : 2;
+    const int bps1 = ic < cc.bps1 ? ic : cc.bps1, bps3 = ec < cc.bps3 ? ec : cc.bps3;
+    size_t sub = sub_batch_docs(MAXD);
+    int ring = kChatRing;
+    const size_t per = (chat_work_bytes(MAXD, sub) + 511) & ~(size_t)255;
+    while (ring > 1 && per * ring > work_cap) ring--;
+    if (per * ring > work_cap) { sub = (work_cap - kWorkHdr - 256) / work_per_doc(layout_of<MAXD>()); ring = 1; }
+    if (sub == 0) return cudaErrorMemoryAllocation;
+    cudaStream_t sI = aux->s[0], sW = aux->s[1], sE = aux->s[2];
+    cudaError_t e;
+    if ((e = cudaEventRecord(aux->fork, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(sI, aux->fork, 0)) != cudaSuccess) return e;
+    int nl = 0, sb = 0;
+    for (uint32_t rel = 0; rel < P.n; rel += (uint32_t)sub, sb++) {
+      const uint32_t doc0 = first + rel;
+      const uint32_t nd = (uint32_t)(P.n - rel < sub ? P.n - rel : sub);
+      const int slot = sb % ring;
+      uint8_t* wk = work + (size_t)slot * per;
+      const WorkPtrs wp = carve(wk, nd, layout_of<MAXD>());
+      long long want = ((long long)nd + WARPS - 1) / WARPS;
+      long long g1 = (long long)sm_count * bps1; if (want < g1) g1 = want;
+      long long g3 = (long long)sm_count * bps3; if (want < g3) g3 = want;
+      if (sb >= ring && (e = cudaStreamWaitEvent(sI, aux->emit_done[slot], 0)) != cudaSuccess) return e;   // the slot's previous tenant has been emitted
+      if ((e = cudaMemsetAsync(wk, 0, kWorkHdr, sI)) != cudaSuccess) return e;
+      chat_index_kernel<MAXD, WARPS><<<(unsigned)g1, WARPS * 32, smem1, sI>>>(P, doc0, nd, wk);
+      if ((e = cudaEventRecord(aux->idx_done[slot], sI)) != cudaSuccess) return e;
+      if ((e = cudaStreamWaitEvent(sW, aux->idx_done[slot], 0)) != cudaSuccess) return e;
+      { const unsigned gs = (nd + 8191) / 8192; chat_sort_kernel<<<gs < 32 ? gs : 32, kBins, 0, sW>>>(wp.ntok, wp.bins, wp.cursor, wp.perm, nd); }
+      if ((e = launch_chat_walk(P, doc0, nd, wk, layout_of<MAXD>(), sW, wc)) != cudaSuccess) return e;
+      if ((e = cudaEventRecord(aux->walk_done[slot], sW)) != cudaSuccess) return e;
+      if ((e = cudaStreamWaitEvent(sE, aux->walk_done[slot], 0)) != cudaSuccess) return e;
+      chat_emit_kernel<MAXD, WARPS><<<(unsigned)g3, WARPS * 32, smem3, sE>>>(P, doc0, nd, wk);
+      if ((e = cudaEventRecord(aux->emit_done[slot], sE)) != cudaSuccess) return e;
+      nl += 4;
+    }
+    // emits complete in order on sE, and every index / walk precedes its emit
+    if ((e = cudaEventRecord(aux->join[0], sE)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(st, aux->join[0], 0)) != cudaSuccess) return e;
+    if (launches) *launches = nl;
+    return cudaGetLastError();
+  }
   const bool overlap = aux && !ev && P.n > 1024 && env_streams > 1;
   const int nstreams = overlap ? (env_streams < kChatStreams ? env_streams : kChatStreams) : 1;
   const size_t half = (work_cap / nstreams) & ~(size_t)255;
@@ -595,7 +643,7 @@ static cudaError_t launch_cls(const ChatParams& P, uint32_t first, int device, i
     chat_index_kernel<MAXD, WARPS><<<(unsigned)g1, WARPS * 32, smem1, s>>>(P, doc0, nd, wk);
     if (timed) cudaEventRecord(ev[4 * sb + 1], s);
     { const unsigned gs = (nd + 8191) / 8192; chat_sort_kernel<<<gs < 32 ? gs : 32, kBins, 0, s>>>(wp.ntok, wp.bins, wp.cursor, wp.perm, nd); }
-    if ((e = launch_chat_walk(P, doc0, nd, wk, layout_of<MAXD>(), s)) != cudaSuccess) return e;
+    if ((e = launch_chat_walk(P, doc0, nd, wk, layout_of<MAXD>(), s, env_walk_ctas)) != cudaSuccess) return e;
     if (timed) cudaEventRecord(ev[4 * sb + 2], s);
     chat_emit_kernel<MAXD, WARPS><<<(unsigned)g3, WARPS * 32, smem3, s>>>(P, doc0, nd, wk);
     if (timed) cudaEventRecord(ev[4 * sb + 3], s);
@@ -622,6 +670,11 @@ size_t chat_work_bytes(uint32_t max_len, size_t ndocs) {
 // workspace that lets a call of n documents run at full overlap: two sub-batches in flight
 size_t chat_work_bytes_for(uint32_t max_len, size_t n) {
   static const int env_streams = getenv("AIGW_CHAT_STREAMS") ? atoi(getenv("AIGW_CHAT_STREAMS")) : 1;
+  static const int env_pipe = getenv("AIGW_CHAT_PIPE") ? atoi(getenv("AIGW_CHAT_PIPE")) : 0;
+  if (env_pipe && n > 4096) {
+    const int maxd = max_len <= 2048 ? 2048 : max_len <= 5120 ? 5120 : max_len <= 9216 ? 9216 : max_len <= 17408 ? 17408 : max_len <= 33792 ? 33792 : 65536;
+    return kChatRing * ((chat_work_bytes(maxd, sub_batch_docs(maxd)) + 511) & ~(size_t)255) + 512;
+  }
   if (n <= 1024 || env_streams <= 1) return chat_work_bytes(max_len, n < 262144 ? n : 262144) + 512;
   const int maxd = max_len <= 2048 ? 2048 : max_len <= 5120 ? 5120 : max_len <= 9216 ? 9216 : max_len <= 17408 ? 17408 : max_len <= 33792 ? 33792 : 65536;
   size_t sub = sub_batch_docs(maxd);

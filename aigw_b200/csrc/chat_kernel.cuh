@@ -248,7 +248,8 @@ struct Cls {
 // Per-device kernel attributes are configured on first use of each (device, size class).
 static constexpr int kMaxDevices = 16;
 static constexpr int kChatStreams = 4;
-struct ChatAux { cudaStream_t s[kChatStreams]; cudaEvent_t fork, join[kChatStreams]; };
+static constexpr int kChatRing = 4;   // sub-batch workspaces in flight in the stage-pipelined mode
+struct ChatAux { cudaStream_t s[kChatStreams]; cudaEvent_t fork, join[kChatStreams], idx_done[kChatRing], walk_done[kChatRing], emit_done[kChatRing]; };
 size_t chat_work_bytes(uint32_t max_len, size_t ndocs);
 size_t chat_work_bytes_for(uint32_t max_len, size_t n);
 cudaError_t launch_chat_translate(const ChatParams& P, uint32_t max_len, int device, int sm_count, cudaStream_t st, uint8_t* work, size_t work_cap, const ChatAux* aux, int* launches,

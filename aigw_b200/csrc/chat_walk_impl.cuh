@@ -1953,7 +1953,7 @@ __global__ void __launch_bounds__(128, AIGW_WALK_BLOCKS) AIGW_CAT(chat_walk_kern
 }  // namespace
 
 cudaError_t AIGW_CAT(launch_chat_walk_g, AIGW_WALK_GROUP)(const ChatParams& P, uint32_t doc0, uint32_t ndocs, uint8_t* work, const WorkLayout& layout, cudaStream_t st, int sms) {
-  const unsigned want = (ndocs + 127) / 128, cap = (unsigned)sms * AIGW_WALK_BLOCKS;
+  const unsigned want = (ndocs + 127) / 128, cap = (unsigned)sms;   // sms = grid cap (SMs x resident blocks the caller wants)
   AIGW_CAT(chat_walk_kernel_g, AIGW_WALK_GROUP)<<<want < cap ? want : cap, 128, 0, st>>>(P, doc0, ndocs, work, layout);
   return cudaGetLastError();
 }

@@ -19,7 +19,7 @@ sec = next(i for i in secs if want in rows[i][1])
 end = next((j for j in secs if j > sec), len(rows))
 h = rows[sec + 1]; data = rows[sec + 2:end]
 iI, iS, iA, iT = h.index('Instructions Executed'), h.index('# Samples'), h.index('Address'), h.index('Thread Instructions Executed')
-key = next(k for k in mapping if want.replace("aigw::", "") .split("<")[0] in k and ("5120" in k or "walk" in k))
+key = next(k for k in mapping if want.replace("aigw::", "") .split("<")[0] in k and ("5120" in k or "walk" in k or len(mapping) == 1))
 offs = mapping[key]
 base = int(data[0][iA], 16)
 agg = collections.defaultdict(lambda: [0, 0, 0]); tot = [0, 0, 0]
@@ -31,7 +31,7 @@ for r in data:
     tot[0] += n; tot[1] += s; tot[2] += t
 src = {}
 import os
-for f in ('chat_kernel.cu', 'chat_kernel.cuh', 'chat_walk.cu', 'chat_internal.cuh', 'bulk.cuh', 'sse_kernel.cu', 'tjson.cuh', 'stream_kernel.cu'):
+for f in ('chat_kernel.cu', 'chat_kernel.cuh', 'chat_walk.cu', 'chat_walk_impl.cuh', 'classify.cuh', 'chat_internal.cuh', 'bulk.cuh', 'sse_kernel.cu', 'tjson.cuh', 'stream_kernel.cu'):
     p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'aigw_b200', 'csrc', f)
     if os.path.exists(p): src[f] = open(p).read().split('\n')
 print(f"{want}: {tot[0]} warp instructions, {tot[1]} samples, avg active threads {tot[2] / max(1, tot[0]):.1f}")
