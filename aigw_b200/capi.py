@@ -41,9 +41,9 @@ assert MutResult.itemsize == 16
 EXPORTS = ["aigw_bind_numa", "aigw_stream_open", "aigw_stream_open_batch", "aigw_stream_chunks", "aigw_stream_chunks_soa", "aigw_stream_chunk", "aigw_stream_close", "aigw_stream_close_batch",
            "aigw_version", "aigw_init", "aigw_destroy", "aigw_last_error", "aigw_device_sm_count", "aigw_host_alloc", "aigw_host_free",
            "aigw_device_alloc", "aigw_device_free", "aigw_memcpy_h2d", "aigw_memcpy_d2h", "aigw_memset_d", "aigw_sync",
-           "aigw_chat_translate_device", "aigw_chat_translate_device_mapped", "aigw_chat_last_profile", "aigw_chat_set_profile", "aigw_chat_translate_host", "aigw_sse_usage_device", "aigw_sse_usage_host", "aigw_response_usage_device", "aigw_response_usage_host", "aigw_embeddings_response_usage_device", "aigw_embeddings_response_usage_host", "aigw_usage_costs_device",
+           "aigw_chat_translate_device", "aigw_chat_translate_device_mapped", "aigw_chat_last_profile", "aigw_chat_set_profile", "aigw_chat_set_small_batch", "aigw_chat_translate_host", "aigw_sse_usage_device", "aigw_sse_usage_host", "aigw_response_usage_device", "aigw_response_usage_host", "aigw_embeddings_response_usage_device", "aigw_embeddings_response_usage_host", "aigw_usage_costs_device",
            "aigw_bedrock_stream_device", "aigw_bedrock_stream_host", "aigw_body_mutate_device", "aigw_body_mutate_host",
-           "aigw_cost_compile", "aigw_cost_program_free", "aigw_usage_costs_cel_device", "aigw_usage_costs_cel_host", "aigw_sha256_device", "aigw_chat_body_sha256_device", "aigw_sha256_host", "aigw_batcher_start", "aigw_batcher_translate", "aigw_batcher_get_stats", "aigw_batcher_stop"]
+           "aigw_cost_compile", "aigw_cost_program_free", "aigw_usage_costs_cel_device", "aigw_usage_costs_cel_host", "aigw_sha256_device", "aigw_chat_body_sha256_device", "aigw_sha256_host", "aigw_batcher_start", "aigw_batcher_add_backend", "aigw_batcher_translate", "aigw_batcher_translate_to", "aigw_batcher_get_stats", "aigw_batcher_stop"]
 
 
 class BackendCfg(C.Structure):
@@ -115,6 +115,7 @@ def load_library():
                                                     C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
     L.aigw_chat_last_profile.argtypes = [C.c_void_p, C.POINTER(C.c_float * 3), C.POINTER(C.c_int)]
     L.aigw_chat_set_profile.argtypes = [C.c_void_p, C.c_int]
+    L.aigw_chat_set_small_batch.argtypes = [C.c_void_p, C.c_int]; L.aigw_chat_set_small_batch.restype = None
     L.aigw_chat_translate_host.argtypes = [C.c_void_p, C.POINTER(BackendCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(_BatchOut)]
     L.aigw_sse_usage_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
     L.aigw_sse_usage_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64),
@@ -138,6 +139,8 @@ def load_library():
     L.aigw_sha256_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     L.aigw_batcher_start.argtypes = [C.c_void_p, C.POINTER(BackendCfg), C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
     L.aigw_batcher_translate.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.aigw_batcher_translate_to.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.aigw_batcher_add_backend.argtypes = [C.c_void_p, C.POINTER(BackendCfg)]
     L.aigw_batcher_get_stats.argtypes = [C.c_void_p, C.c_void_p]
     L.aigw_batcher_stop.argtypes = [C.c_void_p]
     L.aigw_batcher_stop.restype = None
@@ -265,6 +268,10 @@ class Context:
                                                             C.byref(ms) if timed else None), "chat_translate_device_mapped")
         return ms.value
 
+    def chat_set_small_batch(self, max_docs):
+        """calls of at most max_docs small bodies run as one fused kernel (0: always the throughput pipeline, -1: default)"""
+        self.L.aigw_chat_set_small_batch(self.h, int(max_docs))
+
     def chat_set_profile(self, on):
         self.L.aigw_chat_set_profile(self.h, 1 if on else 0)
 
@@ -388,11 +395,17 @@ class Context:
         self._check(self.L.aigw_batcher_start(self.h, C.byref(cfg), max_batch, window_us, C.byref(h)), "batcher_start")
         return h
 
-    def batcher_translate(self, b, body: bytes, out_cap=1 << 17):
+    def batcher_add_backend(self, b, cfg):
+        idx = self.L.aigw_batcher_add_backend(b, C.byref(cfg))
+        if idx < 0:
+            raise RuntimeError(f"batcher_add_backend: {idx}")
+        return idx
+
+    def batcher_translate(self, b, body: bytes, out_cap=1 << 17, backend=0):
         """→ (rc, status, reason, path bytes, body bytes, body_kind).  Releases the GIL while it waits."""
         out = C.create_string_buffer(out_cap)
         res = np.zeros(1, dtype=DocResult)
-        rc = self.L.aigw_batcher_translate(b, body, len(body), out, out_cap, res.ctypes.data)
+        rc = self.L.aigw_batcher_translate_to(b, backend, body, len(body), out, out_cap, res.ctypes.data)
         r = res[0]
         pl, bl = int(r["path_len"]), int(r["body_len"])
         ok = rc == 0 and r["status"] == AIGW_OK

@@ -250,6 +250,9 @@ static constexpr int kMaxDevices = 16;
 static constexpr int kChatStreams = 4;
 static constexpr int kChatRing = 4;   // sub-batch workspaces in flight in the stage-pipelined mode
 struct ChatAux { cudaStream_t s[kChatStreams]; cudaEvent_t fork, join[kChatStreams], idx_done[kChatRing], walk_done[kChatRing], emit_done[kChatRing]; };
+static constexpr uint32_t kSmallMaxLen = 5120;   // the fused small-batch kernel's size class
+// fused index + walk + emit, one CTA per document; out_slot[i] .. out_slot[i+1] is document i's output slot in P.out; no workspace
+cudaError_t launch_chat_small(const ChatParams& P, uint32_t doc0, uint32_t ndocs, const uint64_t* out_slot, cudaStream_t st);
 size_t chat_work_bytes(uint32_t max_len, size_t ndocs);
 size_t chat_work_bytes_for(uint32_t max_len, size_t n);
 cudaError_t launch_chat_translate(const ChatParams& P, uint32_t max_len, int device, int sm_count, cudaStream_t st, uint8_t* work, size_t work_cap, const ChatAux* aux, int* launches,

@@ -2,7 +2,9 @@
 // output as copy ops.  One thread per document; compiled once for every size class (slot sizes are kernel arguments).
 // See chat_kernel.cuh for the design and chat_kernel.cu for the index / emit stages.  sm_100a only.
 //
-// This file is the body of one translation unit per schema group (chat_walk_g*.cu define AIGW_WALK_GROUP and include it): a
+// This file is the body of two translation units per schema group (chat_walk_g*.cu: the throughput walk kernel;
+// chat_small_g*.cu, which also define AIGW_WALK_SMALL: the fused small-batch kernel — one kernel per unit, so that every
+// planner has a single call site and is inlined with the Walker in registers).  They define AIGW_WALK_GROUP and include it: a
 // kernel that carries only its own planner keeps its code and its stack frame small, which is what a latency-bound
 // thread-per-document kernel pays for (measured on B200: the Bedrock walk went 2.95 -> 3.65 ms per 1 M bodies when the
 // Anthropic-response and Gemini planners were added to the single kernel).
@@ -10,7 +12,7 @@
 #ifndef AIGW_WALK_GROUP
 #error "include from chat_walk_g*.cu with AIGW_WALK_GROUP defined"
 #endif
-#include "chat_internal.cuh"
+#include "chat_stage.cuh"
 
 #include <cstdlib>
 
@@ -1871,19 +1873,21 @@ struct Walker {
 //         4 Bedrock Converse response, 5 Anthropic response, 6 embeddings
 static constexpr int G = AIGW_WALK_GROUP;
 
-static __device__ void walk_one(const ChatParams& P, uint32_t doc0, const WorkPtrs& wp, const WorkLayout& C, uint32_t li) {
-  const uint32_t doc = P.doc_map ? P.doc_map[doc0 + li] : doc0 + li;
-  const uint32_t nt_word = wp.ntok[li];
-  PlanOut po; po.nops = 0; po.olen = 0; po.path_len = 0; po.model_off = 0; po.model_len = 0; po.flags = 0; po.reason = 0;
-  if (nt_word & 0x80000000u) { po.reason = (uint8_t)(nt_word & 0xff); wp.plan[li] = po; return; }
+struct WalkBufs { const uint8_t* body; uint32_t len; uint32_t* tw; uint16_t* jmp; uint32_t* ops; uint8_t* scr; int kTok, kOps, kScr; };
+
+// one document: token words in B.tw[0, nt_word) -> jump table, copy ops, scratch; returns the plan header.  The buffers may
+// live in the global workspace (throughput path) or in shared memory (fused small-batch kernel).
+static __device__ __forceinline__ void walk_doc(const ChatParams& P, const WalkBufs B, uint32_t nt_word, PlanOut& po) {
+  po.nops = 0; po.olen = 0; po.path_len = 0; po.model_off = 0; po.model_len = 0; po.flags = 0; po.reason = 0;
+  if (nt_word & 0x80000000u) { po.reason = (uint8_t)(nt_word & 0xff); return; }
   const uint32_t ntok = nt_word;
   Walker W;
-  W.d.s = P.bodies + P.offsets[doc]; W.d.len = P.lens[doc];
-  W.d.tw = wp.tw + (size_t)li * C.kTok; W.d.jmp = wp.jmp + (size_t)li * C.kTok;
+  W.d.s = B.body; W.d.len = B.len;
+  W.d.tw = B.tw; W.d.jmp = B.jmp;
   W.d.nt = (int)ntok; W.d.kind = 0;
-  W.pl.ops = wp.ops + (size_t)li * (C.kOps + kSysCap); W.pl.nops = 0; W.pl.nsys = 0; W.pl.cap = (int)C.kOps; W.pl.clen = 0; W.pl.ckind = 0; W.pl.coff = 0; W.pl.olen = 0; W.pl.err = 0; W.pl.dry = false;
-  W.sc.p = wp.scr + (size_t)li * C.kScr; W.sc.n = 0; W.sc.cap = C.kScr - 20u;
-  W.tw_tail = (uint32_t*)W.d.tw + ntok; W.jmp_tail = W.d.jmp + ntok; W.tail_cap = (int)C.kTok - (int)ntok;
+  W.pl.ops = B.ops; W.pl.nops = 0; W.pl.nsys = 0; W.pl.cap = B.kOps; W.pl.clen = 0; W.pl.ckind = 0; W.pl.coff = 0; W.pl.olen = 0; W.pl.err = 0; W.pl.dry = false;
+  W.sc.p = B.scr; W.sc.n = 0; W.sc.cap = (uint32_t)B.kScr - 20u;
+  W.tw_tail = B.tw + ntok; W.jmp_tail = B.jmp + ntok; W.tail_cap = B.kTok - (int)ntok;
   W.P = &P; W.reason = 0; W.pending = 0;
   int reason = validate_tokens(W.d);
   if (reason == AIGW_R_SYNTAX) reason = AIGW_R_E400_SYNTAX;
@@ -1928,13 +1932,25 @@ static __device__ void walk_one(const ChatParams& P, uint32_t doc0, const WorkPt
     if (!reason && W.pl.nops == 0) reason = AIGW_R_OPS;
   }
   po.reason = (uint8_t)reason; po.nops = (uint32_t)W.pl.nops; po.olen = W.pl.olen; po.path_len = path_len;
+}
+
+#define AIGW_CAT2(a, b) a##b
+#define AIGW_CAT(a, b) AIGW_CAT2(a, b)
+
+#ifndef AIGW_WALK_SMALL
+static __device__ __forceinline__ void walk_one(const ChatParams& P, uint32_t doc0, const WorkPtrs& wp, const WorkLayout& C, uint32_t li) {
+  const uint32_t doc = P.doc_map ? P.doc_map[doc0 + li] : doc0 + li;
+  WalkBufs B;
+  B.body = P.bodies + P.offsets[doc]; B.len = P.lens[doc];
+  B.tw = wp.tw + (size_t)li * C.kTok; B.jmp = wp.jmp + (size_t)li * C.kTok;
+  B.ops = wp.ops + (size_t)li * (C.kOps + kSysCap); B.scr = wp.scr + (size_t)li * C.kScr;
+  B.kTok = (int)C.kTok; B.kOps = (int)C.kOps; B.kScr = (int)C.kScr;
+  PlanOut po; walk_doc(P, B, wp.ntok[li], po);
   wp.plan[li] = po;
 }
 
 // Persistent grid: every warp pulls groups of 32 shape-sorted documents from a counter, heaviest (most tokens) first, so the
 // launch has no wave quantisation and its tail is made of the lightest documents.
-#define AIGW_CAT2(a, b) a##b
-#define AIGW_CAT(a, b) AIGW_CAT2(a, b)
 __global__ void __launch_bounds__(128, AIGW_WALK_BLOCKS) AIGW_CAT(chat_walk_kernel_g, AIGW_WALK_GROUP)(const __grid_constant__ ChatParams P, uint32_t doc0, uint32_t ndocs, uint8_t* work, const WorkLayout C) {
   const WorkPtrs wp = carve(work, ndocs, C);
   const int lane = threadIdx.x & 31;
@@ -1950,12 +1966,121 @@ __global__ void __launch_bounds__(128, AIGW_WALK_BLOCKS) AIGW_CAT(chat_walk_kern
   }
 }
 
+
+#else
+// ---- fused small-batch kernel: index + walk + emit of ONE document per CTA (one warp), every intermediate in shared memory.
+// This is the latency path (a single request, or the few hundred a batching window collects): one launch, no workspace, no
+// memset, no shape sort.  The body is read straight from the caller-visible (mapped pinned) buffer and the record / result
+// go straight back to mapped pinned memory, so the call is launch + kernel + one synchronisation.  Each document owns a
+// fixed output slot (out_slot[i] .. out_slot[i+1]), so there is no bump allocator to reset.  Same stage code as the
+// throughput kernels (chat_stage.cuh, walk_doc), so the bytes are the same by construction.
+static __device__ IdTables g_small_ids = make_id_tables();
+static __device__ IdTables g_small_ids_resp = make_resp_id_tables();
+static __device__ LitTable g_small_lits = make_lit_table();
+
+template <int MAXD>
+struct SmallSmem {
+  using C = Cls<MAXD>;
+  static constexpr int kLits = (int)sizeof(LitTable::bytes);
+  static constexpr int oIn = kLits, oTw = oIn + C::kIn + 16, oBs = oTw + C::kTok * 4, oNc = oBs + C::kTok * 2, oJmp = oNc + (((MAXD / 1024 + 1) * 4 + 15) & ~15),
+                       oOps = oJmp + C::kTok * 2, oScr = oOps + (C::kOps + kSysCap) * 4, oPre = oScr + ((C::kScr + 31) & ~15), oFirst = oPre + (C::kOps + 4) * 4,
+                       oBl = oFirst + kEmitTile * 2, oPo = oBl + (C::kOps + 4) * 4, kBytes = oPo + 32;
+};
+
+template <int MAXD>
+__global__ void __launch_bounds__(32) AIGW_CAT(chat_small_kernel_g, AIGW_WALK_GROUP)(const __grid_constant__ ChatParams P, uint32_t doc0, const uint64_t* out_slot) {
+  using C = Cls<MAXD>;
+  using S = SmallSmem<MAXD>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int lane = threadIdx.x;
+  uint8_t* s_lits = smem;
+  uint8_t* s_in = smem + S::oIn;
+  uint32_t* s_tw = (uint32_t*)(smem + S::oTw);
+  uint16_t* s_bs = (uint16_t*)(smem + S::oBs);
+  uint32_t* s_nc = (uint32_t*)(smem + S::oNc);
+  uint16_t* s_jmp = (uint16_t*)(smem + S::oJmp);
+  uint32_t* s_ops = (uint32_t*)(smem + S::oOps);
+  uint8_t* s_scr = smem + S::oScr;
+  uint32_t* s_pre = (uint32_t*)(smem + S::oPre);
+  uint16_t* s_first = (uint16_t*)(smem + S::oFirst);
+  uint32_t* s_bl = (uint32_t*)(smem + S::oBl);
+  PlanOut* s_po = (PlanOut*)(smem + S::oPo);
+  const uint32_t li = blockIdx.x, doc = doc0 + li;
+  const uint32_t len = P.lens[doc];
+  const uint8_t* g = P.bodies + P.offsets[doc];
+  aigw_doc_result res = blank_result(len);
+  if (len > (uint32_t)MAXD || len == 0) {
+    const uint32_t r = len ? AIGW_R_TOO_LARGE : AIGW_R_E400_SYNTAX;
+    res.reason = r; res.status = r >= 32 ? AIGW_MALFORMED_400 : AIGW_DECLINED;
+    if (lane == 0) P.results[doc] = res;
+    return;
+  }
+  const long long t0 = clock64();
+  // body (the loads of the whole body are in flight together: one PCIe round trip when the buffer is mapped host memory), literals
+  if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) { const uint4* g4 = (const uint4*)g; uint4* d4 = (uint4*)s_in; for (uint32_t i = lane; i < (len + 15u) >> 4; i += 32) d4[i] = g4[i]; }
+  else for (uint32_t i = lane; i < len; i += 32) s_in[i] = g[i];
+  { const uint4* l4 = (const uint4*)g_small_lits.bytes; uint4* d4 = (uint4*)s_lits; for (uint32_t i = lane; i < S::kLits / 16; i += 32) d4[i] = l4[i]; }
+  __syncwarp();
+  const IdTables* ids = (P.schema & 48) == AIGW_SCHEMA_RESP_AWS_BEDROCK ? &g_small_ids_resp : &g_small_ids;
+  const long long t1 = clock64();
+  const uint32_t ntok = index_doc<MAXD>(s_in, len, lane, s_tw, s_bs, s_nc, ids);
+  __syncwarp();
+  const long long t2 = clock64();
+  if (lane == 0) {
+    WalkBufs B;
+    B.body = s_in; B.len = len; B.tw = s_tw; B.jmp = s_jmp; B.ops = s_ops; B.scr = s_scr;
+    B.kTok = C::kTok; B.kOps = C::kOps; B.kScr = C::kScr;
+    PlanOut pw; walk_doc(P, B, ntok, pw);
+    *s_po = pw;
+  }
+  __syncwarp();
+  const long long t3 = clock64();
+  const PlanOut po = *s_po;
+  if (po.reason) {
+    res.reason = po.reason;
+    res.status = po.reason >= 48 ? AIGW_INTERNAL : po.reason >= 40 ? AIGW_INVALID_422 : po.reason >= 32 ? AIGW_MALFORMED_400 : AIGW_DECLINED;
+    if (lane == 0) P.results[doc] = res;
+    return;
+  }
+  const uint32_t nops = po.nops, olen = po.olen;
+  emit_prefix<MAXD>(s_ops, s_ops[lane], nops, olen, s_ops, s_pre, lane);   // the ops are already in place; this computes the prefix
+  const uint32_t rec = (olen + 15u) & ~15u, nchunks = rec >> 4;
+  const uint64_t obase = out_slot[li], ocap = out_slot[li + 1] - obase;
+  __syncwarp();
+  if (rec > ocap || nchunks > 0xffffu) {
+    res.reason = nchunks > 0xffffu ? AIGW_R_OUT_SPACE : AIGW_R_ARENA_FULL;
+    if (lane == 0) P.results[doc] = res;
+    return;
+  }
+  emit_doc<MAXD>(s_in, s_lits, s_scr, s_pre, s_ops, s_first, s_bl, nops, nchunks, (uint4*)(P.out + obase), lane);
+  if (lane == 0) {
+    res.out_off = obase + P.out_bias; res.body_len = olen - po.path_len; res.path_len = (uint16_t)po.path_len; res.status = AIGW_OK; res.reason = 0;
+    res.model_off = po.model_off; res.model_len = po.model_len; res.body_kind = (po.flags & 0x80u) ? AIGW_BODY_UNCHANGED : AIGW_BODY_BYTES; res.flags = po.flags & 0x7fu;
+    P.results[doc] = res;
+    if (P.next_doc && li == 0) { const long long t4 = clock64(); P.next_doc[0] = (unsigned)(t1 - t0); P.next_doc[1] = (unsigned)(t2 - t1); P.next_doc[2] = (unsigned)(t3 - t2); P.next_doc[3] = (unsigned)(t4 - t3); }   // phase clocks (debug)
+  }
+}
+
+#endif
+
 }  // namespace
 
+#ifndef AIGW_WALK_SMALL
 cudaError_t AIGW_CAT(launch_chat_walk_g, AIGW_WALK_GROUP)(const ChatParams& P, uint32_t doc0, uint32_t ndocs, uint8_t* work, const WorkLayout& layout, cudaStream_t st, int sms) {
   const unsigned want = (ndocs + 127) / 128, cap = (unsigned)sms;   // sms = grid cap (SMs x resident blocks the caller wants)
   AIGW_CAT(chat_walk_kernel_g, AIGW_WALK_GROUP)<<<want < cap ? want : cap, 128, 0, st>>>(P, doc0, ndocs, work, layout);
   return cudaGetLastError();
 }
+
+
+#else
+cudaError_t AIGW_CAT(launch_chat_small_g, AIGW_WALK_GROUP)(const ChatParams& P, uint32_t doc0, uint32_t ndocs, const uint64_t* out_slot, cudaStream_t st) {
+  constexpr int kBytes = SmallSmem<5120>::kBytes;
+  static_assert(kBytes <= 48 * 1024, "the small-batch kernel stays under the default dynamic shared memory limit");
+  AIGW_CAT(chat_small_kernel_g, AIGW_WALK_GROUP)<5120><<<ndocs, 32, kBytes, st>>>(P, doc0, out_slot);
+  return cudaGetLastError();
+}
+
+#endif
 
 }  // namespace aigw

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "chat_kernel.cuh"
+#include "lib_internal.h"
 #include "sse_kernel.cuh"
 #include "bedrock_stream_kernel.cuh"
 #include "mutate_kernel.cuh"
@@ -51,6 +52,8 @@ struct aigw_ctx {
   // host-API output (pinned)
   uint8_t* h_out = nullptr; size_t h_out_cap = 0;
   aigw_doc_result* h_res = nullptr; size_t h_res_cap = 0;
+  long small_max = -1;   // aigw_chat_set_small_batch; -1: AIGW_SMALL_MAX or 512
+  uint8_t* h_small = nullptr; size_t h_small_cap = 0;   // small-batch path: tables + bodies, read by the kernel in place (mapped pinned)
   // chat workspace (intermediates of one sub-batch) + per-stage timing events
   uint8_t* d_work = nullptr; size_t work_cap = 0;
   unsigned long long* d_used_arr = nullptr; unsigned long long* h_used_arr = nullptr; size_t used_cap = 0;  // per-chunk bump counters
@@ -121,6 +124,21 @@ static int ensure(aigw_ctx* ctx, void** p, size_t* cap, size_t want, bool host) 
 }
 #define ENSURE(p, cap, want, host) do { int _r = ensure(ctx, (void**)&(p), &(cap), (want), (host)); if (_r) return _r; } while (0)
 
+namespace aigw {
+int ctx_device(const aigw_ctx* ctx) { return ctx->device; }
+bool chat_small_fits(const aigw_backend_cfg* cfg, uint32_t len) {
+  const bool resp = cfg && (cfg->schema & 48) == AIGW_SCHEMA_RESP_AWS_BEDROCK;
+  return len > 0 && (resp ? resp_class_len(len) : len) <= kSmallMaxLen;
+}
+cudaError_t chat_small_launch(const aigw_backend_cfg* cfg, const uint8_t* in, const uint64_t* offsets, const uint32_t* lens, const uint64_t* out_slot, uint32_t n, uint8_t* out,
+                              aigw_doc_result* results, cudaStream_t st) {
+  ChatParams P; fill_params(P, cfg);
+  P.bodies = in; P.offsets = offsets; P.lens = lens; P.n = n;
+  P.out = out; P.out_capacity = 0; P.results = results; P.out_used = nullptr; P.next_doc = nullptr; P.out_bias = 0; P.doc_map = nullptr;
+  return launch_chat_small(P, 0, n, out_slot, st);
+}
+}  // namespace aigw
+
 extern "C" {
 
 const char* aigw_version(void) { return "aigw_b200 0.1 (sm_100a)"; }
@@ -166,7 +184,7 @@ void aigw_destroy(aigw_ctx* ctx) {
     cudaFree(s.d_in); cudaFree(s.d_off); cudaFree(s.d_len); cudaFree(s.d_out); cudaFree(s.d_res); cudaFree(s.d_used); cudaFree(s.d_next); cudaFreeHost(s.h_used);
     cudaEventDestroy(s.ev_h2d); cudaEventDestroy(s.ev_k0); cudaEventDestroy(s.ev_k1); cudaEventDestroy(s.ev_ctr); cudaEventDestroy(s.ev_done);
   }
-  cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_res); cudaFree(ctx->d_counters); cudaFree(ctx->d_work); cudaFree(ctx->d_used_arr); cudaFreeHost(ctx->h_used_arr);
+  cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_res); cudaFreeHost(ctx->h_small); cudaFree(ctx->d_counters); cudaFree(ctx->d_work); cudaFree(ctx->d_used_arr); cudaFreeHost(ctx->h_used_arr);
   for (auto& e2 : ctx->stage_ev) cudaEventDestroy(e2);
   cudaFree(ctx->d_sse_bytes); cudaFree(ctx->d_sse_coff); cudaFree(ctx->d_sse_first); cudaFree(ctx->d_sse_res); cudaFree(ctx->d_bs_work); cudaFree(ctx->d_bs_off[0]); cudaFree(ctx->d_bs_off[1]); cudaFreeHost(ctx->h_sres); cudaFreeHost(ctx->h_mres);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
@@ -274,6 +292,48 @@ int aigw_chat_last_profile(aigw_ctx* ctx, float stage_ms[3], int* launches) {
   return 0;
 }
 
+// Small batches (a single request, or what a batching window collects): one fused kernel, no workspace, no device copies.
+// The bodies are packed into a mapped pinned buffer the kernel reads in place, the records and results are stored straight
+// into the pinned output arenas, and the call is launch + kernel + one synchronisation.
+static int chat_small_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n, aigw_batch_out* out) {
+  uint64_t in_bytes = 0, out_bytes = 0;
+  for (uint32_t i = 0; i < n; i++) { in_bytes += (((uint64_t)lens[i] + 15u) & ~15ull) + 16; out_bytes += ((uint64_t)lens[i] + lens[i] / 4 + 528 + 15) & ~15ull; }
+  const size_t tab = (((size_t)n + 1) * 16 + (size_t)n * 4 + 63) & ~(size_t)63;
+  ENSURE(ctx->h_small, ctx->h_small_cap, tab + in_bytes + 64, true);
+  ENSURE(ctx->h_out, ctx->h_out_cap, out_bytes + 64, true);
+  ENSURE(ctx->h_res, ctx->h_res_cap, (size_t)n * sizeof(aigw_doc_result), true);
+  uint64_t* h_off = (uint64_t*)ctx->h_small; uint64_t* h_slot = h_off + n + 1; uint32_t* h_len = (uint32_t*)(h_slot + n + 1);
+  uint8_t* h_in = ctx->h_small + tab;
+  uint64_t o = 0, so = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    h_off[i] = o; h_slot[i] = so; h_len[i] = lens[i];
+    memcpy(h_in + o, bodies + offsets[i], lens[i]);
+    o += (((uint64_t)lens[i] + 15u) & ~15ull) + 16; so += ((uint64_t)lens[i] + lens[i] / 4 + 528 + 15) & ~15ull;
+  }
+  h_off[n] = o; h_slot[n] = so;
+  uint8_t* d_small = nullptr; uint8_t* d_out = nullptr; aigw_doc_result* d_res = nullptr;
+  CK(cudaHostGetDevicePointer((void**)&d_small, ctx->h_small, 0)); CK(cudaHostGetDevicePointer((void**)&d_out, ctx->h_out, 0)); CK(cudaHostGetDevicePointer((void**)&d_res, ctx->h_res, 0));
+  ChatParams P; fill_params(P, cfg);
+  P.bodies = d_small + tab; P.offsets = (const uint64_t*)d_small; P.lens = (const uint32_t*)(d_small + ((size_t)n + 1) * 16); P.n = n;
+  P.out = d_out; P.out_capacity = so; P.results = d_res; P.out_used = nullptr; P.next_doc = nullptr; P.out_bias = 0; P.doc_map = nullptr;
+  static const bool dbg = getenv("AIGW_SMALL_DBG") != nullptr;
+  static unsigned int* h_dbg = nullptr;
+  if (dbg) { if (!h_dbg) cudaHostAlloc((void**)&h_dbg, 64, cudaHostAllocDefault); P.next_doc = h_dbg; }
+  CK(cudaEventRecord(ctx->ev0, ctx->s_compute));
+  CK(launch_chat_small(P, 0, n, (const uint64_t*)d_small + n + 1, ctx->s_compute));
+  CK(cudaEventRecord(ctx->ev1, ctx->s_compute));
+  CK(cudaEventSynchronize(ctx->ev1));
+  float kms = 0; cudaEventElapsedTime(&kms, ctx->ev0, ctx->ev1);
+  if (dbg) fprintf(stderr, "small n=%u kernel %.1f us  clocks: load %u index %u walk %u emit %u\n", n, kms * 1e3f, h_dbg[0], h_dbg[1], h_dbg[2], h_dbg[3]);
+  uint64_t produced = 0;
+  for (uint32_t i = 0; i < n; i++) if (ctx->h_res[i].status == AIGW_OK) produced += ((uint64_t)ctx->h_res[i].path_len + ctx->h_res[i].body_len + 15u) & ~15ull;
+  out->results = ctx->h_res; out->out = ctx->h_out; out->out_used = so; out->h2d_bytes = in_bytes + tab; out->d2h_bytes = produced + (uint64_t)n * sizeof(aigw_doc_result);
+  out->gpu_launches = 1; out->kernel_ms = kms;
+  return 0;
+}
+
+void aigw_chat_set_small_batch(aigw_ctx* ctx, int max_docs) { if (ctx) ctx->small_max = max_docs; }
+
 int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const uint8_t* bodies, const uint64_t* offsets,
                              const uint32_t* lens, uint32_t n, aigw_batch_out* out) {
   // Three-stage pipeline over 256 MiB chunks, both PCIe directions busy at once:
@@ -285,6 +345,14 @@ int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const u
   memset(out, 0, sizeof *out);
   if (n == 0) return 0;
   CK(cudaSetDevice(ctx->device));
+  {
+    static const long env_small_max = getenv("AIGW_SMALL_MAX") ? atol(getenv("AIGW_SMALL_MAX")) : 512;   // 0 disables the fused small-batch path
+    if ((long)n <= (ctx->small_max >= 0 ? ctx->small_max : env_small_max)) {
+      const bool resp = cfg && (cfg->schema & 48) == AIGW_SCHEMA_RESP_AWS_BEDROCK;
+      uint32_t ml = 0; for (uint32_t i = 0; i < n; i++) if (lens[i] > ml) ml = lens[i];
+      if ((resp ? resp_class_len(ml) : ml) <= kSmallMaxLen) return chat_small_host(ctx, cfg, bodies, offsets, lens, n, out);
+    }
+  }
   static const bool zero_copy = getenv("AIGW_HOST_ZEROCOPY") != nullptr;
   const uint64_t kChunkBytes = 256ull << 20;
   std::vector<uint32_t> cb;  // chunk begin doc index

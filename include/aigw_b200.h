@@ -163,6 +163,12 @@ typedef struct aigw_batch_out {
 } aigw_batch_out;
 int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const uint8_t* bodies, const uint64_t* offsets,
                              const uint32_t* lens, uint32_t n, aigw_batch_out* out);
+/* Calls of at most max_docs bodies whose largest body fits the 5120-byte class run as ONE fused kernel (index + walk + emit of
+ * one document per CTA, bodies read in place from a mapped pinned buffer, records stored straight into the pinned output):
+ * this is the latency path of a single request (ext_proc's per-request call, processor_impl.go:211-295) and of a batching
+ * window.  Default 512 (AIGW_SMALL_MAX overrides); 0 sends every call through the throughput pipeline; -1 restores the default.
+ * Both paths produce the same bytes (same stage code). */
+void aigw_chat_set_small_batch(aigw_ctx* ctx, int max_docs);
 
 /* ---- OpenAI SSE response streams: usage scan (S1) + TokenUsage merge (C1) ----
  * Stream s consists of chunks [chunk_first[s], chunk_first[s+1]); chunk c is bytes
@@ -287,14 +293,22 @@ int aigw_body_mutate_host(aigw_ctx* ctx, const aigw_body_mutation* m, const uint
 
 /* ---- per-GPU request batcher: the synchronous single-request call for the cgo shim ----
  * The reference translates one request per goroutine (internal/extproc/processor_impl.go:211-398); a GPU wants batches.
- * aigw_batcher_translate is called concurrently from any number of threads, blocks until its request has been through ONE
- * aigw_chat_translate_host call shared with the requests that arrived within `window_us` of the batch's first one (or until
- * `max_batch` are queued), and returns the request's own record in `out` (`[:path][body]`, res->out_off == 0).
- * Return: 0, a CUDA error code if the batch failed, -4 if `out_cap` is too small, -5 after stop.  `cfg` strings are copied. */
+ * aigw_batcher_translate[_to] is called concurrently from any number of threads.  The caller's body is copied (by the caller's
+ * own thread) into a slot of the backend's open batch in mapped pinned memory; the batch is launched as ONE fused kernel when
+ * `max_batch` requests have joined or `window_us` after its first one, several batches are in flight at once, and the call
+ * returns the request's own record in `out` (`[:path][body]`, res->out_off == 0).  Bodies above the fused kernel's 5120-byte
+ * class go through aigw_chat_translate_host one at a time.
+ * One batcher serves several backends: aigw_batcher_start registers backend 0, aigw_batcher_add_backend returns the index of
+ * another one (up to 16; every backend has its own batches, since a launch has one schema).  `cfg` strings are copied.
+ * Return: 0 (look at res->status); -4 if `out_cap` is too small (res->body_len = the size to retry with); -5 after stop;
+ * -2 bad argument.  A failed GPU launch is NOT an error: its requests come back with status AIGW_DECLINED, so that the
+ * caller's stock path handles them. */
 typedef struct aigw_batcher aigw_batcher;
 typedef struct aigw_batcher_stats { uint64_t batches, requests; uint32_t max_batch_seen, _pad; } aigw_batcher_stats;
 int  aigw_batcher_start(aigw_ctx* ctx, const aigw_backend_cfg* cfg, uint32_t max_batch, uint32_t window_us, aigw_batcher** out);
-int  aigw_batcher_translate(aigw_batcher* b, const uint8_t* body, uint32_t len, uint8_t* out, uint32_t out_cap, aigw_doc_result* res);
+int  aigw_batcher_add_backend(aigw_batcher* b, const aigw_backend_cfg* cfg);   /* -> backend index, or < 0 */
+int  aigw_batcher_translate(aigw_batcher* b, const uint8_t* body, uint32_t len, uint8_t* out, uint32_t out_cap, aigw_doc_result* res);   /* backend 0 */
+int  aigw_batcher_translate_to(aigw_batcher* b, int backend, const uint8_t* body, uint32_t len, uint8_t* out, uint32_t out_cap, aigw_doc_result* res);
 int  aigw_batcher_get_stats(aigw_batcher* b, aigw_batcher_stats* s);
 void aigw_batcher_stop(aigw_batcher* b);
 

@@ -45,6 +45,31 @@ def test_concurrent_requests_match_oracle(gw):
             assert out == t.body and path.decode() == t.path
 
 
+def test_two_backends_and_large_bodies(gw):
+    """one batcher, two backends (each with its own batches); bodies above the fused kernel's class take the host call"""
+    from aigw_b200 import capi
+    arena, offs, lens = W.chat_corpus(4, 0, 120)
+    bodies = [bytes(arena[int(offs[i]):int(offs[i]) + int(lens[i])]) for i in range(120)]
+    big_arena, bo, bl = W.chat_corpus(4, 0, 6, target=12000, jitter=64)
+    bodies += [bytes(big_arena[int(bo[i]):int(bo[i]) + int(bl[i])]) for i in range(6)]
+    b = gw.batcher_start(capi.Context.cfg("aws-bedrock"), max_batch=32, window_us=100)
+    k = gw.batcher_add_backend(b, capi.Context.cfg("openai"))
+    assert k == 1
+    results = {}
+    def work(t):
+        for i in range(t, len(bodies), 8):
+            results[(i, 0)] = gw.batcher_translate(b, bodies[i], backend=0)
+            results[(i, 1)] = gw.batcher_translate(b, bodies[i], backend=1)
+    th = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    [t.start() for t in th]; [t.join() for t in th]
+    gw.batcher_stop(b)
+    for (i, k), (rc, status, reason, path, out, kind) in results.items():
+        t = O.chat_translate("aws-bedrock" if k == 0 else "openai", bodies[i])
+        assert rc == 0 and status == t.status, (i, k, rc, status, reason, t.status)
+        if status == 0:
+            assert out == (t.body if t.body_kind == O.BYTES else b"") and path.decode() == t.path, (i, k)
+
+
 def test_small_output_buffer_is_reported(gw):
     from aigw_b200 import capi
     b = gw.batcher_start(capi.Context.cfg("aws-bedrock"), max_batch=8, window_us=10)

@@ -29,6 +29,7 @@ int main(int argc, char** argv) {
   if (aigw_batcher_start(ctx, &cfg, max_batch, window_us, &b)) return 1;
   std::vector<std::vector<float>> lat(T);
   std::atomic<uint64_t> ok{0}, declined{0}, failed{0}, out_bytes{0};
+  std::atomic<int> first_reason{-1}, first_rc{0};
   auto worker = [&](int t, int reqs, bool record) {
     std::vector<uint8_t> out(1 << 17);
     for (int r = 0; r < reqs; r++) {
@@ -38,7 +39,7 @@ int main(int argc, char** argv) {
       const int rc = aigw_batcher_translate(b, bodies.data() + offs[i], (uint32_t)(offs[i + 1] - offs[i]), out.data(), (uint32_t)out.size(), &res);
       const float us = std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - t0).count();
       if (record) lat[t].push_back(us);
-      if (rc) failed++; else if (res.status == AIGW_OK) { ok++; out_bytes += res.path_len + res.body_len; } else declined++;
+      if (rc) { failed++; first_rc = rc; } else if (res.status == AIGW_OK) { ok++; out_bytes += res.path_len + res.body_len; } else { declined++; int e = -1; first_reason.compare_exchange_strong(e, (int)res.reason * 16 + (int)res.status); }
     }
   };
   { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(worker, t, std::max(1, R / 10), false); for (auto& x : th) x.join(); }  // warm-up
@@ -52,10 +53,10 @@ int main(int argc, char** argv) {
   std::sort(all.begin(), all.end());
   auto pct = [&](double p) { return all.empty() ? 0.f : all[(size_t)(p * (all.size() - 1))]; };
   printf("{\"threads\": %d, \"requests\": %zu, \"ok\": %llu, \"declined\": %llu, \"failed\": %llu, \"wall_s\": %.4f, \"requests_per_s\": %.1f, "
-         "\"p50_us\": %.1f, \"p90_us\": %.1f, \"p99_us\": %.1f, \"max_us\": %.1f, \"batches\": %llu, \"mean_batch\": %.2f, \"max_batch_seen\": %u, \"max_batch\": %u, \"window_us\": %u}\n",
+         "\"p50_us\": %.1f, \"p90_us\": %.1f, \"p99_us\": %.1f, \"max_us\": %.1f, \"batches\": %llu, \"mean_batch\": %.2f, \"max_batch_seen\": %u, \"max_batch\": %u, \"window_us\": %u, \"first_declined_reason_status\": [%d, %d], \"first_rc\": %d}\n",
          T, all.size(), (unsigned long long)ok.load(), (unsigned long long)declined.load(), (unsigned long long)failed.load(), wall, all.size() / wall,
          pct(0.5), pct(0.9), pct(0.99), all.empty() ? 0.f : all.back(), (unsigned long long)(s1.batches - s0.batches),
-         (s1.batches - s0.batches) ? (double)(s1.requests - s0.requests) / (double)(s1.batches - s0.batches) : 0.0, s1.max_batch_seen, max_batch, window_us);
+         (s1.batches - s0.batches) ? (double)(s1.requests - s0.requests) / (double)(s1.batches - s0.batches) : 0.0, s1.max_batch_seen, max_batch, window_us, first_reason.load() < 0 ? -1 : first_reason.load() / 16, first_reason.load() < 0 ? -1 : first_reason.load() % 16, first_rc.load());
   aigw_batcher_stop(b);
   aigw_destroy(ctx);
   return failed.load() ? 1 : 0;
