@@ -39,7 +39,7 @@ inline void cpu_relax() { __builtin_ia32_pause(); }
 inline int64_t now_ns() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 constexpr uint32_t kInStride = ((aigw::kSmallMaxLen + 15u) & ~15u) + 16;                      // one input slot
-constexpr uint32_t kOutStride = ((aigw::kSmallMaxLen + aigw::kSmallMaxLen / 4 + 528 + 15) & ~15u);   // one output slot
+constexpr uint32_t kOutStride = ((aigw::kSmallMaxLen * 3 + 1024 + 15) & ~15u);   // one output slot (a record that does not fit is DECLINED)
 constexpr int kRing = 4;          // batch buffers per lane
 constexpr int kMaxLanes = 16;
 enum : uint64_t { ST_FREE = 0, ST_OPEN = 1, ST_CLOSED = 2 };

@@ -177,7 +177,9 @@ namespace aigw {
   X(L_GEM_SEED, "\"seed\":")                                                                   \
   X(L_GEM_SYS_OPEN, ",\"system_instruction\":{\"parts\":[")                                    \
   X(L_GEM_SYS_CLOSE, "]}")                                                                     \
-  X(L_EM_LAST, "}]")
+  X(L_EM_LAST, "}]")                                                                            \
+  X(L_TITAN_OPEN, "{\"inputText\":")                                                          \
+  X(L_TITAN_DIMS, ",\"dimensions\":")
 
 enum LitId : int {
 #define X(name, text) name,

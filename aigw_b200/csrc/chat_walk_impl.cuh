@@ -935,6 +935,26 @@ struct Walker {
     if (model >= 0) { if (d.str_has_backslash(model)) { decline(AIGW_R_ESCAPE); return; } model_off = d.str_off(model); model_len = d.str_len(model); }
     const bool need_model = P->override_len != 0;
     if (need_model) for (uint32_t i = 0; i < P->override_len; i++) { const uint32_t c = (uint8_t)P->override_model[i]; if (c < 0x20 || c > 0x7f || c == '"' || c == '\\') { decline(AIGW_R_UNSUPPORTED_FIELD); return; } }
+    // ---- Amazon Titan through InvokeModel (openai_awsbedrock_embeddings.go:35-74): one input text, optional dimensions
+    if (base == AIGW_SCHEMA_AWS_BEDROCK) {
+      int text = -1; bool empty_text = false;
+      if (kind == 1) text = input;
+      else if (kind == 2) {
+        int cnt = 0, first_el = -1;
+        for (int q = input + 1; d.ty(q) != ']'; q = d.after(q)) { if (cnt == 0) first_el = q; cnt++; }
+        if (cnt != 1) { pend(AIGW_R_E422_CONTENT); return; }   // "AWS Bedrock Titan does not support batch embeddings"
+        if (is_null(first_el)) empty_text = true; else text = first_el;
+      } else { pend(AIGW_R_E422_CONTENT); return; }            // "unsupported input type"
+      pl.lit(L_PATH_MODEL); emit_model_tok(model, true); pl.lit(L_AN_INVOKE);
+      if (bad()) return;
+      path_len = pl.olen;
+      body_kind = AIGW_BODY_BYTES;
+      pl.lit(L_TITAN_OPEN);
+      if (empty_text) pl.lit(L_EMPTY_STR); else emit_str(text);
+      if (dims >= 0) { pl.lit(L_TITAN_DIMS); const uint32_t o = d.tok(dims); pl.src(d, o, d.scalar_end(dims) - o); }
+      pl.lit(L_RBRACE);
+      return;
+    }
     // ---- :path
     if (base == AIGW_SCHEMA_OPENAI) emit_cfg_text(P->openai_path, P->prefix_len);
     else {
@@ -1474,10 +1494,11 @@ struct Walker {
   }
 
   // raw model bytes (override or request model) appended as-is (GCP paths) or url.PathEscape'd (AWS paths)
-  __device__ void emit_model(const Top& t, bool escape) {
+  __device__ void emit_model(const Top& t, bool escape) { emit_model_tok(t.model, escape); }
+  __device__ void emit_model_tok(int model_tok, bool escape) {
     const uint8_t* mp; uint32_t ml;
     if (P->override_len) { mp = (const uint8_t*)P->override_model; ml = P->override_len; }
-    else if (t.model >= 0) { mp = d.s + d.str_off(t.model); ml = d.str_len(t.model); }
+    else if (model_tok >= 0) { mp = d.s + d.str_off(model_tok); ml = d.str_len(model_tok); }
     else return;
     if (sc.n + 3 * ml + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
     uint8_t* o = sc.p + sc.n; uint32_t w = 0;

@@ -293,11 +293,13 @@ int aigw_chat_last_profile(aigw_ctx* ctx, float stage_ms[3], int* launches) {
 }
 
 // Small batches (a single request, or what a batching window collects): one fused kernel, no workspace, no device copies.
+// Every body owns a fixed output slot of 3 x its length + 1 KiB (the embeddings -> Vertex instances translation expands short
+// inputs up to 5x; a record that does not fit is DECLINED with AIGW_R_ARENA_FULL, never truncated).
 // The bodies are packed into a mapped pinned buffer the kernel reads in place, the records and results are stored straight
 // into the pinned output arenas, and the call is launch + kernel + one synchronisation.
 static int chat_small_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n, aigw_batch_out* out) {
   uint64_t in_bytes = 0, out_bytes = 0;
-  for (uint32_t i = 0; i < n; i++) { in_bytes += (((uint64_t)lens[i] + 15u) & ~15ull) + 16; out_bytes += ((uint64_t)lens[i] + lens[i] / 4 + 528 + 15) & ~15ull; }
+  for (uint32_t i = 0; i < n; i++) { in_bytes += (((uint64_t)lens[i] + 15u) & ~15ull) + 16; out_bytes += ((uint64_t)lens[i] * 3 + 1024 + 15) & ~15ull; }
   const size_t tab = (((size_t)n + 1) * 16 + (size_t)n * 4 + 63) & ~(size_t)63;
   ENSURE(ctx->h_small, ctx->h_small_cap, tab + in_bytes + 64, true);
   ENSURE(ctx->h_out, ctx->h_out_cap, out_bytes + 64, true);
@@ -308,7 +310,7 @@ static int chat_small_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const uin
   for (uint32_t i = 0; i < n; i++) {
     h_off[i] = o; h_slot[i] = so; h_len[i] = lens[i];
     memcpy(h_in + o, bodies + offsets[i], lens[i]);
-    o += (((uint64_t)lens[i] + 15u) & ~15ull) + 16; so += ((uint64_t)lens[i] + lens[i] / 4 + 528 + 15) & ~15ull;
+    o += (((uint64_t)lens[i] + 15u) & ~15ull) + 16; so += ((uint64_t)lens[i] * 3 + 1024 + 15) & ~15ull;
   }
   h_off[n] = o; h_slot[n] = so;
   uint8_t* d_small = nullptr; uint8_t* d_out = nullptr; aigw_doc_result* d_res = nullptr;

@@ -55,7 +55,8 @@ enum aigw_schema { AIGW_SCHEMA_OPENAI = 0, AIGW_SCHEMA_AWS_BEDROCK = 1, AIGW_SCH
                     * OpenAI / Azure passthrough translators internal/translator/openai_embeddings.go:38-59,
                     * openai_azureopenai_embeddings.go:36-61 or the Vertex predict translator openai_gcpvertexai_embeddings.go:46-180):
                     * AIGW_SCHEMA_EMBEDDINGS | base schema.  openai_prefix / api_version / model_name_override as for chat. */
-                   AIGW_SCHEMA_EMBEDDINGS = 32, AIGW_SCHEMA_EMB_OPENAI = 32, AIGW_SCHEMA_EMB_AZURE_OPENAI = 34, AIGW_SCHEMA_EMB_GCP_VERTEX = 35 };
+                   AIGW_SCHEMA_EMBEDDINGS = 32, AIGW_SCHEMA_EMB_OPENAI = 32, AIGW_SCHEMA_EMB_AWS_BEDROCK = 33 /* Amazon Titan through InvokeModel,
+                    * openai_awsbedrock_embeddings.go:35-74 */, AIGW_SCHEMA_EMB_AZURE_OPENAI = 34, AIGW_SCHEMA_EMB_GCP_VERTEX = 35 };
 
 /* Why a body was declined / rejected (diagnostics; stable numbering). */
 enum aigw_reason {

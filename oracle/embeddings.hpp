@@ -89,7 +89,7 @@ inline void emb_instances_from_item(const EmbItem& it, std::vector<EmbItem>& out
   }
 }
 
-// schema: SCHEMA_OPENAI or SCHEMA_GCP_VERTEX.  prefix: OpenAI path prefix ("v1").
+// schema: SCHEMA_OPENAI, SCHEMA_AZURE_OPENAI, SCHEMA_AWS_BEDROCK (Titan) or SCHEMA_GCP_VERTEX.  prefix: OpenAI path prefix ("v1").
 inline TranslateResult embeddings_translate(int schema, std::string_view body, const std::string& model_override, const std::string& prefix, bool force) {
   TranslateResult res;
   Value root; std::string perr;
@@ -109,6 +109,22 @@ inline TranslateResult embeddings_translate(int schema, std::string_view body, c
     res.headers.push_back({":path", path});
     if (force && (!has || nb.empty())) { nb.assign(body); has = true; }
     if (has && !nb.empty()) { res.body_kind = BYTES; res.body = nb; res.headers.push_back({"content-length", std::to_string(nb.size())}); }
+    return res;
+  }
+  if (schema == SCHEMA_AWS_BEDROCK) {
+    // Amazon Titan Embed Text through InvokeModel (openai_awsbedrock_embeddings.go:35-74): one input text, optional dimensions
+    std::string text;
+    if (r.kind == EmbReq::STR) text = r.str;
+    else if (r.kind == EmbReq::STRS) {
+      if (r.strs.size() != 1) { res.err = invalid("invalid request body: AWS Bedrock Titan does not support batch embeddings (got " + std::to_string(r.strs.size()) + " inputs)"); return res; }
+      text = r.strs[0];
+    } else { res.err = invalid("invalid request body: unsupported input type"); return res; }
+    std::string o = "{\"inputText\":"; oj::enc_str(o, text);
+    if (r.dimensions) o += ",\"dimensions\":" + std::to_string(*r.dimensions);   // *int, omitempty: forwarded whenever present, zero and negatives included
+    o.push_back('}');
+    res.body_kind = BYTES; res.body = o;
+    res.headers.push_back({":path", "/model/" + path_escape(res.request_model) + "/invoke"});
+    res.headers.push_back({"content-length", std::to_string(o.size())});
     return res;
   }
   if (schema != SCHEMA_GCP_VERTEX) { res.err = Error{DECLINED, "schema not restated yet"}; return res; }

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 CASES = json.load(open(os.path.join(HERE, "golden", "testupstream_cases.json"), encoding="utf-8"))["cases"]
 EMB_CASES = [c for c in CASES if c.get("path") == "/v1/embeddings" and "requestBody" in c]
-GPU_SCHEMA = {"openai": "emb-openai", "azure-openai": "emb-azure-openai", "gcp-vertexai": "emb-gcp-vertexai"}
+GPU_SCHEMA = {"openai": "emb-openai", "azure-openai": "emb-azure-openai", "gcp-vertexai": "emb-gcp-vertexai", "aws-bedrock": "emb-aws-bedrock"}
 
 
 @pytest.fixture(scope="module")
@@ -94,15 +94,15 @@ ODD = [
 ]
 
 
-@pytest.mark.parametrize("schema", ["openai", "azure-openai", "gcp-vertexai"])
+@pytest.mark.parametrize("schema", ["openai", "azure-openai", "gcp-vertexai", "aws-bedrock"])
 def test_parity_odd_bodies(gw, schema):
     assert check(gw, schema, ODD) >= 10
     assert check(gw, schema, ODD, model_override="override-model") >= 10
-    if schema != "gcp-vertexai":
+    if schema not in ("gcp-vertexai", "aws-bedrock"):
         assert check(gw, schema, ODD, force=True) >= 10
 
 
-@pytest.mark.parametrize("schema", ["openai", "azure-openai", "gcp-vertexai"])
+@pytest.mark.parametrize("schema", ["openai", "azure-openai", "gcp-vertexai", "aws-bedrock"])
 def test_parity_corpus(gw, schema):
     rng = np.random.default_rng(31)
     bodies = [emb_body(rng) for _ in range(3000)]
@@ -120,3 +120,33 @@ def test_large_inputs(gw):
     assert len(big) > 65536
     g, = run(gw, "gcp-vertexai", [big])
     assert g["status"] == 4
+
+
+# the reference's own table for the Titan translator (internal/translator/openai_awsbedrock_embeddings_test.go:25-130): request as the
+# test marshals it, expected :path, substrings the body must / must not contain, or the 422
+TITAN = [
+    (b'{"input":"hello world","model":"amazon.titan-embed-text-v1:2"}', "", "/model/amazon.titan-embed-text-v1:2/invoke", [b'"inputText":"hello world"'], []),
+    (b'{"input":"hello world","model":"amazon.titan-embed-text-v2:0"}', "", "/model/amazon.titan-embed-text-v2:0/invoke", [b'"inputText":"hello world"'], []),
+    (b'{"input":["hello world"],"model":"amazon.titan-embed-text-v2:0"}', "", "/model/amazon.titan-embed-text-v2:0/invoke", [b'"inputText":"hello world"'], []),
+    (b'{"input":["first","second"],"model":"amazon.titan-embed-text-v2:0"}', "", None, [], []),
+    (b'{"input":[],"model":"amazon.titan-embed-text-v2:0"}', "", None, [], []),
+    (b'{"input":"test","model":"amazon.titan-embed-text-v1:2"}', "", "/model/amazon.titan-embed-text-v1:2/invoke", [b'"inputText":"test"'], [b'"dimensions"', b'"normalize"', b'"embeddingTypes"']),
+    (b'{"input":"test","model":"amazon.titan-embed-text-v2:0","dimensions":256}', "", "/model/amazon.titan-embed-text-v2:0/invoke", [b'"inputText":"test"', b'"dimensions":256'], []),
+    (b'{"input":"test","model":"amazon.titan-embed-text-v2:0"}', "amazon.titan-embed-text-v1:2", "/model/amazon.titan-embed-text-v1:2/invoke", [b'"inputText":"test"'], []),
+    (b'{"input":"escape test","model":"my model v1"}', "", "/model/my%20model%20v1/invoke", [b'"inputText":"escape test"'], []),
+]
+
+
+def test_titan_reference_table(gw):
+    for body, override, path, must, must_not in TITAN:
+        g, = run(gw, "aws-bedrock", [body], model_override=override or None)
+        t = O.embeddings_translate("aws-bedrock", body, model_override=override)
+        if path is None:
+            assert g["status"] == 2 and t.status == 2, (body, g, t.status)   # ErrInvalidRequestBody
+            continue
+        assert g["status"] == 0 and g["path"].decode() == path == t.path, (body, g, t.path)
+        assert g["body"] == t.body
+        for m in must:
+            assert m in g["body"]
+        for m in must_not:
+            assert m not in g["body"]

@@ -465,3 +465,18 @@ def test_gemini_response_goldens():
         assert got == exp, c["name"]
         n += 1
     assert n >= 2
+
+
+def test_titan_embeddings_reference_table():
+    """openai_awsbedrock_embeddings_test.go:25-130: path, body substrings and the 422s of the Titan translator"""
+    import test_embeddings_gpu as E
+    for body, override, path, must, must_not in E.TITAN:
+        t = O.embeddings_translate("aws-bedrock", body, model_override=override)
+        if path is None:
+            assert t.status == 2
+            continue
+        assert t.status == 0 and t.path == path
+        for m in must:
+            assert m in t.body
+        for m in must_not:
+            assert m not in t.body
