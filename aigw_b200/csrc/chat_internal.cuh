@@ -85,6 +85,17 @@ enum RKid : uint8_t {
   X("id", RK_id) X("model", RK_model) X("stop_reason", RK_stop_reason) X("thinking", RK_thinking) X("data", RK_data) X("input_tokens", RK_input_tokens) X("output_tokens", RK_output_tokens) \
   X("cache_read_input_tokens", RK_cache_read_input_tokens) X("cache_creation_input_tokens", RK_cache_creation_input_tokens)
 
+// /v1/messages requests (P.schema & AIGW_SCHEMA_MESSAGES): the members of anthropic.MessagesRequest the restated subset knows
+// (internal/apischema/anthropic/anthropic.go:26-140); every other key has id 0 and declines the body.  Values use AIGW_VALS.
+enum MKid : uint8_t {
+  MK_NONE = 0, MK_model, MK_max_tokens, MK_messages, MK_stream, MK_system, MK_temperature, MK_top_p, MK_top_k, MK_stop_sequences, MK_metadata, MK_user_id, MK_role, MK_content,
+  MK_type, MK_text, MK_cache_control, MK_anthropic_version, MK_COUNT
+};
+#define AIGW_MKEYS(X) \
+  X("model", MK_model) X("max_tokens", MK_max_tokens) X("messages", MK_messages) X("stream", MK_stream) X("system", MK_system) X("temperature", MK_temperature) X("top_p", MK_top_p) \
+  X("top_k", MK_top_k) X("stop_sequences", MK_stop_sequences) X("metadata", MK_metadata) X("user_id", MK_user_id) X("role", MK_role) X("content", MK_content) X("type", MK_type) \
+  X("text", MK_text) X("cache_control", MK_cache_control) X("anthropic_version", MK_anthropic_version)
+
 static constexpr int kKeySlots = 128, kValSlots = 32, kMaxIdLen = 28, kIdWords = 7;
 // slot = { seven little-endian words of the string zero-padded to 28 bytes, len | id << 8 }
 struct IdSlot { uint32_t w[kIdWords]; uint32_t meta; };
@@ -134,6 +145,18 @@ constexpr IdTables make_resp_id_tables() {
 }
 static_assert(id_max_probe(make_resp_id_tables().key, kKeySlots) <= 6, "response id hash table needs more than 6 probes");
 static __device__ __constant__ IdTables c_ids_resp = make_resp_id_tables();
+constexpr IdTables make_msg_id_tables() {
+  IdTables t{};
+#define X(lit, idv) id_insert(t.key, kKeySlots, lit, idv);
+  AIGW_MKEYS(X)
+#undef X
+#define X(lit, idv) id_insert(t.val, kValSlots, lit, idv);
+  AIGW_VALS(X)
+#undef X
+  return t;
+}
+static_assert(id_max_probe(make_msg_id_tables().key, kKeySlots) <= 6, "messages id hash table needs more than 6 probes");
+static __device__ __constant__ IdTables c_ids_msg = make_msg_id_tables();
 
 // id of a short string (1 ≤ n ≤ kMaxIdLen) held in shared memory, against the key or the value table (also in shared
 // memory).  Straight-line code: seven aligned word loads, funnel shifts, length mask, multiplicative hash, ≤ 4 probes.

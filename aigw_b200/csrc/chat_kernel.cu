@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
   IdTables* s_ids = (IdTables*)smem;
   uint64_t* s_bar = (uint64_t*)(smem + sizeof(IdTables));
   {
-    const uint32_t* src = (const uint32_t*)((P.schema & 48) == AIGW_SCHEMA_RESP_AWS_BEDROCK ? &c_ids_resp : &c_ids);
+    const uint32_t* src = (const uint32_t*)((P.schema & AIGW_SCHEMA_MESSAGES) ? &c_ids_msg : (P.schema & 48) == AIGW_SCHEMA_RESP_AWS_BEDROCK ? &c_ids_resp : &c_ids);
     for (uint32_t i = threadIdx.x; i < sizeof(IdTables) / 4; i += blockDim.x) ((uint32_t*)s_ids)[i] = src[i];
   }
   if (threadIdx.x == 0) { for (int w = 0; w < WARPS; w++) mbar_init(&s_bar[w], 1); mbar_fence_init(); }
@@ -84,13 +84,14 @@ __global__ void __launch_bounds__(WARPS * 32) chat_index_kernel(const __grid_con
     // the next document starts its way from DRAM to L2 now (its location was loaded before this one's copy was issued)
     if (lane == 0 && nlen && nlen <= (uint32_t)MAXD && (reinterpret_cast<uintptr_t>(ng) & 15u) == 0) bulk_prefetch_l2(ng, (nlen + 15u) & ~15u);
     // ---- stages 2 + 2.5: structural index (chat_stage.cuh)
-    const uint32_t ntok = index_doc<MAXD>(s_in, len, lane, s_tw, s_bs, s_nc, s_ids);
-    if (ntok & 0x80000000u) { if (lane == 0) { wp.ntok[li] = ntok; atomicAdd(&wp.bins[0], 1u); } AIGW_NEXT_DOC(); continue; }
+    const uint32_t ntw = index_doc<MAXD>(s_in, len, lane, s_tw, s_bs, s_nc, s_ids);
+    if (ntw & 0x80000000u) { if (lane == 0) { wp.ntok[li] = ntw; atomicAdd(&wp.bins[0], 1u); } AIGW_NEXT_DOC(); continue; }
+    const uint32_t ntok = ntw & 0x3fffffffu;
     // ---- write the token words out, coalesced; histogram of token counts for the shape sort
     {
       uint32_t* gt = wp.tw + (size_t)li * C::kTok;
       for (uint32_t i = lane; i < ntok; i += 32) gt[i] = s_tw[i];
-      if (lane == 0) { wp.ntok[li] = ntok; atomicAdd(&wp.bins[bin_of(ntok)], 1u); }
+      if (lane == 0) { wp.ntok[li] = ntw; atomicAdd(&wp.bins[bin_of(ntok)], 1u); }
     }
     __syncwarp();
     AIGW_NEXT_DOC();

@@ -179,7 +179,9 @@ namespace aigw {
   X(L_GEM_SYS_CLOSE, "]}")                                                                     \
   X(L_EM_LAST, "}]")                                                                            \
   X(L_TITAN_OPEN, "{\"inputText\":")                                                          \
-  X(L_TITAN_DIMS, ",\"dimensions\":")
+  X(L_TITAN_DIMS, ",\"dimensions\":")                                                         \
+  X(L_MSG_PATH, "/v1/messages")                                                                \
+  X(L_MSG_VERSION_MEMBER, "\"anthropic_version\":")
 
 enum LitId : int {
 #define X(name, text) name,

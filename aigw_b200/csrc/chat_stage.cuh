@@ -23,7 +23,7 @@ __device__ __forceinline__ aigw_doc_result blank_result(uint32_t len) {
   res.model_off = 0; res.model_len = 0; res.body_kind = AIGW_BODY_UNCHANGED; res.flags = 0; res.in_len = len; res._pad = 0;
   return res;
 }
-__device__ __forceinline__ uint32_t bin_of(uint32_t w) { return (w & 0x80000000u) ? 0u : (w < (uint32_t)kBins ? w : (uint32_t)kBins - 1u); }
+__device__ __forceinline__ uint32_t bin_of(uint32_t w) { const uint32_t n = w & 0x3fffffffu; return (w & 0x80000000u) ? 0u : (n < (uint32_t)kBins ? n : (uint32_t)kBins - 1u); }
 
 // per-byte equality against a 7-bit constant as a most-significant-bit mask (0x80 per matching byte); z = w & 0x7f7f7f7f
 __device__ __forceinline__ uint32_t eq_msb(uint32_t w, uint32_t z, uint32_t c4) { return ~(((z ^ c4) + 0x7f7f7f7fu) | w) & 0x80808080u; }
@@ -37,7 +37,8 @@ __device__ __forceinline__ uint32_t nib_from_msb(uint32_t t) { return (t * 0x002
 // messages costs one pass of ~12 instructions instead of a 28-trip single-lane loop.
 
 // ---- stages 2 + 2.5 of one document, by one warp: structural index of the body staged at s_in[0, len) into token words
-// s_tw[0, ntok) (position | byte | id / run length | escape flags).  Returns ntok, or 0x80000000 | aigw_reason.
+// s_tw[0, ntok) (position | byte | id / run length | escape flags).  Returns ntok (| bit 30: whitespace outside strings), or
+// 0x80000000 | aigw_reason.
 // s_bs: kTok halfwords (running backslash counts, later the lookup list); s_nc: one word per 1 KB round.
 template <int MAXD>
 __device__ __forceinline__ uint32_t index_doc(const uint8_t* s_in, uint32_t len, int lane, uint32_t* s_tw, uint16_t* s_bs, uint32_t* s_nc, const IdTables* s_ids) {
@@ -48,6 +49,7 @@ __device__ __forceinline__ uint32_t index_doc(const uint8_t* s_in, uint32_t len,
   uint32_t ntok = 0, bs_run = 0;
   uint32_t flags = 0;  // bit0 ctrl in string, bit1 bad escape, bit2 token overflow
   uint32_t any_nc = 0; // some round holds a valid escape the encoder re-spells (warp-uniform)
+  uint32_t ws_any = 0; // whitespace outside strings (per lane; reduced at the end)
   for (uint32_t r = 0; r < rounds; r++) {
     const uint32_t rbase = r << 10;
     const uint32_t base = rbase + (lane << 5);
@@ -114,6 +116,7 @@ __device__ __forceinline__ uint32_t index_doc(const uint8_t* s_in, uint32_t len,
     // bytes outside strings: structural characters are tokens, everything that is neither structural nor whitespace is a
     // scalar character (a control character other than \t \n \r lands there and fails the scalar grammar in the walk)
     const uint32_t outside = ~ps & ~uq & valid;
+    ws_any |= outside & bc.ws;
     uint32_t mtok = uq | (bc.op & outside);
     const uint32_t msc = outside & ~bc.op & ~bc.ws;
     {
@@ -220,7 +223,8 @@ __device__ __forceinline__ uint32_t index_doc(const uint8_t* s_in, uint32_t len,
     }
     __syncwarp();
   }
-  return ntok;
+  // bit 30: some byte outside strings is whitespace (the /v1/messages planner needs to know whether the body is compact)
+  return ntok | (__any_sync(FULL, ws_any != 0) ? 0x40000000u : 0u);
 }
 
 static constexpr int kEmitTile = 256;   // chunks per tile of the op-start table

@@ -17,6 +17,7 @@ namespace oracle { TranslateResult gemini_request_body(const ChatReq& r, const s
 #include "sha256.hpp"
 #include "embeddings.hpp"
 #include "mutate.hpp"
+#include "messages.hpp"
 #include "stream.hpp"
 #include "translate.hpp"
 
@@ -59,6 +60,17 @@ void oracle_embeddings_translate(int schema, const char* body, uint64_t len, con
   TranslateResult r = embeddings_translate(schema, std::string_view(body, len), model_override ? model_override : "", prefix ? prefix : "", force != 0);
   memset(out, 0, sizeof *out);
   out->status = r.err.status; out->body_kind = r.body_kind; out->stream = 0; out->has_mutated = 0;
+  std::string path; for (auto& h : r.headers) if (h.name == ":path") path = h.value;
+  out->body = dup(r.body); out->body_len = r.body.size();
+  out->path = dup(path); out->path_len = path.size();
+  out->model = dup(r.model); out->model_len = r.model.size();
+  out->err = dup(r.err.msg); out->err_len = r.err.msg.size();
+  out->mutated = dup(""); out->mutated_len = 0;
+}
+void oracle_messages_translate(int schema, const char* body, uint64_t len, const char* model_override, const char* api_version, int force, oracle_result* out) {
+  TranslateResult r = messages_translate(schema, std::string_view(body, len), model_override ? model_override : "", api_version ? api_version : "", force != 0);
+  memset(out, 0, sizeof *out);
+  out->status = r.err.status; out->body_kind = r.body_kind; out->stream = r.stream ? 1 : 0; out->has_mutated = 0;
   std::string path; for (auto& h : r.headers) if (h.name == ":path") path = h.value;
   out->body = dup(r.body); out->body_len = r.body.size();
   out->path = dup(path); out->path_len = path.size();
