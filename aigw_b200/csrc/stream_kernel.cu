@@ -676,6 +676,146 @@ __device__ void step_gemini_buffered(StreamSlot& S, const StreamStep& st, uint8_
   if (status) { S.flags |= SF_DEAD; S.dead_status = (uint32_t)status; S.dead_reason = w.ovf ? AIGW_R_OUT_SPACE : AIGW_R_UNSUPPORTED_FIELD; R.status = (uint8_t)status; R.reason = (uint8_t)S.dead_reason; }
 }
 
+// ------------------------------------------------------------------ S1 variant: native Anthropic SSE, usage scan only
+// (anthropicToAnthropicTranslator.ResponseBody stream branch, extractUsageFromBufferEvent / reflectStreamingEvent /
+//  updateTotalTokens, internal/translator/anthropic_anthropic.go:86-101,133-201; MessagesStreamChunk.UnmarshalJSON,
+//  internal/apischema/anthropic/anthropic.go:1696-1748).  The body passes through untouched.  Only message_start and
+//  message_delta change the state; they are decoded over the subset include/aigw_b200.h names, anything else kills the
+//  stream with DECLINED (the content-block unions are not restated here).
+struct NUsage { long long in, out, rd, cr; };
+// a token count: integer literal (optional '-'), magnitude below 2^31; null counts as 0.  false: outside the subset
+__device__ bool n_count(const uint8_t* p, int vs, int ve, long long& out) {
+  out = 0;
+  if (p[vs] == 'n') return true;
+  int i = vs; bool neg = false;
+  if (p[i] == '-') { neg = true; i++; }
+  if (i >= ve) return false;
+  long long x = 0;
+  for (; i < ve; i++) { const uint32_t c = p[i] - '0'; if (c > 9u) return false; x = x * 10 + c; if (x >= (1ll << 31)) return false; }
+  out = neg ? -x : x;
+  return true;
+}
+__device__ __forceinline__ bool n_str_or_null(const uint8_t* p, int vs) { return p[vs] == '"' || p[vs] == 'n'; }
+__device__ bool n_usage(const uint8_t* p, int vs, int ve, NUsage& u) {
+  if (p[vs] != '{') return false;
+  int i = vs + 1, ks, kl, a, b; bool kesc; uint32_t seen = 0;
+  while (next_member(p, i, ve, ks, kl, kesc, a, b)) {
+    if (kesc) return false;
+    const uint8_t* k = p + ks;
+    const uint32_t bit = EQ(k, (uint32_t)kl, "input_tokens") ? 1u : EQ(k, (uint32_t)kl, "output_tokens") ? 2u : EQ(k, (uint32_t)kl, "cache_read_input_tokens") ? 4u
+                         : EQ(k, (uint32_t)kl, "cache_creation_input_tokens") ? 8u : 0u;
+    if (!bit) continue;
+    if (seen & bit) return false;
+    seen |= bit;
+    long long x;
+    if (!n_count(p, a, b, x)) return false;
+    if (bit == 1u) u.in = x; else if (bit == 2u) u.out = x; else if (bit == 4u) u.rd = x; else u.cr = x;
+  }
+  return true;
+}
+// one `data: ` payload: 0 handled or ignored, 1 outside the subset
+__device__ int native_event(StreamSlot& S, const uint8_t* p, int n) {
+  int e = skip_any(p, 0, n);
+  if (e < 0) return 0;
+  e = skipws(p, e, n);
+  if (e != n) return 0;                                   // not one JSON value: the line is skipped
+  int r0 = skipws(p, 0, n);
+  if (p[r0] != '{') return 0;                             // no "type" to find
+  int i = r0 + 1, ks, kl, a, b; bool kesc;
+  int ty_s = -1, ty_e = 0, msg_s = -1, msg_e = 0, us_s = -1, us_e = 0, dl_s = -1, dl_e = 0; uint32_t seen = 0;
+  while (next_member(p, i, n, ks, kl, kesc, a, b)) {
+    if (kesc) return 1;
+    const uint8_t* k = p + ks;
+    const uint32_t bit = EQ(k, (uint32_t)kl, "type") ? 1u : EQ(k, (uint32_t)kl, "message") ? 2u : EQ(k, (uint32_t)kl, "usage") ? 4u : EQ(k, (uint32_t)kl, "delta") ? 8u : 0u;
+    if (!bit) continue;
+    if (seen & bit) { if (seen & 1u) return 1; seen |= 16u; continue; }   // a repeated member: decided below once the type is known
+    seen |= bit;
+    if (bit == 1u) { ty_s = a; ty_e = b; } else if (bit == 2u) { msg_s = a; msg_e = b; } else if (bit == 4u) { us_s = a; us_e = b; } else { dl_s = a; dl_e = b; }
+  }
+  if (ty_s < 0) return 0;                                 // "missing type field in stream event"
+  if (p[ty_s] != '"') return 1;
+  if (seen & 16u) return 1;
+  const uint8_t* t = p + ty_s + 1; const uint32_t tl = (uint32_t)(ty_e - ty_s - 2);
+  for (uint32_t k = 0; k < tl; k++) if (t[k] == '\\') return 1;
+  if (EQ(t, tl, "message_start")) {
+    if (msg_s < 0 || p[msg_s] == 'n') return 0;
+    if (p[msg_s] != '{') return 1;
+    int j = msg_s + 1; uint32_t ms = 0; int model_s = -1, model_e = 0, mus_s = -1, mus_e = 0;
+    while (next_member(p, j, msg_e, ks, kl, kesc, a, b)) {
+      if (kesc) return 1;
+      const uint8_t* k = p + ks; const uint32_t l = (uint32_t)kl;
+      const uint32_t bit = EQ(k, l, "id") ? 1u : EQ(k, l, "stop_reason") ? 2u : EQ(k, l, "stop_sequence") ? 4u : EQ(k, l, "model") ? 8u : EQ(k, l, "type") ? 16u : EQ(k, l, "role") ? 32u
+                           : EQ(k, l, "content") ? 64u : EQ(k, l, "usage") ? 128u : 0u;
+      if (!bit) continue;
+      if (ms & bit) return 1;
+      ms |= bit;
+      if (bit <= 4u) { if (!n_str_or_null(p, a)) return 1; }
+      else if (bit == 8u) { if (!n_str_or_null(p, a)) return 1; if (p[a] == '"') { model_s = a + 1; model_e = b - 1; } }
+      else if (bit == 16u) { if (!(p[a] == '"' && EQ(p + a + 1, (uint32_t)(b - a - 2), "message"))) return 1; }
+      else if (bit == 32u) { if (!(p[a] == '"' && EQ(p + a + 1, (uint32_t)(b - a - 2), "assistant"))) return 1; }
+      else if (bit == 64u) { if (p[a] != 'n') { if (p[a] != '[') return 1; const int q = skipws(p, a + 1, b); if (p[q] != ']') return 1; } }
+      else { if (p[a] != 'n') { mus_s = a; mus_e = b; } }
+    }
+    NUsage u{0, 0, 0, 0};
+    if (mus_s >= 0 && !n_usage(p, mus_s, mus_e, u)) return 1;
+    if (mus_s >= 0 && (u.in < 0 || u.out < 0 || u.rd < 0 || u.cr < 0 || u.in + u.rd + u.cr >= (1ll << 31) || u.in + u.rd + u.cr + u.out >= (1ll << 31))) return 1;
+    if (model_s >= 0 && model_e > model_s) {
+      const uint32_t ml = (uint32_t)(model_e - model_s);
+      if (ml > sizeof S.rmodel) return 1;
+      for (uint32_t k = 0; k < ml; k++) { if (p[model_s + k] == '\\') return 1; S.rmodel[k] = (char)p[model_s + k]; }
+      S.rmodel_len = ml;
+    }
+    if (mus_s >= 0) {   // ExtractTokenUsageFromExplicitCaching + Override (metrics.go:292-307)
+      S.usage.input = (uint32_t)(u.in + u.rd + u.cr); S.usage.output = (uint32_t)u.out; S.usage.total = S.usage.input + S.usage.output;
+      S.usage.cached = (uint32_t)u.rd; S.usage.cache_creation = (uint32_t)u.cr; S.usage.mask |= 31u;
+    }
+    return 0;
+  }
+  if (EQ(t, tl, "message_delta")) {
+    NUsage u{0, 0, 0, 0};
+    if (us_s >= 0 && p[us_s] != 'n' && !n_usage(p, us_s, us_e, u)) return 1;
+    if (dl_s >= 0 && p[dl_s] != 'n') {
+      if (p[dl_s] != '{') return 1;
+      int j = dl_s + 1; uint32_t ds = 0;
+      while (next_member(p, j, dl_e, ks, kl, kesc, a, b)) {
+        if (kesc) return 1;
+        const uint32_t bit = EQ(p + ks, (uint32_t)kl, "stop_reason") ? 1u : EQ(p + ks, (uint32_t)kl, "stop_sequence") ? 2u : 0u;
+        if (!bit) continue;
+        if (ds & bit) return 1;
+        ds |= bit;
+        if (!n_str_or_null(p, a)) return 1;
+      }
+    }
+    if (u.out >= 0) { S.usage.output = (uint32_t)u.out; S.usage.mask |= 2u; }
+    return 0;
+  }
+  return 0;
+}
+__device__ void step_anthropic_native(StreamSlot& S, const StreamStep& st, uint8_t* out, aigw_chunk_result& R) {
+  const uint8_t* b = S.buf; const uint32_t n = S.end;
+  uint32_t pos = 0; int status = 0;
+  for (;;) {
+    uint32_t nl = pos; while (nl < n && b[nl] != '\n') nl++;
+    if (nl >= n) break;
+    const uint8_t* line = b + pos; const uint32_t ll = nl - pos;
+    pos = nl + 1;
+    if (!prefix(line, ll, "data: ", 6)) continue;
+    if (native_event(S, line + 6, (int)ll - 6)) { status = AIGW_DECLINED; break; }
+  }
+  if (status) { S.flags |= SF_DEAD; S.dead_status = (uint32_t)status; S.dead_reason = AIGW_R_UNSUPPORTED_FIELD; R.status = (uint8_t)status; R.reason = AIGW_R_UNSUPPORTED_FIELD; return; }
+  {  // updateTotalTokens
+    aigw_usage& u = S.usage;
+    const bool out_set = u.mask & 2u;
+    if (out_set && !(u.mask & 1u)) { u.input = 0; u.mask |= 1u; }
+    if (out_set) { if (!(u.mask & 8u)) { u.cached = 0; u.mask |= 8u; } if (!(u.mask & 16u)) { u.cache_creation = 0; u.mask |= 16u; } }
+    if ((u.mask & 1u) && out_set) { u.total = u.input + u.output; u.mask |= 4u; }
+  }
+  S.beg = pos;
+  R.usage = S.usage; R.body_kind = AIGW_BODY_UNCHANGED; R.out_len = 0;
+  const char* m = S.rmodel_len ? S.rmodel : S.model; const uint32_t ml = S.rmodel_len ? S.rmodel_len : S.model_len;
+  if (ml <= st.out_cap) { for (uint32_t k = 0; k < ml; k++) out[k] = (uint8_t)m[k]; R.model_len = ml; }
+}
+
 // ------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(128) stream_init_kernel(StreamSlot* slots, const uint32_t* slot_ids, uint32_t n, const uint8_t* tmpl) {
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -727,6 +867,7 @@ __global__ void __launch_bounds__(64) stream_step_kernel(const __grid_constant__
       case AIGW_STREAM_GCP_ANTHROPIC: step_anthropic(S, st, out, R); break;
       case AIGW_STREAM_GCP_GEMINI: step_gemini(S, st, out, R); break;
       case AIGW_STREAM_GCP_GEMINI_BUFFERED: step_gemini_buffered(S, st, out, R); break;
+      case AIGW_STREAM_ANTHROPIC: step_anthropic_native(S, st, out, R); break;
       default: R.status = AIGW_DECLINED; R.reason = AIGW_R_SCHEMA; break;
     }
   }

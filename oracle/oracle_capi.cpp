@@ -10,6 +10,7 @@
 #include "bedrock_response.hpp"
 #include "bedrock_stream.hpp"
 #include "anthropic_stream.hpp"
+#include "anthropic_native.hpp"
 #include "gemini.hpp"
 #include "gemini_stream.hpp"
 namespace oracle { TranslateResult gemini_request_body(const ChatReq& r, const std::string& model_override) { return gemini::request_body(r, model_override); } }
@@ -242,6 +243,21 @@ int oracle_anthropic_response(const char* body, uint64_t len, const char* reques
   std::string o, rm; TokenUsage u; const Status s = anthropic_response(std::string_view(body, len), cfg, o, u, rm);
   put(usage, u); *out = dup(o); *out_len = o.size();
   uint64_t n = std::min<uint64_t>(cap, rm.size()); memcpy(model_buf, rm.data(), n); *model_len = rm.size();
+  return (int)s;
+}
+// ---- native /v1/messages responses (usage scan, nothing rewritten)
+void* oracle_native_anthropic_open(const char* request_model) { auto* h = new NativeAnthropicStream(); h->request_model = request_model ? request_model : ""; return h; }
+void oracle_native_anthropic_close(void* h) { delete (NativeAnthropicStream*)h; }
+int oracle_native_anthropic_feed(void* hv, const char* chunk, uint64_t len, oracle_usage* usage, char* model_buf, uint64_t cap, uint64_t* model_len) {
+  auto* h = (NativeAnthropicStream*)hv; TokenUsage u; std::string m;
+  const Status s = native_anthropic_feed(*h, std::string_view(chunk, len), u, m);
+  put(usage, u); uint64_t n = std::min<uint64_t>(cap, m.size()); memcpy(model_buf, m.data(), n); *model_len = m.size();
+  return (int)s;
+}
+int oracle_native_anthropic_response(const char* body, uint64_t len, const char* request_model, oracle_usage* usage, char* model_buf, uint64_t cap, uint64_t* model_len) {
+  TokenUsage u; std::string m;
+  const Status s = native_anthropic_response(std::string_view(body, len), request_model ? request_model : "", u, m);
+  put(usage, u); uint64_t n = std::min<uint64_t>(cap, m.size()); memcpy(model_buf, m.data(), n); *model_len = m.size();
   return (int)s;
 }
 // ---- S4 / R1 (Gemini)

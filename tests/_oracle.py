@@ -252,6 +252,33 @@ def anthropic_response(body: bytes, request_model: bytes, created: int):
     return st, out, u, buf.raw[:ml.value]
 
 
+class NativeAnthropicStream:
+    """anthropicToAnthropicTranslator.ResponseBody(stream) per call: feed(chunk) → (status, Usage so far, response model); the body is never rewritten."""
+    def __init__(self, request_model: bytes):
+        L = lib(); L.oracle_native_anthropic_open.restype = C.c_void_p; L.oracle_native_anthropic_open.argtypes = [C.c_char_p]
+        L.oracle_native_anthropic_feed.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.POINTER(Usage), C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.oracle_native_anthropic_close.argtypes = [C.c_void_p]
+        self.h = L.oracle_native_anthropic_open(request_model)
+
+    def feed(self, chunk: bytes):
+        u = Usage(); buf = C.create_string_buffer(512); ml = C.c_uint64(0)
+        st = lib().oracle_native_anthropic_feed(self.h, chunk, len(chunk), C.byref(u), buf, 512, C.byref(ml))
+        return st, u, buf.raw[:ml.value]
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_native_anthropic_close(self.h); self.h = None
+
+
+def native_anthropic_response(body: bytes, request_model: bytes):
+    """Buffered anthropic.MessagesResponse → (status, Usage, response model)."""
+    L = lib()
+    L.oracle_native_anthropic_response.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.POINTER(Usage), C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    u = Usage(); buf = C.create_string_buffer(512); ml = C.c_uint64(0)
+    st = L.oracle_native_anthropic_response(body, len(body), request_model, C.byref(u), buf, 512, C.byref(ml))
+    return st, u, buf.raw[:ml.value]
+
+
 class BedrockStream:
     """Bedrock ResponseBody(stream) per call (S2): feed(chunk, eos) → (body mutation bytes, Usage of the call)."""
     def __init__(self, request_model: bytes, response_id: bytes, created: int):

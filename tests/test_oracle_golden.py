@@ -499,3 +499,19 @@ def test_messages_native_goldens():
             assert t.body_kind == 0
         n += 1
     assert n == 8
+
+
+def test_native_anthropic_usage_reference_vectors():
+    """anthropic_anthropic_test.go:89-155: buffered response → tokenUsageFrom(9, 0, 0, 16, 25, -1) + model; the stream in two parts →
+    tokenUsageFrom(10, 1, 0, 0, 10, -1) then tokenUsageFrom(10, 1, 0, 16, 26, -1)"""
+    import test_anthropic_native_gpu as N
+    body = ('{"model":"claude-sonnet-4-5-20250929","id":"msg_01J5gW6Sffiem6avXSAooZZw","type":"message","role":"assistant","content":[{"type":"text","text":"Hi! \U0001F44B How can I help you today?"}],'
+            '"stop_reason":"end_turn","stop_sequence":null,"usage":{"input_tokens":9,"cache_creation_input_tokens":0,"cache_read_input_tokens":0,"cache_creation":{"ephemeral_5m_input_tokens":0,'
+            '"ephemeral_1h_input_tokens":0},"output_tokens":16,"service_tier":"standard"}}').encode()
+    st, u, m = O.native_anthropic_response(body, b"")
+    assert st == 0 and u.as_tuple() == (9, 0, 0, 16, 25, -1) and m == b"claude-sonnet-4-5-20250929"
+    s = O.NativeAnthropicStream(b"")
+    st, u, m = s.feed(N.HEAD.encode())
+    assert st == 0 and u.as_tuple() == (10, 1, 0, 0, 10, -1) and m == b"claude-sonnet-4-5-20250929"
+    st, u, m = s.feed(N.TAIL.encode())
+    assert st == 0 and u.as_tuple() == (10, 1, 0, 16, 26, -1) and m == b"claude-sonnet-4-5-20250929"
