@@ -22,7 +22,7 @@ cudaError_t launch_chat_walk(const ChatParams& P, uint32_t doc0, uint32_t ndocs,
   const uint32_t s = P.schema;
   if (s & (uint32_t)AIGW_SCHEMA_MESSAGES) return launch_chat_walk_g7(P, doc0, ndocs, work, layout, st, sms);
   if ((s & 48u) == (uint32_t)AIGW_SCHEMA_RESP_AWS_BEDROCK)
-    return (s & 15u) == (uint32_t)AIGW_SCHEMA_GCP_ANTHROPIC ? launch_chat_walk_g5(P, doc0, ndocs, work, layout, st, sms) : launch_chat_walk_g4(P, doc0, ndocs, work, layout, st, sms);
+    return ((s & 15u) == (uint32_t)AIGW_SCHEMA_GCP_ANTHROPIC || (s & 15u) == (uint32_t)AIGW_SCHEMA_ANTHROPIC) ? launch_chat_walk_g5(P, doc0, ndocs, work, layout, st, sms) : launch_chat_walk_g4(P, doc0, ndocs, work, layout, st, sms);
   if (s & (uint32_t)AIGW_SCHEMA_EMBEDDINGS) return launch_chat_walk_g6(P, doc0, ndocs, work, layout, st, sms);
   switch (s) {
     case AIGW_SCHEMA_AWS_BEDROCK: return launch_chat_walk_g0(P, doc0, ndocs, work, layout, st, sms);
@@ -37,7 +37,7 @@ cudaError_t launch_chat_small(const ChatParams& P, uint32_t doc0, uint32_t ndocs
   const uint32_t s = P.schema;
   if (s & (uint32_t)AIGW_SCHEMA_MESSAGES) return launch_chat_small_g7(P, doc0, ndocs, out_slot, st);
   if ((s & 48u) == (uint32_t)AIGW_SCHEMA_RESP_AWS_BEDROCK)
-    return (s & 15u) == (uint32_t)AIGW_SCHEMA_GCP_ANTHROPIC ? launch_chat_small_g5(P, doc0, ndocs, out_slot, st) : launch_chat_small_g4(P, doc0, ndocs, out_slot, st);
+    return ((s & 15u) == (uint32_t)AIGW_SCHEMA_GCP_ANTHROPIC || (s & 15u) == (uint32_t)AIGW_SCHEMA_ANTHROPIC) ? launch_chat_small_g5(P, doc0, ndocs, out_slot, st) : launch_chat_small_g4(P, doc0, ndocs, out_slot, st);
   if (s & (uint32_t)AIGW_SCHEMA_EMBEDDINGS) return launch_chat_small_g6(P, doc0, ndocs, out_slot, st);
   switch (s) {
     case AIGW_SCHEMA_AWS_BEDROCK: return launch_chat_small_g0(P, doc0, ndocs, out_slot, st);
