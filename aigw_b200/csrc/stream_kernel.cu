@@ -157,6 +157,7 @@ __device__ void an_chunk(StreamSlot& S, Wr& w, const AnDelta& d, const char* fin
 }
 
 // one event block; 0, AIGW_INTERNAL (the reference returns an error) or AIGW_DECLINED
+__device__ int an_event_core(StreamSlot& S, const uint8_t* et, uint32_t etl, const uint8_t* data, uint32_t dl, int ndata, Wr& w);
 __device__ int an_event(StreamSlot& S, const uint8_t* blk, uint32_t bn, Wr& w) {
   const uint8_t* et = nullptr; uint32_t etl = 0; const uint8_t* data = nullptr; uint32_t dl = 0; int ndata = 0;
   uint32_t pos = 0;
@@ -168,6 +169,10 @@ __device__ int an_event(StreamSlot& S, const uint8_t* blk, uint32_t bn, Wr& w) {
     if (nl >= bn) break;
     pos = nl + 1;
   }
+  return an_event_core(S, et, etl, data, dl, ndata, w);
+}
+// one event given as its (trimmed) type and data line
+__device__ int an_event_core(StreamSlot& S, const uint8_t* et, uint32_t etl, const uint8_t* data, uint32_t dl, int ndata, Wr& w) {
   if (!etl || !dl) return 0;
   if (ndata > 1) return AIGW_DECLINED;   // concatenated data lines: stock path
   int ev;  // 1 message_start 2 content_block_start 3 message_delta 4 content_block_delta 5 content_block_stop 6 message_stop 7 error
@@ -259,6 +264,29 @@ __device__ int an_event(StreamSlot& S, const uint8_t* blk, uint32_t bn, Wr& w) {
   }
 }
 
+// end of stream: the final usage chunk and [DONE] (anthropic_helper.go:859-916)
+__device__ int an_finish(StreamSlot& S, Wr& w) {
+  if (S.flags & SF_TOOL_ACTIVE) return AIGW_DECLINED;   // an open tool call is replayed in the final chunk: stock path
+  S.usage.total = S.usage.input + S.usage.output; S.usage.mask |= 4u;
+  if (S.usage.input > 0 || S.usage.output > 0) {
+    WL(w, "data: {");
+    if (S.id_len) { WL(w, "\"id\":\""); w.raw((const uint8_t*)S.id, S.id_len); WL(w, "\","); }
+    WL(w, "\"choices\":[]");
+    if (S.flags & SF_HAVE_CREATED) { WL(w, ",\"created\":"); w.sdec(S.created); }
+    if (S.model_len) { WL(w, ",\"model\":\""); w.raw((const uint8_t*)S.model, S.model_len); w.ch('"'); }
+    WL(w, ",\"object\":\"chat.completion.chunk\",\"usage\":{");
+    bool f = true;
+    auto num = [&](const char* k, uint32_t kl, uint32_t v) { if (!v) return; if (!f) w.ch(','); f = false; w.lit(k, kl); w.dec(v); };
+    num("\"prompt_tokens\":", 16, S.usage.input); num("\"completion_tokens\":", 20, S.usage.output); num("\"total_tokens\":", 15, S.usage.total);
+    if (!f) w.ch(',');
+    WL(w, "\"prompt_tokens_details\":{"); f = true;
+    num("\"cached_tokens\":", 16, S.usage.cached); num("\"cache_creation_input_tokens\":", 30, S.usage.cache_creation);
+    WL(w, "}}}\n\n");
+  }
+  WL(w, "data: [DONE]\n\n");
+  return 0;
+}
+
 // anthropicStreamParser.Process, internal/translator/anthropic_helper.go:826-919
 __device__ void step_anthropic(StreamSlot& S, const StreamStep& st, uint8_t* out, aigw_chunk_result& R) {
   const uint8_t* b = S.buf; const uint32_t n = S.end;
@@ -273,28 +301,7 @@ __device__ void step_anthropic(StreamSlot& S, const StreamStep& st, uint8_t* out
     pos = cut + 2;
   }
   if (!status && st.eos && pos < n) { status = an_event(S, b + pos, n - pos, w); pos = n; }
-  if (!status && st.eos) {
-    if (S.flags & SF_TOOL_ACTIVE) status = AIGW_DECLINED;   // an open tool call is replayed in the final chunk: stock path
-    else {
-      S.usage.total = S.usage.input + S.usage.output; S.usage.mask |= 4u;
-      if (S.usage.input > 0 || S.usage.output > 0) {
-        WL(w, "data: {");
-        if (S.id_len) { WL(w, "\"id\":\""); w.raw((const uint8_t*)S.id, S.id_len); WL(w, "\","); }
-        WL(w, "\"choices\":[]");
-        if (S.flags & SF_HAVE_CREATED) { WL(w, ",\"created\":"); w.sdec(S.created); }
-        if (S.model_len) { WL(w, ",\"model\":\""); w.raw((const uint8_t*)S.model, S.model_len); w.ch('"'); }
-        WL(w, ",\"object\":\"chat.completion.chunk\",\"usage\":{");
-        bool f = true;
-        auto num = [&](const char* k, uint32_t kl, uint32_t v) { if (!v) return; if (!f) w.ch(','); f = false; w.lit(k, kl); w.dec(v); };
-        num("\"prompt_tokens\":", 16, S.usage.input); num("\"completion_tokens\":", 20, S.usage.output); num("\"total_tokens\":", 15, S.usage.total);
-        if (!f) w.ch(',');
-        WL(w, "\"prompt_tokens_details\":{"); f = true;
-        num("\"cached_tokens\":", 16, S.usage.cached); num("\"cache_creation_input_tokens\":", 30, S.usage.cache_creation);
-        WL(w, "}}}\n\n");
-      }
-      WL(w, "data: [DONE]\n\n");
-    }
-  }
+  if (!status && st.eos) status = an_finish(S, w);
   if (!status && w.ovf) status = AIGW_DECLINED;
   if (status) { S.flags |= SF_DEAD; S.dead_status = (uint32_t)status; S.dead_reason = w.ovf ? AIGW_R_OUT_SPACE : AIGW_R_UNSUPPORTED_FIELD; R.status = (uint8_t)status; R.reason = (uint8_t)S.dead_reason; return; }
   S.beg = pos;
@@ -421,6 +428,126 @@ __device__ void step_bedrock(StreamSlot& S, const StreamStep& st, uint8_t* out, 
   S.beg = pos;
   R.usage = u; R.out_len = wn; R.body_kind = wn ? AIGW_BODY_BYTES : AIGW_BODY_EMPTY;
   if (wn + S.model_len <= st.out_cap) { for (uint32_t k = 0; k < S.model_len; k++) out[wn + k] = (uint8_t)S.model[k]; R.model_len = S.model_len; }
+}
+
+// ------------------------------------------------------------------ S3 behind AWS: Anthropic events wrapped in eventstream frames
+// (openAIToAWSAnthropicTranslatorV1ChatCompletion.ResponseBody + extractAnthropicSSEFromEventStream,
+//  internal/translator/openai_awsanthropic.go:162-184,216-261): every frame's payload is {"bytes":"<base64 of the event JSON>"};
+//  the reference decodes it, takes gjson "type" and hands "event: T\ndata: J\n\n" to the Anthropic stream parser.
+__device__ __forceinline__ int skipws(const uint8_t* p, int i, int n);
+__device__ bool next_member(const uint8_t* p, int& i, int n, int& ks, int& kl, bool& kesc, int& vs, int& ve);
+// 0 frame at pos is complete and valid, 1 wait / blocked (decoder error), 2 too large for the carry
+__device__ int es_frame(const uint8_t* b, uint32_t n, uint32_t pos, uint32_t& total, uint32_t& hlen) {
+  if (n - pos < 12u) return 1;
+  const uint8_t* f = b + pos;
+  total = be32(f); hlen = be32(f + 4);
+  if (crc32_dev(f, 8) != be32(f + 8)) return 1;
+  if (hlen > 128u * 1024u || total < 16u || hlen > total - 16u || total - hlen - 16u > 16u * 1024u * 1024u) return 1;
+  if (total > kStreamCarryCap) return 2;
+  if (n - pos < total) return 1;
+  if (crc32_dev(f, total - 4u) != be32(f + total - 4u)) return 1;
+  uint32_t h = 12; const uint32_t hend = 12 + hlen;
+  while (h < hend) {
+    const uint32_t nl = f[h]; h++;
+    if (h + nl + 1 > hend) return 1;
+    h += nl;
+    const uint32_t type = f[h]; h++;
+    int vs;
+    switch (type) { case 0: case 1: vs = 0; break; case 2: vs = 1; break; case 3: vs = 2; break; case 4: vs = 4; break; case 5: case 8: vs = 8; break; case 9: vs = 16; break; case 6: case 7: vs = -1; break; default: vs = -2; }
+    if (vs == -2) return 1;
+    if (vs == -1) { if (h + 2 > hend) return 1; vs = (f[h] << 8) | f[h + 1]; h += 2; }
+    if (h + (uint32_t)vs > hend) return 1;
+    h += (uint32_t)vs;
+  }
+  return 0;
+}
+__device__ __forceinline__ int b64v(uint32_t c) { return c - 'A' < 26u ? (int)(c - 'A') : c - 'a' < 26u ? (int)(c - 'a') + 26 : c - '0' < 10u ? (int)(c - '0') + 52 : c == '+' ? 62 : c == '/' ? 63 : -1; }
+// base64.StdEncoding.DecodeString of p[0, n) written over p (the decoded text is shorter).  Returns the length, -1 = not decodable,
+// -2 = a byte outside the alphabet that Go's decoder would skip or that needs the stock path (CR / LF)
+__device__ int b64_inplace(uint8_t* p, int n) {
+  if (n & 3) return -1;
+  int w = 0;
+  for (int i = 0; i < n; i += 4) {
+    const uint32_t c0 = p[i], c1 = p[i + 1], c2 = p[i + 2], c3 = p[i + 3];
+    if (c0 == '\r' || c0 == '\n' || c1 == '\r' || c1 == '\n' || c2 == '\r' || c2 == '\n' || c3 == '\r' || c3 == '\n') return -2;
+    const int a = b64v(c0), b = b64v(c1);
+    if (a < 0 || b < 0) return -1;
+    const bool last = i + 4 == n;
+    if (c2 == '=') { if (!last || c3 != '=') return -1; p[w++] = (uint8_t)((a << 2) | (b >> 4)); break; }
+    const int c = b64v(c2);
+    if (c < 0) return -1;
+    if (c3 == '=') { if (!last) return -1; p[w++] = (uint8_t)((a << 2) | (b >> 4)); p[w++] = (uint8_t)(((b & 15) << 4) | (c >> 2)); break; }
+    const int d = b64v(c3);
+    if (d < 0) return -1;
+    p[w++] = (uint8_t)((a << 2) | (b >> 4)); p[w++] = (uint8_t)(((b & 15) << 4) | (c >> 2)); p[w++] = (uint8_t)(((c & 3) << 6) | d);
+  }
+  return w;
+}
+__device__ void step_aws_anthropic(StreamSlot& S, const StreamStep& st, uint8_t* out, aigw_chunk_result& R) {
+  uint8_t* b = S.buf; const uint32_t n = S.end;
+  Wr w{out, 0, st.out_cap, 0};
+  uint32_t pos = 0; int status = 0, reason = AIGW_R_UNSUPPORTED_FIELD;
+  for (;;) {
+    uint32_t total, hlen;
+    const int fr = es_frame(b, n, pos, total, hlen);
+    if (fr == 1) break;
+    if (fr == 2) { status = AIGW_DECLINED; reason = AIGW_R_TOO_LARGE; break; }
+    uint8_t* pl = b + pos + 12 + hlen; const int pn = (int)(total - hlen - 16u);
+    pos += total;                                          // the frame is consumed whatever it holds
+    int e = skip_any(pl, 0, pn);
+    if (e < 0 || skipws(pl, e, pn) != pn) continue;        // json.Unmarshal error: the frame is skipped
+    const int r0 = skipws(pl, 0, pn);
+    if (pl[r0] != '{') continue;                           // null decodes to the zero struct, other roots fail: nothing to forward either way
+    int i = r0 + 1, ks, kl, a, c; bool kesc; int bs = -1, be = 0; bool odd = false;
+    while (next_member(pl, i, pn, ks, kl, kesc, a, c)) {
+      if (kesc) { odd = true; break; }
+      if (kl == 5) {
+        const uint8_t* k = pl + ks;
+        if (EQ(k, 5u, "bytes")) { if (bs >= 0) { odd = true; break; } bs = a; be = c; }
+        else if ((k[0] | 32) == 'b' && (k[1] | 32) == 'y' && (k[2] | 32) == 't' && (k[3] | 32) == 'e' && (k[4] | 32) == 's') { odd = true; break; }   // case-insensitive field match: stock path
+      }
+    }
+    if (odd) { status = AIGW_DECLINED; break; }
+    if (bs < 0 || pl[bs] != '"') continue;                  // absent / null: Bytes == "" ; other types: unmarshal error
+    uint8_t* t64 = pl + bs + 1; const int n64 = be - bs - 2;
+    bool esc = false; for (int k = 0; k < n64; k++) if (t64[k] == '\\') esc = true;
+    if (esc) { status = AIGW_DECLINED; break; }
+    if (n64 == 0) continue;
+    const int dl = b64_inplace(t64, n64);
+    if (dl == -2) { status = AIGW_DECLINED; break; }
+    if (dl < 0) continue;                                   // base64 error: skipped
+    const uint8_t* J = t64;
+    bool nlc = false; for (int k = 0; k < dl; k++) if (J[k] == '\n') nlc = true;
+    if (nlc) { status = AIGW_DECLINED; break; }              // a line break inside the event would split the SSE block
+    int je = skip_any(J, 0, dl);
+    if (je < 0 || skipws(J, je, dl) != dl) { status = AIGW_DECLINED; break; }   // gjson on malformed text: stock path
+    const int j0 = skipws(J, 0, dl);
+    const uint8_t* et = nullptr; uint32_t etl = 0;
+    if (J[j0] == '{') {
+      int j = j0 + 1; bool bad = false;
+      while (next_member(J, j, dl, ks, kl, kesc, a, c)) {
+        if (kesc) { bad = true; break; }
+        if (!et && EQ(J + ks, (uint32_t)kl, "type")) {
+          if (J[a] != '"') { bad = true; break; }
+          et = J + a + 1; etl = (uint32_t)(c - a - 2);
+          for (uint32_t k = 0; k < etl; k++) if (et[k] == '\\') bad = true;
+          if (etl == 0) et = nullptr;
+        }
+      }
+      if (bad) { status = AIGW_DECLINED; break; }
+    }
+    if (!et) continue;                                       // "event: \ndata: …": a block without an event type is ignored by the parser
+    { const uint8_t* q = et; uint32_t ql = etl; trim_space(q, ql); et = q; etl = ql; }
+    const uint8_t* dq = J; uint32_t dql = (uint32_t)dl; trim_space(dq, dql);
+    status = an_event_core(S, et, etl, dq, dql, dql ? 1 : 0, w);
+    if (status) break;
+  }
+  if (!status && st.eos) status = an_finish(S, w);
+  if (!status && w.ovf) { status = AIGW_DECLINED; reason = AIGW_R_OUT_SPACE; }
+  if (status) { S.flags |= SF_DEAD; S.dead_status = (uint32_t)status; S.dead_reason = (uint32_t)reason; R.status = (uint8_t)status; R.reason = (uint8_t)reason; return; }
+  S.beg = pos;
+  R.usage = S.usage; R.out_len = w.n; R.body_kind = w.n ? AIGW_BODY_BYTES : AIGW_BODY_EMPTY;
+  if (w.n + S.model_len <= st.out_cap) { for (uint32_t k = 0; k < S.model_len; k++) out[w.n + k] = (uint8_t)S.model[k]; R.model_len = S.model_len; }
 }
 
 // ------------------------------------------------------------------ S4 / R1: Gemini GenerateContentResponse → OpenAI
@@ -868,6 +995,7 @@ __global__ void __launch_bounds__(64) stream_step_kernel(const __grid_constant__
       case AIGW_STREAM_GCP_GEMINI: step_gemini(S, st, out, R); break;
       case AIGW_STREAM_GCP_GEMINI_BUFFERED: step_gemini_buffered(S, st, out, R); break;
       case AIGW_STREAM_ANTHROPIC: step_anthropic_native(S, st, out, R); break;
+      case AIGW_STREAM_AWS_ANTHROPIC: step_aws_anthropic(S, st, out, R); break;
       default: R.status = AIGW_DECLINED; R.reason = AIGW_R_SCHEMA; break;
     }
   }

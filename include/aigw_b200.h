@@ -255,6 +255,9 @@ int aigw_bedrock_stream_host(aigw_ctx* ctx, const aigw_bedrock_stream_cfg* cfg, 
  *                                    (AIGW_BODY_UNCHANGED); usage from message_start / message_delta as anthropic_anthropic.go:133-201
  *                                    accumulates it, response model from message_start.  message_start events with content
  *                                    blocks, non-integer counts and escaped member names kill the stream with DECLINED.
+ *   AIGW_STREAM_AWS_ANTHROPIC        OpenAI chat completions to Anthropic on AWS Bedrock (openai_awsanthropic.go:162-184,216-261): eventstream
+ *                                    frames whose payload is {"bytes": base64(event JSON)} are unwrapped and run through the same
+ *                                    Anthropic → OpenAI SSE parser as AIGW_STREAM_GCP_ANTHROPIC
  *   AIGW_STREAM_GCP_GEMINI_BUFFERED  buffered GenerateContentResponse → ChatCompletionResponse (openai_gcpvertexai.go:139-198): feed the
  *                              body (≤ 15.6 KB) and set eos on the last call; the usage record is the call's `usage`
  * aigw_stream_chunks processes one ResponseBody call for each of n streams in ONE batch (a stream may appear once per call;
@@ -266,7 +269,7 @@ int aigw_bedrock_stream_host(aigw_ctx* ctx, const aigw_bedrock_stream_cfg* cfg, 
  * AIGW_R_TOO_LARGE carry above 15.6 KB, AIGW_R_OUT_SPACE, AIGW_R_ARENA_FULL) — both are sticky for the stream.
  * cfg strings must not need JSON escaping (printable ASCII without '"' and '\\', ≤ 160 bytes), else -2. */
 enum aigw_stream_kind { AIGW_STREAM_OPENAI = 0, AIGW_STREAM_AWS_BEDROCK = 1, AIGW_STREAM_GCP_ANTHROPIC = 2, AIGW_STREAM_GCP_GEMINI = 3, AIGW_STREAM_GCP_GEMINI_BUFFERED = 4,
-                        AIGW_STREAM_ANTHROPIC = 5 };
+                        AIGW_STREAM_ANTHROPIC = 5, AIGW_STREAM_AWS_ANTHROPIC = 6 };
 typedef struct aigw_stream_cfg { int32_t kind; int32_t _pad; int64_t created; const char* request_model; const char* response_id; } aigw_stream_cfg;
 typedef struct aigw_chunk_in { uint64_t handle; const uint8_t* bytes; uint32_t len; uint32_t eos; } aigw_chunk_in;
 typedef struct aigw_chunk_result {

@@ -11,6 +11,7 @@
 #include "bedrock_stream.hpp"
 #include "anthropic_stream.hpp"
 #include "anthropic_native.hpp"
+#include "aws_anthropic_stream.hpp"
 #include "gemini.hpp"
 #include "gemini_stream.hpp"
 namespace oracle { TranslateResult gemini_request_body(const ChatReq& r, const std::string& model_override) { return gemini::request_body(r, model_override); } }
@@ -243,6 +244,17 @@ int oracle_anthropic_response(const char* body, uint64_t len, const char* reques
   std::string o, rm; TokenUsage u; const Status s = anthropic_response(std::string_view(body, len), cfg, o, u, rm);
   put(usage, u); *out = dup(o); *out_len = o.size();
   uint64_t n = std::min<uint64_t>(cap, rm.size()); memcpy(model_buf, rm.data(), n); *model_len = rm.size();
+  return (int)s;
+}
+// ---- S3 behind AWS (eventstream-wrapped Anthropic events)
+struct AwsAnthropicHandle { AwsAnthropicStreamState st; AnthropicStreamCfg cfg; };
+void* oracle_aws_anthropic_open(const char* request_model, int64_t created) { auto* h = new AwsAnthropicHandle(); h->cfg.request_model = request_model ? request_model : ""; h->cfg.created = created; return h; }
+void oracle_aws_anthropic_close(void* h) { delete (AwsAnthropicHandle*)h; }
+int oracle_aws_anthropic_feed(void* hv, const char* chunk, uint64_t len, int eos, char** out, uint64_t* out_len, oracle_usage* usage) {
+  auto* h = (AwsAnthropicHandle*)hv; std::string o; TokenUsage u;
+  const Status s = aws_anthropic_stream_feed(h->st, h->cfg, std::string_view(chunk, len), eos != 0, o, u);
+  if (s != OK) o.clear();
+  put(usage, u); *out = dup(o); *out_len = o.size();
   return (int)s;
 }
 // ---- native /v1/messages responses (usage scan, nothing rewritten)

@@ -252,6 +252,25 @@ def anthropic_response(body: bytes, request_model: bytes, created: int):
     return st, out, u, buf.raw[:ml.value]
 
 
+class AwsAnthropicStream:
+    """OpenAI -> AWS Anthropic ResponseBody(stream) per call: eventstream frames with base64 Anthropic events → (status, OpenAI SSE bytes, Usage)."""
+    def __init__(self, request_model: bytes, created: int):
+        L = lib(); L.oracle_aws_anthropic_open.restype = C.c_void_p; L.oracle_aws_anthropic_open.argtypes = [C.c_char_p, C.c_int64]
+        L.oracle_aws_anthropic_feed.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(Usage)]
+        L.oracle_aws_anthropic_close.argtypes = [C.c_void_p]
+        self.h = L.oracle_aws_anthropic_open(request_model, created)
+
+    def feed(self, chunk: bytes, eos: bool):
+        vp = C.c_void_p(); n = C.c_uint64(0); u = Usage()
+        st = lib().oracle_aws_anthropic_feed(self.h, chunk, len(chunk), int(eos), C.byref(vp), C.byref(n), C.byref(u))
+        out = C.string_at(vp, n.value); lib().oracle_free(vp)
+        return st, out, u
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_aws_anthropic_close(self.h); self.h = None
+
+
 class NativeAnthropicStream:
     """anthropicToAnthropicTranslator.ResponseBody(stream) per call: feed(chunk) → (status, Usage so far, response model); the body is never rewritten."""
     def __init__(self, request_model: bytes):
