@@ -43,7 +43,7 @@ EXPORTS = ["aigw_bind_numa", "aigw_stream_open", "aigw_stream_open_batch", "aigw
            "aigw_device_alloc", "aigw_device_free", "aigw_memcpy_h2d", "aigw_memcpy_d2h", "aigw_memset_d", "aigw_sync",
            "aigw_chat_translate_device", "aigw_chat_translate_device_mapped", "aigw_chat_last_profile", "aigw_chat_set_profile", "aigw_chat_set_small_batch", "aigw_chat_translate_host", "aigw_sse_usage_device", "aigw_sse_usage_host", "aigw_response_usage_device", "aigw_response_usage_host", "aigw_embeddings_response_usage_device", "aigw_embeddings_response_usage_host", "aigw_usage_costs_device",
            "aigw_bedrock_stream_device", "aigw_bedrock_stream_host", "aigw_body_mutate_device", "aigw_body_mutate_host",
-           "aigw_cost_compile", "aigw_cost_program_free", "aigw_usage_costs_cel_device", "aigw_usage_costs_cel_host", "aigw_sha256_device", "aigw_chat_body_sha256_device", "aigw_sha256_host", "aigw_batcher_start", "aigw_batcher_add_backend", "aigw_batcher_translate", "aigw_batcher_translate_to", "aigw_batcher_get_stats", "aigw_batcher_stop"]
+           "aigw_cost_compile", "aigw_cost_program_free", "aigw_usage_costs_cel_device", "aigw_usage_costs_cel_host", "aigw_sha256_device", "aigw_chat_body_sha256_device", "aigw_sha256_host", "aigw_bpe_load", "aigw_bpe_free", "aigw_bpe_count_device", "aigw_bpe_count_host", "aigw_batcher_start", "aigw_batcher_add_backend", "aigw_batcher_translate", "aigw_batcher_translate_to", "aigw_batcher_get_stats", "aigw_batcher_stop"]
 
 
 class BackendCfg(C.Structure):
@@ -388,6 +388,38 @@ class Context:
         ms = C.c_float(0)
         self._check(self.L.aigw_chat_body_sha256_device(self.h, d_out, d_res, n, d_dig, None, C.byref(ms) if timed else None), "chat_body_sha256_device")
         return ms.value
+
+    # ---- K4: BPE token count
+    def bpe_load(self, byte_to_id, merges):
+        b2i = np.ascontiguousarray(np.asarray(byte_to_id, dtype=np.uint16)); mg = np.ascontiguousarray(np.asarray(merges, dtype=np.uint32).reshape(-1, 3))
+        h = C.c_void_p()
+        self.L.aigw_bpe_load.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
+        self._check(self.L.aigw_bpe_load(self.h, b2i.ctypes.data, mg.ctypes.data, len(mg), C.byref(h)), "bpe_load")
+        return h
+
+    def bpe_free(self, bpe):
+        self.L.aigw_bpe_free.argtypes = [C.c_void_p, C.c_void_p]; self.L.aigw_bpe_free.restype = None
+        self.L.aigw_bpe_free(self.h, bpe)
+
+    def bpe_count_host(self, bpe, arena, offs, lens):
+        n = len(lens); counts = np.zeros(n, dtype=np.uint32); h2d = C.c_uint64(0); d2h = C.c_uint64(0); ms = C.c_float(0)
+        self.L.aigw_bpe_count_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_float)]
+        self._check(self.L.aigw_bpe_count_host(self.h, bpe, arena.ctypes.data, offs.ctypes.data, lens.ctypes.data, n, counts.ctypes.data, C.byref(h2d), C.byref(d2h), C.byref(ms)), "bpe_count_host")
+        return counts, {"h2d_bytes": h2d.value, "d2h_bytes": d2h.value, "kernel_ms": ms.value}
+
+    def bpe_count_device(self, bpe, d_text, d_off, d_len, n, d_counts, timed=True):
+        ms = C.c_float(0)
+        self.L.aigw_bpe_count_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+        self._check(self.L.aigw_bpe_count_device(self.h, bpe, d_text, d_off, d_len, n, d_counts, None, C.byref(ms) if timed else None), "bpe_count_device")
+        return ms.value
+
+    def bpe_count(self, bpe, texts):
+        bs = [t.encode() if isinstance(t, str) else bytes(t) for t in texts]
+        lens = np.asarray([len(b) for b in bs], dtype=np.uint32); offs = np.zeros(len(bs), dtype=np.uint64)
+        if len(bs) > 1:
+            offs[1:] = np.cumsum(lens[:-1], dtype=np.uint64)
+        arena = np.frombuffer(b"".join(bs) + b"\0" * 16, dtype=np.uint8).copy()
+        return self.bpe_count_host(bpe, arena, offs, lens)[0]
 
     # ---- request batcher (synchronous single-request call, thread safe)
     def batcher_start(self, cfg, max_batch=256, window_us=50):

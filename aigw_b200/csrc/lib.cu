@@ -17,6 +17,7 @@
 #include "sha256_kernel.cuh"
 #include "cel_kernel.cuh"
 #include "stream_kernel.cuh"
+#include "bpe_kernel.cuh"
 
 #include <mutex>
 
@@ -41,6 +42,8 @@ struct ChunkSlot {
   cudaEvent_t ev_h2d, ev_k0, ev_k1, ev_ctr, ev_done;
 };
 
+struct aigw_bpe { uint2* d_table = nullptr; uint16_t* d_b2i = nullptr; uint32_t slots = 0; };
+
 struct aigw_ctx {
   int device = 0, sm_count = 0;
   cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
@@ -53,6 +56,8 @@ struct aigw_ctx {
   uint8_t* h_out = nullptr; size_t h_out_cap = 0;
   aigw_doc_result* h_res = nullptr; size_t h_res_cap = 0;
   long small_max = -1;   // aigw_chat_set_small_batch; -1: AIGW_SMALL_MAX or 512
+  // BPE count (host form): device staging
+  uint8_t* d_bpe_text = nullptr; size_t bpe_text_cap = 0; uint64_t* d_bpe_off = nullptr; size_t bpe_off_cap = 0; uint32_t* d_bpe_len = nullptr; size_t bpe_len_cap = 0; uint32_t* d_bpe_cnt = nullptr; size_t bpe_cnt_cap = 0;
   uint8_t* h_small = nullptr; size_t h_small_cap = 0;   // small-batch path: tables + bodies, read by the kernel in place (mapped pinned)
   // chat workspace (intermediates of one sub-batch) + per-stage timing events
   uint8_t* d_work = nullptr; size_t work_cap = 0;
@@ -184,7 +189,7 @@ void aigw_destroy(aigw_ctx* ctx) {
     cudaFree(s.d_in); cudaFree(s.d_off); cudaFree(s.d_len); cudaFree(s.d_out); cudaFree(s.d_res); cudaFree(s.d_used); cudaFree(s.d_next); cudaFreeHost(s.h_used);
     cudaEventDestroy(s.ev_h2d); cudaEventDestroy(s.ev_k0); cudaEventDestroy(s.ev_k1); cudaEventDestroy(s.ev_ctr); cudaEventDestroy(s.ev_done);
   }
-  cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_res); cudaFreeHost(ctx->h_small); cudaFree(ctx->d_counters); cudaFree(ctx->d_work); cudaFree(ctx->d_used_arr); cudaFreeHost(ctx->h_used_arr);
+  cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_res); cudaFreeHost(ctx->h_small); cudaFree(ctx->d_bpe_text); cudaFree(ctx->d_bpe_off); cudaFree(ctx->d_bpe_len); cudaFree(ctx->d_bpe_cnt); cudaFree(ctx->d_counters); cudaFree(ctx->d_work); cudaFree(ctx->d_used_arr); cudaFreeHost(ctx->h_used_arr);
   for (auto& e2 : ctx->stage_ev) cudaEventDestroy(e2);
   cudaFree(ctx->d_sse_bytes); cudaFree(ctx->d_sse_coff); cudaFree(ctx->d_sse_first); cudaFree(ctx->d_sse_res); cudaFree(ctx->d_bs_work); cudaFree(ctx->d_bs_off[0]); cudaFree(ctx->d_bs_off[1]); cudaFreeHost(ctx->h_sres); cudaFreeHost(ctx->h_mres);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
@@ -356,7 +361,7 @@ int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const u
     }
   }
   static const bool zero_copy = getenv("AIGW_HOST_ZEROCOPY") != nullptr;
-  const uint64_t kChunkBytes = 256ull << 20;
+  static const uint64_t kChunkBytes = (uint64_t)(getenv("AIGW_CHUNK_MB") ? atol(getenv("AIGW_CHUNK_MB")) : 256) << 20;   // pipeline granularity (fill / drain cost vs per-chunk launches)
   std::vector<uint32_t> cb;  // chunk begin doc index
   cb.push_back(0);
   uint32_t max_len = 0;
@@ -492,6 +497,72 @@ int aigw_chat_translate_host(aigw_ctx* ctx, const aigw_backend_cfg* cfg, const u
   CK(cudaStreamSynchronize(ctx->s_compute));
   float ms_total = 0; cudaEventElapsedTime(&ms_total, ctx->ev0, ctx->ev1);
   out->results = ctx->h_res; out->out = ctx->h_out; out->out_used = total_out_cap; out->h2d_bytes = h2d; out->d2h_bytes = d2h; out->kernel_ms = ms_total;
+  return 0;
+}
+
+// ------------------------------------------------------------------ K4: BPE token count
+int aigw_bpe_load(aigw_ctx* ctx, const uint16_t* byte_to_id, const uint32_t* merges, uint32_t n_merges, aigw_bpe** out) {
+  if (!ctx || !byte_to_id || (!merges && n_merges) || !out || n_merges >= 65535u) return -2;
+  for (uint32_t r = 0; r < n_merges * 3; r++) if (merges[r] >= 65536u) return -2;
+  CK(cudaSetDevice(ctx->device));
+  uint32_t slots = 1024; while (slots < n_merges * 2u) slots <<= 1;
+  if (bpe_smem_bytes(slots) > 220u * 1024u) { ctx->err = "aigw_bpe_load: merge table does not fit shared memory"; return -2; }
+  std::vector<uint2> tab(slots, make_uint2(0xffffffffu, 0xffffffffu));
+  for (uint32_t r = 0; r < n_merges; r++) {
+    const uint32_t key = (merges[3 * r] << 16) | merges[3 * r + 1];
+    uint32_t h = key * 0x9E3779B1u; h ^= h >> 15;
+    uint32_t s = h & (slots - 1);
+    bool dup = false;
+    while (tab[s].x != 0xffffffffu) { if (tab[s].x == key) { dup = true; break; } s = (s + 1) & (slots - 1); }
+    if (dup) continue;   // the first rank of a pair wins (a well-formed merge list has no duplicates)
+    tab[s] = make_uint2(key, (r << 16) | merges[3 * r + 2]);
+  }
+  aigw_bpe* b = new aigw_bpe();
+  b->slots = slots;
+  if (cudaMalloc(&b->d_table, (size_t)slots * 8) != cudaSuccess || cudaMalloc(&b->d_b2i, 512) != cudaSuccess) { cudaFree(b->d_table); delete b; return (int)cudaErrorMemoryAllocation; }
+  CK(cudaMemcpy(b->d_table, tab.data(), (size_t)slots * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(b->d_b2i, byte_to_id, 512, cudaMemcpyHostToDevice));
+  *out = b;
+  return 0;
+}
+void aigw_bpe_free(aigw_ctx* ctx, aigw_bpe* b) { if (!b) return; if (ctx) cudaSetDevice(ctx->device); cudaFree(b->d_table); cudaFree(b->d_b2i); delete b; }
+
+int aigw_bpe_count_device(aigw_ctx* ctx, const aigw_bpe* bpe, const uint8_t* d_text, const uint64_t* d_offsets, const uint32_t* d_lens, uint32_t n, uint32_t* d_counts,
+                          void* stream, float* kernel_ms) {
+  if (!ctx || !bpe) return -2;
+  if (n == 0) { if (kernel_ms) *kernel_ms = 0; return 0; }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->s_compute;
+  BpeParams P; P.text = d_text; P.offsets = d_offsets; P.lens = d_lens; P.n = n; P.counts = d_counts; P.table = bpe->d_table; P.slots = bpe->slots; P.byte_to_id = bpe->d_b2i;
+  P.next = ctx->d_counters + (ctx->counter_next++ & 255);
+  CK(cudaMemsetAsync(P.next, 0, sizeof(unsigned int), st));
+  if (kernel_ms) CK(cudaEventRecord(ctx->ev0, st));
+  CK(launch_bpe_count(P, ctx->sm_count, st));
+  if (kernel_ms) { CK(cudaEventRecord(ctx->ev1, st)); CK(cudaEventSynchronize(ctx->ev1)); CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1)); }
+  return 0;
+}
+
+int aigw_bpe_count_host(aigw_ctx* ctx, const aigw_bpe* bpe, const uint8_t* text, const uint64_t* offsets, const uint32_t* lens, uint32_t n, uint32_t* counts,
+                        uint64_t* h2d_bytes, uint64_t* d2h_bytes, float* kernel_ms) {
+  if (!ctx || !bpe) return -2;
+  if (n == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  uint64_t nbytes = 0; for (uint32_t i = 0; i < n; i++) { const uint64_t e = offsets[i] + lens[i]; if (e > nbytes) nbytes = e; }
+  ENSURE(ctx->d_bpe_text, ctx->bpe_text_cap, nbytes + 64, false);
+  ENSURE(ctx->d_bpe_off, ctx->bpe_off_cap, (size_t)n * 8, false);
+  ENSURE(ctx->d_bpe_len, ctx->bpe_len_cap, (size_t)n * 4, false);
+  ENSURE(ctx->d_bpe_cnt, ctx->bpe_cnt_cap, (size_t)n * 4, false);
+  cudaStream_t st = ctx->s_compute;
+  CK(cudaMemcpyAsync(ctx->d_bpe_text, text, nbytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_bpe_off, offsets, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_bpe_len, lens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  float ms = 0;
+  if (int rc = aigw_bpe_count_device(ctx, bpe, ctx->d_bpe_text, ctx->d_bpe_off, ctx->d_bpe_len, n, ctx->d_bpe_cnt, st, &ms)) return rc;
+  CK(cudaMemcpyAsync(counts, ctx->d_bpe_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (kernel_ms) *kernel_ms = ms;
+  if (h2d_bytes) *h2d_bytes = nbytes + (uint64_t)n * 12;
+  if (d2h_bytes) *d2h_bytes = (uint64_t)n * 4;
   return 0;
 }
 

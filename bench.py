@@ -403,6 +403,104 @@ def run_config1(a, local, ncpu):
     ctx.host_free(pp); ctx.close()
 
 
+# ------------------------------------------------------------------------------------------------ config 3
+def run_config3(a, rank, world, local, ncpu):
+    """/v1/embeddings requests of 1024 inputs x 64 characters: BPE token count per request (K4).  The inputs are given as a text
+    arena (1024 texts per request): the JSON scan of the 68.7 KB bodies is not part of this line (bodies above 64 KiB are outside
+    the index kernel's 16-bit positions)."""
+    import _oracle as O
+    import __graft_entry__ as entry
+    entry.build()
+    import aigw_b200 as A
+    A.load_library().aigw_bind_numa(local)
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    ctx = A.Context(local)
+    vocab = json.load(open(os.path.join(ROOT, "tests", "golden", "bpe_vocab.json")))
+    bpe = ctx.bpe_load(vocab["byte_to_id"], vocab["merges"])
+    nreq = a.requests; per = 1024; tl = 64
+    # Zipf-distributed words (seed 3 + rank) so the merges are exercised; one 16 MiB base text, every request reads its own window
+    r = np.random.default_rng(3 + rank)
+    alpha = np.frombuffer(b"etaoinshrdlcumwfgypbvkjxqz", dtype=np.uint8)
+    nw = 6000; wl = r.integers(1, 12, nw)
+    words = [bytes(alpha[r.integers(0, r.integers(6, 27), int(l))]) for l in wl]
+    ids = np.minimum(r.zipf(1.05, 3_000_000) - 1, nw - 1)
+    base = np.frombuffer(b" ".join(words[i] for i in ids)[: 16 << 20], dtype=np.uint8)
+    nt = nreq * per
+    nbytes = nt * tl
+    arena, ap = ctx.host_array(nbytes + 64)
+    reps = (nbytes + len(base) - 1) // len(base)
+    for k in range(reps):
+        lo = k * len(base); hi = min(nbytes, lo + len(base))
+        arena[lo:hi] = np.roll(base, 7919 * k)[: hi - lo]
+    offs = (np.arange(nt, dtype=np.uint64) * tl); lens = np.full(nt, tl, dtype=np.uint32)
+    d_text = ctx.dalloc(nbytes + 64); d_off = ctx.dalloc(nt * 8); d_len = ctx.dalloc(nt * 4); d_cnt = ctx.dalloc(nt * 4)
+    ctx.h2d(d_text, arena[:nbytes]); ctx.h2d(d_off, offs); ctx.h2d(d_len, lens)
+    sampler = ClockSampler(local); sampler.start()
+    for _ in range(a.warmup):
+        ctx.bpe_count_device(bpe, d_text, d_off, d_len, nt, d_cnt)
+    barrier = (lambda: (dist.barrier(), None)) if dist is not None else (lambda: None)
+    barrier(); ctx.sync()
+    dev_ms = 0.0; t0 = time.perf_counter()
+    for _ in range(a.steps):
+        dev_ms += ctx.bpe_count_device(bpe, d_text, d_off, d_len, nt, d_cnt)
+    ctx.sync(); barrier()
+    wall = time.perf_counter() - t0
+    counts = np.zeros(nt, dtype=np.uint32); ctx.d2h(counts, d_cnt)
+    assert (counts != 0xFFFFFFFF).all()
+    # parity of the timed outputs: every 64th request against the self-oracle
+    orc = O.Bpe(vocab)
+    checked = 0
+    for q in range(0, nreq, 64):
+        exp, _ = orc.count_batch(arena, offs[q * per:(q + 1) * per].copy(), lens[q * per:(q + 1) * per].copy())
+        assert np.array_equal(exp, counts[q * per:(q + 1) * per]), q
+        checked += 1
+    # end to end: host texts -> H2D -> count -> D2H of the per-text counts, per-request sums on the host
+    e2e_wall = None; st = None
+    if not a.skip_e2e:
+        ctx.bpe_count_host(bpe, arena, offs, lens)
+        barrier(); t1 = time.perf_counter()
+        for _ in range(a.steps):
+            c2, st = ctx.bpe_count_host(bpe, arena, offs, lens)
+            req_tokens = c2.reshape(nreq, per).sum(axis=1)
+        barrier(); e2e_wall = time.perf_counter() - t1
+        assert np.array_equal(c2, counts) and int(req_tokens[0]) == int(counts[:per].sum())
+    clocks = sampler.stop()
+    step_s = dev_ms / 1e3 / a.steps
+    if dist is not None:
+        import torch
+        t = torch.tensor([step_s, e2e_wall or 0.0], dtype=torch.float64, device=f"cuda:{local}"); dist.all_reduce(t, op=dist.ReduceOp.MAX); step_s, e2e_wall = float(t[0]), (float(t[1]) if e2e_wall else None)
+    cpu = None
+    if rank == 0 and world == 1:
+        ns = min(nreq, 256) * per
+        _, sec = orc.count_batch(arena, offs[:ns].copy(), lens[:ns].copy(), threads=ncpu)
+        _, sec1 = orc.count_batch(arena, offs[: ns // 8].copy(), lens[: ns // 8].copy(), threads=1)
+        cpu = {"value": (ns / per) / sec, "unit": "requests/s", "cores": ncpu, "kind": "port", "sample": f"first {ns // per} requests of the wave, {ncpu} threads (1 thread: {(ns // 8 / per) / sec1:.1f} requests/s)"}
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        alg = nbytes + nt * 4
+        achieved = alg / step_s / 1e9
+        line = {"metric": "embeddings requests/sec with BPE token count (1024 inputs x 64 chars per request)", "value": nreq * world / step_s, "unit": "requests/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u16", "data": "synthetic",
+                "config": {"workload": f"configs[2]: {nreq} /v1/embeddings requests per GPU per step, 1024 inputs x 64 characters each (Zipf words, seed 3), BPE vocabulary of {vocab['vocab_size']} (tests/golden/bpe_vocab.json); the inputs are given as a text arena, the JSON scan of the 68.7 KB bodies is not included",
+                           "texts_per_step": nt, "l2": f"inputs larger than L2 ({nbytes / 1e6:.0f} MB per step vs 126 MB)", "mean_tokens_per_request": float(counts.reshape(nreq, per).sum(axis=1).mean()),
+                           "requests_checked_vs_self_oracle": checked},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel": "bpe_count_kernel",
+                             "algorithmic_bytes_per_step": alg, "note": "algorithmic bytes = text bytes + 4 B per input (SURVEY 8d); the kernel is bound by the per-lane merge loops (shared-memory table lookups), not by HBM"},
+                "gpu_launches": (a.steps + a.warmup) * 1, "clocks": clocks}
+        if e2e_wall:
+            line["e2e"] = {"value": nreq * world * a.steps / e2e_wall, "unit": "requests/s", "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"])}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    ctx.host_free(ap); ctx.bpe_free(bpe); ctx.close()
+    if dist is not None: dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------ config 4
 def run_config4(a, rank, world, local, ncpu):
     """streams x 256 chunks x 80 B through aigw_stream_chunks (one ResponseBody call per stream per round), OpenAI usage extract"""
@@ -558,6 +656,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
     ap.add_argument("--bodies", type=int, default=int(os.environ.get("AIGW_BENCH_BODIES", 0)), help="bodies per GPU per step (config 2: 1,000,000; config 5: 1,250,000)")
     ap.add_argument("--streams", type=int, default=100_000, help="config 4: streams per GPU")
+    ap.add_argument("--requests", type=int, default=4096, help="config 3: embeddings requests (1024 inputs each) per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=400_000)
     ap.add_argument("--skip-e2e", action="store_true")
@@ -575,8 +674,7 @@ def main():
     elif a.config == 2:
         run_config2(a, rank, world, local, ncpu)
     elif a.config == 3:
-        if rank == 0:
-            print(json.dumps({"metric": "embeddings requests/sec with BPE token count", "unavailable": "configs[2] (68.7 KB requests + GPU BPE count) is not built this round: bodies above 64 KiB need 32-bit token positions; see DESIGN.md §7"}))
+        run_config3(a, rank, world, local, ncpu)
     elif a.config == 4:
         run_config4(a, rank, world, local, ncpu)
     else:

@@ -309,6 +309,23 @@ int aigw_body_mutate_device(aigw_ctx* ctx, const aigw_body_mutation* m, const ui
 int aigw_body_mutate_host(aigw_ctx* ctx, const aigw_body_mutation* m, const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n,
                           aigw_mut_batch_out* out);
 
+/* ---- K4: byte-level BPE token count (token-based rate limiting before the upstream call) ----
+ * The reference has NO tokenizer: the counts it rate-limits on come from provider responses (internal/metrics.TokenUsage).  This
+ * entry point is the north-star component "GPU BPE tokenizer with the merge table staged in shared memory"; its semantics are
+ * fixed here, not by the reference (parity is against HuggingFace `tokenizers` with the same vocabulary: a self-oracle):
+ *   pre-tokenisation  every space (0x20) starts a new piece; a piece is its first byte plus the bytes up to the next space
+ *   model             bytes map to byte_to_id[]; inside a piece the adjacent pair of lowest merge rank is merged (leftmost first
+ *                     among equal ranks) until no adjacent pair is in the merge table; tokens(text) = sum of final piece lengths
+ * merges: n_merges triples (a, b, merged) of token ids < 65536, rank = position; n_merges < 65535.  Texts are raw bytes (already
+ * JSON-unescaped).  counts[i] = 0xFFFFFFFF for a text that holds a space-free run longer than 2048 bytes (declined, not approximated). */
+typedef struct aigw_bpe aigw_bpe;
+int  aigw_bpe_load(aigw_ctx* ctx, const uint16_t* byte_to_id /* 256 */, const uint32_t* merges, uint32_t n_merges, aigw_bpe** out);
+void aigw_bpe_free(aigw_ctx* ctx, aigw_bpe* bpe);
+int  aigw_bpe_count_device(aigw_ctx* ctx, const aigw_bpe* bpe, const uint8_t* d_text, const uint64_t* d_offsets, const uint32_t* d_lens, uint32_t n, uint32_t* d_counts,
+                           void* stream, float* kernel_ms);
+int  aigw_bpe_count_host(aigw_ctx* ctx, const aigw_bpe* bpe, const uint8_t* text, const uint64_t* offsets, const uint32_t* lens, uint32_t n, uint32_t* counts,
+                         uint64_t* h2d_bytes, uint64_t* d2h_bytes, float* kernel_ms);
+
 /* ---- per-GPU request batcher: the synchronous single-request call for the cgo shim ----
  * The reference translates one request per goroutine (internal/extproc/processor_impl.go:211-398); a GPU wants batches.
  * aigw_batcher_translate[_to] is called concurrently from any number of threads.  The caller's body is copied (by the caller's

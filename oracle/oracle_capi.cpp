@@ -15,6 +15,7 @@
 #include "gemini.hpp"
 #include "gemini_stream.hpp"
 namespace oracle { TranslateResult gemini_request_body(const ChatReq& r, const std::string& model_override) { return gemini::request_body(r, model_override); } }
+#include "bpe.hpp"
 #include "cel.hpp"
 #include "sha256.hpp"
 #include "embeddings.hpp"
@@ -245,6 +246,20 @@ int oracle_anthropic_response(const char* body, uint64_t len, const char* reques
   put(usage, u); *out = dup(o); *out_len = o.size();
   uint64_t n = std::min<uint64_t>(cap, rm.size()); memcpy(model_buf, rm.data(), n); *model_len = rm.size();
   return (int)s;
+}
+// ---- K4: byte-level BPE token count (self-oracle)
+void* oracle_bpe_load(const uint16_t* byte_to_id, const uint32_t* merges, uint32_t n) { auto* v = new BpeVocab(); bpe_load(*v, byte_to_id, merges, n); return v; }
+void oracle_bpe_free(void* v) { delete (BpeVocab*)v; }
+// counts[i] = tokens of text i; returns the seconds the count took with `threads` workers
+double oracle_bpe_count_batch(void* vv, const char* text, const uint64_t* off, const uint32_t* len, uint64_t n, int threads, uint32_t* counts) {
+  const BpeVocab& V = *(const BpeVocab*)vv;
+  if (threads < 1) threads = 1;
+  const auto t0 = std::chrono::steady_clock::now();
+  std::atomic<uint64_t> next{0};
+  auto work = [&]() { for (;;) { const uint64_t b = next.fetch_add(256); if (b >= n) break; const uint64_t e = std::min<uint64_t>(n, b + 256); for (uint64_t i = b; i < e; i++) counts[i] = bpe_count(V, std::string_view(text + off[i], len[i])); } };
+  std::vector<std::thread> th; for (int t = 1; t < threads; t++) th.emplace_back(work);
+  work(); for (auto& x : th) x.join();
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 // ---- S3 behind AWS (eventstream-wrapped Anthropic events)
 struct AwsAnthropicHandle { AwsAnthropicStreamState st; AnthropicStreamCfg cfg; };

@@ -344,3 +344,36 @@ def gemini_response(body: bytes, request_model: bytes):
     st = L.oracle_gemini_response(body, len(body), request_model, C.byref(vp), C.byref(n), C.byref(u), buf, 4096, C.byref(ml))
     out = C.string_at(vp, n.value); L.oracle_free(vp)
     return st, out, u, buf.raw[:ml.value]
+
+
+class Bpe:
+    """K4 self-oracle: byte-level BPE token counts for the vocabulary in tests/golden/bpe_vocab.json (oracle/bpe.hpp)."""
+    def __init__(self, vocab=None):
+        import json, os
+        import numpy as np
+        if vocab is None:
+            vocab = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bpe_vocab.json")))
+        self.byte_to_id = np.asarray(vocab["byte_to_id"], dtype=np.uint16)
+        self.merges = np.ascontiguousarray(np.asarray(vocab["merges"], dtype=np.uint32).reshape(-1, 3))
+        L = lib(); L.oracle_bpe_load.restype = C.c_void_p; L.oracle_bpe_load.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.oracle_bpe_count_batch.restype = C.c_double; L.oracle_bpe_count_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+        L.oracle_bpe_free.argtypes = [C.c_void_p]
+        self.h = L.oracle_bpe_load(self.byte_to_id.ctypes.data, self.merges.ctypes.data, len(self.merges))
+
+    def count_batch(self, arena, offs, lens, threads=1):
+        import numpy as np
+        counts = np.zeros(len(lens), dtype=np.uint32)
+        sec = lib().oracle_bpe_count_batch(self.h, arena.ctypes.data, offs.ctypes.data, lens.ctypes.data, len(lens), threads, counts.ctypes.data)
+        return counts, sec
+
+    def count(self, texts):
+        import numpy as np
+        bs = [t.encode() if isinstance(t, str) else bytes(t) for t in texts]
+        lens = np.asarray([len(b) for b in bs], dtype=np.uint32); offs = np.zeros(len(bs), dtype=np.uint64)
+        if len(bs) > 1: offs[1:] = np.cumsum(lens[:-1], dtype=np.uint64)
+        arena = np.frombuffer(b"".join(bs) + b"\0", dtype=np.uint8).copy()
+        return self.count_batch(arena, offs, lens)[0]
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_bpe_free(self.h); self.h = None
