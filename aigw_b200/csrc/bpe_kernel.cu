@@ -18,9 +18,9 @@
 
 namespace aigw {
 
-static constexpr int kBpeWarps = 8;
-static constexpr int kBpeBuf = 2048;            // staged bytes per warp (a piece longer than this is declined)
-static constexpr int kBpeMaxTexts = 128;        // texts per group
+static constexpr int kBpeWarps = 32;            // the merge loops are latency-bound (dependent shared-memory lookups): as many warps as shared memory allows
+static constexpr int kBpeBuf = 512;            // staged bytes per warp (a piece longer than this is declined); small, so that 32 warps fit beside the table
+static constexpr int kBpeMaxTexts = 32;         // texts per group
 static constexpr uint32_t kEmpty = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t bpe_hash(uint32_t key) { key *= 0x9E3779B1u; return key ^ (key >> 15); }

@@ -317,7 +317,7 @@ int aigw_body_mutate_host(aigw_ctx* ctx, const aigw_body_mutation* m, const uint
  *   model             bytes map to byte_to_id[]; inside a piece the adjacent pair of lowest merge rank is merged (leftmost first
  *                     among equal ranks) until no adjacent pair is in the merge table; tokens(text) = sum of final piece lengths
  * merges: n_merges triples (a, b, merged) of token ids < 65536, rank = position; n_merges < 65535.  Texts are raw bytes (already
- * JSON-unescaped).  counts[i] = 0xFFFFFFFF for a text that holds a space-free run longer than 2048 bytes (declined, not approximated). */
+ * JSON-unescaped).  counts[i] = 0xFFFFFFFF for a text that holds a space-free run longer than 512 bytes (declined, not approximated). */
 typedef struct aigw_bpe aigw_bpe;
 int  aigw_bpe_load(aigw_ctx* ctx, const uint16_t* byte_to_id /* 256 */, const uint32_t* merges, uint32_t n_merges, aigw_bpe** out);
 void aigw_bpe_free(aigw_ctx* ctx, aigw_bpe* bpe);
