@@ -312,10 +312,12 @@ class Context:
                         "usage": usage, "carry_len": int(r["carry_len"])})
         return out
 
-    def stream_chunks_soa(self, handles_arr, base_arr, off_arr, len_arr, eos_arr=None):
-        """numpy-array driver: returns (ChunkResult array, arena address)"""
+    def stream_chunks_soa(self, handles_arr, base_arr, off_arr, len_arr, eos_arr=None, res=None):
+        """numpy-array driver: returns (ChunkResult array, arena address); `res` = a caller-owned result array to reuse"""
         n = len(handles_arr)
-        res = np.zeros(n, dtype=ChunkResult); arena = C.c_void_p()
+        if res is None:
+            res = np.zeros(n, dtype=ChunkResult)
+        arena = C.c_void_p()
         self.L.aigw_stream_chunks_soa.argtypes = [C.c_void_p] * 6 + [C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]
         self._check(self.L.aigw_stream_chunks_soa(self.h, handles_arr.ctypes.data, base_arr.ctypes.data, off_arr.ctypes.data, len_arr.ctypes.data,
                                                   eos_arr.ctypes.data if eos_arr is not None else None, n, res.ctypes.data, C.byref(arena)), "stream_chunks_soa")
@@ -333,8 +335,11 @@ class Context:
                 "carry_len": int(r["carry_len"])}
 
     def stream_close(self, handles):
-        arr = (C.c_uint64 * len(handles))(*handles)
         self.L.aigw_stream_close_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        if isinstance(handles, np.ndarray):
+            h = np.ascontiguousarray(handles, dtype=np.uint64)
+            return self.L.aigw_stream_close_batch(self.h, h.ctypes.data, len(h))
+        arr = (C.c_uint64 * len(handles))(*handles)
         return self.L.aigw_stream_close_batch(self.h, arr, len(handles))
 
     # ---- SSE usage

@@ -2,11 +2,13 @@
 // The host path is a 3-slot pipeline: H2D(chunk c+1) ‖ kernel(chunk c) ‖ D2H(chunk c-1) on three
 // CUDA streams; everything computed is computed by the kernels in this directory — there is no
 // CPU fallback anywhere in this library.
+#include <chrono>
 #include <cstdio>
 #include <sched.h>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "chat_kernel.cuh"
@@ -143,6 +145,18 @@ cudaError_t chat_small_launch(const aigw_backend_cfg* cfg, const uint8_t* in, co
   return launch_chat_small(P, 0, n, out_slot, st);
 }
 }  // namespace aigw
+
+// host loops over the calls of one window (byte staging, result hand-back) run on a few threads when the window is large
+template <class F>
+static void host_parallel_for(uint32_t n, F&& f) {
+  static const unsigned hw = [] { unsigned h = 2; const char* e = getenv("AIGW_HOST_THREADS"); if (e) h = (unsigned)atoi(e); return h < 1 ? 1u : (h > 8 ? 8u : h); }();   // measured: more staging threads slow the DMA that follows (17.3 / 20.0 / 19.5 / 15.9 M chunks/s at 1 / 2 / 4 / 8)
+  if (n < 16384 || hw == 1) { f(0u, n); return; }
+  std::vector<std::thread> th;
+  const uint32_t per = (n + hw - 1) / hw;
+  for (unsigned t = 1; t < hw; t++) { const uint32_t b = t * per, e = b + per < n ? b + per : n; if (b < e) th.emplace_back([&f, b, e] { f(b, e); }); }
+  f(0u, per < n ? per : n);
+  for (auto& x : th) x.join();
+}
 
 extern "C" {
 
@@ -672,72 +686,99 @@ int aigw_stream_close_batch(aigw_ctx* ctx, const uint64_t* handles, uint32_t n) 
 }
 int aigw_stream_close(aigw_ctx* ctx, uint64_t handle) { return aigw_stream_close_batch(ctx, &handle, 1); }
 
-static int stream_chunks_locked(aigw_ctx* ctx, const aigw_chunk_in* in, uint32_t n, aigw_chunk_result* results, const uint8_t** arena) {
+// One window of ResponseBody calls.  get(i) = {handle, bytes, len, eos} of call i.  zc_base != nullptr: every call's bytes lie in one
+// mapped pinned buffer starting at zc_base (device view zc_dev): the kernels read them in place, nothing is staged or copied.
+extern "C++" {
+struct StreamCallIn { uint64_t handle; const uint8_t* bytes; uint32_t len; uint32_t eos; };
+template <class GET>
+static int stream_chunks_core(aigw_ctx* ctx, uint32_t n, GET&& get, aigw_chunk_result* results, const uint8_t** arena, const uint8_t* zc_base, const uint8_t* zc_dev) {
   auto& sp = ctx->sp;
   if (arena) *arena = nullptr;
   if (n == 0) return 0;
   CK(cudaSetDevice(ctx->device));
+  static const bool prof = getenv("AIGW_STREAM_PROF") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+  const auto t0 = now();
   ENSURE(sp.h_steps, sp.h_steps_cap, (size_t)n * sizeof(StreamStep), true);
   sp.call_no++;
   uint64_t in_bytes = 0, out_bytes = 0;
   for (uint32_t i = 0; i < n; i++) {
+    const StreamCallIn c = get(i);
     uint32_t slot;
-    if (!stream_handle_ok(ctx, in[i].handle, slot) || (in[i].len && !in[i].bytes)) { ctx->err = "aigw_stream_chunks: bad handle"; return -2; }
+    if (!stream_handle_ok(ctx, c.handle, slot) || (c.len && !c.bytes)) { ctx->err = "aigw_stream_chunks: bad handle"; return -2; }
     if (sp.stamp[slot] == sp.call_no) { ctx->err = "aigw_stream_chunks: a stream appears twice in one call"; return -2; }
     sp.stamp[slot] = sp.call_no;
     StreamStep& s = sp.h_steps[i];
-    s.slot = slot; s.len = in[i].len; s.eos = in[i].eos ? 1u : 0u;
-    s.in_off = in_bytes; in_bytes += ((uint64_t)in[i].len + 15u) & ~15ull;
+    s.slot = slot; s.len = c.len; s.eos = c.eos ? 1u : 0u;
+    if (zc_base) s.in_off = (uint64_t)(c.bytes - zc_base);
+    else { s.in_off = in_bytes; in_bytes += ((uint64_t)c.len + 15u) & ~15ull; }
     // output bound: every unit of input (≥ 20 bytes) yields at most one chunk of ≤ 96 + id + model + its own text
-    const uint64_t oc = 16ull * ((uint64_t)sp.carry[slot] + in[i].len) + 1024u;
+    const uint64_t oc = 16ull * ((uint64_t)sp.carry[slot] + c.len) + 1024u;
     s.out_cap = (uint32_t)(oc > 0x7fffffffull ? 0x7fffffffull : oc);
     s.out_off = out_bytes; out_bytes += ((uint64_t)s.out_cap + 15u) & ~15ull;
   }
-  ENSURE(sp.h_in, sp.h_in_cap, in_bytes + 16, true);
-  ENSURE(sp.d_in, sp.d_in_cap, in_bytes + 16, false);
+  if (!zc_base) { ENSURE(sp.h_in, sp.h_in_cap, in_bytes + 16, true); ENSURE(sp.d_in, sp.d_in_cap, in_bytes + 16, false); }
   ENSURE(sp.d_steps, sp.d_steps_cap, (size_t)n * sizeof(StreamStep), false);
   ENSURE(sp.d_res, sp.d_res_cap, (size_t)n * sizeof(aigw_chunk_result), false);
   ENSURE(sp.h_res, sp.h_res_cap, (size_t)n * sizeof(aigw_chunk_result), true);
   ENSURE(sp.d_out, sp.d_out_cap, out_bytes + 16, false);
   ENSURE(sp.d_packed, sp.d_packed_cap, out_bytes + 16, false);
   if (!sp.d_used) { CK(cudaMalloc(&sp.d_used, 8)); CK(cudaHostAlloc(&sp.h_used, 8, cudaHostAllocDefault)); }
-  for (uint32_t i = 0; i < n; i++) if (in[i].len) memcpy(sp.h_in + sp.h_steps[i].in_off, in[i].bytes, in[i].len);   // no caller pointer is retained
+  const auto t1 = now();
+  if (!zc_base) host_parallel_for(n, [&](uint32_t b, uint32_t e) { for (uint32_t i = b; i < e; i++) { const StreamCallIn c = get(i); if (c.len) memcpy(sp.h_in + sp.h_steps[i].in_off, c.bytes, c.len); } });   // no caller pointer is retained
+  const auto t2 = now();
   cudaStream_t st = ctx->s_compute;
-  CK(cudaMemcpyAsync(sp.d_in, sp.h_in, in_bytes, cudaMemcpyHostToDevice, st));
+  if (!zc_base) CK(cudaMemcpyAsync(sp.d_in, sp.h_in, in_bytes, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(sp.d_steps, sp.h_steps, (size_t)n * sizeof(StreamStep), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(sp.d_used, 0, 8, st));
-  StreamParams P; P.slots = sp.d_slots; P.in = sp.d_in; P.out = sp.d_out; P.packed = sp.d_packed; P.packed_used = sp.d_used; P.packed_cap = sp.d_packed_cap; P.steps = sp.d_steps; P.results = sp.d_res; P.n = n;
+  StreamParams P; P.slots = sp.d_slots; P.in = zc_base ? zc_dev : sp.d_in; P.out = sp.d_out; P.packed = sp.d_packed; P.packed_used = sp.d_used; P.packed_cap = sp.d_packed_cap; P.steps = sp.d_steps; P.results = sp.d_res; P.n = n;
   CK(launch_stream_steps(P, st));
-  CK(cudaMemcpyAsync(sp.h_res, sp.d_res, (size_t)n * sizeof(aigw_chunk_result), cudaMemcpyDeviceToHost, st));
+  // results: straight into the caller's array when it is pinned (one DMA), else through the pinned staging array
+  cudaPointerAttributes ra; const bool res_pinned = cudaPointerGetAttributes(&ra, results) == cudaSuccess && ra.type == cudaMemoryTypeHost;
+  if (!res_pinned) cudaGetLastError();
+  aigw_chunk_result* hres = res_pinned ? results : sp.h_res;
+  CK(cudaMemcpyAsync(hres, sp.d_res, (size_t)n * sizeof(aigw_chunk_result), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(sp.h_used, sp.d_used, 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  const auto t3 = now();
   const uint64_t used = *sp.h_used < sp.d_packed_cap ? *sp.h_used : sp.d_packed_cap;
   if (used) {
     ENSURE(sp.h_packed, sp.h_packed_cap, used + 16, true);
     CK(cudaMemcpyAsync(sp.h_packed, sp.d_packed, used, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }
-  for (uint32_t i = 0; i < n; i++) { results[i] = sp.h_res[i]; sp.carry[sp.h_steps[i].slot] = sp.h_res[i].carry_len; }
+  const auto t4 = now();
+  if (res_pinned) { for (uint32_t i = 0; i < n; i++) sp.carry[sp.h_steps[i].slot] = results[i].carry_len; }
+  else host_parallel_for(n, [&](uint32_t b, uint32_t e) { for (uint32_t i = b; i < e; i++) { results[i] = sp.h_res[i]; sp.carry[sp.h_steps[i].slot] = sp.h_res[i].carry_len; } });   // a stream appears once per call: the carry writes are disjoint
   if (arena) *arena = sp.h_packed;
+  if (prof && (sp.call_no & 63) == 1) fprintf(stderr, "stream_chunks n=%u%s: table %.0f us, byte staging %.0f us, H2D + kernels + D2H results %.0f us, D2H packed %.0f us, result copy %.0f us\n", n, zc_base ? " (zero-copy input)" : "", us(t0, t1), us(t1, t2), us(t2, t3), us(t3, t4), us(t4, now()));
   return 0;
 }
+}  // extern "C++"
 int aigw_stream_chunks(aigw_ctx* ctx, const aigw_chunk_in* in, uint32_t n, aigw_chunk_result* results, const uint8_t** arena) {
   std::lock_guard<std::mutex> lk(ctx->sp.mu);
-  return stream_chunks_locked(ctx, in, n, results, arena);
+  return stream_chunks_core(ctx, n, [&](uint32_t i) { return StreamCallIn{in[i].handle, in[i].bytes, in[i].len, in[i].eos}; }, results, arena, nullptr, nullptr);
 }
-/* structure-of-arrays form: chunk i of the call = base[off[i] .. off[i]+len[i]) for stream handles[i] (batch drivers, bench config 4) */
+/* structure-of-arrays form: chunk i of the call = base[off[i] .. off[i]+len[i]) for stream handles[i] (batch drivers, bench config 4).
+ * When `base` is mapped pinned memory (aigw_host_alloc) the kernels read the chunks in place: no staging copy, no H2D of the bytes. */
 int aigw_stream_chunks_soa(aigw_ctx* ctx, const uint64_t* handles, const uint8_t* base, const uint64_t* off, const uint32_t* len, const uint8_t* eos, uint32_t n,
                            aigw_chunk_result* results, const uint8_t** arena) {
   std::lock_guard<std::mutex> lk(ctx->sp.mu);
-  std::vector<aigw_chunk_in> in(n);
-  for (uint32_t i = 0; i < n; i++) { in[i].handle = handles[i]; in[i].bytes = base + off[i]; in[i].len = len[i]; in[i].eos = eos ? eos[i] : 0u; }
-  return stream_chunks_locked(ctx, in.data(), n, results, arena);
+  const uint8_t* zc_dev = nullptr;
+  {
+    static const bool no_zc = getenv("AIGW_STREAM_NO_ZEROCOPY") != nullptr;
+    cudaPointerAttributes at;
+    if (!no_zc && base && cudaPointerGetAttributes(&at, base) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) zc_dev = (const uint8_t*)at.devicePointer;
+    else cudaGetLastError();
+  }
+  return stream_chunks_core(ctx, n, [&](uint32_t i) { return StreamCallIn{handles[i], base + off[i], len[i], eos ? (uint32_t)eos[i] : 0u}; }, results, arena, zc_dev ? base : nullptr, zc_dev);
 }
 int aigw_stream_chunk(aigw_ctx* ctx, uint64_t handle, const uint8_t* bytes, uint32_t len, int eos, uint8_t* out, uint32_t out_cap, aigw_chunk_result* res) {
   std::lock_guard<std::mutex> lk(ctx->sp.mu);
   aigw_chunk_in in; in.handle = handle; in.bytes = bytes; in.len = len; in.eos = eos ? 1u : 0u;
   const uint8_t* arena = nullptr;
-  const int rc = stream_chunks_locked(ctx, &in, 1, res, &arena);
+  const int rc = stream_chunks_core(ctx, 1, [&](uint32_t) { return StreamCallIn{in.handle, in.bytes, in.len, in.eos}; }, res, &arena, nullptr, nullptr);
   if (rc) return rc;
   const uint32_t tot = res->out_len + res->model_len;
   if (tot > out_cap) return -4;
