@@ -114,7 +114,10 @@ typedef struct aigw_usage { uint32_t input, output, total, cached, cache_creatio
 /* ---- lifecycle ----
  * One context per GPU and per calling thread: a context owns its streams, pinned arenas and workspaces and is NOT thread-safe;
  * the views a host-buffer call returns (results / out pointers) stay valid until the next host-buffer call on that context.
- * aigw_batcher_* is the one entry point meant to be called concurrently. */
+ * The *_device entry points take a caller stream but share the context's workspace, counters and timing events: at most ONE call
+ * may be in flight per context (synchronise, or order the next call after the previous one on the same stream).
+ * aigw_batcher_* is the one entry point meant to be called concurrently (its launches use no context state); aigw_stream_* calls
+ * serialise on a per-context mutex. */
 int  aigw_init(int device, aigw_ctx** ctx);          /* returns 0, or a CUDA error code; never falls back */
 void aigw_destroy(aigw_ctx* ctx);
 const char* aigw_last_error(aigw_ctx* ctx);
