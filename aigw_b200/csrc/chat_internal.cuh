@@ -74,7 +74,9 @@ enum RKid : uint8_t {
   RK_signature, RK_redactedContent, RK_stopReason, RK_usage, RK_inputTokens, RK_outputTokens, RK_totalTokens, RK_cacheReadInputTokens, RK_cacheWriteInputTokens,
   RK_serviceTier, RK_type, RK_metrics, RK_latencyMs, RK_document, RK_image, RK_toolResult, RK_cachePoint,
   // anthropic.Message (buffered GCP / AWS Anthropic responses)
-  RK_id, RK_model, RK_stop_reason, RK_thinking, RK_data, RK_input_tokens, RK_output_tokens, RK_cache_read_input_tokens, RK_cache_creation_input_tokens, RK_stop_sequence, RK_COUNT
+  RK_id, RK_model, RK_stop_reason, RK_thinking, RK_data, RK_input_tokens, RK_output_tokens, RK_cache_read_input_tokens, RK_cache_creation_input_tokens, RK_stop_sequence,
+  // error bodies (Translator.ResponseError)
+  RK_error, RK_status, RK_details, RK_code, RK_request_id, RK_COUNT
 };
 #define AIGW_RKEYS(X) \
   X("output", RK_output) X("message", RK_message) X("content", RK_content) X("role", RK_role) X("text", RK_text) X("toolUse", RK_toolUse) X("toolUseId", RK_toolUseId) \
@@ -83,7 +85,8 @@ enum RKid : uint8_t {
   X("totalTokens", RK_totalTokens) X("cacheReadInputTokens", RK_cacheReadInputTokens) X("cacheWriteInputTokens", RK_cacheWriteInputTokens) X("serviceTier", RK_serviceTier) \
   X("type", RK_type) X("metrics", RK_metrics) X("latencyMs", RK_latencyMs) X("document", RK_document) X("image", RK_image) X("toolResult", RK_toolResult) X("cachePoint", RK_cachePoint) \
   X("id", RK_id) X("model", RK_model) X("stop_reason", RK_stop_reason) X("thinking", RK_thinking) X("data", RK_data) X("input_tokens", RK_input_tokens) X("output_tokens", RK_output_tokens) \
-  X("cache_read_input_tokens", RK_cache_read_input_tokens) X("cache_creation_input_tokens", RK_cache_creation_input_tokens) X("stop_sequence", RK_stop_sequence)
+  X("cache_read_input_tokens", RK_cache_read_input_tokens) X("cache_creation_input_tokens", RK_cache_creation_input_tokens) X("stop_sequence", RK_stop_sequence) \
+  X("error", RK_error) X("status", RK_status) X("details", RK_details) X("code", RK_code) X("request_id", RK_request_id)
 
 // /v1/messages requests (P.schema & AIGW_SCHEMA_MESSAGES): the members of anthropic.MessagesRequest the restated subset knows
 // (internal/apischema/anthropic/anthropic.go:26-140); every other key has id 0 and declines the body.  Values use AIGW_VALS.

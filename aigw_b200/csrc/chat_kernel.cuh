@@ -181,7 +181,15 @@ namespace aigw {
   X(L_TITAN_OPEN, "{\"inputText\":")                                                          \
   X(L_TITAN_DIMS, ",\"dimensions\":")                                                         \
   X(L_MSG_PATH, "/v1/messages")                                                                \
-  X(L_MSG_VERSION_MEMBER, "\"anthropic_version\":")
+  X(L_MSG_VERSION_MEMBER, "\"anthropic_version\":")                                            \
+  X(L_ERR_OPEN, "{\"type\":\"error\",\"error\":{\"type\":")                                   \
+  X(L_ERR_CODE, ",\"code\":\"")                                                               \
+  X(L_ERR_MESSAGE, "\",\"message\":")                                                         \
+  X(L_ERR_CLOSE_AFTER_CODE, "\"}}")                                                            \
+  X(L_ERR_CLOSE, "}}")                                                                         \
+  X(L_ERR_T_AWS, "\"AWSBedrockBackendError\"")                                                \
+  X(L_ERR_T_GCP, "\"GCPBackendError\"")                                                       \
+  X(L_ERR_T_VERTEX, "\"GCPVertexAIBackendError\"")
 
 enum LitId : int {
 #define X(name, text) name,

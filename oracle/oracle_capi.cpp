@@ -20,6 +20,7 @@ namespace oracle { TranslateResult gemini_request_body(const ChatReq& r, const s
 #include "sha256.hpp"
 #include "embeddings.hpp"
 #include "mutate.hpp"
+#include "response_error.hpp"
 #include "messages.hpp"
 #include "stream.hpp"
 #include "translate.hpp"
@@ -245,6 +246,12 @@ int oracle_anthropic_response(const char* body, uint64_t len, const char* reques
   std::string o, rm; TokenUsage u; const Status s = anthropic_response(std::string_view(body, len), cfg, o, u, rm);
   put(usage, u); *out = dup(o); *out_len = o.size();
   uint64_t n = std::min<uint64_t>(cap, rm.size()); memcpy(model_buf, rm.data(), n); *model_len = rm.size();
+  return (int)s;
+}
+// ---- Translator.ResponseError
+int oracle_response_error(int kind, const char* body, uint64_t len, const char* status_code, const char* aws_error_type, int json_content_type, char** out, uint64_t* out_len) {
+  std::string o; const Status s = response_error(kind, std::string_view(body, len), status_code ? status_code : "", aws_error_type ? aws_error_type : "", json_content_type != 0, o);
+  *out = dup(o); *out_len = o.size();
   return (int)s;
 }
 // ---- K4: byte-level BPE token count (self-oracle)

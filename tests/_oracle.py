@@ -252,6 +252,16 @@ def anthropic_response(body: bytes, request_model: bytes, created: int):
     return st, out, u, buf.raw[:ml.value]
 
 
+def response_error(kind, body: bytes, status_code: str, aws_error_type: str = "", json_content_type=True):
+    """Translator.ResponseError (chat completions) for "aws-bedrock" | "gcp-vertexai" | "gcp-anthropicai" → (status, OpenAI error JSON bytes)."""
+    k = {"aws-bedrock": 1, "gcp-vertexai": 3, "gcp-anthropicai": 4}[kind]
+    L = lib(); L.oracle_response_error.argtypes = [C.c_int, C.c_char_p, C.c_uint64, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    vp = C.c_void_p(); n = C.c_uint64(0)
+    st = L.oracle_response_error(k, body, len(body), status_code.encode(), aws_error_type.encode(), int(json_content_type), C.byref(vp), C.byref(n))
+    out = C.string_at(vp, n.value); L.oracle_free(vp)
+    return st, out
+
+
 class AwsAnthropicStream:
     """OpenAI -> AWS Anthropic ResponseBody(stream) per call: eventstream frames with base64 Anthropic events → (status, OpenAI SSE bytes, Usage)."""
     def __init__(self, request_model: bytes, created: int):

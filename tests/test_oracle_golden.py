@@ -515,3 +515,17 @@ def test_native_anthropic_usage_reference_vectors():
     assert st == 0 and u.as_tuple() == (10, 1, 0, 0, 10, -1) and m == b"claude-sonnet-4-5-20250929"
     st, u, m = s.feed(N.TAIL.encode())
     assert st == 0 and u.as_tuple() == (10, 1, 0, 16, 26, -1) and m == b"claude-sonnet-4-5-20250929"
+
+
+def test_response_error_goldens():
+    """Translator.ResponseError: the three chat-completion error goldens of the data-plane suite, byte for byte"""
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "testupstream_cases.json"), encoding="utf-8"))["cases"]
+    code = {"http.StatusTooManyRequests": "429", "http.StatusBadRequest": "400"}
+    n = 0
+    for c in cases:
+        if c.get("backend") in ("aws-bedrock", "gcp-vertexai", "gcp-anthropicai") and c["name"].endswith("/v1/chat/completions - error response"):
+            st, out = O.response_error(c["backend"], c["responseBody"].encode(), code[str(c["expStatus"])], "ThrottledException" if c["backend"] == "aws-bedrock" else "")
+            assert st == 0 and out.decode() == c["expResponseBody"], c["name"]
+            n += 1
+    assert n == 3
+    assert O.response_error("aws-bedrock", b"backend timeout", "503", "", json_content_type=False) == (0, b'{"type":"error","error":{"type":"AWSBedrockBackendError","code":"503","message":"backend timeout"}}')
