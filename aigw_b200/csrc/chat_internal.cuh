@@ -45,7 +45,8 @@ static_assert(K_TOP_END <= 63, "top-level seen mask is 64 bits");
 static_assert(K_COUNT <= 64, "ids are 6 bits in the token word");
 enum Vid : uint8_t {
   V_NONE = 0, V_user, V_assistant, V_system, V_developer, V_tool, V_text, V_refusal, V_thinking, V_redacted_thinking, V_ephemeral,
-  V_enabled, V_disabled, V_adaptive, V_auto, V_required, V_image_url, V_input_audio, V_file
+  V_enabled, V_disabled, V_adaptive, V_auto, V_required, V_image_url, V_input_audio, V_file,
+  V_tool_use, V_tool_result, V_custom, V_any, V_none   // /v1/messages content blocks, tools, tool_choice
 };
 
 // Perfect-enough hash tables (FNV-1a, open addressing, verified by a byte compare) built at compile time and copied to
@@ -66,6 +67,10 @@ enum Vid : uint8_t {
   X("user", V_user) X("tool", V_tool) X("text", V_text) X("auto", V_auto) X("system", V_system) X("refusal", V_refusal) X("enabled", V_enabled) X("thinking", V_thinking) \
   X("disabled", V_disabled) X("adaptive", V_adaptive) X("required", V_required) X("assistant", V_assistant) X("developer", V_developer) X("ephemeral", V_ephemeral) \
   X("redacted_thinking", V_redacted_thinking) X("image_url", V_image_url) X("input_audio", V_input_audio) X("file", V_file)
+// the value strings a /v1/messages request can carry (own table: the chat table above is full enough for its 32 slots)
+#define AIGW_MVALS(X) \
+  X("user", V_user) X("assistant", V_assistant) X("text", V_text) X("ephemeral", V_ephemeral) X("auto", V_auto) X("tool", V_tool) \
+  X("tool_use", V_tool_use) X("tool_result", V_tool_result) X("custom", V_custom) X("any", V_any) X("none", V_none)
 
 // Response direction ((P.schema & 48) == AIGW_SCHEMA_RESP_AWS_BEDROCK): the index kernel loads this key table instead; ids share
 // the 6-bit field of the token word.  awsbedrock.ConverseResponse, internal/apischema/awsbedrock/awsbedrock.go:178-182,264-279,330-432.
@@ -91,13 +96,18 @@ enum RKid : uint8_t {
 // /v1/messages requests (P.schema & AIGW_SCHEMA_MESSAGES): the members of anthropic.MessagesRequest the restated subset knows
 // (internal/apischema/anthropic/anthropic.go:26-140); every other key has id 0 and declines the body.  Values use AIGW_VALS.
 enum MKid : uint8_t {
-  MK_NONE = 0, MK_model, MK_max_tokens, MK_messages, MK_stream, MK_system, MK_temperature, MK_top_p, MK_top_k, MK_stop_sequences, MK_metadata, MK_user_id, MK_role, MK_content,
-  MK_type, MK_text, MK_cache_control, MK_anthropic_version, MK_COUNT
+  MK_NONE = 0, MK_model, MK_max_tokens, MK_messages, MK_stream, MK_system, MK_temperature, MK_top_p, MK_top_k, MK_stop_sequences, MK_metadata,
+  MK_tools, MK_tool_choice,   // top-level members only the full re-maps (OpenAI / Bedrock targets, plan_messages_full) take
+  MK_user_id, MK_role, MK_content, MK_type, MK_text, MK_cache_control, MK_anthropic_version,
+  MK_id, MK_name, MK_input, MK_tool_use_id, MK_is_error, MK_description, MK_input_schema, MK_properties, MK_required, MK_disable_parallel_tool_use, MK_COUNT
 };
+static_assert(MK_COUNT <= 64, "ids are 6 bits in the token word");
 #define AIGW_MKEYS(X) \
   X("model", MK_model) X("max_tokens", MK_max_tokens) X("messages", MK_messages) X("stream", MK_stream) X("system", MK_system) X("temperature", MK_temperature) X("top_p", MK_top_p) \
   X("top_k", MK_top_k) X("stop_sequences", MK_stop_sequences) X("metadata", MK_metadata) X("user_id", MK_user_id) X("role", MK_role) X("content", MK_content) X("type", MK_type) \
-  X("text", MK_text) X("cache_control", MK_cache_control) X("anthropic_version", MK_anthropic_version)
+  X("text", MK_text) X("cache_control", MK_cache_control) X("anthropic_version", MK_anthropic_version) X("tools", MK_tools) X("tool_choice", MK_tool_choice) X("id", MK_id) \
+  X("name", MK_name) X("input", MK_input) X("tool_use_id", MK_tool_use_id) X("is_error", MK_is_error) X("description", MK_description) X("input_schema", MK_input_schema) \
+  X("properties", MK_properties) X("required", MK_required) X("disable_parallel_tool_use", MK_disable_parallel_tool_use)
 
 static constexpr int kKeySlots = 128, kValSlots = 32, kMaxIdLen = 28, kIdWords = 7;
 // slot = { seven little-endian words of the string zero-padded to 28 bytes, len | id << 8 }
@@ -154,11 +164,11 @@ constexpr IdTables make_msg_id_tables() {
   AIGW_MKEYS(X)
 #undef X
 #define X(lit, idv) id_insert(t.val, kValSlots, lit, idv);
-  AIGW_VALS(X)
+  AIGW_MVALS(X)
 #undef X
   return t;
 }
-static_assert(id_max_probe(make_msg_id_tables().key, kKeySlots) <= 6, "messages id hash table needs more than 6 probes");
+static_assert(id_max_probe(make_msg_id_tables().key, kKeySlots) <= 6 && id_max_probe(make_msg_id_tables().val, kValSlots) <= 6, "messages id hash table needs more than 6 probes");
 static __device__ __constant__ IdTables c_ids_msg = make_msg_id_tables();
 
 // id of a short string (1 ≤ n ≤ kMaxIdLen) held in shared memory, against the key or the value table (also in shared

@@ -189,7 +189,28 @@ namespace aigw {
   X(L_ERR_CLOSE, "}}")                                                                         \
   X(L_ERR_T_AWS, "\"AWSBedrockBackendError\"")                                                \
   X(L_ERR_T_GCP, "\"GCPBackendError\"")                                                       \
-  X(L_ERR_T_VERTEX, "\"GCPVertexAIBackendError\"")
+  X(L_ERR_T_VERTEX, "\"GCPVertexAIBackendError\"")                                            \
+  X(L_MX_OPEN, "{\"messages\":")                                                               \
+  X(L_MX_CONTENT_Q, "{\"content\":\"")                                                         \
+  X(L_MX_SYS_CLOSE, "\",\"role\":\"system\"}")                                                 \
+  X(L_MX_USER_CLOSE_Q, "\",\"role\":\"user\"}")                                                \
+  X(L_MX_TOOL_MID, "\",\"role\":\"tool\",\"tool_call_id\":")                                  \
+  X(L_MX_ASST_OPEN, "{\"role\":\"assistant\",\"content\":")                                   \
+  X(L_MX_MAXCT, ",\"max_completion_tokens\":")                                                 \
+  X(L_MX_TOPP, ",\"top_p\":")                                                                  \
+  X(L_MX_TOOLS, ",\"tools\":[")                                                                \
+  X(L_MX_TOOL_OPEN, "{\"type\":\"function\",\"function\":{\"name\":")                          \
+  X(L_MX_SCHEMA_TYPE, "{\"type\":")                                                            \
+  X(L_MX_PROPS, ",\"properties\":")                                                            \
+  X(L_MX_REQUIRED, ",\"required\":[")                                                          \
+  X(L_MX_TC_AUTO, ",\"tool_choice\":\"auto\"")                                                 \
+  X(L_MX_TC_NONE, ",\"tool_choice\":\"none\"")                                                 \
+  X(L_MX_TC_REQUIRED, ",\"tool_choice\":\"required\"")                                         \
+  X(L_MX_TC_NAMED, ",\"tool_choice\":{\"type\":\"function\",\"function\":{\"name\":")         \
+  X(L_MX_STOP, ",\"stop\":[")                                                                  \
+  X(L_MX_TOPK, "\"additionalModelRequestFields\":{\"top_k\":")                                 \
+  X(L_MX_TR_NULL, "{\"toolResult\":{\"content\":null")                                         \
+  X(L_MX_TR_STATUS_ERR, ",\"status\":\"error\",\"toolUseId\":")
 
 enum LitId : int {
 #define X(name, text) name,

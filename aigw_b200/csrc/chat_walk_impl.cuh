@@ -169,6 +169,10 @@ struct Plan {
     const uint32_t o = c_lits.off[id], l = c_lits.off[id + 1] - o;
     if (sys) push_sys(1, o, l); else push(1, o, l);
   }
+  __device__ __forceinline__ void lit_tail(int id, uint32_t skip) {   // literal `id` without its first `skip` bytes
+    const uint32_t o = c_lits.off[id], l = c_lits.off[id + 1] - o;
+    push(1, o + skip, l - skip);
+  }
   __device__ __forceinline__ void src(const Doc& d, uint32_t off, uint32_t len, bool sys = false) {
     if (sys) push_sys(d.kind, off, len); else push(d.kind, off, len);
   }
@@ -358,10 +362,10 @@ struct Walker {
   // a u-escape becomes the character itself (UTF-8; surrogate pairs joined) except for control characters (the two-byte escapes
   // of newline, carriage return, tab, or a lower-case u-escape), the quote and the backslash.  Unchanged stretches stay input ops,
   // each run of rewritten escapes becomes one scratch op.  Lone surrogates and malformed hex are left to the stock path.
-  __device__ void emit_str_respelled(int v, bool sys) {
+  __device__ void emit_str_respelled(int v, bool sys, bool inner = false) {   // inner: without the surrounding quotes
     const uint32_t q0 = d.tok(v), q1 = d.tok(v + 1);
     const uint8_t* s = d.s;
-    uint32_t seg = q0, i = q0 + 1, run_start = sc.n;
+    uint32_t seg = inner ? q0 + 1 : q0, i = q0 + 1, run_start = sc.n;
     bool in_run = false;
     auto put = [&](uint32_t kind, uint32_t off, uint32_t len) { if (!len) return; if (sys) pl.push_sys(kind, off, len); else pl.push(kind, off, len); };
     while (i < q1) {
@@ -401,7 +405,7 @@ struct Walker {
       sc.n += w; i += used;
     }
     if (in_run) { put(2, run_start, sc.n - run_start); seg = q1; }
-    put(d.kind, seg, q1 + 1u - seg);
+    put(d.kind, seg, (inner ? q1 : q1 + 1u) - seg);
   }
 
   // value token of member `key` in object `obj`, -1 when absent or null; duplicates decline
@@ -1634,7 +1638,7 @@ struct Walker {
       uint32_t seen = 0;
       for (int m = 1; d.ty(m) != '}'; m = d.after(m + 3)) {
         const uint32_t id = d.id(m);
-        if (id == MK_NONE || id >= MK_user_id) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }   // top-level members are ids 1..metadata
+        if (id == MK_NONE || id > MK_metadata) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }   // top-level members are ids 1..metadata (tools / tool_choice: only the full re-maps)
         if (seen & (1u << id)) { decline(AIGW_R_DUP_KEY); return; }
         seen |= 1u << id;
         const int v = m + 3; const bool nul = is_null(v);
@@ -1733,6 +1737,410 @@ struct Walker {
     if (!first) pl.lit(L_COMMA);
     pl.lit(L_MSG_VERSION_MEMBER); pl.lit(L_QUOTE); emit_cfg_text(P->api_version, P->version_len); pl.lit(L_QUOTE);
     pl.lit(L_RBRACE);
+  }
+
+  // ---- /v1/messages to the backends that need a full re-map (T5, second part): OpenAI chat completions
+  // (anthropic_openai.go:55-93, buildOpenAIChatCompletionRequest openai_helper.go:27-261, field order of openai.ChatCompletionRequest
+  // openai.go:947-1131) and AWS Bedrock Converse (anthropic_awsbedrock.go:52-163,176-395).  The accepted subset is the one
+  // include/aigw_b200.h names; problems are reported in member order (the first one decides), as the decoder would meet them.
+  struct MxTop { int model, max_tokens, temperature, top_p, top_k, stream, stop, system, messages, tools, tool_choice; };
+  __device__ bool mx_cache_ok(int v) {   // exactly {"type":"ephemeral"}
+    if (!is_obj(v)) return false;
+    const int k = v + 1;
+    return d.ty(k) != '}' && d.id(k) == MK_type && is_str(k + 3) && d.id(k + 3) == V_ephemeral && d.ty(d.after(k + 3)) == '}';
+  }
+  // one content block of a message: 0 text, 1 tool_use, 2 tool_result, -1 declined
+  __device__ int mx_block(int b) {
+    if (!is_obj(b)) { decline(AIGW_R_UNSUPPORTED_FIELD); return -1; }
+    int ty = -1;
+    for (int m = b + 1; d.ty(m) != '}'; m = d.after(m + 3)) if (d.id(m) == MK_type) { if (ty >= 0) { decline(AIGW_R_DUP_KEY); return -1; } ty = m + 3; }
+    if (ty < 0 || !is_str(ty)) { decline(AIGW_R_UNSUPPORTED_FIELD); return -1; }
+    const uint32_t tv = d.id(ty);
+    if (tv == V_text) return msg_text_block(b) ? 0 : -1;
+    if (tv != V_tool_use && tv != V_tool_result) { decline(AIGW_R_UNSUPPORTED_FIELD); return -1; }
+    uint32_t seen = 0;
+    for (int m = b + 1; d.ty(m) != '}'; m = d.after(m + 3)) {
+      const uint32_t id = d.id(m); const int v = m + 3;
+      if (id == MK_NONE || (seen & (1u << (id & 31u)))) { decline(AIGW_R_UNSUPPORTED_FIELD); return -1; }
+      seen |= 1u << (id & 31u);
+      bool ok = true;
+      if (id == MK_type) continue;
+      if (id == MK_cache_control) ok = mx_cache_ok(v);
+      else if (tv == V_tool_use) {
+        if (id == MK_id || id == MK_name) ok = is_str(v);
+        else if (id == MK_input) ok = is_null(v) || is_obj(v);
+        else ok = false;
+      } else {
+        if (id == MK_tool_use_id) ok = is_str(v);
+        else if (id == MK_is_error) ok = is_bool(v);
+        else if (id == MK_content) {
+          if (is_arr(v)) { for (int q = v + 1; d.ty(q) != ']'; q = d.after(q)) if (!msg_text_block(q)) return -1; }
+          else ok = is_null(v) || is_str(v);
+        } else ok = false;
+      }
+      if (!ok) { decline(AIGW_R_UNSUPPORTED_FIELD); return -1; }
+    }
+    const uint32_t need = tv == V_tool_use ? ((1u << (MK_id & 31u)) | (1u << (MK_name & 31u))) : (1u << (MK_tool_use_id & 31u));
+    if ((seen & need) != need) { decline(AIGW_R_UNSUPPORTED_FIELD); return -1; }
+    return tv == V_tool_use ? 1 : 2;
+  }
+  // non-negative integer literal of at most 15 digits, optionally followed by ".0…0" (float64 field, int64() conversion): digit count or 0
+  __device__ uint32_t mx_plain_int(int v) {
+    const uint32_t o = d.tok(v), e = d.scalar_end(v);
+    uint32_t i = o; while (i < e && is_digit(d.s[i])) i++;
+    const uint32_t nd = i - o;
+    if (nd == 0 || nd > 15 || (nd > 1 && d.s[o] == '0')) return 0;
+    if (i < e) { if (d.s[i] != '.' || i + 1 == e) return 0; for (uint32_t k = i + 1; k < e; k++) if (d.s[k] != '0') return 0; }
+    return nd;
+  }
+  __device__ bool mx_scan(MxTop& t) {
+    t.model = t.max_tokens = t.temperature = t.top_p = t.top_k = t.stream = t.stop = t.system = t.messages = t.tools = t.tool_choice = -1;
+    if (is_null(0)) return true;
+    if (!is_obj(0)) { decline(AIGW_R_E400_TYPE); return false; }
+    uint32_t seen = 0;
+    for (int m = 1; d.ty(m) != '}'; m = d.after(m + 3)) {
+      const uint32_t id = d.id(m);
+      if (id == MK_NONE || id > MK_tool_choice) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
+      if (seen & (1u << id)) { decline(AIGW_R_DUP_KEY); return false; }
+      seen |= 1u << id;
+      const int v = m + 3; const bool nul = is_null(v);
+      switch (id) {
+        case MK_model: if (!nul) { if (!is_str(v)) { decline(AIGW_R_E400_TYPE); return false; } t.model = v; } break;
+        case MK_max_tokens: if (!nul) { if (!is_num(v)) { decline(AIGW_R_E400_TYPE); return false; } if (!mx_plain_int(v)) { decline(AIGW_R_NUMBER); return false; } t.max_tokens = v; } break;
+        case MK_temperature: if (!nul) { if (!is_num(v)) { decline(AIGW_R_E400_TYPE); return false; } t.temperature = v; } break;
+        case MK_top_p: if (!nul) { if (!is_num(v)) { decline(AIGW_R_E400_TYPE); return false; } t.top_p = v; } break;
+        case MK_top_k:
+          if (!nul) {
+            if (!is_num(v)) { decline(AIGW_R_E400_TYPE); return false; }
+            const uint32_t o = d.tok(v), e = d.scalar_end(v);
+            if (e - o > 9u) { decline(AIGW_R_NUMBER); return false; }
+            for (uint32_t i = o; i < e; i++) if (!is_digit(d.s[i])) { decline(AIGW_R_NUMBER); return false; }
+            t.top_k = v;
+          }
+          break;
+        case MK_stream: if (!nul) { if (!is_bool(v)) { decline(AIGW_R_E400_TYPE); return false; } t.stream = v; } break;
+        case MK_stop_sequences:
+          if (!nul) { if (!is_arr(v)) { decline(AIGW_R_E400_TYPE); return false; } for (int q = v + 1; d.ty(q) != ']'; q = d.after(q)) if (!is_str(q)) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; } t.stop = v; }
+          break;
+        case MK_metadata:
+          if (!nul) {
+            if (!is_obj(v)) { decline(AIGW_R_E400_TYPE); return false; }
+            const int k = v + 1;
+            if (d.ty(k) != '}') {
+              if (d.ty(d.after(k + 3)) != '}') { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
+              if (d.id(k) != MK_user_id || !(is_str(k + 3) || is_null(k + 3))) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
+            }
+          }
+          break;
+        case MK_system:
+          t.system = v;
+          if (is_str(v)) break;
+          if (!is_arr(v)) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
+          for (int q = v + 1; d.ty(q) != ']'; q = d.after(q)) if (!msg_text_block(q)) return false;
+          break;
+        case MK_messages:
+          if (nul) break;
+          if (!is_arr(v)) { decline(AIGW_R_E400_TYPE); return false; }
+          t.messages = v;
+          for (int q = v + 1; d.ty(q) != ']'; q = d.after(q)) {
+            if (!is_obj(q)) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
+            uint32_t ms = 0;
+            for (int k = q + 1; d.ty(k) != '}'; k = d.after(k + 3)) {
+              const int cv = k + 3;
+              if (d.id(k) == MK_role) { if ((ms & 1u) || !is_str(cv)) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; } ms |= 1u; }
+              else if (d.id(k) == MK_content) {
+                if (ms & 2u) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
+                ms |= 2u;
+                if (is_str(cv)) continue;
+                if (!is_arr(cv)) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
+                for (int b = cv + 1; d.ty(b) != ']'; b = d.after(b)) if (mx_block(b) < 0) return false;
+              } else { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
+            }
+            if (ms != 3u) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
+          }
+          break;
+        case MK_tools:
+          if (nul) break;
+          if (!is_arr(v)) { decline(AIGW_R_E400_TYPE); return false; }
+          t.tools = v;
+          for (int q = v + 1; d.ty(q) != ']'; q = d.after(q)) {
+            if (!is_obj(q)) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
+            uint32_t ts = 0;
+            for (int k = q + 1; d.ty(k) != '}'; k = d.after(k + 3)) {
+              const uint32_t kid = d.id(k); const int tv = k + 3;
+              if (kid == MK_NONE || (ts & (1u << (kid & 31u)))) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
+              ts |= 1u << (kid & 31u);
+              bool ok;
+              if (kid == MK_type) ok = is_str(tv) && (d.str_len(tv) == 0 || d.id(tv) == V_custom);
+              else if (kid == MK_name || kid == MK_description) ok = is_str(tv);
+              else if (kid == MK_cache_control) ok = mx_cache_ok(tv);
+              else if (kid == MK_input_schema) {
+                ok = is_obj(tv);
+                if (ok) {
+                  // members the decoder keeps: type / properties / required, each at most once; every other member is dropped, so a
+                  // second spelling of a dropped key is harmless for the decoder, but duplicates are outside the decided subset everywhere else, so here too
+                  for (int s = tv + 1; ok && d.ty(s) != '}'; s = d.after(s + 3)) {
+                    if (d.str_has_backslash(s)) { ok = false; break; }
+                    for (int s2 = tv + 1; s2 != s; s2 = d.after(s2 + 3)) if (cmp_keys(d, s, s2) == 0) { ok = false; break; }
+                    if (!ok) break;
+                    const uint32_t sid = d.id(s); const int sv = s + 3;
+                    if (sid == MK_type) ok = is_str(sv);
+                    else if (sid == MK_properties) ok = is_null(sv) || is_obj(sv);
+                    else if (sid == MK_required) { ok = is_null(sv) || is_arr(sv); if (ok && is_arr(sv)) for (int e = sv + 1; d.ty(e) != ']'; e = d.after(e)) if (!is_str(e)) { ok = false; break; } }
+                  }
+                }
+              }
+              else ok = false;
+              if (!ok) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
+            }
+            const uint32_t need = (1u << (MK_name & 31u)) | (1u << (MK_input_schema & 31u));
+            if ((ts & need) != need) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
+          }
+          break;
+        case MK_tool_choice: {
+          if (nul) break;
+          if (!is_obj(v)) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
+          int ty = -1, nm = -1; uint32_t cs = 0;
+          for (int k = v + 1; d.ty(k) != '}'; k = d.after(k + 3)) {
+            const uint32_t kid = d.id(k);
+            if (kid == MK_NONE || (cs & (1u << (kid & 31u)))) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
+            cs |= 1u << (kid & 31u);
+            if (kid == MK_type) ty = k + 3;
+            else if (kid == MK_name) nm = k + 3;
+            else if (kid == MK_disable_parallel_tool_use) { if (!(is_bool(k + 3) || is_null(k + 3))) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; } }
+            else { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
+          }
+          if (ty < 0 || !is_str(ty)) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
+          const uint32_t tv = d.id(ty);
+          const bool known = tv == V_auto || tv == V_any || tv == V_none || tv == V_tool;
+          if (!known || (tv == V_tool ? (nm < 0 || !is_str(nm)) : nm >= 0)) { decline(AIGW_R_UNSUPPORTED_FIELD); return false; }
+          t.tool_choice = v;
+          break;
+        }
+      }
+    }
+    return true;
+  }
+  // the decoded bytes of string token v without the surrounding quotes (concatenation of text blocks into one JSON string)
+  __device__ __forceinline__ void emit_str_inner(int v) {
+    if (d.str_nc(v)) emit_str_respelled(v, false, true);
+    else pl.src(d, d.tok(v) + 1u, d.str_len(v));
+  }
+  // anthropicContentToText (openai_helper.go:194-205) of an array content: is the concatenation non-empty / emit its inner bytes
+  __device__ bool mx_array_text_nonempty(int arr) {
+    for (int b = arr + 1; d.ty(b) != ']'; b = d.after(b)) {
+      const int ty = find(b, MK_type);
+      if (ty >= 0 && d.id(ty) == V_text) { const int tx = find(b, MK_text); if (tx >= 0 && d.str_len(tx)) return true; }
+    }
+    return false;
+  }
+  __device__ void mx_array_text_inner(int arr) {
+    for (int b = arr + 1; d.ty(b) != ']'; b = d.after(b)) {
+      const int ty = find(b, MK_type);
+      if (ty >= 0 && d.id(ty) == V_text) { const int tx = find(b, MK_text); if (tx >= 0) emit_str_inner(tx); }
+    }
+  }
+  __device__ int mx_role(int msg) { const int r = find(msg, MK_role); return r < 0 ? 0 : (int)d.id(r); }
+  __device__ int mx_block_kind(int b) { const int ty = find(b, MK_type); const uint32_t tv = ty < 0 ? 0u : d.id(ty); return tv == V_text ? 0 : tv == V_tool_use ? 1 : tv == V_tool_result ? 2 : -1; }
+  // ToolInputSchema marshalled: {"type":T[,"properties":{…}][,"required":[…]]}  (anthropic.go:1097-1101)
+  __device__ void mx_schema(int sch) {
+    const int ty = find(sch, MK_type), pr = find(sch, MK_properties), rq = find(sch, MK_required);
+    pl.lit(L_MX_SCHEMA_TYPE);
+    if (ty >= 0) emit_str(ty); else pl.lit(L_EMPTY_STR);
+    if (pr >= 0 && d.ty(pr + 1) != '}') { pl.lit(L_MX_PROPS); emit_any(d, pl, pr); }
+    if (rq >= 0 && d.ty(rq + 1) != ']') {
+      pl.lit(L_MX_REQUIRED);
+      for (int e = rq + 1; d.ty(e) != ']'; e = d.after(e)) { if (e != rq + 1) pl.lit(L_COMMA); emit_str(e); }
+      pl.lit(L_RBRACK);
+    }
+    pl.lit(L_RBRACE);
+  }
+  __device__ void mx_str_array(int arr) { for (int e = arr + 1; d.ty(e) != ']'; e = d.after(e)) { if (e != arr + 1) pl.lit(L_COMMA); emit_str(e); } }
+  __device__ void mx_max_tokens(const MxTop& t) { if (t.max_tokens >= 0) pl.src(d, d.tok(t.max_tokens), mx_plain_int(t.max_tokens)); else pl.lit(L_ZERO); }
+
+  __device__ void mx_openai(const MxTop& t, bool stream) {
+    // stop sequences: sjson marshals the []string with encoding/json; only spellings it shares with sonic are decided here
+    if (t.stop >= 0) for (int e = t.stop + 1; d.ty(e) != ']'; e = d.after(e)) {
+      if (d.str_nc(e)) { decline(AIGW_R_ESCAPE); return; }
+      const uint32_t o = d.str_off(e), n = d.str_len(e);
+      for (uint32_t i = 0; i < n; i++) { const uint32_t c = d.s[o + i]; if (c >= 0x7fu || c == '<' || c == '>' || c == '&') { decline(AIGW_R_UNSUPPORTED_FIELD); return; } }
+    }
+    pl.lit(L_MX_OPEN);
+    bool any = false;
+    auto sep = [&] { pl.lit(any ? L_COMMA : L_LBRACK); any = true; };
+    if (t.system >= 0) {
+      const int sv = t.system;
+      if (is_str(sv)) { if (d.str_len(sv)) { sep(); pl.lit(L_MX_CONTENT_Q); emit_str_inner(sv); pl.lit(L_MX_SYS_CLOSE); } }
+      else {
+        bool ne = false; for (int q = sv + 1; d.ty(q) != ']'; q = d.after(q)) { const int tx = find(q, MK_text); if (tx >= 0 && d.str_len(tx)) ne = true; }
+        if (ne) { sep(); pl.lit(L_MX_CONTENT_Q); for (int q = sv + 1; d.ty(q) != ']'; q = d.after(q)) { const int tx = find(q, MK_text); if (tx >= 0) emit_str_inner(tx); } pl.lit(L_MX_SYS_CLOSE); }
+      }
+    }
+    if (t.messages >= 0) for (int q = t.messages + 1; d.ty(q) != ']'; q = d.after(q)) {
+      if (bad()) return;
+      const int role = mx_role(q), c = find(q, MK_content);
+      if (c < 0) continue;   // cannot happen: content was required and is a string or an array
+      if (role == V_user) {
+        if (is_arr(c)) for (int b = c + 1; d.ty(b) != ']'; b = d.after(b)) {
+          if (mx_block_kind(b) != 2) continue;
+          sep(); pl.lit(L_MX_CONTENT_Q);
+          const int rc = find(b, MK_content);
+          if (rc >= 0) { if (is_str(rc)) emit_str_inner(rc); else mx_array_text_inner_items(rc); }
+          pl.lit(L_MX_TOOL_MID); emit_str(find(b, MK_tool_use_id)); pl.lit(L_RBRACE);
+        }
+        if (is_str(c)) { if (d.str_len(c)) { sep(); pl.lit(L_EM_CONTENT); emit_str(c); pl.lit_tail(L_MX_USER_CLOSE_Q, 1); } }
+        else if (mx_array_text_nonempty(c)) { sep(); pl.lit(L_MX_CONTENT_Q); mx_array_text_inner(c); pl.lit(L_MX_USER_CLOSE_Q); }
+      } else if (role == V_assistant) {
+        sep(); pl.lit(L_MX_ASST_OPEN);
+        if (is_str(c)) { if (d.str_len(c)) emit_str(c); else pl.lit(L_NULL); }
+        else if (mx_array_text_nonempty(c)) { pl.lit(L_QUOTE); mx_array_text_inner(c); pl.lit(L_QUOTE); }
+        else pl.lit(L_NULL);
+        bool calls = false;
+        if (is_arr(c)) for (int b = c + 1; d.ty(b) != ']'; b = d.after(b)) {
+          if (mx_block_kind(b) != 1) continue;
+          { pl.lit(L_COMMA); if (!calls) pl.lit(L_R_TOOLCALLS); }; calls = true;
+          pl.lit(L_R_TC_ID); emit_str(find(b, MK_id)); pl.lit(L_R_TC_ARGS);
+          const int in = find(b, MK_input);
+          if (in >= 0) emit_escaped_json(in); else pl.lit(L_NULL);
+          if (bad()) return;
+          pl.lit(L_R_TC_NAME); emit_str(find(b, MK_name)); pl.lit(L_R_TC_END);
+        }
+        if (calls) pl.lit(L_RBRACK);
+        pl.lit(L_RBRACE);
+      }
+    }
+    pl.lit(any ? L_RBRACK : L_NULL);
+    pl.lit(L_R_MODEL_KEY);
+    if (P->override_len) { pl.lit(L_QUOTE); emit_cfg_text(P->override_model, P->override_len); pl.lit(L_QUOTE); } else emit_str(t.model);
+    pl.lit(L_MX_MAXCT); mx_max_tokens(t);
+    if (stream) { pl.lit(L_AN_STREAM); pl.lit(L_COMMA); pl.lit(L_STREAMOPT_APPEND); };
+    if (t.temperature >= 0) { pl.lit(L_COMMA); pl.lit(L_TEMP); emit_num_field(t.temperature, false); }
+    if (t.top_p >= 0) { pl.lit(L_MX_TOPP); emit_num_field(t.top_p, false); }
+    if (t.tools >= 0 && d.ty(t.tools + 1) != ']') {
+      pl.lit(L_MX_TOOLS);
+      for (int q = t.tools + 1; d.ty(q) != ']'; q = d.after(q)) {
+        if (bad()) return;
+        if (q != t.tools + 1) pl.lit(L_COMMA);
+        pl.lit(L_MX_TOOL_OPEN); emit_str(find(q, MK_name));
+        const int ds = find(q, MK_description);
+        if (ds >= 0 && d.str_len(ds)) { pl.lit(L_COMMA); pl.lit(L_DESC); emit_str(ds); }
+        pl.lit(L_COMMA); pl.lit(L_GEM_PARAMS); mx_schema(find(q, MK_input_schema)); pl.lit(L_R_RBRACE2);
+      }
+      pl.lit(L_RBRACK);
+      if (t.tool_choice >= 0) {
+        const uint32_t tv = d.id(find(t.tool_choice, MK_type));
+        if (tv == V_auto) pl.lit(L_MX_TC_AUTO); else if (tv == V_none) pl.lit(L_MX_TC_NONE); else if (tv == V_any) pl.lit(L_MX_TC_REQUIRED);
+        else { pl.lit(L_MX_TC_NAMED); emit_str(find(t.tool_choice, MK_name)); pl.lit(L_R_RBRACE2); }
+      }
+    }
+    if (t.stop >= 0 && d.ty(t.stop + 1) != ']') { pl.lit(L_MX_STOP); mx_str_array(t.stop); pl.lit(L_RBRACK); }
+    pl.lit(L_RBRACE);
+  }
+  // the text items of a tool_result's array content, inner bytes (toolResultToText, openai_helper.go:160-175)
+  __device__ void mx_array_text_inner_items(int arr) { for (int q = arr + 1; d.ty(q) != ']'; q = d.after(q)) { const int tx = find(q, MK_text); if (tx >= 0) emit_str_inner(tx); } }
+
+  // convertToolResultBlock (anthropic_awsbedrock.go:264-291)
+  __device__ void mx_bedrock_tool_result(int b) {
+    const int rc = find(b, MK_content), ie = find(b, MK_is_error);
+    if (rc >= 0 && is_str(rc) && d.str_len(rc)) { pl.lit(L_TOOLRESULT_OPEN); pl.lit(L_TEXT_OPEN); emit_str(rc); pl.lit(L_RBRACE); pl.lit(L_RBRACK); }
+    else if (rc >= 0 && is_arr(rc) && d.ty(rc + 1) != ']') {
+      pl.lit(L_TOOLRESULT_OPEN);
+      for (int q = rc + 1; d.ty(q) != ']'; q = d.after(q)) { if (q != rc + 1) pl.lit(L_COMMA); pl.lit(L_TEXT_OPEN); emit_str(find(q, MK_text)); pl.lit(L_RBRACE); }
+      pl.lit(L_RBRACK);
+    } else pl.lit(L_MX_TR_NULL);
+    if (ie >= 0 && d.ty(ie) == 't') pl.lit(L_MX_TR_STATUS_ERR); else pl.lit_tail(L_TOOLRESULT_MID, 1);
+    emit_str(find(b, MK_tool_use_id)); pl.lit(L_TOOLRESULT_CLOSE);
+  }
+  __device__ void mx_bedrock(const MxTop& t) {
+    pl.lit(L_LBRACE);
+    if (t.top_k >= 0) { pl.lit(L_MX_TOPK); pl.src(d, d.tok(t.top_k), d.scalar_end(t.top_k) - d.tok(t.top_k)); pl.lit(L_RBRACE); pl.lit(L_COMMA); }
+    pl.lit(L_INF_OPEN); pl.lit(L_MAXTOK); mx_max_tokens(t);
+    if (t.stop >= 0 && d.ty(t.stop + 1) != ']') { pl.lit(L_COMMA); pl.lit(L_STOPSEQ); mx_str_array(t.stop); pl.lit(L_RBRACK); }
+    if (t.temperature >= 0) { pl.lit(L_COMMA); pl.lit(L_TEMP); emit_num_field(t.temperature, false); }
+    if (t.top_p >= 0) { pl.lit(L_COMMA); pl.lit(L_TOPP); emit_num_field(t.top_p, false); }
+    pl.lit(L_INF_CLOSE_MSGS);
+    bool first = true;
+    if (t.messages >= 0) for (int q = t.messages + 1; d.ty(q) != ']'; q = d.after(q)) {
+      if (bad()) return;
+      const int role = mx_role(q), c = find(q, MK_content);
+      if (role != V_user && role != V_assistant) { pend(AIGW_R_E422_ROLE); return; }   // "unexpected role: …"
+      const bool user = role == V_user;
+      if (!first) pl.lit(L_COMMA); first = false;
+      pl.lit(L_MSG_CONTENT_OPEN);
+      if (c >= 0 && is_str(c)) { if (d.str_len(c)) { pl.lit(L_TEXT_OPEN); emit_str(c); pl.lit(L_RBRACE); } }
+      else if (c >= 0) {
+        bool bf = true;
+        for (int b = c + 1; d.ty(b) != ']'; b = d.after(b)) {
+          const int k = mx_block_kind(b);
+          if (!(k == 0 || (user && k == 2) || (!user && k == 1))) continue;
+          if (!bf) pl.lit(L_COMMA); bf = false;
+          if (k == 0) { pl.lit(L_TEXT_OPEN); emit_str(find(b, MK_text)); pl.lit(L_RBRACE); }
+          else if (k == 2) mx_bedrock_tool_result(b);
+          else {
+            pl.lit(L_TOOLUSE_OPEN); emit_str(find(b, MK_name)); pl.lit(L_TOOLUSE_INPUT);
+            const int in = find(b, MK_input);
+            if (in >= 0) emit_any(d, pl, in); else pl.lit(L_NULL);
+            pl.lit(L_TOOLUSE_ID); emit_str(find(b, MK_id)); pl.lit(L_TOOLRESULT_CLOSE);
+          }
+        }
+      }
+      pl.lit(user ? L_USER_CLOSE : L_ASST_CLOSE);
+    }
+    pl.lit(L_RBRACK);
+    if (t.system >= 0) {   // convertSystemPrompt (:332-345); an empty slice is dropped by omitempty
+      const int sv = t.system;
+      if (is_str(sv)) { if (d.str_len(sv)) { pl.lit(L_SYSTEM_OPEN); pl.lit(L_TEXT_OPEN); emit_str(sv); pl.lit(L_RBRACE); pl.lit(L_RBRACK); } }
+      else if (d.ty(sv + 1) != ']') {
+        pl.lit(L_SYSTEM_OPEN);
+        for (int q = sv + 1; d.ty(q) != ']'; q = d.after(q)) { if (q != sv + 1) pl.lit(L_COMMA); pl.lit(L_TEXT_OPEN); emit_str(find(q, MK_text)); pl.lit(L_RBRACE); }
+        pl.lit(L_RBRACK);
+      }
+    }
+    if (t.tools >= 0 && d.ty(t.tools + 1) != ']') {   // convertTools (:347-395)
+      pl.lit(L_TOOLCFG_OPEN);
+      if (t.tool_choice >= 0) {
+        const uint32_t tv = d.id(find(t.tool_choice, MK_type));
+        if (tv == V_auto) pl.lit(L_TOOLCHOICE_AUTO); else if (tv == V_any) pl.lit(L_TOOLCHOICE_ANY);
+        else if (tv == V_tool) { pl.lit(L_TOOLCHOICE_TOOL); emit_str(find(t.tool_choice, MK_name)); pl.lit(L_TOOLCHOICE_TOOL_END); }
+      }
+      pl.lit(L_TOOLS_OPEN);
+      for (int q = t.tools + 1; d.ty(q) != ']'; q = d.after(q)) {
+        if (bad()) return;
+        if (q != t.tools + 1) pl.lit(L_COMMA);
+        pl.lit(L_TOOLSPEC_OPEN);
+        const int ds = find(q, MK_description);
+        if (ds >= 0 && d.str_len(ds)) { pl.lit(L_DESC); emit_str(ds); pl.lit(L_COMMA); }
+        pl.lit(L_INPUTSCHEMA); mx_schema(find(q, MK_input_schema)); pl.lit(L_NAME); emit_str(find(q, MK_name)); pl.lit(L_R_RBRACE2);
+      }
+      pl.lit(L_TOOLS_CLOSE);
+    }
+    pl.lit(L_RBRACE);
+  }
+  __device__ void plan_messages_full(uint32_t& path_len, uint32_t& model_off, uint32_t& model_len, uint32_t& out_flags, uint32_t& body_kind) {
+    const int base = P->schema & 15;
+    body_kind = AIGW_BODY_BYTES;
+    MxTop t;
+    if (!mx_scan(t)) return;
+    if (bad()) return;
+    if (t.model < 0 || d.str_len(t.model) == 0) { decline(AIGW_R_E422_MODEL); return; }   // "model field is required"
+    if (d.str_has_backslash(t.model)) { decline(AIGW_R_ESCAPE); return; }
+    model_off = d.str_off(t.model); model_len = d.str_len(t.model);
+    const bool stream = t.stream >= 0 && d.ty(t.stream) == 't';
+    out_flags = stream ? 1u : 0u;
+    for (uint32_t i = 0; i < P->override_len; i++) { const uint32_t c = (uint8_t)P->override_model[i]; if (c < 0x20 || c > 0x7e || c == '"' || c == '\\') { decline(AIGW_R_UNSUPPORTED_FIELD); return; } }
+    if (base == AIGW_SCHEMA_OPENAI) {
+      const uint32_t n = P->prefix_len;   // ":path" = path.Join("/", prefix, "chat/completions")
+      if (sc.n + n + 2 > sc.cap) { decline(AIGW_R_SCRATCH); return; }
+      for (uint32_t i = 0; i < n; i++) sc.p[sc.n + i] = (uint8_t)P->openai_path[i];
+      pl.push(2, sc.n, n); sc.n += (n + 1u) & ~1u;
+      path_len = pl.olen;
+      mx_openai(t, stream);
+    } else if (base == AIGW_SCHEMA_AWS_BEDROCK) {
+      pl.lit(L_PATH_MODEL); emit_model_tok(t.model, true); pl.lit(L_PATH_CONVERSE); if (stream) pl.lit(L_PATH_STREAM);
+      if (bad()) return;
+      path_len = pl.olen;
+      mx_bedrock(t);
+    } else decline(AIGW_R_SCHEMA);
   }
 
   // ---- OpenAI → Azure OpenAI (openai_azureopenai.go:37-62): the body is never rewritten; ":path" carries the deployment
@@ -2223,9 +2631,10 @@ static __device__ __forceinline__ void walk_doc(const ChatParams& P, const WalkB
       reason = W.reason ? W.reason : W.pl.err;
       if (!reason && W.pl.nops == 0) reason = AIGW_R_OPS;
     }
-  } else if constexpr (G == 7) {
+  } else if constexpr (G == 7 || G == 9) {
     if (!reason) {
       uint32_t mo = 0, mlen = 0, fl = 0, bk = AIGW_BODY_UNCHANGED;
+      if constexpr (G == 9) W.plan_messages_full(path_len, mo, mlen, fl, bk); else
       W.plan_messages(path_len, mo, mlen, fl, bk);
       po.model_off = mo; po.model_len = (uint16_t)mlen; po.flags = (uint8_t)(fl | (bk == AIGW_BODY_UNCHANGED ? 0x80u : 0u));
       W.pl.flush();

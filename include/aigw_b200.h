@@ -72,7 +72,12 @@ enum aigw_schema { AIGW_SCHEMA_OPENAI = 0, AIGW_SCHEMA_AWS_BEDROCK = 1, AIGW_SCH
                     * delete model) and anthropic_awsanthropic.go:59-93 (+ delete stream).  api_version carries the backend's
                     * anthropic_version.  Text messages / system / sampling parameters / stop_sequences / metadata are decided here,
                     * every other member (tools, thinking, images, …) is DECLINED.  AIGW_SCHEMA_MESSAGES | base schema. */
-                   AIGW_SCHEMA_ANTHROPIC = 6, AIGW_SCHEMA_MESSAGES = 64, AIGW_SCHEMA_MSG_GCP_ANTHROPIC = 68, AIGW_SCHEMA_MSG_AWS_ANTHROPIC = 69, AIGW_SCHEMA_MSG_ANTHROPIC = 70 };
+                   AIGW_SCHEMA_ANTHROPIC = 6, AIGW_SCHEMA_MESSAGES = 64, AIGW_SCHEMA_MSG_GCP_ANTHROPIC = 68, AIGW_SCHEMA_MSG_AWS_ANTHROPIC = 69, AIGW_SCHEMA_MSG_ANTHROPIC = 70,
+                   /* /v1/messages requests to the backends that need a full re-map of the request: OpenAI chat completions
+                    * (internal/translator/anthropic_openai.go:55-93 + openai_helper.go:27-261; openai_prefix as for chat) and AWS Bedrock
+                    * Converse (anthropic_awsbedrock.go:52-163,176-395).  Subset: text / tool_use / tool_result blocks, string or
+                    * text-block system prompt, sampling parameters, stop sequences, custom tools, tool_choice; the rest is DECLINED. */
+                   AIGW_SCHEMA_MSG_OPENAI = 64, AIGW_SCHEMA_MSG_AWS_BEDROCK = 65 };
 
 /* Why a body was declined / rejected (diagnostics; stable numbering). */
 enum aigw_reason {
@@ -83,7 +88,7 @@ enum aigw_reason {
   /* definite reference errors, reported with the matching status (the shim builds the user-facing message):
    * 32..39 ⇒ AIGW_MALFORMED_400 (ParseBody), 40..47 ⇒ AIGW_INVALID_422 (translator), 48..55 ⇒ AIGW_INTERNAL */
   AIGW_R_E400_SYNTAX = 32, AIGW_R_E400_TYPE = 33, AIGW_R_E400_ROLE = 34, AIGW_R_E400_CONTENT = 35,
-  AIGW_R_E422_CONTENT = 40, AIGW_R_E422_MODEL = 41 /* /v1/messages: "model field is required" */, AIGW_R_E500_ARGS = 48, AIGW_R_E500_DECODE = 49
+  AIGW_R_E422_CONTENT = 40, AIGW_R_E422_MODEL = 41 /* /v1/messages: "model field is required" */, AIGW_R_E422_ROLE = 42 /* /v1/messages to Bedrock: "unexpected role" */, AIGW_R_E500_ARGS = 48, AIGW_R_E500_DECODE = 49
 };
 
 /* One record per body.  Output record layout in the arena at out_off: [path bytes][body bytes]. */

@@ -22,6 +22,7 @@ namespace oracle { TranslateResult gemini_request_body(const ChatReq& r, const s
 #include "mutate.hpp"
 #include "response_error.hpp"
 #include "messages.hpp"
+#include "messages_translated.hpp"
 #include "stream.hpp"
 #include "translate.hpp"
 
@@ -72,7 +73,11 @@ void oracle_embeddings_translate(int schema, const char* body, uint64_t len, con
   out->mutated = dup(""); out->mutated_len = 0;
 }
 void oracle_messages_translate(int schema, const char* body, uint64_t len, const char* model_override, const char* api_version, int force, oracle_result* out) {
-  TranslateResult r = messages_translate(schema, std::string_view(body, len), model_override ? model_override : "", api_version ? api_version : "", force != 0);
+  // base 0 / 1 (OpenAI / AWS Bedrock): the full re-map (messages_translated.hpp); api_version then carries the OpenAI path prefix
+  const int mbase = schema & 15;
+  TranslateResult r = (mbase == SCHEMA_MSG_OPENAI || mbase == SCHEMA_MSG_AWS_BEDROCK)
+                          ? messages_translate_full(schema, std::string_view(body, len), model_override ? model_override : "", api_version ? api_version : "")
+                          : messages_translate(schema, std::string_view(body, len), model_override ? model_override : "", api_version ? api_version : "", force != 0);
   memset(out, 0, sizeof *out);
   out->status = r.err.status; out->body_kind = r.body_kind; out->stream = r.stream ? 1 : 0; out->has_mutated = 0;
   std::string path; for (auto& h : r.headers) if (h.name == ":path") path = h.value;

@@ -501,6 +501,45 @@ def test_messages_native_goldens():
     assert n == 8
 
 
+def test_messages_full_remap_goldens():
+    """/v1/messages to the OpenAI and AWS Bedrock backends (full re-map of the request): exact expRequestBody and expPath of the six
+    "anthropic-openai" data-plane cases and of "aws-bedrock - /anthropic/v1/messages" (tests/data-plane/testupstream_test.go)"""
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "testupstream_cases.json"), encoding="utf-8"))["cases"]
+    n = 0
+    for c in cases:
+        if "messages" not in (c.get("path") or "") or c["backend"] not in ("openai", "aws-bedrock") or "expRequestBody" not in c:
+            continue
+        t = O.messages_translate(c["backend"], c["requestBody"].encode(), api_version="v1" if c["backend"] == "openai" else "")
+        assert t.status == 0 and t.path == c["expPath"] and t.body.decode() == c["expRequestBody"], c["name"]
+        assert t.stream == ('"stream":true' in c["requestBody"])
+        n += 1
+    assert n == 7
+    tr = lambda d, b="openai", **kw: O.messages_translate(b, json.dumps(d).encode(), api_version="v1" if b == "openai" else "", **kw)
+    # tool conversation (anthropic_openai_test.go:729-784): tool_use -> tool_calls with marshalled (sorted) arguments, tool_result -> tool message first
+    conv = {"model": "claude-3", "max_tokens": 100, "messages": [
+        {"role": "user", "content": "write hello to file"},
+        {"role": "assistant", "content": [{"type": "tool_use", "id": "tool-1", "name": "Write", "input": {"file_path": "test.txt", "content": "hello"}}]},
+        {"role": "user", "content": [{"type": "tool_result", "tool_use_id": "tool-1", "content": "File written successfully"}, {"type": "text", "text": "thanks"}]}]}
+    assert tr(conv).body == (b'{"messages":[{"content":"write hello to file","role":"user"},{"role":"assistant","content":null,"tool_calls":[{"id":"tool-1","function":{"arguments":'
+                             b'"{\\"content\\":\\"hello\\",\\"file_path\\":\\"test.txt\\"}","name":"Write"},"type":"function"}]},{"content":"File written successfully","role":"tool","tool_call_id":"tool-1"},'
+                             b'{"content":"thanks","role":"user"}],"model":"claude-3","max_completion_tokens":100}')
+    assert tr(conv, "aws-bedrock").body == (b'{"inferenceConfig":{"maxTokens":100},"messages":[{"content":[{"text":"write hello to file"}],"role":"user"},{"content":[{"toolUse":{"name":"Write","input":'
+                                           b'{"content":"hello","file_path":"test.txt"},"toolUseId":"tool-1"}}],"role":"assistant"},{"content":[{"toolResult":{"content":[{"text":"File written successfully"}],'
+                                           b'"status":null,"toolUseId":"tool-1"}},{"text":"thanks"}],"role":"user"}]}')
+    # sampling parameters, stop sequences (sjson-appended last for OpenAI), tool_choice mapping, model override
+    full = {"model": "m", "max_tokens": 5, "temperature": 0.5, "top_p": 1, "top_k": 3, "stop_sequences": ["END"], "system": [{"type": "text", "text": "a"}, {"type": "text", "text": "b"}],
+            "messages": [], "tools": [{"name": "t", "description": "d", "input_schema": {"type": "object", "additionalProperties": False}}], "tool_choice": {"type": "any"}}
+    assert tr(full, model_override="o").body == (b'{"messages":[{"content":"ab","role":"system"}],"model":"o","max_completion_tokens":5,"temperature":0.5,"top_p":1,"tools":[{"type":"function","function":'
+                                                 b'{"name":"t","description":"d","parameters":{"type":"object"}}}],"tool_choice":"required","stop":["END"]}')
+    assert tr(full, "aws-bedrock").body == (b'{"additionalModelRequestFields":{"top_k":3},"inferenceConfig":{"maxTokens":5,"stopSequences":["END"],"temperature":0.5,"topP":1},"messages":[],"system":[{"text":"a"},{"text":"b"}],'
+                                           b'"toolConfig":{"toolChoice":{"any":{}},"tools":[{"toolSpec":{"description":"d","inputSchema":{"json":{"type":"object"}},"name":"t"}}]}}')
+    assert tr({"model": "m", "messages": [{"role": "system", "content": "x"}]}, "aws-bedrock").status == 2      # "unexpected role"
+    assert tr({"model": "m", "messages": [{"role": "system", "content": "x"}]}).body == b'{"messages":null,"model":"m","max_completion_tokens":0}'
+    assert tr({"model": "m", "thinking": {"type": "enabled", "budget_tokens": 5}}).status == O.DECLINED
+    assert tr({"model": "m", "stop_sequences": ["<"]}).status == O.DECLINED and tr({"model": "m", "stop_sequences": ["<"]}, "aws-bedrock").status == 0
+    assert tr({"messages": []}).status == 2 and tr({"model": 5}).status == 1
+
+
 def test_native_anthropic_usage_reference_vectors():
     """anthropic_anthropic_test.go:89-155: buffered response → tokenUsageFrom(9, 0, 0, 16, 25, -1) + model; the stream in two parts →
     tokenUsageFrom(10, 1, 0, 0, 10, -1) then tokenUsageFrom(10, 1, 0, 16, 26, -1)"""
