@@ -13,6 +13,9 @@ SCHEMA = {"openai": 0, "aws-bedrock": 1, "azure-openai": 2, "gcp-vertexai": 3, "
 DocResult = np.dtype([("out_off", "<u8"), ("body_len", "<u4"), ("path_len", "<u2"), ("status", "u1"), ("reason", "u1"),
                       ("model_off", "<u4"), ("model_len", "<u2"), ("body_kind", "u1"), ("flags", "u1"), ("in_len", "<u4"), ("_pad", "<u4")])
 assert DocResult.itemsize == 32
+EmbCountResult = np.dtype([("status", "u1"), ("reason", "u1"), ("model_len", "<u2"), ("model_off", "<u4"), ("n_inputs", "<u4"), ("tokens", "<u4"), ("first_text", "<u4"), ("in_len", "<u4"),
+                           ("declined_inputs", "<u4"), ("reserved", "<u4")])
+assert EmbCountResult.itemsize == 32
 SseResult = np.dtype([("input", "<u4"), ("output", "<u4"), ("total", "<u4"), ("cached", "<u4"), ("cache_creation", "<u4"), ("reasoning", "<u4"),
                       ("mask", "<u4"), ("_pad", "<u4"), ("model_off", "<u8"), ("model_len", "<u4"), ("status", "<u4")])
 assert SseResult.itemsize == 48
@@ -43,7 +46,7 @@ EXPORTS = ["aigw_bind_numa", "aigw_stream_open", "aigw_stream_open_batch", "aigw
            "aigw_device_alloc", "aigw_device_free", "aigw_memcpy_h2d", "aigw_memcpy_d2h", "aigw_memset_d", "aigw_sync",
            "aigw_chat_translate_device", "aigw_chat_translate_device_mapped", "aigw_chat_last_profile", "aigw_chat_set_profile", "aigw_chat_set_small_batch", "aigw_chat_translate_host", "aigw_sse_usage_device", "aigw_sse_usage_host", "aigw_response_usage_device", "aigw_response_usage_host", "aigw_embeddings_response_usage_device", "aigw_embeddings_response_usage_host", "aigw_usage_costs_device",
            "aigw_bedrock_stream_device", "aigw_bedrock_stream_host", "aigw_body_mutate_device", "aigw_body_mutate_host",
-           "aigw_cost_compile", "aigw_cost_program_free", "aigw_usage_costs_cel_device", "aigw_usage_costs_cel_host", "aigw_sha256_device", "aigw_chat_body_sha256_device", "aigw_sha256_host", "aigw_bpe_load", "aigw_bpe_free", "aigw_bpe_count_device", "aigw_bpe_count_host", "aigw_batcher_start", "aigw_batcher_add_backend", "aigw_batcher_translate", "aigw_batcher_translate_to", "aigw_batcher_get_stats", "aigw_batcher_stop"]
+           "aigw_cost_compile", "aigw_cost_program_free", "aigw_usage_costs_cel_device", "aigw_usage_costs_cel_host", "aigw_sha256_device", "aigw_chat_body_sha256_device", "aigw_sha256_host", "aigw_bpe_load", "aigw_bpe_free", "aigw_bpe_count_device", "aigw_bpe_count_host", "aigw_embeddings_count_device", "aigw_embeddings_count_host", "aigw_batcher_start", "aigw_batcher_add_backend", "aigw_batcher_translate", "aigw_batcher_translate_to", "aigw_batcher_get_stats", "aigw_batcher_stop"]
 
 
 class BackendCfg(C.Structure):
@@ -276,7 +279,7 @@ class Context:
         self.L.aigw_chat_set_profile(self.h, 1 if on else 0)
 
     def chat_last_profile(self):
-        ms = (C.c_float * 3)()
+        ms = (C.c_float * 4)()
         nl = C.c_int(0)
         self.L.aigw_chat_last_profile(self.h, C.byref(ms), C.byref(nl))
         return {"index_ms": ms[0], "walk_ms": ms[1], "emit_ms": ms[2], "launches": nl.value}
@@ -425,6 +428,23 @@ class Context:
             offs[1:] = np.cumsum(lens[:-1], dtype=np.uint64)
         arena = np.frombuffer(b"".join(bs) + b"\0" * 16, dtype=np.uint8).copy()
         return self.bpe_count_host(bpe, arena, offs, lens)[0]
+
+    # ---- large /v1/embeddings requests: ParseBody + BPE count of every input (BASELINE config 3)
+    def embeddings_count_host(self, bpe, arena, offs, lens):
+        n = len(lens); res = np.zeros(n, dtype=EmbCountResult); h2d = C.c_uint64(0); d2h = C.c_uint64(0); ms = (C.c_float * 4)()
+        self.L.aigw_embeddings_count_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]
+        self._check(self.L.aigw_embeddings_count_host(self.h, bpe, arena.ctypes.data, offs.ctypes.data, lens.ctypes.data, n, res.ctypes.data, C.byref(h2d), C.byref(d2h), ms), "embeddings_count_host")
+        return res, {"h2d_bytes": h2d.value, "d2h_bytes": d2h.value, "kernel_ms": list(ms)}
+
+    def embeddings_count_device(self, bpe, d_bodies, d_off, d_len, n, max_len, total_bytes, d_results, timed=True):
+        ms = (C.c_float * 4)()
+        self.L.aigw_embeddings_count_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        self._check(self.L.aigw_embeddings_count_device(self.h, bpe, d_bodies, d_off, d_len, n, max_len, total_bytes, d_results, None, ms if timed else None), "embeddings_count_device")
+        return list(ms)
+
+    def embeddings_count(self, bpe, bodies):
+        arena, offs, lens = pack_bodies(bodies)
+        return self.embeddings_count_host(bpe, arena, offs, lens)[0]
 
     # ---- request batcher (synchronous single-request call, thread safe)
     def batcher_start(self, cfg, max_batch=256, window_us=50):

@@ -20,6 +20,7 @@
 #include "cel_kernel.cuh"
 #include "stream_kernel.cuh"
 #include "bpe_kernel.cuh"
+#include "emb_kernel.cuh"
 
 #include <mutex>
 
@@ -60,6 +61,10 @@ struct aigw_ctx {
   long small_max = -1;   // aigw_chat_set_small_batch; -1: AIGW_SMALL_MAX or 512
   // BPE count (host form): device staging
   uint8_t* d_bpe_text = nullptr; size_t bpe_text_cap = 0; uint64_t* d_bpe_off = nullptr; size_t bpe_off_cap = 0; uint32_t* d_bpe_len = nullptr; size_t bpe_len_cap = 0; uint32_t* d_bpe_cnt = nullptr; size_t bpe_cnt_cap = 0;
+  // large embeddings requests (aigw_embeddings_count_*): token workspace, text table, counts, host-form staging
+  uint32_t* d_emb_tok = nullptr; size_t emb_tok_cap = 0; uint64_t* d_emb_toff = nullptr; size_t emb_toff_cap = 0; uint32_t* d_emb_tlen = nullptr; size_t emb_tlen_cap = 0;
+  uint32_t* d_emb_cnt = nullptr; size_t emb_cnt_cap = 0; uint8_t* d_emb_body = nullptr; size_t emb_body_cap = 0; uint64_t* d_emb_off = nullptr; size_t emb_off_cap = 0;
+  uint32_t* d_emb_len = nullptr; size_t emb_len_cap = 0; aigw_emb_count_result* d_emb_res = nullptr; size_t emb_res_cap = 0;
   uint8_t* h_small = nullptr; size_t h_small_cap = 0;   // small-batch path: tables + bodies, read by the kernel in place (mapped pinned)
   // chat workspace (intermediates of one sub-batch) + per-stage timing events
   uint8_t* d_work = nullptr; size_t work_cap = 0;
@@ -203,7 +208,7 @@ void aigw_destroy(aigw_ctx* ctx) {
     cudaFree(s.d_in); cudaFree(s.d_off); cudaFree(s.d_len); cudaFree(s.d_out); cudaFree(s.d_res); cudaFree(s.d_used); cudaFree(s.d_next); cudaFreeHost(s.h_used);
     cudaEventDestroy(s.ev_h2d); cudaEventDestroy(s.ev_k0); cudaEventDestroy(s.ev_k1); cudaEventDestroy(s.ev_ctr); cudaEventDestroy(s.ev_done);
   }
-  cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_res); cudaFreeHost(ctx->h_small); cudaFree(ctx->d_bpe_text); cudaFree(ctx->d_bpe_off); cudaFree(ctx->d_bpe_len); cudaFree(ctx->d_bpe_cnt); cudaFree(ctx->d_counters); cudaFree(ctx->d_work); cudaFree(ctx->d_used_arr); cudaFreeHost(ctx->h_used_arr);
+  cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_res); cudaFreeHost(ctx->h_small); cudaFree(ctx->d_bpe_text); cudaFree(ctx->d_bpe_off); cudaFree(ctx->d_bpe_len); cudaFree(ctx->d_bpe_cnt); cudaFree(ctx->d_emb_tok); cudaFree(ctx->d_emb_toff); cudaFree(ctx->d_emb_tlen); cudaFree(ctx->d_emb_cnt); cudaFree(ctx->d_emb_body); cudaFree(ctx->d_emb_off); cudaFree(ctx->d_emb_len); cudaFree(ctx->d_emb_res); cudaFree(ctx->d_counters); cudaFree(ctx->d_work); cudaFree(ctx->d_used_arr); cudaFreeHost(ctx->h_used_arr);
   for (auto& e2 : ctx->stage_ev) cudaEventDestroy(e2);
   cudaFree(ctx->d_sse_bytes); cudaFree(ctx->d_sse_coff); cudaFree(ctx->d_sse_first); cudaFree(ctx->d_sse_res); cudaFree(ctx->d_bs_work); cudaFree(ctx->d_bs_off[0]); cudaFree(ctx->d_bs_off[1]); cudaFreeHost(ctx->h_sres); cudaFreeHost(ctx->h_mres);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
@@ -577,6 +582,77 @@ int aigw_bpe_count_host(aigw_ctx* ctx, const aigw_bpe* bpe, const uint8_t* text,
   if (kernel_ms) *kernel_ms = ms;
   if (h2d_bytes) *h2d_bytes = nbytes + (uint64_t)n * 12;
   if (d2h_bytes) *d2h_bytes = (uint64_t)n * 4;
+  return 0;
+}
+
+// ------------------------------------------------------------------ large /v1/embeddings requests: ParseBody + BPE count (BASELINE config 3)
+int aigw_embeddings_count_device(aigw_ctx* ctx, const aigw_bpe* bpe, const uint8_t* d_bodies, const uint64_t* d_offsets, const uint32_t* d_lens, uint32_t n, uint32_t max_len,
+                                 uint64_t total_bytes, aigw_emb_count_result* d_results, void* stream, float* kernel_ms) {
+  if (!ctx || !bpe) return -2;
+  if (kernel_ms) kernel_ms[0] = kernel_ms[1] = kernel_ms[2] = kernel_ms[3] = 0;
+  if (n == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->s_compute;
+  // every input costs at least three request bytes (two quotes and a comma); one row per four bytes covers inputs of two characters and up,
+  // a request that would overflow the table is declined (AIGW_R_ARENA_FULL)
+  const uint64_t text_cap64 = total_bytes / 4 + 1024;
+  if (text_cap64 >= (1ull << 32)) { ctx->err = "aigw_embeddings_count: more than 16 GiB in one call; split it into waves"; return -2; }
+  const uint32_t text_cap = (uint32_t)text_cap64;
+  const uint32_t tok_cap = max_len / 2 + 64;
+  const int grid = emb_scan_grid(ctx->sm_count);
+  ENSURE(ctx->d_emb_tok, ctx->emb_tok_cap, (size_t)grid * tok_cap * 4, false);
+  ENSURE(ctx->d_emb_toff, ctx->emb_toff_cap, (size_t)text_cap * 8, false);
+  ENSURE(ctx->d_emb_tlen, ctx->emb_tlen_cap, (size_t)text_cap * 4, false);
+  ENSURE(ctx->d_emb_cnt, ctx->emb_cnt_cap, (size_t)text_cap * 4, false);
+  unsigned int* c0 = ctx->d_counters + (ctx->counter_next++ & 255);
+  unsigned int* c1 = ctx->d_counters + (ctx->counter_next++ & 255);
+  unsigned int* c2 = ctx->d_counters + (ctx->counter_next++ & 255);
+  CK(cudaMemsetAsync(c0, 0, sizeof(unsigned int), st)); CK(cudaMemsetAsync(c1, 0, sizeof(unsigned int), st)); CK(cudaMemsetAsync(c2, 0, sizeof(unsigned int), st));
+  EmbScanParams E; E.bodies = d_bodies; E.offsets = d_offsets; E.lens = d_lens; E.n = n; E.results = d_results; E.tok_ws = ctx->d_emb_tok; E.tok_cap = tok_cap;
+  E.text_off = ctx->d_emb_toff; E.text_len = ctx->d_emb_tlen; E.text_cap = text_cap; E.next = c0; E.text_used = c1;
+  cudaEvent_t* ev = ctx->stage_ev;
+  if (kernel_ms) CK(cudaEventRecord(ev[0], st));
+  CK(launch_emb_scan(E, ctx->sm_count, st));
+  if (kernel_ms) CK(cudaEventRecord(ev[1], st));
+  // the number of texts is only known on the device: read the row count back (4 bytes; the count kernel's grid is sized by it)
+  unsigned int n_texts = 0;
+  CK(cudaMemcpyAsync(&n_texts, c1, sizeof n_texts, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (n_texts > text_cap) n_texts = text_cap;   // requests past the capacity were declined; rows below it are all valid
+  if (kernel_ms) CK(cudaEventRecord(ev[2], st));
+  if (n_texts) {
+    BpeParams P; P.text = d_bodies; P.offsets = ctx->d_emb_toff; P.lens = ctx->d_emb_tlen; P.n = n_texts; P.counts = ctx->d_emb_cnt; P.table = bpe->d_table; P.slots = bpe->slots; P.byte_to_id = bpe->d_b2i; P.next = c2;
+    CK(launch_bpe_count(P, ctx->sm_count, st));
+  }
+  if (kernel_ms) CK(cudaEventRecord(ev[3], st));
+  CK(launch_emb_sum(d_results, n, ctx->d_emb_cnt, st));
+  if (kernel_ms) {
+    CK(cudaEventRecord(ev[4], st)); CK(cudaEventSynchronize(ev[4]));
+    CK(cudaEventElapsedTime(&kernel_ms[0], ev[0], ev[1])); CK(cudaEventElapsedTime(&kernel_ms[1], ev[2], ev[3])); CK(cudaEventElapsedTime(&kernel_ms[2], ev[3], ev[4])); CK(cudaEventElapsedTime(&kernel_ms[3], ev[0], ev[4]));
+  }
+  return 0;
+}
+
+int aigw_embeddings_count_host(aigw_ctx* ctx, const aigw_bpe* bpe, const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n,
+                               aigw_emb_count_result* results, uint64_t* h2d_bytes, uint64_t* d2h_bytes, float* kernel_ms) {
+  if (!ctx || !bpe) return -2;
+  if (n == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  uint64_t nbytes = 0; uint32_t max_len = 0;
+  for (uint32_t i = 0; i < n; i++) { const uint64_t e = offsets[i] + lens[i]; if (e > nbytes) nbytes = e; if (lens[i] > max_len) max_len = lens[i]; if (offsets[i] & 15u) { ctx->err = "aigw_embeddings_count_host: request starts must be 16-byte aligned"; return -2; } }
+  ENSURE(ctx->d_emb_body, ctx->emb_body_cap, nbytes + 64, false);
+  ENSURE(ctx->d_emb_off, ctx->emb_off_cap, (size_t)n * 8, false);
+  ENSURE(ctx->d_emb_len, ctx->emb_len_cap, (size_t)n * 4, false);
+  ENSURE(ctx->d_emb_res, ctx->emb_res_cap, (size_t)n * sizeof(aigw_emb_count_result), false);
+  cudaStream_t st = ctx->s_compute;
+  CK(cudaMemcpyAsync(ctx->d_emb_body, bodies, nbytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_emb_off, offsets, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_emb_len, lens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  if (int rc = aigw_embeddings_count_device(ctx, bpe, ctx->d_emb_body, ctx->d_emb_off, ctx->d_emb_len, n, max_len, nbytes, ctx->d_emb_res, st, kernel_ms)) return rc;
+  CK(cudaMemcpyAsync(results, ctx->d_emb_res, (size_t)n * sizeof(aigw_emb_count_result), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (h2d_bytes) *h2d_bytes = nbytes + (uint64_t)n * 12;
+  if (d2h_bytes) *d2h_bytes = (uint64_t)n * sizeof(aigw_emb_count_result) + 4;
   return 0;
 }
 

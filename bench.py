@@ -405,13 +405,14 @@ def run_config1(a, local, ncpu):
 
 # ------------------------------------------------------------------------------------------------ config 3
 def run_config3(a, rank, world, local, ncpu):
-    """/v1/embeddings requests of 1024 inputs x 64 characters: BPE token count per request (K4).  The inputs are given as a text
-    arena (1024 texts per request): the JSON scan of the 68.7 KB bodies is not part of this line (bodies above 64 KiB are outside
-    the index kernel's 16-bit positions)."""
+    """/v1/embeddings requests of 1024 inputs x 64 characters (68.7 KB of JSON each): EmbeddingsEndpointSpec.ParseBody + the BPE token
+    count of every input, one call (aigw_embeddings_count_*): request scan kernel -> text table -> BPE count kernel reading the inputs in
+    place from the request bytes -> per-request sums."""
     import _oracle as O
     import __graft_entry__ as entry
     entry.build()
     import aigw_b200 as A
+    from aigw_b200 import capi
     A.load_library().aigw_bind_numa(local)
     dist = None
     if world > 1:
@@ -423,7 +424,7 @@ def run_config3(a, rank, world, local, ncpu):
     vocab = json.load(open(os.path.join(ROOT, "tests", "golden", "bpe_vocab.json")))
     bpe = ctx.bpe_load(vocab["byte_to_id"], vocab["merges"])
     nreq = a.requests; per = 1024; tl = 64
-    # Zipf-distributed words (seed 3 + rank) so the merges are exercised; one 16 MiB base text, every request reads its own window
+    # Zipf-distributed words (seed 3 + rank) so the merges are exercised; one 16 MiB base text, every input reads its own window
     r = np.random.default_rng(3 + rank)
     alpha = np.frombuffer(b"etaoinshrdlcumwfgypbvkjxqz", dtype=np.uint8)
     nw = 6000; wl = r.integers(1, 12, nw)
@@ -431,67 +432,82 @@ def run_config3(a, rank, world, local, ncpu):
     ids = np.minimum(r.zipf(1.05, 3_000_000) - 1, nw - 1)
     base = np.frombuffer(b" ".join(words[i] for i in ids)[: 16 << 20], dtype=np.uint8)
     nt = nreq * per
-    nbytes = nt * tl
-    arena, ap = ctx.host_array(nbytes + 64)
-    reps = (nbytes + len(base) - 1) // len(base)
+    tbytes = nt * tl
+    texts = np.empty(tbytes, dtype=np.uint8)
+    reps = (tbytes + len(base) - 1) // len(base)
     for k in range(reps):
-        lo = k * len(base); hi = min(nbytes, lo + len(base))
-        arena[lo:hi] = np.roll(base, 7919 * k)[: hi - lo]
-    offs = (np.arange(nt, dtype=np.uint64) * tl); lens = np.full(nt, tl, dtype=np.uint32)
-    d_text = ctx.dalloc(nbytes + 64); d_off = ctx.dalloc(nt * 8); d_len = ctx.dalloc(nt * 4); d_cnt = ctx.dalloc(nt * 4)
-    ctx.h2d(d_text, arena[:nbytes]); ctx.h2d(d_off, offs); ctx.h2d(d_len, lens)
+        lo = k * len(base); hi = min(tbytes, lo + len(base))
+        texts[lo:hi] = np.roll(base, 7919 * k)[: hi - lo]
+    # the requests: {"model":"text-embedding-3-small","input":["<64 chars>", ... x 1024]}, 16-byte aligned starts in one pinned arena
+    head = b'{"model":"text-embedding-3-small","input":['
+    H = len(head); blen = H + per * (tl + 3) - 1 + 2
+    stride = (blen + 15) // 16 * 16
+    nbytes = nreq * stride
+    arena, ap = ctx.host_array(nbytes + 64)
+    arena[:] = 0x20
+    bodies2d = arena[:nbytes].reshape(nreq, stride)
+    bodies2d[:, :H] = np.frombuffer(head, dtype=np.uint8)
+    cells = bodies2d[:, H:H + per * (tl + 3)].reshape(nreq, per, tl + 3)
+    cells[:, :, 0] = ord('"'); cells[:, :, 1:1 + tl] = texts.reshape(nreq, per, tl); cells[:, :, 1 + tl] = ord('"'); cells[:, :, 2 + tl] = ord(',')
+    bodies2d[:, blen - 2] = ord(']'); bodies2d[:, blen - 1] = ord('}')
+    offs = (np.arange(nreq, dtype=np.uint64) * stride); lens = np.full(nreq, blen, dtype=np.uint32)
+    assert blen > 65536 and json.loads(bytes(bodies2d[0, :blen]))["input"][per - 1] == bytes(texts[(per - 1) * tl: per * tl]).decode()
+    d_body = ctx.dalloc(nbytes + 64); d_off = ctx.dalloc(nreq * 8); d_len = ctx.dalloc(nreq * 4); d_res = ctx.dalloc(nreq * 32)
+    ctx.h2d(d_body, arena[:nbytes]); ctx.h2d(d_off, offs); ctx.h2d(d_len, lens)
     sampler = ClockSampler(local); sampler.start()
     for _ in range(a.warmup):
-        ctx.bpe_count_device(bpe, d_text, d_off, d_len, nt, d_cnt)
+        ctx.embeddings_count_device(bpe, d_body, d_off, d_len, nreq, blen, nbytes, d_res)
     barrier = (lambda: (dist.barrier(), None)) if dist is not None else (lambda: None)
     barrier(); ctx.sync()
-    dev_ms = 0.0; t0 = time.perf_counter()
+    stage = np.zeros(4); t0 = time.perf_counter()
     for _ in range(a.steps):
-        dev_ms += ctx.bpe_count_device(bpe, d_text, d_off, d_len, nt, d_cnt)
+        stage += np.asarray(ctx.embeddings_count_device(bpe, d_body, d_off, d_len, nreq, blen, nbytes, d_res))
     ctx.sync(); barrier()
     wall = time.perf_counter() - t0
-    counts = np.zeros(nt, dtype=np.uint32); ctx.d2h(counts, d_cnt)
-    assert (counts != 0xFFFFFFFF).all()
-    # parity of the timed outputs: every 64th request against the self-oracle
+    res = np.zeros(nreq, dtype=capi.EmbCountResult); ctx.d2h(res, d_res)
+    assert (res["status"] == 0).all() and (res["n_inputs"] == per).all() and (res["declined_inputs"] == 0).all()
+    # parity of the timed outputs: every 64th request against the CPU restatement (ParseBody + count of every input)
     orc = O.Bpe(vocab)
-    checked = 0
-    for q in range(0, nreq, 64):
-        exp, _ = orc.count_batch(arena, offs[q * per:(q + 1) * per].copy(), lens[q * per:(q + 1) * per].copy())
-        assert np.array_equal(exp, counts[q * per:(q + 1) * per]), q
-        checked += 1
-    # end to end: host texts -> H2D -> count -> D2H of the per-text counts, per-request sums on the host
+    sel = np.arange(0, nreq, 64)
+    exp_tok, exp_n, _ = orc.embeddings_count_batch(arena, offs[sel].copy(), lens[sel].copy(), threads=ncpu)
+    assert np.array_equal(exp_tok, res["tokens"][sel]) and (exp_n == per).all()
+    checked = len(sel)
+    # end to end: host request bytes -> H2D -> scan + count + sum -> D2H of the 32-byte result rows
     e2e_wall = None; st = None
     if not a.skip_e2e:
-        ctx.bpe_count_host(bpe, arena, offs, lens)
+        ctx.embeddings_count_host(bpe, arena, offs, lens)
         barrier(); t1 = time.perf_counter()
         for _ in range(a.steps):
-            c2, st = ctx.bpe_count_host(bpe, arena, offs, lens)
-            req_tokens = c2.reshape(nreq, per).sum(axis=1)
+            r2, st = ctx.embeddings_count_host(bpe, arena, offs, lens)
         barrier(); e2e_wall = time.perf_counter() - t1
-        assert np.array_equal(c2, counts) and int(req_tokens[0]) == int(counts[:per].sum())
+        assert np.array_equal(r2["tokens"], res["tokens"])
     clocks = sampler.stop()
-    step_s = dev_ms / 1e3 / a.steps
+    step_s = stage[3] / 1e3 / a.steps
     if dist is not None:
         import torch
         t = torch.tensor([step_s, e2e_wall or 0.0], dtype=torch.float64, device=f"cuda:{local}"); dist.all_reduce(t, op=dist.ReduceOp.MAX); step_s, e2e_wall = float(t[0]), (float(t[1]) if e2e_wall else None)
     cpu = None
     if rank == 0 and world == 1:
-        ns = min(nreq, 256) * per
-        _, sec = orc.count_batch(arena, offs[:ns].copy(), lens[:ns].copy(), threads=ncpu)
-        _, sec1 = orc.count_batch(arena, offs[: ns // 8].copy(), lens[: ns // 8].copy(), threads=1)
-        cpu = {"value": (ns / per) / sec, "unit": "requests/s", "cores": ncpu, "kind": "port", "sample": f"first {ns // per} requests of the wave, {ncpu} threads (1 thread: {(ns // 8 / per) / sec1:.1f} requests/s)"}
+        ns = min(nreq, 8 * ncpu, 512)
+        _, _, sec = orc.embeddings_count_batch(arena, offs[:ns].copy(), lens[:ns].copy(), threads=ncpu)
+        n1 = max(1, ns // 16)
+        _, _, sec1 = orc.embeddings_count_batch(arena, offs[:n1].copy(), lens[:n1].copy(), threads=1)
+        cpu = {"value": ns / sec, "unit": "requests/s", "cores": ncpu, "kind": "port", "sample": f"first {ns} requests of the wave (JSON decode + BPE count of every input), {ncpu} threads (1 thread: {n1 / sec1:.1f} requests/s)"}
     if rank == 0:
         peak, peak_src = hbm_peak()
-        alg = nbytes + nt * 4
-        achieved = alg / step_s / 1e9
+        alg = nreq * (blen + 4 * per)          # bytes_in + 4 B per input
+        scan_s = stage[0] / 1e3 / a.steps
         line = {"metric": "embeddings requests/sec with BPE token count (1024 inputs x 64 chars per request)", "value": nreq * world / step_s, "unit": "requests/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u16", "data": "synthetic",
-                "config": {"workload": f"configs[2]: {nreq} /v1/embeddings requests per GPU per step, 1024 inputs x 64 characters each (Zipf words, seed 3), BPE vocabulary of {vocab['vocab_size']} (tests/golden/bpe_vocab.json); the inputs are given as a text arena, the JSON scan of the 68.7 KB bodies is not included",
-                           "texts_per_step": nt, "l2": f"inputs larger than L2 ({nbytes / 1e6:.0f} MB per step vs 126 MB)", "mean_tokens_per_request": float(counts.reshape(nreq, per).sum(axis=1).mean()),
-                           "requests_checked_vs_self_oracle": checked},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel": "bpe_count_kernel",
-                             "algorithmic_bytes_per_step": alg, "note": "algorithmic bytes = text bytes + 4 B per input (SURVEY 8d); the kernel is bound by the per-lane merge loops (shared-memory table lookups), not by HBM"},
-                "gpu_launches": (a.steps + a.warmup) * 1, "clocks": clocks}
+                "config": {"workload": f"configs[2]: {nreq} /v1/embeddings requests per GPU per step, each a {blen}-byte JSON body with 1024 inputs x 64 characters (Zipf words, seed 3): ParseBody (request scan) + BPE count of every input "
+                                       f"(vocabulary of {vocab['vocab_size']}, tests/golden/bpe_vocab.json) + per-request sums",
+                           "inputs_per_step": nt, "l2": f"requests larger than L2 ({nbytes / 1e6:.0f} MB per step vs 126 MB)", "mean_tokens_per_request": float(res["tokens"].mean()),
+                           "requests_checked_vs_cpu_restatement": checked, "wall_ms_per_step": wall / a.steps * 1e3},
+                "stage_ms_per_step": {"emb_scan_kernel": stage[0] / a.steps, "bpe_count_kernel": stage[1] / a.steps, "emb_sum_kernel": stage[2] / a.steps, "whole_call_incl_readback": stage[3] / a.steps},
+                "roofline": {"bound": "hbm", "achieved": alg / step_s / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / step_s / 1e9 / peak, "traffic": None, "peak_source": peak_src, "kernel": "emb_scan_kernel + bpe_count_kernel",
+                             "algorithmic_bytes_per_step": alg, "scan_kernel_alone": {"achieved": nreq * blen / scan_s / 1e9, "frac": nreq * blen / scan_s / 1e9 / peak},
+                             "note": "algorithmic bytes = request bytes + 4 B per input (SURVEY 8d); the scan streams the request once, the count kernel re-reads the inputs and is bound by its per-lane merge loops (shared-memory table lookups), not by HBM"},
+                "gpu_launches": (a.steps + a.warmup) * 3, "clocks": clocks}
         if e2e_wall:
             line["e2e"] = {"value": nreq * world * a.steps / e2e_wall, "unit": "requests/s", "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"])}
         if cpu:

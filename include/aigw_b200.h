@@ -341,6 +341,33 @@ int  aigw_bpe_count_device(aigw_ctx* ctx, const aigw_bpe* bpe, const uint8_t* d_
 int  aigw_bpe_count_host(aigw_ctx* ctx, const aigw_bpe* bpe, const uint8_t* text, const uint64_t* offsets, const uint32_t* lens, uint32_t n, uint32_t* counts,
                          uint64_t* h2d_bytes, uint64_t* d2h_bytes, float* kernel_ms);
 
+/* ---- BASELINE config 3: /v1/embeddings requests of any size, ParseBody + BPE token count of every input in one call ----
+ * EmbeddingsEndpointSpec.ParseBody (internal/endpointspec/endpointspec.go:231-240) over the string forms of the input union
+ * (internal/apischema/openai/union.go:71-147: "input" a string or an array of strings; openai.go:316-375 for the other members),
+ * then the K4 count of every input, read in place from the request bytes (no text copy).  Requests may be far above the 64 KiB
+ * ceiling of aigw_chat_translate_* (1024 inputs of 64 characters are 68.7 KB); one CTA streams one request.
+ * status AIGW_OK: model span, n_inputs, tokens = sum of the inputs' counts (declined_inputs of them hold a space-free run above
+ * 512 bytes and are not in the sum).  AIGW_MALFORMED_400: what ParseBody rejects (syntax, model / encoding_format / user not a
+ * string, dimensions not an integer, input a number or a boolean).  AIGW_DECLINED (stock path decides): any backslash in the
+ * request, nested containers (object inputs, token-id arrays), null or non-string array elements, members other than
+ * model / input / encoding_format / dimensions / user, requests of 16 MiB and above. */
+typedef struct aigw_emb_count_result {
+  uint8_t  status;          /* enum aigw_status */
+  uint8_t  reason;          /* enum aigw_reason */
+  uint16_t model_len;
+  uint32_t model_off;       /* EmbeddingRequest.Model: span inside the request */
+  uint32_t n_inputs;
+  uint32_t tokens;
+  uint32_t first_text;      /* row of the request's first input in the call's text table (diagnostics) */
+  uint32_t in_len;
+  uint32_t declined_inputs;
+  uint32_t reserved;
+} aigw_emb_count_result;    /* 32 bytes */
+int aigw_embeddings_count_device(aigw_ctx* ctx, const aigw_bpe* bpe, const uint8_t* d_bodies, const uint64_t* d_offsets, const uint32_t* d_lens, uint32_t n, uint32_t max_len,
+                                 uint64_t total_bytes, aigw_emb_count_result* d_results, void* stream, float* kernel_ms /* NULL or 4 floats: scan, count, sum, whole call (includes the 4-byte read-back between scan and count) */);
+int aigw_embeddings_count_host(aigw_ctx* ctx, const aigw_bpe* bpe, const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n,
+                               aigw_emb_count_result* results, uint64_t* h2d_bytes, uint64_t* d2h_bytes, float* kernel_ms /* NULL or 4 floats */);
+
 /* ---- per-GPU request batcher: the synchronous single-request call for the cgo shim ----
  * The reference translates one request per goroutine (internal/extproc/processor_impl.go:211-398); a GPU wants batches.
  * aigw_batcher_translate[_to] is called concurrently from any number of threads.  The caller's body is copied (by the caller's

@@ -273,6 +273,31 @@ double oracle_bpe_count_batch(void* vv, const char* text, const uint64_t* off, c
   work(); for (auto& x : th) x.join();
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
+// BASELINE config 3 on the CPU: per request EmbeddingsEndpointSpec.ParseBody (decode of the whole body) + the BPE count of every string input.
+// tokens[i] = sum over request i's inputs, 0xFFFFFFFF when ParseBody fails or the input is not a list of strings; returns the seconds taken.
+double oracle_embeddings_count_batch(void* vv, const char* bodies, const uint64_t* off, const uint32_t* len, uint64_t n, int threads, uint32_t* tokens, uint32_t* n_inputs) {
+  const BpeVocab& V = *(const BpeVocab*)vv;
+  if (threads < 1) threads = 1;
+  const auto t0 = std::chrono::steady_clock::now();
+  std::atomic<uint64_t> next{0};
+  auto work = [&]() {
+    for (;;) {
+      const uint64_t i = next.fetch_add(1); if (i >= n) break;
+      tokens[i] = 0xffffffffu; if (n_inputs) n_inputs[i] = 0;
+      Value root; std::string perr;
+      if (!oj::parse(std::string_view(bodies + off[i], len[i]), root, perr)) continue;
+      EmbReq r; if (parse_embedding_request(root, r)) continue;
+      uint32_t sum = 0;
+      if (r.kind == EmbReq::STR) { sum = bpe_count(V, r.str); if (n_inputs) n_inputs[i] = 1; }
+      else if (r.kind == EmbReq::STRS) { for (auto& t : r.strs) sum += bpe_count(V, t); if (n_inputs) n_inputs[i] = (uint32_t)r.strs.size(); }
+      else if (r.kind != EmbReq::NONE) continue;
+      tokens[i] = sum;
+    }
+  };
+  std::vector<std::thread> th; for (int t = 1; t < threads; t++) th.emplace_back(work);
+  work(); for (auto& x : th) x.join();
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
 // ---- S3 behind AWS (eventstream-wrapped Anthropic events)
 struct AwsAnthropicHandle { AwsAnthropicStreamState st; AnthropicStreamCfg cfg; };
 void* oracle_aws_anthropic_open(const char* request_model, int64_t created) { auto* h = new AwsAnthropicHandle(); h->cfg.request_model = request_model ? request_model : ""; h->cfg.created = created; return h; }

@@ -377,6 +377,15 @@ class Bpe:
         sec = lib().oracle_bpe_count_batch(self.h, arena.ctypes.data, offs.ctypes.data, lens.ctypes.data, len(lens), threads, counts.ctypes.data)
         return counts, sec
 
+    def embeddings_count_batch(self, arena, offs, lens, threads=1):
+        """BASELINE config 3 on the CPU: ParseBody of every request + the count of its string inputs -> (tokens per request, n_inputs, seconds)"""
+        import numpy as np
+        n = len(lens); tokens = np.zeros(n, dtype=np.uint32); nin = np.zeros(n, dtype=np.uint32)
+        L = lib(); L.oracle_embeddings_count_batch.restype = C.c_double
+        L.oracle_embeddings_count_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+        sec = L.oracle_embeddings_count_batch(self.h, arena.ctypes.data, offs.ctypes.data, lens.ctypes.data, n, threads, tokens.ctypes.data, nin.ctypes.data)
+        return tokens, nin, sec
+
     def count(self, texts):
         import numpy as np
         bs = [t.encode() if isinstance(t, str) else bytes(t) for t in texts]
