@@ -83,12 +83,15 @@ __global__ void __launch_bounds__(kEmbThreads, 4) emb_scan_kernel(const EmbScanP
     if (len >= (1u << 24) || len == 0) fail = len ? AIGW_R_TOO_LARGE : AIGW_R_E400_SYNTAX;
     else if (((uintptr_t)body) & 15u) fail = AIGW_R_ARGS;   // the arena convention: every request starts 16-byte aligned
     uint32_t in_str = 0, prev_sc = 0;   // carries across tiles (uniform over the CTA)
+    // the next tile's 32 bytes are requested before the current tile is classified (two tiles of loads in flight per thread)
+    uint4 na = make_uint4(0, 0, 0, 0), nb = na;
+    if (!fail && tid * 32u + 32u <= len) { na = __ldg((const uint4*)(body + tid * 32u)); nb = __ldg((const uint4*)(body + tid * 32u + 16)); }
     if (!fail) for (uint32_t base = 0, it = 0; base < len; base += kTile, it ^= 1u) {
       const uint32_t pos0 = base + tid * 32u;
       uint32_t w[8];
       if (pos0 + 32u <= len) {
-        const uint4 a = __ldg((const uint4*)(body + pos0)), b = __ldg((const uint4*)(body + pos0 + 16));
-        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+        w[0] = na.x; w[1] = na.y; w[2] = na.z; w[3] = na.w; w[4] = nb.x; w[5] = nb.y; w[6] = nb.z; w[7] = nb.w;
+        if (pos0 + kTile + 32u <= len) { na = __ldg((const uint4*)(body + pos0 + kTile)); nb = __ldg((const uint4*)(body + pos0 + kTile + 16)); }
       } else {
 #pragma unroll
         for (int k = 0; k < 8; k++) {
