@@ -210,7 +210,16 @@ namespace aigw {
   X(L_MX_STOP, ",\"stop\":[")                                                                  \
   X(L_MX_TOPK, "\"additionalModelRequestFields\":{\"top_k\":")                                 \
   X(L_MX_TR_NULL, "{\"toolResult\":{\"content\":null")                                         \
-  X(L_MX_TR_STATUS_ERR, ",\"status\":\"error\",\"toolUseId\":")
+  X(L_MX_TR_STATUS_ERR, ",\"status\":\"error\",\"toolUseId\":")                             \
+  X(L_AM_HEAD, "\",\"type\":\"message\",\"role\":\"assistant\",\"content\":[")                 \
+  X(L_AM_TEXT, "{\"type\":\"text\",\"text\":")                                                 \
+  X(L_AM_TOOLUSE, "{\"type\":\"tool_use\",\"id\":")                                            \
+  X(L_AM_THINKING, "{\"type\":\"thinking\",\"thinking\":")                                     \
+  X(L_AM_STOP, ",\"stop_reason\":")                                                            \
+  X(L_AM_END_TURN, "\"end_turn\"")                                                             \
+  X(L_AM_CACHE_READ, ",\"cache_read_input_tokens\":")                                          \
+  X(L_AM_INPUT, ",\"input_tokens\":")                                                          \
+  X(L_AM_OUTPUT, ",\"output_tokens\":")
 
 enum LitId : int {
 #define X(name, text) name,
@@ -221,7 +230,7 @@ enum LitId : int {
 
 struct alignas(16) LitTable {
   uint16_t off[L_COUNT + 1];
-  alignas(16) char bytes[3072];   // copied to shared memory with 32-bit loads
+  alignas(16) char bytes[3328];   // copied to shared memory with 32-bit loads
 };
 constexpr LitTable make_lit_table() {
   LitTable t{};

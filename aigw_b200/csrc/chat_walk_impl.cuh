@@ -658,6 +658,45 @@ struct Walker {
       pl.push(2, sc.n, 32); sc.n += 32;
       path_len = 32;
     }
+    if (P->schema == AIGW_SCHEMA_RESP_MESSAGES_AWS_BEDROCK) {
+      // ---- the /v1/messages form (anthropicToAWSBedrockTranslator.ResponseBody, anthropic_awsbedrock.go:429-510): anthropic.MessagesResponse
+      // {id, type, role, content[every block in order], model, stop_reason?, usage?} (anthropic.go:1413-1440,1603-1612)
+      pl.lit(L_LBRACE); pl.lit(L_R_ID_OPEN); emit_cfg_text(P->response_id, P->rid_len); pl.lit(L_AM_HEAD);
+      bool bf = true;
+      if (content >= 0) for (int e = content + 1; d.ty(e) != ']'; e = d.after(e)) {
+        int q[7]; if (!rmembers(e, kb, 7, q)) return;
+        if (q[0] >= 0) { if (!bf) pl.lit(L_COMMA); bf = false; pl.lit(L_AM_TEXT); emit_str(q[0]); pl.lit(L_RBRACE); }
+        else if (q[1] >= 0) {
+          static const uint8_t kt[] = {RK_name, RK_input, RK_toolUseId}; int t[3]; if (!rmembers(q[1], kt, 3, t)) return;
+          if (!bf) pl.lit(L_COMMA); bf = false;
+          pl.lit(L_AM_TOOLUSE); if (t[2] >= 0) emit_str(t[2]); else pl.lit(L_EMPTY_STR);
+          pl.lit(L_AN_NAME); if (t[0] >= 0) emit_str(t[0]); else pl.lit(L_EMPTY_STR);
+          pl.lit(L_TOOLUSE_INPUT); if (t[1] >= 0) emit_any(d, pl, t[1]); else pl.lit(L_NULL);
+          if (bad()) return;
+          pl.lit(L_RBRACE);
+        } else if (q[2] >= 0) {
+          static const uint8_t kr[] = {RK_reasoningText, RK_redactedContent}; int t[2]; if (!rmembers(q[2], kr, 2, t)) return;
+          if (t[0] < 0) { if (t[1] >= 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; } continue; }   // redacted_thinking: bytes re-encoded, stock path
+          static const uint8_t kx[] = {RK_text, RK_signature}; int x[2]; if (!rmembers(t[0], kx, 2, x)) return;
+          if (!bf) pl.lit(L_COMMA); bf = false;
+          pl.lit(L_AM_THINKING); if (x[0] >= 0) emit_str(x[0]); else pl.lit(L_EMPTY_STR);
+          if (x[1] >= 0 && d.str_len(x[1]) > 0) { pl.lit(L_R_RSIG); emit_str(x[1]); }
+          pl.lit(L_RBRACE);
+        }
+      }
+      pl.lit(L_RBRACK); pl.lit(L_R_MODEL_KEY); pl.lit(L_QUOTE); emit_cfg_text(P->override_model, P->override_len); pl.lit(L_QUOTE);
+      if (stop >= 0) {
+        if (d.str_has_backslash(stop)) { decline(AIGW_R_ESCAPE); return; }
+        pl.lit(L_AM_STOP);
+        if (str_is(stop, "max_tokens", 10) || str_is(stop, "stop_sequence", 13) || str_is(stop, "tool_use", 8)) emit_str(stop); else pl.lit(L_AM_END_TURN);
+      }
+      if (has_usage) {
+        pl.lit(L_R_USAGE); pl.lit(L_R_CC); emit_dec(has_wr ? u_wr : 0u); pl.lit(L_AM_CACHE_READ); emit_dec(has_rd ? u_rd : 0u);
+        pl.lit(L_AM_INPUT); emit_dec(u_in); pl.lit(L_AM_OUTPUT); emit_dec(u_out); pl.lit(L_RBRACE);
+      }
+      pl.lit(L_RBRACE);
+      return;
+    }
     // ---- body, fields in struct order (internal/apischema/openai/openai.go:1269-1306,1365-1422)
     pl.lit(L_LBRACE);
     if (P->rid_len) { pl.lit(L_R_ID_OPEN); emit_cfg_text(P->response_id, P->rid_len); pl.lit(L_R_QUOTE_COMMA); }

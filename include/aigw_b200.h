@@ -45,6 +45,10 @@ enum aigw_schema { AIGW_SCHEMA_OPENAI = 0, AIGW_SCHEMA_AWS_BEDROCK = 1, AIGW_SCH
                     * path_len == 32 and the usage struct sits where request schemas put the :path.
                     * status AIGW_INTERNAL = "failed to unmarshal body". */
                    AIGW_SCHEMA_RESP_AWS_BEDROCK = 16,
+                   /* the same Converse response for a /v1/messages caller: anthropic.MessagesResponse (anthropicToAWSBedrockTranslator.ResponseBody,
+                    * internal/translator/anthropic_awsbedrock.go:429-510).  cfg: response_id = the x-amzn-requestid header (the message id),
+                    * model_name_override = the request model.  Record layout as above. */
+                   AIGW_SCHEMA_RESP_MESSAGES_AWS_BEDROCK = 17,
                    /* buffered anthropic.Message → OpenAI ChatCompletionResponse: Translator.ResponseBody of the GCP / AWS Anthropic
                     * translators (internal/translator/openai_gcpanthropic.go:237-278, messageToChatCompletion anthropic_helper.go:1165-1255).
                     * cfg: model_name_override = the request model (used when the response carries no model), created.  Record layout as

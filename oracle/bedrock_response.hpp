@@ -19,7 +19,12 @@
 namespace oracle {
 
 // encoding/json-style re-marshal of a decoded `any` value: sorted keys, float64 numbers (translate.hpp enc_any)
-inline Status bedrock_response(std::string_view body, const BedrockStreamCfg& cfg, std::string& out, TokenUsage& usage) {
+// to_anthropic: the /v1/messages form of the same response (anthropicToAWSBedrockTranslator.ResponseBody, non-stream:
+// internal/translator/anthropic_awsbedrock.go:429-510, stop reasons :720-735; anthropic.MessagesResponse field order
+// internal/apischema/anthropic/anthropic.go:1413-1440,1450-1480,1603-1612) — every block in order (text, else tool_use, else thinking /
+// redacted_thinking), id = the x-amzn-requestid header, model = the request model, usage as the four float64 counters.
+// Pinned by the data-plane golden "aws-bedrock - /anthropic/v1/messages" (exact expResponseBody; the reference compares it with JSONEq).
+inline Status bedrock_response(std::string_view body, const BedrockStreamCfg& cfg, std::string& out, TokenUsage& usage, bool to_anthropic = false) {
   out.clear(); usage = TokenUsage{};
   Value v;
   oj::Parser ps(body.data(), body.size());  // json.Decoder reads ONE value; trailing bytes are not an error
@@ -46,6 +51,7 @@ inline Status bedrock_response(std::string_view body, const BedrockStreamCfg& cf
   if (o && !obj_or_null(o)) return INTERNAL;
   // message
   std::string role; std::optional<std::string> content; std::string tool_calls, reasoning; bool has_reasoning = false;
+  std::string an_blocks; bool an_any = false;
   bool decl = false;
   if (o && o->is_obj()) {
     const Value* m = o->get("message");
@@ -76,6 +82,14 @@ inline Status bedrock_response(std::string_view body, const BedrockStreamCfg& cf
             if (rt && rt->is_obj()) { has_rt = true; if (!plain_str(rt->get("text"), rtext) || !plain_str(rt->get("signature"), rsig)) return INTERNAL; }
             if (const Value* rd2 = rc->get("redactedContent"); rd2 && !rd2->is_null()) { if (!rd2->is_str() || !oj::b64dec(rd2->s, red)) return INTERNAL; }
           }
+          if (to_anthropic) {
+            std::string b;
+            if (text) { b = "{\"type\":\"text\",\"text\":"; oj::enc_str(b, *text); b.push_back('}'); }
+            else if (has_tu) { b = "{\"type\":\"tool_use\",\"id\":"; oj::enc_str(b, id); b += ",\"name\":"; oj::enc_str(b, name); b += ",\"input\":" + args + "}"; }
+            else if (has_rc && has_rt) { b = "{\"type\":\"thinking\",\"thinking\":"; oj::enc_str(b, rtext); if (!rsig.empty()) { b += ",\"signature\":"; oj::enc_str(b, rsig); } b.push_back('}'); }
+            else if (has_rc) { if (const Value* rd2 = rc->get("redactedContent"); rd2 && !rd2->is_null()) { b = "{\"type\":\"redacted_thinking\",\"data\":"; oj::enc_str(b, red); b.push_back('}'); } }
+            if (!b.empty()) { if (an_any) an_blocks.push_back(','); an_any = true; an_blocks += b; }
+          }
           if (has_tu) {
             if (!tool_calls.empty()) tool_calls.push_back(',');
             tool_calls += "{\"id\":"; oj::enc_str(tool_calls, id); tool_calls += ",\"function\":{\"arguments\":"; oj::enc_str(tool_calls, args);
@@ -93,6 +107,20 @@ inline Status bedrock_response(std::string_view body, const BedrockStreamCfg& cf
   }
   if (!o || o->is_null()) return DECLINED;  // bedrockResp.Output.Message on a nil Output panics
   if (decl) return DECLINED;
+  if (to_anthropic) {
+    if (has_usage) usage = explicit_caching_usage(in_tok, out_tok, rd, wr);
+    out = "{\"id\":"; oj::enc_str(out, cfg.response_id); out += ",\"type\":\"message\",\"role\":\"assistant\",\"content\":[" + an_blocks + "],\"model\":"; oj::enc_str(out, cfg.request_model);
+    if (stop) {
+      const std::string& s = *stop;
+      out += ",\"stop_reason\":\""; out += (s == "max_tokens" || s == "stop_sequence" || s == "tool_use") ? s : std::string("end_turn"); out += "\"";
+    }
+    if (has_usage) {
+      out += ",\"usage\":{\"cache_creation_input_tokens\":" + std::to_string((long long)(wr ? *wr : 0)) + ",\"cache_read_input_tokens\":" + std::to_string((long long)(rd ? *rd : 0));
+      out += ",\"input_tokens\":" + std::to_string((long long)in_tok) + ",\"output_tokens\":" + std::to_string((long long)out_tok) + "}";
+    }
+    out += "}";
+    return OK;
+  }
   // usage
   std::string usage_json;
   if (has_usage) {

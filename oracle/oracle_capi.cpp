@@ -209,6 +209,12 @@ int oracle_bedrock_response(const char* body, uint64_t len, const char* request_
   put(usage, u); *out = dup(o); *out_len = o.size();
   return (int)st;
 }
+int oracle_bedrock_response_anthropic(const char* body, uint64_t len, const char* request_model, const char* response_id, char** out, uint64_t* out_len, oracle_usage* usage) {
+  BedrockStreamCfg cfg; cfg.request_model = request_model ? request_model : ""; cfg.response_id = response_id ? response_id : ""; cfg.created = 0;
+  std::string o; TokenUsage u; const Status st = bedrock_response(std::string_view(body, len), cfg, o, u, true);
+  put(usage, u); *out = dup(o); *out_len = o.size();
+  return (int)st;
+}
 double oracle_bedrock_response_batch(const uint8_t* bodies, const uint64_t* offsets, uint32_t n, int threads, uint64_t* total_out) {
   std::atomic<uint32_t> next{0}; std::atomic<uint64_t> tot{0};
   auto t0 = std::chrono::steady_clock::now();

@@ -154,6 +154,16 @@ def bedrock_response(body: bytes, request_model: bytes, response_id: bytes, crea
     return st, out, u
 
 
+def bedrock_response_anthropic(body: bytes, request_model: bytes, response_id: bytes):
+    """Buffered Bedrock Converse response → (status, anthropic.MessagesResponse JSON bytes, Usage): the /v1/messages form."""
+    n = C.c_uint64(0); u = Usage(); L = lib()
+    L.oracle_bedrock_response_anthropic.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(Usage)]
+    vp = C.c_void_p()
+    st = L.oracle_bedrock_response_anthropic(body, len(body), request_model, response_id, C.byref(vp), C.byref(n), C.byref(u))
+    out = C.string_at(vp, n.value); L.oracle_free(vp)
+    return st, out, u
+
+
 def body_mutate(body: bytes, removes, sets):
     """BodyMutator.Mutate: removes = [path str], sets = [(path, value)] → (rc, mutated bytes); rc 1 = not restated."""
     L = lib()

@@ -540,6 +540,18 @@ def test_messages_full_remap_goldens():
     assert tr({"messages": []}).status == 2 and tr({"model": 5}).status == 1
 
 
+def test_messages_bedrock_response_golden():
+    """the buffered Converse response of a /v1/messages call -> anthropic.MessagesResponse: expResponseBody of "aws-bedrock - /anthropic/v1/messages" """
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "testupstream_cases.json"), encoding="utf-8"))["cases"]
+    c = [c for c in cases if c["name"] == "aws-bedrock - /anthropic/v1/messages"][0]
+    st, out, u = O.bedrock_response_anthropic(c["responseBody"].encode(), b"anthropic.claude-3-sonnet-20240229-v1:0", b"bedrock-msg-123")
+    assert st == 0 and out.decode() == c["expResponseBody"] and (u.input, u.output, u.total) == (10, 20, 30)
+    st, out, _ = O.bedrock_response_anthropic(b'{"output":{"message":{"content":[{"toolUse":{"name":"n","input":{"b":1,"a":"x"},"toolUseId":"t"}},{"reasoningContent":{"reasoningText":{"text":"th","signature":"s"}}}]}},'
+                                              b'"stopReason":"content_filtered","usage":{"inputTokens":1,"outputTokens":2,"totalTokens":3,"cacheReadInputTokens":4}}', b"m", b"")
+    assert st == 0 and out == (b'{"id":"","type":"message","role":"assistant","content":[{"type":"tool_use","id":"t","name":"n","input":{"a":"x","b":1}},{"type":"thinking","thinking":"th","signature":"s"}],'
+                               b'"model":"m","stop_reason":"end_turn","usage":{"cache_creation_input_tokens":0,"cache_read_input_tokens":4,"input_tokens":1,"output_tokens":2}}')
+
+
 def test_native_anthropic_usage_reference_vectors():
     """anthropic_anthropic_test.go:89-155: buffered response → tokenUsageFrom(9, 0, 0, 16, 25, -1) + model; the stream in two parts →
     tokenUsageFrom(10, 1, 0, 0, 10, -1) then tokenUsageFrom(10, 1, 0, 16, 26, -1)"""
