@@ -39,9 +39,10 @@ __device__ __forceinline__ uint32_t bpe_lookup(const uint2* tab, uint32_t mask, 
 
 struct BpeWarpSmem {
   uint8_t bytes[kBpeBuf + 16];
-  uint16_t sym[kBpeBuf];
-  uint16_t rk[kBpeBuf];          // rank of the pair (sym[i], sym[i+1]); 0xffff = not mergeable
+  uint32_t sr[kBpeBuf];          // symbol | rank << 16 of the pair (this symbol, next live symbol); rank 0xffff = not mergeable, 0xfffe = slot merged away
   uint16_t start[kBpeBuf + 1];   // piece starts, ascending; start[np] = end of data
+  uint32_t stmask[kBpeBuf / 32 + 1];   // bit i of word b: byte 32 b + i starts a piece
+  uint32_t next_piece;           // pieces handed out so far in this run (lanes take the next one when theirs is done)
   uint32_t tcount[kBpeMaxTexts];
   uint32_t tend[kBpeMaxTexts];   // staged end offset of each text of the group
 };
@@ -93,42 +94,70 @@ __global__ void __launch_bounds__(kBpeWarps * 32, 1) bpe_count_kernel(const BpeP
       if (nt == 0) continue;
       __syncwarp();
       // ---- symbols and piece starts: a piece starts at every space and at the first byte of every staged text
-      for (uint32_t i = lane; i < fill; i += 32) W.rk[i] = 0;
+      for (uint32_t i = lane; i < fill; i += 32) W.sr[i] = 0;
       __syncwarp();
-      for (uint32_t k = lane; k < nt; k += 32) { const uint32_t s0 = k == 0 ? 0u : W.tend[k - 1]; if (s0 < fill) W.rk[s0] = 1; }
+      for (uint32_t k = lane; k < nt; k += 32) { const uint32_t s0 = k == 0 ? 0u : W.tend[k - 1]; if (s0 < fill) W.sr[s0] = 1; }
       __syncwarp();
       uint32_t np = 0;
       for (uint32_t b0 = 0; b0 < fill; b0 += 32) {
         const uint32_t i = b0 + lane;
         const uint32_t c = i < fill ? W.bytes[i] : 0u;
-        if (i < fill) W.sym[i] = s_b2i[c];
-        const bool st = i < fill && (c == ' ' || W.rk[i] != 0);
+        const bool st = i < fill && (c == ' ' || W.sr[i] != 0);   // the text-start flag is read before the slot takes the symbol
+        if (i < fill) W.sr[i] = s_b2i[c];
         const uint32_t m = __ballot_sync(0xffffffffu, st);
         if (st) W.start[np + __popc(m & lt)] = (uint16_t)i;
+        if (lane == 0) W.stmask[b0 >> 5] = m;
         np += __popc(m);
       }
-      if (lane == 0) W.start[np] = (uint16_t)fill;
+      if (lane == 0) { W.start[np] = (uint16_t)fill; W.stmask[(fill + 31) >> 5] = 0xffffffffu; W.next_piece = 0; }
       __syncwarp();
-      // ---- one piece per lane at a time
-      for (uint32_t p0 = 0; p0 < np; p0 += 32) {
-        const uint32_t pi = p0 + lane;
-        if (pi < np) {
-          const uint32_t a = W.start[pi], e = W.start[pi + 1];
-          uint32_t L = e - a;
-          uint16_t* s = W.sym + a; uint16_t* r = W.rk + a;
-          for (uint32_t k = 0; k + 1 < L; k++) { const uint32_t v = bpe_lookup(tab, mask, s[k], s[k + 1]); r[k] = v == kEmpty ? 0xffffu : (uint16_t)(v >> 16); }
-          while (L > 1) {
-            uint32_t best = 0xffffu, at = 0;
-            for (uint32_t k = 0; k + 1 < L; k++) { const uint32_t v = r[k]; if (v < best) { best = v; at = k; } }
-            if (best == 0xffffu) break;
-            s[at] = (uint16_t)(bpe_lookup(tab, mask, s[at], s[at + 1]) & 0xffffu);
-            for (uint32_t k = at + 1; k + 1 < L; k++) { s[k] = s[k + 1]; r[k] = r[k + 1]; }
-            L--;
-            if (at > 0) { const uint32_t v = bpe_lookup(tab, mask, s[at - 1], s[at]); r[at - 1] = v == kEmpty ? 0xffffu : (uint16_t)(v >> 16); }
-            if (at + 1 < L) { const uint32_t v = bpe_lookup(tab, mask, s[at], s[at + 1]); r[at] = v == kEmpty ? 0xffffu : (uint16_t)(v >> 16); }
+      // ---- ranks of all adjacent pairs, one lane per byte position (a pair never spans two pieces)
+      for (uint32_t b0 = 0; b0 < fill; b0 += 32) {
+        const uint32_t i = b0 + lane;
+        if (i < fill) {
+          const uint32_t nx = i + 1;
+          const bool last = nx >= fill || ((W.stmask[nx >> 5] >> (nx & 31u)) & 1u);
+          const uint32_t sy = W.sr[i] & 0xffffu;
+          uint32_t rk = 0xffff0000u;
+          if (!last) { const uint32_t v = bpe_lookup(tab, mask, sy, W.sr[nx] & 0xffffu); if (v != kEmpty) rk = v & 0xffff0000u; }
+          W.sr[i] = sy | rk;
+        }
+      }
+      __syncwarp();
+      // ---- merges: every lane works on one piece and takes the next unclaimed one when it is done, so the lanes stay busy
+      // whatever the piece lengths are (one piece per lane per round left 10 of 32 lanes active on average)
+      {
+        uint32_t a = 0, L0 = 0, L = 0; uint32_t* q = W.sr; bool have = false, done = false;
+        for (;;) {
+          if (!have && !done) {
+            const uint32_t pi = atomicAdd(&W.next_piece, 1u);
+            if (pi >= np) done = true;
+            else { a = W.start[pi]; L0 = W.start[pi + 1] - a; L = L0; q = W.sr + a; have = true; }
           }
-          uint32_t lo = 0; while (W.tend[lo] <= a) lo++;      // the text this piece belongs to (empty texts own no piece)
-          atomicAdd(&W.tcount[lo], L);
+          if (__all_sync(0xffffffffu, done)) break;
+          if (have) {
+            uint32_t best = 0xfffeu, at = 0;
+            if (L > 1) for (uint32_t k = 0; k < L0; k++) { const uint32_t r = q[k] >> 16; if (r < best) { best = r; at = k; } }   // leftmost lowest rank; 0xfffe (merged away) / 0xffff never win
+            if (best == 0xfffeu) {   // nothing left to merge: the piece is worth L tokens
+              uint32_t lo = 0; while (W.tend[lo] <= a) lo++;      // the text this piece belongs to (empty texts own no piece)
+              atomicAdd(&W.tcount[lo], L);
+              have = false;
+            } else {
+              uint32_t j = at + 1; while ((q[j] >> 16) == 0xfffeu) j++;              // the right partner (a mergeable pair has one)
+              const uint32_t merged = bpe_lookup(tab, mask, q[at] & 0xffffu, q[j] & 0xffffu) & 0xffffu;
+              q[j] = 0xfffe0000u;
+              uint32_t rank_at = 0xffffu;
+              uint32_t j2 = j + 1; while (j2 < L0 && (q[j2] >> 16) == 0xfffeu) j2++;   // the merged symbol's new right neighbour, if any
+              if (j2 < L0) { const uint32_t v = bpe_lookup(tab, mask, merged, q[j2] & 0xffffu); if (v != kEmpty) rank_at = v >> 16; }
+              q[at] = merged | (rank_at << 16);
+              if (at > 0) {
+                uint32_t i = at - 1; bool live = true;
+                while ((q[i] >> 16) == 0xfffeu) { if (i == 0) { live = false; break; } i--; }
+                if (live) { const uint32_t v = bpe_lookup(tab, mask, q[i] & 0xffffu, merged); q[i] = (q[i] & 0xffffu) | (v == kEmpty ? 0xffff0000u : (v & 0xffff0000u)); }
+              }
+              L--;
+            }
+          }
         }
       }
       __syncwarp();
