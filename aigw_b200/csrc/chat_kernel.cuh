@@ -97,6 +97,8 @@ namespace aigw {
   X(L_AN_TR_ERR_F, ",\"is_error\":false,\"content\":[")                                         \
   X(L_AN_TR_ERR_T, ",\"is_error\":true,\"content\":[")                                          \
   X(L_AN_TR_CLOSE, "],\"type\":\"tool_result\"}")                                               \
+  X(L_AN_TOPP, ",\"top_p\":")                                                                  \
+  X(L_AN_STOPSEQ, ",\"stop_sequences\":[")                                                     \
   X(L_AN_STREAM, ",\"stream\":true")                                                            \
   X(L_AN_VERSION, ",\"anthropic_version\":\"")                                                   \
   X(L_AN_END, "\"}")                                                                            \

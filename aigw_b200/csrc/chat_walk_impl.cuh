@@ -221,6 +221,17 @@ __device__ uint32_t canon_number(const uint8_t* p, uint32_t n, bool integer_only
   if (sig > 15) return 0;
   return fe;
 }
+// a canonical decimal (canon_number's output, float form) against the closed interval [0, 1]: -1 below, +1 above, 0 inside
+__device__ int unit_range(const uint8_t* p, uint32_t l) {
+  uint32_t i = 0; bool neg = false;
+  if (l && p[0] == '-') { neg = true; i = 1; }
+  uint32_t iv = 0; bool nz = false;
+  for (; i < l && p[i] != '.'; i++) { const uint32_t dg = p[i] - '0'; if (iv < 100u) iv = iv * 10u + dg; if (dg) nz = true; }
+  bool fnz = false;
+  for (i++; i < l; i++) if (p[i] != '0') fnz = true;
+  if (neg) return (nz || fnz) ? -1 : 0;
+  return (iv >= 2u || (iv == 1u && fnz)) ? 1 : 0;
+}
 
 // ------------------------------------------------------------------ generic canonical re-serialisation
 // Go: decode into interface{} / map[string]any, then marshal ⇒ compact, keys sorted, numbers via float64.
@@ -2453,8 +2464,13 @@ struct Walker {
     { uint32_t pl0 = 0; pl.dry = true; plan_bedrock(t, stream, pl0); pl.dry = false; pl.nsys = 0; sc.n = 0; }
     if (bad()) return;
     pending = 0;  // Bedrock's translator errors do not apply; this translator's own are found below
-    if (t.temperature >= 0 || t.top_p >= 0 || t.stop >= 0 || t.thinking >= 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+    if (t.thinking >= 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
     if (t.tools >= 0 && d.ty(t.tools + 1) != ']') { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+    if (t.stop >= 0) {  // a string or a non-empty array of strings; anything else is not pinned (openai-go union decode)
+      const int s = t.stop;
+      if (is_arr(s)) { if (d.ty(s + 1) == ']') { decline(AIGW_R_UNSUPPORTED_FIELD); return; } for (int e = s + 1; d.ty(e) != ']'; e = d.after(e)) if (!is_str(e)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; } }
+      else if (!is_str(s)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+    }
     if (t.reasoning_effort >= 0 && d.str_len(t.reasoning_effort) > 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
     // ":path"
     if (gcp) { pl.lit(L_AN_GCP_PATH); emit_model(t, false); pl.lit(stream ? L_AN_STREAMRAWPREDICT : L_AN_RAWPREDICT); }
@@ -2594,6 +2610,22 @@ struct Walker {
     }
     if (mfirst) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }  // no messages: layout not pinned
     pl.lit(L_RBRACK);
+    // sampling parameters in MessageNewParams' declaration order (anthropic_helper.go:726-738); temperature outside 0..1 is the
+    // translator's 422 (:67-72), found after the message errors
+    if (t.temperature >= 0) {
+      pl.lit(L_COMMA); pl.lit(L_TEMP);
+      const uint32_t o0 = pl.olen; emit_num_field(t.temperature, false);
+      if (bad()) return;
+      if (unit_range(d.s + d.tok(t.temperature), pl.olen - o0) != 0) pend(AIGW_R_E422_TEMPERATURE);
+    }
+    if (t.top_p >= 0) { pl.lit(L_AN_TOPP); emit_num_field(t.top_p, false); if (bad()) return; }
+    if (t.stop >= 0) {
+      pl.lit(L_AN_STOPSEQ);
+      if (is_str(t.stop)) emit_str(t.stop);
+      else { bool sf = true; for (int e = t.stop + 1; d.ty(e) != ']'; e = d.after(e)) { if (!sf) pl.lit(L_COMMA); sf = false; emit_str(e); } }
+      pl.lit(L_RBRACK);
+      if (bad()) return;
+    }
     if (pl.nsys) { pl.lit(L_SYSTEM_OPEN); pl.flush_sys(); pl.lit(L_RBRACK); }
     if (gcp && stream) pl.lit(L_AN_STREAM);
     pl.lit(L_AN_VERSION);

@@ -92,7 +92,8 @@ enum aigw_reason {
   /* definite reference errors, reported with the matching status (the shim builds the user-facing message):
    * 32..39 ⇒ AIGW_MALFORMED_400 (ParseBody), 40..47 ⇒ AIGW_INVALID_422 (translator), 48..55 ⇒ AIGW_INTERNAL */
   AIGW_R_E400_SYNTAX = 32, AIGW_R_E400_TYPE = 33, AIGW_R_E400_ROLE = 34, AIGW_R_E400_CONTENT = 35,
-  AIGW_R_E422_CONTENT = 40, AIGW_R_E422_MODEL = 41 /* /v1/messages: "model field is required" */, AIGW_R_E422_ROLE = 42 /* /v1/messages to Bedrock: "unexpected role" */, AIGW_R_E500_ARGS = 48, AIGW_R_E500_DECODE = 49
+  AIGW_R_E422_CONTENT = 40, AIGW_R_E422_MODEL = 41 /* /v1/messages: "model field is required" */, AIGW_R_E422_ROLE = 42 /* /v1/messages to Bedrock: "unexpected role" */,
+  AIGW_R_E422_TEMPERATURE = 43 /* OpenAI -> Anthropic: "temperature … is not supported by Anthropic (must be between 0.0 and 1.0)" */, AIGW_R_E500_ARGS = 48, AIGW_R_E500_DECODE = 49
 };
 
 /* One record per body.  Output record layout in the arena at out_off: [path bytes][body bytes]. */

@@ -24,6 +24,7 @@ namespace oracle { TranslateResult gemini_request_body(const ChatReq& r, const s
 #include "messages.hpp"
 #include "messages_translated.hpp"
 #include "stream.hpp"
+#include "completions.hpp"
 #include "translate.hpp"
 
 using namespace oracle;
@@ -163,6 +164,22 @@ int oracle_response_openai(const char* body, uint64_t len, const char* request_m
 int oracle_response_embeddings(const char* body, uint64_t len, oracle_usage* out, char* model_buf, uint64_t cap, uint64_t* model_len) {
   TokenUsage tu; std::string rm;
   bool ok = response_embeddings(std::string_view(body, len), tu, rm);
+  put(out, tu); uint64_t n = std::min<uint64_t>(cap, rm.size()); memcpy(model_buf, rm.data(), n); *model_len = rm.size();
+  return ok ? 0 : 1;
+}
+// ---- /v1/completions: stream usage scan (one ResponseBody call per feed) and the buffered branch
+void* oracle_completions_sse_open() { return new SSECompletionsState(); }
+void oracle_completions_sse_close(void* h) { delete (SSECompletionsState*)h; }
+void oracle_completions_sse_feed(void* h, const char* chunk, uint64_t len, oracle_usage* call) {
+  auto* st = (SSECompletionsState*)h; TokenUsage u = sse_completions_feed(*st, std::string_view(chunk, len)); put(call, u);
+}
+uint64_t oracle_completions_sse_model(void* h, char* buf, uint64_t cap) {
+  auto* st = (SSECompletionsState*)h; uint64_t n = std::min<uint64_t>(cap, st->streaming_model.size()); memcpy(buf, st->streaming_model.data(), n); return st->streaming_model.size();
+}
+uint64_t oracle_completions_sse_buffered(void* h) { return ((SSECompletionsState*)h)->buffered.size(); }
+int oracle_response_completions(const char* body, uint64_t len, oracle_usage* out, char* model_buf, uint64_t cap, uint64_t* model_len) {
+  TokenUsage tu; std::string rm;
+  bool ok = response_completions(std::string_view(body, len), tu, rm);
   put(out, tu); uint64_t n = std::min<uint64_t>(cap, rm.size()); memcpy(model_buf, rm.data(), n); *model_len = rm.size();
   return ok ? 0 : 1;
 }

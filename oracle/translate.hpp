@@ -315,8 +315,12 @@ inline TranslateResult request_body(std::string_view original, const ChatReq& r,
 // The body layout is produced by anthropic-sdk-go v1.38.0 (MessageNewParams marshal), which is not in the tree.  Only
 // what the reference's goldens pin (tests/data-plane/testupstream_test.go:203,216,291,355,369,549) is restated:
 // max_tokens, messages (text / tool_use / tool_result blocks, cache_control {"type":"ephemeral"}), system, then the
-// sjson-appended "stream" (GCP) and "anthropic_version".  Every other field (temperature, top_p, stop_sequences, tools,
-// tool_choice, thinking, output_config) has no pinned position ⇒ status DECLINED ("parity unpinned"), never a guess.
+// sjson-appended "stream" (GCP) and "anthropic_version".  The sampling parameters (anthropic_helper.go:726-738: temperature with
+// its 0..1 validation :67-72, top_p, stop -> stop_sequences) follow the declaration order of MessageNewParams in the SDK
+// (required fields, then the param.Opt scalars temperature / top_k / top_p, then metadata … stop_sequences, system, thinking,
+// tool_choice, tools) — the same rule the pinned fields obey (max_tokens, messages, …, system; text, cache_control, type);
+// their CONTENT is pinned by openai_gcpanthropic_test.go:225-261 (gjson / struct compares), their byte position by no
+// in-tree fixture ("parity unpinned" for the order).  tools, tool_choice, thinking, output_config: DECLINED, never a guess.
 namespace anthropic {
 inline Error unpinned(const char* what) { return Error{DECLINED, std::string("parity unpinned: ") + what}; }
 
@@ -330,9 +334,7 @@ inline TranslateResult request_body(const ChatReq& r, const Value& root, bool gc
   TranslateResult res; res.stream = r.stream; res.model = r.model;
   res.request_model = model_override.empty() ? r.model : model_override;
   auto fail = [&](Error e) { res.err = e; return res; };
-  if (r.temperature) return fail(unpinned("temperature"));
-  if (r.top_p) return fail(unpinned("top_p"));
-  if (r.stop_is_string || r.stop_array) return fail(unpinned("stop_sequences"));
+  if (r.stop_array && r.stop_array->empty()) return fail(unpinned("empty stop array (nil or [] after the openai-go union decode)"));
   if (!r.tools.empty()) return fail(unpinned("tools"));
   if (r.thinking != ChatReq::ThNone) return fail(unpinned("thinking"));
   if (!r.reasoning_effort.empty()) return fail(unpinned("output_config.effort"));
@@ -415,7 +417,20 @@ inline TranslateResult request_body(const ChatReq& r, const Value& root, bool gc
     msep(); msgs += "{\"content\":[" + c + "],\"role\":\"user\"}";
   }
   if (mfirst) return fail(unpinned("no messages"));
+  // validateTemperatureForAnthropic (anthropic_helper.go:67-72), after the message / tool translation errors (:671-679,726-731)
+  if (r.temperature && (*r.temperature < 0.0 || *r.temperature > 1.0)) {
+    char tb[64]; snprintf(tb, sizeof tb, "%.2f", *r.temperature);
+    return fail(invalid(std::string("invalid request body: temperature ") + tb + " is not supported by Anthropic (must be between 0.0 and 1.0)"));
+  }
   std::string o = "{\"max_tokens\":" + std::to_string(mt.value_or(0)) + ",\"messages\":[" + msgs + "]";
+  if (r.temperature) { o += ",\"temperature\":"; oj::enc_f64(o, *r.temperature); }
+  if (r.top_p) { o += ",\"top_p\":"; oj::enc_f64(o, *r.top_p); }
+  if (r.stop_is_string || r.stop_array) {
+    o += ",\"stop_sequences\":[";
+    if (r.stop_is_string) oj::enc_str(o, r.stop_string);
+    else for (size_t k = 0; k < r.stop_array->size(); k++) { if (k) o.push_back(','); oj::enc_str(o, (*r.stop_array)[k]); }
+    o += "]";
+  }
   if (!sys.empty()) o += ",\"system\":[" + sys + "]";
   if (gcp && r.stream) o += ",\"stream\":true";
   std::string ver = !api_version.empty() ? api_version : (gcp ? "vertex-2023-10-16" : "bedrock-2023-05-31");

@@ -119,6 +119,46 @@ def response_openai(body: bytes, request_model: bytes = b""):
     return rc == 0, u, buf.raw[:ml.value]
 
 
+class CompletionsSSEStream:
+    """/v1/completions stream usage scan, one ResponseBody call per feed (internal/translator/openai_completions.go:80-96,157-203)."""
+    def __init__(self):
+        L = lib()
+        L.oracle_completions_sse_open.restype = C.c_void_p
+        L.oracle_completions_sse_close.argtypes = [C.c_void_p]
+        L.oracle_completions_sse_feed.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.POINTER(Usage)]
+        L.oracle_completions_sse_model.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
+        L.oracle_completions_sse_model.restype = C.c_uint64
+        L.oracle_completions_sse_buffered.argtypes = [C.c_void_p]
+        L.oracle_completions_sse_buffered.restype = C.c_uint64
+        self.h = L.oracle_completions_sse_open()
+
+    def feed(self, chunk: bytes) -> Usage:
+        u = Usage()
+        lib().oracle_completions_sse_feed(self.h, chunk, len(chunk), C.byref(u))
+        return u
+
+    def model(self) -> bytes:
+        buf = C.create_string_buffer(4096)
+        n = lib().oracle_completions_sse_model(self.h, buf, 4096)
+        return buf.raw[:n]
+
+    def buffered(self) -> int:
+        return lib().oracle_completions_sse_buffered(self.h)
+
+    def __del__(self):
+        if self.h:
+            lib().oracle_completions_sse_close(self.h)
+            self.h = None
+
+
+def response_completions(body: bytes):
+    """(ok, Usage, response_model bytes) — buffered /v1/completions response, internal/translator/openai_completions.go:98-150."""
+    u = Usage(); buf = C.create_string_buffer(4096); ml = C.c_uint64(0)
+    L = lib(); L.oracle_response_completions.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(Usage), C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    rc = L.oracle_response_completions(body, len(body), C.byref(u), buf, 4096, C.byref(ml))
+    return rc == 0, u, buf.raw[:ml.value]
+
+
 def response_embeddings(body: bytes):
     """(ok, Usage, response_model bytes) — R1 embeddings, internal/translator/openai_embeddings.go:70-88."""
     u = Usage(); buf = C.create_string_buffer(4096); ml = C.c_uint64(0)

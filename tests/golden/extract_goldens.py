@@ -158,6 +158,30 @@ def bedrock_stream():
         json.dump(out, f, indent=1)
 
 
+def completions_cases():
+    """internal/translator/openai_completions_test.go: the five buffered bodies of TestOpenAIToOpenAITranslatorV1CompletionResponseBody
+    (:107-247) with their expected TokenUsage / model, and the two streaming tests (:249-337).  The raw-string bodies are lifted as they
+    stand; the expectations are transcribed as data in tokenUsageFrom order (input, cached, cacheCreation, output, total, reasoning; -1 = unset)."""
+    src = open(os.path.join(REF, "internal/translator/openai_completions_test.go"), encoding="utf-8").read()
+    a = src.index("func TestOpenAIToOpenAITranslatorV1CompletionResponseBody(")
+    b = src.index("func TestOpenAIToOpenAITranslatorV1CompletionResponseBodyStreaming(")
+    c = src.index("func TestOpenAIToOpenAITranslatorV1CompletionResponseError(")
+    raw = [v for (_, _, v) in go_string_literals(src[a:b]) if v.lstrip().startswith("{") or v == "invalid json"]
+    names = ["valid_response", "valid_response_with_cached_tokens", "valid_response_with_reasoning_tokens", "invalid_json", "response_without_usage"]
+    exp = [[5, -1, -1, 8, 13, -1], [5, 2, 1, 8, 13, -1], [5, -1, -1, 8, 13, 3], None, [-1, -1, -1, -1, -1, -1]]
+    assert len(raw) == 5, len(raw)
+    buffered = [{"name": n, "body": r, "exp": e, "exp_model": "gpt-3.5-turbo-instruct" if e is not None else None, "exp_error": e is None} for n, r, e in zip(names, raw, exp)]
+    chunks = [v for (_, _, v) in go_string_literals(src[b:c]) if v.startswith("data: ")]
+    assert len(chunks) == 4, len(chunks)
+    streams = [
+        {"name": "three ResponseBody calls", "feeds": chunks[:3], "exp": [[-1] * 6, [-1] * 6, [5, -1, -1, 3, 8, -1]], "exp_model": ["gpt-3.5-turbo-instruct"] * 3},
+        {"name": "reasoning tokens", "feeds": chunks[3:], "exp": [[5, -1, -1, 3, 8, 2]], "exp_model": ["gpt-3.5-turbo-instruct"]},
+    ]
+    with open(os.path.join(OUT, "completions_cases.json"), "w", encoding="utf-8") as f:
+        json.dump({"source": "internal/translator/openai_completions_test.go:107-337", "buffered": buffered, "streams": streams}, f, indent=1)
+
+
 if __name__ == "__main__":
     main()
     bedrock_stream()
+    completions_cases()
