@@ -348,6 +348,35 @@ __global__ void __launch_bounds__(128) response_usage_kernel(const uint8_t* bodi
   results[d] = r;
 }
 
+// Buffered /v1/completions responses (openai_completions.go:98-150): json.Unmarshal of the whole body (no trailing bytes) into
+// openai.CompletionResponse; responseModel = resp.Model; every counter is set only when it is >= 0 — a negative or >= 2^31
+// counter is outside the integer captures' range and DECLINES.  The schema is read in place from device memory.
+__device__ SchemaBlob g_cmpl_resp_schema;
+__global__ void __launch_bounds__(128) completions_response_kernel(const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n, aigw_sse_result* results) {
+  const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n) return;
+  const uint8_t* p = bodies + offsets[d];
+  Capture cp; cp.int_set = 0; cp.obj_seen = 0; cp.span_set = 0; cp.span_esc = 0; cp.weird = 0; cp.big = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) cp.ints[k] = 0;
+  const bool ok = walk(p, (int)lens[d], g_cmpl_resp_schema.nodes, g_cmpl_resp_schema.fields, g_cmpl_resp_schema.keys, N_ROOT, cp, /*allow_trailing=*/false);
+  aigw_sse_result r; memset(&r, 0, sizeof r);
+  if (cp.weird || (cp.span_esc & 1u)) r.status = AIGW_DECLINED;
+  else if (!ok) r.status = AIGW_INTERNAL;  // "failed to unmarshal body"
+  else {
+    if (cp.obj_seen & (1u << C_OBJ_USAGE)) {
+      if (cp.big) r.status = AIGW_DECLINED;
+      else {
+        r.usage.input = cp.ints[C_PROMPT]; r.usage.output = cp.ints[C_COMPLETION]; r.usage.total = cp.ints[C_TOTAL]; r.usage.mask = 1u | 2u | 4u;
+        if (cp.obj_seen & (1u << C_OBJ_PTD)) { r.usage.cached = cp.ints[C_CACHED]; r.usage.cache_creation = cp.ints[C_CACHE_CREATION]; r.usage.mask |= 8u | 16u; }
+        if (cp.obj_seen & (1u << C_OBJ_CTD)) { r.usage.reasoning = cp.ints[C_REASONING]; r.usage.mask |= 32u; }
+      }
+    }
+    if ((cp.span_set & 1u) && cp.span_len[0] > 0) { r.model_off = offsets[d] + cp.span_off[0]; r.model_len = cp.span_len[0]; }
+  }
+  results[d] = r;
+}
+
 // C2: evalCost's direct selectors over a table of usages (internal/extproc/processor_impl.go:707-756)
 __global__ void usage_costs_kernel(const aigw_sse_result* results, uint32_t n, const int32_t* cost_types, uint32_t n_costs, unsigned long long* out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -363,11 +392,13 @@ cudaError_t launch_response_usage(const uint8_t* bodies, const uint64_t* offsets
   {
     const cudaError_t e0 = device_once(once, nullptr, [&](int*) {
       RespSchemaBlob b = build_resp_schema(); cudaError_t e = cudaMemcpyToSymbol(g_resp_schema, &b, sizeof b); if (e != cudaSuccess) return e;
-      RespSchemaBlob b2 = build_emb_schema(); return cudaMemcpyToSymbol(g_emb_schema, &b2, sizeof b2);
+      RespSchemaBlob b2 = build_emb_schema(); e = cudaMemcpyToSymbol(g_emb_schema, &b2, sizeof b2); if (e != cudaSuccess) return e;
+      SchemaBlob b3 = build_completion_schema(); return cudaMemcpyToSymbol(g_cmpl_resp_schema, &b3, sizeof b3);
     });
     if (e0 != cudaSuccess) return e0;
   }
   if (n == 0) return cudaSuccess;
+  if (embeddings == 2) { completions_response_kernel<<<(n + 127) / 128, 128, 0, st>>>(bodies, offsets, lens, n, results); return cudaGetLastError(); }
   response_usage_kernel<<<(n + 127) / 128, 128, 0, st>>>(bodies, offsets, lens, n, results, embeddings);
   return cudaGetLastError();
 }

@@ -15,7 +15,8 @@ enum Cap : uint8_t { C_PROMPT = 0, C_COMPLETION = 1, C_TOTAL = 2, C_REASONING = 
                      C_OBJ_USAGE = 0, C_OBJ_CTD = 1, C_OBJ_PTD = 2, C_SPAN_MODEL = 0, NOCAP = 0xff };
 enum N : uint8_t { N_ANY = 0, N_STR, N_INT, N_FLOAT, N_ROOT, N_CHOICES, N_CHOICE, N_DELTA, N_TOOLCALLS, N_TOOLCALL, N_FUNC, N_ANNOTS, N_ANNOT, N_URLCIT,
                    N_REASON, N_B64, N_LOGPROBS, N_TOKLPS, N_TOKLP, N_INTS, N_TOPLPS, N_TOPLP, N_USAGE, N_CTD, N_PTD, N_CREATED, N_MODEL,
-                   N_PROMPT, N_COMPLETION, N_TOTAL, N_REASONING_TOK, N_CACHED, N_CACHE_CREATION, N_COUNT };
+                   N_PROMPT, N_COMPLETION, N_TOTAL, N_REASONING_TOK, N_CACHED, N_CACHE_CREATION,
+                   N_CM_CHOICES, N_CM_CHOICE, N_CM_LOGPROBS, N_STRS, N_FLOATS, N_CM_TOPS, N_MAPF, N_COUNT };
 
 struct FieldDef { uint8_t owner; const char* key; uint8_t node; };
 static const FieldDef kFields[] = {
@@ -71,5 +72,43 @@ static inline SchemaBlob build_schema() {
   return b;
 }
 
+// ------------------------------------------------------------------ schema: CompletionResponse (legacy /v1/completions; the stream
+// chunks and the buffered body share the shape: internal/apischema/openai/openai.go:2000-2055; Usage :2064-2081)
+static const FieldDef kCmplFields[] = {
+  {N_ROOT, "id", N_STR}, {N_ROOT, "object", N_STR}, {N_ROOT, "created", N_CREATED}, {N_ROOT, "model", N_MODEL}, {N_ROOT, "system_fingerprint", N_STR},
+  {N_ROOT, "choices", N_CM_CHOICES}, {N_ROOT, "usage", N_USAGE},
+  {N_CM_CHOICE, "text", N_STR}, {N_CM_CHOICE, "index", N_INT}, {N_CM_CHOICE, "logprobs", N_CM_LOGPROBS}, {N_CM_CHOICE, "finish_reason", N_STR},
+  {N_CM_LOGPROBS, "tokens", N_STRS}, {N_CM_LOGPROBS, "token_logprobs", N_FLOATS}, {N_CM_LOGPROBS, "top_logprobs", N_CM_TOPS}, {N_CM_LOGPROBS, "text_offset", N_INTS},
+  {N_USAGE, "prompt_tokens", N_PROMPT}, {N_USAGE, "completion_tokens", N_COMPLETION}, {N_USAGE, "total_tokens", N_TOTAL},
+  {N_USAGE, "completion_tokens_details", N_CTD}, {N_USAGE, "prompt_tokens_details", N_PTD},
+  {N_CTD, "text_tokens", N_INT}, {N_CTD, "accepted_prediction_tokens", N_INT}, {N_CTD, "audio_tokens", N_INT}, {N_CTD, "reasoning_tokens", N_REASONING_TOK}, {N_CTD, "rejected_prediction_tokens", N_INT},
+  {N_PTD, "text_tokens", N_INT}, {N_PTD, "audio_tokens", N_INT}, {N_PTD, "cached_tokens", N_CACHED}, {N_PTD, "cache_creation_input_tokens", N_CACHE_CREATION},
+};
+static constexpr int kNumCmplFields = sizeof(kCmplFields) / sizeof(kCmplFields[0]);
+static_assert(kNumCmplFields <= 64, "field table too small");
+
+static inline SchemaBlob build_completion_schema() {
+  SchemaBlob b; memset(&b, 0, sizeof b);
+  auto set = [&](int n, uint8_t kind, uint8_t cap = NOCAP, uint8_t elem = 0) { b.nodes[n].kind = kind; b.nodes[n].cap = cap; b.nodes[n].elem = elem; };
+  set(N_ANY, K_ANY); set(N_STR, K_STR); set(N_INT, K_INT); set(N_FLOAT, K_FLOAT);
+  set(N_ROOT, K_OBJ); set(N_CM_CHOICES, K_ARR, NOCAP, N_CM_CHOICE); set(N_CM_CHOICE, K_OBJ); set(N_CM_LOGPROBS, K_OBJ);
+  set(N_STRS, K_ARR, NOCAP, N_STR); set(N_FLOATS, K_ARR, NOCAP, N_FLOAT); set(N_INTS, K_ARR, NOCAP, N_INT);
+  set(N_CM_TOPS, K_ARR, NOCAP, N_MAPF); set(N_MAPF, K_MAP, NOCAP, N_FLOAT);   // []map[string]float64
+  set(N_USAGE, K_OBJ, C_OBJ_USAGE); set(N_CTD, K_OBJ, C_OBJ_CTD); set(N_PTD, K_OBJ, C_OBJ_PTD);
+  set(N_CREATED, K_CREATED); set(N_MODEL, K_STR, C_SPAN_MODEL);
+  set(N_PROMPT, K_INT, C_PROMPT); set(N_COMPLETION, K_INT, C_COMPLETION); set(N_TOTAL, K_INT, C_TOTAL);
+  set(N_REASONING_TOK, K_INT, C_REASONING); set(N_CACHED, K_INT, C_CACHED); set(N_CACHE_CREATION, K_INT, C_CACHE_CREATION);
+  int ko = 0;
+  for (int f = 0; f < kNumCmplFields; f++) {
+    const FieldDef& d = kCmplFields[f];
+    Node& o = b.nodes[d.owner];
+    if (o.nf == 0) o.f0 = (uint8_t)f;   // fields of one owner are contiguous in kCmplFields
+    o.nf++;
+    int kl = (int)strlen(d.key);
+    b.fields[f].koff = (uint16_t)ko; b.fields[f].klen = (uint8_t)kl; b.fields[f].node = d.node;
+    memcpy(b.keys + ko, d.key, kl); ko += kl;
+  }
+  return b;
+}
 
 }  // namespace aigw

@@ -12,6 +12,7 @@ namespace {
 
 // ------------------------------------------------------------------ device tables (one copy per device, uploaded on first use)
 __device__ SchemaBlob g_chunk_schema;        // openai.ChatCompletionResponseChunk
+__device__ SchemaBlob g_cmpl_schema;         // openai.CompletionResponse (legacy /v1/completions)
 __device__ BedrockSchema g_conv_schema;      // awsbedrock.ConverseStreamEvent
 __device__ uint32_t g_crc_tab[256];          // IEEE CRC-32
 
@@ -96,7 +97,10 @@ __device__ __forceinline__ void cap_reset(CAP& cp) {
 // ------------------------------------------------------------------ S1: OpenAI SSE usage scan, one ResponseBody call
 // (openAIToOpenAITranslatorV1ChatCompletion.ResponseBody stream branch + extractUsageFromBufferEvent,
 //  internal/translator/openai_openai.go:131-145,179-215)
-__device__ void step_openai(StreamSlot& S, const StreamStep& st, uint8_t* out, aigw_chunk_result& R) {
+// `completions`: the legacy /v1/completions translator (openai_completions.go:80-96,157-203) — the same loop over
+// openai.CompletionResponse chunks; responseModel is the stream's own model only (no fallback to the request model)
+__device__ void step_openai(StreamSlot& S, const StreamStep& st, uint8_t* out, aigw_chunk_result& R, bool completions = false) {
+  const SchemaBlob& sch = completions ? g_cmpl_schema : g_chunk_schema;
   const uint8_t* b = S.buf; const uint32_t n = S.end;
   uint32_t pos = 0;
   aigw_usage u; memset(&u, 0, sizeof u);
@@ -108,7 +112,7 @@ __device__ void step_openai(StreamSlot& S, const StreamStep& st, uint8_t* out, a
     pos = nl + 1;
     if (!prefix(line, ll, "data: ", 6)) continue;
     Capture cp; cap_reset(cp);
-    const bool ok = walk(line + 6, (int)ll - 6, g_chunk_schema.nodes, g_chunk_schema.fields, g_chunk_schema.keys, N_ROOT, cp);
+    const bool ok = walk(line + 6, (int)ll - 6, sch.nodes, sch.fields, sch.keys, N_ROOT, cp);
     if (cp.weird || (cp.span_esc & 1u)) { status = AIGW_DECLINED; break; }
     if (!ok) continue;   // not a chunk (e.g. [DONE]): skipped silently
     if ((cp.span_set & 1u) && cp.span_len[0] > 0) {
@@ -126,7 +130,7 @@ __device__ void step_openai(StreamSlot& S, const StreamStep& st, uint8_t* out, a
   S.beg = pos;
   R.usage = u; R.body_kind = AIGW_BODY_UNCHANGED; R.out_len = 0;
   // responseModel = cmp.Or(streamingResponseModel, requestModel): placed after the (empty) body
-  const char* m = S.rmodel_len ? S.rmodel : S.model; const uint32_t ml = S.rmodel_len ? S.rmodel_len : S.model_len;
+  const char* m = S.rmodel_len ? S.rmodel : S.model; const uint32_t ml = S.rmodel_len ? S.rmodel_len : completions ? 0u : S.model_len;
   if (ml <= st.out_cap) { for (uint32_t k = 0; k < ml; k++) out[k] = (uint8_t)m[k]; R.model_len = ml; }
 }
 
@@ -996,6 +1000,7 @@ __global__ void __launch_bounds__(64) stream_step_kernel(const __grid_constant__
       case AIGW_STREAM_GCP_GEMINI_BUFFERED: step_gemini_buffered(S, st, out, R); break;
       case AIGW_STREAM_ANTHROPIC: step_anthropic_native(S, st, out, R); break;
       case AIGW_STREAM_AWS_ANTHROPIC: step_aws_anthropic(S, st, out, R); break;
+      case AIGW_STREAM_OPENAI_COMPLETIONS: step_openai(S, st, out, R, true); break;
       default: R.status = AIGW_DECLINED; R.reason = AIGW_R_SCHEMA; break;
     }
   }
@@ -1031,6 +1036,7 @@ cudaError_t launch_stream_steps(const StreamParams& P, cudaStream_t st) {
   {
     const cudaError_t e0 = device_once(once, nullptr, [&](int*) {
       SchemaBlob a = build_schema(); cudaError_t e = cudaMemcpyToSymbol(g_chunk_schema, &a, sizeof a); if (e != cudaSuccess) return e;
+      a = build_completion_schema(); e = cudaMemcpyToSymbol(g_cmpl_schema, &a, sizeof a); if (e != cudaSuccess) return e;
       BedrockSchema b = build_schema_bedrock(); e = cudaMemcpyToSymbol(g_conv_schema, &b, sizeof b); if (e != cudaSuccess) return e;
       AnSchema c = build_an_schema(); e = cudaMemcpyToSymbol(g_an_schema, &c, sizeof c); if (e != cudaSuccess) return e;
       uint32_t tab[256];

@@ -11,7 +11,8 @@
 
 namespace aigw { namespace tj {
 
-enum Kind : uint8_t { K_ANY = 0, K_STR, K_INT, K_FLOAT, K_BOOL, K_OBJ, K_ARR, K_CREATED, K_B64, K_STROBJ /* string, or the object node in `elem` */ };
+enum Kind : uint8_t { K_ANY = 0, K_STR, K_INT, K_FLOAT, K_BOOL, K_OBJ, K_ARR, K_CREATED, K_B64, K_STROBJ /* string, or the object node in `elem` */,
+                      K_MAP /* map[string]T: an object with arbitrary keys whose values are all of node `elem` */ };
 
 struct Field { uint16_t koff; uint8_t klen; uint8_t node; };  // key bytes at keys[koff..koff+klen)
 struct Node { uint8_t kind; uint8_t cap; uint8_t f0; uint8_t nf; uint8_t elem; };
@@ -193,7 +194,7 @@ __device__ inline bool walk(const uint8_t* p, int n, const Node* nodes, const Fi
         else return false;
         break;
       }
-      case K_OBJ: {
+      case K_OBJ: case K_MAP: {
         if (c != '{') return false;
         if (nd.cap != 0xff) cap.obj_seen |= 1u << nd.cap;
         i++; while (i < n && ws(p[i])) i++;
@@ -244,6 +245,7 @@ __device__ inline bool walk(const uint8_t* p, int n, const Node* nodes, const Fi
         const Field fd = fields[par.f0 + f];
         if (fd.klen == kl) { const char* fk = keys + fd.koff; int t = 0; while (t < kl && k[t] == (uint8_t)fk[t]) t++; if (t == kl) { child = fd.node; if (st_seen[sp - 1] & (1u << f)) cap.weird = 1; st_seen[sp - 1] |= 1u << f; break; } }
       }
+      if (par.kind == K_MAP) child = par.elem;
       node = child < 0 ? 0 /* node 0 is K_ANY by convention */ : child;
       break;
     }

@@ -229,6 +229,14 @@ int aigw_embeddings_response_usage_device(aigw_ctx* ctx, const uint8_t* d_bodies
                                           aigw_sse_result* d_results, void* stream, float* kernel_ms);
 int aigw_embeddings_response_usage_host(aigw_ctx* ctx, const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n,
                                         aigw_sse_result* results, const int32_t* cost_types, uint32_t n_costs, uint64_t* costs /* n * n_costs, may be NULL */);
+/* Same for the legacy /v1/completions endpoint: openAIToOpenAITranslatorV1Completion.ResponseBody, buffered branch
+ * (internal/translator/openai_completions.go:98-150) — json.Unmarshal of the whole body into openai.CompletionResponse (trailing bytes
+ * are an error here: AIGW_INTERNAL), responseModel = resp.Model with NO fallback (model_len 0 ⇒ empty), every counter set only when the
+ * body's value is >= 0 (a negative or >= 2^31 counter: AIGW_DECLINED). */
+int aigw_completions_response_usage_device(aigw_ctx* ctx, const uint8_t* d_bodies, const uint64_t* d_offsets, const uint32_t* d_lens, uint32_t n,
+                                           aigw_sse_result* d_results, void* stream, float* kernel_ms);
+int aigw_completions_response_usage_host(aigw_ctx* ctx, const uint8_t* bodies, const uint64_t* offsets, const uint32_t* lens, uint32_t n,
+                                         aigw_sse_result* results, const int32_t* cost_types, uint32_t n_costs, uint64_t* costs /* n * n_costs, may be NULL */);
 int aigw_usage_costs_device(aigw_ctx* ctx, const aigw_sse_result* d_results, uint32_t n, const int32_t* d_cost_types, uint32_t n_costs,
                             uint64_t* d_costs, void* stream);
 
@@ -278,6 +286,9 @@ int aigw_bedrock_stream_host(aigw_ctx* ctx, const aigw_bedrock_stream_cfg* cfg, 
  *   AIGW_STREAM_AWS_ANTHROPIC        OpenAI chat completions to Anthropic on AWS Bedrock (openai_awsanthropic.go:162-184,216-261): eventstream
  *                                    frames whose payload is {"bytes": base64(event JSON)} are unwrapped and run through the same
  *                                    Anthropic → OpenAI SSE parser as AIGW_STREAM_GCP_ANTHROPIC
+ *   AIGW_STREAM_OPENAI_COMPLETIONS   legacy /v1/completions passthrough (openai_completions.go:80-96,157-203): usage scan over
+ *                                    openai.CompletionResponse chunks, body UNCHANGED; responseModel is the stream's own model (model_len 0
+ *                                    until a chunk carried one: this translator has no fallback to the request model)
  *   AIGW_STREAM_GCP_GEMINI_BUFFERED  buffered GenerateContentResponse → ChatCompletionResponse (openai_gcpvertexai.go:139-198): feed the
  *                              body (≤ 15.6 KB) and set eos on the last call; the usage record is the call's `usage`
  * aigw_stream_chunks processes one ResponseBody call for each of n streams in ONE batch (a stream may appear once per call;
@@ -289,7 +300,7 @@ int aigw_bedrock_stream_host(aigw_ctx* ctx, const aigw_bedrock_stream_cfg* cfg, 
  * AIGW_R_TOO_LARGE carry above 15.6 KB, AIGW_R_OUT_SPACE, AIGW_R_ARENA_FULL) — both are sticky for the stream.
  * cfg strings must not need JSON escaping (printable ASCII without '"' and '\\', ≤ 160 bytes), else -2. */
 enum aigw_stream_kind { AIGW_STREAM_OPENAI = 0, AIGW_STREAM_AWS_BEDROCK = 1, AIGW_STREAM_GCP_ANTHROPIC = 2, AIGW_STREAM_GCP_GEMINI = 3, AIGW_STREAM_GCP_GEMINI_BUFFERED = 4,
-                        AIGW_STREAM_ANTHROPIC = 5, AIGW_STREAM_AWS_ANTHROPIC = 6 };
+                        AIGW_STREAM_ANTHROPIC = 5, AIGW_STREAM_AWS_ANTHROPIC = 6, AIGW_STREAM_OPENAI_COMPLETIONS = 7 };
 typedef struct aigw_stream_cfg { int32_t kind; int32_t _pad; int64_t created; const char* request_model; const char* response_id; } aigw_stream_cfg;
 typedef struct aigw_chunk_in { uint64_t handle; const uint8_t* bytes; uint32_t len; uint32_t eos; } aigw_chunk_in;
 typedef struct aigw_chunk_result {
