@@ -116,7 +116,7 @@ def load_library():
                                              C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
     L.aigw_chat_translate_device_mapped.argtypes = [C.c_void_p, C.POINTER(BackendCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
                                                     C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
-    L.aigw_chat_last_profile.argtypes = [C.c_void_p, C.POINTER(C.c_float * 3), C.POINTER(C.c_int)]
+    L.aigw_chat_last_profile.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
     L.aigw_chat_set_profile.argtypes = [C.c_void_p, C.c_int]
     L.aigw_chat_set_small_batch.argtypes = [C.c_void_p, C.c_int]; L.aigw_chat_set_small_batch.restype = None
     L.aigw_chat_translate_host.argtypes = [C.c_void_p, C.POINTER(BackendCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(_BatchOut)]
