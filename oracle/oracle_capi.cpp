@@ -25,6 +25,7 @@ namespace oracle { TranslateResult gemini_request_body(const ChatReq& r, const s
 #include "messages_translated.hpp"
 #include "stream.hpp"
 #include "completions.hpp"
+#include "messages_openai_response.hpp"
 #include "translate.hpp"
 
 using namespace oracle;
@@ -182,6 +183,25 @@ int oracle_response_completions(const char* body, uint64_t len, oracle_usage* ou
   bool ok = response_completions(std::string_view(body, len), tu, rm);
   put(out, tu); uint64_t n = std::min<uint64_t>(cap, rm.size()); memcpy(model_buf, rm.data(), n); *model_len = rm.size();
   return ok ? 0 : 1;
+}
+// ---- T5 response direction, OpenAI backend: OpenAI SSE -> Anthropic SSE (one ResponseBody call per feed) and the buffered form
+struct o2a_handle { OpenAIToAnthropicStream st; std::string model; };
+void* oracle_messages_openai_stream_open(const char* request_model) { auto* h = new o2a_handle(); h->st.request_model = request_model ? request_model : ""; return h; }
+void oracle_messages_openai_stream_close(void* h) { delete (o2a_handle*)h; }
+// returns malloc'd output (free with oracle_free)
+char* oracle_messages_openai_stream_feed(void* hv, const char* chunk, uint64_t len, int eos, uint64_t* out_len, oracle_usage* usage, int* status) {
+  auto* h = (o2a_handle*)hv; std::string o; TokenUsage u;
+  const Status s = messages_openai_stream_feed(h->st, std::string_view(chunk, len), eos != 0, o, u, h->model);
+  put(usage, u); *status = (int)s; *out_len = o.size();
+  char* r = (char*)malloc(o.size() + 1); memcpy(r, o.data(), o.size()); r[o.size()] = 0; return r;
+}
+uint64_t oracle_messages_openai_stream_model(void* hv, char* buf, uint64_t cap) { auto* h = (o2a_handle*)hv; uint64_t n = std::min<uint64_t>(cap, h->model.size()); memcpy(buf, h->model.data(), n); return h->model.size(); }
+uint64_t oracle_messages_openai_stream_buffered(void* hv) { return ((o2a_handle*)hv)->st.buffer.size(); }
+char* oracle_messages_openai_response(const char* body, uint64_t len, const char* request_model, uint64_t* out_len, oracle_usage* usage, char* model_buf, uint64_t cap, uint64_t* model_len, int* ok) {
+  std::string o, rm; TokenUsage u;
+  *ok = messages_openai_response(std::string_view(body, len), request_model ? request_model : "", o, u, rm) ? 1 : 0;
+  put(usage, u); uint64_t n = std::min<uint64_t>(cap, rm.size()); memcpy(model_buf, rm.data(), n); *model_len = rm.size(); *out_len = o.size();
+  char* r = (char*)malloc(o.size() + 1); memcpy(r, o.data(), o.size()); r[o.size()] = 0; return r;
 }
 uint64_t oracle_eval_cost(int type, const oracle_usage* u) { TokenUsage t; t.input = u->input; t.output = u->output; t.total = u->total; t.cached = u->cached; t.cache_creation = u->cache_creation; t.reasoning = u->reasoning; t.mask = u->mask; return eval_cost(type, t); }
 

@@ -119,6 +119,50 @@ def response_openai(body: bytes, request_model: bytes = b""):
     return rc == 0, u, buf.raw[:ml.value]
 
 
+class MessagesOpenAIStream:
+    """/v1/messages served by an OpenAI backend, stream direction (T5): feed(chunk, eos) -> (status, Anthropic SSE bytes, Usage);
+    model() = responseModel of the last call (internal/translator/anthropic_openai.go:154-185, openai_helper.go:340-766)."""
+    def __init__(self, request_model: bytes):
+        L = lib()
+        L.oracle_messages_openai_stream_open.restype = C.c_void_p; L.oracle_messages_openai_stream_open.argtypes = [C.c_char_p]
+        L.oracle_messages_openai_stream_close.argtypes = [C.c_void_p]
+        L.oracle_messages_openai_stream_feed.restype = C.c_void_p
+        L.oracle_messages_openai_stream_feed.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(Usage), C.POINTER(C.c_int)]
+        L.oracle_messages_openai_stream_model.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]; L.oracle_messages_openai_stream_model.restype = C.c_uint64
+        L.oracle_messages_openai_stream_buffered.argtypes = [C.c_void_p]; L.oracle_messages_openai_stream_buffered.restype = C.c_uint64
+        self.h = L.oracle_messages_openai_stream_open(request_model)
+
+    def feed(self, chunk: bytes, eos: bool):
+        n = C.c_uint64(0); u = Usage(); st = C.c_int(0)
+        vp = lib().oracle_messages_openai_stream_feed(self.h, chunk, len(chunk), int(eos), C.byref(n), C.byref(u), C.byref(st))
+        out = C.string_at(vp, n.value); lib().oracle_free(vp)
+        return st.value, out, u
+
+    def model(self) -> bytes:
+        buf = C.create_string_buffer(4096)
+        n = lib().oracle_messages_openai_stream_model(self.h, buf, 4096)
+        return buf.raw[:n]
+
+    def buffered(self) -> int:
+        return lib().oracle_messages_openai_stream_buffered(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_messages_openai_stream_close(self.h); self.h = None
+
+
+def messages_openai_response(body: bytes, request_model: bytes = b""):
+    """(ok, anthropic.MessagesResponse bytes, Usage, response_model) — buffered ChatCompletionResponse of a /v1/messages call
+    (internal/translator/anthropic_openai.go:112-152, openai_helper.go:263-338)."""
+    L = lib()
+    L.oracle_messages_openai_response.restype = C.c_void_p
+    L.oracle_messages_openai_response.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(Usage), C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+    n = C.c_uint64(0); u = Usage(); buf = C.create_string_buffer(4096); ml = C.c_uint64(0); ok = C.c_int(0)
+    vp = L.oracle_messages_openai_response(body, len(body), request_model, C.byref(n), C.byref(u), buf, 4096, C.byref(ml), C.byref(ok))
+    out = C.string_at(vp, n.value); L.oracle_free(vp)
+    return bool(ok.value), out, u, buf.raw[:ml.value]
+
+
 class CompletionsSSEStream:
     """/v1/completions stream usage scan, one ResponseBody call per feed (internal/translator/openai_completions.go:80-96,157-203)."""
     def __init__(self):

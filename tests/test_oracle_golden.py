@@ -643,3 +643,63 @@ def test_anthropic_sampling_parameters():
         o = O.chat_translate(schema, b'{"model":"claude-3","messages":[{"role":"user"}],"temperature":2.5}', prefix="")
         assert o.status == O.INTERNAL, (o.status, o.err)
         assert O.chat_translate(schema, (base % ',"stop":[]').encode(), prefix="").status == O.DECLINED
+
+
+def _sse_lines(body):
+    """the fake upstream's line-by-line mode (tests/internal/testupstreamlib/server.go:303-320): every non-empty line becomes one event"""
+    return [b"data: " + l.encode() + b"\n\n" for l in body.split("\n") if l]
+
+
+MSG_OPENAI = [c for c in CASES if c["name"].startswith("anthropic-openai") and "responseBody" in c and "error" not in c["name"]]
+
+
+def test_messages_openai_response_goldens():
+    """T5 response direction, OpenAI backend (anthropic_openai.go:102-185, openai_helper.go:263-766): the three buffered data-plane
+    goldens and the two streamed ones byte for byte; the streams also one byte per call and as one call."""
+    assert len(MSG_OPENAI) == 5
+    for c in MSG_OPENAI:
+        req_model = json.loads(c["requestBody"])["model"].encode()
+        if c.get("responseType") == "sse":
+            whole = b"".join(_sse_lines(c["responseBody"]))
+            for chunks in (_sse_lines(c["responseBody"]), [whole], [whole[i:i + 1] for i in range(len(whole))]):
+                st = O.MessagesOpenAIStream(req_model); out = b""
+                for ch in chunks + [None]:
+                    s, o, u = st.feed(ch or b"", ch is None)
+                    assert s == O.OK
+                    out += o
+                assert out.decode().strip() == c["expResponseBody"].strip(), c["name"]
+                exp_in, exp_out = (10, 3) if "text" in c["name"] else (50, 15)
+                assert u.as_tuple() == (exp_in, 0, 0, exp_out, exp_in + exp_out, -1)
+                assert st.model() == b"gpt-4o" and st.buffered() == 0
+        else:
+            ok, out, u, model = O.messages_openai_response(c["responseBody"].encode(), req_model)
+            assert ok and out.decode() == c["expResponseBody"], c["name"]
+            j = json.loads(c["responseBody"])
+            assert model == (j.get("model") or req_model.decode()).encode()
+            p, q = j.get("usage", {}).get("prompt_tokens", 0), j.get("usage", {}).get("completion_tokens", 0)
+            assert u.as_tuple() == (p, -1, -1, q, p + q, -1)
+
+
+def test_messages_openai_response_rules():
+    # stream: text then a tool call closes the text block and opens block 1; a second delta of the same tool index reuses it; no usage
+    # chunk: the closing events come at end of stream with output_tokens 0; malformed chunks and [DONE] are skipped
+    st = O.MessagesOpenAIStream(b"req")
+    feeds = [b'data: {"choices":[{"delta":{"content":"a"}}]}\n\n', b'data: not json\n\ndata: [DONE]\n\n',
+             b'data: {"id":"x","choices":[{"delta":{"tool_calls":[{"index":3,"id":"c1","function":{"name":"f","arguments":""}},{"index":3,"function":{"arguments":"{}"}}]},"finish_reason":"length"}]}\n\n']
+    out = b""
+    for f in feeds:
+        out += st.feed(f, False)[1]
+    s, o, u = st.feed(b"", True); out += o
+    ev = [l for l in out.decode().split("\n") if l.startswith("data: ")]
+    assert [json.loads(e[6:])["type"] for e in ev] == ["message_start", "content_block_start", "content_block_delta", "content_block_stop", "content_block_start",
+                                                        "content_block_delta", "content_block_stop", "message_delta", "message_stop"]
+    assert json.loads(ev[0][6:])["message"]["model"] == "req" and json.loads(ev[0][6:])["message"]["id"] == ""
+    assert json.loads(ev[4][6:])["index"] == 1 and json.loads(ev[5][6:])["delta"]["partial_json"] == "{}"
+    assert json.loads(ev[7][6:]) == {"type": "message_delta", "delta": {"stop_reason": "max_tokens", "stop_sequence": None}, "usage": {"output_tokens": 0}}
+    assert u.mask == 0 and st.model() == b"req"
+    # buffered: no choices -> content null and no stop_reason; unparsable arguments -> {}; decode failure -> error
+    ok, out, u, m = O.messages_openai_response(b'{"id":"i","choices":[]}', b"req")
+    assert ok and out == b'{"id":"i","type":"message","role":"assistant","content":null,"model":"req","usage":{"cache_creation_input_tokens":0,"cache_read_input_tokens":0,"input_tokens":0,"output_tokens":0}}'
+    ok, out, u, m = O.messages_openai_response(b'{"choices":[{"message":{"tool_calls":[{"id":"t","function":{"name":"f","arguments":"{\\"b\\": 1, \\"a\\": [true]}"}},{"function":{"arguments":"oops"}}]},"finish_reason":"content_filter"}]}', b"req")
+    assert ok and b'"input":{"a":[true],"b":1}' in out and b'{"type":"tool_use","id":"","name":"","input":{}}' in out and b'"stop_reason":"refusal"' in out
+    assert not O.messages_openai_response(b'{"choices":{}}', b"req")[0]
