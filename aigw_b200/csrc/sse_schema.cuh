@@ -111,4 +111,67 @@ static inline SchemaBlob build_completion_schema() {
   return b;
 }
 
+// ------------------------------------------------------------------ R1: non-stream ChatCompletionResponse usage
+// json.NewDecoder(body).Decode(&openai.ChatCompletionResponse{}) then usage / model
+// (internal/translator/openai_openai.go:146-174; struct internal/apischema/openai/openai.go:1269-1306,1365-1422).
+enum RN : uint8_t { R_ANY = 0, R_STR, R_INT, R_FLOAT, R_ROOT, R_CHOICES, R_CHOICE, R_MSG, R_TOOLCALLS, R_TOOLCALL, R_FUNC, R_CACHE, R_ANNOTS, R_ANNOT, R_URLCIT,
+                  R_AUDIO, R_REASON_U, R_REASON_O, R_REASON_BLOCK, R_REASON_TEXT, R_B64, R_THINKS, R_THINK, R_LOGPROBS, R_TOKLPS, R_TOKLP, R_INTS, R_TOPLPS, R_TOPLP,
+                  R_USAGE, R_CTD, R_PTD, R_CREATED, R_MODEL, R_PROMPT, R_COMPLETION, R_TOTAL, R_REASONING_TOK, R_CACHED, R_CACHE_CREATION,
+                  R_EM_DATA, R_EM_ITEM, R_EM_VEC, R_EM_FLOATS, R_EM_USAGE, R_COUNT };
+static const FieldDef kRespFields[] = {
+  {R_ROOT, "id", R_STR}, {R_ROOT, "choices", R_CHOICES}, {R_ROOT, "created", R_CREATED}, {R_ROOT, "model", R_MODEL}, {R_ROOT, "service_tier", R_STR},
+  {R_ROOT, "system_fingerprint", R_STR}, {R_ROOT, "object", R_STR}, {R_ROOT, "usage", R_USAGE}, {R_ROOT, "obfuscation", R_STR},
+  {R_CHOICE, "finish_reason", R_STR}, {R_CHOICE, "index", R_INT}, {R_CHOICE, "logprobs", R_LOGPROBS}, {R_CHOICE, "message", R_MSG},
+  {R_MSG, "content", R_STR}, {R_MSG, "role", R_STR}, {R_MSG, "tool_calls", R_TOOLCALLS}, {R_MSG, "annotations", R_ANNOTS}, {R_MSG, "audio", R_AUDIO},
+  {R_MSG, "reasoning_content", R_REASON_U}, {R_MSG, "thinking_blocks", R_THINKS}, {R_MSG, "safety_ratings", R_ANY}, {R_MSG, "grounding_metadata", R_ANY},
+  {R_TOOLCALL, "id", R_STR}, {R_TOOLCALL, "function", R_FUNC}, {R_TOOLCALL, "type", R_STR}, {R_TOOLCALL, "cache_control", R_CACHE},
+  {R_FUNC, "arguments", R_STR}, {R_FUNC, "name", R_STR},
+  {R_CACHE, "type", R_STR}, {R_CACHE, "ttl", R_STR},
+  {R_ANNOT, "type", R_STR}, {R_ANNOT, "url_citation", R_URLCIT},
+  {R_URLCIT, "end_index", R_INT}, {R_URLCIT, "start_index", R_INT}, {R_URLCIT, "url", R_STR}, {R_URLCIT, "title", R_STR},
+  {R_AUDIO, "data", R_STR}, {R_AUDIO, "expires_at", R_INT}, {R_AUDIO, "id", R_STR}, {R_AUDIO, "transcript", R_STR},
+  {R_REASON_O, "reasoningContent", R_REASON_BLOCK},
+  {R_REASON_BLOCK, "reasoningText", R_REASON_TEXT}, {R_REASON_BLOCK, "redactedContent", R_B64},
+  {R_REASON_TEXT, "text", R_STR}, {R_REASON_TEXT, "signature", R_STR},
+  {R_THINK, "type", R_STR}, {R_THINK, "thinking", R_STR}, {R_THINK, "signature", R_STR}, {R_THINK, "data", R_STR},
+  {R_LOGPROBS, "content", R_TOKLPS}, {R_LOGPROBS, "refusal", R_TOKLPS},
+  {R_TOKLP, "token", R_STR}, {R_TOKLP, "bytes", R_INTS}, {R_TOKLP, "logprob", R_FLOAT}, {R_TOKLP, "top_logprobs", R_TOPLPS},
+  {R_TOPLP, "token", R_STR}, {R_TOPLP, "bytes", R_INTS}, {R_TOPLP, "logprob", R_FLOAT},
+  {R_USAGE, "prompt_tokens", R_PROMPT}, {R_USAGE, "completion_tokens", R_COMPLETION}, {R_USAGE, "total_tokens", R_TOTAL},
+  {R_USAGE, "completion_tokens_details", R_CTD}, {R_USAGE, "prompt_tokens_details", R_PTD},
+  {R_CTD, "text_tokens", R_INT}, {R_CTD, "accepted_prediction_tokens", R_INT}, {R_CTD, "audio_tokens", R_INT}, {R_CTD, "reasoning_tokens", R_REASONING_TOK}, {R_CTD, "rejected_prediction_tokens", R_INT},
+  {R_PTD, "text_tokens", R_INT}, {R_PTD, "audio_tokens", R_INT}, {R_PTD, "cached_tokens", R_CACHED}, {R_PTD, "cache_creation_input_tokens", R_CACHE_CREATION},
+};
+static constexpr int kNumRespFields = sizeof(kRespFields) / sizeof(kRespFields[0]);
+struct alignas(16) RespSchemaBlob { Node nodes[R_COUNT]; Field fields[80]; char keys[1024]; };
+static_assert(kNumRespFields <= 80, "response field table too small");
+
+static inline RespSchemaBlob build_resp_schema() {
+  RespSchemaBlob b; memset(&b, 0, sizeof b);
+  auto set = [&](int n, uint8_t kind, uint8_t cap = NOCAP, uint8_t elem = 0) { b.nodes[n].kind = kind; b.nodes[n].cap = cap; b.nodes[n].elem = elem; };
+  set(R_ANY, K_ANY); set(R_STR, K_STR); set(R_INT, K_INT); set(R_FLOAT, K_FLOAT);
+  set(R_ROOT, K_OBJ); set(R_CHOICES, K_ARR, NOCAP, R_CHOICE); set(R_CHOICE, K_OBJ); set(R_MSG, K_OBJ);
+  set(R_TOOLCALLS, K_ARR, NOCAP, R_TOOLCALL); set(R_TOOLCALL, K_OBJ); set(R_FUNC, K_OBJ); set(R_CACHE, K_OBJ);
+  set(R_ANNOTS, K_ARR, NOCAP, R_ANNOT); set(R_ANNOT, K_OBJ); set(R_URLCIT, K_OBJ); set(R_AUDIO, K_OBJ);
+  set(R_REASON_U, K_STROBJ, NOCAP, R_REASON_O); set(R_REASON_O, K_OBJ); set(R_REASON_BLOCK, K_OBJ); set(R_REASON_TEXT, K_OBJ); set(R_B64, K_B64);
+  set(R_THINKS, K_ARR, NOCAP, R_THINK); set(R_THINK, K_OBJ);
+  set(R_LOGPROBS, K_OBJ); set(R_TOKLPS, K_ARR, NOCAP, R_TOKLP); set(R_TOKLP, K_OBJ); set(R_INTS, K_ARR, NOCAP, R_INT); set(R_TOPLPS, K_ARR, NOCAP, R_TOPLP); set(R_TOPLP, K_OBJ);
+  set(R_USAGE, K_OBJ, C_OBJ_USAGE); set(R_CTD, K_OBJ, C_OBJ_CTD); set(R_PTD, K_OBJ, C_OBJ_PTD);
+  set(R_CREATED, K_CREATED); set(R_MODEL, K_STR, C_SPAN_MODEL);
+  set(R_PROMPT, K_INT, C_PROMPT); set(R_COMPLETION, K_INT, C_COMPLETION); set(R_TOTAL, K_INT, C_TOTAL);
+  set(R_REASONING_TOK, K_INT, C_REASONING); set(R_CACHED, K_INT, C_CACHED); set(R_CACHE_CREATION, K_INT, C_CACHE_CREATION);
+  int ko = 0;
+  for (int f = 0; f < kNumRespFields; f++) {
+    const FieldDef& d = kRespFields[f];
+    Node& o = b.nodes[d.owner];
+    if (o.nf == 0) o.f0 = (uint8_t)f;
+    o.nf++;
+    int kl = (int)strlen(d.key);
+    b.fields[f].koff = (uint16_t)ko; b.fields[f].klen = (uint8_t)kl; b.fields[f].node = d.node;
+    memcpy(b.keys + ko, d.key, kl); ko += kl;
+  }
+  return b;
+}
+
+
 }  // namespace aigw

@@ -13,6 +13,7 @@ namespace {
 // ------------------------------------------------------------------ device tables (one copy per device, uploaded on first use)
 __device__ SchemaBlob g_chunk_schema;        // openai.ChatCompletionResponseChunk
 __device__ SchemaBlob g_cmpl_schema;         // openai.CompletionResponse (legacy /v1/completions)
+__device__ RespSchemaBlob g_o2a_resp_schema; // openai.ChatCompletionResponse (buffered /v1/messages response of an OpenAI backend)
 __device__ BedrockSchema g_conv_schema;      // awsbedrock.ConverseStreamEvent
 __device__ uint32_t g_crc_tab[256];          // IEEE CRC-32
 
@@ -947,6 +948,9 @@ __device__ void step_anthropic_native(StreamSlot& S, const StreamStep& st, uint8
   if (ml <= st.out_cap) { for (uint32_t k = 0; k < ml; k++) out[k] = (uint8_t)m[k]; R.model_len = ml; }
 }
 
+#include "stream_messages_openai.cuh"
+
+#ifndef AIGW_HOST_HARNESS
 // ------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(128) stream_init_kernel(StreamSlot* slots, const uint32_t* slot_ids, uint32_t n, const uint8_t* tmpl) {
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -1001,6 +1005,8 @@ __global__ void __launch_bounds__(64) stream_step_kernel(const __grid_constant__
       case AIGW_STREAM_ANTHROPIC: step_anthropic_native(S, st, out, R); break;
       case AIGW_STREAM_AWS_ANTHROPIC: step_aws_anthropic(S, st, out, R); break;
       case AIGW_STREAM_OPENAI_COMPLETIONS: step_openai(S, st, out, R, true); break;
+      case AIGW_STREAM_MESSAGES_OPENAI: step_messages_openai(S, st, out, R); break;
+      case AIGW_STREAM_MESSAGES_OPENAI_BUFFERED: step_messages_openai_buffered(S, st, out, R); break;
       default: R.status = AIGW_DECLINED; R.reason = AIGW_R_SCHEMA; break;
     }
   }
@@ -1037,6 +1043,7 @@ cudaError_t launch_stream_steps(const StreamParams& P, cudaStream_t st) {
     const cudaError_t e0 = device_once(once, nullptr, [&](int*) {
       SchemaBlob a = build_schema(); cudaError_t e = cudaMemcpyToSymbol(g_chunk_schema, &a, sizeof a); if (e != cudaSuccess) return e;
       a = build_completion_schema(); e = cudaMemcpyToSymbol(g_cmpl_schema, &a, sizeof a); if (e != cudaSuccess) return e;
+      { RespSchemaBlob r = build_resp_schema(); e = cudaMemcpyToSymbol(g_o2a_resp_schema, &r, sizeof r); if (e != cudaSuccess) return e; }
       BedrockSchema b = build_schema_bedrock(); e = cudaMemcpyToSymbol(g_conv_schema, &b, sizeof b); if (e != cudaSuccess) return e;
       AnSchema c = build_an_schema(); e = cudaMemcpyToSymbol(g_an_schema, &c, sizeof c); if (e != cudaSuccess) return e;
       uint32_t tab[256];
@@ -1051,5 +1058,8 @@ cudaError_t launch_stream_steps(const StreamParams& P, cudaStream_t st) {
   stream_pack_kernel<<<(P.n * 32 + 127) / 128, 128, 0, st>>>(P);
   return cudaGetLastError();
 }
+#else   // the CPU-side parser harness (tools/stream_host_check.cpp) compiles only the per-thread step functions above
+}  // namespace
+#endif  // AIGW_HOST_HARNESS
 
 }  // namespace aigw

@@ -289,6 +289,16 @@ int aigw_bedrock_stream_host(aigw_ctx* ctx, const aigw_bedrock_stream_cfg* cfg, 
  *   AIGW_STREAM_OPENAI_COMPLETIONS   legacy /v1/completions passthrough (openai_completions.go:80-96,157-203): usage scan over
  *                                    openai.CompletionResponse chunks, body UNCHANGED; responseModel is the stream's own model (model_len 0
  *                                    until a chunk carried one: this translator has no fallback to the request model)
+ *   AIGW_STREAM_MESSAGES_OPENAI      /v1/messages served by an OpenAI-schema backend, response direction (anthropic_openai.go:154-185,
+ *                                    openai_helper.go:436-766): OpenAI chat-completion SSE chunks become Anthropic SSE events (message_start,
+ *                                    content_block_start / delta / stop for text and tool_use blocks, message_delta, message_stop); the
+ *                                    usage chunk or end of stream closes the message.  Body EMPTY when a call produced no event (the
+ *                                    reference suppresses the upstream bytes); responseModel = the stream's model, else the request's.
+ *                                    Strings that would need re-escaping, null tool calls and more than 15 tool indices DECLINE.
+ *   AIGW_STREAM_MESSAGES_OPENAI_BUFFERED  the buffered form (anthropic_openai.go:112-152, openai_helper.go:263-338): feed the
+ *                                    ChatCompletionResponse (≤ 15.6 KB), eos on the last call; the result body is the
+ *                                    anthropic.MessagesResponse.  A tool call's `arguments` must already be the compact, key-sorted
+ *                                    JSON object the reference's map round trip produces (else DECLINED).
  *   AIGW_STREAM_GCP_GEMINI_BUFFERED  buffered GenerateContentResponse → ChatCompletionResponse (openai_gcpvertexai.go:139-198): feed the
  *                              body (≤ 15.6 KB) and set eos on the last call; the usage record is the call's `usage`
  * aigw_stream_chunks processes one ResponseBody call for each of n streams in ONE batch (a stream may appear once per call;
@@ -300,7 +310,8 @@ int aigw_bedrock_stream_host(aigw_ctx* ctx, const aigw_bedrock_stream_cfg* cfg, 
  * AIGW_R_TOO_LARGE carry above 15.6 KB, AIGW_R_OUT_SPACE, AIGW_R_ARENA_FULL) — both are sticky for the stream.
  * cfg strings must not need JSON escaping (printable ASCII without '"' and '\\', ≤ 160 bytes), else -2. */
 enum aigw_stream_kind { AIGW_STREAM_OPENAI = 0, AIGW_STREAM_AWS_BEDROCK = 1, AIGW_STREAM_GCP_ANTHROPIC = 2, AIGW_STREAM_GCP_GEMINI = 3, AIGW_STREAM_GCP_GEMINI_BUFFERED = 4,
-                        AIGW_STREAM_ANTHROPIC = 5, AIGW_STREAM_AWS_ANTHROPIC = 6, AIGW_STREAM_OPENAI_COMPLETIONS = 7 };
+                        AIGW_STREAM_ANTHROPIC = 5, AIGW_STREAM_AWS_ANTHROPIC = 6, AIGW_STREAM_OPENAI_COMPLETIONS = 7,
+                        AIGW_STREAM_MESSAGES_OPENAI = 8, AIGW_STREAM_MESSAGES_OPENAI_BUFFERED = 9 };
 typedef struct aigw_stream_cfg { int32_t kind; int32_t _pad; int64_t created; const char* request_model; const char* response_id; } aigw_stream_cfg;
 typedef struct aigw_chunk_in { uint64_t handle; const uint8_t* bytes; uint32_t len; uint32_t eos; } aigw_chunk_in;
 typedef struct aigw_chunk_result {

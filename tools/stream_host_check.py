@@ -1,0 +1,112 @@
+"""Test tooling (CPU only): run the stream corpora of tests/test_messages_openai_response_gpu.py and tests/test_completions_gpu.py through the
+HOST build of the per-thread stream step functions (tools/stream_host_check.cpp) and compare every call with the oracle — the same
+assertions the GPU tests make, before spending GPU time.  Usage: python tools/stream_host_check.py"""
+import importlib.util
+import json
+import os
+import random
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
+import _oracle as O  # noqa: E402
+
+KIND = {"openai": 0, "openai-completions": 7, "messages-openai": 8, "messages-openai-buffered": 9}
+
+
+def load(name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tests", name + ".py")); m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m); return m
+
+
+class Host:
+    def __init__(self):
+        exe = "/tmp/stream_host_check"
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-I/usr/local/cuda/include", "-o", exe, os.path.join(ROOT, "tools", "stream_host_check.cpp")], stderr=subprocess.DEVNULL)
+        self.p = subprocess.Popen([exe], stdin=subprocess.PIPE, stdout=subprocess.PIPE)
+
+    def open(self, kind, model):
+        self.p.stdin.write(("open %d %s\n" % (KIND[kind], model.decode() or "-")).encode())
+
+    def feed(self, chunk, eos):
+        self.p.stdin.write(("feed %s %d\n" % (chunk.hex() or "-", int(eos))).encode()); self.p.stdin.flush()
+        f = self.p.stdout.readline().decode().split()
+        st, bk, carry = int(f[0]), int(f[1]), int(f[2])
+        i, o, t, c, cc, r, m = [int(x) for x in f[3:10]]
+        usage = (i if m & 1 else -1, c if m & 8 else -1, cc if m & 16 else -1, o if m & 2 else -1, t if m & 4 else -1, r if m & 32 else -1)
+        unh = lambda h: b"" if h == "-" else bytes.fromhex(h)
+        return {"status": st, "body_kind": bk, "carry_len": carry, "usage": usage, "model": unh(f[10]), "body": unh(f[11])}
+
+
+def main():
+    T = load("test_messages_openai_response_gpu")
+    H = Host()
+    # goldens under four chunkings
+    for c in T.GOLD:
+        req_model = json.loads(c["requestBody"])["model"].encode()
+        if c.get("responseType") == "sse":
+            blocks = T.sse_lines(c["responseBody"])
+            for name, chunks in T.chunkings(b"".join(blocks), blocks).items():
+                H.open("messages-openai", req_model); orc = O.MessagesOpenAIStream(req_model); out = b""
+                for ch in chunks + [None]:
+                    r = H.feed(ch or b"", ch is None); s, o, u = orc.feed(ch or b"", ch is None)
+                    assert r["status"] == s == 0 and r["body"] == o and r["usage"] == u.as_tuple() and r["model"] == orc.model() and r["carry_len"] == orc.buffered(), (c["name"], name, r, o)
+                    assert r["body_kind"] == (1 if o else 2)
+                    out += r["body"]
+                assert out.decode().strip() == c["expResponseBody"].strip(), c["name"]
+        else:
+            b = c["responseBody"].encode()
+            H.open("messages-openai-buffered", req_model); H.feed(b[: len(b) // 2], False); r = H.feed(b[len(b) // 2:], True)
+            assert r["status"] == 0 and r["body"] == c["expResponseBody"].encode(), (c["name"], r)
+    print("goldens ok")
+    # stream corpus
+    rng = random.Random(31); dead = 0; produced = 0; n = 256
+    for s in range(n):
+        data = T.gen_stream(rng, s)
+        cuts = sorted(rng.sample(range(1, len(data)), min(rng.randint(0, 12), len(data) - 1)))
+        chunks = [data[a:b] for a, b in zip([0] + cuts, cuts + [len(data)])] + [b""]
+        H.open("messages-openai", b"req-model"); orc = O.MessagesOpenAIStream(b"req-model")
+        for k, ch in enumerate(chunks):
+            e = k == len(chunks) - 1
+            r = H.feed(ch, e); st, o, u = orc.feed(ch, e)
+            if r["status"] == 4: dead += 1; break
+            assert r["status"] == st == 0, (s, k, r)
+            assert r["body"] == o, (s, k, ch, r["body"], o)
+            assert r["usage"] == u.as_tuple() and r["model"] == orc.model() and r["carry_len"] == orc.buffered(), (s, k, r, u.as_tuple(), orc.model())
+            assert r["body_kind"] == (1 if o else 2)
+            produced += len(o)
+    print("stream corpus: declined", dead, "of", n, "bytes", produced)
+    assert dead < n // 2 and produced > 50_000
+    # buffered corpus
+    rng = random.Random(9)
+    bodies = [(T.gen_response(rng, i), b"req-model") for i in range(1500)]
+    bodies += [(b, b"req-model") for b in (b"null", b"{}", b"[]", b"", b'{"choices":[{"message":{"tool_calls":[null]}}]}', b'{"id":"a\\u0062"}', b'{"usage":{"prompt_tokens":-1}}')]
+    n_ok = n_err = n_decl = 0
+    for b, m in bodies:
+        H.open("messages-openai-buffered", m); H.feed(b[: len(b) // 2], False); g = H.feed(b[len(b) // 2:], True)
+        ok, o, u, model = O.messages_openai_response(b, m)
+        if g["status"] == 4: n_decl += 1; continue
+        if not ok:
+            assert g["status"] == 3, (b, g); n_err += 1; continue
+        assert g["status"] == 0 and g["body_kind"] == 1 and g["body"] == o, (b, g["body"], o)
+        assert g["usage"] == u.as_tuple() and g["model"] == model, (b, g, u.as_tuple(), model)
+        n_ok += 1
+    print("buffered corpus: ok", n_ok, "errors", n_err, "declined", n_decl)
+    assert n_ok > 800 and n_err > 60
+    # the /v1/completions kind over its GPU-test corpus
+    C = load("test_completions_gpu")
+    rng = random.Random(21); dead = 0; with_usage = 0
+    for s in range(192):
+        data = C._stream(rng, rng.randint(1, 14))
+        cuts = sorted(rng.sample(range(1, len(data)), min(rng.randint(0, 9), len(data) - 1)))
+        H.open("openai-completions", b"req-model"); orc = O.CompletionsSSEStream()
+        for ch in [data[a:b] for a, b in zip([0] + cuts, cuts + [len(data)])]:
+            r = H.feed(ch, False); u = orc.feed(ch)
+            if r["status"] == 4: dead += 1; break
+            assert r["status"] == 0 and r["usage"] == u.as_tuple() and r["model"] == orc.model() and r["carry_len"] == orc.buffered(), (s, ch, r, u.as_tuple())
+            with_usage += 1 if u.mask else 0
+    print("completions stream corpus: declined", dead, "with usage", with_usage)
+
+
+if __name__ == "__main__":
+    main()
