@@ -727,7 +727,7 @@ int aigw_stream_open_batch(aigw_ctx* ctx, const aigw_stream_cfg* cfg, uint32_t n
   auto& sp = ctx->sp;
   std::lock_guard<std::mutex> lk(sp.mu);
   const char* model = cfg->request_model ? cfg->request_model : ""; const char* id = cfg->response_id ? cfg->response_id : "";
-  if (cfg->kind < AIGW_STREAM_OPENAI || cfg->kind > AIGW_STREAM_MESSAGES_OPENAI_BUFFERED || strlen(model) > 160 || strlen(id) > 160 || !plain_json_text(model) || !plain_json_text(id)) {
+  if (cfg->kind < AIGW_STREAM_OPENAI || cfg->kind > AIGW_STREAM_MESSAGES_AWS_ANTHROPIC || strlen(model) > 160 || strlen(id) > 160 || !plain_json_text(model) || !plain_json_text(id)) {
     ctx->err = "stream cfg: unknown kind, or request_model / response_id need JSON escaping or exceed 160 bytes"; return -2;
   }
   if (sp.free_list.size() < n) { const int rc = stream_pool_grow(ctx, sp.cap + (uint32_t)(n - sp.free_list.size())); if (rc) return rc; }

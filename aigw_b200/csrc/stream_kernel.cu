@@ -949,6 +949,7 @@ __device__ void step_anthropic_native(StreamSlot& S, const StreamStep& st, uint8
 }
 
 #include "stream_messages_openai.cuh"
+#include "stream_messages_aws_anthropic.cuh"
 
 #ifndef AIGW_HOST_HARNESS
 // ------------------------------------------------------------------ kernels
@@ -1007,6 +1008,7 @@ __global__ void __launch_bounds__(64) stream_step_kernel(const __grid_constant__
       case AIGW_STREAM_OPENAI_COMPLETIONS: step_openai(S, st, out, R, true); break;
       case AIGW_STREAM_MESSAGES_OPENAI: step_messages_openai(S, st, out, R); break;
       case AIGW_STREAM_MESSAGES_OPENAI_BUFFERED: step_messages_openai_buffered(S, st, out, R); break;
+      case AIGW_STREAM_MESSAGES_AWS_ANTHROPIC: step_messages_aws_anthropic(S, st, out, R); break;
       default: R.status = AIGW_DECLINED; R.reason = AIGW_R_SCHEMA; break;
     }
   }

@@ -299,6 +299,11 @@ int aigw_bedrock_stream_host(aigw_ctx* ctx, const aigw_bedrock_stream_cfg* cfg, 
  *                                    ChatCompletionResponse (≤ 15.6 KB), eos on the last call; the result body is the
  *                                    anthropic.MessagesResponse.  A tool call's `arguments` must already be the compact, key-sorted
  *                                    JSON object the reference's map round trip produces (else DECLINED).
+ *   AIGW_STREAM_MESSAGES_AWS_ANTHROPIC  /v1/messages served by Anthropic on AWS Bedrock, streamed (anthropic_awsanthropic.go:93-160): every
+ *                                    eventstream frame carries {"bytes": base64(MessagesStreamChunk JSON)}; a chunk that decodes is forwarded as
+ *                                    "event: <type>\ndata: <decoded bytes>\n\n" and reflected into the usage (message_start / message_delta,
+ *                                    totals at eos), one that does not is dropped; message_start with content blocks, non-integer counts,
+ *                                    web_search_tool_result blocks and escaped member names DECLINE.
  *   AIGW_STREAM_GCP_GEMINI_BUFFERED  buffered GenerateContentResponse → ChatCompletionResponse (openai_gcpvertexai.go:139-198): feed the
  *                              body (≤ 15.6 KB) and set eos on the last call; the usage record is the call's `usage`
  * aigw_stream_chunks processes one ResponseBody call for each of n streams in ONE batch (a stream may appear once per call;
@@ -311,7 +316,7 @@ int aigw_bedrock_stream_host(aigw_ctx* ctx, const aigw_bedrock_stream_cfg* cfg, 
  * cfg strings must not need JSON escaping (printable ASCII without '"' and '\\', ≤ 160 bytes), else -2. */
 enum aigw_stream_kind { AIGW_STREAM_OPENAI = 0, AIGW_STREAM_AWS_BEDROCK = 1, AIGW_STREAM_GCP_ANTHROPIC = 2, AIGW_STREAM_GCP_GEMINI = 3, AIGW_STREAM_GCP_GEMINI_BUFFERED = 4,
                         AIGW_STREAM_ANTHROPIC = 5, AIGW_STREAM_AWS_ANTHROPIC = 6, AIGW_STREAM_OPENAI_COMPLETIONS = 7,
-                        AIGW_STREAM_MESSAGES_OPENAI = 8, AIGW_STREAM_MESSAGES_OPENAI_BUFFERED = 9 };
+                        AIGW_STREAM_MESSAGES_OPENAI = 8, AIGW_STREAM_MESSAGES_OPENAI_BUFFERED = 9, AIGW_STREAM_MESSAGES_AWS_ANTHROPIC = 10 };
 typedef struct aigw_stream_cfg { int32_t kind; int32_t _pad; int64_t created; const char* request_model; const char* response_id; } aigw_stream_cfg;
 typedef struct aigw_chunk_in { uint64_t handle; const uint8_t* bytes; uint32_t len; uint32_t eos; } aigw_chunk_in;
 typedef struct aigw_chunk_result {

@@ -26,6 +26,7 @@ namespace oracle { TranslateResult gemini_request_body(const ChatReq& r, const s
 #include "stream.hpp"
 #include "completions.hpp"
 #include "messages_openai_response.hpp"
+#include "messages_aws_anthropic_stream.hpp"
 #include "translate.hpp"
 
 using namespace oracle;
@@ -203,6 +204,18 @@ char* oracle_messages_openai_response(const char* body, uint64_t len, const char
   put(usage, u); uint64_t n = std::min<uint64_t>(cap, rm.size()); memcpy(model_buf, rm.data(), n); *model_len = rm.size(); *out_len = o.size();
   char* r = (char*)malloc(o.size() + 1); memcpy(r, o.data(), o.size()); r[o.size()] = 0; return r;
 }
+// ---- T5: /v1/messages on Anthropic behind AWS Bedrock, stream (eventstream-wrapped chunks -> Anthropic SSE)
+struct maa_handle { MessagesAwsAnthropicStream st; std::string model; };
+void* oracle_messages_aws_anthropic_open(const char* request_model) { auto* h = new maa_handle(); h->st.nat.request_model = request_model ? request_model : ""; return h; }
+void oracle_messages_aws_anthropic_close(void* h) { delete (maa_handle*)h; }
+char* oracle_messages_aws_anthropic_feed(void* hv, const char* chunk, uint64_t len, int eos, uint64_t* out_len, oracle_usage* usage, int* status) {
+  auto* h = (maa_handle*)hv; std::string o; TokenUsage u;
+  const Status s = messages_aws_anthropic_stream_feed(h->st, std::string_view(chunk, len), eos != 0, o, u, h->model);
+  put(usage, u); *status = (int)s; *out_len = o.size();
+  char* r = (char*)malloc(o.size() + 1); memcpy(r, o.data(), o.size()); r[o.size()] = 0; return r;
+}
+uint64_t oracle_messages_aws_anthropic_model(void* hv, char* buf, uint64_t cap) { auto* h = (maa_handle*)hv; uint64_t n = std::min<uint64_t>(cap, h->model.size()); memcpy(buf, h->model.data(), n); return h->model.size(); }
+uint64_t oracle_messages_aws_anthropic_buffered(void* hv) { return ((maa_handle*)hv)->st.buffered.size(); }
 uint64_t oracle_eval_cost(int type, const oracle_usage* u) { TokenUsage t; t.input = u->input; t.output = u->output; t.total = u->total; t.cached = u->cached; t.cache_creation = u->cache_creation; t.reasoning = u->reasoning; t.mask = u->mask; return eval_cost(type, t); }
 
 // ---- S2: Bedrock eventstream → OpenAI SSE.  Replays ResponseBody over the given chunking; returns malloc'd output.

@@ -163,6 +163,38 @@ def messages_openai_response(body: bytes, request_model: bytes = b""):
     return bool(ok.value), out, u, buf.raw[:ml.value]
 
 
+class MessagesAwsAnthropicStream:
+    """/v1/messages on Anthropic behind AWS Bedrock, stream (T5): feed(chunk, eos) -> (status, Anthropic SSE bytes, Usage)
+    (internal/translator/anthropic_awsanthropic.go:93-160)."""
+    def __init__(self, request_model: bytes):
+        L = lib()
+        L.oracle_messages_aws_anthropic_open.restype = C.c_void_p; L.oracle_messages_aws_anthropic_open.argtypes = [C.c_char_p]
+        L.oracle_messages_aws_anthropic_close.argtypes = [C.c_void_p]
+        L.oracle_messages_aws_anthropic_feed.restype = C.c_void_p
+        L.oracle_messages_aws_anthropic_feed.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(Usage), C.POINTER(C.c_int)]
+        L.oracle_messages_aws_anthropic_model.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]; L.oracle_messages_aws_anthropic_model.restype = C.c_uint64
+        L.oracle_messages_aws_anthropic_buffered.argtypes = [C.c_void_p]; L.oracle_messages_aws_anthropic_buffered.restype = C.c_uint64
+        self.h = L.oracle_messages_aws_anthropic_open(request_model)
+
+    def feed(self, chunk: bytes, eos: bool):
+        n = C.c_uint64(0); u = Usage(); st = C.c_int(0)
+        vp = lib().oracle_messages_aws_anthropic_feed(self.h, chunk, len(chunk), int(eos), C.byref(n), C.byref(u), C.byref(st))
+        out = C.string_at(vp, n.value); lib().oracle_free(vp)
+        return st.value, out, u
+
+    def model(self) -> bytes:
+        buf = C.create_string_buffer(4096)
+        n = lib().oracle_messages_aws_anthropic_model(self.h, buf, 4096)
+        return buf.raw[:n]
+
+    def buffered(self) -> int:
+        return lib().oracle_messages_aws_anthropic_buffered(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_messages_aws_anthropic_close(self.h); self.h = None
+
+
 class CompletionsSSEStream:
     """/v1/completions stream usage scan, one ResponseBody call per feed (internal/translator/openai_completions.go:80-96,157-203)."""
     def __init__(self):

@@ -18,6 +18,7 @@ static void hex(const uint8_t* p, size_t n) { if (!n) { printf("-"); return; } f
 
 int main() {
   g_chunk_schema = build_schema(); g_cmpl_schema = build_completion_schema(); g_o2a_resp_schema = build_resp_schema();
+  for (uint32_t i = 0; i < 256; i++) { uint32_t v = i; for (int k = 0; k < 8; k++) v = (v & 1u) ? 0xEDB88320u ^ (v >> 1) : v >> 1; g_crc_tab[i] = v; }
   StreamSlot* S = new StreamSlot();
   std::vector<uint8_t> out(1 << 22);
   std::string cmd;
@@ -42,6 +43,8 @@ int main() {
         case AIGW_STREAM_OPENAI_COMPLETIONS: step_openai(*S, st, out.data(), R, true); break;
         case AIGW_STREAM_MESSAGES_OPENAI: step_messages_openai(*S, st, out.data(), R); break;
         case AIGW_STREAM_MESSAGES_OPENAI_BUFFERED: step_messages_openai_buffered(*S, st, out.data(), R); break;
+        case AIGW_STREAM_MESSAGES_AWS_ANTHROPIC: step_messages_aws_anthropic(*S, st, out.data(), R); break;
+        case AIGW_STREAM_ANTHROPIC: step_anthropic_native(*S, st, out.data(), R); break;
         default: R.status = AIGW_DECLINED;
       }
       R.carry_len = S->end - S->beg;
