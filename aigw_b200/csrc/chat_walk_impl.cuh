@@ -790,7 +790,12 @@ struct Walker {
   // the whole body as a JSON string (ASCII only: other bytes go to the stock path)
   __device__ void err_raw_message() {
     if (d.len == 0) { pl.lit(L_ERR_CLOSE_AFTER_CODE); return; }
-    pl.lit(L_ERR_MESSAGE); pl.lit(L_QUOTE);
+    pl.lit(L_ERR_MESSAGE); err_quoted_body();
+    if (bad()) return;
+    pl.lit(L_ERR_CLOSE);
+  }
+  __device__ void err_quoted_body() {
+    pl.lit(L_QUOTE);
     uint32_t run = 0;
     for (uint32_t i = 0; i <= d.len; i++) {
       const uint32_t c = i < d.len ? d.s[i] : 0x100u;
@@ -808,7 +813,58 @@ struct Walker {
       pl.push(2, sc.n, w); sc.n += (w + 1u) & ~1u;
       if (bad()) return;
     }
-    pl.lit(L_QUOTE); pl.lit(L_ERR_CLOSE);
+    pl.lit(L_QUOTE);
+  }
+  // /v1/messages served by an OpenAI-schema backend: openai.Error -> anthropic.ErrorResponse
+  // {"error":{"message":M,"type":T},"request_id":"","type":"error"} (anthropicToOpenAIV1ChatCompletionTranslator.ResponseError,
+  // internal/translator/anthropic_openai.go:187-253).  cfg as for the other error schemas: model_name_override = ":status",
+  // force_body_mutation = the upstream content-type is not JSON (the raw body is the message, the type follows the status).
+  __device__ bool err_extra_strings(int obj, bool with_param) {   // event_id / param: *string members outside the key table
+    for (int m = obj + 1; d.ty(m) != '}'; m = d.after(m + 3)) {
+      if (d.id(m)) continue;
+      if (str_is(m, "event_id", 8) || (with_param && str_is(m, "param", 5))) { if (!is_null(m + 3) && !is_str(m + 3)) { decline(AIGW_R_E500_DECODE); return false; } }
+    }
+    return true;
+  }
+  // the fixed parts go through the scratch area: the literal table (shared memory in the emit kernels) is full
+  __device__ void aerr_open() { emit_cfg_text("{\"error\":{\"message\":", 20); }
+  __device__ void aerr_type() { emit_cfg_text(",\"type\":", 8); }
+  __device__ void aerr_close() { emit_cfg_text("},\"request_id\":\"\",\"type\":\"error\"}", 33); }
+  __device__ void plan_messages_openai_error(bool tokens_ok) {
+    if (P->force_mutation) {
+      const char* t = "internal_server_error"; uint32_t tl = 21;
+      if (P->override_len == 3) {
+        const char* c = P->override_model;
+        const uint32_t code = (uint32_t)(c[0] - '0') * 100u + (uint32_t)(c[1] - '0') * 10u + (uint32_t)(c[2] - '0');
+        switch (code) {
+          case 400: t = "invalid_request_error"; tl = 21; break; case 401: t = "authentication_error"; tl = 20; break; case 403: t = "permission_error"; tl = 16; break;
+          case 404: t = "not_found_error"; tl = 15; break; case 413: t = "request_too_large"; tl = 17; break; case 429: t = "rate_limit_error"; tl = 16; break;
+          case 503: t = "service_unavailable_error"; tl = 25; break; case 529: t = "overloaded_error"; tl = 16; break; default: break;
+        }
+      }
+      aerr_open(); err_quoted_body();
+      if (bad()) return;
+      aerr_type(); pl.lit(L_QUOTE); emit_cfg_text(t, tl); pl.lit(L_QUOTE); aerr_close();
+      return;
+    }
+    if (!tokens_ok) { decline(AIGW_R_SYNTAX); return; }
+    int msg = -1, type = -1;
+    if (!is_null(0)) {
+      if (!is_obj(0)) { decline(AIGW_R_E500_DECODE); return; }   // "failed to unmarshal OpenAI error body"
+      static const uint8_t k[] = {RK_error, RK_type}; int r[2]; if (!rmembers(0, k, 2, r)) return;
+      if (r[1] >= 0 && !is_str(r[1])) { decline(AIGW_R_E500_DECODE); return; }
+      if (!err_extra_strings(0, false)) return;
+      if (r[0] >= 0) {
+        if (!is_obj(r[0])) { decline(AIGW_R_E500_DECODE); return; }
+        static const uint8_t k1[] = {RK_message, RK_type, RK_code}; int r1[3]; if (!rmembers(r[0], k1, 3, r1)) return;
+        for (int q = 0; q < 3; q++) if (r1[q] >= 0 && !is_str(r1[q])) { decline(AIGW_R_E500_DECODE); return; }
+        if (!err_extra_strings(r[0], true)) return;
+        msg = r1[0]; type = r1[1];
+      }
+    }
+    aerr_open(); if (msg >= 0) emit_str(msg); else pl.lit(L_EMPTY_STR);
+    aerr_type(); if (type >= 0) emit_str(type); else pl.lit(L_EMPTY_STR);
+    aerr_close();
   }
   __device__ void err_tail(int msg) {   // after the type: code, then the message string token (omitted when absent or empty)
     err_code();
@@ -820,6 +876,7 @@ struct Walker {
     const int base = P->schema & 7;
     if (d.len == 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }   // an empty error body is left to the stock path
     for (uint32_t i = 0; i < P->override_len; i++) { const uint32_t c = (uint8_t)P->override_model[i]; if (c < 0x20 || c > 0x7e || c == '"' || c == '\\') { decline(AIGW_R_UNSUPPORTED_FIELD); return; } }
+    if (base == AIGW_SCHEMA_OPENAI) { plan_messages_openai_error(tokens_ok); return; }
     if (base == AIGW_SCHEMA_GCP_VERTEX) {
       bool typed = tokens_ok; int msg = -1, status = -1;
       if (typed && !is_null(0)) {

@@ -16,7 +16,7 @@
 
 namespace oracle {
 
-enum { ERR_AWS_BEDROCK = 1, ERR_GCP_VERTEX = 3, ERR_GCP_ANTHROPIC = 4 };
+enum { ERR_MESSAGES_OPENAI = 0, ERR_AWS_BEDROCK = 1, ERR_GCP_VERTEX = 3, ERR_GCP_ANTHROPIC = 4 };
 
 inline void error_json(std::string& out, const std::string& type, const std::string& code, const std::string& message) {
   out = "{\"type\":\"error\",\"error\":{\"type\":"; oj::enc_str(out, type);
@@ -31,8 +31,44 @@ inline bool str_field(const Value& o, const char* key, std::string& dst, bool& t
 }
 
 // json_content_type: the upstream's content-type contains "application/json" (Bedrock and GCP Anthropic look at it; Vertex does not)
+// /v1/messages served by an OpenAI-schema backend: openai.Error -> anthropic.ErrorResponse
+// (anthropicToOpenAIV1ChatCompletionTranslator.ResponseError, internal/translator/anthropic_openai.go:187-253; ErrorResponse /
+// ErrorResponseMessage field order internal/apischema/anthropic/anthropic.go:1751-1763).  Pinned by the data-plane golden
+// "anthropic-openai - … - OpenAI JSON error translated to Anthropic error" (exact text).
+inline const char* anthropic_error_type_of_status(const std::string& code) {
+  if (code == "400") return "invalid_request_error";
+  if (code == "401") return "authentication_error";
+  if (code == "403") return "permission_error";
+  if (code == "404") return "not_found_error";
+  if (code == "413") return "request_too_large";
+  if (code == "429") return "rate_limit_error";
+  if (code == "500") return "internal_server_error";
+  if (code == "503") return "service_unavailable_error";
+  if (code == "529") return "overloaded_error";
+  return "internal_server_error";
+}
+inline void anthropic_error_json(std::string& out, const std::string& type, const std::string& message) {
+  out = "{\"error\":{\"message\":"; oj::enc_str(out, message); out += ",\"type\":"; oj::enc_str(out, type); out += "},\"request_id\":\"\",\"type\":\"error\"}";
+}
+inline Status messages_openai_error(std::string_view body, const std::string& status_code, bool json_content_type, std::string& out) {
+  if (!json_content_type) { anthropic_error_json(out, anthropic_error_type_of_status(status_code), std::string(body)); return OK; }
+  Value v; { oj::Parser ps(body.data(), body.size()); ps.ws(); if (!ps.value(v)) return INTERNAL; }   // "failed to unmarshal OpenAI error body"
+  bool te = false; std::string type, msg, dummy;
+  if (v.is_obj()) {
+    str_field(v, "event_id", dummy, te); str_field(v, "type", dummy, te);
+    if (const Value* e = v.get("error")) {
+      if (e->is_obj()) { str_field(*e, "type", type, te); str_field(*e, "code", dummy, te); str_field(*e, "message", msg, te); str_field(*e, "param", dummy, te); str_field(*e, "event_id", dummy, te); }
+      else if (!e->is_null()) te = true;
+    }
+  } else if (!v.is_null()) te = true;
+  if (te) return INTERNAL;
+  anthropic_error_json(out, type, msg);
+  return OK;
+}
+
 inline Status response_error(int kind, std::string_view body, const std::string& status_code, const std::string& aws_error_type, bool json_content_type, std::string& out) {
   out.clear();
+  if (kind == ERR_MESSAGES_OPENAI) return messages_openai_error(body, status_code, json_content_type, out);
   if (kind == ERR_GCP_VERTEX) {
     Value v; std::string err; std::string status, msg; bool ok = oj::parse(body, v, err), te = false;
     if (ok) {

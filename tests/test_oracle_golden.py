@@ -732,3 +732,17 @@ def test_messages_aws_anthropic_stream_golden():
     assert s == O.OK and o.decode().count("event: ") == 2 and "tool_use" in o.decode() and "future_block" in o.decode() and st.model() == b"req-model" and u.mask == 0
     st = O.MessagesAwsAnthropicStream(b"m")
     assert st.feed(wrap(b'{"type":"message_start","message":{"content":[{"type":"text","text":"x"}]}}'), False)[0] == O.DECLINED
+
+
+def test_messages_openai_error_golden():
+    """/v1/messages on an OpenAI backend, ResponseError (anthropic_openai.go:187-253): the data-plane golden byte for byte; the raw-body branch's status table"""
+    c = next(c for c in CASES if c["name"].endswith("OpenAI JSON error translated to Anthropic error"))
+    st, out = O.response_error("messages-openai", c["responseBody"].encode(), "400", "", True)
+    assert st == O.OK and out.decode() == c["expResponseBody"]
+    for code, typ in (("400", "invalid_request_error"), ("401", "authentication_error"), ("403", "permission_error"), ("404", "not_found_error"), ("413", "request_too_large"),
+                      ("429", "rate_limit_error"), ("500", "internal_server_error"), ("503", "service_unavailable_error"), ("529", "overloaded_error"), ("502", "internal_server_error")):
+        st, out = O.response_error("messages-openai", b'bad "gateway"', code, "", False)
+        assert st == O.OK and json.loads(out) == {"error": {"message": 'bad "gateway"', "type": typ}, "request_id": "", "type": "error"}
+    assert O.response_error("messages-openai", b'{"error":{"message":5}}', "400", "", True)[0] == O.INTERNAL
+    assert O.response_error("messages-openai", b'{"error":{"param":5}}', "400", "", True)[0] == O.INTERNAL
+    assert O.response_error("messages-openai", b'null', "400", "", True)[1] == b'{"error":{"message":"","type":""},"request_id":"","type":"error"}'

@@ -89,3 +89,51 @@ def test_corpus_vs_oracle(gw, kind, json_ct):
         assert a == got[:300]
     finally:
         gw.chat_set_small_batch(-1)
+
+
+# ---------------------------------------------------------------- /v1/messages served by an OpenAI backend: openai.Error -> anthropic.ErrorResponse
+def test_messages_openai_error_golden_and_corpus(gw):
+    """anthropicToOpenAIV1ChatCompletionTranslator.ResponseError (internal/translator/anthropic_openai.go:187-253): the data-plane golden
+    "OpenAI JSON error translated to Anthropic error" byte for byte; JSON and raw-body branches against the oracle through both launch paths."""
+    c = next(c for c in CASES if c["name"].endswith("OpenAI JSON error translated to Anthropic error"))
+    g, = run(gw, "messages-openai", [c["responseBody"].encode()], status="400")
+    assert g["status"] == 0 and g["body"].decode() == c["expResponseBody"]
+    r = random.Random(17)
+    bodies = []
+    for i in range(1500):
+        msg = r.choice(["Model not found", "Rate limit reached for requests", 'quo"ted \\ text', "line\nbreak\ttab", "", "ünïcode ✓", "x" * 300])
+        e = {"type": r.choice(["invalid_request_error", "rate_limit_error", ""]), "message": msg, "code": r.choice(["model_not_found", None]), "param": r.choice([None, "model"])}
+        d = {"error": e}
+        k = r.random()
+        if k < 0.05: e["message"] = 5
+        elif k < 0.09: e["param"] = 7
+        elif k < 0.12: d["event_id"] = r.choice(["ev_1", 3])
+        elif k < 0.15: d["error"] = r.choice([None, "oops", []])
+        elif k < 0.18: d = r.choice([None, [1], "str", 5])
+        elif k < 0.21: e["event_id"] = r.choice([None, "e", True]); del e["code"]
+        elif k < 0.24: e["code"] = 404
+        elif k < 0.27: d["type"] = r.choice(["error", 1])
+        b = json.dumps(d, separators=r.choice([(",", ":"), (", ", ": ")]), ensure_ascii=r.random() < 0.3).encode()
+        if r.random() < 0.04: b = b[: r.randint(1, max(1, len(b) - 1))]
+        bodies.append(b)
+    raw = [b"upstream connect error or disconnect/reset before headers", b"<html>502 Bad Gateway</html>", b'plain "quoted" \\ text\n', b"tab\there", b"{not json"]
+    for small in (0, 1 << 20):
+        gw.chat_set_small_batch(small)
+        try:
+            got = run(gw, "messages-openai", bodies, status="404")
+            n_ok = n_err = 0
+            for b, g in zip(bodies, got):
+                st, o = O.response_error("messages-openai", b, "404", "", True)
+                if g["status"] == 4: continue
+                assert g["status"] == st, (b, g["status"], g["reason"], st)
+                if st == 0:
+                    assert g["body"] == o, (b, g["body"], o); n_ok += 1
+                else:
+                    n_err += 1
+            assert n_ok > 900 and n_err > 100, (n_ok, n_err)
+            for status in ("400", "401", "403", "404", "413", "429", "500", "503", "529", "418", "50"):
+                for b, g in zip(raw, run(gw, "messages-openai", raw, status=status, json_ct=False)):
+                    st, o = O.response_error("messages-openai", b, status, "", False)
+                    assert g["status"] == st == 0 and g["body"] == o, (status, b, g["body"], o)
+        finally:
+            gw.chat_set_small_batch(-1)
