@@ -830,23 +830,37 @@ struct Walker {
   __device__ void aerr_open() { emit_cfg_text("{\"error\":{\"message\":", 20); }
   __device__ void aerr_type() { emit_cfg_text(",\"type\":", 8); }
   __device__ void aerr_close() { emit_cfg_text("},\"request_id\":\"\",\"type\":\"error\"}", 33); }
-  __device__ void plan_messages_openai_error(bool tokens_ok) {
-    if (P->force_mutation) {
-      const char* t = "internal_server_error"; uint32_t tl = 21;
-      if (P->override_len == 3) {
-        const char* c = P->override_model;
-        const uint32_t code = (uint32_t)(c[0] - '0') * 100u + (uint32_t)(c[1] - '0') * 10u + (uint32_t)(c[2] - '0');
-        switch (code) {
-          case 400: t = "invalid_request_error"; tl = 21; break; case 401: t = "authentication_error"; tl = 20; break; case 403: t = "permission_error"; tl = 16; break;
-          case 404: t = "not_found_error"; tl = 15; break; case 413: t = "request_too_large"; tl = 17; break; case 429: t = "rate_limit_error"; tl = 16; break;
-          case 503: t = "service_unavailable_error"; tl = 25; break; case 529: t = "overloaded_error"; tl = 16; break; default: break;
-        }
+  // the Anthropic error type of the ":status" text; `bedrock`: httpStatusToAnthropicErrorType (anthropic_awsbedrock.go:775-794) has no 413 / 529
+  __device__ void aerr_status_type(bool bedrock) {
+    const char* t = "internal_server_error"; uint32_t tl = 21;
+    if (P->override_len == 3) {
+      const char* c = P->override_model;
+      const uint32_t code = (uint32_t)(c[0] - '0') * 100u + (uint32_t)(c[1] - '0') * 10u + (uint32_t)(c[2] - '0');
+      switch (code) {
+        case 400: t = "invalid_request_error"; tl = 21; break; case 401: t = "authentication_error"; tl = 20; break; case 403: t = "permission_error"; tl = 16; break;
+        case 404: t = "not_found_error"; tl = 15; break; case 429: t = "rate_limit_error"; tl = 16; break; case 503: t = "service_unavailable_error"; tl = 25; break;
+        case 413: if (!bedrock) { t = "request_too_large"; tl = 17; } break; case 529: if (!bedrock) { t = "overloaded_error"; tl = 16; } break; default: break;
       }
-      aerr_open(); err_quoted_body();
-      if (bad()) return;
-      aerr_type(); pl.lit(L_QUOTE); emit_cfg_text(t, tl); pl.lit(L_QUOTE); aerr_close();
-      return;
     }
+    pl.lit(L_QUOTE); emit_cfg_text(t, tl); pl.lit(L_QUOTE);
+  }
+  // /v1/messages served by AWS Bedrock Converse: awsbedrock.BedrockException (or the raw body) -> anthropic.ErrorResponse whose type
+  // follows the status (anthropicToAWSBedrockTranslator.ResponseError, internal/translator/anthropic_awsbedrock.go:738-794)
+  __device__ void plan_messages_bedrock_error(bool tokens_ok) {
+    if (P->force_mutation) { aerr_open(); err_quoted_body(); if (bad()) return; aerr_type(); aerr_status_type(true); aerr_close(); return; }
+    if (!tokens_ok) { decline(AIGW_R_SYNTAX); return; }
+    int msg = -1;
+    if (!is_null(0)) {
+      if (!is_obj(0)) { decline(AIGW_R_E500_DECODE); return; }   // "failed to unmarshal error body"
+      static const uint8_t k[] = {RK_message, RK_code, RK_type}; int r[3]; if (!rmembers(0, k, 3, r)) return;
+      for (int q = 0; q < 3; q++) if (r[q] >= 0 && !is_str(r[q])) { decline(AIGW_R_E500_DECODE); return; }
+      msg = r[0];
+    }
+    aerr_open(); if (msg >= 0) emit_str(msg); else pl.lit(L_EMPTY_STR);
+    aerr_type(); aerr_status_type(true); aerr_close();
+  }
+  __device__ void plan_messages_openai_error(bool tokens_ok) {
+    if (P->force_mutation) { aerr_open(); err_quoted_body(); if (bad()) return; aerr_type(); aerr_status_type(false); aerr_close(); return; }
     if (!tokens_ok) { decline(AIGW_R_SYNTAX); return; }
     int msg = -1, type = -1;
     if (!is_null(0)) {
@@ -877,6 +891,7 @@ struct Walker {
     if (d.len == 0) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }   // an empty error body is left to the stock path
     for (uint32_t i = 0; i < P->override_len; i++) { const uint32_t c = (uint8_t)P->override_model[i]; if (c < 0x20 || c > 0x7e || c == '"' || c == '\\') { decline(AIGW_R_UNSUPPORTED_FIELD); return; } }
     if (base == AIGW_SCHEMA_OPENAI) { plan_messages_openai_error(tokens_ok); return; }
+    if (base == 6) { plan_messages_bedrock_error(tokens_ok); return; }   // AIGW_SCHEMA_RESP_ERROR_MESSAGES_AWS_BEDROCK
     if (base == AIGW_SCHEMA_GCP_VERTEX) {
       bool typed = tokens_ok; int msg = -1, status = -1;
       if (typed && !is_null(0)) {

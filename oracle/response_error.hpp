@@ -16,7 +16,7 @@
 
 namespace oracle {
 
-enum { ERR_MESSAGES_OPENAI = 0, ERR_AWS_BEDROCK = 1, ERR_GCP_VERTEX = 3, ERR_GCP_ANTHROPIC = 4 };
+enum { ERR_MESSAGES_AWS_BEDROCK = 6, ERR_MESSAGES_OPENAI = 0, ERR_AWS_BEDROCK = 1, ERR_GCP_VERTEX = 3, ERR_GCP_ANTHROPIC = 4 };
 
 inline void error_json(std::string& out, const std::string& type, const std::string& code, const std::string& message) {
   out = "{\"type\":\"error\",\"error\":{\"type\":"; oj::enc_str(out, type);
@@ -66,9 +66,26 @@ inline Status messages_openai_error(std::string_view body, const std::string& st
   return OK;
 }
 
+// /v1/messages served by AWS Bedrock Converse (anthropicToAWSBedrockTranslator.ResponseError, internal/translator/anthropic_awsbedrock.go:738-794):
+// the message is BedrockException.message (JSON content type) or the raw body; the type follows the status through a table without
+// 413 / 529.  Content pinned by anthropic_awsbedrock_test.go:563-638 (struct compares); the byte layout is the golden-pinned ErrorResponse's.
+inline Status messages_bedrock_error(std::string_view body, const std::string& status_code, bool json_content_type, std::string& out) {
+  std::string type = anthropic_error_type_of_status(status_code);
+  if (status_code == "413" || status_code == "529") type = "internal_server_error";
+  if (!json_content_type) { anthropic_error_json(out, type, std::string(body)); return OK; }
+  Value v; { oj::Parser ps(body.data(), body.size()); ps.ws(); if (!ps.value(v)) return INTERNAL; }   // "failed to unmarshal error body"
+  bool te = false; std::string msg, dummy;
+  if (v.is_obj()) { str_field(v, "code", dummy, te); str_field(v, "type", dummy, te); str_field(v, "message", msg, te); }
+  else if (!v.is_null()) te = true;
+  if (te) return INTERNAL;
+  anthropic_error_json(out, type, msg);
+  return OK;
+}
+
 inline Status response_error(int kind, std::string_view body, const std::string& status_code, const std::string& aws_error_type, bool json_content_type, std::string& out) {
   out.clear();
   if (kind == ERR_MESSAGES_OPENAI) return messages_openai_error(body, status_code, json_content_type, out);
+  if (kind == ERR_MESSAGES_AWS_BEDROCK) return messages_bedrock_error(body, status_code, json_content_type, out);
   if (kind == ERR_GCP_VERTEX) {
     Value v; std::string err; std::string status, msg; bool ok = oj::parse(body, v, err), te = false;
     if (ok) {

@@ -746,3 +746,15 @@ def test_messages_openai_error_golden():
     assert O.response_error("messages-openai", b'{"error":{"message":5}}', "400", "", True)[0] == O.INTERNAL
     assert O.response_error("messages-openai", b'{"error":{"param":5}}', "400", "", True)[0] == O.INTERNAL
     assert O.response_error("messages-openai", b'null', "400", "", True)[1] == b'{"error":{"message":"","type":""},"request_id":"","type":"error"}'
+
+
+def test_messages_bedrock_error_reference_cases():
+    """/v1/messages on AWS Bedrock, ResponseError (anthropic_awsbedrock.go:738-794): the reference test's cases (anthropic_awsbedrock_test.go:563-638)"""
+    st, out = O.response_error("messages-aws-bedrock", b'{"message":"Model not found"}', "404", "", True)
+    assert st == O.OK and json.loads(out) == {"type": "error", "error": {"type": "not_found_error", "message": "Model not found"}, "request_id": ""}
+    st, out = O.response_error("messages-aws-bedrock", b"Service Unavailable", "503", "", False)
+    assert st == O.OK and json.loads(out)["error"] == {"type": "service_unavailable_error", "message": "Service Unavailable"}
+    for status, typ in (("400", "invalid_request_error"), ("401", "authentication_error"), ("403", "permission_error"), ("404", "not_found_error"), ("429", "rate_limit_error"),
+                        ("500", "internal_server_error"), ("503", "service_unavailable_error"), ("502", "internal_server_error")):
+        assert json.loads(O.response_error("messages-aws-bedrock", b"error", status, "", False)[1])["error"]["type"] == typ
+    assert O.response_error("messages-aws-bedrock", b'{"message":5}', "400", "", True)[0] == O.INTERNAL

@@ -137,3 +137,34 @@ def test_messages_openai_error_golden_and_corpus(gw):
                     assert g["status"] == st == 0 and g["body"] == o, (status, b, g["body"], o)
         finally:
             gw.chat_set_small_batch(-1)
+
+
+def test_messages_bedrock_error(gw):
+    """anthropicToAWSBedrockTranslator.ResponseError (internal/translator/anthropic_awsbedrock.go:738-794): the reference test's cases
+    (anthropic_awsbedrock_test.go:563-638: JSON body at 404, text body at 503, the status table) and a corpus against the oracle."""
+    g, = run(gw, "messages-aws-bedrock", [b'{"message":"Model not found"}'], status="404")
+    assert g["status"] == 0 and json.loads(g["body"]) == {"type": "error", "error": {"type": "not_found_error", "message": "Model not found"}, "request_id": ""}
+    g, = run(gw, "messages-aws-bedrock", [b"Service Unavailable"], status="503", json_ct=False)
+    assert g["status"] == 0 and json.loads(g["body"])["error"] == {"type": "service_unavailable_error", "message": "Service Unavailable"}
+    for status, typ in (("400", "invalid_request_error"), ("401", "authentication_error"), ("403", "permission_error"), ("404", "not_found_error"), ("429", "rate_limit_error"),
+                        ("500", "internal_server_error"), ("503", "service_unavailable_error"), ("502", "internal_server_error"), ("413", "internal_server_error"), ("529", "internal_server_error")):
+        g, = run(gw, "messages-aws-bedrock", [b"error"], status=status, json_ct=False)
+        assert g["status"] == 0 and json.loads(g["body"])["error"]["type"] == typ, status
+    r = random.Random(23)
+    bodies = [err_body(r, "aws-bedrock") for _ in range(1200)] + [b"null", b"[]", b"{}", b'{"message":null}', b"{oops"]
+    for small in (0, 1 << 20):
+        gw.chat_set_small_batch(small)
+        try:
+            for status in ("429", "404"):
+                n_ok = n_err = 0
+                for b, g in zip(bodies, run(gw, "messages-aws-bedrock", bodies, status=status)):
+                    st, o = O.response_error("messages-aws-bedrock", b, status, "", True)
+                    if g["status"] == 4: continue
+                    assert g["status"] == st, (b, g["status"], g["reason"], st)
+                    if st == 0:
+                        assert g["body"] == o, (b, g["body"], o); n_ok += 1
+                    else:
+                        n_err += 1
+                assert n_ok > 700 and n_err > 30, (n_ok, n_err)
+        finally:
+            gw.chat_set_small_batch(-1)
