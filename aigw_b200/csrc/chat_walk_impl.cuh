@@ -892,6 +892,11 @@ struct Walker {
     for (uint32_t i = 0; i < P->override_len; i++) { const uint32_t c = (uint8_t)P->override_model[i]; if (c < 0x20 || c > 0x7e || c == '"' || c == '\\') { decline(AIGW_R_UNSUPPORTED_FIELD); return; } }
     if (base == AIGW_SCHEMA_OPENAI) { plan_messages_openai_error(tokens_ok); return; }
     if (base == 6) { plan_messages_bedrock_error(tokens_ok); return; }   // AIGW_SCHEMA_RESP_ERROR_MESSAGES_AWS_BEDROCK
+    if (base == AIGW_SCHEMA_AZURE_OPENAI) {   // AIGW_SCHEMA_RESP_ERROR_OPENAI: convertErrorOpenAIToOpenAIError (openai_openai.go:94-120)
+      if (!P->force_mutation) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }   // a JSON error body is forwarded untouched: nothing to compute
+      pl.lit(L_ERR_OPEN); pl.lit(L_QUOTE); emit_cfg_text("OpenAIBackendError", 18); pl.lit(L_QUOTE); err_code(); err_raw_message();
+      return;
+    }
     if (base == AIGW_SCHEMA_GCP_VERTEX) {
       bool typed = tokens_ok; int msg = -1, status = -1;
       if (typed && !is_null(0)) {

@@ -28,7 +28,8 @@ using namespace aigw;
 
 struct aigw_cost_program { aigw::CelProgramHost h; };
 
-#define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(_e); return (int)_e; } } while (0)
+// a failed call is reported once: its code is also taken off the thread's "last error", so that the launch check of a later call does not find it
+#define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(_e); (void)cudaGetLastError(); return (int)_e; } } while (0)
 
 static constexpr int kSlots = 3;
 static bool plain_json_text(const char* s) { for (; *s; s++) { unsigned char c = (unsigned char)*s; if (c < 0x20 || c > 0x7e || c == '"' || c == '\\') return false; } return true; }
@@ -172,10 +173,12 @@ int aigw_init(int device, aigw_ctx** out) {
   aigw_ctx* ctx = new aigw_ctx();
   ctx->device = device;
   cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) { fprintf(stderr, "aigw_init: cudaSetDevice(%d): %s\n", device, cudaGetErrorString(e)); delete ctx; return (int)e; }
+  // a failed runtime call leaves its code as the thread's "last error": clear it, or the next launch check of ANOTHER context on this
+  // thread (cudaGetLastError after a kernel launch) reports it as its own (found by tests/test_multi_context_gpu.py)
+  if (e != cudaSuccess) { fprintf(stderr, "aigw_init: cudaSetDevice(%d): %s\n", device, cudaGetErrorString(e)); (void)cudaGetLastError(); delete ctx; return (int)e; }
   cudaDeviceProp prop;
   e = cudaGetDeviceProperties(&prop, device);
-  if (e != cudaSuccess) { delete ctx; return (int)e; }
+  if (e != cudaSuccess) { (void)cudaGetLastError(); delete ctx; return (int)e; }
   ctx->sm_count = prop.multiProcessorCount;
   if (prop.major < 10) { fprintf(stderr, "aigw_init: device %d is sm_%d%d; this library is built for sm_100a only\n", device, prop.major, prop.minor); delete ctx; return (int)cudaErrorNoKernelImageForDevice; }
   // every allocation is checked on its own: a half-built context is destroyed, never returned

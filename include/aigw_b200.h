@@ -65,7 +65,7 @@ enum aigw_schema { AIGW_SCHEMA_OPENAI = 0, AIGW_SCHEMA_AWS_BEDROCK = 1, AIGW_SCH
                     * force_body_mutation = 1 when the upstream content-type is NOT application/json (the raw body becomes the message).
                     * Record = the JSON only (path_len 0).  Vertex bodies with `details` are DECLINED. */
                    AIGW_SCHEMA_RESP_ERROR = 24, AIGW_SCHEMA_RESP_ERROR_MESSAGES_OPENAI = 24 /* /v1/messages on an OpenAI backend: openai.Error -> anthropic.ErrorResponse, anthropic_openai.go:187-253 */,
-                   AIGW_SCHEMA_RESP_ERROR_AWS_BEDROCK = 25, AIGW_SCHEMA_RESP_ERROR_MESSAGES_AWS_BEDROCK = 30 /* /v1/messages on AWS Bedrock Converse: BedrockException -> anthropic.ErrorResponse, anthropic_awsbedrock.go:738-794 */, AIGW_SCHEMA_RESP_ERROR_GCP_VERTEX = 27, AIGW_SCHEMA_RESP_ERROR_GCP_ANTHROPIC = 28,
+                   AIGW_SCHEMA_RESP_ERROR_AWS_BEDROCK = 25, AIGW_SCHEMA_RESP_ERROR_OPENAI = 26 /* OpenAI / Azure passthrough translators (chat, embeddings, completions): a non-JSON upstream error becomes an OpenAIBackendError, openai_openai.go:94-120; JSON bodies are forwarded untouched (do not call) */, AIGW_SCHEMA_RESP_ERROR_MESSAGES_AWS_BEDROCK = 30 /* /v1/messages on AWS Bedrock Converse: BedrockException -> anthropic.ErrorResponse, anthropic_awsbedrock.go:738-794 */, AIGW_SCHEMA_RESP_ERROR_GCP_VERTEX = 27, AIGW_SCHEMA_RESP_ERROR_GCP_ANTHROPIC = 28,
                    /* /v1/embeddings requests (EmbeddingsEndpointSpec.ParseBody, internal/endpointspec/endpointspec.go:231-240, then the
                     * OpenAI / Azure passthrough translators internal/translator/openai_embeddings.go:38-59,
                     * openai_azureopenai_embeddings.go:36-61 or the Vertex predict translator openai_gcpvertexai_embeddings.go:46-180):

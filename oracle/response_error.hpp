@@ -16,7 +16,7 @@
 
 namespace oracle {
 
-enum { ERR_MESSAGES_AWS_BEDROCK = 6, ERR_MESSAGES_OPENAI = 0, ERR_AWS_BEDROCK = 1, ERR_GCP_VERTEX = 3, ERR_GCP_ANTHROPIC = 4 };
+enum { ERR_OPENAI = 2, ERR_MESSAGES_AWS_BEDROCK = 6, ERR_MESSAGES_OPENAI = 0, ERR_AWS_BEDROCK = 1, ERR_GCP_VERTEX = 3, ERR_GCP_ANTHROPIC = 4 };
 
 inline void error_json(std::string& out, const std::string& type, const std::string& code, const std::string& message) {
   out = "{\"type\":\"error\",\"error\":{\"type\":"; oj::enc_str(out, type);
@@ -86,6 +86,11 @@ inline Status response_error(int kind, std::string_view body, const std::string&
   out.clear();
   if (kind == ERR_MESSAGES_OPENAI) return messages_openai_error(body, status_code, json_content_type, out);
   if (kind == ERR_MESSAGES_AWS_BEDROCK) return messages_bedrock_error(body, status_code, json_content_type, out);
+  if (kind == ERR_OPENAI) {   // convertErrorOpenAIToOpenAIError (openai_openai.go:94-120): only a non-JSON body is rewritten
+    if (json_content_type) return DECLINED;   // forwarded untouched: the shim does not call
+    error_json(out, "OpenAIBackendError", status_code, std::string(body));
+    return OK;
+  }
   if (kind == ERR_GCP_VERTEX) {
     Value v; std::string err; std::string status, msg; bool ok = oj::parse(body, v, err), te = false;
     if (ok) {

@@ -381,7 +381,7 @@ def anthropic_response(body: bytes, request_model: bytes, created: int):
 
 def response_error(kind, body: bytes, status_code: str, aws_error_type: str = "", json_content_type=True):
     """Translator.ResponseError (chat completions) for "aws-bedrock" | "gcp-vertexai" | "gcp-anthropicai" → (status, OpenAI error JSON bytes)."""
-    k = {"messages-aws-bedrock": 6, "messages-openai": 0, "aws-bedrock": 1, "gcp-vertexai": 3, "gcp-anthropicai": 4}[kind]
+    k = {"openai": 2, "messages-aws-bedrock": 6, "messages-openai": 0, "aws-bedrock": 1, "gcp-vertexai": 3, "gcp-anthropicai": 4}[kind]
     L = lib(); L.oracle_response_error.argtypes = [C.c_int, C.c_char_p, C.c_uint64, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     vp = C.c_void_p(); n = C.c_uint64(0)
     st = L.oracle_response_error(k, body, len(body), status_code.encode(), aws_error_type.encode(), int(json_content_type), C.byref(vp), C.byref(n))

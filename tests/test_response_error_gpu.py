@@ -168,3 +168,23 @@ def test_messages_bedrock_error(gw):
                 assert n_ok > 700 and n_err > 30, (n_ok, n_err)
         finally:
             gw.chat_set_small_batch(-1)
+
+
+def test_openai_passthrough_error(gw):
+    """convertErrorOpenAIToOpenAIError (internal/translator/openai_openai.go:94-120; the OpenAI / Azure chat, embeddings and completions
+    translators): a non-JSON upstream error becomes an OpenAIBackendError — the data-plane golden "non json upstream error mapped to OpenAI"
+    (JSON-equal, as the reference compares it) and raw bodies against the oracle; a JSON body is forwarded untouched (nothing to compute)."""
+    c = next(c for c in CASES if c["name"].endswith("non json upstream error mapped to OpenAI"))
+    g, = run(gw, "openai", [c["responseBody"].encode()], status="503", json_ct=False)
+    assert g["status"] == 0 and json.loads(g["body"]) == json.loads(c["expResponseBody"])
+    raw = [b"backend timeout", b"upstream connect error or disconnect/reset before headers", b"<html>502 Bad Gateway</html>", b'plain "quoted" \\ text\n', b"tab\there", b"{not json", b'{"looks":"like json"}']
+    for small in (0, 1 << 20):
+        gw.chat_set_small_batch(small)
+        try:
+            for status in ("400", "503", "504"):
+                for b, g in zip(raw, run(gw, "openai", raw, status=status, json_ct=False)):
+                    st, o = O.response_error("openai", b, status, "", False)
+                    assert g["status"] == st == 0 and g["body"] == o, (status, b, g["body"], o)
+            assert all(g["status"] == 4 for g in run(gw, "openai", raw, status="400", json_ct=True))
+        finally:
+            gw.chat_set_small_batch(-1)
