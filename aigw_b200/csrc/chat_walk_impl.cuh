@@ -457,7 +457,13 @@ struct Walker {
     else if (kind == 1) ok = is_bool(v);
     else {
       ok = is_num(v);
-      if (ok && kind == 2) { const uint32_t e = d.scalar_end(v), o = d.tok(v); ok = canon_number(d.s + o, e - o, true) != 0; if (!ok) { decline(AIGW_R_NUMBER); return false; } }
+      if (ok && kind == 2) {
+        const uint32_t e = d.scalar_end(v), o = d.tok(v); ok = canon_number(d.s + o, e - o, true) != 0;
+        if (!ok) {   // a fraction or an exponent in an integer field is the decoder's type error ("cannot unmarshal number 1.5 into … int64"): ParseBody's 400
+          bool frac = false; for (uint32_t i = o; i < e; i++) { const uint32_t c = d.s[i]; if (c == '.' || c == 'e' || c == 'E') frac = true; }
+          decline(frac ? AIGW_R_E400_TYPE : AIGW_R_NUMBER); return false;
+        }
+      }
     }
     if (!ok) decline(AIGW_R_E400_TYPE);
     return ok;

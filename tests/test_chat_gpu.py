@@ -102,6 +102,7 @@ def test_error_statuses(ctx):
         (b'{"model":5,"messages":[]}', 1), (b'{"model":"m","messages":{}}', 1), (b'{"model":"m","temperature":"hot"}', 1),
         (b'{"model":"m","messages":[{"role":"system","content":null}]}', 1),
         (b'{"model":"m","thinking":{"type":"bogus"}}', 1), (b'{"model":"m","tool_choice":7}', 1),
+        (b'{"model":"m","messages":[],"max_tokens":1.5}', 1), (b'{"model":"m","messages":[],"max_tokens":1.0}', 1), (b'{"model":"m","messages":[],"n":1e2}', 1), (b'{"model":"m","messages":[],"seed":0.5E1}', 1),
         (b'{"model":"m","messages":[{"role":"user"}]}', 2), (b'{"model":"m","messages":[{"role":"system"}]}', 2), (b'{"model":"m","messages":[{"role":"tool","tool_call_id":"x"}]}', 2),
         (b'{"model":"m","messages":[{"role":"user"},{"role":"user","content":7}]}', 1),             # a later ParseBody error outranks the translator error
         (b'{"model":"m","messages":[{"role":"assistant","tool_calls":[{"id":"a","function":{"name":"f","arguments":"not json"}}]}]}', 3),
