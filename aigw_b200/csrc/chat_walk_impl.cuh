@@ -973,9 +973,25 @@ struct Walker {
         if (!is_arr(r[6])) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
         for (int e = r[6] + 1; d.ty(e) != ']'; e = d.after(e)) {
           if (!is_obj(e)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
-          int nm = 0, ty = -1, tx = -1;
-          for (int m = e + 1; d.ty(m) != '}'; m = d.after(m + 3)) { nm++; if (d.id(m) == RK_type) ty = m + 3; else if (d.id(m) == RK_text) tx = m + 3; }
-          if (nm != 2 || ty < 0 || tx < 0 || !is_str(ty) || !str_is(ty, "text", 4) || !is_str(tx)) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+          // MessagesContentBlock.UnmarshalJSON (anthropic.go:1505-1557) over the block types text / tool_use / server_tool_use / thinking /
+          // redacted_thinking, members of the declared JSON types (null allowed), no repeated member; anything else: stock path
+          static const uint8_t kb[] = {RK_type, RK_text, RK_id, RK_name, RK_input, RK_thinking, RK_signature, RK_data};
+          int q[8]; uint32_t seen = 0; bool odd = false; int cit = -1;
+          for (int k = 0; k < 8; k++) q[k] = -2;   // -2 absent, -1 null, else the value token
+          for (int m = e + 1; d.ty(m) != '}'; m = d.after(m + 3)) {
+            const uint32_t id = d.id(m);
+            if (!id) { if (str_is(m, "citations", 9)) { if (cit != -1) odd = true; cit = m + 3; } continue; }
+            for (int k = 0; k < 8; k++) if (kb[k] == id) { if (seen & (1u << k)) odd = true; seen |= 1u << k; q[k] = is_null(m + 3) ? -1 : m + 3; }
+          }
+          auto son = [&](int k) { return q[k] < 0 || is_str(q[k]); };   // string, null or absent
+          if (odd || q[0] < 0 || !is_str(q[0]) || d.str_has_backslash(q[0])) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
+          bool ok;
+          if (str_is(q[0], "text", 4)) ok = son(1) && (cit < 0 || is_null(cit));
+          else if (str_is(q[0], "tool_use", 8) || str_is(q[0], "server_tool_use", 15)) ok = son(2) && son(3) && (q[4] < 0 || is_obj(q[4]));
+          else if (str_is(q[0], "thinking", 8)) ok = son(5) && son(6);
+          else if (str_is(q[0], "redacted_thinking", 17)) ok = son(7);
+          else ok = false;
+          if (!ok) { decline(AIGW_R_UNSUPPORTED_FIELD); return; }
         }
       }
       if (r[7] >= 0) {

@@ -153,13 +153,20 @@ inline Status native_anthropic_response(std::string_view body, const std::string
     else if (k == "model") { if (!native::str_or_null(v)) return DECLINED; if (v.is_str()) m = v.s; }
     else if (k == "type") { if (!(v.is_str() && v.s == "message")) return DECLINED; }
     else if (k == "role") { if (!(v.is_str() && v.s == "assistant")) return DECLINED; }
-    else if (k == "content") {   // text blocks only: the other block types' decode rules are not restated
-      if (v.is_null()) continue;
+    else if (k == "content") {   // MessagesContentBlock.UnmarshalJSON (anthropic.go:1505-1557) over the block types text / tool_use /
+      if (v.is_null()) continue;  // server_tool_use / thinking / redacted_thinking with members of the declared JSON types; the rest is DECLINED
       if (!v.is_arr()) return DECLINED;
       for (auto& b : v.arr) {
         if (!b.is_obj()) return DECLINED;
-        const Value* t = b.get_first("type"); const Value* x = b.get_first("text");
-        if (!t || !t->is_str() || t->s != "text" || !x || !x->is_str() || b.obj.size() != 2) return DECLINED;
+        for (const char* kk : {"type", "text", "citations", "id", "name", "input", "thinking", "signature", "data"}) { int c = 0; for (auto& kv2 : b.obj) if (kv2.first == kk) c++; if (c > 1) return DECLINED; }
+        const Value* t = b.get_first("type");
+        if (!t || !t->is_str()) return DECLINED;
+        auto son = [&](const char* kk) { const Value* x = b.get_first(kk); return !x || x->is_null() || x->is_str(); };
+        if (t->s == "text") { const Value* c = b.get_first("citations"); if (!son("text") || (c && !c->is_null())) return DECLINED; }
+        else if (t->s == "tool_use" || t->s == "server_tool_use") { const Value* in = b.get_first("input"); if (!son("id") || !son("name") || (in && !in->is_null() && !in->is_obj())) return DECLINED; }
+        else if (t->s == "thinking") { if (!son("thinking") || !son("signature")) return DECLINED; }
+        else if (t->s == "redacted_thinking") { if (!son("data")) return DECLINED; }
+        else return DECLINED;
       }
     }
     else if (k == "usage") { if (!v.is_null()) us = &v; }

@@ -44,6 +44,13 @@ def raw7(u):
     return (u.input, u.output, u.total, u.cached, u.cache_creation, u.reasoning, u.mask)
 
 
+# content blocks beyond text: the block types MessagesContentBlock.UnmarshalJSON decodes (anthropic.go:1505-1557) and shapes outside the subset
+BLOCKS = [{"type": "tool_use", "id": "toolu_1", "name": "get_weather", "input": {"location": "Paris", "n": [1, {"a": None}]}}, {"type": "tool_use", "id": "t", "name": "f", "input": {}},
+          {"type": "thinking", "thinking": "let me think", "signature": "c2ln"}, {"type": "redacted_thinking", "data": "abc"}, {"type": "server_tool_use", "id": "s", "name": "web_search", "input": {"q": "x"}},
+          {"type": "text", "text": "cited", "citations": None}, {"type": "text", "text": "cited", "citations": [{"type": "char_location"}]}, {"type": "tool_use", "id": 7, "name": "f", "input": {}},
+          {"type": "tool_use", "id": "t", "name": "f", "input": [1]}, {"type": "web_search_tool_result", "tool_use_id": "s", "content": []}, {"type": "future_block"}, {"text": "no type"}, {"type": "thinking", "thinking": 5}]
+
+
 def resp_body(r):
     usage = {"input_tokens": r.randint(0, 9000), "output_tokens": r.randint(0, 4000)}
     if r.random() < 0.6:
@@ -51,11 +58,11 @@ def resp_body(r):
     if r.random() < 0.5:
         usage["service_tier"] = "standard"; usage["cache_creation"] = {"ephemeral_5m_input_tokens": 0, "ephemeral_1h_input_tokens": 0}
     d = {"model": r.choice(["claude-sonnet-4-5-20250929", "claude-3-haiku", ""]), "id": "msg_%d" % r.randint(0, 99999), "type": "message", "role": "assistant",
-         "content": [{"type": "text", "text": r.choice(["Hi! \U0001F44B", "line\nbreak", 'q"uote', "plain text " * 5])} for _ in range(r.randint(0, 3))],
+         "content": [r.choice([{"type": "text", "text": r.choice(["Hi! \U0001F44B", "line\nbreak", 'q"uote', "plain text " * 5])}] * 6 + BLOCKS) for _ in range(r.randint(0, 3))],
          "stop_reason": r.choice(["end_turn", "max_tokens", None]), "stop_sequence": None, "usage": usage}
     odd = r.random()
     if odd < 0.05:
-        d["content"].append({"type": "tool_use", "id": "t1", "name": "f", "input": {}})   # other block types: not decoded here
+        d["content"].append({"type": "tool_use", "id": "t1", "name": "f", "input": {}})
     elif odd < 0.08:
         usage["output_tokens"] = 1.5
     elif odd < 0.11:
@@ -92,7 +99,16 @@ def test_parity(gw):
             assert m == om, (b[:200], m, om)
             ok += 1
     print("ok", ok, "declined", decl)
-    assert ok > 1000
+    assert ok > 600
+
+
+def test_tool_use_and_thinking_blocks_are_accepted(gw):
+    """agentic traffic: a response whose content carries tool_use / thinking blocks is decoded (usage + model), not declined"""
+    b = json.dumps({"id": "msg_1", "type": "message", "role": "assistant", "model": "claude-sonnet-4-5", "stop_reason": "tool_use", "stop_sequence": None,
+                    "content": [BLOCKS[2], {"type": "text", "text": "I will look it up."}, BLOCKS[0], BLOCKS[3], BLOCKS[4]], "usage": {"input_tokens": 12, "output_tokens": 34, "cache_read_input_tokens": 5}}).encode()
+    (st, u, m), = run(gw, [b])
+    ost, ou, om = O.native_anthropic_response(b, b"")
+    assert st == ost == 0 and u == raw7(ou) == (17, 34, 51, 5, 0, 0, 31) and m == om == b"claude-sonnet-4-5"
 
 
 def test_reference_vector(gw):
