@@ -13,6 +13,7 @@
 #error "include from chat_walk_g*.cu with AIGW_WALK_GROUP defined"
 #endif
 #include "chat_stage.cuh"
+#include "shortest_f64.cuh"
 
 #include <cstdlib>
 
@@ -218,7 +219,7 @@ __device__ uint32_t canon_number(const uint8_t* p, uint32_t n, bool integer_only
     if (z > 5) return 0;  // < 1e-6 switches strconv to exponent form
     sig = frac_digits - z;
   } else sig = int_digits + frac_digits;
-  if (sig > 15) return 0;
+  if (sig > 15) return (sig <= 17u && shortest_f64_decimal(p, fe)) ? fe : 0;   // 16 / 17 digits: only when the text is already the float64's shortest form
   return fe;
 }
 // a canonical decimal (canon_number's output, float form) against the closed interval [0, 1]: -1 below, +1 above, 0 inside

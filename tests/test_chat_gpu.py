@@ -270,6 +270,27 @@ def test_anthropic_sampling_parameters(ctx, schema):
         assert accepted > len(sub) // 2 and d.get("status%d" % A.AIGW_INVALID_422, 0) > len(sub) // 12
 
 
+def test_sixteen_and_seventeen_digit_floats(ctx):
+    """a 16- / 17-digit decimal is copied only when it is already the float64's shortest form (what Go prints); else the body is declined"""
+    import aigw_b200 as A
+    base = '{"model":"m","messages":[{"role":"user","content":"hi"}],"temperature":%s,"top_p":%s}'
+    cands = ["0.30000000000000004", "0.7000000000000001", "1.0000000000000002", "12345.678901234567", "0.15000000000000002", "2.675000000000001",
+             "0.10000000000000001", "0.30000000000000005", "0.70000000000000007", "0.299999999999999989", "0.07000000000000001"]
+    same = [v for v in cands if repr(float(v)) == v]; respelled = [v for v in cands if repr(float(v)) != v]
+    assert len(same) >= 5 and len(respelled) >= 4
+    bodies = [(base % (v, "0.5")).encode() for v in same + respelled] + [(base % ("0.5", v)).encode() for v in same]
+    got = ctx.chat_translate(ctx.cfg("aws-bedrock"), bodies)
+    for b, g in zip(bodies, got):
+        o = O.chat_translate("aws-bedrock", b)
+        assert o.status == O.OK
+        if g["status"] == A.AIGW_OK:
+            assert g["body"] == o.body, (b, g["body"], o.body)
+    for v, g in zip(same, got):
+        assert g["status"] == A.AIGW_OK and ('"temperature":%s' % v).encode() in g["body"], (v, g["status"], g["reason"])
+    for v, g in zip(respelled, got[len(same):]):
+        assert g["status"] == A.AIGW_DECLINED and g["reason"] == 12, (v, g["status"], g["reason"])   # AIGW_R_NUMBER
+
+
 def test_model_override_path(ctx):
     bodies = [b'{"model":"gpt-4o","messages":[{"role":"user","content":"hi"}],"stream":true}',
               b'{"messages":[{"role":"user","content":"no model"}]}']
