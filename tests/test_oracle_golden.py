@@ -758,3 +758,34 @@ def test_messages_bedrock_error_reference_cases():
                         ("500", "internal_server_error"), ("503", "service_unavailable_error"), ("502", "internal_server_error")):
         assert json.loads(O.response_error("messages-aws-bedrock", b"error", status, "", False)[1])["error"]["type"] == typ
     assert O.response_error("messages-aws-bedrock", b'{"message":5}', "400", "", True)[0] == O.INTERNAL
+
+
+def test_messages_openai_response_reference_unit_cases():
+    """the reference's own unit tests of the /v1/messages response direction for an OpenAI backend (anthropic_openai_test.go:150-416), transcribed:
+    the struct-level expectations of the four buffered cases and the event list / JSONEq payloads of the two streamed ones"""
+    # buffered: text content, usage, model; model fallback; tool call
+    ok, out, u, model = O.messages_openai_response(b'{"id":"chatcmpl-123","choices":[{"finish_reason":"stop","index":0,"message":{"content":"Hello from OpenAI!","role":"assistant"}}],"model":"gpt-4o","usage":{"prompt_tokens":10,"completion_tokens":20}}', b"claude-3-haiku")
+    j = json.loads(out)
+    assert ok and model == b"gpt-4o" and (u.input, u.output) == (10, 20) and u.mask & 3 == 3
+    assert j["id"] == "chatcmpl-123" and j["model"] == "gpt-4o" and j["content"] == [{"type": "text", "text": "Hello from OpenAI!"}] and j["stop_reason"] == "end_turn"
+    ok, out, u, model = O.messages_openai_response(b'{"choices":[{"finish_reason":"stop","index":0,"message":{"content":"Hi!"}}],"usage":{}}', b"claude-3-haiku")
+    assert ok and model == b"claude-3-haiku" and json.loads(out)["model"] == "claude-3-haiku"
+    ok, out, u, model = O.messages_openai_response(b'{"id":"chatcmpl-456","choices":[{"finish_reason":"tool_calls","index":0,"message":{"tool_calls":[{"id":"call-abc","function":{"arguments":"{\\"location\\":\\"NYC\\"}","name":"get_weather"},"type":"function"}]}}],"model":"gpt-4o","usage":{"prompt_tokens":15,"completion_tokens":8}}', b"claude-3")
+    j = json.loads(out)
+    assert ok and j["content"] == [{"type": "tool_use", "id": "call-abc", "name": "get_weather", "input": {"location": "NYC"}}] and j["stop_reason"] == "tool_use"
+    # streamed: six events, the JSONEq payloads, usage and model
+    st = O.MessagesOpenAIStream(b"claude-3-haiku")
+    data = (b'data: {"id":"chatcmpl-xyz","choices":[{"index":0,"delta":{"role":"assistant","content":"Hello!"}}],"model":"gpt-4o"}\n\n'
+            b'data: {"id":"chatcmpl-xyz","choices":[{"index":0,"delta":{},"finish_reason":"stop"}]}\n\n'
+            b'data: {"id":"chatcmpl-xyz","choices":[],"usage":{"prompt_tokens":10,"completion_tokens":5}}\n\n'
+            b'data: [DONE]\n\n')
+    s, out, u = st.feed(data, True)
+    blocks = [b for b in out.decode().split("\n\n") if b]
+    assert s == O.OK and [b.split("\n")[0] for b in blocks] == ["event: " + e for e in ("message_start", "content_block_start", "content_block_delta", "content_block_stop", "message_delta", "message_stop")]
+    payload = [json.loads(b.split("\n")[1][6:]) for b in blocks]
+    assert payload[2] == {"type": "content_block_delta", "index": 0, "delta": {"type": "text_delta", "text": "Hello!"}}
+    assert payload[4] == {"type": "message_delta", "delta": {"stop_reason": "end_turn", "stop_sequence": None}, "usage": {"output_tokens": 5}} and payload[5] == {"type": "message_stop"}
+    assert (u.input, u.output) == (10, 5) and st.model() == b"gpt-4o"
+    st = O.MessagesOpenAIStream(b"my-override")   # the translator's request model is the override when one is configured
+    s, out, u = st.feed(b'data: {"id":"chatcmpl-noop","choices":[],"usage":{"prompt_tokens":5,"completion_tokens":2}}\n\n', True)
+    assert s == O.OK and st.model() == b"my-override"
