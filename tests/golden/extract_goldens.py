@@ -181,7 +181,20 @@ def completions_cases():
         json.dump({"source": "internal/translator/openai_completions_test.go:107-337", "buffered": buffered, "streams": streams}, f, indent=1)
 
 
+def aws_anthropic_messages_real():
+    """internal/translator/anthropic_awsanthropic_test.go:237-330: eventstream chunks "extracted from a real streaming response" of Anthropic on
+    AWS Bedrock (base64) and the exact Anthropic SSE text the /v1/messages translator must produce for them, fed ONE BYTE PER CALL in the reference test."""
+    src = open(os.path.join(REF, "internal/translator/anthropic_awsanthropic_test.go"), encoding="utf-8").read()
+    a = src.index("awsBase64Chunks := []string{"); b = src.index("\n\t}\n", a)
+    chunks = re.findall(r'"([A-Za-z0-9+/=]+)"', src[a:b])
+    i = src.index("require.Equal(t, `event: message_start", b); j = src.index("`", i); k = src.index("`", j + 1)
+    assert len(chunks) >= 5
+    with open(os.path.join(OUT, "aws_anthropic_messages_real.json"), "w", encoding="utf-8") as f:
+        json.dump({"source": "internal/translator/anthropic_awsanthropic_test.go:237-330", "chunks_base64": chunks, "expected_sse": src[j + 1:k], "expect_input_tokens": 10, "expect_output_tokens": 15}, f, indent=1)
+
+
 if __name__ == "__main__":
     main()
     bedrock_stream()
     completions_cases()
+    aws_anthropic_messages_real()

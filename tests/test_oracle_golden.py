@@ -789,3 +789,18 @@ def test_messages_openai_response_reference_unit_cases():
     st = O.MessagesOpenAIStream(b"my-override")   # the translator's request model is the override when one is configured
     s, out, u = st.feed(b'data: {"id":"chatcmpl-noop","choices":[],"usage":{"prompt_tokens":5,"completion_tokens":2}}\n\n', True)
     assert s == O.OK and st.model() == b"my-override"
+
+
+def test_messages_aws_anthropic_real_capture_one_byte_per_call():
+    """anthropic_awsanthropic_test.go:237-330: a real AWS Bedrock capture of a /v1/messages stream (eventstream frames with the service's own
+    headers), fed one byte per ResponseBody call as the reference test does: the exact Anthropic SSE text, input 10 / output 15 tokens"""
+    import base64
+    g = json.load(open(os.path.join(G, "aws_anthropic_messages_real.json"), encoding="utf-8"))
+    data = b"".join(base64.b64decode(c) for c in g["chunks_base64"])
+    st = O.MessagesAwsAnthropicStream(b"req-model"); out = b""
+    for i in range(len(data)):
+        s, o, u = st.feed(data[i:i + 1], i == len(data) - 1)
+        assert s == O.OK
+        out += o
+    assert out.decode() == g["expected_sse"]
+    assert (u.input, u.output) == (g["expect_input_tokens"], g["expect_output_tokens"]) and u.mask & 3 == 3
