@@ -288,10 +288,12 @@ def run_config2(a, rank, world, local, ncpu):
             r2, o2, st = c.chat_translate_host(cfg, arena, offs[b:e], lens[b:e])
             nout = min(int(st["d2h_bytes"]), len(o2), (sink_off[k + 1] if k + 1 < parts else len(sink)) - sink_off[k])     # the bytes the call produced, copied to caller memory
             WL.wl_memcpy_mt(C.c_void_p(sink.ctypes.data + sink_off[k]), C.c_void_p(o2.ctypes.data), C.c_uint64(nout), C.c_int(threads))
-            part_res[k] = np.array(r2); part_st[k] = st
-            if sample:   # 1 % of the records of this (timed) call, taken from the library's arena before the next call reuses it
-                fo = r2["out_off"].astype(np.int64); fl = r2["path_len"].astype(np.int64) + r2["body_len"].astype(np.int64)
-                part_samples[k] = [(i, bytes(o2[int(fo[i - b]):int(fo[i - b] + fl[i - b])])) for i in range(-(-b // 100) * 100, e, 100)]
+            part_st[k] = st
+            if sample:   # last timed step only: the result table and 1 % of the records of this call, taken before the next call on the context reuses them
+                part_res[k] = np.array(r2)
+                idx = np.arange(-(-b // 100) * 100, e, 100) - b
+                fo = r2["out_off"][idx].astype(np.int64); fl = r2["path_len"][idx].astype(np.int64) + r2["body_len"][idx].astype(np.int64)
+                part_samples[k] = [(int(b + j), bytes(o2[int(a0):int(a0 + l0)])) for j, a0, l0 in zip(idx, fo, fl)]
         def e2e_step(nl, sample=False):
             if nl == 1:
                 for k in range(parts):
