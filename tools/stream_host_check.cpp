@@ -18,14 +18,20 @@ static void hex(const uint8_t* p, size_t n) { if (!n) { printf("-"); return; } f
 
 int main() {
   g_chunk_schema = build_schema(); g_cmpl_schema = build_completion_schema(); g_o2a_resp_schema = build_resp_schema();
+  g_conv_schema = build_schema_bedrock(); g_an_schema = build_an_schema();
   for (uint32_t i = 0; i < 256; i++) { uint32_t v = i; for (int k = 0; k < 8; k++) v = (v & 1u) ? 0xEDB88320u ^ (v >> 1) : v >> 1; g_crc_tab[i] = v; }
   StreamSlot* S = new StreamSlot();
   std::vector<uint8_t> out(1 << 22);
   std::string cmd;
   while (std::cin >> cmd) {
     if (cmd == "open") {
-      int kind; std::string model; std::cin >> kind >> model; if (model == "-") model.clear();
+      // open <kind> <request_model> [<response_id> <created>]: the slot template aigw_stream_open_batch builds (lib.cu)
+      int kind; std::string model, rest; std::cin >> kind >> model; if (model == "-") model.clear();
+      std::getline(std::cin, rest);
+      std::string rid; long long created = 0; { char buf[200] = {0}; if (sscanf(rest.c_str(), " %199s %lld", buf, &created) >= 1) rid = buf; if (rid == "-") rid.clear(); }
       memset(S, 0, sizeof *S); S->kind = (uint32_t)kind; S->active_index = -1; S->model_len = (uint32_t)model.size(); memcpy(S->model, model.data(), model.size());
+      S->tool_index = kind == AIGW_STREAM_GCP_ANTHROPIC ? -1 : 0; S->created = created;
+      if (kind == AIGW_STREAM_AWS_BEDROCK) { S->id_len = (uint32_t)rid.size(); memcpy(S->id, rid.data(), rid.size()); S->flags |= SF_HAVE_CREATED; }
     } else if (cmd == "feed") {
       std::string h; int eos; std::cin >> h >> eos; if (h == "-") h.clear();
       std::vector<uint8_t> in = unhex(h);
@@ -40,6 +46,11 @@ int main() {
       if (S->flags & SF_DEAD) { R.status = (uint8_t)S->dead_status; }
       else switch (S->kind) {
         case AIGW_STREAM_OPENAI: step_openai(*S, st, out.data(), R); break;
+        case AIGW_STREAM_AWS_BEDROCK: step_bedrock(*S, st, out.data(), R); break;
+        case AIGW_STREAM_GCP_ANTHROPIC: step_anthropic(*S, st, out.data(), R); break;
+        case AIGW_STREAM_GCP_GEMINI: step_gemini(*S, st, out.data(), R); break;
+        case AIGW_STREAM_GCP_GEMINI_BUFFERED: step_gemini_buffered(*S, st, out.data(), R); break;
+        case AIGW_STREAM_AWS_ANTHROPIC: step_aws_anthropic(*S, st, out.data(), R); break;
         case AIGW_STREAM_OPENAI_COMPLETIONS: step_openai(*S, st, out.data(), R, true); break;
         case AIGW_STREAM_MESSAGES_OPENAI: step_messages_openai(*S, st, out.data(), R); break;
         case AIGW_STREAM_MESSAGES_OPENAI_BUFFERED: step_messages_openai_buffered(*S, st, out.data(), R); break;
